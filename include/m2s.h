@@ -1,0 +1,199 @@
+/* m2s.h — C ABI of the B200-native mesh -> 3D-gaussian-splat conversion path.
+ *
+ * This is the drop-in boundary for ONE path of electronicarts/mesh2splat: the
+ * conversion pass.  Every entry point names the reference interface it stands
+ * in for (paths relative to the reference tree):
+ *
+ *   reference                                                  here
+ *   ---------------------------------------------------------  ----------------------------
+ *   SceneManager::setupMeshBuffers + glUtils::generateTextures  m2s_scene_upload
+ *     (src/utils/SceneManager.cpp:468-576,
+ *      src/utils/glUtils.cpp:252-317)
+ *   ConversionPass::execute / ::conversion                      m2s_convert, m2s_convert_enqueue,
+ *     (src/renderer/renderPasses/ConversionPass.cpp:9-117)      m2s_convert_host
+ *     + converter{VS,GS,FS}.glsl + SSBO atomic append
+ *   SceneManager::exportPly + parsers::savePlyVector            m2s_ply_encode, m2s_ply_write
+ *     (src/utils/SceneManager.cpp:651-678,
+ *      src/parsers/parsers.cpp:232-316,339-428,431-514,631-651)
+ *   SceneManager::loadModel -> execute -> exportPly             m2s_convert_file
+ *     (src/utils/SceneManager.hpp:18-20)
+ *
+ * Plain pointers and sizes only; no C++/torch types.  All functions return an
+ * m2s_status; m2s_last_error() gives the thread-local message of the last
+ * failure.  The library has NO CPU fallback: without a usable CUDA device every
+ * compute entry point fails with M2S_E_NOGPU.
+ */
+#ifndef M2S_H
+#define M2S_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define M2S_VERSION 100 /* 0.1.0 */
+
+typedef enum m2s_status {
+    M2S_OK = 0,
+    M2S_E_INVALID = 1,  /* bad argument */
+    M2S_E_NOGPU = 2,    /* no CUDA device / driver */
+    M2S_E_CUDA = 3,     /* CUDA runtime error (message in m2s_last_error) */
+    M2S_E_CAPACITY = 4, /* more gaussians generated than the output holds; result.total has the
+                           true count (the reference silently discards: converterFS.glsl:48-51) */
+    M2S_E_IO = 5,
+    M2S_E_FORMAT = 6    /* malformed .glb / unsupported feature */
+} m2s_status;
+
+/* Output record layouts (stride in bytes = m2s_record_stride(layout)). */
+typedef enum m2s_layout {
+    /* 6 x float4, bit-compatible with GaussianDataSSBO (src/utils/utils.hpp:145-152) /
+     * GaussianVertex (converterFS.glsl:21-28): position.xyz1 | color.rgba | scale.xyz0 (raw) |
+     * normal.xyz0 | rotation (w,x,y,z) | pbr (metallic, roughness, 0, 1). */
+    M2S_LAYOUT_REF96 = 0,
+    /* 14 floats: xyz | rot (w,x,y,z) | log(scale*sigma/R) xyz | SH0 rgb | opacity logit — the values
+     * parsers.cpp:469-511 derives from the SSBO record, minus normal and f_rest. */
+    M2S_LAYOUT_PACKED56 = 1,
+    /* one row of the three .ply bodies the reference writes (format 0/1/2 of savePlyVector) */
+    M2S_LAYOUT_PLY_STANDARD = 2,   /* 62 floats = 248 B, parsers.cpp:431-514 */
+    M2S_LAYOUT_PLY_PBR = 3,        /* 19 floats =  76 B, parsers.cpp:232-316 */
+    M2S_LAYOUT_PLY_COMPRESSED = 4  /* 48 B,               parsers.cpp:339-428 */
+} m2s_layout;
+
+enum {
+    M2S_FLAG_NONE = 0,
+    /* cap = min(6*R*R*primitive_count, 7 000 000) exactly as ConversionPass.cpp:21-24 when
+     * max_gaussians == 0 (default).  With this flag and max_gaussians == 0 the cap is only the
+     * capacity of the output buffer handed in. */
+    M2S_FLAG_UNCAPPED = 1u << 0
+};
+
+#define M2S_FLOATS_PER_VERTEX 12u   /* pos3 normal3 tangent4 uv2: the live part of the reference's
+                                       17-float vertex (SceneManager.cpp:484-512) */
+#define M2S_FLOATS_PER_TRIANGLE 36u /* 144 B */
+#define M2S_MAX_MIP_LEVEL 4u        /* GL_TEXTURE_MAX_LEVEL 4, glUtils.cpp:313 */
+#define M2S_REFERENCE_MAX_GAUSSIANS 7000000u /* MAX_GAUSSIANS_TO_SORT, RenderPass.hpp:8 */
+
+/* RGBA8 image, row 0 first, exactly the bytes tinygltf hands to glTexImage2D
+ * (glUtils.cpp:292-303); wrap REPEAT, trilinear, levels 0..4 generated on upload. */
+typedef struct m2s_texture {
+    const uint8_t* rgba;
+    uint32_t width, height;
+} m2s_texture;
+
+/* One glTF primitive = one utils::Mesh = one glDrawArrays of the reference
+ * (ConversionPass.cpp:70-117). */
+typedef struct m2s_primitive {
+    uint64_t first_triangle;
+    uint64_t triangle_count;
+    float bbox_min[3];           /* u_bboxMin (ConversionPass.cpp:111) */
+    float bbox_max[3];           /* u_bboxMax */
+    float base_color_factor[4];  /* u_materialFactor (ConversionPass.cpp:110) */
+    int32_t albedo_texture;      /* index into m2s_scene.textures, -1 = hasAlbedoMap 0 */
+    int32_t normal_texture;
+    int32_t metallic_roughness_texture;
+    int32_t reserved;
+} m2s_primitive;
+
+typedef struct m2s_scene {
+    /* triangle soup, world space, M2S_FLOATS_PER_TRIANGLE floats per triangle:
+     * 3 x { position xyz, normal xyz, tangent xyzw, uv } */
+    const float* triangles;
+    uint64_t triangle_count;
+    const m2s_primitive* primitives;
+    uint32_t primitive_count;
+    const m2s_texture* textures;
+    uint32_t texture_count;
+} m2s_scene;
+
+typedef struct m2s_params {
+    uint32_t resolution;    /* R = resolutionTarget (ConversionPass.cpp:45): 1..4096 */
+    float gaussian_std;     /* sigma (main.cpp:26 default 0.65); used by every layout but REF96 */
+    uint64_t max_gaussians; /* 0 = reference rule (see M2S_FLAG_UNCAPPED) */
+    uint32_t layout;        /* m2s_layout */
+    uint32_t flags;
+    /* shard of the flattened triangle list this call converts (multi-GPU: one contiguous range
+     * per rank); triangle_count == 0 means "to the end" */
+    uint64_t first_triangle;
+    uint64_t triangle_count;
+} m2s_params;
+
+typedef struct m2s_result {
+    uint64_t total;    /* fragments generated = the reference's numberOfGaussians
+                          (may exceed capacity, ConversionPass.cpp:56-59) */
+    uint64_t written;  /* records actually stored = min(total, cap) */
+    uint64_t cap;      /* effective cap applied */
+    float device_ms;   /* device time of the conversion kernel(s), CUDA events */
+} m2s_result;
+
+typedef struct m2s_ctx m2s_ctx;       /* one per GPU; externally synchronised */
+typedef struct m2s_dscene m2s_dscene; /* device-resident scene (triangles, primitive table, mip chains) */
+
+/* ---- housekeeping ------------------------------------------------------------------------- */
+int m2s_version(void);
+const char* m2s_last_error(void);
+const char* m2s_status_string(m2s_status s);
+uint32_t m2s_record_stride(uint32_t layout);
+/* min(6*R*R*max(1,primitive_count), 7 000 000): ConversionPass.cpp:21-24 */
+uint64_t m2s_reference_capacity(uint32_t resolution, uint32_t primitive_count);
+void m2s_params_default(m2s_params* p);
+
+m2s_status m2s_ctx_create(int device, m2s_ctx** out);
+void m2s_ctx_destroy(m2s_ctx* ctx);
+int m2s_ctx_device(const m2s_ctx* ctx);
+int m2s_ctx_sm_count(const m2s_ctx* ctx);
+
+/* ---- inputs: replaces setupMeshBuffers + generateTextures ---------------------------------- */
+/* Fills primitives[i].bbox_{min,max} from the triangle positions.  cumulative != 0 reproduces
+ * the reference, where primitive k gets the union bbox of primitives 0..k
+ * (SceneManager.cpp:476-477,514-520,527); 0 gives each primitive its own box. Host-only. */
+m2s_status m2s_compute_bboxes(const float* triangles, m2s_primitive* primitives,
+                              uint32_t primitive_count, int cumulative);
+
+/* Copies triangles + primitive table + textures to the device and builds mip levels 1..4
+ * (2x2 box, round-to-nearest) on the GPU.  Host pointers may be pageable. */
+m2s_status m2s_scene_upload(m2s_ctx* ctx, const m2s_scene* scene, m2s_dscene** out);
+void m2s_scene_free(m2s_ctx* ctx, m2s_dscene* scene);
+/* Copies one generated mip level (RGBA8, tightly packed) back to the host; for parity tests. */
+m2s_status m2s_scene_read_mip(m2s_ctx* ctx, const m2s_dscene* scene, uint32_t texture,
+                              uint32_t level, uint8_t* dst, uint32_t* width, uint32_t* height);
+
+/* ---- the hot path: replaces ConversionPass::execute ---------------------------------------- */
+/* Enqueue-only form.  d_out: device buffer of out_capacity records; d_keys: optional device
+ * array of out_capacity uint64 (fragment identity: triangle << 24 | y << 12 | x), may be NULL;
+ * d_total: device uint64 receiving the fragment count; stream: cudaStream_t (NULL = context
+ * stream).  Nothing is synchronised. */
+m2s_status m2s_convert_enqueue(m2s_ctx* ctx, const m2s_dscene* scene, const m2s_params* params,
+                               void* d_out, uint64_t out_capacity, uint64_t* d_keys,
+                               uint64_t* d_total, void* stream);
+/* enqueue + wait + read the counter back (the glFinish + counter readback of
+ * ConversionPass.cpp:54-59).  Returns M2S_E_CAPACITY if total > cap (records up to cap are valid). */
+m2s_status m2s_convert(m2s_ctx* ctx, const m2s_dscene* scene, const m2s_params* params,
+                       void* d_out, uint64_t out_capacity, uint64_t* d_keys, m2s_result* result);
+/* Host-buffer form: upload scene, convert, download records (and keys if h_keys != NULL).
+ * Everything a caller holding CPU data pays for. */
+m2s_status m2s_convert_host(m2s_ctx* ctx, const m2s_scene* scene, const m2s_params* params,
+                            void* h_out, uint64_t out_capacity, uint64_t* h_keys,
+                            m2s_result* result);
+
+/* ---- outputs: replaces exportPly / savePlyVector -------------------------------------------- */
+/* ASCII header of format 0/1/2 for `count` vertices; returns bytes written (excl. NUL) or the
+ * needed size if dst is too small. */
+size_t m2s_ply_header(uint32_t format, uint64_t count, char* dst, size_t dst_size);
+/* GPU encoder: REF96 device records -> .ply body rows on the device (format 0/1/2). */
+m2s_status m2s_ply_encode(m2s_ctx* ctx, const void* d_ref96, uint64_t count, uint32_t format,
+                          float scale_multiplier, void* d_rows, void* stream);
+/* Host writer: REF96 host records -> file, byte-identical to parsers::savePlyVector. */
+m2s_status m2s_ply_write(const char* path, const void* h_ref96, uint64_t count, uint32_t format,
+                         float scale_multiplier);
+
+/* ---- file-level surface: loadModel -> execute -> exportPly --------------------------------- */
+m2s_status m2s_convert_file(m2s_ctx* ctx, const char* glb_path, uint32_t resolution,
+                            float gaussian_std, uint32_t ply_format, const char* ply_path,
+                            m2s_result* result);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* M2S_H */

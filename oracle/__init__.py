@@ -1,0 +1,195 @@
+"""Python bindings of the CPU checkers (TEST INFRASTRUCTURE).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this package.  mesh2splat_b200 never does.
+
+  convert(...)            the plain-C restatement (oracle/m2s_oracle.c) of the whole pass
+  triangle_setup(...)     its per-triangle stage, field by field
+  ref_gs / ref_fs         the reference's own GLSL compiled as C++ (oracle/_ref), if built
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from mesh2splat_b200 import _abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+_ref = None
+
+
+class orc_setup(C.Structure):
+    _fields_ = [("ouv", (C.c_float * 2) * 3), ("quat", C.c_float * 4), ("scale", C.c_float * 3),
+                ("X", C.c_int32 * 3), ("Y", C.c_int32 * 3), ("area2", C.c_int64),
+                ("axis", C.c_int32), ("valid", C.c_int32),
+                ("A", C.c_int64 * 3), ("B", C.c_int64 * 3), ("Cc", C.c_int64 * 3),
+                ("incl", C.c_int32 * 3), ("x0", C.c_int32), ("y0", C.c_int32),
+                ("x1", C.c_int32), ("y1", C.c_int32)]
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        path = os.path.join(_HERE, "libm2s_oracle.so")
+        if not os.path.exists(path):
+            from . import build as _b  # noqa: WPS433
+            _b.build_oracle()
+        _lib = C.CDLL(path)
+        _lib.orc_convert.restype = C.c_uint64
+        _lib.orc_convert.argtypes = [C.POINTER(_abi.m2s_scene), C.POINTER(_abi.m2s_params), C.c_void_p,
+                                     C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64), C.c_int]
+        _lib.orc_triangle_setup.restype = C.c_int
+        _lib.orc_triangle_setup.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(orc_setup)]
+        _lib.orc_mip_level.restype = C.c_int
+        _lib.orc_mip_level.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
+                                       C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        _lib.orc_mip_count.restype = C.c_uint32
+        _lib.orc_mip_count.argtypes = [C.c_uint32, C.c_uint32]
+        _lib.orc_sample.restype = None
+        _lib.orc_sample.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_void_p]
+        _lib.orc_fragment.restype = None
+        _lib.orc_fragment.argtypes = [C.c_void_p] * 8 + [C.c_uint32, C.c_void_p, C.c_void_p]
+        _lib.orc_encode.restype = None
+        _lib.orc_encode.argtypes = [C.c_uint32, C.c_void_p, C.c_float, C.c_void_p]
+        _lib.orc_ply_header.restype = C.c_size_t
+        _lib.orc_ply_header.argtypes = [C.c_uint32, C.c_uint64, C.c_char_p, C.c_size_t]
+        _lib.orc_record_stride.restype = C.c_uint32
+        _lib.orc_record_stride.argtypes = [C.c_uint32]
+        _lib.orc_compute_bboxes.restype = None
+        _lib.orc_compute_bboxes.argtypes = [C.c_void_p, C.POINTER(_abi.m2s_primitive), C.c_uint32, C.c_int]
+        _lib.orc_max_threads.restype = C.c_int
+    return _lib
+
+
+def ref_lib():
+    """The reference-shader library, or None if it was never built (no /root/reference)."""
+    global _ref
+    if _ref is None:
+        path = os.path.join(_HERE, "_ref", "libm2s_refshader.so")
+        if not os.path.exists(path):
+            return None
+        _ref = C.CDLL(path)
+        _ref.ref_gs.restype = C.c_int
+        _ref.ref_gs.argtypes = [C.c_void_p] * 6
+        _ref.ref_fs.restype = C.c_int
+        _ref.ref_fs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
+                                C.c_uint32, C.c_int, C.c_void_p, C.POINTER(C.c_uint32)]
+    return _ref
+
+
+def max_threads() -> int:
+    return int(lib().orc_max_threads())
+
+
+def convert(scene: _abi.Scene, resolution: int, layout: int = _abi.LAYOUT_REF96, gaussian_std: float = 0.65,
+            max_gaussians: int = 0, flags: int = 0, first_triangle: int = 0, triangle_count: int = 0,
+            capacity: int | None = None, want_keys: bool = True, threads: int = 0):
+    """Whole pass on the CPU. Returns (records[structured], keys|None, total)."""
+    cs, keep = scene.c_struct()
+    p = _abi.make_params(resolution, layout, gaussian_std, max_gaussians, flags, first_triangle, triangle_count)
+    if capacity is None:
+        capacity = max_gaussians if max_gaussians else (
+            _abi.reference_capacity(resolution, len(scene.primitives)) if not (flags & _abi.FLAG_UNCAPPED)
+            else 6 * resolution * resolution * max(1, len(scene.primitives)))
+    stride = _abi.STRIDES[layout]
+    out = np.zeros(capacity * stride, np.uint8)
+    keys = np.zeros(capacity, np.uint64) if want_keys else None
+    total = C.c_uint64(0)
+    n = lib().orc_convert(C.byref(cs), C.byref(p), out.ctypes.data, capacity,
+                          keys.ctypes.data if want_keys else None, C.byref(total), threads)
+    del keep
+    rec = out[: n * stride].view(_abi.record_dtype(layout))
+    return rec, (keys[:n] if want_keys else None), int(total.value)
+
+
+def triangle_setup(tri36: np.ndarray, bmin, bmax, resolution: int) -> orc_setup:
+    t = np.ascontiguousarray(tri36, np.float32)
+    a = np.asarray(bmin, np.float32); b = np.asarray(bmax, np.float32)
+    s = orc_setup()
+    lib().orc_triangle_setup(t.ctypes.data, a.ctypes.data, b.ctypes.data, resolution, C.byref(s))
+    return s
+
+
+def mip_level(img: np.ndarray, level: int) -> np.ndarray:
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape[:2]
+    dst = np.zeros((h, w, 4), np.uint8)
+    ow, oh = C.c_uint32(0), C.c_uint32(0)
+    r = lib().orc_mip_level(img.ctypes.data, w, h, level, dst.ctypes.data, C.byref(ow), C.byref(oh))
+    if r != 0:
+        raise ValueError("level out of range")
+    return dst.reshape(-1)[: ow.value * oh.value * 4].reshape(oh.value, ow.value, 4).copy()
+
+
+def mip_count(w: int, h: int) -> int:
+    return int(lib().orc_mip_count(w, h))
+
+
+def sample(img: np.ndarray, u: float, v: float, lam: float) -> np.ndarray:
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.zeros(4, np.float32)
+    lib().orc_sample(img.ctypes.data, img.shape[1], img.shape[0], u, v, lam, out.ctypes.data)
+    return out
+
+
+def fragment(P, N, T, scale, quat, albedo, nrm, mr, flags: int, factor) -> np.ndarray:
+    arrs = [np.ascontiguousarray(x, np.float32) for x in (P, N, T, scale, quat, albedo, nrm, mr)]
+    f = np.ascontiguousarray(factor, np.float32)
+    rec = np.zeros(24, np.float32)
+    lib().orc_fragment(*[a.ctypes.data for a in arrs], flags, f.ctypes.data, rec.ctypes.data)
+    return rec
+
+
+def encode(layout: int, rec24: np.ndarray, mult: float) -> np.ndarray:
+    r = np.ascontiguousarray(rec24, np.float32)
+    dst = np.zeros(_abi.STRIDES[layout], np.uint8)
+    lib().orc_encode(layout, r.ctypes.data, mult, dst.ctypes.data)
+    return dst
+
+
+def ply_header(fmt: int, count: int) -> bytes:
+    buf = C.create_string_buffer(8192)
+    n = lib().orc_ply_header(fmt, count, buf, 8192)
+    return buf.raw[:n]
+
+
+def ply_bytes(ref96: np.ndarray, fmt: int, mult: float) -> bytes:
+    """Whole .ply file (header + body) from REF96 records, as parsers::savePlyVector writes it."""
+    layout = _abi.PLY_FORMAT_LAYOUT.get(fmt, _abi.LAYOUT_PLY_STANDARD)
+    flat = np.ascontiguousarray(ref96).view(np.float32).reshape(-1, 24)
+    stride = _abi.STRIDES[layout]
+    body = np.zeros(len(flat) * stride, np.uint8)
+    L = lib()
+    for i in range(len(flat)):
+        L.orc_encode(layout, flat[i].ctypes.data, mult, body.ctypes.data + i * stride)
+    return ply_header(fmt, len(flat)) + body.tobytes()
+
+
+def ref_gs(tri36, bmin, bmax):
+    """Reference geometry shader. Returns (glpos[3,4], scale[3], quat_wxyz[4]) or None if unavailable."""
+    r = ref_lib()
+    if r is None:
+        return None
+    t = np.ascontiguousarray(tri36, np.float32)
+    a = np.asarray(bmin, np.float32); b = np.asarray(bmax, np.float32)
+    glpos = np.zeros((3, 4), np.float32); sc = np.zeros(3, np.float32); q = np.zeros(4, np.float32)
+    n = r.ref_gs(t.ctypes.data, a.ctypes.data, b.ctypes.data, glpos.ctypes.data, sc.ctypes.data, q.ctypes.data)
+    assert n == 3
+    return glpos, sc, q
+
+
+def ref_fs(varyings19, albedo, nrm, mr, flags: int, factor, counter_start: int = 0, max_gaussians: int = 1 << 30):
+    """Reference fragment shader. Returns (written, rec24, counter_after) or None if unavailable."""
+    r = ref_lib()
+    if r is None:
+        return None
+    arrs = [np.ascontiguousarray(x, np.float32) for x in (varyings19, albedo, nrm, mr)]
+    f = np.ascontiguousarray(factor, np.float32)
+    rec = np.zeros(24, np.float32)
+    cnt = C.c_uint32(0)
+    w = r.ref_fs(arrs[0].ctypes.data, arrs[1].ctypes.data, arrs[2].ctypes.data, arrs[3].ctypes.data, flags,
+                 f.ctypes.data, counter_start, max_gaussians, rec.ctypes.data, C.byref(cnt))
+    return bool(w), rec, int(cnt.value)

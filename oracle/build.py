@@ -1,0 +1,122 @@
+#!/usr/bin/env python3
+"""Build the checkers under oracle/ (TEST INFRASTRUCTURE — never linked into the product).
+
+  libm2s_oracle.so            the plain-C restatement (m2s_oracle.c), always built (gcc, OpenMP)
+  _ref/libm2s_refshader.so    the REFERENCE's own conversion shaders — converterGS.glsl and
+                              converterFS.glsl, read where they lie under /root/reference and
+                              turned into a C++ translation unit by the mechanical token rewrites
+                              below — compiled against the reference's vendored GLM.  Only built
+                              when /root/reference exists (this container); the GPU box uses the
+                              prebuilt .so that travels with the snapshot.  Nothing from the
+                              reference is written into the repository: generated files and the
+                              .so live in oracle/_ref/ (git-ignored).
+
+The reference application itself (Win32 + OpenGL 4.6 + GLFW/GLEW .lib files, CMake non-Windows
+branch is a todo) cannot be built here; see DESIGN.md.  What _ref pins is the shader ARITHMETIC
+(per-triangle stage and per-fragment stage); the rasteriser and the texture unit are GL-driver
+behaviour and have no reference source to compile.
+"""
+from __future__ import annotations
+
+import os
+import re
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("M2S_REFERENCE", "/root/reference")
+REF_OUT = os.path.join(HERE, "_ref")
+CFLAGS = ["-O2", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-fvisibility=hidden"]
+
+
+def _run(cmd: list[str]) -> None:
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        raise RuntimeError("build failed: " + cmd[0])
+
+
+def _newer(target: str, *deps: str) -> bool:
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(d) <= t for d in deps if os.path.exists(d))
+
+
+def build_oracle(force: bool = False) -> str:
+    src = os.path.join(HERE, "m2s_oracle.c")
+    out = os.path.join(HERE, "libm2s_oracle.so")
+    hdr = os.path.join(HERE, "..", "include", "m2s.h")
+    if force or not _newer(out, src, hdr, __file__):
+        _run(["gcc", "-std=c11", "-fopenmp", *CFLAGS, "-o", out, src, "-lm"])
+    return out
+
+
+# ---- GLSL -> C++ token rewrites (mechanical; the arithmetic is untouched) -------------------
+_FLOAT_LIT = re.compile(r"(?<![\w.])((?:\d+\.\d*|\.\d+)(?:[eE][-+]?\d+)?|\d+[eE][-+]?\d+)(?![\w.])")
+
+
+def _common(src: str) -> str:
+    src = re.sub(r"^\s*#version.*$", "", src, flags=re.M)
+    src = _FLOAT_LIT.sub(lambda m: m.group(1) + "f", src)  # GLSL literals are float
+    return src
+
+
+def glsl_gs_to_cpp(src: str) -> str:
+    src = _common(src)
+    src = re.sub(r"^\s*layout\s*\([^)]*\)\s*(in|out)\s*;\s*$", "", src, flags=re.M)
+    src = re.sub(r"in\s+VS_OUT\s*\{(.*?)\}\s*gs_in\[\]\s*;", r"struct VS_OUT {\1}; static VS_OUT gs_in[3];", src, flags=re.S)
+    src = re.sub(r"^\s*uniform\s+", "static ", src, flags=re.M)
+    src = re.sub(r"^\s*(?:flat\s+)?out\s+(\w+\s+\w+\s*;)", r"static \1", src, flags=re.M)
+    # parameter qualifiers
+    src = re.sub(r"([(,]\s*)in\s+(\w+\s+\w+)", r"\1\2", src)
+    src = re.sub(r"([(,]\s*)out\s+(\w+)\s+(\w+)", r"\1\2& \3", src)
+    src = src.replace("void main()", "void gs_main()")
+    return src
+
+
+def glsl_fs_to_cpp(src: str) -> str:
+    src = _common(src)
+    src = re.sub(r"layout\s*\(std430[^)]*\)\s*buffer\s+GaussianBuffer\s*\{.*?\}\s*gaussianBuffer\s*;",
+                 "static struct { GaussianVertex* vertices; } gaussianBuffer;", src, flags=re.S)
+    src = re.sub(r"layout\s*\([^)]*\)\s*uniform\s+atomic_uint", "static atomic_uint", src)
+    src = re.sub(r"^\s*uniform\s+", "static ", src, flags=re.M)
+    src = re.sub(r"^\s*in\s+(\w+\s+\w+\s*;)", r"static \1", src, flags=re.M)
+    src = re.sub(r"\bdiscard\s*;", "return;", src)
+    # swizzles used by the shader: .xyz of vec3/vec4 -> vec3(...), .bg -> helper
+    src = re.sub(r"(texture\([^()]*\))\.xyz", r"vec3(\1)", src)
+    src = re.sub(r"(texture\([^()]*\))\.bg", r"swz_bg(\1)", src)
+    src = re.sub(r"\b(\w+)\.xyz\b", r"vec3(\1)", src)
+    src = src.replace("void main()", "void fs_main()")
+    return src
+
+
+def build_ref(force: bool = False) -> str | None:
+    gs = os.path.join(REF, "src", "shaders", "conversion", "converterGS.glsl")
+    fs = os.path.join(REF, "src", "shaders", "conversion", "converterFS.glsl")
+    glm = os.path.join(REF, "thirdParty", "glm")
+    out = os.path.join(REF_OUT, "libm2s_refshader.so")
+    if not (os.path.exists(gs) and os.path.exists(fs) and os.path.isdir(glm)):
+        return out if os.path.exists(out) else None
+    harness = os.path.join(HERE, "ref_harness.cpp")
+    if not force and _newer(out, gs, fs, harness, __file__):
+        return out
+    os.makedirs(REF_OUT, exist_ok=True)
+    with open(gs) as f:
+        gs_cpp = glsl_gs_to_cpp(f.read())
+    with open(fs) as f:
+        fs_cpp = glsl_fs_to_cpp(f.read())
+    with open(os.path.join(REF_OUT, "converterGS.inc"), "w") as f:
+        f.write(gs_cpp)
+    with open(os.path.join(REF_OUT, "converterFS.inc"), "w") as f:
+        f.write(fs_cpp)
+    _run(["g++", "-std=gnu++17", *CFLAGS, "-w", "-I", glm, "-I", REF_OUT, "-o", out, harness])
+    return out
+
+
+def build_all(force: bool = False) -> dict:
+    return {"oracle": build_oracle(force), "ref": build_ref(force)}
+
+
+if __name__ == "__main__":
+    print(build_all(force="--force" in sys.argv))
