@@ -189,6 +189,15 @@ m2s_status m2s_ply_write(const char* path, const void* h_ref96, uint64_t count, 
                          float scale_multiplier);
 
 /* ---- file-level surface: loadModel -> execute -> exportPly --------------------------------- */
+/* .glb -> host scene: SceneManager::parseGltfFile + setupMeshBuffers (bbox rule) + loadTextures
+ * (src/utils/SceneManager.cpp:195-459,468-649): scene-graph world transforms, de-indexing, flat
+ * normal / per-face tangent fallbacks, one primitive per glTF primitive, RGBA8 images.
+ * cumulative_bbox != 0 keeps the reference's running-union bbox. */
+typedef struct m2s_hscene m2s_hscene;
+m2s_status m2s_glb_load(const char* glb_path, int cumulative_bbox, m2s_hscene** out);
+const m2s_scene* m2s_hscene_view(const m2s_hscene* scene);
+void m2s_hscene_free(m2s_hscene* scene);
+
 m2s_status m2s_convert_file(m2s_ctx* ctx, const char* glb_path, uint32_t resolution,
                             float gaussian_std, uint32_t ply_format, const char* ply_path,
                             m2s_result* result);

@@ -1,0 +1,445 @@
+// m2s_api.cu — C-ABI implementation (include/m2s.h) over the kernels in m2s_kernels.cu.
+// Host orchestration only: context, device-resident scene, launches, counter read-back.
+// There is deliberately NO CPU compute path: without a CUDA device every entry point fails.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/m2s.h"
+#include "m2s_device.cuh"
+
+namespace m2s {
+size_t convert_smem_bytes(int layout);
+cudaError_t convert_configure(int layout, int* blocks_per_sm);
+cudaError_t convert_launch(int layout, const ConvertArgs& args, int grid, cudaStream_t stream);
+cudaError_t mip_down_launch(const uint32_t* src, uint32_t sw, uint32_t sh, uint32_t* dst, uint32_t dw, uint32_t dh,
+                            cudaStream_t stream);
+cudaError_t ply_rows_launch(const void* ref96, unsigned long long count, const unsigned long long* d_count,
+                            uint32_t format, float mult, void* rows, cudaStream_t stream);
+// host-side helpers implemented in m2s_host.cpp
+void set_error(const std::string& msg);
+}  // namespace m2s
+
+using namespace m2s;
+
+#define M2S_EXPORT extern "C" __attribute__((visibility("default")))
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                          \
+            return (_e == cudaErrorNoDevice || _e == cudaErrorInsufficientDriver) ? M2S_E_NOGPU : M2S_E_CUDA; \
+        }                                                                                           \
+    } while (0)
+
+struct m2s_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    uint32_t* d_sched = nullptr;             // 8 x u32
+    unsigned long long* d_counter = nullptr; // running fragment counter
+    unsigned long long* d_total = nullptr;   // published count
+    uint2* d_queue = nullptr;
+    uint32_t queue_cap = 1u << 20;
+    unsigned long long* h_total = nullptr;   // pinned
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int blocks_per_sm[2] = {0, 0};
+    bool dirty = true;                       // scheduler state needs a memset before the next launch
+    // scratch owned by the context (grown on demand)
+    void* d_scratch = nullptr;  size_t scratch_bytes = 0;   // REF96 staging for the .ply row layouts
+    void* d_out = nullptr;      size_t out_bytes = 0;       // convert_host output
+    unsigned long long* d_keys = nullptr; size_t keys_bytes = 0;
+};
+
+struct m2s_dscene {
+    float4* d_tris = nullptr;
+    uint64_t ntri = 0;
+    DRange* d_ranges = nullptr;
+    uint32_t nranges = 0;
+    DPrim* d_prims = nullptr;
+    uint32_t nprims = 0;
+    DTexture* d_texs = nullptr;
+    uint32_t ntex = 0;
+    std::vector<DTexture> h_texs;
+    std::vector<void*> allocs;
+};
+
+static m2s_status grow(m2s_ctx* ctx, void** p, size_t* have, size_t need) {
+    if (*have >= need) return M2S_OK;
+    if (*p) CUDA_TRY(cudaFreeAsync(*p, ctx->stream));
+    *p = nullptr; *have = 0;
+    CUDA_TRY(cudaMallocAsync(p, need, ctx->stream));
+    *have = need;
+    return M2S_OK;
+}
+
+// ---- housekeeping ---------------------------------------------------------------------------
+M2S_EXPORT int m2s_version(void) { return M2S_VERSION; }
+
+M2S_EXPORT const char* m2s_status_string(m2s_status s) {
+    switch (s) {
+        case M2S_OK: return "ok";
+        case M2S_E_INVALID: return "invalid argument";
+        case M2S_E_NOGPU: return "no CUDA device";
+        case M2S_E_CUDA: return "CUDA error";
+        case M2S_E_CAPACITY: return "output capacity exceeded";
+        case M2S_E_IO: return "I/O error";
+        case M2S_E_FORMAT: return "unsupported or malformed input";
+    }
+    return "unknown";
+}
+
+M2S_EXPORT uint32_t m2s_record_stride(uint32_t layout) {
+    switch (layout) {
+        case M2S_LAYOUT_REF96: return 96;
+        case M2S_LAYOUT_PACKED56: return 56;
+        case M2S_LAYOUT_PLY_STANDARD: return 248;
+        case M2S_LAYOUT_PLY_PBR: return 76;
+        case M2S_LAYOUT_PLY_COMPRESSED: return 48;
+    }
+    return 0;
+}
+
+M2S_EXPORT uint64_t m2s_reference_capacity(uint32_t R, uint32_t primitive_count) {
+    const uint64_t mc = primitive_count ? primitive_count : 1;
+    return std::min<uint64_t>((uint64_t)R * R * 6ull * mc, M2S_REFERENCE_MAX_GAUSSIANS);
+}
+
+M2S_EXPORT void m2s_params_default(m2s_params* p) {
+    if (!p) return;
+    std::memset(p, 0, sizeof(*p));
+    p->resolution = 520;  // int(16 + 0.5 * (1024 - 16)): ImGuiUI.cpp:512 with the default quality
+    p->gaussian_std = 0.65f;
+    p->layout = M2S_LAYOUT_REF96;
+}
+
+M2S_EXPORT m2s_status m2s_ctx_create(int device, m2s_ctx** out) {
+    if (!out) { set_error("m2s_ctx_create: out is NULL"); return M2S_E_INVALID; }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        set_error(std::string("no CUDA device available: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0"));
+        return M2S_E_NOGPU;
+    }
+    if (device < 0 || device >= n) { set_error("m2s_ctx_create: bad device index"); return M2S_E_INVALID; }
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) { set_error("mesh2splat_b200 kernels are built for sm_100a only"); return M2S_E_NOGPU; }
+    m2s_ctx* c = new m2s_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    cudaMemPool_t pool;
+    CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thresh = UINT64_MAX;  // keep freed blocks cached: uploads in steady state never hit cudaMalloc
+    CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    CUDA_TRY(cudaMalloc(&c->d_sched, 8 * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&c->d_counter, sizeof(unsigned long long)));
+    CUDA_TRY(cudaMalloc(&c->d_total, sizeof(unsigned long long)));
+    CUDA_TRY(cudaMalloc(&c->d_queue, (size_t)c->queue_cap * sizeof(uint2)));
+    CUDA_TRY(cudaMallocHost(&c->h_total, sizeof(unsigned long long)));
+    CUDA_TRY(cudaEventCreate(&c->ev0));
+    CUDA_TRY(cudaEventCreate(&c->ev1));
+    for (int l = 0; l < 2; ++l) {
+        CUDA_TRY(convert_configure(l, &c->blocks_per_sm[l]));
+        if (c->blocks_per_sm[l] < 1) { set_error("conversion kernel does not fit on this device"); return M2S_E_CUDA; }
+    }
+    *out = c;
+    return M2S_OK;
+}
+
+M2S_EXPORT void m2s_ctx_destroy(m2s_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->d_scratch) cudaFreeAsync(c->d_scratch, c->stream);
+    if (c->d_out) cudaFreeAsync(c->d_out, c->stream);
+    if (c->d_keys) cudaFreeAsync(c->d_keys, c->stream);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_sched); cudaFree(c->d_counter); cudaFree(c->d_total); cudaFree(c->d_queue);
+    cudaFreeHost(c->h_total);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+M2S_EXPORT int m2s_ctx_device(const m2s_ctx* c) { return c ? c->device : -1; }
+M2S_EXPORT int m2s_ctx_sm_count(const m2s_ctx* c) { return c ? c->sm_count : 0; }
+
+// ---- inputs ---------------------------------------------------------------------------------
+M2S_EXPORT m2s_status m2s_compute_bboxes(const float* tris, m2s_primitive* prims, uint32_t nprim, int cumulative) {
+    if ((!tris && nprim) || (!prims && nprim)) { set_error("m2s_compute_bboxes: NULL input"); return M2S_E_INVALID; }
+    // SceneManager.cpp:476-477,514-520,527 — minBB/maxBB live outside the mesh loop
+    float mn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f};
+    float mx[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
+    for (uint32_t p = 0; p < nprim; ++p) {
+        if (!cumulative)
+            for (int c = 0; c < 3; ++c) { mn[c] = 3.402823466e+38f; mx[c] = -3.402823466e+38f; }
+        const uint64_t a = prims[p].first_triangle, b = a + prims[p].triangle_count;
+        for (uint64_t t = a; t < b; ++t)
+            for (int k = 0; k < 3; ++k)
+                for (int c = 0; c < 3; ++c) {
+                    const float v = tris[t * M2S_FLOATS_PER_TRIANGLE + M2S_FLOATS_PER_VERTEX * k + c];
+                    mn[c] = std::min(mn[c], v);
+                    mx[c] = std::max(mx[c], v);
+                }
+        for (int c = 0; c < 3; ++c) { prims[p].bbox_min[c] = mn[c]; prims[p].bbox_max[c] = mx[c]; }
+    }
+    return M2S_OK;
+}
+
+static uint32_t mip_levels(uint32_t w, uint32_t h) {
+    uint32_t m = std::max(w, h), q = 0;
+    while ((m >> (q + 1)) != 0) ++q;
+    return std::min<uint32_t>(q, M2S_MAX_MIP_LEVEL) + 1;
+}
+
+M2S_EXPORT void m2s_scene_free(m2s_ctx* ctx, m2s_dscene* s) {
+    if (!s) return;
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        for (void* p : s->allocs) cudaFreeAsync(p, ctx->stream);
+    }
+    delete s;
+}
+
+M2S_EXPORT m2s_status m2s_scene_upload(m2s_ctx* ctx, const m2s_scene* sc, m2s_dscene** out) {
+    if (!ctx || !sc || !out) { set_error("m2s_scene_upload: NULL argument"); return M2S_E_INVALID; }
+    *out = nullptr;
+    if (sc->triangle_count && !sc->triangles) { set_error("m2s_scene_upload: triangles is NULL"); return M2S_E_INVALID; }
+    if (sc->triangle_count >= (1ull << 32) - kBatch) { set_error("m2s_scene_upload: too many triangles (< 2^32 supported)"); return M2S_E_INVALID; }
+    if ((sc->primitive_count && !sc->primitives) || (sc->texture_count && !sc->textures)) {
+        set_error("m2s_scene_upload: primitive/texture table is NULL"); return M2S_E_INVALID;
+    }
+    // primitive ranges: inside the triangle list, pairwise disjoint
+    std::vector<DRange> ranges;
+    std::vector<DPrim> prims(sc->primitive_count);
+    for (uint32_t p = 0; p < sc->primitive_count; ++p) {
+        const m2s_primitive& src = sc->primitives[p];
+        if (src.first_triangle + src.triangle_count > sc->triangle_count) {
+            set_error("m2s_scene_upload: primitive range exceeds the triangle list"); return M2S_E_INVALID;
+        }
+        const int32_t ti[3] = {src.albedo_texture, src.normal_texture, src.metallic_roughness_texture};
+        for (int m = 0; m < 3; ++m) {
+            if (ti[m] >= (int32_t)sc->texture_count) { set_error("m2s_scene_upload: texture index out of range"); return M2S_E_INVALID; }
+            prims[p].tex[m] = ti[m] < 0 ? -1 : ti[m];
+        }
+        for (int c = 0; c < 3; ++c) { prims[p].bmin[c] = src.bbox_min[c]; prims[p].bmax[c] = src.bbox_max[c]; }
+        for (int c = 0; c < 4; ++c) prims[p].factor[c] = src.base_color_factor[c];
+        prims[p].pad = 0;
+        if (src.triangle_count)
+            ranges.push_back({(uint32_t)src.first_triangle, (uint32_t)(src.first_triangle + src.triangle_count), p, 0});
+    }
+    std::sort(ranges.begin(), ranges.end(), [](const DRange& a, const DRange& b) { return a.first < b.first; });
+    for (size_t i = 1; i < ranges.size(); ++i)
+        if (ranges[i].first < ranges[i - 1].end) { set_error("m2s_scene_upload: primitive triangle ranges overlap"); return M2S_E_INVALID; }
+    for (uint32_t t = 0; t < sc->texture_count; ++t)
+        if (!sc->textures[t].rgba || !sc->textures[t].width || !sc->textures[t].height ||
+            sc->textures[t].width > 32768 || sc->textures[t].height > 32768) {
+            set_error("m2s_scene_upload: bad texture"); return M2S_E_INVALID;
+        }
+
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    m2s_dscene* d = new m2s_dscene();
+    auto fail = [&](m2s_status st) { m2s_scene_free(ctx, d); return st; };
+#define UP_TRY(expr)                                                                 \
+    do {                                                                             \
+        cudaError_t _e = (expr);                                                     \
+        if (_e != cudaSuccess) {                                                     \
+            set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));           \
+            return fail(M2S_E_CUDA);                                                 \
+        }                                                                            \
+    } while (0)
+    auto dalloc = [&](void** p, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMallocAsync(p, std::max<size_t>(bytes, 16), ctx->stream);
+        if (e == cudaSuccess) d->allocs.push_back(*p);
+        return e;
+    };
+    d->ntri = sc->triangle_count;
+    UP_TRY(dalloc((void**)&d->d_tris, sc->triangle_count * (size_t)kTriBytes));
+    if (sc->triangle_count)
+        UP_TRY(cudaMemcpyAsync(d->d_tris, sc->triangles, sc->triangle_count * (size_t)kTriBytes, cudaMemcpyHostToDevice, ctx->stream));
+    d->nranges = (uint32_t)ranges.size();
+    UP_TRY(dalloc((void**)&d->d_ranges, ranges.size() * sizeof(DRange)));
+    if (!ranges.empty())
+        UP_TRY(cudaMemcpyAsync(d->d_ranges, ranges.data(), ranges.size() * sizeof(DRange), cudaMemcpyHostToDevice, ctx->stream));
+    d->nprims = sc->primitive_count;
+    UP_TRY(dalloc((void**)&d->d_prims, prims.size() * sizeof(DPrim)));
+    if (!prims.empty())
+        UP_TRY(cudaMemcpyAsync(d->d_prims, prims.data(), prims.size() * sizeof(DPrim), cudaMemcpyHostToDevice, ctx->stream));
+    // textures: one allocation per texture holding all levels; levels 1.. built on the GPU
+    d->ntex = sc->texture_count;
+    d->h_texs.resize(sc->texture_count);
+    for (uint32_t t = 0; t < sc->texture_count; ++t) {
+        DTexture& dt = d->h_texs[t];
+        std::memset(&dt, 0, sizeof(dt));
+        dt.nlevels = mip_levels(sc->textures[t].width, sc->textures[t].height);
+        size_t texels = 0;
+        uint32_t w = sc->textures[t].width, h = sc->textures[t].height;
+        size_t off[kMaxLevels];
+        for (uint32_t l = 0; l < dt.nlevels; ++l) {
+            dt.w[l] = w; dt.h[l] = h; off[l] = texels;
+            texels += (size_t)w * h;
+            texels = (texels + 63) & ~(size_t)63;  // 256-byte aligned levels
+            w = std::max(1u, w / 2); h = std::max(1u, h / 2);
+        }
+        uint32_t* base = nullptr;
+        UP_TRY(dalloc((void**)&base, texels * 4));
+        for (uint32_t l = 0; l < dt.nlevels; ++l) dt.level[l] = base + off[l];
+        for (uint32_t l = dt.nlevels; l < kMaxLevels; ++l) { dt.level[l] = dt.level[dt.nlevels - 1]; dt.w[l] = dt.w[dt.nlevels - 1]; dt.h[l] = dt.h[dt.nlevels - 1]; }
+        UP_TRY(cudaMemcpyAsync(base, sc->textures[t].rgba, (size_t)dt.w[0] * dt.h[0] * 4, cudaMemcpyHostToDevice, ctx->stream));
+        for (uint32_t l = 1; l < dt.nlevels; ++l)
+            UP_TRY(mip_down_launch(dt.level[l - 1], dt.w[l - 1], dt.h[l - 1], const_cast<uint32_t*>(dt.level[l]), dt.w[l], dt.h[l], ctx->stream));
+    }
+    UP_TRY(dalloc((void**)&d->d_texs, d->h_texs.size() * sizeof(DTexture)));
+    if (!d->h_texs.empty())
+        UP_TRY(cudaMemcpyAsync(d->d_texs, d->h_texs.data(), d->h_texs.size() * sizeof(DTexture), cudaMemcpyHostToDevice, ctx->stream));
+    UP_TRY(cudaStreamSynchronize(ctx->stream));
+#undef UP_TRY
+    *out = d;
+    return M2S_OK;
+}
+
+M2S_EXPORT m2s_status m2s_scene_read_mip(m2s_ctx* ctx, const m2s_dscene* s, uint32_t texture, uint32_t level, uint8_t* dst,
+                                         uint32_t* width, uint32_t* height) {
+    if (!ctx || !s || !dst) { set_error("m2s_scene_read_mip: NULL argument"); return M2S_E_INVALID; }
+    if (texture >= s->ntex || level >= s->h_texs[texture].nlevels) { set_error("m2s_scene_read_mip: out of range"); return M2S_E_INVALID; }
+    const DTexture& t = s->h_texs[texture];
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaMemcpyAsync(dst, t.level[level], (size_t)t.w[level] * t.h[level] * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (width) *width = t.w[level];
+    if (height) *height = t.h[level];
+    return M2S_OK;
+}
+
+// ---- the hot path -----------------------------------------------------------------------------
+static uint64_t effective_cap(const m2s_dscene* s, const m2s_params* p, uint64_t out_capacity) {
+    uint64_t cap = p->max_gaussians;
+    if (cap == 0) cap = (p->flags & M2S_FLAG_UNCAPPED) ? out_capacity : m2s_reference_capacity(p->resolution, s->nprims);
+    return std::min(cap, out_capacity);
+}
+
+M2S_EXPORT m2s_status m2s_convert_enqueue(m2s_ctx* ctx, const m2s_dscene* s, const m2s_params* p, void* d_out,
+                                          uint64_t out_capacity, uint64_t* d_keys, uint64_t* d_total, void* stream_) {
+    if (!ctx || !s || !p) { set_error("m2s_convert: NULL argument"); return M2S_E_INVALID; }
+    if (p->resolution < 1 || p->resolution > 4096) { set_error("m2s_convert: resolution must be in 1..4096"); return M2S_E_INVALID; }
+    if (p->layout > M2S_LAYOUT_PLY_COMPRESSED) { set_error("m2s_convert: unknown layout"); return M2S_E_INVALID; }
+    if (!d_out && out_capacity) { set_error("m2s_convert: output buffer is NULL"); return M2S_E_INVALID; }
+    if (!(p->gaussian_std > 0.0f) && p->layout != M2S_LAYOUT_REF96) { set_error("m2s_convert: gaussian_std must be > 0"); return M2S_E_INVALID; }
+    uint64_t first = std::min<uint64_t>(p->first_triangle, s->ntri);
+    uint64_t count = p->triangle_count;
+    if (count == 0 || first + count > s->ntri) count = s->ntri - first;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : ctx->stream;
+    const uint64_t cap = effective_cap(s, p, out_capacity);
+    const bool ply_rows = p->layout >= M2S_LAYOUT_PLY_STANDARD;
+    const int klayout = ply_rows ? 0 : (int)p->layout;
+    void* kout = d_out;
+    if (ply_rows) {  // REF96 into scratch, then the row encoder
+        m2s_status st = grow(ctx, &ctx->d_scratch, &ctx->scratch_bytes, std::max<uint64_t>(cap, 1) * 96);
+        if (st != M2S_OK) return st;
+        kout = ctx->d_scratch;
+    }
+    if (ctx->dirty) {
+        CUDA_TRY(cudaMemsetAsync(ctx->d_sched, 0, 8 * sizeof(uint32_t), stream));
+        CUDA_TRY(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), stream));
+        ctx->dirty = false;
+    }
+    ConvertArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.tris = s->d_tris;
+    a.tri_first = (uint32_t)first;
+    a.tri_count = (uint32_t)count;
+    a.ranges = s->d_ranges; a.nranges = s->nranges;
+    a.prims = s->d_prims; a.texs = s->d_texs; a.ntex = s->ntex;
+    a.R = p->resolution;
+    a.half_R = (float)p->resolution * 0.5f;
+    a.mult = p->gaussian_std / (float)p->resolution;
+    a.out = (uint8_t*)kout;
+    a.cap = cap;
+    a.keys = (unsigned long long*)d_keys;
+    a.counter = ctx->d_counter;
+    a.total_out = d_total ? (unsigned long long*)d_total : ctx->d_total;
+    a.sched = ctx->d_sched;
+    a.n_batches = (uint32_t)((count + kBatch - 1) / kBatch);
+    a.queue = ctx->d_queue;
+    a.queue_cap = ctx->queue_cap;
+    const int grid = ctx->sm_count * ctx->blocks_per_sm[klayout];
+    cudaError_t e = convert_launch(klayout, a, grid, stream);
+    if (e != cudaSuccess) { ctx->dirty = true; set_error(std::string("convert launch: ") + cudaGetErrorString(e)); return M2S_E_CUDA; }
+    if (ply_rows) {
+        // the count is only known on the device here: the encoder reads it and stops at min(cap, total)
+        const uint32_t fmt = p->layout - M2S_LAYOUT_PLY_STANDARD;
+        CUDA_TRY(ply_rows_launch(ctx->d_scratch, cap, a.total_out, fmt, a.mult, d_out, stream));
+    }
+    return M2S_OK;
+}
+
+M2S_EXPORT m2s_status m2s_convert(m2s_ctx* ctx, const m2s_dscene* s, const m2s_params* p, void* d_out, uint64_t out_capacity,
+                                  uint64_t* d_keys, m2s_result* res) {
+    if (!ctx) { set_error("m2s_convert: ctx is NULL"); return M2S_E_INVALID; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+    m2s_status st = m2s_convert_enqueue(ctx, s, p, d_out, out_capacity, d_keys, nullptr, ctx->stream);
+    if (st != M2S_OK) return st;
+    CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_total, ctx->d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { ctx->dirty = true; set_error(std::string("convert: ") + cudaGetErrorString(e)); return M2S_E_CUDA; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    const uint64_t cap = effective_cap(s, p, out_capacity);
+    const uint64_t total = *ctx->h_total;
+    if (res) { res->total = total; res->cap = cap; res->written = std::min(total, cap); res->device_ms = ms; }
+    if (total > cap) {
+        char buf[160];
+        std::snprintf(buf, sizeof(buf), "m2s_convert: %llu gaussians generated, capacity %llu", (unsigned long long)total, (unsigned long long)cap);
+        set_error(buf);
+        return M2S_E_CAPACITY;
+    }
+    return M2S_OK;
+}
+
+M2S_EXPORT m2s_status m2s_convert_host(m2s_ctx* ctx, const m2s_scene* sc, const m2s_params* p, void* h_out, uint64_t out_capacity,
+                                       uint64_t* h_keys, m2s_result* res) {
+    if (!ctx || !sc || !p || (!h_out && out_capacity)) { set_error("m2s_convert_host: NULL argument"); return M2S_E_INVALID; }
+    const uint32_t stride = m2s_record_stride(p->layout);
+    if (!stride) { set_error("m2s_convert_host: unknown layout"); return M2S_E_INVALID; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    m2s_dscene* ds = nullptr;
+    m2s_status st = m2s_scene_upload(ctx, sc, &ds);
+    if (st != M2S_OK) return st;
+    st = grow(ctx, &ctx->d_out, &ctx->out_bytes, std::max<uint64_t>(out_capacity, 1) * stride);
+    if (st == M2S_OK && h_keys) st = grow(ctx, (void**)&ctx->d_keys, &ctx->keys_bytes, std::max<uint64_t>(out_capacity, 1) * 8);
+    if (st != M2S_OK) { m2s_scene_free(ctx, ds); return st; }
+    m2s_result r;
+    std::memset(&r, 0, sizeof(r));
+    st = m2s_convert(ctx, ds, p, ctx->d_out, out_capacity, h_keys ? (uint64_t*)ctx->d_keys : nullptr, &r);
+    if (st == M2S_OK || st == M2S_E_CAPACITY) {
+        cudaError_t e = cudaSuccess;
+        if (r.written) e = cudaMemcpyAsync(h_out, ctx->d_out, r.written * stride, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess && h_keys && r.written) e = cudaMemcpyAsync(h_keys, ctx->d_keys, r.written * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { set_error(std::string("convert_host download: ") + cudaGetErrorString(e)); st = M2S_E_CUDA; }
+    }
+    if (res) *res = r;
+    m2s_scene_free(ctx, ds);
+    return st;
+}
+
+// ---- outputs ----------------------------------------------------------------------------------
+M2S_EXPORT m2s_status m2s_ply_encode(m2s_ctx* ctx, const void* d_ref96, uint64_t count, uint32_t format, float mult, void* d_rows,
+                                     void* stream_) {
+    if (!ctx || (count && (!d_ref96 || !d_rows))) { set_error("m2s_ply_encode: NULL argument"); return M2S_E_INVALID; }
+    if (format > 2) format = 0;  // savePlyVector default branch (parsers.cpp:646-648)
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(ply_rows_launch(d_ref96, count, nullptr, format, mult, d_rows, stream_ ? (cudaStream_t)stream_ : ctx->stream));
+    return M2S_OK;
+}

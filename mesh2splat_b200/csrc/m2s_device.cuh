@@ -1,0 +1,67 @@
+// m2s_device.cuh — device-side data layout shared by the kernels and the C-ABI host code.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace m2s {
+
+constexpr int kMaxLevels = 5;        // levels 0..4 (GL_TEXTURE_MAX_LEVEL 4, glUtils.cpp:313)
+constexpr int kBatch = 128;          // triangles staged per TMA batch (128 * 144 B = 18 KB)
+constexpr int kThreads = 256;        // threads per CTA
+constexpr int kWarps = kThreads / 32;
+constexpr int kQueue = 2048;         // fragment ids compacted per round (per CTA)
+constexpr int kTriBytes = 144;       // 36 floats
+constexpr uint32_t kBigCand = 4 * kQueue;    // a triangle with more candidate pixels is deferred
+constexpr uint32_t kChunkCand = 8 * kQueue;  // candidates per deferred work item
+constexpr float kGuard = 8192.0f;    // window-coordinate guard band (|xw| beyond -> triangle dropped)
+
+// RGBA8 mip chain of one texture. Levels are pitch-linear, tightly packed, row 0 first.
+struct DTexture {
+    const uint32_t* level[kMaxLevels];
+    uint32_t w[kMaxLevels];
+    uint32_t h[kMaxLevels];
+    uint32_t nlevels;  // q + 1, q = min(4, floor(log2(max(w,h))))
+    uint32_t pad;
+};
+
+// One glTF primitive: the uniforms ConversionPass::conversion uploads per draw call
+// (ConversionPass.cpp:77-112).
+struct DPrim {
+    float bmin[3];
+    float bmax[3];
+    float factor[4];
+    int tex[3];  // albedo, normal, metallic-roughness; -1 = has*Map == 0
+    int pad;
+};
+
+// sorted, disjoint triangle ranges -> primitive
+struct DRange {
+    uint32_t first, end, prim, pad;
+};
+
+struct ConvertArgs {
+    const float4* tris;   // 9 float4 per triangle (3 x {pos3 nrm3 tan4 uv2})
+    uint32_t tri_first;   // shard
+    uint32_t tri_count;
+    const DRange* ranges;
+    uint32_t nranges;
+    const DPrim* prims;
+    const DTexture* texs;
+    uint32_t ntex;
+    uint32_t R;
+    float half_R;
+    float mult;  // sigma / R (SceneManager.cpp:668)
+    uint8_t* out;
+    unsigned long long cap;
+    unsigned long long* keys;          // optional
+    unsigned long long* counter;       // fragments generated (the reference's atomic counter); context-owned,
+                                       // zero at launch, re-zeroed by the last CTA
+    unsigned long long* total_out;     // receives the final count (last CTA out)
+    // scheduling state (zeroed before launch)
+    uint32_t* sched;                   // [0] batch counter [1] batches done [2] queue tail [3] queue head [4] CTAs finished
+    uint32_t n_batches;
+    uint2* queue;                      // deferred big-triangle chunks: (triangle, chunk)
+    uint32_t queue_cap;
+};
+
+}  // namespace m2s

@@ -1,0 +1,694 @@
+// m2s_glb.cpp — .glb -> host scene, and the file-level convert(glb, density) -> .ply surface.
+//
+// Re-implements the INPUT side of the path with the semantics of the reference's loader
+// (src/utils/SceneManager.cpp):
+//   parseGltfFile     :195-459  scene-graph traversal with world transforms (matrix or T*R*S),
+//                               one output primitive per glTF primitive (name "<mesh>_<counter>"),
+//                               de-indexing (u8/u16/u32 indices or sequential), positions * world,
+//                               normals * normalMatrix then normalised or flat face normal,
+//                               tangents * mat3(world) normalised (w kept) or per-face uv-derived
+//                               tangent with handedness, TEXCOORD_0 only
+//   getBufferData     :50-61    accessors are read as TIGHTLY PACKED (bufferView.byteStride is
+//                               ignored) — reproduced, see DESIGN.md "quirks"
+//   parseGltfMaterial :99-193   baseColorFactor, baseColor / normal / metallicRoughness textures
+//   setupMeshBuffers  :468-576  per-primitive bbox = running union over primitives 0..k
+//   loadTextures + glUtils::generateTextures: RGBA8 images (tinygltf forces 4 channels,
+//                               thirdParty/tiny_gltf.h:2609)
+// No third-party code: own GLB/JSON reader, own inflate + PNG decoder.  JPEG images are NOT
+// supported yet (M2S_E_FORMAT) — see DESIGN.md.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/m2s.h"
+
+namespace m2s {
+void set_error(const std::string& msg);
+m2s_status write_ply_rows(const char* path, uint32_t format, const void* rows, uint64_t count);
+}
+
+#define M2S_EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+struct FormatError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+// ---- minimal JSON DOM ---------------------------------------------------------------------------
+struct JValue {
+    enum Type { Null, Bool, Number, String, Array, Object } type = Null;
+    bool b = false;
+    double num = 0.0;
+    std::string str;
+    std::vector<JValue> arr;
+    std::vector<std::pair<std::string, JValue>> obj;
+
+    const JValue* get(const char* key) const {
+        if (type != Object) return nullptr;
+        for (auto& kv : obj)
+            if (kv.first == key) return &kv.second;
+        return nullptr;
+    }
+    int as_int(int dflt) const { return type == Number ? (int)num : dflt; }
+    double as_num(double dflt) const { return type == Number ? num : dflt; }
+    int get_int(const char* key, int dflt) const { const JValue* v = get(key); return v ? v->as_int(dflt) : dflt; }
+    std::string get_str(const char* key) const { const JValue* v = get(key); return (v && v->type == String) ? v->str : std::string(); }
+    size_t size() const { return type == Array ? arr.size() : 0; }
+};
+
+struct JParser {
+    const char* p;
+    const char* end;
+    void ws() { while (p < end && (*p == ' ' || *p == '\n' || *p == '\r' || *p == '\t')) ++p; }
+    [[noreturn]] void fail(const char* what) { throw FormatError(std::string("JSON: ") + what); }
+    JValue parse() { ws(); JValue v = value(0); ws(); return v; }
+    JValue value(int depth) {
+        if (depth > 256) fail("nesting too deep");
+        ws();
+        if (p >= end) fail("unexpected end");
+        JValue v;
+        const char c = *p;
+        if (c == '{') {
+            v.type = JValue::Object; ++p; ws();
+            if (p < end && *p == '}') { ++p; return v; }
+            while (true) {
+                ws();
+                if (p >= end || *p != '"') fail("expected key");
+                std::string k = string();
+                ws();
+                if (p >= end || *p != ':') fail("expected ':'");
+                ++p;
+                v.obj.emplace_back(std::move(k), value(depth + 1));
+                ws();
+                if (p < end && *p == ',') { ++p; continue; }
+                if (p < end && *p == '}') { ++p; break; }
+                fail("expected ',' or '}'");
+            }
+        } else if (c == '[') {
+            v.type = JValue::Array; ++p; ws();
+            if (p < end && *p == ']') { ++p; return v; }
+            while (true) {
+                v.arr.push_back(value(depth + 1));
+                ws();
+                if (p < end && *p == ',') { ++p; continue; }
+                if (p < end && *p == ']') { ++p; break; }
+                fail("expected ',' or ']'");
+            }
+        } else if (c == '"') {
+            v.type = JValue::String; v.str = string();
+        } else if (c == 't' && end - p >= 4 && !std::strncmp(p, "true", 4)) { v.type = JValue::Bool; v.b = true; p += 4; }
+        else if (c == 'f' && end - p >= 5 && !std::strncmp(p, "false", 5)) { v.type = JValue::Bool; v.b = false; p += 5; }
+        else if (c == 'n' && end - p >= 4 && !std::strncmp(p, "null", 4)) { v.type = JValue::Null; p += 4; }
+        else {
+            const char* s = p;
+            while (p < end && (std::strchr("+-0123456789.eE", *p) != nullptr)) ++p;
+            if (s == p) fail("unexpected character");
+            v.type = JValue::Number;
+            v.num = std::strtod(std::string(s, p).c_str(), nullptr);
+        }
+        return v;
+    }
+    std::string string() {
+        ++p;  // opening quote
+        std::string out;
+        while (p < end && *p != '"') {
+            if (*p == '\\') {
+                ++p;
+                if (p >= end) fail("bad escape");
+                switch (*p) {
+                    case 'n': out += '\n'; break; case 't': out += '\t'; break; case 'r': out += '\r'; break;
+                    case 'b': out += '\b'; break; case 'f': out += '\f'; break;
+                    case 'u': {
+                        if (end - p < 5) fail("bad \\u");
+                        unsigned cp = (unsigned)std::strtoul(std::string(p + 1, p + 5).c_str(), nullptr, 16);
+                        p += 4;
+                        if (cp < 0x80) out += (char)cp;
+                        else if (cp < 0x800) { out += (char)(0xC0 | (cp >> 6)); out += (char)(0x80 | (cp & 0x3F)); }
+                        else { out += (char)(0xE0 | (cp >> 12)); out += (char)(0x80 | ((cp >> 6) & 0x3F)); out += (char)(0x80 | (cp & 0x3F)); }
+                        break;
+                    }
+                    default: out += *p;
+                }
+                ++p;
+            } else out += *p++;
+        }
+        if (p >= end) fail("unterminated string");
+        ++p;
+        return out;
+    }
+};
+
+// ---- inflate (RFC 1951) + zlib wrapper ------------------------------------------------------------
+struct BitReader {
+    const uint8_t* p; const uint8_t* end; uint32_t buf = 0; int cnt = 0;
+    uint32_t bits(int n) {
+        while (cnt < n) { if (p >= end) throw FormatError("inflate: out of input"); buf |= (uint32_t)(*p++) << cnt; cnt += 8; }
+        const uint32_t v = buf & ((n == 32) ? 0xffffffffu : ((1u << n) - 1u));
+        buf >>= n; cnt -= n;
+        return v;
+    }
+};
+struct Huff {
+    uint16_t count[16]; uint16_t symbol[288];
+    void build(const uint8_t* len, int n) {
+        std::memset(count, 0, sizeof(count));
+        for (int i = 0; i < n; ++i) count[len[i]]++;
+        count[0] = 0;
+        uint16_t offs[16]; offs[1] = 0;
+        for (int i = 1; i < 15; ++i) offs[i + 1] = offs[i] + count[i];
+        for (int i = 0; i < n; ++i) if (len[i]) symbol[offs[len[i]]++] = (uint16_t)i;
+    }
+    int decode(BitReader& br) const {
+        int code = 0, first = 0, index = 0;
+        for (int len = 1; len <= 15; ++len) {
+            code |= (int)br.bits(1);
+            const int c = count[len];
+            if (code - c < first) return symbol[index + (code - first)];
+            index += c; first += c; first <<= 1; code <<= 1;
+        }
+        throw FormatError("inflate: bad code");
+    }
+};
+std::vector<uint8_t> inflate_zlib(const uint8_t* src, size_t n, size_t expected) {
+    if (n < 6) throw FormatError("zlib: too short");
+    if ((src[0] & 0x0f) != 8 || ((src[0] << 8 | src[1]) % 31) != 0 || (src[1] & 0x20)) throw FormatError("zlib: bad header");
+    BitReader br{src + 2, src + n};
+    std::vector<uint8_t> out;
+    out.reserve(expected);
+    static const uint16_t lbase[29] = {3,4,5,6,7,8,9,10,11,13,15,17,19,23,27,31,35,43,51,59,67,83,99,115,131,163,195,227,258};
+    static const uint16_t lext[29] = {0,0,0,0,0,0,0,0,1,1,1,1,2,2,2,2,3,3,3,3,4,4,4,4,5,5,5,5,0};
+    static const uint16_t dbase[30] = {1,2,3,4,5,7,9,13,17,25,33,49,65,97,129,193,257,385,513,769,1025,1537,2049,3073,4097,6145,8193,12289,16385,24577};
+    static const uint16_t dext[30] = {0,0,0,0,1,1,2,2,3,3,4,4,5,5,6,6,7,7,8,8,9,9,10,10,11,11,12,12,13,13};
+    int last;
+    do {
+        last = (int)br.bits(1);
+        const int type = (int)br.bits(2);
+        if (type == 0) {
+            br.buf = 0; br.cnt = 0;
+            if (br.end - br.p < 4) throw FormatError("inflate: stored block");
+            const unsigned len = br.p[0] | (br.p[1] << 8);
+            br.p += 4;
+            if ((size_t)(br.end - br.p) < len) throw FormatError("inflate: stored block");
+            out.insert(out.end(), br.p, br.p + len);
+            br.p += len;
+        } else if (type == 1 || type == 2) {
+            Huff hl, hd;
+            uint8_t lens[320];
+            if (type == 1) {
+                int i = 0;
+                for (; i < 144; ++i) lens[i] = 8;
+                for (; i < 256; ++i) lens[i] = 9;
+                for (; i < 280; ++i) lens[i] = 7;
+                for (; i < 288; ++i) lens[i] = 8;
+                hl.build(lens, 288);
+                for (i = 0; i < 30; ++i) lens[i] = 5;
+                hd.build(lens, 30);
+            } else {
+                const int nlen = (int)br.bits(5) + 257, ndist = (int)br.bits(5) + 1, ncode = (int)br.bits(4) + 4;
+                static const uint8_t order[19] = {16,17,18,0,8,7,9,6,10,5,11,4,12,3,13,2,14,1,15};
+                uint8_t cl[19] = {0};
+                for (int i = 0; i < ncode; ++i) cl[order[i]] = (uint8_t)br.bits(3);
+                Huff hc; hc.build(cl, 19);
+                int idx = 0;
+                while (idx < nlen + ndist) {
+                    int sym = hc.decode(br);
+                    if (sym < 16) lens[idx++] = (uint8_t)sym;
+                    else {
+                        int rep, val = 0;
+                        if (sym == 16) { if (!idx) throw FormatError("inflate: repeat"); val = lens[idx - 1]; rep = 3 + (int)br.bits(2); }
+                        else if (sym == 17) rep = 3 + (int)br.bits(3);
+                        else rep = 11 + (int)br.bits(7);
+                        if (idx + rep > nlen + ndist) throw FormatError("inflate: too many lengths");
+                        while (rep--) lens[idx++] = (uint8_t)val;
+                    }
+                }
+                hl.build(lens, nlen);
+                hd.build(lens + nlen, ndist);
+            }
+            while (true) {
+                int sym = hl.decode(br);
+                if (sym < 256) out.push_back((uint8_t)sym);
+                else if (sym == 256) break;
+                else {
+                    sym -= 257;
+                    if (sym >= 29) throw FormatError("inflate: bad length");
+                    const int len = lbase[sym] + (int)br.bits(lext[sym]);
+                    const int ds = hd.decode(br);
+                    if (ds >= 30) throw FormatError("inflate: bad distance");
+                    const size_t dist = dbase[ds] + br.bits(dext[ds]);
+                    if (dist > out.size()) throw FormatError("inflate: distance too far");
+                    size_t from = out.size() - dist;
+                    for (int i = 0; i < len; ++i) out.push_back(out[from + i]);
+                }
+            }
+        } else throw FormatError("inflate: bad block type");
+    } while (!last);
+    return out;
+}
+
+// ---- PNG (8-bit, non-interlaced; gray / gray+alpha / rgb / rgba / palette [+tRNS]) -> RGBA8 -------
+struct Image { uint32_t w = 0, h = 0; std::vector<uint8_t> rgba; };
+uint32_t be32(const uint8_t* p) { return (uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3]; }
+
+Image decode_png(const uint8_t* d, size_t n) {
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    if (n < 8 || std::memcmp(d, sig, 8)) throw FormatError("png: bad signature");
+    size_t pos = 8;
+    uint32_t w = 0, h = 0; int depth = 0, ctype = 0, interlace = 0;
+    std::vector<uint8_t> idat, plte, trns;
+    bool have_trns = false;
+    while (pos + 12 <= n) {
+        const uint32_t len = be32(d + pos);
+        const uint8_t* type = d + pos + 4;
+        const uint8_t* data = d + pos + 8;
+        if (pos + 12 + (size_t)len > n) throw FormatError("png: truncated chunk");
+        if (!std::memcmp(type, "IHDR", 4)) {
+            if (len < 13) throw FormatError("png: bad IHDR");
+            w = be32(data); h = be32(data + 4); depth = data[8]; ctype = data[9]; interlace = data[12];
+        } else if (!std::memcmp(type, "PLTE", 4)) plte.assign(data, data + len);
+        else if (!std::memcmp(type, "tRNS", 4)) { trns.assign(data, data + len); have_trns = true; }
+        else if (!std::memcmp(type, "IDAT", 4)) idat.insert(idat.end(), data, data + len);
+        else if (!std::memcmp(type, "IEND", 4)) break;
+        pos += 12 + (size_t)len;
+    }
+    if (!w || !h || w > 32768 || h > 32768) throw FormatError("png: bad dimensions");
+    if (depth != 8) throw FormatError("png: only 8-bit channels are supported");
+    if (interlace) throw FormatError("png: interlaced images are not supported");
+    int ch;
+    switch (ctype) { case 0: ch = 1; break; case 2: ch = 3; break; case 3: ch = 1; break; case 4: ch = 2; break; case 6: ch = 4; break;
+                     default: throw FormatError("png: bad colour type"); }
+    const size_t stride = (size_t)w * ch;
+    std::vector<uint8_t> raw = inflate_zlib(idat.data(), idat.size(), (stride + 1) * h);
+    if (raw.size() < (stride + 1) * h) throw FormatError("png: not enough pixel data");
+    std::vector<uint8_t> img(stride * h);
+    std::vector<uint8_t> zero(stride, 0);
+    for (uint32_t y = 0; y < h; ++y) {
+        const uint8_t ft = raw[(stride + 1) * y];
+        const uint8_t* in = raw.data() + (stride + 1) * y + 1;
+        uint8_t* cur = img.data() + stride * y;
+        const uint8_t* up = y ? img.data() + stride * (y - 1) : zero.data();
+        for (size_t i = 0; i < stride; ++i) {
+            const int a = i >= (size_t)ch ? cur[i - ch] : 0, b = up[i], c = i >= (size_t)ch ? up[i - ch] : 0;
+            int pred = 0;
+            switch (ft) {
+                case 0: pred = 0; break; case 1: pred = a; break; case 2: pred = b; break; case 3: pred = (a + b) >> 1; break;
+                case 4: { const int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c);
+                          pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); break; }
+                default: throw FormatError("png: bad filter");
+            }
+            cur[i] = (uint8_t)(in[i] + pred);
+        }
+    }
+    Image out; out.w = w; out.h = h; out.rgba.resize((size_t)w * h * 4);
+    for (size_t i = 0; i < (size_t)w * h; ++i) {
+        uint8_t* o = &out.rgba[i * 4];
+        const uint8_t* s = &img[i * ch];
+        switch (ctype) {
+            case 0: o[0] = o[1] = o[2] = s[0]; o[3] = (have_trns && trns.size() >= 2 && trns[1] == s[0]) ? 0 : 255; break;
+            case 2: o[0] = s[0]; o[1] = s[1]; o[2] = s[2];
+                    o[3] = (have_trns && trns.size() >= 6 && trns[1] == s[0] && trns[3] == s[1] && trns[5] == s[2]) ? 0 : 255; break;
+            case 3: { const size_t k = s[0]; if (k * 3 + 2 >= plte.size()) throw FormatError("png: palette index");
+                      o[0] = plte[k * 3]; o[1] = plte[k * 3 + 1]; o[2] = plte[k * 3 + 2]; o[3] = k < trns.size() ? trns[k] : 255; break; }
+            case 4: o[0] = o[1] = o[2] = s[0]; o[3] = s[1]; break;
+            case 6: o[0] = s[0]; o[1] = s[1]; o[2] = s[2]; o[3] = s[3]; break;
+        }
+    }
+    return out;
+}
+
+Image decode_image(const uint8_t* d, size_t n) {
+    if (n >= 8 && d[0] == 0x89 && d[1] == 'P') return decode_png(d, n);
+    if (n >= 3 && d[0] == 0xff && d[1] == 0xd8) throw FormatError("JPEG images are not supported by this loader yet");
+    throw FormatError("unknown image format");
+}
+
+// ---- small linear algebra (column-major, GLM conventions) ----------------------------------------
+struct M4 { float m[4][4]; };  // m[col][row]
+M4 identity() { M4 r; std::memset(&r, 0, sizeof(r)); for (int i = 0; i < 4; ++i) r.m[i][i] = 1.0f; return r; }
+M4 mul(const M4& a, const M4& b) {
+    M4 r;
+    for (int c = 0; c < 4; ++c)
+        for (int row = 0; row < 4; ++row) {
+            float s = 0.0f;
+            for (int k = 0; k < 4; ++k) s += a.m[k][row] * b.m[c][k];
+            r.m[c][row] = s;
+        }
+    return r;
+}
+struct V3 { float x, y, z; };
+V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+V3 operator*(V3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+V3 cross(V3 a, V3 b) { return {a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y}; }
+float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+V3 normalize(V3 a) { const float inv = 1.0f / std::sqrt(dot(a, a)); return a * inv; }
+V3 xform_point(const M4& M, V3 p) {
+    return {M.m[0][0] * p.x + M.m[1][0] * p.y + M.m[2][0] * p.z + M.m[3][0], M.m[0][1] * p.x + M.m[1][1] * p.y + M.m[2][1] * p.z + M.m[3][1],
+            M.m[0][2] * p.x + M.m[1][2] * p.y + M.m[2][2] * p.z + M.m[3][2]};
+}
+struct M3 { float m[3][3]; };
+V3 mul3(const M3& M, V3 p) {
+    return {M.m[0][0] * p.x + M.m[1][0] * p.y + M.m[2][0] * p.z, M.m[0][1] * p.x + M.m[1][1] * p.y + M.m[2][1] * p.z,
+            M.m[0][2] * p.x + M.m[1][2] * p.y + M.m[2][2] * p.z};
+}
+M3 upper3(const M4& M) { M3 r; for (int c = 0; c < 3; ++c) for (int row = 0; row < 3; ++row) r.m[c][row] = M.m[c][row]; return r; }
+M3 inverse_transpose(const M3& a) {  // transpose(inverse(a)) = cofactor matrix / det
+    const float (*m)[3] = a.m;
+    const float c00 = m[1][1] * m[2][2] - m[2][1] * m[1][2], c01 = m[1][2] * m[2][0] - m[1][0] * m[2][2], c02 = m[1][0] * m[2][1] - m[1][1] * m[2][0];
+    const float det = m[0][0] * c00 + m[0][1] * c01 + m[0][2] * c02;
+    const float id = 1.0f / det;
+    M3 r;
+    r.m[0][0] = c00 * id; r.m[0][1] = c01 * id; r.m[0][2] = c02 * id;
+    r.m[1][0] = (m[2][1] * m[0][2] - m[0][1] * m[2][2]) * id; r.m[1][1] = (m[0][0] * m[2][2] - m[2][0] * m[0][2]) * id; r.m[1][2] = (m[2][0] * m[0][1] - m[0][0] * m[2][1]) * id;
+    r.m[2][0] = (m[0][1] * m[1][2] - m[1][1] * m[0][2]) * id; r.m[2][1] = (m[1][0] * m[0][2] - m[0][0] * m[1][2]) * id; r.m[2][2] = (m[0][0] * m[1][1] - m[1][0] * m[0][1]) * id;
+    return r;
+}
+M4 trs(const JValue& node) {
+    M4 T = identity(), R = identity(), S = identity();
+    const JValue* t = node.get("translation");
+    if (t && t->size() == 3) for (int i = 0; i < 3; ++i) T.m[3][i] = (float)t->arr[i].as_num(0);
+    const JValue* q = node.get("rotation");
+    if (q && q->size() == 4) {  // glm::mat4_cast(quat(w,x,y,z))
+        const float x = (float)q->arr[0].as_num(0), y = (float)q->arr[1].as_num(0), z = (float)q->arr[2].as_num(0), w = (float)q->arr[3].as_num(1);
+        const float qxx = x * x, qyy = y * y, qzz = z * z, qxz = x * z, qxy = x * y, qyz = y * z, qwx = w * x, qwy = w * y, qwz = w * z;
+        R.m[0][0] = 1 - 2 * (qyy + qzz); R.m[0][1] = 2 * (qxy + qwz); R.m[0][2] = 2 * (qxz - qwy);
+        R.m[1][0] = 2 * (qxy - qwz); R.m[1][1] = 1 - 2 * (qxx + qzz); R.m[1][2] = 2 * (qyz + qwx);
+        R.m[2][0] = 2 * (qxz + qwy); R.m[2][1] = 2 * (qyz - qwx); R.m[2][2] = 1 - 2 * (qxx + qyy);
+    }
+    const JValue* s = node.get("scale");
+    if (s && s->size() == 3) for (int i = 0; i < 3; ++i) S.m[i][i] = (float)s->arr[i].as_num(1);
+    return mul(mul(T, R), S);
+}
+
+}  // namespace
+
+// ---- the host scene object -------------------------------------------------------------------------
+struct m2s_hscene {
+    std::vector<float> triangles;
+    std::vector<m2s_primitive> primitives;
+    std::vector<std::string> names;
+    std::vector<Image> images;
+    std::vector<m2s_texture> textures;
+    m2s_scene view;
+};
+
+namespace {
+
+struct Glb {
+    JValue json;
+    const uint8_t* bin = nullptr;
+    size_t bin_size = 0;
+};
+
+struct AccessorView { const uint8_t* data; size_t count; int componentType; std::string type; size_t avail; };
+
+AccessorView accessor(const Glb& g, int index) {
+    const JValue* accs = g.json.get("accessors");
+    if (!accs || index < 0 || (size_t)index >= accs->size()) throw FormatError("accessor index out of range");
+    const JValue& a = accs->arr[index];
+    const int bv = a.get_int("bufferView", -1);
+    const JValue* bvs = g.json.get("bufferViews");
+    if (!bvs || bv < 0 || (size_t)bv >= bvs->size()) throw FormatError("accessor without bufferView (sparse accessors unsupported)");
+    const JValue& v = bvs->arr[bv];
+    if (v.get_int("buffer", 0) != 0) throw FormatError("only the GLB-embedded buffer 0 is supported");
+    const size_t off = (size_t)v.get_int("byteOffset", 0) + (size_t)a.get_int("byteOffset", 0);
+    if (off > g.bin_size) throw FormatError("accessor offset beyond the BIN chunk");
+    AccessorView r;
+    r.data = g.bin + off; r.avail = g.bin_size - off;
+    r.count = (size_t)a.get_int("count", 0);
+    r.componentType = a.get_int("componentType", 0);
+    r.type = a.get_str("type");
+    return r;
+}
+
+// getBufferData<T> (SceneManager.cpp:50-61): tightly packed float arrays, stride ignored
+const float* float_array(const Glb& g, int acc, int comps, size_t* count) {
+    const AccessorView v = accessor(g, acc);
+    if (v.componentType != 5126) throw FormatError("vertex attribute is not FLOAT (normalised integer attributes unsupported, as in the reference)");
+    if (v.count * comps * sizeof(float) > v.avail) throw FormatError("vertex attribute exceeds the BIN chunk");
+    *count = v.count;
+    return reinterpret_cast<const float*>(v.data);
+}
+
+int texture_image(const Glb& g, const JValue* texinfo) {
+    if (!texinfo) return -1;
+    const int ti = texinfo->get_int("index", -1);
+    const JValue* texs = g.json.get("textures");
+    if (!texs || ti < 0 || (size_t)ti >= texs->size()) return -1;
+    const int src = texs->arr[ti].get_int("source", -1);
+    const JValue* imgs = g.json.get("images");
+    if (!imgs || src < 0 || (size_t)src >= imgs->size()) return -1;
+    return src;
+}
+
+}  // namespace
+
+M2S_EXPORT void m2s_hscene_free(m2s_hscene* s) { delete s; }
+M2S_EXPORT const m2s_scene* m2s_hscene_view(const m2s_hscene* s) { return s ? &s->view : nullptr; }
+
+M2S_EXPORT m2s_status m2s_glb_load(const char* path, int cumulative_bbox, m2s_hscene** out) {
+    if (!path || !out) { m2s::set_error("m2s_glb_load: NULL argument"); return M2S_E_INVALID; }
+    *out = nullptr;
+    std::vector<uint8_t> file;
+    {
+        FILE* f = std::fopen(path, "rb");
+        if (!f) { m2s::set_error(std::string("Failed to load glTF: cannot open ") + path); return M2S_E_IO; }
+        std::fseek(f, 0, SEEK_END);
+        const long sz = std::ftell(f);
+        std::fseek(f, 0, SEEK_SET);
+        file.resize(sz > 0 ? (size_t)sz : 0);
+        const size_t rd = file.empty() ? 0 : std::fread(file.data(), 1, file.size(), f);
+        std::fclose(f);
+        if (rd != file.size()) { m2s::set_error(std::string("short read from ") + path); return M2S_E_IO; }
+    }
+    std::unique_ptr<m2s_hscene> hs(new m2s_hscene());
+    try {
+        if (file.size() < 20 || std::memcmp(file.data(), "glTF", 4)) throw FormatError("not a binary glTF (.glb) file");
+        auto le32 = [&](size_t o) { return (uint32_t)file[o] | (uint32_t)file[o + 1] << 8 | (uint32_t)file[o + 2] << 16 | (uint32_t)file[o + 3] << 24; };
+        if (le32(4) != 2) throw FormatError("unsupported glTF container version");
+        const size_t total = std::min<size_t>(le32(8), file.size());
+        Glb g;
+        size_t pos = 12;
+        bool have_json = false;
+        while (pos + 8 <= total) {
+            const uint32_t clen = le32(pos), ctype = le32(pos + 4);
+            if (pos + 8 + (size_t)clen > total) throw FormatError("truncated chunk");
+            if (ctype == 0x4E4F534A && !have_json) {
+                JParser jp{reinterpret_cast<const char*>(file.data() + pos + 8), reinterpret_cast<const char*>(file.data() + pos + 8 + clen)};
+                g.json = jp.parse();
+                have_json = true;
+            } else if (ctype == 0x004E4942 && !g.bin) { g.bin = file.data() + pos + 8; g.bin_size = clen; }
+            pos += 8 + (size_t)clen;
+            pos = (pos + 3) & ~(size_t)3;
+        }
+        if (!have_json) throw FormatError("no JSON chunk");
+
+        // ---- scene graph -> mesh instances (SceneManager.cpp:213-283) ----
+        struct Inst { int mesh; M4 world; };
+        std::vector<Inst> insts;
+        const JValue* nodes = g.json.get("nodes");
+        const JValue* meshes = g.json.get("meshes");
+        const size_t nmesh = meshes ? meshes->size() : 0;
+        struct Frame { int node; M4 parent; };
+        auto traverse = [&](int root) {
+            std::vector<Frame> stack{{root, identity()}};
+            size_t visited = 0;
+            while (!stack.empty()) {
+                Frame fr = stack.back(); stack.pop_back();
+                if (!nodes || fr.node < 0 || (size_t)fr.node >= nodes->size()) continue;
+                if (++visited > 4 * nodes->size() + 16) throw FormatError("node graph has a cycle");
+                const JValue& nd = nodes->arr[fr.node];
+                M4 local = identity();
+                const JValue* mat = nd.get("matrix");
+                if (mat && mat->size() == 16) { for (int c = 0; c < 4; ++c) for (int r = 0; r < 4; ++r) local.m[c][r] = (float)mat->arr[c * 4 + r].as_num(0); }
+                else local = trs(nd);
+                const M4 world = mul(fr.parent, local);
+                const int mi = nd.get_int("mesh", -1);
+                if (mi >= 0 && (size_t)mi < nmesh) insts.push_back({mi, world});
+                const JValue* ch = nd.get("children");
+                if (ch) for (size_t i = ch->size(); i-- > 0;) stack.push_back({ch->arr[i].as_int(-1), world});  // reversed: pre-order like the recursion
+            }
+        };
+        const JValue* scenes = g.json.get("scenes");
+        if (scenes && scenes->size()) {
+            int si = g.json.get_int("scene", -1);
+            if (si < 0 || (size_t)si >= scenes->size()) si = 0;
+            const JValue* roots = scenes->arr[si].get("nodes");
+            if (roots) for (auto& r : roots->arr) traverse(r.as_int(-1));
+        }
+        if (insts.empty()) for (size_t i = 0; i < nmesh; ++i) insts.push_back({(int)i, identity()});
+
+        // ---- images are decoded once and shared ----
+        std::map<int, int> image_to_tex;
+        auto get_texture = [&](int image) -> int {
+            if (image < 0) return -1;
+            auto it = image_to_tex.find(image);
+            if (it != image_to_tex.end()) return it->second;
+            const JValue& im = g.json.get("images")->arr[image];
+            const int bv = im.get_int("bufferView", -1);
+            const JValue* bvs = g.json.get("bufferViews");
+            if (bv < 0 || !bvs || (size_t)bv >= bvs->size()) throw FormatError("image without bufferView (external uri images unsupported in .glb)");
+            const JValue& v = bvs->arr[bv];
+            const size_t off = (size_t)v.get_int("byteOffset", 0), len = (size_t)v.get_int("byteLength", 0);
+            if (off + len > g.bin_size) throw FormatError("image exceeds the BIN chunk");
+            hs->images.push_back(decode_image(g.bin + off, len));
+            const int idx = (int)hs->images.size() - 1;
+            image_to_tex[image] = idx;
+            return idx;
+        };
+
+        // ---- primitives (SceneManager.cpp:286-457) ----
+        int meshCounter = 0;
+        const JValue* materials = g.json.get("materials");
+        for (const Inst& in : insts) {
+            const JValue& mesh = meshes->arr[in.mesh];
+            const M3 world3 = upper3(in.world);
+            const M3 normalMatrix = inverse_transpose(world3);
+            const JValue* prims = mesh.get("primitives");
+            if (!prims) continue;
+            for (const JValue& pr : prims->arr) {
+                const int mode = pr.get_int("mode", 4);
+                if (mode != 4) continue;  // non-triangle primitive skipped (:291-294)
+                const JValue* attrs = pr.get("attributes");
+                if (!attrs || !attrs->get("POSITION")) continue;  // (:297-300)
+                std::string base = mesh.get_str("name");
+                if (base.empty()) base = "mesh";
+                const std::string name = base + "_" + std::to_string(meshCounter++);
+
+                size_t nverts = 0;
+                const float* pos = float_array(g, attrs->get("POSITION")->as_int(-1), 3, &nverts);
+                std::vector<uint32_t> indices;
+                const int ia = pr.get_int("indices", -1);
+                if (ia >= 0) {
+                    const AccessorView iv = accessor(g, ia);
+                    indices.resize(iv.count);
+                    const size_t es = iv.componentType == 5123 ? 2 : (iv.componentType == 5125 ? 4 : (iv.componentType == 5121 ? 1 : 0));
+                    if (!es) continue;  // unsupported index type: primitive skipped (:336-339)
+                    if (iv.count * es > iv.avail) throw FormatError("index accessor exceeds the BIN chunk");
+                    for (size_t i = 0; i < iv.count; ++i) {
+                        if (es == 2) { uint16_t v; std::memcpy(&v, iv.data + 2 * i, 2); indices[i] = v; }
+                        else if (es == 4) { uint32_t v; std::memcpy(&v, iv.data + 4 * i, 4); indices[i] = v; }
+                        else indices[i] = iv.data[i];
+                    }
+                } else { indices.resize(nverts); for (size_t i = 0; i < nverts; ++i) indices[i] = (uint32_t)i; }
+                if (indices.size() < 3 || indices.size() % 3 != 0) continue;  // (:350-353)
+                for (uint32_t ix : indices) if (ix >= nverts) throw FormatError("vertex index out of range");
+
+                size_t cnt = 0;
+                const float* nrm = attrs->get("NORMAL") ? float_array(g, attrs->get("NORMAL")->as_int(-1), 3, &cnt) : nullptr;
+                if (nrm && cnt < nverts) throw FormatError("NORMAL accessor shorter than POSITION");
+                const float* uvs = attrs->get("TEXCOORD_0") ? float_array(g, attrs->get("TEXCOORD_0")->as_int(-1), 2, &cnt) : nullptr;
+                if (uvs && cnt < nverts) throw FormatError("TEXCOORD_0 accessor shorter than POSITION");
+                const float* tan = attrs->get("TANGENT") ? float_array(g, attrs->get("TANGENT")->as_int(-1), 4, &cnt) : nullptr;
+                if (tan && cnt < nverts) throw FormatError("TANGENT accessor shorter than POSITION");
+
+                m2s_primitive P;
+                std::memset(&P, 0, sizeof(P));
+                P.base_color_factor[0] = P.base_color_factor[1] = P.base_color_factor[2] = P.base_color_factor[3] = 1.0f;
+                P.albedo_texture = P.normal_texture = P.metallic_roughness_texture = -1;
+                const int mi = pr.get_int("material", -1);
+                if (materials && mi >= 0 && (size_t)mi < materials->size()) {  // parseGltfMaterial (:99-193)
+                    const JValue& m = materials->arr[mi];
+                    const JValue* pbr = m.get("pbrMetallicRoughness");
+                    if (pbr) {
+                        const JValue* bf = pbr->get("baseColorFactor");
+                        if (bf && bf->size() == 4) for (int i = 0; i < 4; ++i) P.base_color_factor[i] = (float)bf->arr[i].as_num(1);
+                        P.albedo_texture = get_texture(texture_image(g, pbr->get("baseColorTexture")));
+                        P.metallic_roughness_texture = get_texture(texture_image(g, pbr->get("metallicRoughnessTexture")));
+                    }
+                    P.normal_texture = get_texture(texture_image(g, m.get("normalTexture")));
+                }
+
+                P.first_triangle = hs->triangles.size() / M2S_FLOATS_PER_TRIANGLE;
+                P.triangle_count = indices.size() / 3;
+                hs->triangles.resize(hs->triangles.size() + P.triangle_count * M2S_FLOATS_PER_TRIANGLE);
+                float* dst = hs->triangles.data() + P.first_triangle * M2S_FLOATS_PER_TRIANGLE;
+                for (size_t i = 0; i < indices.size(); i += 3, dst += M2S_FLOATS_PER_TRIANGLE) {
+                    V3 p[3], n[3]; float t4[3][4], uv[3][2];
+                    for (int e = 0; e < 3; ++e) {
+                        const uint32_t ix = indices[i + e];
+                        p[e] = xform_point(in.world, {pos[3 * ix], pos[3 * ix + 1], pos[3 * ix + 2]});
+                        uv[e][0] = uvs ? uvs[2 * ix] : 0.0f; uv[e][1] = uvs ? uvs[2 * ix + 1] : 0.0f;
+                        if (nrm) n[e] = normalize(mul3(normalMatrix, {nrm[3 * ix], nrm[3 * ix + 1], nrm[3 * ix + 2]}));
+                    }
+                    if (!nrm) { const V3 fn = normalize(cross(p[1] - p[0], p[2] - p[0])); n[0] = n[1] = n[2] = fn; }  // (:406-413)
+                    if (tan) {
+                        for (int e = 0; e < 3; ++e) {
+                            const uint32_t ix = indices[i + e];
+                            const V3 tv = normalize(mul3(world3, {tan[4 * ix], tan[4 * ix + 1], tan[4 * ix + 2]}));
+                            t4[e][0] = tv.x; t4[e][1] = tv.y; t4[e][2] = tv.z; t4[e][3] = tan[4 * ix + 3];
+                        }
+                    } else {  // (:421-451)
+                        const V3 dp1 = p[1] - p[0], dp2 = p[2] - p[0];
+                        const float du1 = uv[1][0] - uv[0][0], dv1 = uv[1][1] - uv[0][1], du2 = uv[2][0] - uv[0][0], dv2 = uv[2][1] - uv[0][1];
+                        float det = du1 * dv2 - dv1 * du2;
+                        if (std::fabs(det) < 1e-8f) det = 1.0f;
+                        const float inv = 1.0f / det;
+                        V3 tg = (dp1 * dv2 - dp2 * dv1) * inv, bt = (dp2 * du1 - dp1 * du2) * inv;
+                        tg = normalize(tg); bt = normalize(bt);
+                        const V3 nn = normalize(cross(dp1, dp2));
+                        const float hd = dot(cross(nn, tg), bt) < 0.0f ? -1.0f : 1.0f;
+                        for (int e = 0; e < 3; ++e) { t4[e][0] = tg.x; t4[e][1] = tg.y; t4[e][2] = tg.z; t4[e][3] = hd; }
+                    }
+                    for (int e = 0; e < 3; ++e) {
+                        float* v = dst + 12 * e;
+                        v[0] = p[e].x; v[1] = p[e].y; v[2] = p[e].z; v[3] = n[e].x; v[4] = n[e].y; v[5] = n[e].z;
+                        v[6] = t4[e][0]; v[7] = t4[e][1]; v[8] = t4[e][2]; v[9] = t4[e][3]; v[10] = uv[e][0]; v[11] = uv[e][1];
+                    }
+                }
+                hs->primitives.push_back(P);
+                hs->names.push_back(name);
+            }
+        }
+        m2s_compute_bboxes(hs->triangles.data(), hs->primitives.data(), (uint32_t)hs->primitives.size(), cumulative_bbox);
+        for (const Image& im : hs->images) hs->textures.push_back({im.rgba.data(), im.w, im.h});
+    } catch (const FormatError& e) {
+        m2s::set_error(std::string("Failed to load glTF: ") + e.what());
+        return M2S_E_FORMAT;
+    } catch (const std::bad_alloc&) {
+        m2s::set_error("Failed to load glTF: out of memory");
+        return M2S_E_IO;
+    }
+    hs->view.triangles = hs->triangles.data();
+    hs->view.triangle_count = hs->triangles.size() / M2S_FLOATS_PER_TRIANGLE;
+    hs->view.primitives = hs->primitives.data();
+    hs->view.primitive_count = (uint32_t)hs->primitives.size();
+    hs->view.textures = hs->textures.data();
+    hs->view.texture_count = (uint32_t)hs->textures.size();
+    *out = hs.release();
+    return M2S_OK;
+}
+
+// loadModel -> ConversionPass::execute -> exportPly in one call
+M2S_EXPORT m2s_status m2s_convert_file(m2s_ctx* ctx, const char* glb_path, uint32_t resolution, float gaussian_std, uint32_t ply_format,
+                                       const char* ply_path, m2s_result* result) {
+    if (!ctx || !glb_path || !ply_path) { m2s::set_error("m2s_convert_file: NULL argument"); return M2S_E_INVALID; }
+    if (ply_format > 2) ply_format = 0;
+    m2s_hscene* hs = nullptr;
+    m2s_status st = m2s_glb_load(glb_path, 1, &hs);
+    if (st != M2S_OK) return st;
+    m2s_params p;
+    m2s_params_default(&p);
+    p.resolution = resolution;
+    p.gaussian_std = gaussian_std;
+    p.layout = M2S_LAYOUT_PLY_STANDARD + ply_format;  // rows are encoded on the GPU
+    const uint64_t cap = m2s_reference_capacity(resolution, hs->view.primitive_count);
+    const uint32_t stride = m2s_record_stride(p.layout);
+    std::vector<uint8_t> rows;
+    try { rows.resize((size_t)cap * stride); } catch (const std::bad_alloc&) { m2s_hscene_free(hs); m2s::set_error("out of memory"); return M2S_E_IO; }
+    m2s_result r;
+    std::memset(&r, 0, sizeof(r));
+    st = m2s_convert_host(ctx, &hs->view, &p, rows.data(), cap, nullptr, &r);
+    m2s_hscene_free(hs);
+    if (result) *result = r;
+    if (st != M2S_OK && st != M2S_E_CAPACITY) return st;
+    const m2s_status wst = m2s::write_ply_rows(ply_path, ply_format, rows.data(), r.written);
+    return wst != M2S_OK ? wst : st;
+}

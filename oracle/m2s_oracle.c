@@ -170,7 +170,7 @@ ORC_API int orc_triangle_setup(const float* tri, const float bmin[3], const floa
     for (int k = 0; k < 3; ++k) {
         float ndx = s->ouv[k][0] * 2.0f - 1.0f, ndy = s->ouv[k][1] * 2.0f - 1.0f;
         float xw = ndx * half + half, yw = ndy * half + half;
-        if (!isfinite(xw) || !isfinite(yw) || fabsf(xw) > 1.0e6f || fabsf(yw) > 1.0e6f) { s->valid = 0; xw = yw = 0.0f; }
+        if (!isfinite(xw) || !isfinite(yw) || fabsf(xw) > 8192.0f || fabsf(yw) > 8192.0f) { s->valid = 0; xw = yw = 0.0f; }
         s->X[k] = (int32_t)lrintf(xw * 256.0f);
         s->Y[k] = (int32_t)lrintf(yw * 256.0f);
     }

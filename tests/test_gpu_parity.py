@@ -1,0 +1,251 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+All marked gpu; they run on the B200 box.  /root/reference is never touched here.
+"""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+import oracle
+from mesh2splat_b200 import _abi, synth
+from mesh2splat_b200._abi import (FLAG_UNCAPPED, LAYOUT_PACKED56, LAYOUT_PLY_COMPRESSED, LAYOUT_PLY_PBR,
+                                  LAYOUT_PLY_STANDARD, LAYOUT_REF96, Primitive, Scene)
+from util import assert_records_match
+
+pytestmark = pytest.mark.gpu
+
+
+def run_both(ctx, scene, R, layout=LAYOUT_REF96, **kw):
+    ds = ctx.upload(scene)
+    out = ctx.convert(ds, R, layout, want_keys=True, **kw)
+    rec, keys, total = oracle.convert(scene, R, layout, want_keys=True, capacity=out.cap if out.cap else 1, **kw)
+    ds.free()
+    return out, rec, keys, total
+
+
+def check(ctx, scene, R, layout=LAYOUT_REF96, **kw):
+    out, rec, keys, total = run_both(ctx, scene, R, layout, **kw)
+    assert out.total == total, f"total {out.total} != oracle {total}"
+    assert out.written == len(rec)
+    assert_records_match(scene, layout, out.numpy(), out.keys_numpy(), rec, keys)
+    return out
+
+
+# ---- KATs ------------------------------------------------------------------------------
+def test_unit_quad_kat(gpu_ctx):
+    s = synth.unit_quad()
+    out = check(gpu_ctx, s, 64)
+    assert out.total == 4096 and out.written == 4096 and not out.overflow
+    rec, keys = out.numpy(), out.keys_numpy()
+    tri = (keys >> np.uint64(24)).astype(np.int64)
+    assert np.bincount(tri).tolist() == [2080, 2016]  # diagonal centres belong to triangle 0 (left edge)
+    px = (keys & np.uint64(0xfff)).astype(np.float32)
+    py = ((keys >> np.uint64(12)) & np.uint64(0xfff)).astype(np.float32)
+    np.testing.assert_allclose(rec["position"][:, 0], (px + 0.5) / 64, atol=1e-6)
+    np.testing.assert_allclose(rec["position"][:, 1], (py + 0.5) / 64, atol=1e-6)
+    assert np.all(rec["position"][:, 2] == 0)
+    np.testing.assert_allclose(rec["scale"], np.tile(np.array([1, 1, 1e-7, 0], np.float32), (4096, 1)), rtol=1e-6)
+    q0 = np.array([0, 0.9238795, 0.38268343, 0], np.float32)
+    q1 = np.array([0.9238795, 0, 0, 0.38268343], np.float32)
+    np.testing.assert_allclose(rec["rotation"][tri == 0], np.tile(q0, (2080, 1)), atol=1e-6)
+    np.testing.assert_allclose(rec["rotation"][tri == 1], np.tile(q1, (2016, 1)), atol=1e-6)
+    assert np.all(rec["color"] == 1.0)
+    np.testing.assert_allclose(rec["pbr"], np.tile(np.array([0.1, 0.5, 0, 1], np.float32), (4096, 1)))
+    np.testing.assert_allclose(rec["normal"], np.tile(np.array([0, 0, 1, 0], np.float32), (4096, 1)), atol=1e-6)
+
+
+def test_unit_quad_textured(gpu_ctx):
+    s = synth.unit_quad()
+    s.textures = [synth.random_texture(256, 256, 7)]
+    s.primitives[0].albedo_texture = 0
+    s.primitives[0].base_color_factor = (0.5, 0.25, 1.0, 0.8)
+    check(gpu_ctx, s, 64)
+    check(gpu_ctx, s, 300)   # magnification
+    check(gpu_ctx, s, 16)    # lambda at the level-4 clamp
+
+
+def test_box_axis_selection(gpu_ctx):
+    s = synth.box((1.0, 2.0, 3.0))
+    out = check(gpu_ctx, s, 96)
+    assert out.total > 0
+    s2 = synth.box((2.0, 2.0, 2.0), origin=(-1, -1, -1))  # |nx| == |ny| style ties on a cube
+    check(gpu_ctx, s2, 50)
+
+
+@pytest.mark.parametrize("R", [33, 128, 256])
+def test_textured_sphere(gpu_ctx, R):
+    tri = synth.displaced_sphere(48, 24, seed=3, amplitude=0.1)
+    tex = synth.make_material_textures(256, 11)
+    s = Scene(tri, [Primitive(0, len(tri), (0.9, 0.8, 0.7, 1.0), 0, 1, 2)], tex)
+    s.compute_bboxes()
+    check(gpu_ctx, s, R)
+
+
+def test_npot_textures_and_repeat(gpu_ctx):
+    tri = synth.random_soup(600, seed=5, tri_size=0.3)
+    tex = [synth.random_texture(100, 37, 1), synth.random_texture(17, 129, 2), synth.random_texture(1, 1, 3),
+           synth.random_texture(5, 3, 4)]
+    prims = [Primitive(0, 200, (1, 1, 1, 1), 0, 1, 2), Primitive(200, 200, (0.3, 0.6, 0.9, 0.5), 3, -1, 0),
+             Primitive(400, 200, (1, 1, 1, 1), -1, 2, -1)]
+    s = Scene(tri, prims, tex)
+    s.compute_bboxes(cumulative=True)
+    check(gpu_ctx, s, 200, flags=FLAG_UNCAPPED)
+
+
+def test_multi_primitive_cumulative_bbox(gpu_ctx):
+    a = synth.displaced_sphere(24, 12, seed=1, center=(0, 0, 0))
+    b = synth.displaced_sphere(24, 12, seed=2, center=(3, 1, 0), radius=0.5)
+    c = synth.box((1, 1, 1), origin=(-3, 0, 0)).triangles
+    tri = np.concatenate([a, b, c])
+    prims = [Primitive(0, len(a)), Primitive(len(a), len(b)), Primitive(len(a) + len(b), len(c))]
+    s = Scene(tri, prims, [])
+    s.compute_bboxes(cumulative=True)
+    check(gpu_ctx, s, 128)
+    s.compute_bboxes(cumulative=False)
+    check(gpu_ctx, s, 128)
+
+
+def test_big_triangles_are_deferred_and_split(gpu_ctx):
+    s = synth.unit_quad()
+    s.textures = synth.make_material_textures(128, 21)
+    p = s.primitives[0]
+    p.albedo_texture, p.normal_texture, p.metallic_roughness_texture = 0, 1, 2
+    out = check(gpu_ctx, s, 512, flags=FLAG_UNCAPPED)
+    assert out.total == 512 * 512
+    out = check(gpu_ctx, s, 1024, flags=FLAG_UNCAPPED)
+    assert out.total == 1024 * 1024
+
+
+def test_mixed_big_and_small(gpu_ctx):
+    room = synth.sponza_standin(tex_size=64, n_prims=12, n_materials=3, target_tris=6000)
+    check(gpu_ctx, room, 256, flags=FLAG_UNCAPPED)
+
+
+def test_degenerate_and_empty(gpu_ctx):
+    # zero-area, collinear, NaN and sub-pixel triangles; plus an empty scene
+    t = synth.random_soup(64, seed=9, tri_size=0.5)
+    v = t.reshape(-1, 3, 12)
+    v[0, 1, :3] = v[0, 0, :3]; v[0, 2, :3] = v[0, 0, :3]            # point
+    v[1, 2, :3] = 2 * v[1, 1, :3] - v[1, 0, :3]                      # collinear
+    v[2, 0, 0] = np.nan
+    v[3, :, :3] = v[3, 0, :3] + np.random.default_rng(0).random((3, 3)).astype(np.float32) * 1e-6
+    s = Scene(v.reshape(-1, 36))
+    s.compute_bboxes()
+    s.primitives[0].bbox_min = (0.0, 0.0, 0.0)   # NaN vertex must not poison the box
+    s.primitives[0].bbox_max = (1.5, 1.5, 1.5)
+    check(gpu_ctx, s, 64)
+    empty = Scene(np.zeros((0, 36), np.float32))
+    out = gpu_ctx.convert(gpu_ctx.upload(empty), 64)
+    assert out.total == 0 and out.written == 0
+
+
+def test_capacity_overflow(gpu_ctx):
+    s = synth.unit_quad()
+    ds = gpu_ctx.upload(s)
+    out = gpu_ctx.convert(ds, 64, max_gaussians=1000, want_keys=True)
+    assert out.overflow and out.total == 4096 and out.written == 1000 and out.cap == 1000
+    rec, keys = out.numpy(), out.keys_numpy()
+    assert len(np.unique(keys)) == 1000           # 1000 distinct, valid fragments survive
+    full, fkeys, _ = oracle.convert(s, 64, want_keys=True)
+    lut = {int(k): i for i, k in enumerate(fkeys)}
+    idx = np.array([lut[int(k)] for k in keys])
+    np.testing.assert_allclose(rec["position"], full["position"][idx], atol=1e-6)
+    # reference rule: min(6 R^2 meshCount, 7e6)
+    out = gpu_ctx.convert(ds, 64)
+    assert out.cap == 6 * 64 * 64
+    ds.free()
+
+
+def test_shard_ranges_partition_the_output(gpu_ctx):
+    tri = synth.displaced_sphere(40, 20, seed=8)
+    s = Scene(tri, [Primitive(0, len(tri), (1, 1, 1, 1), 0, -1, -1)], [synth.random_texture(64, 64, 3)])
+    s.compute_bboxes()
+    ds = gpu_ctx.upload(s)
+    whole = gpu_ctx.convert(ds, 128, want_keys=True)
+    parts, n = [], len(tri)
+    cuts = [0, 137, 138, 900, n]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        o = gpu_ctx.convert(ds, 128, first_triangle=a, triangle_count=b - a, want_keys=True)
+        k = o.keys_numpy()
+        assert np.all((k >> np.uint64(24)) >= a) and np.all((k >> np.uint64(24)) < b)
+        rec, keys, total = oracle.convert(s, 128, first_triangle=a, triangle_count=b - a)
+        assert o.total == total
+        assert_records_match(s, LAYOUT_REF96, o.numpy(), k, rec, keys)
+        parts.append(k)
+    assert np.array_equal(np.sort(np.concatenate(parts)), np.sort(whole.keys_numpy()))
+    ds.free()
+
+
+@pytest.mark.parametrize("layout", [LAYOUT_PACKED56, LAYOUT_PLY_STANDARD, LAYOUT_PLY_PBR, LAYOUT_PLY_COMPRESSED])
+def test_other_layouts(gpu_ctx, layout):
+    tri = synth.displaced_sphere(32, 16, seed=4)
+    s = Scene(tri, [Primitive(0, len(tri), (0.9, 1.0, 0.8, 0.9), 0, 1, 2)], synth.make_material_textures(128, 5))
+    s.compute_bboxes()
+    check(gpu_ctx, s, 96, layout, gaussian_std=0.65)
+    check(gpu_ctx, s, 64, layout, gaussian_std=1.3)
+
+
+def test_mip_chain_bit_exact(gpu_ctx):
+    imgs = [synth.random_texture(256, 256, 1), synth.random_texture(100, 37, 2), synth.random_texture(3, 1, 3),
+            synth.random_texture(1, 1, 4), synth.random_texture(33, 64, 5)]
+    s = synth.unit_quad()
+    s.textures = imgs
+    ds = gpu_ctx.upload(s)
+    for t, img in enumerate(imgs):
+        n = oracle.mip_count(img.shape[1], img.shape[0])
+        for l in range(n):
+            assert np.array_equal(ds.read_mip(t, l), oracle.mip_level(img, l)), f"texture {t} level {l}"
+    ds.free()
+
+
+def test_convert_host_matches_resident(gpu_ctx):
+    tri = synth.displaced_sphere(32, 16, seed=6)
+    s = Scene(tri, [Primitive(0, len(tri), (1, 1, 1, 1), 0, 1, 2)], synth.make_material_textures(64, 9))
+    s.compute_bboxes()
+    rec, keys, res = gpu_ctx.convert_host(s, 100, want_keys=True)
+    want, wkeys, total = oracle.convert(s, 100)
+    assert res.total == total
+    assert_records_match(s, LAYOUT_REF96, rec, keys, want, wkeys)
+
+
+def test_repeated_launches_rearm_the_scheduler(gpu_ctx):
+    s = synth.unit_quad()
+    ds = gpu_ctx.upload(s)
+    for R in (64, 700, 32, 64, 513):
+        out = gpu_ctx.convert(ds, R, flags=FLAG_UNCAPPED)
+        assert out.total == R * R
+    ds.free()
+
+
+def test_reference_shaped_interface(tmp_path):
+    from mesh2splat_b200.api import ConversionPass, RenderContext, SceneManager
+    rc = RenderContext(0)
+    sm = SceneManager(rc)
+    s = synth.unit_quad()
+    assert sm.setScene(s)
+    rc.resolutionTarget = 64
+    p = ConversionPass()
+    p.setIsEnabled(True)
+    assert p.isEnabled()
+    p.execute(rc)
+    assert rc.numberOfGaussians == 4096
+    path = tmp_path / "quad.ply"
+    sm.exportPly(str(path), 0)
+    data = path.read_bytes()
+    want_rec, _, _ = oracle.convert(s, 64, want_keys=False)
+    hdr = oracle.ply_header(0, 4096)
+    assert data[: len(hdr)] == hdr and len(data) == len(hdr) + 4096 * 248
+    body = np.frombuffer(data[len(hdr):], np.float32).reshape(4096, 62)
+    np.testing.assert_allclose(body[:, 55], np.log(np.float32(1.0) * np.float32(0.65) / np.float32(64)), rtol=1e-6)
+    assert np.all(np.isposinf(body[:, 54]))  # alpha == 1 -> opacity = +inf (utils.hpp:270)
+    rc.ctx.close()
+
+
+# ---- full-size properties (BASELINE config 2 stand-in) -------------------------------------------------
+def test_helmet_standin_density_512_full_parity(gpu_ctx):
+    s = synth.helmet_standin(1024)
+    out = check(gpu_ctx, s, 512, LAYOUT_REF96)
+    assert 0.4e6 < out.total < 1.2e6
+    out2 = check(gpu_ctx, s, 512, LAYOUT_PACKED56)
+    assert out2.total == out.total

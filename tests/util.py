@@ -1,0 +1,112 @@
+"""Shared helpers for the parity tests: order-independent comparison keyed on fragment identity.
+
+Tolerances (stated once, used everywhere):
+  coverage (which (triangle, pixel) pairs emit a gaussian) ........ bit-exact (integer edge functions)
+  position ........................................................ 1e-5 * bbox diagonal (absolute)
+  raw scale / log-scale, quaternion (same sign convention) ........ 1e-5 relative (+1e-7 abs)
+  colour / SH0 / metallic-roughness ............................... 1e-4 abs vs the oracle's fp32 sampler
+                                                                    (2/255 is the bound vs a real GL driver)
+  normal (TBN path) ............................................... 1e-4 abs
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from mesh2splat_b200 import _abi
+
+POS_TOL_REL_DIAG = 1e-5
+REL_TOL = 1e-5
+COLOR_TOL = 1e-4
+NORMAL_TOL = 1e-4
+
+
+def scene_diag(scene: _abi.Scene) -> float:
+    pos = scene.triangles.reshape(-1, 3, 12)[:, :, :3].reshape(-1, 3)
+    if len(pos) == 0:
+        return 1.0
+    return float(np.linalg.norm(pos.max(axis=0) - pos.min(axis=0))) or 1.0
+
+
+def sort_by_key(rec: np.ndarray, keys: np.ndarray):
+    order = np.argsort(keys, kind="stable")
+    return rec[order], keys[order]
+
+
+def _close(a, b, rtol, atol, what):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    both_nan = np.isnan(a) & np.isnan(b)
+    both_inf = np.isinf(a) & np.isinf(b) & (np.sign(a) == np.sign(b))
+    ok = both_nan | both_inf | (np.abs(a - b) <= atol + rtol * np.abs(b))
+    if not ok.all():
+        bad = np.argwhere(~ok)[0]
+        raise AssertionError(f"{what}: {np.count_nonzero(~ok)} mismatches, first at {tuple(bad)}: "
+                             f"got {a[tuple(bad)]!r} want {b[tuple(bad)]!r}; max abs err "
+                             f"{np.nanmax(np.abs(np.where(np.isfinite(a - b), a - b, 0)))}")
+
+
+def assert_records_match(scene: _abi.Scene, layout: int, got, got_keys, want, want_keys):
+    """Set comparison: same fragment identities (exact), same values (tolerances above)."""
+    assert len(got) == len(want), f"count {len(got)} != {len(want)}"
+    g, gk = sort_by_key(got, np.asarray(got_keys, np.uint64))
+    w, wk = sort_by_key(want, np.asarray(want_keys, np.uint64))
+    assert np.array_equal(gk, wk), "coverage differs (fragment identity sets are not equal)"
+    assert len(np.unique(gk)) == len(gk), "duplicate fragment identities"
+    diag = scene_diag(scene)
+    if layout == _abi.LAYOUT_REF96:
+        _close(g["position"][:, :3], w["position"][:, :3], 0, POS_TOL_REL_DIAG * diag, "position")
+        assert np.all(g["position"][:, 3] == 1.0)
+        _close(g["scale"], w["scale"], REL_TOL, 1e-12, "scale")
+        _close(g["rotation"], w["rotation"], REL_TOL, 1e-6, "rotation")
+        _close(g["color"], w["color"], 0, COLOR_TOL, "color")
+        _close(g["normal"], w["normal"], 0, NORMAL_TOL, "normal")
+        _close(g["pbr"], w["pbr"], 0, COLOR_TOL, "pbr")
+    elif layout == _abi.LAYOUT_PACKED56:
+        _close(g["xyz"], w["xyz"], 0, POS_TOL_REL_DIAG * diag, "xyz")
+        _close(g["rot"], w["rot"], REL_TOL, 1e-6, "rot")
+        _close(g["log_scale"], w["log_scale"], REL_TOL, 1e-5, "log_scale")
+        _close(g["sh0"], w["sh0"], 0, COLOR_TOL / 0.28209479177387814, "sh0")
+        _close(g["opacity"], w["opacity"], 1e-4, 1e-3, "opacity")
+    elif layout in (_abi.LAYOUT_PLY_STANDARD, _abi.LAYOUT_PLY_PBR):
+        _close(g["xyz"], w["xyz"], 0, POS_TOL_REL_DIAG * diag, "xyz")
+        _close(g["normal"], w["normal"], 0, NORMAL_TOL, "normal")
+        _close(g["f_dc"], w["f_dc"], 0, COLOR_TOL / 0.28209479177387814, "f_dc")
+        _close(g["opacity"], w["opacity"], 1e-4, 1e-3, "opacity")
+        _close(g["scale"], w["scale"], REL_TOL, 1e-5, "scale")
+        _close(g["rot"], w["rot"], REL_TOL, 1e-6, "rot")
+        if layout == _abi.LAYOUT_PLY_STANDARD:
+            assert not g["f_rest"].any()
+        else:
+            _close(g["metallic"], w["metallic"], 0, COLOR_TOL, "metallic")
+            _close(g["roughness"], w["roughness"], 0, COLOR_TOL, "roughness")
+    elif layout == _abi.LAYOUT_PLY_COMPRESSED:
+        _close(g["xyz"], w["xyz"], 0, POS_TOL_REL_DIAG * diag, "xyz")
+        _close(g["rot"], w["rot"], REL_TOL, 1e-6, "rot")
+        _close(g["scale"], w["scale"], REL_TOL, 1e-5, "scale")
+        for f in ("rgba", "octa", "roughness", "metallic"):  # u8 quantisation: off by one at rounding boundaries
+            d = np.abs(g[f].astype(np.int32) - w[f].astype(np.int32))
+            assert d.max(initial=0) <= 1, f"{f}: max byte diff {d.max()}"
+            assert np.count_nonzero(d) <= max(4, 0.002 * d.size), f"{f}: too many byte diffs"
+    else:
+        raise ValueError(layout)
+
+
+def png_bytes(img: np.ndarray) -> bytes:
+    """Minimal PNG writer (RGBA8 / RGB8 / gray8, filter 0) for loader tests."""
+    import struct
+    import zlib
+
+    img = np.ascontiguousarray(img, np.uint8)
+    if img.ndim == 2:
+        ctype, ch = 0, 1
+    else:
+        ch = img.shape[2]
+        ctype = {1: 0, 2: 4, 3: 2, 4: 6}[ch]
+    h, w = img.shape[:2]
+    raw = b"".join(b"\x00" + img[y].tobytes() for y in range(h))
+
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xffffffff)
+
+    return (b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, ctype, 0, 0, 0))
+            + chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))
