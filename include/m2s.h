@@ -196,6 +196,8 @@ m2s_status m2s_ply_write(const char* path, const void* h_ref96, uint64_t count, 
 typedef struct m2s_hscene m2s_hscene;
 m2s_status m2s_glb_load(const char* glb_path, int cumulative_bbox, m2s_hscene** out);
 const m2s_scene* m2s_hscene_view(const m2s_hscene* scene);
+/* "<mesh name or 'mesh'>_<counter>" exactly as utils::Mesh::name (SceneManager.cpp:305-307) */
+const char* m2s_hscene_primitive_name(const m2s_hscene* scene, uint32_t primitive);
 void m2s_hscene_free(m2s_hscene* scene);
 
 m2s_status m2s_convert_file(m2s_ctx* ctx, const char* glb_path, uint32_t resolution,

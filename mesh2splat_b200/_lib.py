@@ -18,7 +18,7 @@ SYMBOLS = [
     "m2s_compute_bboxes", "m2s_scene_upload", "m2s_scene_free", "m2s_scene_read_mip",
     "m2s_convert_enqueue", "m2s_convert", "m2s_convert_host",
     "m2s_ply_header", "m2s_ply_encode", "m2s_ply_write", "m2s_convert_file",
-    "m2s_glb_load", "m2s_hscene_view", "m2s_hscene_free",
+    "m2s_glb_load", "m2s_hscene_view", "m2s_hscene_primitive_name", "m2s_hscene_free",
 ]
 
 
@@ -87,6 +87,8 @@ def lib() -> C.CDLL:
     L.m2s_glb_load.argtypes = [C.c_char_p, i32, C.POINTER(vp)]
     L.m2s_hscene_view.restype = C.POINTER(_abi.m2s_scene)
     L.m2s_hscene_view.argtypes = [vp]
+    L.m2s_hscene_primitive_name.restype = C.c_char_p
+    L.m2s_hscene_primitive_name.argtypes = [vp, u32]
     L.m2s_hscene_free.restype = None
     L.m2s_hscene_free.argtypes = [vp]
     _lib = L

@@ -452,6 +452,9 @@ int texture_image(const Glb& g, const JValue* texinfo) {
 
 M2S_EXPORT void m2s_hscene_free(m2s_hscene* s) { delete s; }
 M2S_EXPORT const m2s_scene* m2s_hscene_view(const m2s_hscene* s) { return s ? &s->view : nullptr; }
+M2S_EXPORT const char* m2s_hscene_primitive_name(const m2s_hscene* s, uint32_t i) {
+    return (s && i < s->names.size()) ? s->names[i].c_str() : "";
+}
 
 M2S_EXPORT m2s_status m2s_glb_load(const char* path, int cumulative_bbox, m2s_hscene** out) {
     if (!path || !out) { m2s::set_error("m2s_glb_load: NULL argument"); return M2S_E_INVALID; }

@@ -1,0 +1,99 @@
+#!/usr/bin/env python3
+"""Generates tests/golden/ref_shader_vectors.npz from the REFERENCE's own shaders.
+
+Runs only in the build container (needs /root/reference): oracle/build.py compiles
+src/shaders/conversion/converter{GS,FS}.glsl (unmodified arithmetic, token-level GLSL->C++
+rewrites) against the reference's vendored GLM into oracle/_ref/libm2s_refshader.so; this script
+feeds it seeded inputs and stores inputs + outputs.  The committed .npz is what travels: the tests
+that consume it (CPU: oracle vs golden; GPU: CUDA vs golden) never touch /root/reference.
+
+    python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+import oracle  # noqa: E402
+from oracle import build as obuild  # noqa: E402
+
+
+def gs_inputs(rng, n):
+    tris = np.zeros((n, 36), np.float32)
+    bmin = np.zeros((n, 3), np.float32)
+    bmax = np.zeros((n, 3), np.float32)
+    for i in range(n):
+        kind = i % 8
+        ext = rng.random(3).astype(np.float32) * 4 + 0.5
+        lo = (rng.random(3).astype(np.float32) - 0.5) * 10
+        if kind == 0:    # generic
+            p = lo + rng.random((3, 3)).astype(np.float32) * ext
+        elif kind == 1:  # axis aligned right triangle in a random plane, exact ties likely
+            ax = rng.integers(0, 3)
+            p = np.tile(lo + ext * 0.5, (3, 1)).astype(np.float32)
+            a, b = [k for k in range(3) if k != ax]
+            p[1, a] += 1.0; p[2, a] += 1.0; p[2, b] += 1.0
+        elif kind == 2:  # equilateral-ish: equal edge lengths
+            c = lo + ext * 0.5
+            p = np.stack([c + [1, 0, 0], c + [0, 1, 0], c + [0, 0, 1]]).astype(np.float32)
+        elif kind == 3:  # tiny
+            p = lo + ext * 0.5 + rng.random((3, 3)).astype(np.float32) * 1e-3
+        elif kind == 4:  # 45 degree tilt: |nx| == |ny|
+            c = lo + ext * 0.25
+            p = np.stack([c, c + [1, -1, 0], c + [0, 0, 1]]).astype(np.float32)
+        elif kind == 5:  # degenerate in projection (collinear) -> inverse2x2 returns 0
+            c = lo + ext * 0.25
+            d = rng.random(3).astype(np.float32)
+            p = np.stack([c, c + d, c + 2 * d]).astype(np.float32)
+        elif kind == 6:  # long thin
+            c = lo + ext * 0.1
+            d = rng.random(3).astype(np.float32) * ext * 0.8
+            p = np.stack([c, c + d, c + d * 0.5 + rng.random(3).astype(np.float32) * 1e-2]).astype(np.float32)
+        else:            # unit-quad triangles (SURVEY 8c KAT i)
+            q = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0]], np.float32)
+            p = q[[0, 1, 2]] if (i // 8) % 2 == 0 else q[[0, 2, 3]]
+            lo = np.zeros(3, np.float32); ext = np.array([1, 1, 0], np.float32)
+        v = tris[i].reshape(3, 12)
+        v[:, 0:3] = p
+        v[:, 3:6] = rng.normal(size=(3, 3))
+        v[:, 6:10] = rng.normal(size=(3, 4))
+        v[:, 10:12] = rng.random((3, 2))
+        mn = np.minimum(p.min(axis=0), lo); mx = np.maximum(p.max(axis=0), lo + ext)
+        bmin[i] = mn; bmax[i] = mx
+    return tris, bmin, bmax
+
+
+def main():
+    obuild.build_all()
+    if oracle.ref_lib() is None:
+        raise SystemExit("oracle/_ref is not built (no /root/reference here)")
+    rng = np.random.default_rng(20260922)
+    n = 256
+    tris, bmin, bmax = gs_inputs(rng, n)
+    glpos = np.zeros((n, 3, 4), np.float32); scale = np.zeros((n, 3), np.float32); quat = np.zeros((n, 4), np.float32)
+    for i in range(n):
+        glpos[i], scale[i], quat[i] = oracle.ref_gs(tris[i], bmin[i], bmax[i])
+    m = 256
+    vary = rng.normal(size=(m, 19)).astype(np.float32)
+    vary[:, 9] = np.where(rng.random(m) < 0.5, -1.0, 1.0)  # tangent.w
+    tex = rng.integers(0, 256, size=(m, 3, 4)).astype(np.float32) / np.float32(255.0)
+    flags = rng.integers(0, 8, size=m).astype(np.uint32)
+    factor = rng.random((m, 4)).astype(np.float32)
+    start = rng.integers(0, 1000, size=m).astype(np.uint32)
+    maxg = np.where(rng.random(m) < 0.8, 1 << 20, 500).astype(np.int32)
+    rec = np.zeros((m, 24), np.float32); written = np.zeros(m, np.uint8); after = np.zeros(m, np.uint32)
+    for i in range(m):
+        w, r, c = oracle.ref_fs(vary[i], tex[i, 0], tex[i, 1], tex[i, 2], int(flags[i]), factor[i], int(start[i]), int(maxg[i]))
+        written[i] = w; rec[i] = r; after[i] = c
+    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_shader_vectors.npz")
+    np.savez_compressed(out, gs_tris=tris, gs_bmin=bmin, gs_bmax=bmax, gs_glpos=glpos, gs_scale=scale, gs_quat=quat,
+                        fs_varyings=vary, fs_texels=tex, fs_flags=flags, fs_factor=factor, fs_counter_start=start,
+                        fs_max_gaussians=maxg, fs_rec=rec, fs_written=written, fs_counter_after=after)
+    print("wrote", out, os.path.getsize(out), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,248 @@
+"""CPU tests of the C-ABI library's host side: exports, error behaviour without a GPU, .ply writer
+bytes, bbox rule, .glb loader.  No compute kernels are launched here."""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import re
+import struct
+
+import numpy as np
+import pytest
+
+import oracle
+from mesh2splat_b200 import _abi, _lib, synth
+from mesh2splat_b200._abi import Primitive, Scene
+from util import png_bytes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu() -> bool:
+    h = C.c_void_p(0)
+    st = _lib.lib().m2s_ctx_create(0, C.byref(h))
+    if st == _abi.M2S_OK:
+        _lib.lib().m2s_ctx_destroy(h)
+        return True
+    return False
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "m2s.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(m2s_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    L = C.CDLL(_lib.LIB_PATH)
+    missing = [n for n in sorted(declared) if not hasattr(L, n)]
+    assert not missing, f"libm2s.so does not export {missing}"
+    assert declared == set(_lib.SYMBOLS), f"binding list out of sync: {declared ^ set(_lib.SYMBOLS)}"
+    assert _lib.lib().m2s_version() == 100
+
+
+def test_struct_layouts_match_the_header():
+    # sizes the C compiler gives the structs in include/m2s.h (checked against ctypes mirrors)
+    assert C.sizeof(_abi.m2s_texture) == 16
+    assert C.sizeof(_abi.m2s_primitive) == 72
+    assert C.sizeof(_abi.m2s_scene) == 48
+    assert C.sizeof(_abi.m2s_params) == 40
+    assert C.sizeof(_abi.m2s_result) == 32
+    L = _lib.lib()
+    for layout, stride in _abi.STRIDES.items():
+        assert L.m2s_record_stride(layout) == stride == oracle.lib().orc_record_stride(layout)
+        assert _abi.record_dtype(layout).itemsize == stride
+    assert L.m2s_record_stride(99) == 0
+    assert L.m2s_reference_capacity(64, 1) == 24576
+    assert L.m2s_reference_capacity(64, 0) == 24576
+    assert L.m2s_reference_capacity(1024, 100) == 7_000_000
+    p = _abi.m2s_params()
+    L.m2s_params_default(C.byref(p))
+    assert p.resolution == 520 and abs(p.gaussian_std - 0.65) < 1e-7 and p.layout == 0
+
+
+def test_no_gpu_means_loud_failure_not_cpu_fallback():
+    if _has_gpu():
+        pytest.skip("a CUDA device is present")
+    L = _lib.lib()
+    h = C.c_void_p(0)
+    st = L.m2s_ctx_create(0, C.byref(h))
+    assert st == _abi.M2S_E_NOGPU and not h.value
+    assert b"CUDA" in L.m2s_last_error()
+    from mesh2splat_b200.api import Context
+    with pytest.raises(_lib.M2SError) as e:
+        Context(0)
+    assert e.value.status == _abi.M2S_E_NOGPU
+    # compute entry points reject a NULL context instead of computing anything
+    assert L.m2s_convert(None, None, None, None, 0, None, None) == _abi.M2S_E_INVALID
+
+
+def test_compute_bboxes_matches_reference_rule():
+    a = synth.displaced_sphere(8, 4, seed=1); b = synth.displaced_sphere(8, 4, seed=2, center=(4, 1, -2))
+    s = Scene(np.concatenate([a, b]), [Primitive(0, len(a)), Primitive(len(a), len(b))])
+    for cumulative in (1, 0):
+        s.compute_bboxes(cumulative=bool(cumulative))
+        cs, keep = s.c_struct()
+        prims = (_abi.m2s_primitive * 2)()
+        for i in range(2):
+            prims[i].first_triangle = cs.primitives[i].first_triangle
+            prims[i].triangle_count = cs.primitives[i].triangle_count
+        assert _lib.lib().m2s_compute_bboxes(s.triangles.ctypes.data, prims, 2, cumulative) == 0
+        o = (_abi.m2s_primitive * 2)()
+        for i in range(2):
+            o[i].first_triangle = prims[i].first_triangle; o[i].triangle_count = prims[i].triangle_count
+        oracle.lib().orc_compute_bboxes(s.triangles.ctypes.data, o, 2, cumulative)
+        for i in range(2):
+            assert tuple(prims[i].bbox_min) == s.primitives[i].bbox_min == tuple(o[i].bbox_min)
+            assert tuple(prims[i].bbox_max) == s.primitives[i].bbox_max == tuple(o[i].bbox_max)
+
+
+@pytest.mark.parametrize("fmt", [0, 1, 2, 7])
+def test_ply_writer_is_byte_identical_to_the_restated_savePlyVector(tmp_path, fmt):
+    from mesh2splat_b200.api import ply_header, ply_write
+    tri = synth.displaced_sphere(16, 8, seed=3)
+    s = Scene(tri, [Primitive(0, len(tri), (0.9, 0.7, 0.8, 0.9), 0, 1, 2)], synth.make_material_textures(32, 2))
+    s.compute_bboxes()
+    rec, _, _ = oracle.convert(s, 48, want_keys=False)
+    assert len(rec) > 500
+    mult = float(np.float32(0.65) / np.float32(48))
+    path = tmp_path / f"out{fmt}.ply"
+    ply_write(str(path), rec, fmt, mult)
+    eff = fmt if fmt <= 2 else 0     # default branch of savePlyVector (parsers.cpp:646-648)
+    want = oracle.ply_bytes(rec, eff, mult)
+    got = path.read_bytes()
+    assert ply_header(eff, len(rec)) == oracle.ply_header(eff, len(rec))
+    assert got[:200] == want[:200]
+    assert got == want
+    hdr = want[: want.index(b"end_header\n") + 11].decode()
+    assert hdr.startswith("ply\nformat binary_little_endian 1.0\nelement vertex %d\n" % len(rec))
+    assert (len(want) - len(hdr)) == len(rec) * {0: 248, 1: 76, 2: 48}[eff]
+    assert hdr.count("property") == {0: 62, 1: 19, 2: 18}[eff]
+
+
+# ---- .glb loader ------------------------------------------------------------------------------------
+def _make_glb(path, *, indexed=True, with_normals=True, with_tangents=True, with_uv=True, with_texture=True,
+              matrix=None, trs=None, two_prims=False):
+    rng = np.random.default_rng(5)
+    pos = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0.5]], np.float32)
+    nrm = np.tile(np.array([0, 0, 1], np.float32), (4, 1))
+    tan = np.tile(np.array([1, 0, 0, -1], np.float32), (4, 1))
+    uv = pos[:, :2].copy()
+    idx = np.array([0, 1, 2, 0, 2, 3], np.uint16)
+    img = rng.integers(0, 256, size=(5, 7, 4), dtype=np.uint8)
+    img_rgb = rng.integers(0, 256, size=(4, 4, 3), dtype=np.uint8)
+    blobs, views, accessors = [], [], []
+
+    def add_view(b):
+        off = sum(len(x) for x in blobs)
+        pad = (-len(b)) % 4
+        blobs.append(b + b"\x00" * pad)
+        views.append({"buffer": 0, "byteOffset": off, "byteLength": len(b)})
+        return len(views) - 1
+
+    def add_acc(arr, ctype, typ):
+        v = add_view(arr.tobytes())
+        accessors.append({"bufferView": v, "componentType": ctype, "count": len(arr), "type": typ})
+        return len(accessors) - 1
+
+    if not indexed:
+        pos_, nrm_, tan_, uv_ = pos[idx], nrm[idx], tan[idx], uv[idx]
+    else:
+        pos_, nrm_, tan_, uv_ = pos, nrm, tan, uv
+    attrs = {"POSITION": add_acc(pos_, 5126, "VEC3")}
+    if with_normals: attrs["NORMAL"] = add_acc(nrm_, 5126, "VEC3")
+    if with_tangents: attrs["TANGENT"] = add_acc(tan_, 5126, "VEC4")
+    if with_uv: attrs["TEXCOORD_0"] = add_acc(uv_, 5126, "VEC2")
+    prim = {"attributes": attrs, "material": 0}
+    if indexed: prim["indices"] = add_acc(idx, 5123, "SCALAR")
+    prims = [prim]
+    if two_prims:
+        prims.append({"attributes": {"POSITION": add_acc(pos_ + np.float32(3.0), 5126, "VEC3")}, "mode": 4})
+        prims.append({"attributes": {"POSITION": attrs["POSITION"]}, "mode": 1})   # lines: skipped
+    gltf = {"asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0]}],
+            "nodes": [{"children": [1], "name": "root"}, {"mesh": 0}],
+            "meshes": [{"name": "quad", "primitives": prims}],
+            "materials": [{"pbrMetallicRoughness": {"baseColorFactor": [0.5, 0.6, 0.7, 0.8]}}]}
+    if matrix is not None: gltf["nodes"][0]["matrix"] = [float(x) for x in np.asarray(matrix, np.float32).T.reshape(-1)]
+    if trs is not None:
+        gltf["nodes"][1].update({"translation": trs[0], "rotation": trs[1], "scale": trs[2]})
+    if with_texture:
+        iv = add_view(png_bytes(img)); iv2 = add_view(png_bytes(img_rgb))
+        gltf["images"] = [{"bufferView": iv, "mimeType": "image/png"}, {"bufferView": iv2, "mimeType": "image/png"}]
+        gltf["textures"] = [{"source": 0}, {"source": 1}]
+        gltf["materials"][0]["pbrMetallicRoughness"]["baseColorTexture"] = {"index": 0}
+        gltf["materials"][0]["pbrMetallicRoughness"]["metallicRoughnessTexture"] = {"index": 1}
+        gltf["materials"][0]["normalTexture"] = {"index": 0, "scale": 2.0}
+    gltf["bufferViews"] = views; gltf["accessors"] = accessors
+    binblob = b"".join(blobs)
+    gltf["buffers"] = [{"byteLength": len(binblob)}]
+    js = json.dumps(gltf).encode()
+    js += b" " * ((-len(js)) % 4)
+    total = 12 + 8 + len(js) + 8 + len(binblob)
+    with open(path, "wb") as f:
+        f.write(struct.pack("<4sII", b"glTF", 2, total))
+        f.write(struct.pack("<I4s", len(js), b"JSON")); f.write(js)
+        f.write(struct.pack("<I4s", len(binblob), b"BIN\x00")); f.write(binblob)
+    return dict(pos=pos, nrm=nrm, tan=tan, uv=uv, idx=idx, img=img, img_rgb=img_rgb)
+
+
+def test_glb_loader_basic(tmp_path):
+    from mesh2splat_b200.gltf import load_glb
+    p = tmp_path / "a.glb"
+    src = _make_glb(str(p))
+    s = load_glb(str(p))
+    assert s.triangle_count == 2 and len(s.primitives) == 1 and s.primitives[0].name == "quad_0"
+    v = s.triangles.reshape(2, 3, 12)
+    tri_idx = src["idx"].reshape(2, 3)
+    assert np.array_equal(v[:, :, 0:3], src["pos"][tri_idx])
+    assert np.array_equal(v[:, :, 3:6], src["nrm"][tri_idx])
+    assert np.array_equal(v[:, :, 6:10], src["tan"][tri_idx])
+    assert np.array_equal(v[:, :, 10:12], src["uv"][tri_idx])
+    pr = s.primitives[0]
+    np.testing.assert_allclose(pr.base_color_factor, (0.5, 0.6, 0.7, 0.8), rtol=1e-6)
+    assert pr.albedo_texture == 0 and pr.normal_texture == 0 and pr.metallic_roughness_texture == 1  # images shared
+    assert np.array_equal(s.textures[0], src["img"])
+    assert np.array_equal(s.textures[1][..., :3], src["img_rgb"]) and np.all(s.textures[1][..., 3] == 255)
+    assert pr.bbox_min == (0.0, 0.0, 0.0) and pr.bbox_max == (1.0, 1.0, 0.5)
+
+
+def test_glb_loader_fallbacks_and_transforms(tmp_path):
+    from mesh2splat_b200.gltf import load_glb
+    p = tmp_path / "b.glb"
+    M = np.eye(4, dtype=np.float32); M[:3, :3] = np.diag([2.0, 1.0, 0.5]); M[:3, 3] = (1, 2, 3)
+    src = _make_glb(str(p), indexed=False, with_normals=False, with_tangents=False, with_texture=False, matrix=M,
+                    trs=([0.5, 0.0, 0.0], [0.0, 0.0, 0.70710678, 0.70710678], [1.0, 1.0, 2.0]), two_prims=True)
+    s = load_glb(str(p))
+    assert [q.name for q in s.primitives] == ["quad_0", "quad_1"]     # the LINES primitive is skipped, no counter bump
+    assert s.triangle_count == 4
+    # world = M * (T R S)
+    c = 0.70710678
+    R = np.array([[0, -1, 0], [1, 0, 0], [0, 0, 1]], np.float32)       # 90 deg about z
+    L = np.eye(4, dtype=np.float32); L[:3, :3] = R @ np.diag([1, 1, 2]).astype(np.float32); L[:3, 3] = (0.5, 0, 0)
+    W = M @ L
+    pos = src["pos"][src["idx"]]
+    want = (np.c_[pos, np.ones(len(pos))] @ W.T)[:, :3].reshape(2, 3, 3)
+    v = s.triangles.reshape(4, 3, 12)
+    np.testing.assert_allclose(v[:2, :, 0:3], want, rtol=1e-5, atol=1e-6)
+    for t in range(2):                                                 # flat face normal (SceneManager.cpp:406-413)
+        fn = np.cross(want[t, 1] - want[t, 0], want[t, 2] - want[t, 0]); fn /= np.linalg.norm(fn)
+        np.testing.assert_allclose(v[t, :, 3:6], np.tile(fn, (3, 1)), atol=1e-5)
+        assert abs(np.linalg.norm(v[t, 0, 6:9]) - 1) < 1e-5 and abs(v[t, 0, 9]) == 1.0   # per-face tangent + handedness
+    assert np.all(v[2:, :, 10:12] == 0)                                # no TEXCOORD_0 -> zeros
+    # cumulative bbox: primitive 1 includes primitive 0's extent
+    assert s.primitives[1].bbox_min[0] <= s.primitives[0].bbox_min[0]
+    assert s.primitives[1].albedo_texture == -1
+
+
+def test_glb_loader_errors(tmp_path):
+    from mesh2splat_b200.gltf import load_glb
+    with pytest.raises(OSError):
+        load_glb(str(tmp_path / "missing.glb"))
+    bad = tmp_path / "bad.glb"
+    bad.write_bytes(b"not a glb at all, definitely")
+    with pytest.raises(ValueError):
+        load_glb(str(bad))
+    from mesh2splat_b200.api import SceneManager
+
+    class _RC:  # loadModel prints and returns False on failure, like the reference (SceneManager.cpp:24-27)
+        deviceScene = None
+    assert SceneManager(_RC()).loadModel(str(bad)) is False
