@@ -1,0 +1,328 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark of the conversion path (contract in the task statement).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" = one ConversionPass::execute over the workload: BASELINE.json configs[1] — the
+SciFiHelmet stand-in (seeded displaced sphere, 70 074 triangles, 3 x 2048^2 RGBA8 maps; the Khronos
+asset is not available offline) at density 512.  Metric: Mgaussians/s.
+
+  value      device-resident: scene already in HBM, CUDA events around the convert launch only,
+             L2 flushed (256 MiB memset) before every timed step
+  e2e        same metric through m2s_convert_host (the C-ABI call with HOST buffers): pinned
+             triangle+texture upload, GPU mip generation, convert, download of the records
+  roofline   algorithmic bytes (N*B_out + T*144 + sum_maps min(4N, 4WH)) / kernel time
+             against the MEASURED HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline / --impl reference
+             the CPU restatement (oracle/, OpenMP, all host cores) on the same workload — the
+             reference itself is an OpenGL 4.6 + Win32 GUI program and cannot be built or run here
+             (no GL driver / Mesa on the box), so kind = "port".
+N > 1 (torchrun): the triangle list is sharded into N contiguous ranges, one per rank/GPU; per-rank
+gaussian buffers are concatenated on every rank with an NCCL all-gather (counts, then max-padded
+payload) — total work is fixed, so scaling = "strong".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from mesh2splat_b200 import _abi, synth  # noqa: E402
+
+DENSITY = 512
+WORKLOAD = "helmet_standin"  # BASELINE.json configs[1] (SciFiHelmet.glb stand-in)
+METRIC = "Mgaussians/s at density 512"
+UNIT = "Mgaussians/s"
+LAYOUTS = {"packed56": _abi.LAYOUT_PACKED56, "ref96": _abi.LAYOUT_REF96}
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def algorithmic_bytes(scene, n_gaussians: int, layout: int, n_triangles: int | None = None) -> int:
+    """SURVEY 8(d) / BASELINE.md: N*B_out + T*144 + sum over maps the layout consumes of min(4N, 4WH)."""
+    t = scene.triangle_count if n_triangles is None else n_triangles
+    maps = set()
+    for p in scene.primitives:
+        ids = [p.albedo_texture] if layout == _abi.LAYOUT_PACKED56 else \
+            [p.albedo_texture, p.normal_texture, p.metallic_roughness_texture]
+        maps.update(i for i in ids if i >= 0)
+    tex = sum(min(4 * n_gaussians, scene.textures[i].nbytes) for i in maps)
+    return n_gaussians * _abi.STRIDES[layout] + t * 144 + tex
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:  # noqa: BLE001
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def profiled_traffic(layout_name: str):
+    """dram bytes per launch from the committed ncu capture, if there is one for this layout."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(layout_name)
+    except Exception:  # noqa: BLE001
+        return None
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:  # noqa: BLE001
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def pinned_scene(scene, torch):
+    """Copies the scene's arrays into pinned host memory (what a caller doing H2D every step would hold)."""
+    keep = []
+
+    def pin(a):
+        t = torch.empty(a.nbytes, dtype=torch.uint8).pin_memory()
+        v = t.numpy().view(a.dtype).reshape(a.shape)
+        v[...] = a
+        keep.append(t)
+        return v
+
+    s = _abi.Scene.__new__(_abi.Scene)
+    s.triangles = pin(scene.triangles)
+    s.primitives = scene.primitives
+    s.textures = [pin(t) for t in scene.textures]
+    return s, keep
+
+
+# ---------------------------------------------------------------------------------------------
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path, all host cores, same workload/config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    scene = synth.helmet_standin(2048)
+    layout = LAYOUTS[args.layout]
+    prep = oracle.Prepared(scene)
+    cores = oracle.max_threads()
+    out = None
+    for _ in range(max(1, min(args.warmup, 2))):
+        n, total, out = prep.convert(DENSITY, layout, out=out)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        n, total, out = prep.convert(DENSITY, layout, out=out)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = n / dt / 1e6
+    sample = f"full workload ({scene.triangle_count} triangles -> {n} gaussians) per step, {args.steps} steps"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "density": DENSITY, "layout": args.layout, "triangles": scene.triangle_count,
+                       "gaussians": n, "textures": "3x2048^2 RGBA8"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "note": "CPU restatement of the reference shaders + GL-spec raster/sampler (oracle/), OpenMP; "
+                                     "the reference's OpenGL path cannot run here (no GL driver/Mesa, Win32-only build)"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from mesh2splat_b200.api import Context
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    layout = LAYOUTS[args.layout]
+    stride = _abi.STRIDES[layout]
+    scene = synth.helmet_standin(2048)
+    ctx = Context(local)
+    ds = ctx.upload(scene)
+    T = scene.triangle_count
+    # shard: contiguous, equal triangle counts (the stand-in's triangles are uniform in size)
+    lo = (T * rank) // world
+    hi = (T * (rank + 1)) // world
+    cap_total = 6 * DENSITY * DENSITY
+    stream = torch.cuda.current_stream(dev)
+    params = _abi.make_params(DENSITY, layout, 0.65, 0, _abi.FLAG_UNCAPPED, lo, hi - lo)
+    out = torch.empty(cap_total * stride, dtype=torch.uint8, device=dev)
+    d_total = torch.zeros(1, dtype=torch.int64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    gathered = torch.empty(world * cap_total * stride, dtype=torch.uint8, device=dev) if world > 1 else None
+    counts = torch.zeros(world, dtype=torch.int64, device=dev) if world > 1 else None
+    final = torch.empty(cap_total * stride, dtype=torch.uint8, device=dev) if world > 1 else None
+
+    def step(timed_events=None):
+        flush.zero_()  # evict L2 (126 MB) — untimed
+        if timed_events is not None:
+            timed_events[0].record(stream)
+        ctx.convert_enqueue(ds, params, out, cap_total, None, d_total, stream.cuda_stream)
+        n_total = None
+        if world > 1:  # concatenate per-rank buffers on every rank: counts, then max-padded payload
+            dist.all_gather_into_tensor(counts, d_total)
+            c = counts.cpu()
+            mx = int(c.max())
+            dist.all_gather_into_tensor(gathered[: world * mx * stride], out[: mx * stride])
+            off = 0
+            for r in range(world):
+                nr = int(c[r])
+                final[off * stride:(off + nr) * stride].copy_(gathered[r * mx * stride: r * mx * stride + nr * stride])
+                off += nr
+            n_total = off
+        if timed_events is not None:
+            timed_events[1].record(stream)
+        return n_total
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    clocks = ClockSampler(local) if rank == 0 else None
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    n_total = None
+    for k in range(args.steps):
+        n_total = step(evs[k])
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+    n_local = int(d_total.item())
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        n_all = int(n_total)
+    else:
+        n_all = n_local
+    clk = clocks.stop() if clocks else None
+
+    line = None
+    if rank == 0:
+        value = n_all / (ms * 1e-3) / 1e6
+        # ---- e2e through the C-ABI host-buffer call (this rank's GPU; N=1 semantics) ----
+        pscene, keep = pinned_scene(scene, torch)
+        cs = pscene.c_struct()
+        h_out = torch.empty(cap_total * stride, dtype=torch.uint8).pin_memory()
+        h_np = h_out.numpy()
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            rec, _, res = ctx.convert_host(pscene, DENSITY, layout, flags=_abi.FLAG_UNCAPPED, capacity=cap_total, out=h_np, c_scene=cs)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            rec, _, res = ctx.convert_host(pscene, DENSITY, layout, flags=_abi.FLAG_UNCAPPED, capacity=cap_total, out=h_np, c_scene=cs)
+        torch.cuda.synchronize(dev)
+        e2e_dt = (time.perf_counter() - t0) / e2e_steps
+        h2d = scene.triangles.nbytes + scene.texture_bytes()
+        d2h = int(res.written) * stride + 8
+        e2e = {"value": int(res.written) / e2e_dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": e2e_dt * 1e3, "api": "m2s_convert_host (pinned host buffers; upload + mip generation + convert + download)"}
+        # ---- roofline of the conversion kernel (the step IS one launch at N=1) ----
+        peak, peak_src = measured_peak()
+        kernel_ms = ms
+        if world > 1:  # kernel-only time of rank 0's shard
+            ke = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+            for a, b in ke:
+                flush.zero_(); a.record(stream)
+                ctx.convert_enqueue(ds, params, out, cap_total, None, d_total, stream.cuda_stream)
+                b.record(stream)
+            torch.cuda.synchronize(dev)
+            kernel_ms = float(np.median([a.elapsed_time(b) for a, b in ke]))
+        alg = algorithmic_bytes(scene, n_local, layout, hi - lo)
+        achieved = alg / (kernel_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "m2s::convert_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": profiled_traffic(args.layout), "algorithmic_bytes": alg,
+                    "kernel_ms": kernel_ms, "peak_source": peak_src}
+        # ---- CPU baseline on a bounded sample (the whole workload, a few repeats) ----
+        import oracle
+        prep = oracle.Prepared(scene)
+        o = None
+        n, _, o = prep.convert(DENSITY, layout, out=o)
+        reps = 3
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            n, _, o = prep.convert(DENSITY, layout, out=o)
+        cdt = (time.perf_counter() - t0) / reps
+        cpu = {"value": n / cdt / 1e6, "unit": UNIT, "cores": oracle.max_threads(), "kind": "port",
+               "sample": f"full workload x{reps} ({scene.triangle_count} triangles -> {n} gaussians each)"}
+        launches = args.steps  # one convert_kernel launch per timed step (+0 memsets: the kernel re-arms its own scheduler)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "density": DENSITY, "layout": args.layout, "record_bytes": stride,
+                           "triangles": T, "gaussians": n_all, "textures": "3x2048^2 RGBA8 (+mips 1..4)",
+                           "l2": "flushed between iterations (256 MiB memset, untimed)",
+                           "parallelism": f"triangle shards x{world}" + (" + NCCL all-gather (counts, padded payload)" if world > 1 else "")},
+                "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ds.free()
+    ctx.close()
+    if line is not None:
+        print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--layout", default="packed56", choices=sorted(LAYOUTS))
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -41,6 +41,13 @@ def lib() -> C.CDLL:
         _lib.orc_convert.restype = C.c_uint64
         _lib.orc_convert.argtypes = [C.POINTER(_abi.m2s_scene), C.POINTER(_abi.m2s_params), C.c_void_p,
                                      C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64), C.c_int]
+        _lib.orc_prepare.restype = C.c_void_p
+        _lib.orc_prepare.argtypes = [C.POINTER(_abi.m2s_scene)]
+        _lib.orc_release.restype = None
+        _lib.orc_release.argtypes = [C.c_void_p]
+        _lib.orc_convert_prepared.restype = C.c_uint64
+        _lib.orc_convert_prepared.argtypes = [C.POINTER(_abi.m2s_scene), C.c_void_p, C.POINTER(_abi.m2s_params), C.c_void_p,
+                                              C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64), C.c_int]
         _lib.orc_triangle_setup.restype = C.c_int
         _lib.orc_triangle_setup.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(orc_setup)]
         _lib.orc_mip_level.restype = C.c_int
@@ -103,6 +110,42 @@ def convert(scene: _abi.Scene, resolution: int, layout: int = _abi.LAYOUT_REF96,
     del keep
     rec = out[: n * stride].view(_abi.record_dtype(layout))
     return rec, (keys[:n] if want_keys else None), int(total.value)
+
+
+class Prepared:
+    """Scene with its mip chains built once; convert() can then be timed like the reference's
+    steady-state ConversionPass::execute (mesh + textures already resident)."""
+
+    def __init__(self, scene: _abi.Scene):
+        self.scene = scene
+        self.cs, self._keep = scene.c_struct()
+        self.handle = lib().orc_prepare(C.byref(self.cs))
+
+    def convert(self, resolution: int, layout: int = _abi.LAYOUT_REF96, gaussian_std: float = 0.65, max_gaussians: int = 0,
+                flags: int = 0, capacity: int | None = None, out: np.ndarray | None = None, threads: int = 0):
+        p = _abi.make_params(resolution, layout, gaussian_std, max_gaussians, flags)
+        if capacity is None:
+            capacity = max_gaussians or (_abi.reference_capacity(resolution, len(self.scene.primitives))
+                                         if not (flags & _abi.FLAG_UNCAPPED)
+                                         else 6 * resolution * resolution * max(1, len(self.scene.primitives)))
+        stride = _abi.STRIDES[layout]
+        if out is None:
+            out = np.empty(capacity * stride, np.uint8)
+        total = C.c_uint64(0)
+        n = lib().orc_convert_prepared(C.byref(self.cs), self.handle, C.byref(p), out.ctypes.data, capacity, None,
+                                       C.byref(total), threads)
+        return int(n), int(total.value), out
+
+    def close(self):
+        if self.handle:
+            lib().orc_release(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
 
 
 def triangle_setup(tri36: np.ndarray, bmin, bmax, resolution: int) -> orc_setup:

@@ -497,8 +497,24 @@ static uint64_t count_fragments(const orc_setup* s) {
 
 /* Converts params->{first_triangle, triangle_count} of the scene. Output order is deterministic:
  * triangle-major, then row-major (y, x).  Returns written records; *total = all fragments. */
-ORC_API uint64_t orc_convert(const m2s_scene* sc, const m2s_params* pr, void* out, uint64_t out_capacity,
-                             uint64_t* keys, uint64_t* total_out, int threads) {
+/* mip chains built once per scene (the reference builds them at load time, glUtils.cpp:305) */
+typedef struct orc_prepared { orc_tex* tex; uint32_t ntex; } orc_prepared;
+
+ORC_API orc_prepared* orc_prepare(const m2s_scene* sc) {
+    orc_prepared* p = (orc_prepared*)calloc(1, sizeof(orc_prepared));
+    p->ntex = sc->texture_count;
+    p->tex = (orc_tex*)calloc(sc->texture_count ? sc->texture_count : 1, sizeof(orc_tex));
+    for (uint32_t i = 0; i < sc->texture_count; ++i) orc_tex_build(&p->tex[i], &sc->textures[i]);
+    return p;
+}
+ORC_API void orc_release(orc_prepared* p) {
+    if (!p) return;
+    for (uint32_t i = 0; i < p->ntex; ++i) orc_tex_free(&p->tex[i]);
+    free(p->tex); free(p);
+}
+
+ORC_API uint64_t orc_convert_prepared(const m2s_scene* sc, const orc_prepared* prep, const m2s_params* pr, void* out,
+                                      uint64_t out_capacity, uint64_t* keys, uint64_t* total_out, int threads) {
     const uint32_t R = pr->resolution;
     const uint32_t stride = orc_record_stride(pr->layout);
     uint64_t first = pr->first_triangle, cnt = pr->triangle_count;
@@ -520,8 +536,7 @@ ORC_API uint64_t orc_convert(const m2s_scene* sc, const m2s_params* pr, void* ou
 #else
     (void)threads;
 #endif
-    orc_tex* tex = (orc_tex*)calloc(sc->texture_count ? sc->texture_count : 1, sizeof(orc_tex));
-    for (uint32_t i = 0; i < sc->texture_count; ++i) orc_tex_build(&tex[i], &sc->textures[i]);
+    const orc_tex* tex = prep->tex;
 
     /* triangle -> primitive */
     uint32_t* prim_of = (uint32_t*)malloc(sizeof(uint32_t) * (cnt ? cnt : 1));
@@ -590,10 +605,17 @@ ORC_API uint64_t orc_convert(const m2s_scene* sc, const m2s_params* pr, void* ou
                 if (keys) keys[my] = ((first + (uint64_t)t) << 24) | ((uint64_t)j << 12) | (uint64_t)i;
             }
     }
-    for (uint32_t i = 0; i < sc->texture_count; ++i) orc_tex_free(&tex[i]);
-    free(tex); free(prim_of); free(offs); free(tc);
+    free(prim_of); free(offs); free(tc);
     if (total_out) *total_out = total;
     return total < cap ? total : cap;
+}
+
+ORC_API uint64_t orc_convert(const m2s_scene* sc, const m2s_params* pr, void* out, uint64_t out_capacity,
+                             uint64_t* keys, uint64_t* total_out, int threads) {
+    orc_prepared* p = orc_prepare(sc);
+    const uint64_t n = orc_convert_prepared(sc, p, pr, out, out_capacity, keys, total_out, threads);
+    orc_release(p);
+    return n;
 }
 
 /* single texture fetch, for sampler unit tests */
