@@ -186,7 +186,9 @@ def run_ours(args):
     lo = (T * rank) // world
     hi = (T * (rank + 1)) // world
     cap_total = 6 * DENSITY * DENSITY
-    stream = torch.cuda.current_stream(dev)
+    # a dedicated (non-default) stream: everything timed is enqueued on it and the events are recorded on it
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
     params = _abi.make_params(DENSITY, layout, 0.65, 0, _abi.FLAG_UNCAPPED, lo, hi - lo)
     out = torch.empty(cap_total * stride, dtype=torch.uint8, device=dev)
     d_total = torch.zeros(1, dtype=torch.int64, device=dev)

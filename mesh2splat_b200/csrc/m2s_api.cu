@@ -13,6 +13,7 @@
 
 namespace m2s {
 size_t convert_smem_bytes(int layout);
+int convert_warps_per_cta(int layout);
 cudaError_t convert_configure(int layout, int* blocks_per_sm);
 cudaError_t convert_launch(int layout, const ConvertArgs& args, int grid, cudaStream_t stream);
 cudaError_t mip_down_launch(const uint32_t* src, uint32_t sw, uint32_t sh, uint32_t* dst, uint32_t dw, uint32_t dh,
@@ -63,6 +64,7 @@ struct m2s_dscene {
     DPrim* d_prims = nullptr;
     uint32_t nprims = 0;
     DTexture* d_texs = nullptr;
+    uint32_t* d_arena = nullptr;  // all mip chains of all textures
     uint32_t ntex = 0;
     std::vector<DTexture> h_texs;
     std::vector<void*> allocs;
@@ -213,7 +215,7 @@ M2S_EXPORT m2s_status m2s_scene_upload(m2s_ctx* ctx, const m2s_scene* sc, m2s_ds
     if (!ctx || !sc || !out) { set_error("m2s_scene_upload: NULL argument"); return M2S_E_INVALID; }
     *out = nullptr;
     if (sc->triangle_count && !sc->triangles) { set_error("m2s_scene_upload: triangles is NULL"); return M2S_E_INVALID; }
-    if (sc->triangle_count >= (1ull << 32) - kBatch) { set_error("m2s_scene_upload: too many triangles (< 2^32 supported)"); return M2S_E_INVALID; }
+    if (sc->triangle_count >= (1ull << 32) - 64) { set_error("m2s_scene_upload: too many triangles (< 2^32 supported)"); return M2S_E_INVALID; }
     if ((sc->primitive_count && !sc->primitives) || (sc->texture_count && !sc->textures)) {
         set_error("m2s_scene_upload: primitive/texture table is NULL"); return M2S_E_INVALID;
     }
@@ -273,29 +275,33 @@ M2S_EXPORT m2s_status m2s_scene_upload(m2s_ctx* ctx, const m2s_scene* sc, m2s_ds
     UP_TRY(dalloc((void**)&d->d_prims, prims.size() * sizeof(DPrim)));
     if (!prims.empty())
         UP_TRY(cudaMemcpyAsync(d->d_prims, prims.data(), prims.size() * sizeof(DPrim), cudaMemcpyHostToDevice, ctx->stream));
-    // textures: one allocation per texture holding all levels; levels 1.. built on the GPU
+    // textures: ONE arena for all mip chains (levels addressed by 32-bit texel offsets); levels 1..
+    // are built on the GPU
     d->ntex = sc->texture_count;
     d->h_texs.resize(sc->texture_count);
+    size_t arena_texels = 64;
     for (uint32_t t = 0; t < sc->texture_count; ++t) {
         DTexture& dt = d->h_texs[t];
         std::memset(&dt, 0, sizeof(dt));
         dt.nlevels = mip_levels(sc->textures[t].width, sc->textures[t].height);
-        size_t texels = 0;
         uint32_t w = sc->textures[t].width, h = sc->textures[t].height;
-        size_t off[kMaxLevels];
-        for (uint32_t l = 0; l < dt.nlevels; ++l) {
-            dt.w[l] = w; dt.h[l] = h; off[l] = texels;
-            texels += (size_t)w * h;
-            texels = (texels + 63) & ~(size_t)63;  // 256-byte aligned levels
-            w = std::max(1u, w / 2); h = std::max(1u, h / 2);
+        for (uint32_t l = 0; l < (uint32_t)kMaxLevels; ++l) {
+            if (l < dt.nlevels) {
+                dt.w[l] = (uint16_t)w; dt.h[l] = (uint16_t)h;
+                if (arena_texels + (size_t)w * h >= (1ull << 32)) { set_error("m2s_scene_upload: textures exceed the 16 GiB arena"); return fail(M2S_E_INVALID); }
+                dt.off[l] = (uint32_t)arena_texels;
+                arena_texels += (size_t)w * h;
+                arena_texels = (arena_texels + 63) & ~(size_t)63;  // 256-byte aligned levels
+                w = std::max(1u, w / 2); h = std::max(1u, h / 2);
+            } else { dt.w[l] = dt.w[dt.nlevels - 1]; dt.h[l] = dt.h[dt.nlevels - 1]; dt.off[l] = dt.off[dt.nlevels - 1]; }
         }
-        uint32_t* base = nullptr;
-        UP_TRY(dalloc((void**)&base, texels * 4));
-        for (uint32_t l = 0; l < dt.nlevels; ++l) dt.level[l] = base + off[l];
-        for (uint32_t l = dt.nlevels; l < kMaxLevels; ++l) { dt.level[l] = dt.level[dt.nlevels - 1]; dt.w[l] = dt.w[dt.nlevels - 1]; dt.h[l] = dt.h[dt.nlevels - 1]; }
-        UP_TRY(cudaMemcpyAsync(base, sc->textures[t].rgba, (size_t)dt.w[0] * dt.h[0] * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    UP_TRY(dalloc((void**)&d->d_arena, arena_texels * 4));
+    for (uint32_t t = 0; t < sc->texture_count; ++t) {
+        const DTexture& dt = d->h_texs[t];
+        UP_TRY(cudaMemcpyAsync(d->d_arena + dt.off[0], sc->textures[t].rgba, (size_t)dt.w[0] * dt.h[0] * 4, cudaMemcpyHostToDevice, ctx->stream));
         for (uint32_t l = 1; l < dt.nlevels; ++l)
-            UP_TRY(mip_down_launch(dt.level[l - 1], dt.w[l - 1], dt.h[l - 1], const_cast<uint32_t*>(dt.level[l]), dt.w[l], dt.h[l], ctx->stream));
+            UP_TRY(mip_down_launch(d->d_arena + dt.off[l - 1], dt.w[l - 1], dt.h[l - 1], d->d_arena + dt.off[l], dt.w[l], dt.h[l], ctx->stream));
     }
     UP_TRY(dalloc((void**)&d->d_texs, d->h_texs.size() * sizeof(DTexture)));
     if (!d->h_texs.empty())
@@ -312,7 +318,7 @@ M2S_EXPORT m2s_status m2s_scene_read_mip(m2s_ctx* ctx, const m2s_dscene* s, uint
     if (texture >= s->ntex || level >= s->h_texs[texture].nlevels) { set_error("m2s_scene_read_mip: out of range"); return M2S_E_INVALID; }
     const DTexture& t = s->h_texs[texture];
     CUDA_TRY(cudaSetDevice(ctx->device));
-    CUDA_TRY(cudaMemcpyAsync(dst, t.level[level], (size_t)t.w[level] * t.h[level] * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(dst, s->d_arena + t.off[level], (size_t)t.w[level] * t.h[level] * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     if (width) *width = t.w[level];
     if (height) *height = t.h[level];
@@ -358,7 +364,7 @@ M2S_EXPORT m2s_status m2s_convert_enqueue(m2s_ctx* ctx, const m2s_dscene* s, con
     a.tri_first = (uint32_t)first;
     a.tri_count = (uint32_t)count;
     a.ranges = s->d_ranges; a.nranges = s->nranges;
-    a.prims = s->d_prims; a.texs = s->d_texs; a.ntex = s->ntex;
+    a.prims = s->d_prims; a.texs = s->d_texs; a.tex_base = s->d_arena; a.ntex = s->ntex;
     a.R = p->resolution;
     a.half_R = (float)p->resolution * 0.5f;
     a.mult = p->gaussian_std / (float)p->resolution;
@@ -368,10 +374,18 @@ M2S_EXPORT m2s_status m2s_convert_enqueue(m2s_ctx* ctx, const m2s_dscene* s, con
     a.counter = ctx->d_counter;
     a.total_out = d_total ? (unsigned long long*)d_total : ctx->d_total;
     a.sched = ctx->d_sched;
-    a.n_batches = (uint32_t)((count + kBatch - 1) / kBatch);
+    const int grid = ctx->sm_count * ctx->blocks_per_sm[klayout];
+    {   // work-unit size: as large as 32 triangles, but small enough that every warp of the grid gets the
+        // same number of units (a 70 k-triangle mesh is only ~1 unit of 32 per resident warp)
+        const uint64_t warps = (uint64_t)grid * convert_warps_per_cta(klayout);
+        const uint64_t rounds = std::max<uint64_t>(1, (count + warps * kUnitTris - 1) / (warps * kUnitTris));
+        uint64_t unit = (count + warps * rounds - 1) / (warps * rounds);
+        unit = std::min<uint64_t>(std::max<uint64_t>(unit, 1), kUnitTris);
+        a.unit_tris = (uint32_t)unit;
+        a.n_units = (uint32_t)((count + unit - 1) / unit);
+    }
     a.queue = ctx->d_queue;
     a.queue_cap = ctx->queue_cap;
-    const int grid = ctx->sm_count * ctx->blocks_per_sm[klayout];
     cudaError_t e = convert_launch(klayout, a, grid, stream);
     if (e != cudaSuccess) { ctx->dirty = true; set_error(std::string("convert launch: ") + cudaGetErrorString(e)); return M2S_E_CUDA; }
     if (ply_rows) {

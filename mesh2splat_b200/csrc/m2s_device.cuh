@@ -5,24 +5,25 @@
 
 namespace m2s {
 
-constexpr int kMaxLevels = 5;        // levels 0..4 (GL_TEXTURE_MAX_LEVEL 4, glUtils.cpp:313)
-constexpr int kBatch = 128;          // triangles staged per TMA batch (128 * 144 B = 18 KB)
-constexpr int kThreads = 256;        // threads per CTA
-constexpr int kWarps = kThreads / 32;
-constexpr int kQueue = 2048;         // fragment ids compacted per round (per CTA)
-constexpr int kTriBytes = 144;       // 36 floats
-constexpr uint32_t kBigCand = 4 * kQueue;    // a triangle with more candidate pixels is deferred
-constexpr uint32_t kChunkCand = 8 * kQueue;  // candidates per deferred work item
-constexpr float kGuard = 8192.0f;    // window-coordinate guard band (|xw| beyond -> triangle dropped)
+constexpr int kMaxLevels = 5;            // levels 0..4 (GL_TEXTURE_MAX_LEVEL 4, glUtils.cpp:313)
+constexpr int kUnitTris = 32;            // max triangles per work unit (one lane per triangle)
+constexpr int kQueue = 512;              // fragment ids compacted per warp before a flush
+constexpr int kTriBytes = 144;           // 36 floats
+constexpr uint32_t kSmallCand = 64;      // <= this many candidate pixels: lane-per-triangle raster
+constexpr uint32_t kBigCand = 1024;      // > this many: deferred, split into chunks over all warps
+constexpr uint32_t kChunkCand = 512;     // candidates per deferred work item
+constexpr float kGuard = 8192.0f;        // window-coordinate guard band (|xw| beyond -> triangle dropped)
 
-// RGBA8 mip chain of one texture. Levels are pitch-linear, tightly packed, row 0 first.
+// RGBA8 mip chain of one texture inside the texture arena (one allocation for all textures).
+// Levels are pitch-linear, tightly packed, row 0 first; off[] are TEXEL offsets from the arena base.
 struct DTexture {
-    const uint32_t* level[kMaxLevels];
-    uint32_t w[kMaxLevels];
-    uint32_t h[kMaxLevels];
+    uint32_t off[kMaxLevels];
+    uint16_t w[kMaxLevels];
+    uint16_t h[kMaxLevels];
     uint32_t nlevels;  // q + 1, q = min(4, floor(log2(max(w,h))))
     uint32_t pad;
 };
+static_assert(sizeof(DTexture) == 48, "DTexture layout");
 
 // One glTF primitive: the uniforms ConversionPass::conversion uploads per draw call
 // (ConversionPass.cpp:77-112).
@@ -47,6 +48,7 @@ struct ConvertArgs {
     uint32_t nranges;
     const DPrim* prims;
     const DTexture* texs;
+    const uint32_t* tex_base;  // texture arena
     uint32_t ntex;
     uint32_t R;
     float half_R;
@@ -57,9 +59,10 @@ struct ConvertArgs {
     unsigned long long* counter;       // fragments generated (the reference's atomic counter); context-owned,
                                        // zero at launch, re-zeroed by the last CTA
     unsigned long long* total_out;     // receives the final count (last CTA out)
-    // scheduling state (zeroed before launch)
-    uint32_t* sched;                   // [0] batch counter [1] batches done [2] queue tail [3] queue head [4] CTAs finished
-    uint32_t n_batches;
+    // scheduling state (zero at launch, re-armed by the last CTA)
+    uint32_t* sched;                   // [0] unit counter [1] units done [2] queue tail [3] queue head [4] CTAs finished
+    uint32_t unit_tris;                // triangles per work unit (<= 32), chosen by the host for balance
+    uint32_t n_units;
     uint2* queue;                      // deferred big-triangle chunks: (triangle, chunk)
     uint32_t queue_cap;
 };

@@ -1,28 +1,30 @@
 // m2s_kernels.cu — the conversion pass as hand-written sm_100a CUDA.
 //
 // ONE persistent kernel replaces the reference's geometry shader, fixed-function rasteriser,
-// fragment shader and SSBO atomic append (converter{GS,FS}.glsl, ConversionPass.cpp:114-116):
+// fragment shader and SSBO atomic append (converter{GS,FS}.glsl, ConversionPass.cpp:114-116).
 //
-//   per CTA, until the batch counter runs dry
-//     TMA (cp.async.bulk, mbarrier complete_tx) stages the next 128-triangle batch (18 KB) into
-//       the idle half of a double buffer while the current one is processed
-//     per-triangle stage (one thread per triangle; converterGS.glsl:326-443): longest edge,
-//       face normal, dominant axis, orthographic uv, quaternion, UV->3D Jacobian scale, then
-//       rasteriser set-up: 24.8 fixed-point window coords, int64 edge functions, top-left
-//       ownership bits, candidate pixel box, per-map texture LOD
-//     block scan of candidate counts -> flat candidate index space over the whole batch
-//     rounds of <= 2048 candidates:
-//       phase A  every lane tests one candidate pixel centre (exact integer edge functions) and
-//                survivors are compacted warp-ballot-wise into a shared-memory fragment queue
-//       one global atomicAdd per ROUND reserves the output range (not one per fragment, as the
-//                reference's atomicCounterIncrement does)
-//       phase B  (converterFS.glsl:44-104) full warps take 32 queued fragments: barycentric
-//                interpolation from the staged vertex data, trilinear RGBA8 fetches, TBN normal,
-//                record encode; records are transposed through shared memory so each warp
-//                writes one contiguous 32*stride-byte span with vector stores
-//   triangles whose pixel box exceeds 8192 candidates are pushed to a global chunk queue and
-//   rasterised by ALL CTAs after the batches are done (keeps a 2-triangle quad at R=2048 from
-//   serialising on one SM).
+// Every WARP is an autonomous pipeline with its own slice of shared memory (no __syncthreads in
+// the steady state, so warps sit in different stages and cover each other's latencies):
+//
+//   claim a work unit (<= 32 consecutive triangles) from a global counter
+//   TMA (cp.async.bulk + mbarrier complete_tx) stages the unit's 144 B/triangle into shared memory
+//   per-triangle stage, one LANE per triangle (converterGS.glsl:326-443): longest edge, face normal,
+//     dominant axis, orthographic uv, quaternion, UV->3D Jacobian scale; then rasteriser set-up:
+//     24.8 fixed-point window coords, int64 edge functions, top-left ownership bits, candidate pixel
+//     box, and the triangle's fully resolved sampler state (mip level pair, blend fraction, level
+//     base offsets and sizes) so the fragment stage never chases descriptors in global memory
+//   coverage, three regimes by candidate-pixel count:
+//     small  (<= 64, fits int32)  lane-per-triangle, lock-step incremental edge functions
+//     medium (<= 1024)            warp-per-triangle, 32 candidates per step, int64 edge functions
+//     big                         pushed as 512-candidate chunks to a global queue and rasterised by
+//                                 ALL warps of the grid after the units are done
+//     survivors are ballot-compacted into the warp's fragment queue (512 ids)
+//   flush: ONE global atomicAdd reserves the output range for up to 512 fragments (the reference
+//     does one atomicCounterIncrement per fragment), then the fragment stage
+//     (converterFS.glsl:44-104) runs on full warps: barycentric interpolation from the staged
+//     vertex data, all texel loads of all maps issued back to back, trilinear filter, TBN normal,
+//     record encode; records are transposed through shared memory so the warp writes one
+//     contiguous 32*stride-byte span with vector stores.
 //
 // Bit-exactness: every float operation that feeds a DECISION (edge ordering, dominant axis,
 // fixed-point snapping => coverage) is written with __f*_rn intrinsics in the operation order of
@@ -96,82 +98,80 @@ __device__ __forceinline__ f3 cross3(f3 x, f3 y) {
 }
 
 // ------------------------------------------------------------------------------------------
-// shared-memory records
+// per-warp shared-memory records
 // ------------------------------------------------------------------------------------------
-struct __align__(16) TriRaster {  // 64 B
+struct __align__(16) TriRaster {  // 64 B — sign-normalised edge functions E_k(i,j) = A_k i + B_k j + C_k
     long long C[3];
     int A[3];
     int B[3];
-    unsigned short x0, y0, w, h;
+    unsigned short x0, y0, w, h;  // candidate pixel box
     float inv_area;
-    unsigned incl;
+    unsigned incl;                // bit k: edge k owns its E == 0 samples (top-left rule)
 };
-struct __align__(16) TriFrag {  // 48 B
-    float quat[4];   // (w,x,y,z)
-    float scale[3];  // raw (REF96) or log(scale * sigma/R)
-    float lod[3];
-    int prim;
-    unsigned tri;    // global triangle index
+struct __align__(8) TexRef {  // 16 B — one map, resolved for one triangle
+    uint32_t off0, off1;          // texel offsets of the two mip levels in the arena; off0 == ~0u: no map
+    unsigned short w0, h0, w1, h1;
+};
+template <int NMAPS>
+struct __align__(16) TriFragT {  // 64 + 16*NMAPS bytes
+    float quat[4];    // (w,x,y,z)
+    float scale[3];   // raw (REF96) or log(scale * sigma/R)
+    unsigned tri;     // global triangle index
+    float factor[4];  // u_materialFactor
+    float frac[3];    // trilinear blend per map (0 => single level)
+    unsigned pad;
+    TexRef tex[NMAPS];
 };
 
 template <int LAYOUT>
-struct LayoutTraits;
+struct Cfg;
 template <>
-struct LayoutTraits<0> {  // REF96
+struct Cfg<0> {  // REF96
     static constexpr int kStride = 96;
-    static constexpr int kStagePitch = 112;  // padded: conflict-free float4 staging writes
-    static constexpr bool kNeedNormal = true, kNeedMR = true, kLogScale = false;
+    static constexpr int kPitch = 112;  // padded: conflict-free float4 staging writes
+    static constexpr int kMaps = 3;
+    static constexpr bool kLogScale = false;
+    static constexpr int kWarps = 14;
 };
 template <>
-struct LayoutTraits<1> {  // PACKED56
+struct Cfg<1> {  // PACKED56
     static constexpr int kStride = 56;
-    static constexpr int kStagePitch = 56;
-    static constexpr bool kNeedNormal = false, kNeedMR = false, kLogScale = true;
+    static constexpr int kPitch = 56;
+    static constexpr int kMaps = 1;
+    static constexpr bool kLogScale = true;
+    static constexpr int kWarps = 16;
 };
 
-struct SmemLayout {
-    static constexpr int kTriIn = 0;                                     // 2 * kBatch * 144
-    static constexpr int kRast = kTriIn + 2 * kBatch * kTriBytes;        // kBatch * 64
-    static constexpr int kFrag = kRast + kBatch * 64;                    // kBatch * 48
-    static constexpr int kPrefix = kFrag + kBatch * 48;                  // (kBatch + 4) * 4
-    static constexpr int kQueueOff = kPrefix + (kBatch + 4) * 4;         // kQueue * 4
-    static constexpr int kStage = kQueueOff + kQueue * 4;                // kWarps * 32 * pitch
-    __host__ __device__ static constexpr int stage_bytes(int pitch) { return kWarps * 32 * pitch; }
-    __host__ __device__ static constexpr int misc(int pitch) { return kStage + stage_bytes(pitch); }  // 64 B of scalars
-    __host__ __device__ static constexpr int total(int pitch) { return misc(pitch) + 64; }
-};
-
-struct Misc {
-    uint64_t bar[2];
-    int batch[2];
-    unsigned qcount;
-    unsigned item;
-    unsigned long long base;
-    unsigned wsum[4];
+template <int LAYOUT>
+struct __align__(128) WarpBlock {
+    float4 tri[kUnitTris * 9];                   // 4608 B, TMA destination
+    TriRaster rast[kUnitTris];                   // 2048 B
+    TriFragT<Cfg<LAYOUT>::kMaps> frag[kUnitTris];
+    uint32_t queue[kQueue];                      // 2048 B: slot << 24 | y << 12 | x
+    unsigned char stage[32 * Cfg<LAYOUT>::kPitch];
+    uint64_t bar;
 };
 
 // ------------------------------------------------------------------------------------------
-// per-triangle stage + rasteriser set-up.  t: 36 floats in shared memory.
+// per-triangle stage + rasteriser set-up.  t4: 9 float4 in shared memory.
 // Returns the number of candidate pixels (0 => nothing to rasterise).
 // ------------------------------------------------------------------------------------------
 template <int LAYOUT>
 __device__ uint32_t setup_triangle(const float4* __restrict__ t4, uint32_t tri_global, const ConvertArgs& a,
-                                   TriRaster& tr, TriFrag& tf) {
-    using LT = LayoutTraits<LAYOUT>;
+                                   TriRaster& tr, TriFragT<Cfg<LAYOUT>::kMaps>& tf) {
+    using C = Cfg<LAYOUT>;
     tr.w = 0; tr.h = 0; tr.x0 = 0; tr.y0 = 0; tr.incl = 0; tr.inv_area = 0.f;
     tf.tri = tri_global;
-    tf.prim = -1;
     // triangle -> primitive (sorted disjoint ranges)
     int lo = 0, hi = (int)a.nranges - 1, found = -1;
     while (lo <= hi) {
-        int mid = (lo + hi) >> 1;
-        DRange r = a.ranges[mid];
+        const int mid = (lo + hi) >> 1;
+        const DRange r = a.ranges[mid];
         if (tri_global < r.first) hi = mid - 1;
         else if (tri_global >= r.end) lo = mid + 1;
         else { found = (int)r.prim; break; }
     }
     if (found < 0) return 0;
-    tf.prim = found;
     const DPrim pr = a.prims[found];
 
     // vertex data: 3 x {pos3 nrm3 tan4 uv2} = 9 float4
@@ -190,20 +190,18 @@ __device__ uint32_t setup_triangle(const float4* __restrict__ t4, uint32_t tri_g
     const float ax = fabsf(n.x), ay = fabsf(n.y), az = fabsf(n.z);
     const int axis = (ax > ay && ax > az) ? 0 : ((ay > az) ? 1 : 2);
 
-    // :354-397 orthogonal uv
+    // :354-397 orthogonal uv: X -> (y,z), Y -> (x,z), Z -> (x,y), over max(range_a, range_b)
     float ou[3], ov[3];
     {
-        const int ia = axis == 0 ? 1 : 0, ib = axis == 2 ? 1 : 2;
-        const float ra = __fsub_rn(pr.bmax[ia], pr.bmin[ia]), rb = __fsub_rn(pr.bmax[ib], pr.bmin[ib]);
+        const float mina = axis == 0 ? pr.bmin[1] : pr.bmin[0], maxa = axis == 0 ? pr.bmax[1] : pr.bmax[0];
+        const float minb = axis == 2 ? pr.bmin[1] : pr.bmin[2], maxb = axis == 2 ? pr.bmax[1] : pr.bmax[2];
+        const float ra = __fsub_rn(maxa, mina), rb = __fsub_rn(maxb, minb);
         const float range = (ra < rb) ? rb : ra;
-        const f3 Ps[3] = {P0, P1, P2};
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const float pa = ia == 0 ? Ps[k].x : Ps[k].y;
-            const float pb = ib == 1 ? Ps[k].y : Ps[k].z;
-            ou[k] = __fdiv_rn(__fsub_rn(pa, pr.bmin[ia]), range);
-            ov[k] = __fdiv_rn(__fsub_rn(pb, pr.bmin[ib]), range);
-        }
+        const float pa0 = axis == 0 ? P0.y : P0.x, pa1 = axis == 0 ? P1.y : P1.x, pa2 = axis == 0 ? P2.y : P2.x;
+        const float pb0 = axis == 2 ? P0.y : P0.z, pb1 = axis == 2 ? P1.y : P1.z, pb2 = axis == 2 ? P2.y : P2.z;
+        ou[0] = __fdiv_rn(__fsub_rn(pa0, mina), range); ov[0] = __fdiv_rn(__fsub_rn(pb0, minb), range);
+        ou[1] = __fdiv_rn(__fsub_rn(pa1, mina), range); ov[1] = __fdiv_rn(__fsub_rn(pb1, minb), range);
+        ou[2] = __fdiv_rn(__fsub_rn(pa2, mina), range); ov[2] = __fdiv_rn(__fsub_rn(pb2, minb), range);
     }
 
     // :399-407 rotation -> quaternion (w,x,y,z), quat_cast :131-183
@@ -244,10 +242,11 @@ __device__ uint32_t setup_triangle(const float4* __restrict__ t4, uint32_t tri_g
         const f3 Jv = {__fadd_rn(__fmul_rn(V0.x, i10), __fmul_rn(V1.x, i11)), __fadd_rn(__fmul_rn(V0.y, i10), __fmul_rn(V1.y, i11)),
                        __fadd_rn(__fmul_rn(V0.z, i10), __fmul_rn(V1.z, i11))};
         const float sx = len3(Ju), sy = len3(Jv), sz = 1e-7f;
-        if (LT::kLogScale) {  // parsers.cpp:497-499 log(scale * sigma/R)
+        if (C::kLogScale) {  // parsers.cpp:497-499 log(scale * sigma/R)
             tf.scale[0] = logf(__fmul_rn(sx, a.mult)); tf.scale[1] = logf(__fmul_rn(sy, a.mult)); tf.scale[2] = logf(__fmul_rn(sz, a.mult));
         } else { tf.scale[0] = sx; tf.scale[1] = sy; tf.scale[2] = sz; }
     }
+    tf.factor[0] = pr.factor[0]; tf.factor[1] = pr.factor[1]; tf.factor[2] = pr.factor[2]; tf.factor[3] = pr.factor[3];
 
     // rasteriser set-up: gl_Position = ouv*2-1 (:439), viewport R x R, 8 sub-pixel bits
     int X[3], Y[3];
@@ -261,19 +260,19 @@ __device__ uint32_t setup_triangle(const float4* __restrict__ t4, uint32_t tri_g
         Y[k] = __float2int_rn(__fmul_rn(yw, 256.0f));
     }
     if (!valid) return 0;
-    long long area2 = (long long)(X[1] - X[0]) * (Y[2] - Y[0]) - (long long)(X[2] - X[0]) * (Y[1] - Y[0]);
+    const long long area2 = (long long)(X[1] - X[0]) * (Y[2] - Y[0]) - (long long)(X[2] - X[0]) * (Y[1] - Y[0]);
     if (area2 == 0) return 0;
-    const long long sg = area2 < 0 ? -1 : 1;
+    const int sg = area2 < 0 ? -1 : 1;
     unsigned incl = 0;
     int Ak[3], Bk[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const int va = (k + 1) % 3, vb = (k + 2) % 3;
-        const long long dx = X[vb] - X[va], dy = Y[vb] - Y[va];
-        const long long A = sg * (-dy * 256), B = sg * (dx * 256);
-        tr.A[k] = Ak[k] = (int)A;
-        tr.B[k] = Bk[k] = (int)B;
-        tr.C[k] = sg * (dx * (128 - (long long)Y[va]) - dy * (128 - (long long)X[va]));
+        const int dx = X[vb] - X[va], dy = Y[vb] - Y[va];
+        const int A = sg * (-dy * 256), B = sg * (dx * 256);
+        tr.A[k] = Ak[k] = A;
+        tr.B[k] = Bk[k] = B;
+        tr.C[k] = (long long)sg * ((long long)dx * (128 - Y[va]) - (long long)dy * (128 - X[va]));
         if (A > 0 || (A == 0 && B > 0)) incl |= 1u << k;
     }
     tr.incl = incl;
@@ -288,7 +287,8 @@ __device__ uint32_t setup_triangle(const float4* __restrict__ t4, uint32_t tri_g
     tr.x0 = (unsigned short)x0; tr.y0 = (unsigned short)y0;
     tr.w = (unsigned short)(x1 - x0 + 1); tr.h = (unsigned short)(y1 - y0 + 1);
 
-    // texture LOD (GL 4.6 8.14): per-pixel steps of the mesh uv are constant per triangle
+    // sampler state (GL 4.6 8.14): the per-pixel steps of the mesh uv are constant per triangle, so
+    // lambda, the level pair and the blend fraction are too
     float dudx = 0.f, dvdx = 0.f, dudy = 0.f, dvdy = 0.f;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -297,17 +297,28 @@ __device__ uint32_t setup_triangle(const float4* __restrict__ t4, uint32_t tri_g
         dudy += uvx[k] * cb; dvdy += uvy[k] * cb;
     }
 #pragma unroll
-    for (int m = 0; m < 3; ++m) {
-        float lam = 0.f;
-        const bool need = (m == 0) || (m == 1 && LT::kNeedNormal) || (m == 2 && LT::kNeedMR);
+    for (int m = 0; m < C::kMaps; ++m) {
+        TexRef ref;
+        ref.off0 = 0xffffffffu; ref.off1 = 0; ref.w0 = ref.h0 = ref.w1 = ref.h1 = 1;
+        float frac = 0.f;
         const int ti = pr.tex[m];
-        if (need && ti >= 0) {
-            const float W = (float)a.texs[ti].w[0], H = (float)a.texs[ti].h[0];
+        if (ti >= 0) {
+            const DTexture t = a.texs[ti];
+            const float W = (float)t.w[0], H = (float)t.h[0];
             const float axx = dudx * W, bxx = dvdx * H, ayy = dudy * W, byy = dvdy * H;
             const float rx = sqrtf(axx * axx + bxx * bxx), ry = sqrtf(ayy * ayy + byy * byy);
-            lam = log2f(fmaxf(rx, ry));
+            const float lam = log2f(fmaxf(rx, ry));
+            const int q = (int)t.nlevels - 1;
+            int l0 = 0;
+            if (!(lam > 0.0f)) { l0 = 0; }                       // magnification: LINEAR on level 0
+            else if (lam >= (float)q) { l0 = q; }                 // clamped to the last level
+            else { const float d = floorf(lam); l0 = (int)d; frac = lam - d; }
+            const int l1 = min(l0 + 1, q);
+            ref.off0 = t.off[l0]; ref.off1 = t.off[l1];
+            ref.w0 = t.w[l0]; ref.h0 = t.h[l0]; ref.w1 = t.w[l1]; ref.h1 = t.h[l1];
         }
-        tf.lod[m] = lam;
+        tf.tex[m] = ref;
+        tf.frac[m] = frac;
     }
     return (uint32_t)tr.w * (uint32_t)tr.h;
 }
@@ -315,43 +326,38 @@ __device__ uint32_t setup_triangle(const float4* __restrict__ t4, uint32_t tri_g
 // ------------------------------------------------------------------------------------------
 // sampler: RGBA8 unorm, REPEAT, bilinear within a level, linear between levels
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float4 unpack_rgba8(uint32_t t) {
-    const float k = 1.0f / 255.0f;
-    return make_float4((float)(t & 0xffu) * k, (float)((t >> 8) & 0xffu) * k, (float)((t >> 16) & 0xffu) * k,
-                       (float)(t >> 24) * k);
-}
-__device__ __forceinline__ float4 lerp4(float4 a, float4 b, float t) {
-    return make_float4(a.x + t * (b.x - a.x), a.y + t * (b.y - a.y), a.z + t * (b.z - a.z), a.w + t * (b.w - a.w));
-}
-__device__ __forceinline__ float4 bilinear(const uint32_t* __restrict__ lv, uint32_t W, uint32_t H, float u, float v) {
+struct Bilin {          // addresses + weights of one bilinear footprint
+    uint32_t i00, i10, i01, i11;
+    float w00, w10, w01, w11;  // already scaled by 1/255
+};
+__device__ __forceinline__ Bilin bilin_setup(uint32_t off, uint32_t W, uint32_t H, float u, float v) {
     // REPEAT: wrap in the normalised domain (exact for u in [0,1)), then fix the one-texel overhang
     u -= floorf(u);
     v -= floorf(v);
     const float x = u * (float)W - 0.5f, y = v * (float)H - 0.5f;
     const float fx = floorf(x), fy = floorf(y);
     const float ax = x - fx, ay = y - fy;
-    int ix = (int)fx, iy = (int)fy;
-    int x0 = ix < 0 ? (int)W - 1 : (ix >= (int)W ? ix - (int)W : ix);
-    int y0 = iy < 0 ? (int)H - 1 : (iy >= (int)H ? iy - (int)H : iy);
-    int x1 = x0 + 1 >= (int)W ? 0 : x0 + 1;
-    int y1 = y0 + 1 >= (int)H ? 0 : y0 + 1;
-    const uint32_t* r0 = lv + (size_t)y0 * W;
-    const uint32_t* r1 = lv + (size_t)y1 * W;
-    const uint32_t t00 = __ldg(r0 + x0), t10 = __ldg(r0 + x1), t01 = __ldg(r1 + x0), t11 = __ldg(r1 + x1);
-    const float4 top = lerp4(unpack_rgba8(t00), unpack_rgba8(t10), ax);
-    const float4 bot = lerp4(unpack_rgba8(t01), unpack_rgba8(t11), ax);
-    return lerp4(top, bot, ay);
+    const int ix = (int)fx, iy = (int)fy;
+    const int x0 = ix < 0 ? (int)W - 1 : (ix >= (int)W ? ix - (int)W : ix);
+    const int y0 = iy < 0 ? (int)H - 1 : (iy >= (int)H ? iy - (int)H : iy);
+    const int x1 = x0 + 1 >= (int)W ? 0 : x0 + 1;
+    const int y1 = y0 + 1 >= (int)H ? 0 : y0 + 1;
+    Bilin b;
+    const uint32_t r0 = off + (uint32_t)y0 * W, r1 = off + (uint32_t)y1 * W;
+    b.i00 = r0 + x0; b.i10 = r0 + x1; b.i01 = r1 + x0; b.i11 = r1 + x1;
+    const float k = 1.0f / 255.0f;
+    const float bx = 1.0f - ax, by = (1.0f - ay) * k, cy = ay * k;
+    b.w00 = bx * by; b.w10 = ax * by; b.w01 = bx * cy; b.w11 = ax * cy;
+    return b;
 }
-__device__ __forceinline__ float4 sample_trilinear(const DTexture& t, float u, float v, float lambda) {
-    const int q = (int)t.nlevels - 1;
-    if (!(lambda > 0.0f)) return bilinear(t.level[0], t.w[0], t.h[0], u, v);
-    if (lambda >= (float)q) return bilinear(t.level[q], t.w[q], t.h[q], u, v);
-    const float d = floorf(lambda), f = lambda - d;
-    const int l = (int)d;
-    const float4 a = bilinear(t.level[l], t.w[l], t.h[l], u, v);
-    if (f == 0.0f) return a;
-    const float4 b = bilinear(t.level[l + 1], t.w[l + 1], t.h[l + 1], u, v);
-    return lerp4(a, b, f);
+// byte c of a texel as float, without the conversion pipe: 0x4B000000 | byte is 2^23 + byte
+template <int CH>
+__device__ __forceinline__ float tex_ch(uint32_t t) {
+    return __uint_as_float(__byte_perm(t, 0x4B000000u, 0x7440u | CH)) - 8388608.0f;
+}
+template <int CH>
+__device__ __forceinline__ float filt(const Bilin& b, uint32_t t00, uint32_t t10, uint32_t t01, uint32_t t11) {
+    return b.w00 * tex_ch<CH>(t00) + b.w10 * tex_ch<CH>(t10) + b.w01 * tex_ch<CH>(t01) + b.w11 * tex_ch<CH>(t11);
 }
 
 __device__ __forceinline__ float inv_sigmoid(float a) {  // utils.hpp:270
@@ -360,167 +366,212 @@ __device__ __forceinline__ float inv_sigmoid(float a) {  // utils.hpp:270
 }
 
 // ------------------------------------------------------------------------------------------
-// rounds over a flat candidate range of the triangles currently set up in shared memory
+// flush: reserve the output range, run the fragment stage over the warp's queue, write records
 // ------------------------------------------------------------------------------------------
 template <int LAYOUT>
-__device__ void raster_rounds(const ConvertArgs& a, unsigned char* smem, const float4* tri_in, uint32_t ntri,
-                              uint32_t cand_begin, uint32_t cand_end) {
-    using LT = LayoutTraits<LAYOUT>;
-    constexpr int kPitch = LT::kStagePitch;
-    const TriRaster* rast = reinterpret_cast<const TriRaster*>(smem + SmemLayout::kRast);
-    const TriFrag* frag = reinterpret_cast<const TriFrag*>(smem + SmemLayout::kFrag);
-    const uint32_t* prefix = reinterpret_cast<const uint32_t*>(smem + SmemLayout::kPrefix);
-    uint32_t* queue = reinterpret_cast<uint32_t*>(smem + SmemLayout::kQueueOff);
-    Misc* misc = reinterpret_cast<Misc*>(smem + SmemLayout::misc(kPitch));
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    unsigned char* stage = smem + SmemLayout::kStage + warp * 32 * kPitch;
+__device__ __noinline__ void flush_queue(const ConvertArgs& a, WarpBlock<LAYOUT>& wb, uint32_t qn, int lane) {
+    using C = Cfg<LAYOUT>;
+    constexpr int kPitch = C::kPitch;
+    if (qn == 0) return;
+    __syncwarp();
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(a.counter, (unsigned long long)qn);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    const uint32_t* __restrict__ texb = a.tex_base;
 
-    for (uint32_t r0 = cand_begin; r0 < cand_end; r0 += kQueue) {
-        const uint32_t r1 = min(r0 + (uint32_t)kQueue, cand_end);
-        if (tid == 0) misc->qcount = 0;
-        __syncthreads();
-        // ---- phase A: coverage test + compaction -------------------------------------------
-        for (uint32_t cb = r0 + warp * 32; cb < r1; cb += kThreads) {
-            const uint32_t c = cb + lane;
-            bool pass = false;
-            uint32_t id = 0;
-            if (c < r1) {
-                uint32_t lo = 0, hi = ntri;  // largest s with prefix[s] <= c
-                while (hi - lo > 1) {
-                    const uint32_t mid = (lo + hi) >> 1;
-                    if (prefix[mid] <= c) lo = mid; else hi = mid;
-                }
-                const TriRaster& tr = rast[lo];
-                const uint32_t k = c - prefix[lo];
-                const uint32_t w = tr.w;
-                const uint32_t row = k / w, col = k - row * w;
-                const int px = tr.x0 + col, py = tr.y0 + row;
-                pass = true;
-#pragma unroll
-                for (int e = 0; e < 3; ++e) {
-                    const long long E = tr.C[e] + (long long)tr.A[e] * px + (long long)tr.B[e] * py;
-                    pass = pass && (E > 0 || (E == 0 && ((tr.incl >> e) & 1u)));
-                }
-                id = (lo << 24) | ((uint32_t)py << 12) | (uint32_t)px;
+    for (uint32_t fb = 0; fb < qn; fb += 32) {
+        const uint32_t nfr = min(32u, qn - fb);
+        unsigned long long key = 0;
+        if ((uint32_t)lane < nfr) {
+            const uint32_t id = wb.queue[fb + lane];
+            const uint32_t slot = id >> 24;
+            const int py = (id >> 12) & 0xfff, px = id & 0xfff;
+            const TriRaster& tr = wb.rast[slot];
+            const TriFragT<C::kMaps>& tf = wb.frag[slot];
+            float l0, l1, l2;
+            {
+                const float ia = tr.inv_area;
+                l0 = __ll2float_rn(tr.C[0] + (long long)tr.A[0] * px + (long long)tr.B[0] * py) * ia;
+                l1 = __ll2float_rn(tr.C[1] + (long long)tr.A[1] * px + (long long)tr.B[1] * py) * ia;
+                l2 = __ll2float_rn(tr.C[2] + (long long)tr.A[2] * px + (long long)tr.B[2] * py) * ia;
             }
-            const unsigned m = __ballot_sync(0xffffffffu, pass);
-            if (m) {
-                unsigned base = 0;
-                if (lane == 0) base = atomicAdd(&misc->qcount, (unsigned)__popc(m));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (pass) queue[base + __popc(m & ((1u << lane) - 1u))] = id;
-            }
-        }
-        __syncthreads();
-        const uint32_t qn = misc->qcount;
-        if (tid == 0 && qn) misc->base = atomicAdd(a.counter, (unsigned long long)qn);
-        __syncthreads();
-        if (qn == 0) continue;
-        const unsigned long long base = misc->base;
+            const float4* v = wb.tri + slot * 9;
+            // uv first: the texel addresses depend on nothing else
+            const float4 a2 = v[2], b2 = v[5], c2 = v[8];
+            const float u = l0 * a2.z + l1 * b2.z + l2 * c2.z, vv = l0 * a2.w + l1 * b2.w + l2 * c2.w;
 
-        // ---- phase B: fragment stage ---------------------------------------------------------
-        for (uint32_t fb = warp * 32; fb < qn; fb += kThreads) {
-            const uint32_t nfr = min(32u, qn - fb);
-            unsigned long long key = 0;
-            if ((uint32_t)lane < nfr) {
-                const uint32_t id = queue[fb + lane];
-                const uint32_t slot = id >> 24;
-                const int py = (id >> 12) & 0xfff, px = id & 0xfff;
-                const TriRaster& tr = rast[slot];
-                const TriFrag& tf = frag[slot];
-                float l[3];
+            // ---- issue every texel load of every bound map back to back ----
+            uint32_t tx[C::kMaps][8];
+            Bilin bl[C::kMaps][2];
+            bool has[C::kMaps], two[C::kMaps];
 #pragma unroll
-                for (int e = 0; e < 3; ++e)
-                    l[e] = __ll2float_rn(tr.C[e] + (long long)tr.A[e] * px + (long long)tr.B[e] * py) * tr.inv_area;
-                const float4* v = tri_in + slot * 9;
-                float at[12];
-                {
-                    const float4 a0 = v[0], a1 = v[1], a2 = v[2], b0 = v[3], b1 = v[4], b2 = v[5], c0 = v[6], c1 = v[7], c2 = v[8];
-                    at[0] = l[0] * a0.x + l[1] * b0.x + l[2] * c0.x; at[1] = l[0] * a0.y + l[1] * b0.y + l[2] * c0.y;
-                    at[2] = l[0] * a0.z + l[1] * b0.z + l[2] * c0.z; at[3] = l[0] * a0.w + l[1] * b0.w + l[2] * c0.w;
-                    at[4] = l[0] * a1.x + l[1] * b1.x + l[2] * c1.x; at[5] = l[0] * a1.y + l[1] * b1.y + l[2] * c1.y;
-                    at[6] = l[0] * a1.z + l[1] * b1.z + l[2] * c1.z; at[7] = l[0] * a1.w + l[1] * b1.w + l[2] * c1.w;
-                    at[8] = l[0] * a2.x + l[1] * b2.x + l[2] * c2.x; at[9] = l[0] * a2.y + l[1] * b2.y + l[2] * c2.y;
-                    at[10] = l[0] * a2.z + l[1] * b2.z + l[2] * c2.z; at[11] = l[0] * a2.w + l[1] * b2.w + l[2] * c2.w;
-                }
-                const DPrim& pr = a.prims[tf.prim];
-                const float u = at[10], vv = at[11];
-                // converterFS.glsl:55-62,99
-                float4 col = make_float4(1.f, 1.f, 1.f, 1.f);
-                const int ta = pr.tex[0];
-                if (ta >= 0) col = sample_trilinear(a.texs[ta], u, vv, tf.lod[0]);
-                col.x *= pr.factor[0]; col.y *= pr.factor[1]; col.z *= pr.factor[2]; col.w *= pr.factor[3];
-                float* srec = reinterpret_cast<float*>(stage + lane * kPitch);
-                if (LAYOUT == 0) {
-                    // :64-81 normal
-                    float nx = at[3], ny = at[4], nz = at[5];
-                    const int tn = pr.tex[1];
-                    if (tn >= 0) {
-                        const float4 nm = sample_trilinear(a.texs[tn], u, vv, tf.lod[1]);
-                        float rx = nm.x * 2.0f - 1.0f, ry = nm.y * 2.0f - 1.0f, rz = nm.z * 2.0f - 1.0f;
-                        float inv = 1.0f / sqrtf(rx * rx + ry * ry + rz * rz);
-                        rx *= inv; ry *= inv; rz *= inv;
-                        const float tx = at[6], ty = at[7], tz = at[8], tw = at[9];
-                        float bx = ny * tz - ty * nz, by = nz * tx - tz * nx, bz = nx * ty - tx * ny;  // cross(N,T)
-                        inv = tw / sqrtf(bx * bx + by * by + bz * bz);
-                        bx *= inv; by *= inv; bz *= inv;
-                        inv = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz);
-                        const float nnx = nx * inv, nny = ny * inv, nnz = nz * inv;
-                        float ox = tx * rx + bx * ry + nnx * rz, oy = ty * rx + by * ry + nny * rz, oz = tz * rx + bz * ry + nnz * rz;
-                        inv = 1.0f / sqrtf(ox * ox + oy * oy + oz * oz);
-                        nx = ox * inv; ny = oy * inv; nz = oz * inv;
-                    }
-                    // :83-95 metallic-roughness (.bg)
-                    float metal = 0.1f, rough = 0.5f;
-                    const int tm = pr.tex[2];
-                    if (tm >= 0) {
-                        const float4 mr = sample_trilinear(a.texs[tm], u, vv, tf.lod[2]);
-                        metal = mr.z; rough = mr.y;
-                    }
-                    float4* s4 = reinterpret_cast<float4*>(srec);
-                    s4[0] = make_float4(at[0], at[1], at[2], 1.0f);
-                    s4[1] = col;
-                    s4[2] = make_float4(tf.scale[0], tf.scale[1], tf.scale[2], 0.0f);
-                    s4[3] = make_float4(nx, ny, nz, 0.0f);
-                    s4[4] = make_float4(tf.quat[0], tf.quat[1], tf.quat[2], tf.quat[3]);
-                    s4[5] = make_float4(metal, rough, 0.0f, 1.0f);
-                } else {
-                    // parsers.cpp:484-499: SH0, opacity logit, log scale (per triangle)
-                    const float kC0 = 0.28209479177387814f;  // SH_COEFF0, params.hpp:17
-                    float2* s2 = reinterpret_cast<float2*>(srec);
-                    s2[0] = make_float2(at[0], at[1]);
-                    s2[1] = make_float2(at[2], tf.quat[0]);
-                    s2[2] = make_float2(tf.quat[1], tf.quat[2]);
-                    s2[3] = make_float2(tf.quat[3], tf.scale[0]);
-                    s2[4] = make_float2(tf.scale[1], tf.scale[2]);
-                    s2[5] = make_float2(__fdiv_rn(col.x - 0.5f, kC0), __fdiv_rn(col.y - 0.5f, kC0));
-                    s2[6] = make_float2(__fdiv_rn(col.z - 0.5f, kC0), inv_sigmoid(col.w));
-                }
-                key = ((unsigned long long)tf.tri << 24) | ((unsigned long long)py << 12) | (unsigned long long)px;
+            for (int m = 0; m < C::kMaps; ++m) {
+                const TexRef ref = tf.tex[m];
+                has[m] = ref.off0 != 0xffffffffu;
+                two[m] = has[m] && tf.frac[m] > 0.0f;
+                bl[m][0] = bilin_setup(has[m] ? ref.off0 : 0u, ref.w0, ref.h0, u, vv);
+                bl[m][1] = bilin_setup(ref.off1, ref.w1, ref.h1, u, vv);
             }
-            __syncwarp();
-            // ---- coalesced copy-out of this warp's contiguous span --------------------------
-            const unsigned long long wbase = base + fb;  // first output index of this warp's span
-            uint32_t nvalid = 0;                          // converterFS.glsl:48-51: idx >= cap dropped
-            if (wbase < a.cap) nvalid = (uint32_t)min((unsigned long long)nfr, a.cap - wbase);
+#pragma unroll
+            for (int m = 0; m < C::kMaps; ++m) {
+                tx[m][0] = has[m] ? __ldg(texb + bl[m][0].i00) : 0u; tx[m][1] = has[m] ? __ldg(texb + bl[m][0].i10) : 0u;
+                tx[m][2] = has[m] ? __ldg(texb + bl[m][0].i01) : 0u; tx[m][3] = has[m] ? __ldg(texb + bl[m][0].i11) : 0u;
+                tx[m][4] = two[m] ? __ldg(texb + bl[m][1].i00) : 0u; tx[m][5] = two[m] ? __ldg(texb + bl[m][1].i10) : 0u;
+                tx[m][6] = two[m] ? __ldg(texb + bl[m][1].i01) : 0u; tx[m][7] = two[m] ? __ldg(texb + bl[m][1].i11) : 0u;
+            }
+            // ---- interpolate the remaining varyings while the loads are in flight ----
+            const float4 a0 = v[0], b0 = v[3], c0 = v[6];
+            const float Px = l0 * a0.x + l1 * b0.x + l2 * c0.x, Py = l0 * a0.y + l1 * b0.y + l2 * c0.y,
+                        Pz = l0 * a0.z + l1 * b0.z + l2 * c0.z;
+            float* srec = reinterpret_cast<float*>(wb.stage + lane * kPitch);
+
+            // colour (converterFS.glsl:55-62,99)
+            float cr = 1.f, cg = 1.f, cb = 1.f, ca = 1.f;
+            if (has[0]) {
+                const float f = tf.frac[0];
+                cr = filt<0>(bl[0][0], tx[0][0], tx[0][1], tx[0][2], tx[0][3]);
+                cg = filt<1>(bl[0][0], tx[0][0], tx[0][1], tx[0][2], tx[0][3]);
+                cb = filt<2>(bl[0][0], tx[0][0], tx[0][1], tx[0][2], tx[0][3]);
+                ca = filt<3>(bl[0][0], tx[0][0], tx[0][1], tx[0][2], tx[0][3]);
+                if (two[0]) {
+                    cr += f * (filt<0>(bl[0][1], tx[0][4], tx[0][5], tx[0][6], tx[0][7]) - cr);
+                    cg += f * (filt<1>(bl[0][1], tx[0][4], tx[0][5], tx[0][6], tx[0][7]) - cg);
+                    cb += f * (filt<2>(bl[0][1], tx[0][4], tx[0][5], tx[0][6], tx[0][7]) - cb);
+                    ca += f * (filt<3>(bl[0][1], tx[0][4], tx[0][5], tx[0][6], tx[0][7]) - ca);
+                }
+            }
+            cr *= tf.factor[0]; cg *= tf.factor[1]; cb *= tf.factor[2]; ca *= tf.factor[3];
+
             if (LAYOUT == 0) {
-                float4* dst = reinterpret_cast<float4*>(a.out + wbase * 96ull);
-#pragma unroll
-                for (int j = 0; j < 6; ++j) {
-                    const uint32_t c = lane + 32 * j, rec = c / 6, part = c - rec * 6;
-                    if (rec < nvalid) dst[c] = *reinterpret_cast<const float4*>(stage + rec * kPitch + part * 16);
+                const float Nx = l0 * a0.w + l1 * b0.w + l2 * c0.w;
+                const float4 a1 = v[1], b1 = v[4], c1 = v[7];
+                const float Ny = l0 * a1.x + l1 * b1.x + l2 * c1.x, Nz = l0 * a1.y + l1 * b1.y + l2 * c1.y;
+                float nx = Nx, ny = Ny, nz = Nz;
+                constexpr int MN = C::kMaps > 1 ? 1 : 0, MM = C::kMaps > 2 ? 2 : 0;
+                if (has[MN]) {  // :64-77 TBN
+                    const float f = tf.frac[MN];
+                    float mx = filt<0>(bl[MN][0], tx[MN][0], tx[MN][1], tx[MN][2], tx[MN][3]);
+                    float my = filt<1>(bl[MN][0], tx[MN][0], tx[MN][1], tx[MN][2], tx[MN][3]);
+                    float mz = filt<2>(bl[MN][0], tx[MN][0], tx[MN][1], tx[MN][2], tx[MN][3]);
+                    if (two[MN]) {
+                        mx += f * (filt<0>(bl[MN][1], tx[MN][4], tx[MN][5], tx[MN][6], tx[MN][7]) - mx);
+                        my += f * (filt<1>(bl[MN][1], tx[MN][4], tx[MN][5], tx[MN][6], tx[MN][7]) - my);
+                        mz += f * (filt<2>(bl[MN][1], tx[MN][4], tx[MN][5], tx[MN][6], tx[MN][7]) - mz);
+                    }
+                    const float Tx = l0 * a1.z + l1 * b1.z + l2 * c1.z, Ty = l0 * a1.w + l1 * b1.w + l2 * c1.w;
+                    const float Tz = l0 * a2.x + l1 * b2.x + l2 * c2.x, Tw = l0 * a2.y + l1 * b2.y + l2 * c2.y;
+                    float rx = mx * 2.0f - 1.0f, ry = my * 2.0f - 1.0f, rz = mz * 2.0f - 1.0f;
+                    float inv = rsqrtf(rx * rx + ry * ry + rz * rz);
+                    rx *= inv; ry *= inv; rz *= inv;
+                    float bx = Ny * Tz - Ty * Nz, by = Nz * Tx - Tz * Nx, bz = Nx * Ty - Tx * Ny;  // cross(N,T)
+                    inv = Tw * rsqrtf(bx * bx + by * by + bz * bz);
+                    bx *= inv; by *= inv; bz *= inv;
+                    inv = rsqrtf(Nx * Nx + Ny * Ny + Nz * Nz);
+                    const float ox = Tx * rx + bx * ry + Nx * inv * rz, oy = Ty * rx + by * ry + Ny * inv * rz,
+                                oz = Tz * rx + bz * ry + Nz * inv * rz;
+                    inv = rsqrtf(ox * ox + oy * oy + oz * oz);
+                    nx = ox * inv; ny = oy * inv; nz = oz * inv;
                 }
+                float metal = 0.1f, rough = 0.5f;  // :83-95 (.bg)
+                if (has[MM]) {
+                    const float f = tf.frac[MM];
+                    rough = filt<1>(bl[MM][0], tx[MM][0], tx[MM][1], tx[MM][2], tx[MM][3]);
+                    metal = filt<2>(bl[MM][0], tx[MM][0], tx[MM][1], tx[MM][2], tx[MM][3]);
+                    if (two[MM]) {
+                        rough += f * (filt<1>(bl[MM][1], tx[MM][4], tx[MM][5], tx[MM][6], tx[MM][7]) - rough);
+                        metal += f * (filt<2>(bl[MM][1], tx[MM][4], tx[MM][5], tx[MM][6], tx[MM][7]) - metal);
+                    }
+                }
+                float4* s4 = reinterpret_cast<float4*>(srec);
+                s4[0] = make_float4(Px, Py, Pz, 1.0f);
+                s4[1] = make_float4(cr, cg, cb, ca);
+                s4[2] = make_float4(tf.scale[0], tf.scale[1], tf.scale[2], 0.0f);
+                s4[3] = make_float4(nx, ny, nz, 0.0f);
+                s4[4] = make_float4(tf.quat[0], tf.quat[1], tf.quat[2], tf.quat[3]);
+                s4[5] = make_float4(metal, rough, 0.0f, 1.0f);
             } else {
-                float2* dst = reinterpret_cast<float2*>(a.out + wbase * 56ull);
-#pragma unroll
-                for (int j = 0; j < 7; ++j) {
-                    const uint32_t c = lane + 32 * j, rec = c / 7, part = c - rec * 7;
-                    if (rec < nvalid) dst[c] = *reinterpret_cast<const float2*>(stage + rec * kPitch + part * 8);
-                }
+                // parsers.cpp:484-499: SH0, opacity logit, log scale (per triangle)
+                const float kC0 = 0.28209479177387814f;  // SH_COEFF0, params.hpp:17
+                float2* s2 = reinterpret_cast<float2*>(srec);
+                s2[0] = make_float2(Px, Py);
+                s2[1] = make_float2(Pz, tf.quat[0]);
+                s2[2] = make_float2(tf.quat[1], tf.quat[2]);
+                s2[3] = make_float2(tf.quat[3], tf.scale[0]);
+                s2[4] = make_float2(tf.scale[1], tf.scale[2]);
+                s2[5] = make_float2(__fdiv_rn(cr - 0.5f, kC0), __fdiv_rn(cg - 0.5f, kC0));
+                s2[6] = make_float2(__fdiv_rn(cb - 0.5f, kC0), inv_sigmoid(ca));
             }
-            if (a.keys && (uint32_t)lane < nvalid) a.keys[wbase + lane] = key;
-            __syncwarp();
+            key = ((unsigned long long)tf.tri << 24) | ((unsigned long long)py << 12) | (unsigned long long)px;
         }
+        __syncwarp();
+        // ---- coalesced copy-out of this warp's contiguous span --------------------------------
+        const unsigned long long wbase = base + fb;
+        uint32_t nvalid = 0;  // converterFS.glsl:48-51: idx >= cap dropped
+        if (wbase < a.cap) nvalid = (uint32_t)min((unsigned long long)nfr, a.cap - wbase);
+        if (LAYOUT == 0) {
+            float4* dst = reinterpret_cast<float4*>(a.out + wbase * 96ull);
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                const uint32_t c = lane + 32 * j, rec = c / 6, part = c - rec * 6;
+                if (rec < nvalid) dst[c] = *reinterpret_cast<const float4*>(wb.stage + rec * kPitch + part * 16);
+            }
+        } else {
+            float2* dst = reinterpret_cast<float2*>(a.out + wbase * 56ull);
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+                const uint32_t c = lane + 32 * j, rec = c / 7, part = c - rec * 7;
+                if (rec < nvalid) dst[c] = *reinterpret_cast<const float2*>(wb.stage + rec * kPitch + part * 8);
+            }
+        }
+        if (a.keys && (uint32_t)lane < nvalid) a.keys[wbase + lane] = key;
+        __syncwarp();
+    }
+}
+
+// enqueue the lanes whose `inside` is set; flush when the queue could overflow on the next step
+template <int LAYOUT>
+__device__ __forceinline__ void enqueue(const ConvertArgs& a, WarpBlock<LAYOUT>& wb, uint32_t& qn, bool inside, uint32_t id,
+                                        int lane) {
+    const unsigned m = __ballot_sync(0xffffffffu, inside);
+    if (m) {
+        if (inside) wb.queue[qn + __popc(m & ((1u << lane) - 1u))] = id;
+        qn += __popc(m);
+        if (qn > kQueue - 32) {
+            flush_queue<LAYOUT>(a, wb, qn, lane);
+            qn = 0;
+        }
+    }
+}
+
+// warp-per-triangle coverage of candidates [c0, c1) of the triangle in `slot` (int64 edge functions)
+template <int LAYOUT>
+__device__ void raster_one(const ConvertArgs& a, WarpBlock<LAYOUT>& wb, uint32_t& qn, uint32_t slot, uint32_t c0, uint32_t c1,
+                           int lane) {
+    const TriRaster& tr = wb.rast[slot];
+    const uint32_t w = tr.w;
+    const float rcp = 1.0f / (float)w;
+    const long long C0 = tr.C[0], C1 = tr.C[1], C2 = tr.C[2];
+    const int A0 = tr.A[0], A1 = tr.A[1], A2 = tr.A[2], B0 = tr.B[0], B1 = tr.B[1], B2 = tr.B[2];
+    const unsigned incl = tr.incl;
+    const int bx = tr.x0, by = tr.y0;
+    for (uint32_t cb = c0; cb < c1; cb += 32) {
+        const uint32_t c = cb + lane;
+        bool inside = false;
+        uint32_t id = 0;
+        if (c < c1) {
+            uint32_t row = (uint32_t)((float)c * rcp);  // c < 2^24: exact in fp32, quotient off by at most 1
+            int col = (int)(c - row * w);
+            if (col < 0) { --row; col += (int)w; }
+            else if (col >= (int)w) { ++row; col -= (int)w; }
+            const int px = bx + col, py = by + (int)row;
+            const long long E0 = C0 + (long long)A0 * px + (long long)B0 * py;
+            const long long E1 = C1 + (long long)A1 * px + (long long)B1 * py;
+            const long long E2 = C2 + (long long)A2 * px + (long long)B2 * py;
+            inside = (E0 > 0 || (E0 == 0 && (incl & 1u))) && (E1 > 0 || (E1 == 0 && (incl & 2u))) &&
+                     (E2 > 0 || (E2 == 0 && (incl & 4u)));
+            id = (slot << 24) | ((uint32_t)py << 12) | (uint32_t)px;
+        }
+        enqueue<LAYOUT>(a, wb, qn, inside, id, lane);
     }
 }
 
@@ -528,132 +579,146 @@ __device__ void raster_rounds(const ConvertArgs& a, unsigned char* smem, const f
 // the kernel
 // ------------------------------------------------------------------------------------------
 template <int LAYOUT>
-__global__ void __launch_bounds__(kThreads, 2) convert_kernel(const __grid_constant__ ConvertArgs a) {
-    using LT = LayoutTraits<LAYOUT>;
-    constexpr int kPitch = LT::kStagePitch;
+__global__ void __launch_bounds__(Cfg<LAYOUT>::kWarps * 32, 1) convert_kernel(const __grid_constant__ ConvertArgs a) {
+    using C = Cfg<LAYOUT>;
     extern __shared__ __align__(128) unsigned char smem[];
-    float4* tri_buf[2] = {reinterpret_cast<float4*>(smem + SmemLayout::kTriIn),
-                          reinterpret_cast<float4*>(smem + SmemLayout::kTriIn + kBatch * kTriBytes)};
-    TriRaster* rast = reinterpret_cast<TriRaster*>(smem + SmemLayout::kRast);
-    TriFrag* frag = reinterpret_cast<TriFrag*>(smem + SmemLayout::kFrag);
-    uint32_t* prefix = reinterpret_cast<uint32_t*>(smem + SmemLayout::kPrefix);
-    Misc* misc = reinterpret_cast<Misc*>(smem + SmemLayout::misc(kPitch));
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpBlock<LAYOUT>& wb = *reinterpret_cast<WarpBlock<LAYOUT>*>(smem + (size_t)warp * sizeof(WarpBlock<LAYOUT>));
     const unsigned char* tri_bytes = reinterpret_cast<const unsigned char*>(a.tris);
 
-    auto issue = [&](int stage, uint32_t b) {  // thread 0 only
-        const uint32_t ntri = min((uint32_t)kBatch, a.tri_count - b * kBatch);
-        const uint32_t bytes = ntri * kTriBytes;
-        fence_proxy_async();
-        mbar_arrive_expect_tx(&misc->bar[stage], bytes);
-        tma_load_1d(tri_buf[stage], tri_bytes + ((size_t)a.tri_first + (size_t)b * kBatch) * kTriBytes, bytes,
-                    &misc->bar[stage]);
-    };
-
-    if (tid == 0) {
-        mbar_init(&misc->bar[0], 1);
-        mbar_init(&misc->bar[1], 1);
+    if (lane == 0) {
+        mbar_init(&wb.bar, 1);
         fence_barrier_init();
-        const uint32_t b = atomicAdd(&a.sched[0], 1u);
-        misc->batch[0] = (int)min(b, a.n_batches);
-        if (b < a.n_batches) issue(0, b);
     }
-    __syncthreads();
+    __syncwarp();
+    uint32_t phase = 0, qn = 0;
 
-    int stage = 0;
-    uint32_t phase[2] = {0, 0};
+    // ---- work units ---------------------------------------------------------------------------
     while (true) {
-        const uint32_t b = (uint32_t)misc->batch[stage];
-        if (b >= a.n_batches) break;
-        if (tid == 0) {  // claim + prefetch the next batch into the idle buffer
-            const uint32_t nb = atomicAdd(&a.sched[0], 1u);
-            misc->batch[stage ^ 1] = (int)min(nb, a.n_batches);
-            if (nb < a.n_batches) issue(stage ^ 1, nb);
+        uint32_t unit = 0;
+        if (lane == 0) unit = atomicAdd(&a.sched[0], 1u);
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        if (unit >= a.n_units) break;
+        const uint32_t t0 = unit * a.unit_tris;
+        const uint32_t ntri = min(a.unit_tris, a.tri_count - t0);
+        if (lane == 0) {
+            const uint32_t bytes = ntri * kTriBytes;
+            fence_proxy_async();
+            mbar_arrive_expect_tx(&wb.bar, bytes);
+            tma_load_1d(wb.tri, tri_bytes + ((size_t)a.tri_first + t0) * kTriBytes, bytes, &wb.bar);
         }
-        mbar_wait(&misc->bar[stage], phase[stage]);
-        phase[stage] ^= 1;
+        mbar_wait(&wb.bar, phase);
+        phase ^= 1;
 
-        const uint32_t ntri = min((uint32_t)kBatch, a.tri_count - b * kBatch);
-        const float4* tin = tri_buf[stage];
-        // ---- per-triangle stage ----------------------------------------------------------------
+        // per-triangle stage: one lane per triangle
         uint32_t cnt = 0;
-        if (tid < kBatch) {
-            if ((uint32_t)tid < ntri) {
-                const uint32_t tg = a.tri_first + b * kBatch + tid;
-                cnt = setup_triangle<LAYOUT>(tin + tid * 9, tg, a, rast[tid], frag[tid]);
-                if (cnt > kBigCand) {  // defer: push chunks to the global queue
-                    const uint32_t nch = (cnt + kChunkCand - 1) / kChunkCand;
-                    uint32_t old = a.sched[2];
-                    bool ok = false;
-                    while (old + nch <= a.queue_cap) {
-                        const uint32_t prev = atomicCAS(&a.sched[2], old, old + nch);
-                        if (prev == old) { ok = true; break; }
-                        old = prev;
-                    }
-                    if (ok) {
-                        for (uint32_t i = 0; i < nch; ++i) a.queue[old + i] = make_uint2(tg, i);
-                        __threadfence();
-                        cnt = 0;
-                    }
+        if ((uint32_t)lane < ntri) cnt = setup_triangle<LAYOUT>(wb.tri + lane * 9, a.tri_first + t0 + lane, a, wb.rast[lane], wb.frag[lane]);
+
+        // classify: small (lane-per-triangle, int32), medium (warp-per-triangle), big (deferred)
+        int e0 = 0, e1 = 0, e2 = 0, a0 = 0, a1 = 0, a2 = 0, r0 = 0, r1 = 0, r2 = 0, w = 1, bx = 0, by = 0;
+        bool small = false;
+        if (cnt) {
+            const TriRaster& tr = wb.rast[lane];
+            w = tr.w; bx = tr.x0; by = tr.y0;
+            const int h = tr.h;
+            a0 = tr.A[0]; a1 = tr.A[1]; a2 = tr.A[2];
+            const int b0 = tr.B[0], b1 = tr.B[1], b2 = tr.B[2];
+            // E at the box origin, with the ownership bias folded in: inside <=> all E' >= 0
+            const long long E0 = tr.C[0] + (long long)a0 * bx + (long long)b0 * by - ((tr.incl & 1u) ? 0 : 1);
+            const long long E1 = tr.C[1] + (long long)a1 * bx + (long long)b1 * by - ((tr.incl & 2u) ? 0 : 1);
+            const long long E2 = tr.C[2] + (long long)a2 * bx + (long long)b2 * by - ((tr.incl & 4u) ? 0 : 1);
+            const long long lim = 0x7fffffffll;
+            const long long s0 = llabs(E0) + (long long)(w - 1) * abs(a0) + (long long)(h - 1) * abs(b0);
+            const long long s1 = llabs(E1) + (long long)(w - 1) * abs(a1) + (long long)(h - 1) * abs(b1);
+            const long long s2 = llabs(E2) + (long long)(w - 1) * abs(a2) + (long long)(h - 1) * abs(b2);
+            small = cnt <= kSmallCand && s0 < lim && s1 < lim && s2 < lim;
+            if (small) {
+                e0 = (int)E0; e1 = (int)E1; e2 = (int)E2;
+                r0 = b0 - (w - 1) * a0; r1 = b1 - (w - 1) * a1; r2 = b2 - (w - 1) * a2;  // step to the next row's first pixel
+            } else if (cnt > kBigCand) {  // defer: push chunks to the global queue
+                const uint32_t nch = (cnt + kChunkCand - 1) / kChunkCand;
+                uint32_t old = *reinterpret_cast<volatile uint32_t*>(&a.sched[2]);
+                bool ok = false;
+                while (old + nch <= a.queue_cap) {
+                    const uint32_t prev = atomicCAS(&a.sched[2], old, old + nch);
+                    if (prev == old) { ok = true; break; }
+                    old = prev;
+                }
+                if (ok) {
+                    const uint32_t tg = a.tri_first + t0 + lane;
+                    for (uint32_t i = 0; i < nch; ++i) a.queue[old + i] = make_uint2(tg, i);
+                    __threadfence();
+                    cnt = 0;
                 }
             }
-            // inclusive warp scan of cnt over the first 4 warps
-            uint32_t incl = cnt;
+        }
+        __syncwarp();
+
+        // small triangles: every lane walks its own pixel box in lock-step
+        {
+            uint32_t mine = small ? cnt : 0u;
+            uint32_t maxc = mine;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += n;
+            for (int d = 16; d > 0; d >>= 1) maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, d));
+            int col = 0, row = 0;
+            for (uint32_t it = 0; it < maxc; ++it) {
+                const bool inside = it < mine && (e0 | e1 | e2) >= 0;
+                const uint32_t id = ((uint32_t)lane << 24) | ((uint32_t)(by + row) << 12) | (uint32_t)(bx + col);
+                enqueue<LAYOUT>(a, wb, qn, inside, id, lane);
+                if (++col == w) { col = 0; ++row; e0 += r0; e1 += r1; e2 += r2; }
+                else { e0 += a0; e1 += a1; e2 += a2; }
             }
-            if (lane == 31) misc->wsum[warp] = incl;
-            cnt = incl;  // keep inclusive value
         }
-        __syncthreads();
-        if (tid < kBatch) {
-            uint32_t off = 0;
-            for (int w = 0; w < warp; ++w) off += misc->wsum[w];
-            prefix[tid + 1] = off + cnt;
-            if (tid == 0) prefix[0] = 0;
+        // medium triangles: the whole warp covers one triangle at a time
+        {
+            unsigned mm = __ballot_sync(0xffffffffu, cnt != 0 && !small);
+            while (mm) {
+                const int s = __ffs(mm) - 1;
+                mm &= mm - 1;
+                const uint32_t cs = __shfl_sync(0xffffffffu, cnt, s);
+                raster_one<LAYOUT>(a, wb, qn, (uint32_t)s, 0u, cs, lane);
+            }
         }
-        __syncthreads();
-        const uint32_t total = prefix[kBatch];
-        raster_rounds<LAYOUT>(a, smem, tin, kBatch, 0, total);
-        __syncthreads();
-        if (tid == 0) {
+        flush_queue<LAYOUT>(a, wb, qn, lane);
+        qn = 0;
+        __syncwarp();
+        if (lane == 0) {
             __threadfence();
             atomicAdd(&a.sched[1], 1u);
         }
-        stage ^= 1;
     }
 
-    // ---- drain: deferred big triangles, chunk by chunk, all CTAs ----------------------------
-    if (tid == 0) {
-        while (ld_acquire_u32(&a.sched[1]) < a.n_batches) __nanosleep(64);
+    // ---- drain: deferred big triangles, chunk by chunk, all warps ------------------------------
+    if (lane == 0) {
+        while (ld_acquire_u32(&a.sched[1]) < a.n_units) __nanosleep(128);
         __threadfence();
     }
-    __syncthreads();
-    const uint32_t tail = ld_acquire_u32(&a.sched[2]);
+    __syncwarp();
+    uint32_t tail = 0;
+    if (lane == 0) tail = ld_acquire_u32(&a.sched[2]);
+    tail = __shfl_sync(0xffffffffu, tail, 0);
     while (tail) {
-        if (tid == 0) misc->item = atomicAdd(&a.sched[3], 1u);
-        __syncthreads();
-        const uint32_t it = misc->item;
+        uint32_t it = 0;
+        if (lane == 0) it = atomicAdd(&a.sched[3], 1u);
+        it = __shfl_sync(0xffffffffu, it, 0);
         if (it >= tail) break;
         const uint2 item = a.queue[it];
-        if (tid < 9) tri_buf[0][tid] = a.tris[(size_t)item.x * 9 + tid];
-        __syncthreads();
-        if (tid == 0) {
-            const uint32_t c = setup_triangle<LAYOUT>(tri_buf[0], item.x, a, rast[0], frag[0]);
-            prefix[0] = 0;
-            prefix[1] = c;
-        }
-        __syncthreads();
-        const uint32_t c0 = item.y * kChunkCand, c1 = min(prefix[1], c0 + kChunkCand);
-        raster_rounds<LAYOUT>(a, smem, tri_buf[0], 1, c0, c1);
-        __syncthreads();
+        if (lane < 9) wb.tri[lane] = a.tris[(size_t)item.x * 9 + lane];
+        __syncwarp();
+        uint32_t c = 0;
+        if (lane == 0) c = setup_triangle<LAYOUT>(wb.tri, item.x, a, wb.rast[0], wb.frag[0]);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        __syncwarp();
+        const uint32_t c0 = item.y * kChunkCand, c1 = min(c, c0 + kChunkCand);
+        raster_one<LAYOUT>(a, wb, qn, 0u, c0, c1, lane);
+        flush_queue<LAYOUT>(a, wb, qn, lane);
+        qn = 0;
+        __syncwarp();
     }
 
-    // ---- last CTA out publishes the count and re-arms the scheduler for the next launch ------
+    // ---- last CTA out publishes the count and re-arms the scheduler for the next launch ---------
     __syncthreads();
-    if (tid == 0) {
+    if (threadIdx.x == 0) {
         __threadfence();
         const uint32_t done = atomicAdd(&a.sched[4], 1u);
         if (done == gridDim.x - 1) {
@@ -743,8 +808,9 @@ __global__ void ply_rows_kernel(const float4* __restrict__ rec, unsigned long lo
 // launch wrappers used by m2s_api.cu
 // ------------------------------------------------------------------------------------------
 size_t convert_smem_bytes(int layout) {
-    return layout == 0 ? SmemLayout::total(LayoutTraits<0>::kStagePitch) : SmemLayout::total(LayoutTraits<1>::kStagePitch);
+    return layout == 0 ? sizeof(WarpBlock<0>) * Cfg<0>::kWarps : sizeof(WarpBlock<1>) * Cfg<1>::kWarps;
 }
+int convert_warps_per_cta(int layout) { return layout == 0 ? Cfg<0>::kWarps : Cfg<1>::kWarps; }
 
 cudaError_t convert_configure(int layout, int* blocks_per_sm) {
     cudaError_t e;
@@ -752,17 +818,17 @@ cudaError_t convert_configure(int layout, int* blocks_per_sm) {
     if (layout == 0) {
         e = cudaFuncSetAttribute(convert_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, convert_kernel<0>, kThreads, smem);
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, convert_kernel<0>, Cfg<0>::kWarps * 32, smem);
     }
     e = cudaFuncSetAttribute(convert_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, convert_kernel<1>, kThreads, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, convert_kernel<1>, Cfg<1>::kWarps * 32, smem);
 }
 
 cudaError_t convert_launch(int layout, const ConvertArgs& args, int grid, cudaStream_t stream) {
     const size_t smem = convert_smem_bytes(layout);
-    if (layout == 0) convert_kernel<0><<<grid, kThreads, smem, stream>>>(args);
-    else convert_kernel<1><<<grid, kThreads, smem, stream>>>(args);
+    if (layout == 0) convert_kernel<0><<<grid, Cfg<0>::kWarps * 32, smem, stream>>>(args);
+    else convert_kernel<1><<<grid, Cfg<1>::kWarps * 32, smem, stream>>>(args);
     return cudaGetLastError();
 }
 

@@ -4,7 +4,7 @@ Tolerances (stated once, used everywhere):
   coverage (which (triangle, pixel) pairs emit a gaussian) ........ bit-exact (integer edge functions)
   position ........................................................ 1e-5 * bbox diagonal (absolute)
   raw scale / log-scale, quaternion (same sign convention) ........ 1e-5 relative (+1e-7 abs)
-  colour / SH0 / metallic-roughness ............................... 1e-4 abs vs the oracle's fp32 sampler
+  colour / SH0 / opacity (compared as sigmoid(logit)) / metallic-roughness  1e-4 abs vs the oracle's fp32 sampler
                                                                     (2/255 is the bound vs a real GL driver)
   normal (TBN path) ............................................... 1e-3 abs
 """
@@ -22,6 +22,9 @@ NORMAL_TOL = 1e-3  # FMA-order noise is amplified by ill-conditioned TBN bases i
 
 def scene_diag(scene: _abi.Scene) -> float:
     pos = scene.triangles.reshape(-1, 3, 12)[:, :, :3].reshape(-1, 3)
+    if len(pos) == 0:
+        return 1.0
+    pos = pos[np.isfinite(pos).all(axis=1)]
     if len(pos) == 0:
         return 1.0
     return float(np.linalg.norm(pos.max(axis=0) - pos.min(axis=0))) or 1.0
@@ -45,6 +48,12 @@ def _close(a, b, rtol, atol, what):
                              f"{np.nanmax(np.abs(np.where(np.isfinite(a - b), a - b, 0)))}")
 
 
+def _sigmoid(x):
+    x = np.asarray(x, np.float64)
+    with np.errstate(over="ignore"):
+        return 1.0 / (1.0 + np.exp(-x))
+
+
 def assert_records_match(scene: _abi.Scene, layout: int, got, got_keys, want, want_keys):
     """Set comparison: same fragment identities (exact), same values (tolerances above)."""
     assert len(got) == len(want), f"count {len(got)} != {len(want)}"
@@ -66,12 +75,12 @@ def assert_records_match(scene: _abi.Scene, layout: int, got, got_keys, want, wa
         _close(g["rot"], w["rot"], REL_TOL, 1e-6, "rot")
         _close(g["log_scale"], w["log_scale"], REL_TOL, 1e-5, "log_scale")
         _close(g["sh0"], w["sh0"], 0, COLOR_TOL / 0.28209479177387814, "sh0")
-        _close(g["opacity"], w["opacity"], 1e-4, 1e-3, "opacity")
+        _close(_sigmoid(g["opacity"]), _sigmoid(w["opacity"]), 0, COLOR_TOL, "sigmoid(opacity)")
     elif layout in (_abi.LAYOUT_PLY_STANDARD, _abi.LAYOUT_PLY_PBR):
         _close(g["xyz"], w["xyz"], 0, POS_TOL_REL_DIAG * diag, "xyz")
         _close(g["normal"], w["normal"], 0, NORMAL_TOL, "normal")
         _close(g["f_dc"], w["f_dc"], 0, COLOR_TOL / 0.28209479177387814, "f_dc")
-        _close(g["opacity"], w["opacity"], 1e-4, 1e-3, "opacity")
+        _close(_sigmoid(g["opacity"]), _sigmoid(w["opacity"]), 0, COLOR_TOL, "sigmoid(opacity)")
         _close(g["scale"], w["scale"], REL_TOL, 1e-5, "scale")
         _close(g["rot"], w["rot"], REL_TOL, 1e-6, "rot")
         if layout == _abi.LAYOUT_PLY_STANDARD:
