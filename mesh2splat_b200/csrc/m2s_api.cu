@@ -41,7 +41,7 @@ struct m2s_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
-    uint32_t* d_sched = nullptr;             // 8 x u32
+    uint32_t* d_sched = nullptr;             // 8 x 128 B (one scheduler word per cache line)
     unsigned long long* d_counter = nullptr; // running fragment counter
     unsigned long long* d_total = nullptr;   // published count
     uint2* d_queue = nullptr;
@@ -141,7 +141,7 @@ M2S_EXPORT m2s_status m2s_ctx_create(int device, m2s_ctx** out) {
     CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t thresh = UINT64_MAX;  // keep freed blocks cached: uploads in steady state never hit cudaMalloc
     CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
-    CUDA_TRY(cudaMalloc(&c->d_sched, 8 * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&c->d_sched, 8 * 128));
     CUDA_TRY(cudaMalloc(&c->d_counter, sizeof(unsigned long long)));
     CUDA_TRY(cudaMalloc(&c->d_total, sizeof(unsigned long long)));
     CUDA_TRY(cudaMalloc(&c->d_queue, (size_t)c->queue_cap * sizeof(uint2)));
@@ -354,7 +354,7 @@ M2S_EXPORT m2s_status m2s_convert_enqueue(m2s_ctx* ctx, const m2s_dscene* s, con
         kout = ctx->d_scratch;
     }
     if (ctx->dirty) {
-        CUDA_TRY(cudaMemsetAsync(ctx->d_sched, 0, 8 * sizeof(uint32_t), stream));
+        CUDA_TRY(cudaMemsetAsync(ctx->d_sched, 0, 8 * 128, stream));
         CUDA_TRY(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), stream));
         ctx->dirty = false;
     }
@@ -427,8 +427,25 @@ M2S_EXPORT m2s_status m2s_convert_host(m2s_ctx* ctx, const m2s_scene* sc, const 
     const uint32_t stride = m2s_record_stride(p->layout);
     if (!stride) { set_error("m2s_convert_host: unknown layout"); return M2S_E_INVALID; }
     CUDA_TRY(cudaSetDevice(ctx->device));
+    // Upload only the maps this layout consumes: PACKED56 carries neither normal nor metallic/roughness,
+    // the standard .ply row no metallic/roughness — their texels would cross PCIe for nothing.
+    const bool need_normal = p->layout != M2S_LAYOUT_PACKED56;
+    const bool need_mr = p->layout == M2S_LAYOUT_REF96 || p->layout == M2S_LAYOUT_PLY_PBR || p->layout == M2S_LAYOUT_PLY_COMPRESSED;
+    std::vector<m2s_primitive> prims(sc->primitives, sc->primitives + sc->primitive_count);
+    std::vector<m2s_texture> texs;
+    std::vector<int32_t> remap(sc->texture_count, -1);
+    auto use = [&](int32_t& idx, bool needed) {
+        if (idx < 0 || !needed || (uint32_t)idx >= sc->texture_count) { if (idx >= 0 && (uint32_t)idx < sc->texture_count) idx = -1; return; }
+        if (remap[idx] < 0) { remap[idx] = (int32_t)texs.size(); texs.push_back(sc->textures[idx]); }
+        idx = remap[idx];
+    };
+    for (auto& pr : prims) { use(pr.albedo_texture, true); use(pr.normal_texture, need_normal); use(pr.metallic_roughness_texture, need_mr); }
+    m2s_scene slim = *sc;
+    slim.primitives = prims.data();
+    slim.textures = texs.data();
+    slim.texture_count = (uint32_t)texs.size();
     m2s_dscene* ds = nullptr;
-    m2s_status st = m2s_scene_upload(ctx, sc, &ds);
+    m2s_status st = m2s_scene_upload(ctx, &slim, &ds);
     if (st != M2S_OK) return st;
     st = grow(ctx, &ctx->d_out, &ctx->out_bytes, std::max<uint64_t>(out_capacity, 1) * stride);
     if (st == M2S_OK && h_keys) st = grow(ctx, (void**)&ctx->d_keys, &ctx->keys_bytes, std::max<uint64_t>(out_capacity, 1) * 8);

@@ -60,7 +60,8 @@ struct ConvertArgs {
                                        // zero at launch, re-zeroed by the last CTA
     unsigned long long* total_out;     // receives the final count (last CTA out)
     // scheduling state (zero at launch, re-armed by the last CTA)
-    uint32_t* sched;                   // [0] unit counter [1] units done [2] queue tail [3] queue head [4] CTAs finished
+    uint32_t* sched;                   // 5 words, 128 B apart: unit counter, units past set-up, queue tail, queue head,
+                                       // CTAs finished
     uint32_t unit_tris;                // triangles per work unit (<= 32), chosen by the host for balance
     uint32_t n_units;
     uint2* queue;                      // deferred big-triangle chunks: (triangle, chunk)

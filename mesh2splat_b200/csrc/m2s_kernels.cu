@@ -73,6 +73,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+constexpr int kSchedStride = 32;  // scheduler words live on separate 128-byte lines
+#define SCHED(a, i) ((a).sched + (i) * kSchedStride)
+__device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -119,7 +124,7 @@ struct __align__(16) TriFragT {  // 64 + 16*NMAPS bytes
     unsigned tri;     // global triangle index
     float factor[4];  // u_materialFactor
     float frac[3];    // trilinear blend per map (0 => single level)
-    unsigned pad;
+    unsigned share;   // bit m: map m has the same level sizes as map 0 (=> same footprint and weights)
     TexRef tex[NMAPS];
 };
 
@@ -128,10 +133,12 @@ struct Cfg;
 template <>
 struct Cfg<0> {  // REF96
     static constexpr int kStride = 96;
-    static constexpr int kPitch = 112;  // padded: conflict-free float4 staging writes
+    static constexpr int kPitch = 96;   // = stride: the warp's 32 records are one contiguous 3 KB span
     static constexpr int kMaps = 3;
     static constexpr bool kLogScale = false;
-    static constexpr int kWarps = 14;
+    // warps are allocated registers in groups of 4, so the warp count is a multiple of 4
+    static constexpr int kWarps = 12;
+    static constexpr int kMaxRegs = 168;  // 12 warps * 32 * 168 <= 64 K registers
 };
 template <>
 struct Cfg<1> {  // PACKED56
@@ -140,6 +147,7 @@ struct Cfg<1> {  // PACKED56
     static constexpr int kMaps = 1;
     static constexpr bool kLogScale = true;
     static constexpr int kWarps = 16;
+    static constexpr int kMaxRegs = 128;  // 16 warps * 32 * 128 = 64 K registers
 };
 
 template <int LAYOUT>
@@ -157,7 +165,7 @@ struct __align__(128) WarpBlock {
 // Returns the number of candidate pixels (0 => nothing to rasterise).
 // ------------------------------------------------------------------------------------------
 template <int LAYOUT>
-__device__ uint32_t setup_triangle(const float4* __restrict__ t4, uint32_t tri_global, const ConvertArgs& a,
+__device__ __noinline__ uint32_t setup_triangle(const float4* __restrict__ t4, uint32_t tri_global, const ConvertArgs& a,
                                    TriRaster& tr, TriFragT<Cfg<LAYOUT>::kMaps>& tf) {
     using C = Cfg<LAYOUT>;
     tr.w = 0; tr.h = 0; tr.x0 = 0; tr.y0 = 0; tr.incl = 0; tr.inv_area = 0.f;
@@ -178,7 +186,6 @@ __device__ uint32_t setup_triangle(const float4* __restrict__ t4, uint32_t tri_g
     const float4 q0 = t4[0], q3 = t4[3], q6 = t4[6];
     const float4 q2 = t4[2], q5 = t4[5], q8 = t4[8];
     const f3 P0 = {q0.x, q0.y, q0.z}, P1 = {q3.x, q3.y, q3.z}, P2 = {q6.x, q6.y, q6.z};
-    const float uvx[3] = {q2.z, q5.z, q8.z}, uvy[3] = {q2.w, q5.w, q8.w};
 
     // converterGS.glsl:327-347
     f3 e1 = sub3(P1, P0), e2 = sub3(P2, P0), e3 = sub3(P2, P1);
@@ -287,15 +294,35 @@ __device__ uint32_t setup_triangle(const float4* __restrict__ t4, uint32_t tri_g
     tr.x0 = (unsigned short)x0; tr.y0 = (unsigned short)y0;
     tr.w = (unsigned short)(x1 - x0 + 1); tr.h = (unsigned short)(y1 - y0 + 1);
 
-    // sampler state (GL 4.6 8.14): the per-pixel steps of the mesh uv are constant per triangle, so
-    // lambda, the level pair and the blend fraction are too
-    float dudx = 0.f, dvdx = 0.f, dudy = 0.f, dvdy = 0.f;
+    // Attribute plane equations, in place over the staged vertex data: attr(px,py) = c0 + cx*(px-x0) +
+    // cy*(py-y0), from the barycentric planes lambda_k = E_k / area2 (GL 4.6 14.6.1 eq. 14.9 with w = 1).
+    // Layout afterwards: t4[0..2] = c0 (12 attrs), t4[3..5] = cx, t4[6..8] = cy.
+    float dudx, dvdx, dudy, dvdy;
+    {
+        float lam0[3], ldx[3], ldy[3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const float ca = (float)Ak[k] * ia, cb = (float)Bk[k] * ia;
-        dudx += uvx[k] * ca; dvdx += uvy[k] * ca;
-        dudy += uvx[k] * cb; dvdy += uvy[k] * cb;
+        for (int k = 0; k < 3; ++k) {
+            lam0[k] = __ll2float_rn(tr.C[k] + (long long)Ak[k] * x0 + (long long)Bk[k] * y0) * ia;
+            ldx[k] = (float)Ak[k] * ia;
+            ldy[k] = (float)Bk[k] * ia;
+        }
+        float4* w4 = const_cast<float4*>(t4);
+        const float4 q1 = t4[1], q4 = t4[4], q7 = t4[7];  // every input is in registers before the first store
+#define M2S_PLANE4(L, va, vb, vc) make_float4(L[0] * va.x + L[1] * vb.x + L[2] * vc.x, L[0] * va.y + L[1] * vb.y + L[2] * vc.y, \
+                                              L[0] * va.z + L[1] * vb.z + L[2] * vc.z, L[0] * va.w + L[1] * vb.w + L[2] * vc.w)
+        w4[0] = M2S_PLANE4(lam0, q0, q3, q6); w4[1] = M2S_PLANE4(lam0, q1, q4, q7); w4[2] = M2S_PLANE4(lam0, q2, q5, q8);
+        w4[3] = M2S_PLANE4(ldx, q0, q3, q6); w4[4] = M2S_PLANE4(ldx, q1, q4, q7);
+        w4[6] = M2S_PLANE4(ldy, q0, q3, q6); w4[7] = M2S_PLANE4(ldy, q1, q4, q7);
+        const float4 cxc = M2S_PLANE4(ldx, q2, q5, q8), cyc = M2S_PLANE4(ldy, q2, q5, q8);
+        w4[5] = cxc; w4[8] = cyc;
+#undef M2S_PLANE4
+        dudx = cxc.z; dvdx = cxc.w; dudy = cyc.z; dvdy = cyc.w;  // per-pixel steps of the mesh uv
     }
+
+    // sampler state (GL 4.6 8.14): the steps of the mesh uv are constant per triangle, so lambda, the
+    // level pair and the blend fraction are too
+    unsigned share = 0;
+    TexRef ref0;
 #pragma unroll
     for (int m = 0; m < C::kMaps; ++m) {
         TexRef ref;
@@ -317,33 +344,50 @@ __device__ uint32_t setup_triangle(const float4* __restrict__ t4, uint32_t tri_g
             ref.off0 = t.off[l0]; ref.off1 = t.off[l1];
             ref.w0 = t.w[l0]; ref.h0 = t.h[l0]; ref.w1 = t.w[l1]; ref.h1 = t.h[l1];
         }
+        if (m == 0) ref0 = ref;
+        else if (ti >= 0 && ref0.off0 != 0xffffffffu && ref.w0 == ref0.w0 && ref.h0 == ref0.h0 && ref.w1 == ref0.w1 &&
+                 ref.h1 == ref0.h1 && frac == tf.frac[0])
+            share |= 1u << m;
         tf.tex[m] = ref;
         tf.frac[m] = frac;
     }
+    tf.share = share;
     return (uint32_t)tr.w * (uint32_t)tr.h;
 }
 
 // ------------------------------------------------------------------------------------------
 // sampler: RGBA8 unorm, REPEAT, bilinear within a level, linear between levels
 // ------------------------------------------------------------------------------------------
-struct Bilin {          // addresses + weights of one bilinear footprint
+struct Bilin {          // one bilinear footprint: texel indices relative to the level start + weights
     uint32_t i00, i10, i01, i11;
     float w00, w10, w01, w11;  // already scaled by 1/255
 };
-__device__ __forceinline__ Bilin bilin_setup(uint32_t off, uint32_t W, uint32_t H, float u, float v) {
+// small non-negative int -> float on the FMA pipe (no I2F): 2^23 | v is the float 2^23 + v
+__device__ __forceinline__ float u2f(uint32_t v) { return __uint_as_float(0x4B000000u | v) - 8388608.0f; }
+// floor for |x| < 2^22 on the FMA pipe: round-to-nearest of x - 0.5 via the 1.5*2^23 trick.  At exact
+// integers it may return x - 1 with fraction 1, which selects the same texels with the same weights.
+__device__ __forceinline__ float fast_floor(float x, int& i) {
+    const float t = (x - 0.5f) + 12582912.0f;
+    i = __float_as_int(t) - 0x4B400000;
+    return t - 12582912.0f;
+}
+__device__ __forceinline__ Bilin bilin_setup(uint32_t W, uint32_t H, float u, float v) {
     // REPEAT: wrap in the normalised domain (exact for u in [0,1)), then fix the one-texel overhang
-    u -= floorf(u);
-    v -= floorf(v);
-    const float x = u * (float)W - 0.5f, y = v * (float)H - 0.5f;
-    const float fx = floorf(x), fy = floorf(y);
+    int ix, iy;
+    u -= fast_floor(u, ix);
+    v -= fast_floor(v, iy);
+    const float x = u * u2f(W) - 0.5f, y = v * u2f(H) - 0.5f;
+    const float fx = fast_floor(x, ix), fy = fast_floor(y, iy);
     const float ax = x - fx, ay = y - fy;
-    const int ix = (int)fx, iy = (int)fy;
-    const int x0 = ix < 0 ? (int)W - 1 : (ix >= (int)W ? ix - (int)W : ix);
-    const int y0 = iy < 0 ? (int)H - 1 : (iy >= (int)H ? iy - (int)H : iy);
+    // ix in [-1, W]: wrap, then clamp so that even NaN/huge uv can never index outside the level
+    int x0 = ix < 0 ? ix + (int)W : ix;
+    int y0 = iy < 0 ? iy + (int)H : iy;
+    x0 = min(max(x0, 0), (int)W - 1);
+    y0 = min(max(y0, 0), (int)H - 1);
     const int x1 = x0 + 1 >= (int)W ? 0 : x0 + 1;
     const int y1 = y0 + 1 >= (int)H ? 0 : y0 + 1;
     Bilin b;
-    const uint32_t r0 = off + (uint32_t)y0 * W, r1 = off + (uint32_t)y1 * W;
+    const uint32_t r0 = (uint32_t)y0 * W, r1 = (uint32_t)y1 * W;
     b.i00 = r0 + x0; b.i10 = r0 + x1; b.i01 = r1 + x0; b.i11 = r1 + x1;
     const float k = 1.0f / 255.0f;
     const float bx = 1.0f - ax, by = (1.0f - ay) * k, cy = ay * k;
@@ -374,10 +418,11 @@ __device__ __noinline__ void flush_queue(const ConvertArgs& a, WarpBlock<LAYOUT>
     constexpr int kPitch = C::kPitch;
     if (qn == 0) return;
     __syncwarp();
-    unsigned long long base = 0;
+    unsigned long long base = 0;  // lane 0 reserves; everyone else learns the value at the first copy-out, so the
+                                  // atomic's round trip overlaps the first 32 fragments' work
     if (lane == 0) base = atomicAdd(a.counter, (unsigned long long)qn);
-    base = __shfl_sync(0xffffffffu, base, 0);
     const uint32_t* __restrict__ texb = a.tex_base;
+    const bool want_keys = a.keys != nullptr;
 
     for (uint32_t fb = 0; fb < qn; fb += 32) {
         const uint32_t nfr = min(32u, qn - fb);
@@ -388,41 +433,41 @@ __device__ __noinline__ void flush_queue(const ConvertArgs& a, WarpBlock<LAYOUT>
             const int py = (id >> 12) & 0xfff, px = id & 0xfff;
             const TriRaster& tr = wb.rast[slot];
             const TriFragT<C::kMaps>& tf = wb.frag[slot];
-            float l0, l1, l2;
-            {
-                const float ia = tr.inv_area;
-                l0 = __ll2float_rn(tr.C[0] + (long long)tr.A[0] * px + (long long)tr.B[0] * py) * ia;
-                l1 = __ll2float_rn(tr.C[1] + (long long)tr.A[1] * px + (long long)tr.B[1] * py) * ia;
-                l2 = __ll2float_rn(tr.C[2] + (long long)tr.A[2] * px + (long long)tr.B[2] * py) * ia;
-            }
-            const float4* v = wb.tri + slot * 9;
+            const float dx = u2f((uint32_t)(px - (int)tr.x0)), dy = u2f((uint32_t)(py - (int)tr.y0));
+            const float4* v = wb.tri + slot * 9;  // plane equations: c0 | cx | cy
             // uv first: the texel addresses depend on nothing else
-            const float4 a2 = v[2], b2 = v[5], c2 = v[8];
-            const float u = l0 * a2.z + l1 * b2.z + l2 * c2.z, vv = l0 * a2.w + l1 * b2.w + l2 * c2.w;
+            const float4 c0c = v[2], cxc = v[5], cyc = v[8];
+            const float u = c0c.z + cxc.z * dx + cyc.z * dy, vv = c0c.w + cxc.w * dx + cyc.w * dy;
 
             // ---- issue every texel load of every bound map back to back ----
             uint32_t tx[C::kMaps][8];
             Bilin bl[C::kMaps][2];
             bool has[C::kMaps], two[C::kMaps];
+            uint32_t offs0[C::kMaps], offs1[C::kMaps];
 #pragma unroll
             for (int m = 0; m < C::kMaps; ++m) {
                 const TexRef ref = tf.tex[m];
                 has[m] = ref.off0 != 0xffffffffu;
                 two[m] = has[m] && tf.frac[m] > 0.0f;
-                bl[m][0] = bilin_setup(has[m] ? ref.off0 : 0u, ref.w0, ref.h0, u, vv);
-                bl[m][1] = bilin_setup(ref.off1, ref.w1, ref.h1, u, vv);
+                offs0[m] = has[m] ? ref.off0 : 0u;
+                offs1[m] = ref.off1;
+                if (m == 0 || !((tf.share >> m) & 1u)) {
+                    bl[m][0] = bilin_setup(ref.w0, ref.h0, u, vv);
+                    bl[m][1] = bilin_setup(ref.w1, ref.h1, u, vv);
+                } else { bl[m][0] = bl[0][0]; bl[m][1] = bl[0][1]; }
             }
 #pragma unroll
             for (int m = 0; m < C::kMaps; ++m) {
-                tx[m][0] = has[m] ? __ldg(texb + bl[m][0].i00) : 0u; tx[m][1] = has[m] ? __ldg(texb + bl[m][0].i10) : 0u;
-                tx[m][2] = has[m] ? __ldg(texb + bl[m][0].i01) : 0u; tx[m][3] = has[m] ? __ldg(texb + bl[m][0].i11) : 0u;
-                tx[m][4] = two[m] ? __ldg(texb + bl[m][1].i00) : 0u; tx[m][5] = two[m] ? __ldg(texb + bl[m][1].i10) : 0u;
-                tx[m][6] = two[m] ? __ldg(texb + bl[m][1].i01) : 0u; tx[m][7] = two[m] ? __ldg(texb + bl[m][1].i11) : 0u;
+                const uint32_t o0 = offs0[m], o1 = offs1[m];  // uniform base + 32-bit texel index
+                tx[m][0] = has[m] ? __ldg(texb + (o0 + bl[m][0].i00)) : 0u; tx[m][1] = has[m] ? __ldg(texb + (o0 + bl[m][0].i10)) : 0u;
+                tx[m][2] = has[m] ? __ldg(texb + (o0 + bl[m][0].i01)) : 0u; tx[m][3] = has[m] ? __ldg(texb + (o0 + bl[m][0].i11)) : 0u;
+                tx[m][4] = two[m] ? __ldg(texb + (o1 + bl[m][1].i00)) : 0u; tx[m][5] = two[m] ? __ldg(texb + (o1 + bl[m][1].i10)) : 0u;
+                tx[m][6] = two[m] ? __ldg(texb + (o1 + bl[m][1].i01)) : 0u; tx[m][7] = two[m] ? __ldg(texb + (o1 + bl[m][1].i11)) : 0u;
             }
             // ---- interpolate the remaining varyings while the loads are in flight ----
-            const float4 a0 = v[0], b0 = v[3], c0 = v[6];
-            const float Px = l0 * a0.x + l1 * b0.x + l2 * c0.x, Py = l0 * a0.y + l1 * b0.y + l2 * c0.y,
-                        Pz = l0 * a0.z + l1 * b0.z + l2 * c0.z;
+            const float4 c0a = v[0], cxa = v[3], cya = v[6];
+            const float Px = c0a.x + cxa.x * dx + cya.x * dy, Py = c0a.y + cxa.y * dx + cya.y * dy,
+                        Pz = c0a.z + cxa.z * dx + cya.z * dy;
             float* srec = reinterpret_cast<float*>(wb.stage + lane * kPitch);
 
             // colour (converterFS.glsl:55-62,99)
@@ -443,9 +488,9 @@ __device__ __noinline__ void flush_queue(const ConvertArgs& a, WarpBlock<LAYOUT>
             cr *= tf.factor[0]; cg *= tf.factor[1]; cb *= tf.factor[2]; ca *= tf.factor[3];
 
             if (LAYOUT == 0) {
-                const float Nx = l0 * a0.w + l1 * b0.w + l2 * c0.w;
-                const float4 a1 = v[1], b1 = v[4], c1 = v[7];
-                const float Ny = l0 * a1.x + l1 * b1.x + l2 * c1.x, Nz = l0 * a1.y + l1 * b1.y + l2 * c1.y;
+                const float Nx = c0a.w + cxa.w * dx + cya.w * dy;
+                const float4 c0b = v[1], cxb = v[4], cyb = v[7];
+                const float Ny = c0b.x + cxb.x * dx + cyb.x * dy, Nz = c0b.y + cxb.y * dx + cyb.y * dy;
                 float nx = Nx, ny = Ny, nz = Nz;
                 constexpr int MN = C::kMaps > 1 ? 1 : 0, MM = C::kMaps > 2 ? 2 : 0;
                 if (has[MN]) {  // :64-77 TBN
@@ -458,8 +503,8 @@ __device__ __noinline__ void flush_queue(const ConvertArgs& a, WarpBlock<LAYOUT>
                         my += f * (filt<1>(bl[MN][1], tx[MN][4], tx[MN][5], tx[MN][6], tx[MN][7]) - my);
                         mz += f * (filt<2>(bl[MN][1], tx[MN][4], tx[MN][5], tx[MN][6], tx[MN][7]) - mz);
                     }
-                    const float Tx = l0 * a1.z + l1 * b1.z + l2 * c1.z, Ty = l0 * a1.w + l1 * b1.w + l2 * c1.w;
-                    const float Tz = l0 * a2.x + l1 * b2.x + l2 * c2.x, Tw = l0 * a2.y + l1 * b2.y + l2 * c2.y;
+                    const float Tx = c0b.z + cxb.z * dx + cyb.z * dy, Ty = c0b.w + cxb.w * dx + cyb.w * dy;
+                    const float Tz = c0c.x + cxc.x * dx + cyc.x * dy, Tw = c0c.y + cxc.y * dx + cyc.y * dy;
                     float rx = mx * 2.0f - 1.0f, ry = my * 2.0f - 1.0f, rz = mz * 2.0f - 1.0f;
                     float inv = rsqrtf(rx * rx + ry * ry + rz * rz);
                     rx *= inv; ry *= inv; rz *= inv;
@@ -501,29 +546,34 @@ __device__ __noinline__ void flush_queue(const ConvertArgs& a, WarpBlock<LAYOUT>
                 s2[5] = make_float2(__fdiv_rn(cr - 0.5f, kC0), __fdiv_rn(cg - 0.5f, kC0));
                 s2[6] = make_float2(__fdiv_rn(cb - 0.5f, kC0), inv_sigmoid(ca));
             }
-            key = ((unsigned long long)tf.tri << 24) | ((unsigned long long)py << 12) | (unsigned long long)px;
+            if (want_keys) key = ((unsigned long long)tf.tri << 24) | ((unsigned long long)py << 12) | (unsigned long long)px;
         }
         __syncwarp();
         // ---- coalesced copy-out of this warp's contiguous span --------------------------------
+        if (fb == 0) base = __shfl_sync(0xffffffffu, base, 0);
         const unsigned long long wbase = base + fb;
         uint32_t nvalid = 0;  // converterFS.glsl:48-51: idx >= cap dropped
         if (wbase < a.cap) nvalid = (uint32_t)min((unsigned long long)nfr, a.cap - wbase);
         if (LAYOUT == 0) {
             float4* dst = reinterpret_cast<float4*>(a.out + wbase * 96ull);
+            const float4* src = reinterpret_cast<const float4*>(wb.stage);
+            const uint32_t n16 = nvalid * 6;  // 16-byte pieces to copy
 #pragma unroll
             for (int j = 0; j < 6; ++j) {
-                const uint32_t c = lane + 32 * j, rec = c / 6, part = c - rec * 6;
-                if (rec < nvalid) dst[c] = *reinterpret_cast<const float4*>(wb.stage + rec * kPitch + part * 16);
+                const uint32_t c = lane + 32 * j;
+                if (c < n16) dst[c] = src[c];
             }
         } else {
             float2* dst = reinterpret_cast<float2*>(a.out + wbase * 56ull);
+            const float2* src = reinterpret_cast<const float2*>(wb.stage);
+            const uint32_t n8 = nvalid * 7;  // 8-byte pieces to copy
 #pragma unroll
             for (int j = 0; j < 7; ++j) {
-                const uint32_t c = lane + 32 * j, rec = c / 7, part = c - rec * 7;
-                if (rec < nvalid) dst[c] = *reinterpret_cast<const float2*>(wb.stage + rec * kPitch + part * 8);
+                const uint32_t c = lane + 32 * j;
+                if (c < n8) dst[c] = src[c];
             }
         }
-        if (a.keys && (uint32_t)lane < nvalid) a.keys[wbase + lane] = key;
+        if (want_keys && (uint32_t)lane < nvalid) a.keys[wbase + lane] = key;
         __syncwarp();
     }
 }
@@ -579,7 +629,7 @@ __device__ void raster_one(const ConvertArgs& a, WarpBlock<LAYOUT>& wb, uint32_t
 // the kernel
 // ------------------------------------------------------------------------------------------
 template <int LAYOUT>
-__global__ void __launch_bounds__(Cfg<LAYOUT>::kWarps * 32, 1) convert_kernel(const __grid_constant__ ConvertArgs a) {
+__global__ void __launch_bounds__(Cfg<LAYOUT>::kWarps * 32) __maxnreg__(Cfg<LAYOUT>::kMaxRegs) convert_kernel(const __grid_constant__ ConvertArgs a) {
     using C = Cfg<LAYOUT>;
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -594,18 +644,24 @@ __global__ void __launch_bounds__(Cfg<LAYOUT>::kWarps * 32, 1) convert_kernel(co
     uint32_t phase = 0, qn = 0;
 
     // ---- work units ---------------------------------------------------------------------------
-    while (true) {
-        uint32_t unit = 0;
-        if (lane == 0) unit = atomicAdd(&a.sched[0], 1u);
-        unit = __shfl_sync(0xffffffffu, unit, 0);
-        if (unit >= a.n_units) break;
+    uint32_t unit = 0;
+    if (lane == 0) unit = atomicAdd(SCHED(a, 0), 1u);
+    unit = __shfl_sync(0xffffffffu, unit, 0);
+    while (unit < a.n_units) {
         const uint32_t t0 = unit * a.unit_tris;
         const uint32_t ntri = min(a.unit_tris, a.tri_count - t0);
+        uint32_t next = 0;
         if (lane == 0) {
             const uint32_t bytes = ntri * kTriBytes;
             fence_proxy_async();
             mbar_arrive_expect_tx(&wb.bar, bytes);
             tma_load_1d(wb.tri, tri_bytes + ((size_t)a.tri_first + t0) * kTriBytes, bytes, &wb.bar);
+            // claim the next unit now and pull its triangles into L2: both latencies overlap this unit
+            next = atomicAdd(SCHED(a, 0), 1u);
+            if (next < a.n_units) {
+                const uint32_t nt0 = next * a.unit_tris;
+                prefetch_l2(tri_bytes + ((size_t)a.tri_first + nt0) * kTriBytes, min(a.unit_tris, a.tri_count - nt0) * kTriBytes);
+            }
         }
         mbar_wait(&wb.bar, phase);
         phase ^= 1;
@@ -637,10 +693,10 @@ __global__ void __launch_bounds__(Cfg<LAYOUT>::kWarps * 32, 1) convert_kernel(co
                 r0 = b0 - (w - 1) * a0; r1 = b1 - (w - 1) * a1; r2 = b2 - (w - 1) * a2;  // step to the next row's first pixel
             } else if (cnt > kBigCand) {  // defer: push chunks to the global queue
                 const uint32_t nch = (cnt + kChunkCand - 1) / kChunkCand;
-                uint32_t old = *reinterpret_cast<volatile uint32_t*>(&a.sched[2]);
+                uint32_t old = *reinterpret_cast<volatile uint32_t*>(SCHED(a, 2));
                 bool ok = false;
                 while (old + nch <= a.queue_cap) {
-                    const uint32_t prev = atomicCAS(&a.sched[2], old, old + nch);
+                    const uint32_t prev = atomicCAS(SCHED(a, 2), old, old + nch);
                     if (prev == old) { ok = true; break; }
                     old = prev;
                 }
@@ -653,6 +709,9 @@ __global__ void __launch_bounds__(Cfg<LAYOUT>::kWarps * 32, 1) convert_kernel(co
             }
         }
         __syncwarp();
+        // every chunk this unit defers is in the global queue now (pushers fenced): count the unit as
+        // "past set-up" so idle warps only wait for set-ups in flight, not for whole units
+        if (lane == 0) atomicAdd(SCHED(a, 1), 1u);
 
         // small triangles: every lane walks its own pixel box in lock-step
         {
@@ -660,13 +719,14 @@ __global__ void __launch_bounds__(Cfg<LAYOUT>::kWarps * 32, 1) convert_kernel(co
             uint32_t maxc = mine;
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, d));
-            int col = 0, row = 0;
+            int col = 0;
+            uint32_t id = ((uint32_t)lane << 24) | ((uint32_t)by << 12) | (uint32_t)bx;
+            const uint32_t idrow = (1u << 12) - (uint32_t)(w - 1);  // next row, first column
             for (uint32_t it = 0; it < maxc; ++it) {
                 const bool inside = it < mine && (e0 | e1 | e2) >= 0;
-                const uint32_t id = ((uint32_t)lane << 24) | ((uint32_t)(by + row) << 12) | (uint32_t)(bx + col);
                 enqueue<LAYOUT>(a, wb, qn, inside, id, lane);
-                if (++col == w) { col = 0; ++row; e0 += r0; e1 += r1; e2 += r2; }
-                else { e0 += a0; e1 += a1; e2 += a2; }
+                if (++col == w) { col = 0; id += idrow; e0 += r0; e1 += r1; e2 += r2; }
+                else { ++id; e0 += a0; e1 += a1; e2 += a2; }
             }
         }
         // medium triangles: the whole warp covers one triangle at a time
@@ -682,24 +742,22 @@ __global__ void __launch_bounds__(Cfg<LAYOUT>::kWarps * 32, 1) convert_kernel(co
         flush_queue<LAYOUT>(a, wb, qn, lane);
         qn = 0;
         __syncwarp();
-        if (lane == 0) {
-            __threadfence();
-            atomicAdd(&a.sched[1], 1u);
-        }
+        unit = __shfl_sync(0xffffffffu, next, 0);
     }
 
     // ---- drain: deferred big triangles, chunk by chunk, all warps ------------------------------
     if (lane == 0) {
-        while (ld_acquire_u32(&a.sched[1]) < a.n_units) __nanosleep(128);
+        unsigned ns = 200;
+        while (ld_acquire_u32(SCHED(a, 1)) < a.n_units) { __nanosleep(ns); ns = min(ns * 2u, 2000u); }
         __threadfence();
     }
     __syncwarp();
     uint32_t tail = 0;
-    if (lane == 0) tail = ld_acquire_u32(&a.sched[2]);
+    if (lane == 0) tail = ld_acquire_u32(SCHED(a, 2));
     tail = __shfl_sync(0xffffffffu, tail, 0);
     while (tail) {
         uint32_t it = 0;
-        if (lane == 0) it = atomicAdd(&a.sched[3], 1u);
+        if (lane == 0) it = atomicAdd(SCHED(a, 3), 1u);
         it = __shfl_sync(0xffffffffu, it, 0);
         if (it >= tail) break;
         const uint2 item = a.queue[it];
@@ -720,12 +778,12 @@ __global__ void __launch_bounds__(Cfg<LAYOUT>::kWarps * 32, 1) convert_kernel(co
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        const uint32_t done = atomicAdd(&a.sched[4], 1u);
+        const uint32_t done = atomicAdd(SCHED(a, 4), 1u);
         if (done == gridDim.x - 1) {
             __threadfence();
             *a.total_out = *reinterpret_cast<volatile unsigned long long*>(a.counter);
             *a.counter = 0ull;
-            a.sched[0] = 0; a.sched[1] = 0; a.sched[2] = 0; a.sched[3] = 0; a.sched[4] = 0;
+            *SCHED(a, 0) = 0; *SCHED(a, 1) = 0; *SCHED(a, 2) = 0; *SCHED(a, 3) = 0; *SCHED(a, 4) = 0;
             __threadfence();
         }
     }

@@ -1,0 +1,81 @@
+"""Multi-GPU host logic: triangle sharding and concatenation of per-rank gaussian buffers.
+
+The reference has one atomic counter as its only shared state (converterFS.glsl:34,46); every
+triangle is independent given the per-primitive constants.  So the triangle list is cut into one
+contiguous range per rank (m2s_params.first_triangle / triangle_count), every rank converts its
+range on its own GPU, and the per-rank buffers are concatenated on every rank:
+
+    counts   all_gather of one int64 per rank  -> exclusive scan = global offsets
+    payload  all_gather of max-count-padded buffers, then compaction to offsets (rank-major order)
+
+Works with any torch.distributed backend: NCCL on GPUs, gloo in the CPU tests.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def plan_shards(triangle_count: int, world: int, cost: np.ndarray | None = None) -> list:
+    """Contiguous (first, count) per rank.  With `cost` (per-triangle estimated work, e.g. bbox pixel
+    area) the cuts balance cumulative cost; otherwise triangle counts."""
+    if world < 1:
+        raise ValueError("world must be >= 1")
+    if cost is None or triangle_count == 0:
+        cuts = [(triangle_count * r) // world for r in range(world + 1)]
+    else:
+        c = np.asarray(cost, np.float64)
+        if len(c) != triangle_count:
+            raise ValueError("cost must have one entry per triangle")
+        cum = np.concatenate([[0.0], np.cumsum(np.maximum(c, 0.0) + 1e-9)])
+        targets = cum[-1] * np.arange(world + 1) / world
+        cuts = np.searchsorted(cum, targets, side="left").astype(np.int64)
+        cuts[0], cuts[-1] = 0, triangle_count
+        cuts = np.maximum.accumulate(np.clip(cuts, 0, triangle_count)).tolist()
+    return [(int(cuts[r]), int(cuts[r + 1] - cuts[r])) for r in range(world)]
+
+
+def estimate_cost(triangles: np.ndarray, bbox_min, bbox_max, resolution: int) -> np.ndarray:
+    """Per-triangle candidate-pixel estimate: area of the dominant-axis projection's bounding box on
+    the R x R grid (+1 for the fixed per-triangle set-up)."""
+    t = np.asarray(triangles, np.float32).reshape(-1, 3, 12)[:, :, :3]
+    e1, e2 = t[:, 1] - t[:, 0], t[:, 2] - t[:, 0]
+    n = np.abs(np.cross(e1, e2))
+    axis = np.where((n[:, 0] > n[:, 1]) & (n[:, 0] > n[:, 2]), 0, np.where(n[:, 1] > n[:, 2], 1, 2))
+    ext = t.max(axis=1) - t.min(axis=1)
+    rng = np.asarray(bbox_max, np.float32) - np.asarray(bbox_min, np.float32)
+    ia = np.where(axis == 0, 1, 0)
+    ib = np.where(axis == 2, 1, 2)
+    idx = np.arange(len(t))
+    r = np.maximum(rng[ia], rng[ib])
+    r = np.where(r > 0, r, 1.0)
+    w = ext[idx, ia] / r * resolution + 1.0
+    h = ext[idx, ib] / r * resolution + 1.0
+    return (w * h + 1.0).astype(np.float64)
+
+
+def all_gather_records(local, n_local: int, stride: int, dist, torch, out=None):
+    """Concatenate per-rank record buffers on every rank.
+
+    local: 1-D uint8 tensor holding at least n_local*stride bytes (this rank's gaussians).
+    Returns (buffer, counts): `buffer` holds sum(counts)*stride bytes, rank-major; counts is a list."""
+    world = dist.get_world_size()
+    dev = local.device
+    cnt = torch.tensor([n_local], dtype=torch.int64, device=dev)
+    counts = torch.zeros(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts, cnt)
+    c = [int(x) for x in counts.cpu().tolist()]
+    mx = max(c) if c else 0
+    total = sum(c)
+    if out is None:
+        out = torch.empty(max(1, total) * stride, dtype=torch.uint8, device=dev)
+    if mx == 0:
+        return out[:0], c
+    padded = torch.zeros(mx * stride, dtype=torch.uint8, device=dev)
+    padded[: n_local * stride] = local[: n_local * stride]
+    gathered = torch.empty(world * mx * stride, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(gathered, padded)
+    off = 0
+    for r in range(world):
+        out[off * stride:(off + c[r]) * stride] = gathered[r * mx * stride: r * mx * stride + c[r] * stride]
+        off += c[r]
+    return out[: total * stride], c
