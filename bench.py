@@ -75,41 +75,57 @@ def profiled_traffic(layout_name: str):
 
 
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock + throttle reasons of one GPU from a background thread (NVML, ~1 ms period)
+    while the timed region runs; falls back to one nvidia-smi query if NVML is unavailable."""
 
     def __init__(self, index: int):
-        self.p = None
+        import threading
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
         except Exception:  # noqa: BLE001
-            self.p = None
+            self._nv = None
+
+    def _run(self):
+        nv = self._nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                r = int(get_reasons(self._h))
+                for n, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+            except Exception:  # noqa: BLE001
+                break
+            time.sleep(0.001)
 
     def stop(self) -> dict:
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.p.terminate()
-        try:
-            out, _ = self.p.communicate(timeout=5)
-        except Exception:  # noqa: BLE001
-            self.p.kill()
-            out = ""
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in out.splitlines():
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 7:
-                continue
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join(timeout=2)
+        if self._nv is None or not self.samples:
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+                a, b = [float(x) for x in out.strip().split(",")[:2]]
+                return {"sm_mhz": a, "sm_max_mhz": b, "reasons": [], "samples": 1, "source": "nvidia-smi (after the timed region)"}
+            except Exception:  # noqa: BLE001
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples), "source": "NVML, sampled during the timed region"}
 
 
 def pinned_scene(scene, torch):
@@ -182,9 +198,11 @@ def run_ours(args):
     ctx = Context(local)
     ds = ctx.upload(scene)
     T = scene.triangle_count
-    # shard: contiguous, equal triangle counts (the stand-in's triangles are uniform in size)
-    lo = (T * rank) // world
-    hi = (T * (rank + 1)) // world
+    # shard: contiguous ranges balanced by estimated candidate pixels (mesh2splat_b200/shard.py)
+    from mesh2splat_b200.shard import estimate_cost, plan_shards
+    cost = estimate_cost(scene.triangles, scene.primitives[0].bbox_min, scene.primitives[0].bbox_max, DENSITY)
+    lo, cnt_ = plan_shards(T, world, cost)[rank]
+    hi = lo + cnt_
     cap_total = 6 * DENSITY * DENSITY
     # a dedicated (non-default) stream: everything timed is enqueued on it and the events are recorded on it
     stream = torch.cuda.Stream(dev)
@@ -261,7 +279,11 @@ def run_ours(args):
             rec, _, res = ctx.convert_host(pscene, DENSITY, layout, flags=_abi.FLAG_UNCAPPED, capacity=cap_total, out=h_np, c_scene=cs)
         torch.cuda.synchronize(dev)
         e2e_dt = (time.perf_counter() - t0) / e2e_steps
-        h2d = scene.triangles.nbytes + scene.texture_bytes()
+        # m2s_convert_host uploads the triangles and only the maps the layout consumes
+        used = {p.albedo_texture for p in scene.primitives}
+        if layout != _abi.LAYOUT_PACKED56:
+            used |= {p.normal_texture for p in scene.primitives} | {p.metallic_roughness_texture for p in scene.primitives}
+        h2d = scene.triangles.nbytes + sum(scene.textures[i].nbytes for i in used if i >= 0)
         d2h = int(res.written) * stride + 8
         e2e = {"value": int(res.written) / e2e_dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": e2e_dt * 1e3, "api": "m2s_convert_host (pinned host buffers; upload + mip generation + convert + download)"}
@@ -314,7 +336,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layout", default="packed56", choices=sorted(LAYOUTS))
