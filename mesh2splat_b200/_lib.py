@@ -8,7 +8,7 @@ import os
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libm2s.so")
+LIB_PATH = os.environ.get("M2S_LIB") or os.path.join(_HERE, "libm2s.so")  # M2S_LIB: tuning variants (build.py --out)
 _lib = None
 
 # every symbol include/m2s.h declares (tests check the .so exports all of them)

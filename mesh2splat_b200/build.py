@@ -34,12 +34,15 @@ def _stale() -> bool:
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, out: str | None = None, defs: list | None = None) -> str:
+    """out/defs: build a tuning variant (e.g. defs=['M2S_WARPS_REF96=12','M2S_REGS_REF96=168']) to another file;
+    select it at run time with the M2S_LIB environment variable."""
+    if out is None and not defs and not force and not _stale():
         return OUT
+    out = out or OUT
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     cmd = [_nvcc(), "-std=c++17", "-O3", "-lineinfo", *ARCH, "-shared", "-Xcompiler", "-fPIC,-fvisibility=hidden",
-           "--cudart", "static", "-o", OUT, *srcs]
+           "--cudart", "static", "-o", out, *[f"-D{d}" for d in (defs or [])], *srcs]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -48,8 +51,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed")
     if verbose:
         sys.stderr.write(r.stdout + r.stderr)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    out = None
+    defs = []
+    for a in sys.argv[1:]:
+        if a.startswith("--out="):
+            out = a[6:]
+        if a.startswith("--def="):
+            defs.append(a[6:])
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, out=out, defs=defs))

@@ -12,10 +12,10 @@
 #include "m2s_device.cuh"
 
 namespace m2s {
-size_t convert_smem_bytes(int layout);
 int convert_warps_per_cta(int layout);
-cudaError_t convert_configure(int layout, int* blocks_per_sm);
-cudaError_t convert_launch(int layout, const ConvertArgs& args, int grid, cudaStream_t stream);
+size_t tri_frag_bytes(int layout);
+cudaError_t convert_configure(int layout, int* raster_blocks_per_sm, int* fragment_blocks_per_sm);
+cudaError_t convert_launch(int layout, const ConvertArgs& args, int raster_grid, int fragment_grid, cudaStream_t stream);
 cudaError_t mip_down_launch(const uint32_t* src, uint32_t sw, uint32_t sh, uint32_t* dst, uint32_t dw, uint32_t dh,
                             cudaStream_t stream);
 cudaError_t ply_rows_launch(const void* ref96, unsigned long long count, const unsigned long long* d_count,
@@ -48,12 +48,17 @@ struct m2s_ctx {
     uint32_t queue_cap = 1u << 20;
     unsigned long long* h_total = nullptr;   // pinned
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    int blocks_per_sm[2] = {0, 0};
+    int blocks_per_sm[2] = {0, 0};       // raster kernel (persistent)
+    int frag_blocks_per_sm[2] = {0, 0};  // fragment kernel
     bool dirty = true;                       // scheduler state needs a memset before the next launch
     // scratch owned by the context (grown on demand)
     void* d_scratch = nullptr;  size_t scratch_bytes = 0;   // REF96 staging for the .ply row layouts
     void* d_out = nullptr;      size_t out_bytes = 0;       // convert_host output
     unsigned long long* d_keys = nullptr; size_t keys_bytes = 0;
+    // intermediates between the raster and the fragment kernel
+    void* d_ids = nullptr;      size_t ids_bytes = 0;       // uint2 per fragment
+    void* d_planes = nullptr;   size_t planes_bytes = 0;    // 144 B per triangle of the shard
+    void* d_trifrag = nullptr;  size_t trifrag_bytes = 0;   // TriFragT per triangle of the shard
 };
 
 struct m2s_dscene {
@@ -149,8 +154,8 @@ M2S_EXPORT m2s_status m2s_ctx_create(int device, m2s_ctx** out) {
     CUDA_TRY(cudaEventCreate(&c->ev0));
     CUDA_TRY(cudaEventCreate(&c->ev1));
     for (int l = 0; l < 2; ++l) {
-        CUDA_TRY(convert_configure(l, &c->blocks_per_sm[l]));
-        if (c->blocks_per_sm[l] < 1) { set_error("conversion kernel does not fit on this device"); return M2S_E_CUDA; }
+        CUDA_TRY(convert_configure(l, &c->blocks_per_sm[l], &c->frag_blocks_per_sm[l]));
+        if (c->blocks_per_sm[l] < 1 || c->frag_blocks_per_sm[l] < 1) { set_error("conversion kernel does not fit on this device"); return M2S_E_CUDA; }
     }
     *out = c;
     return M2S_OK;
@@ -163,6 +168,9 @@ M2S_EXPORT void m2s_ctx_destroy(m2s_ctx* c) {
     if (c->d_scratch) cudaFreeAsync(c->d_scratch, c->stream);
     if (c->d_out) cudaFreeAsync(c->d_out, c->stream);
     if (c->d_keys) cudaFreeAsync(c->d_keys, c->stream);
+    if (c->d_ids) cudaFreeAsync(c->d_ids, c->stream);
+    if (c->d_planes) cudaFreeAsync(c->d_planes, c->stream);
+    if (c->d_trifrag) cudaFreeAsync(c->d_trifrag, c->stream);
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_sched); cudaFree(c->d_counter); cudaFree(c->d_total); cudaFree(c->d_queue);
     cudaFreeHost(c->h_total);
@@ -353,6 +361,13 @@ M2S_EXPORT m2s_status m2s_convert_enqueue(m2s_ctx* ctx, const m2s_dscene* s, con
         if (st != M2S_OK) return st;
         kout = ctx->d_scratch;
     }
+    if (reinterpret_cast<uintptr_t>(kout) & 15u) { set_error("m2s_convert: the output buffer must be 16-byte aligned"); return M2S_E_INVALID; }
+    {   // scratch between the two kernels (grown on demand, kept by the context)
+        m2s_status st = grow(ctx, &ctx->d_ids, &ctx->ids_bytes, std::max<uint64_t>(cap, 1) * sizeof(uint2));
+        if (st == M2S_OK) st = grow(ctx, &ctx->d_planes, &ctx->planes_bytes, std::max<uint64_t>(count, 1) * (size_t)kTriBytes);
+        if (st == M2S_OK) st = grow(ctx, &ctx->d_trifrag, &ctx->trifrag_bytes, std::max<uint64_t>(count, 1) * tri_frag_bytes(klayout));
+        if (st != M2S_OK) return st;
+    }
     if (ctx->dirty) {
         CUDA_TRY(cudaMemsetAsync(ctx->d_sched, 0, 8 * 128, stream));
         CUDA_TRY(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), stream));
@@ -368,6 +383,9 @@ M2S_EXPORT m2s_status m2s_convert_enqueue(m2s_ctx* ctx, const m2s_dscene* s, con
     a.R = p->resolution;
     a.half_R = (float)p->resolution * 0.5f;
     a.mult = p->gaussian_std / (float)p->resolution;
+    a.frag_ids = (uint2*)ctx->d_ids;
+    a.tri_planes = (const float4*)ctx->d_planes;
+    a.tri_frag = (unsigned char*)ctx->d_trifrag;
     a.out = (uint8_t*)kout;
     a.cap = cap;
     a.keys = (unsigned long long*)d_keys;
@@ -386,7 +404,8 @@ M2S_EXPORT m2s_status m2s_convert_enqueue(m2s_ctx* ctx, const m2s_dscene* s, con
     }
     a.queue = ctx->d_queue;
     a.queue_cap = ctx->queue_cap;
-    cudaError_t e = convert_launch(klayout, a, grid, stream);
+    const int fgrid = ctx->sm_count * ctx->frag_blocks_per_sm[klayout];
+    cudaError_t e = convert_launch(klayout, a, grid, fgrid, stream);
     if (e != cudaSuccess) { ctx->dirty = true; set_error(std::string("convert launch: ") + cudaGetErrorString(e)); return M2S_E_CUDA; }
     if (ply_rows) {
         // the count is only known on the device here: the encoder reads it and stops at min(cap, total)

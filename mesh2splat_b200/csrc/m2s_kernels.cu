@@ -1,36 +1,52 @@
 // m2s_kernels.cu — the conversion pass as hand-written sm_100a CUDA.
 //
-// ONE persistent kernel replaces the reference's geometry shader, fixed-function rasteriser,
-// fragment shader and SSBO atomic append (converter{GS,FS}.glsl, ConversionPass.cpp:114-116).
+// Two kernels on one stream replace the reference's geometry shader, fixed-function rasteriser,
+// fragment shader and SSBO atomic append (converter{GS,FS}.glsl, ConversionPass.cpp:114-116); the data
+// between them (8-byte fragment ids, 224-256 B per-triangle records) stays in the 126 MB L2.
 //
-// Every WARP is an autonomous pipeline with its own slice of shared memory (no __syncthreads in
-// the steady state, so warps sit in different stages and cover each other's latencies):
-//
-//   claim a work unit (<= 32 consecutive triangles) from a global counter
+// raster_kernel (persistent, one CTA per SM, every WARP an autonomous pipeline, no __syncthreads in the
+// steady state):
+//   claim a work unit (<= 32 consecutive triangles) from a global counter; claim the next one at once
+//     and prefetch its bytes into L2
 //   TMA (cp.async.bulk + mbarrier complete_tx) stages the unit's 144 B/triangle into shared memory
 //   per-triangle stage, one LANE per triangle (converterGS.glsl:326-443): longest edge, face normal,
-//     dominant axis, orthographic uv, quaternion, UV->3D Jacobian scale; then rasteriser set-up:
-//     24.8 fixed-point window coords, int64 edge functions, top-left ownership bits, candidate pixel
-//     box, and the triangle's fully resolved sampler state (mip level pair, blend fraction, level
-//     base offsets and sizes) so the fragment stage never chases descriptors in global memory
+//     dominant axis, orthographic uv, quaternion, UV->3D Jacobian scale; rasteriser set-up: 24.8
+//     fixed-point window coords, int64 edge functions, top-left ownership bits, candidate pixel box;
+//     attribute plane equations in place over the staged vertices; the triangle's resolved sampler
+//     state (mip level pair, blend fraction, level offsets and sizes)
+//   the unit's records leave shared memory as two TMA bulk stores (cp.async.bulk.global.shared::cta)
 //   coverage, three regimes by candidate-pixel count:
 //     small  (<= 64, fits int32)  lane-per-triangle, lock-step incremental edge functions
 //     medium (<= 1024)            warp-per-triangle, 32 candidates per step, int64 edge functions
 //     big                         pushed as 512-candidate chunks to a global queue and rasterised by
-//                                 ALL warps of the grid after the units are done
-//     survivors are ballot-compacted into the warp's fragment queue (512 ids)
-//   flush: ONE global atomicAdd reserves the output range for up to 512 fragments (the reference
-//     does one atomicCounterIncrement per fragment), then the fragment stage
-//     (converterFS.glsl:44-104) runs on full warps: barycentric interpolation from the staged
-//     vertex data, all texel loads of all maps issued back to back, trilinear filter, TBN normal,
-//     record encode; records are transposed through shared memory so the warp writes one
-//     contiguous 32*stride-byte span with vector stores.
+//                                 ALL warps of the grid after the units are set up
+//     survivors are ballot-compacted into the warp's queue; one global atomicAdd per <= 512 fragments
+//     reserves the output range (the reference: one atomicCounterIncrement per fragment) and the ids
+//     are written coalesced.  Fragment i of the id list IS output record i.
+// fragment_kernel (converterFS.glsl:44-104; lean registers, high occupancy, grid-stride):
+//   a warp takes 32 consecutive fragments: 2 FFMA per attribute from the plane equations, all texel
+//   loads of all bound maps issued back to back, trilinear filter on the FMA pipe (u8->f32 by
+//   PRMT+FADD), TBN normal, encode; the 32 records are transposed through shared memory and written as
+//   one contiguous, 16-byte-vectorised span.
 //
 // Bit-exactness: every float operation that feeds a DECISION (edge ordering, dominant axis,
 // fixed-point snapping => coverage) is written with __f*_rn intrinsics in the operation order of
 // the oracle (and of GLM, which the reference's GLSL-as-C++ build uses), so coverage is bit-exact.
 // Per-fragment values may use FMA contraction and are compared with a tolerance.
 #include "m2s_device.cuh"
+
+// resident warps per SM / register cap per layout (warps are a multiple of 4: register allocation granularity)
+#ifndef M2S_WARPS_REF96
+#define M2S_WARPS_REF96 16
+#define M2S_REGS_REF96 128
+#endif
+#ifndef M2S_WARPS_PACKED56
+#define M2S_WARPS_PACKED56 16
+#define M2S_REGS_PACKED56 128
+#endif
+#ifndef M2S_FRAG_THREADS
+#define M2S_FRAG_THREADS 256
+#endif
 
 namespace m2s {
 
@@ -73,6 +89,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+__device__ __forceinline__ void tma_store_1d(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 constexpr int kSchedStride = 32;  // scheduler words live on separate 128-byte lines
 #define SCHED(a, i) ((a).sched + (i) * kSchedStride)
 __device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
@@ -124,7 +147,8 @@ struct __align__(16) TriFragT {  // 64 + 16*NMAPS bytes
     unsigned tri;     // global triangle index
     float factor[4];  // u_materialFactor
     float frac[3];    // trilinear blend per map (0 => single level)
-    unsigned share;   // bit m: map m has the same level sizes as map 0 (=> same footprint and weights)
+    unsigned meta;    // bits 0-2: map m has the same level sizes as map 0 (=> same footprint and weights);
+                      // bits 4-15: x0, bits 16-27: y0 of the candidate pixel box
     TexRef tex[NMAPS];
 };
 
@@ -137,8 +161,8 @@ struct Cfg<0> {  // REF96
     static constexpr int kMaps = 3;
     static constexpr bool kLogScale = false;
     // warps are allocated registers in groups of 4, so the warp count is a multiple of 4
-    static constexpr int kWarps = 12;
-    static constexpr int kMaxRegs = 168;  // 12 warps * 32 * 168 <= 64 K registers
+    static constexpr int kWarps = M2S_WARPS_REF96;
+    static constexpr int kMaxRegs = M2S_REGS_REF96;   // warps * 32 * regs <= 64 K registers
 };
 template <>
 struct Cfg<1> {  // PACKED56
@@ -146,17 +170,15 @@ struct Cfg<1> {  // PACKED56
     static constexpr int kPitch = 56;
     static constexpr int kMaps = 1;
     static constexpr bool kLogScale = true;
-    static constexpr int kWarps = 16;
-    static constexpr int kMaxRegs = 128;  // 16 warps * 32 * 128 = 64 K registers
+    static constexpr int kWarps = M2S_WARPS_PACKED56;
+    static constexpr int kMaxRegs = M2S_REGS_PACKED56;
 };
 
 template <int LAYOUT>
 struct __align__(128) WarpBlock {
     float4 tri[kUnitTris * 9];                   // 4608 B, TMA destination
-    TriRaster rast[kUnitTris];                   // 2048 B
     TriFragT<Cfg<LAYOUT>::kMaps> frag[kUnitTris];
     uint32_t queue[kQueue];                      // 2048 B: slot << 24 | y << 12 | x
-    unsigned char stage[32 * Cfg<LAYOUT>::kPitch];
     uint64_t bar;
 };
 
@@ -351,7 +373,7 @@ __device__ __noinline__ uint32_t setup_triangle(const float4* __restrict__ t4, u
         tf.tex[m] = ref;
         tf.frac[m] = frac;
     }
-    tf.share = share;
+    tf.meta = share | ((unsigned)x0 << 4) | ((unsigned)y0 << 16);
     return (uint32_t)tr.w * (uint32_t)tr.h;
 }
 
@@ -410,33 +432,321 @@ __device__ __forceinline__ float inv_sigmoid(float a) {  // utils.hpp:270
 }
 
 // ------------------------------------------------------------------------------------------
-// flush: reserve the output range, run the fragment stage over the warp's queue, write records
+// flush: reserve the output range and write the warp's fragment ids (coalesced)
 // ------------------------------------------------------------------------------------------
 template <int LAYOUT>
-__device__ __noinline__ void flush_queue(const ConvertArgs& a, WarpBlock<LAYOUT>& wb, uint32_t qn, int lane) {
-    using C = Cfg<LAYOUT>;
-    constexpr int kPitch = C::kPitch;
+__device__ __forceinline__ void flush_ids(const ConvertArgs& a, WarpBlock<LAYOUT>& wb, uint32_t qn, int lane) {
     if (qn == 0) return;
     __syncwarp();
-    unsigned long long base = 0;  // lane 0 reserves; everyone else learns the value at the first copy-out, so the
-                                  // atomic's round trip overlaps the first 32 fragments' work
+    unsigned long long base = 0;
     if (lane == 0) base = atomicAdd(a.counter, (unsigned long long)qn);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (uint32_t i = lane; i < qn; i += 32) {
+        const uint32_t id = wb.queue[i];
+        const unsigned long long idx = base + i;
+        if (idx < a.cap)  // converterFS.glsl:48-51: the counter keeps counting, records beyond the cap are dropped
+            a.frag_ids[idx] = make_uint2(wb.frag[id >> 24].tri, id & 0xffffffu);
+    }
+    __syncwarp();
+}
+
+// enqueue the lanes whose `inside` is set; flush when the queue could overflow on the next step
+template <int LAYOUT>
+__device__ __forceinline__ void enqueue(const ConvertArgs& a, WarpBlock<LAYOUT>& wb, uint32_t& qn, bool inside, uint32_t id,
+                                        int lane) {
+    const unsigned m = __ballot_sync(0xffffffffu, inside);
+    if (m) {
+        if (inside) wb.queue[qn + __popc(m & ((1u << lane) - 1u))] = id;
+        qn += __popc(m);
+        if (qn > kQueue - 32) {
+            flush_ids<LAYOUT>(a, wb, qn, lane);
+            qn = 0;
+        }
+    }
+}
+
+// warp-per-triangle coverage of candidates [c0, c1) of the triangle in `slot` (int64 edge functions)
+template <int LAYOUT>
+__device__ void raster_one(const ConvertArgs& a, WarpBlock<LAYOUT>& wb, uint32_t& qn, uint32_t slot, uint32_t c0, uint32_t c1,
+                           int lane, const TriRaster& mine) {
+    // the raster state lives in the registers of lane `slot`: broadcast it
+    const unsigned full = 0xffffffffu;
+    const int src = (int)slot;
+    const uint32_t w = __shfl_sync(full, (uint32_t)mine.w, src);
+    const float rcp = 1.0f / (float)w;
+    const long long C0 = __shfl_sync(full, mine.C[0], src), C1 = __shfl_sync(full, mine.C[1], src), C2 = __shfl_sync(full, mine.C[2], src);
+    const int A0 = __shfl_sync(full, mine.A[0], src), A1 = __shfl_sync(full, mine.A[1], src), A2 = __shfl_sync(full, mine.A[2], src);
+    const int B0 = __shfl_sync(full, mine.B[0], src), B1 = __shfl_sync(full, mine.B[1], src), B2 = __shfl_sync(full, mine.B[2], src);
+    const unsigned incl = __shfl_sync(full, mine.incl, src);
+    const int bx = __shfl_sync(full, (int)mine.x0, src), by = __shfl_sync(full, (int)mine.y0, src);
+    for (uint32_t cb = c0; cb < c1; cb += 32) {
+        const uint32_t c = cb + lane;
+        bool inside = false;
+        uint32_t id = 0;
+        if (c < c1) {
+            uint32_t row = (uint32_t)((float)c * rcp);  // c < 2^24: exact in fp32, quotient off by at most 1
+            int col = (int)(c - row * w);
+            if (col < 0) { --row; col += (int)w; }
+            else if (col >= (int)w) { ++row; col -= (int)w; }
+            const int px = bx + col, py = by + (int)row;
+            const long long E0 = C0 + (long long)A0 * px + (long long)B0 * py;
+            const long long E1 = C1 + (long long)A1 * px + (long long)B1 * py;
+            const long long E2 = C2 + (long long)A2 * px + (long long)B2 * py;
+            inside = (E0 > 0 || (E0 == 0 && (incl & 1u))) && (E1 > 0 || (E1 == 0 && (incl & 2u))) &&
+                     (E2 > 0 || (E2 == 0 && (incl & 4u)));
+            id = (slot << 24) | ((uint32_t)py << 12) | (uint32_t)px;
+        }
+        enqueue<LAYOUT>(a, wb, qn, inside, id, lane);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------
+template <int LAYOUT>
+__global__ void __launch_bounds__(Cfg<LAYOUT>::kWarps * 32) __maxnreg__(Cfg<LAYOUT>::kMaxRegs) raster_kernel(const __grid_constant__ ConvertArgs a) {
+    using C = Cfg<LAYOUT>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpBlock<LAYOUT>& wb = *reinterpret_cast<WarpBlock<LAYOUT>*>(smem + (size_t)warp * sizeof(WarpBlock<LAYOUT>));
+    const unsigned char* tri_bytes = reinterpret_cast<const unsigned char*>(a.tris);
+
+    if (lane == 0) {
+        mbar_init(&wb.bar, 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    uint32_t phase = 0, qn = 0;
+
+    // ---- work units ---------------------------------------------------------------------------
+    // the first unit of every warp is static (unit = global warp id): no atomic, and nobody can grab two
+    // units while a neighbour gets none; further units are claimed dynamically one unit ahead
+    const uint32_t nwarps_total = gridDim.x * (blockDim.x >> 5);
+    uint32_t unit = blockIdx.x + gridDim.x * warp;  // warp w of every CTA before warp w+1 of any: SMs fill evenly
+    while (unit < a.n_units) {
+        const uint32_t t0 = unit * a.unit_tris;
+        const uint32_t ntri = min(a.unit_tris, a.tri_count - t0);
+        uint32_t next = 0xffffffffu;
+        if (lane == 0) {
+            const uint32_t bytes = ntri * kTriBytes;
+            tma_store_wait_read();  // the previous unit's record stores have finished reading this slice
+            fence_proxy_async();
+            mbar_arrive_expect_tx(&wb.bar, bytes);
+            tma_load_1d(wb.tri, tri_bytes + ((size_t)a.tri_first + t0) * kTriBytes, bytes, &wb.bar);
+            if (a.n_units > nwarps_total) {  // more units than warps: claim the next one now, pull its bytes into L2
+                next = nwarps_total + atomicAdd(SCHED(a, 0), 1u);
+                if (next < a.n_units) {
+                    const uint32_t nt0 = next * a.unit_tris;
+                    prefetch_l2(tri_bytes + ((size_t)a.tri_first + nt0) * kTriBytes, min(a.unit_tris, a.tri_count - nt0) * kTriBytes);
+                }
+            }
+        }
+        mbar_wait(&wb.bar, phase);
+        phase ^= 1;
+
+        // per-triangle stage: one lane per triangle
+        uint32_t cnt = 0;
+        TriRaster tr;  // raster state stays with the lane that owns the triangle
+        tr.w = 0; tr.h = 0; tr.x0 = 0; tr.y0 = 0; tr.incl = 0;
+        tr.A[0] = tr.A[1] = tr.A[2] = tr.B[0] = tr.B[1] = tr.B[2] = 0; tr.C[0] = tr.C[1] = tr.C[2] = 0;
+        if ((uint32_t)lane < ntri) cnt = setup_triangle<LAYOUT>(wb.tri + lane * 9, a.tri_first + t0 + lane, a, tr, wb.frag[lane]);
+
+        // classify: small (lane-per-triangle, int32), medium (warp-per-triangle), big (deferred)
+        int e0 = 0, e1 = 0, e2 = 0, a0 = 0, a1 = 0, a2 = 0, r0 = 0, r1 = 0, r2 = 0, w = 1, bx = 0, by = 0;
+        bool small = false, deferred = false;
+        if (cnt) {
+            w = tr.w; bx = tr.x0; by = tr.y0;
+            const int h = tr.h;
+            a0 = tr.A[0]; a1 = tr.A[1]; a2 = tr.A[2];
+            const int b0 = tr.B[0], b1 = tr.B[1], b2 = tr.B[2];
+            // E at the box origin, with the ownership bias folded in: inside <=> all E' >= 0
+            const long long E0 = tr.C[0] + (long long)a0 * bx + (long long)b0 * by - ((tr.incl & 1u) ? 0 : 1);
+            const long long E1 = tr.C[1] + (long long)a1 * bx + (long long)b1 * by - ((tr.incl & 2u) ? 0 : 1);
+            const long long E2 = tr.C[2] + (long long)a2 * bx + (long long)b2 * by - ((tr.incl & 4u) ? 0 : 1);
+            const long long lim = 0x7fffffffll;
+            const long long s0 = llabs(E0) + (long long)(w - 1) * abs(a0) + (long long)(h - 1) * abs(b0);
+            const long long s1 = llabs(E1) + (long long)(w - 1) * abs(a1) + (long long)(h - 1) * abs(b1);
+            const long long s2 = llabs(E2) + (long long)(w - 1) * abs(a2) + (long long)(h - 1) * abs(b2);
+            small = cnt <= kSmallCand && s0 < lim && s1 < lim && s2 < lim;
+            if (small) {
+                e0 = (int)E0; e1 = (int)E1; e2 = (int)E2;
+                r0 = b0 - (w - 1) * a0; r1 = b1 - (w - 1) * a1; r2 = b2 - (w - 1) * a2;  // step to the next row's first pixel
+            } else if (cnt > kBigCand) {  // defer: push chunks to the global queue
+                const uint32_t nch = (cnt + kChunkCand - 1) / kChunkCand;
+                uint32_t old = *reinterpret_cast<volatile uint32_t*>(SCHED(a, 2));
+                bool ok = false;
+                while (old + nch <= a.queue_cap) {
+                    const uint32_t prev = atomicCAS(SCHED(a, 2), old, old + nch);
+                    if (prev == old) { ok = true; break; }
+                    old = prev;
+                }
+                if (ok) {
+                    const uint32_t tg = a.tri_first + t0 + lane;
+                    for (uint32_t i = 0; i < nch; ++i) a.queue[old + i] = make_uint2(tg, i);
+                    __threadfence();
+                    cnt = 0;
+                    deferred = true;
+                }
+            }
+        }
+        __syncwarp();
+        // every chunk this unit defers is in the global queue now (pushers fenced): count the unit as
+        // "past set-up" so idle warps only wait for set-ups in flight, not for whole units
+        if (lane == 0) atomicAdd(SCHED(a, 1), 1u);
+        // the unit's per-triangle records (plane equations + shading state) go to global memory for the
+        // fragment kernel: two TMA bulk stores straight out of this warp's shared-memory slice
+        if (__any_sync(0xffffffffu, cnt != 0 || deferred)) {
+            if (lane == 0) {
+                fence_proxy_async();
+                tma_store_1d(const_cast<float4*>(a.tri_planes) + (size_t)t0 * 9, wb.tri, ntri * kTriBytes);
+                tma_store_1d(a.tri_frag + (size_t)t0 * sizeof(TriFragT<C::kMaps>), wb.frag, ntri * (uint32_t)sizeof(TriFragT<C::kMaps>));
+                tma_store_commit();
+            }
+        }
+
+        // small triangles: every lane walks its own pixel box in lock-step, twice.  Walk 1 records the
+        // covered candidates in a 64-bit mask (no ballots, no stores); a warp scan of the hit counts gives
+        // every triangle a contiguous output range; walk 2 writes the ids there.  Fragments therefore
+        // leave TRIANGLE-MAJOR, which is what keeps the fragment kernel's record and texel loads coherent.
+        {
+            const uint32_t mine = small ? cnt : 0u;
+            uint32_t maxc = mine;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, d));
+            unsigned long long hits = 0;
+            {
+                int col = 0, f0 = e0, f1 = e1, f2 = e2;
+                for (uint32_t it = 0; it < maxc; ++it) {
+                    const bool inside = it < mine && (f0 | f1 | f2) >= 0;
+                    hits |= (unsigned long long)inside << it;
+                    if (++col == w) { col = 0; f0 += r0; f1 += r1; f2 += r2; }
+                    else { f0 += a0; f1 += a1; f2 += a2; }
+                }
+            }
+            const uint32_t nh = (uint32_t)__popcll(hits);
+            uint32_t incl = nh;  // inclusive warp scan
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            if (total) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(a.counter, (unsigned long long)total);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                unsigned long long idx = base + (incl - nh);
+                const uint32_t tg = a.tri_first + t0 + lane;
+                uint32_t pxy = ((uint32_t)by << 12) | (uint32_t)bx;
+                const uint32_t pxyrow = (1u << 12) - (uint32_t)(w - 1);  // next row, first column
+                int col = 0;
+                uint32_t maxh = 64u - (uint32_t)__clzll((long long)hits);  // walk only up to the last hit
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) maxh = max(maxh, __shfl_xor_sync(0xffffffffu, maxh, d));
+                for (uint32_t it = 0; it < maxh; ++it) {
+                    if ((hits >> it) & 1ull) {
+                        if (idx < a.cap) a.frag_ids[idx] = make_uint2(tg, pxy);  // converterFS.glsl:48-51 beyond the cap
+                        ++idx;
+                    }
+                    if (++col == w) { col = 0; pxy += pxyrow; } else ++pxy;
+                }
+            }
+        }
+        // medium triangles: the whole warp covers one triangle at a time
+        {
+            unsigned mm = __ballot_sync(0xffffffffu, cnt != 0 && !small);
+            while (mm) {
+                const int s = __ffs(mm) - 1;
+                mm &= mm - 1;
+                const uint32_t cs = __shfl_sync(0xffffffffu, cnt, s);
+                raster_one<LAYOUT>(a, wb, qn, (uint32_t)s, 0u, cs, lane, tr);
+            }
+        }
+        flush_ids<LAYOUT>(a, wb, qn, lane);
+        qn = 0;
+        __syncwarp();
+        unit = __shfl_sync(0xffffffffu, next, 0);
+    }
+
+    // ---- drain: deferred big triangles, chunk by chunk, all warps ------------------------------
+    if (lane == 0) {
+        unsigned ns = 200;
+        while (ld_acquire_u32(SCHED(a, 1)) < a.n_units) { __nanosleep(ns); ns = min(ns * 2u, 2000u); }
+        __threadfence();
+    }
+    __syncwarp();
+    uint32_t tail = 0;
+    if (lane == 0) tail = ld_acquire_u32(SCHED(a, 2));
+    tail = __shfl_sync(0xffffffffu, tail, 0);
+    while (tail) {
+        uint32_t it = 0;
+        if (lane == 0) it = atomicAdd(SCHED(a, 3), 1u);
+        it = __shfl_sync(0xffffffffu, it, 0);
+        if (it >= tail) break;
+        const uint2 item = a.queue[it];
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+        if (lane < 9) wb.tri[lane] = a.tris[(size_t)item.x * 9 + lane];
+        __syncwarp();
+        uint32_t c = 0;
+        TriRaster tr;
+        tr.w = 1; tr.h = 0; tr.x0 = 0; tr.y0 = 0; tr.incl = 0;
+        tr.A[0] = tr.A[1] = tr.A[2] = tr.B[0] = tr.B[1] = tr.B[2] = 0; tr.C[0] = tr.C[1] = tr.C[2] = 0;
+        if (lane == 0) c = setup_triangle<LAYOUT>(wb.tri, item.x, a, tr, wb.frag[0]);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        __syncwarp();
+        const uint32_t c0 = item.y * kChunkCand, c1 = min(c, c0 + kChunkCand);
+        raster_one<LAYOUT>(a, wb, qn, 0u, c0, c1, lane, tr);
+        flush_ids<LAYOUT>(a, wb, qn, lane);
+        qn = 0;
+        __syncwarp();
+    }
+
+    if (lane == 0) tma_store_wait_all();  // record stores are complete (not just read) before the kernel ends
+    // ---- last CTA out publishes the count and re-arms the scheduler for the next launch ---------
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const uint32_t done = atomicAdd(SCHED(a, 4), 1u);
+        if (done == gridDim.x - 1) {
+            __threadfence();
+            *a.total_out = *reinterpret_cast<volatile unsigned long long*>(a.counter);
+            *a.counter = 0ull;
+            *SCHED(a, 0) = 0; *SCHED(a, 1) = 0; *SCHED(a, 2) = 0; *SCHED(a, 3) = 0; *SCHED(a, 4) = 0;
+            __threadfence();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// fragment stage: one warp = 32 consecutive fragments = 32 consecutive output records
+// ------------------------------------------------------------------------------------------
+template <int LAYOUT>
+__global__ void __launch_bounds__(M2S_FRAG_THREADS) fragment_kernel(const __grid_constant__ ConvertArgs a) {
+    using C = Cfg<LAYOUT>;
+    constexpr int kStride = C::kStride;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* stage = smem + (size_t)warp * 32 * kStride;  // this warp's 32 records
+    const unsigned long long total = *reinterpret_cast<const volatile unsigned long long*>(a.total_out);
+    const unsigned long long n = total < a.cap ? total : a.cap;
     const uint32_t* __restrict__ texb = a.tex_base;
     const bool want_keys = a.keys != nullptr;
-
-    for (uint32_t fb = 0; fb < qn; fb += 32) {
-        const uint32_t nfr = min(32u, qn - fb);
+    const unsigned long long nwarps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+    for (unsigned long long g = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + warp; g * 32 < n; g += nwarps) {
+        const unsigned long long wbase = g * 32;
+        const uint32_t nfr = (uint32_t)min(32ull, n - wbase);
         unsigned long long key = 0;
         if ((uint32_t)lane < nfr) {
-            const uint32_t id = wb.queue[fb + lane];
-            const uint32_t slot = id >> 24;
-            const int py = (id >> 12) & 0xfff, px = id & 0xfff;
-            const TriRaster& tr = wb.rast[slot];
-            const TriFragT<C::kMaps>& tf = wb.frag[slot];
-            const float dx = u2f((uint32_t)(px - (int)tr.x0)), dy = u2f((uint32_t)(py - (int)tr.y0));
-            const float4* v = wb.tri + slot * 9;  // plane equations: c0 | cx | cy
+            const uint2 fid = __ldg(a.frag_ids + wbase + lane);
+            const uint32_t tl = fid.x - a.tri_first;
+            const int py = (fid.y >> 12) & 0xfff, px = fid.y & 0xfff;
+            const TriFragT<C::kMaps> tf = *reinterpret_cast<const TriFragT<C::kMaps>*>(a.tri_frag + (size_t)tl * sizeof(TriFragT<C::kMaps>));
+            const unsigned meta = tf.meta;
+            const float dx = u2f((uint32_t)(px - (int)((meta >> 4) & 0xfffu))), dy = u2f((uint32_t)(py - (int)((meta >> 16) & 0xfffu)));
+            const float4* __restrict__ v = a.tri_planes + (size_t)tl * 9;  // plane equations: c0 | cx | cy
             // uv first: the texel addresses depend on nothing else
-            const float4 c0c = v[2], cxc = v[5], cyc = v[8];
+            const float4 c0c = __ldg(v + 2), cxc = __ldg(v + 5), cyc = __ldg(v + 8);
             const float u = c0c.z + cxc.z * dx + cyc.z * dy, vv = c0c.w + cxc.w * dx + cyc.w * dy;
 
             // ---- issue every texel load of every bound map back to back ----
@@ -451,7 +761,7 @@ __device__ __noinline__ void flush_queue(const ConvertArgs& a, WarpBlock<LAYOUT>
                 two[m] = has[m] && tf.frac[m] > 0.0f;
                 offs0[m] = has[m] ? ref.off0 : 0u;
                 offs1[m] = ref.off1;
-                if (m == 0 || !((tf.share >> m) & 1u)) {
+                if (m == 0 || !((meta >> m) & 1u)) {
                     bl[m][0] = bilin_setup(ref.w0, ref.h0, u, vv);
                     bl[m][1] = bilin_setup(ref.w1, ref.h1, u, vv);
                 } else { bl[m][0] = bl[0][0]; bl[m][1] = bl[0][1]; }
@@ -465,10 +775,10 @@ __device__ __noinline__ void flush_queue(const ConvertArgs& a, WarpBlock<LAYOUT>
                 tx[m][6] = two[m] ? __ldg(texb + (o1 + bl[m][1].i01)) : 0u; tx[m][7] = two[m] ? __ldg(texb + (o1 + bl[m][1].i11)) : 0u;
             }
             // ---- interpolate the remaining varyings while the loads are in flight ----
-            const float4 c0a = v[0], cxa = v[3], cya = v[6];
+            const float4 c0a = __ldg(v + 0), cxa = __ldg(v + 3), cya = __ldg(v + 6);
             const float Px = c0a.x + cxa.x * dx + cya.x * dy, Py = c0a.y + cxa.y * dx + cya.y * dy,
                         Pz = c0a.z + cxa.z * dx + cya.z * dy;
-            float* srec = reinterpret_cast<float*>(wb.stage + lane * kPitch);
+            float* srec = reinterpret_cast<float*>(stage + lane * kStride);
 
             // colour (converterFS.glsl:55-62,99)
             float cr = 1.f, cg = 1.f, cb = 1.f, ca = 1.f;
@@ -489,7 +799,7 @@ __device__ __noinline__ void flush_queue(const ConvertArgs& a, WarpBlock<LAYOUT>
 
             if (LAYOUT == 0) {
                 const float Nx = c0a.w + cxa.w * dx + cya.w * dy;
-                const float4 c0b = v[1], cxb = v[4], cyb = v[7];
+                const float4 c0b = __ldg(v + 1), cxb = __ldg(v + 4), cyb = __ldg(v + 7);
                 const float Ny = c0b.x + cxb.x * dx + cyb.x * dy, Nz = c0b.y + cxb.y * dx + cyb.y * dy;
                 float nx = Nx, ny = Ny, nz = Nz;
                 constexpr int MN = C::kMaps > 1 ? 1 : 0, MM = C::kMaps > 2 ? 2 : 0;
@@ -546,246 +856,25 @@ __device__ __noinline__ void flush_queue(const ConvertArgs& a, WarpBlock<LAYOUT>
                 s2[5] = make_float2(__fdiv_rn(cr - 0.5f, kC0), __fdiv_rn(cg - 0.5f, kC0));
                 s2[6] = make_float2(__fdiv_rn(cb - 0.5f, kC0), inv_sigmoid(ca));
             }
-            if (want_keys) key = ((unsigned long long)tf.tri << 24) | ((unsigned long long)py << 12) | (unsigned long long)px;
+            if (want_keys) key = ((unsigned long long)fid.x << 24) | (unsigned long long)fid.y;
         }
         __syncwarp();
-        // ---- coalesced copy-out of this warp's contiguous span --------------------------------
-        if (fb == 0) base = __shfl_sync(0xffffffffu, base, 0);
-        const unsigned long long wbase = base + fb;
-        uint32_t nvalid = 0;  // converterFS.glsl:48-51: idx >= cap dropped
-        if (wbase < a.cap) nvalid = (uint32_t)min((unsigned long long)nfr, a.cap - wbase);
-        if (LAYOUT == 0) {
-            float4* dst = reinterpret_cast<float4*>(a.out + wbase * 96ull);
-            const float4* src = reinterpret_cast<const float4*>(wb.stage);
-            const uint32_t n16 = nvalid * 6;  // 16-byte pieces to copy
+        // ---- the warp's records are one contiguous, 16-byte aligned span: straight vector copy ----
+        {
+            float4* dst = reinterpret_cast<float4*>(a.out + wbase * (unsigned long long)kStride);
+            const float4* src = reinterpret_cast<const float4*>(stage);
+            const uint32_t n16 = nfr * kStride / 16;  // 32*stride is a multiple of 16; a short tail group too (stride*nfr%16==0 or 8)
 #pragma unroll
-            for (int j = 0; j < 6; ++j) {
+            for (int j = 0; j < (32 * kStride / 16 + 31) / 32; ++j) {
                 const uint32_t c = lane + 32 * j;
                 if (c < n16) dst[c] = src[c];
             }
-        } else {
-            float2* dst = reinterpret_cast<float2*>(a.out + wbase * 56ull);
-            const float2* src = reinterpret_cast<const float2*>(wb.stage);
-            const uint32_t n8 = nvalid * 7;  // 8-byte pieces to copy
-#pragma unroll
-            for (int j = 0; j < 7; ++j) {
-                const uint32_t c = lane + 32 * j;
-                if (c < n8) dst[c] = src[c];
+            if ((nfr * kStride) & 8u) {  // odd number of 56-byte records: one trailing 8-byte piece
+                if (lane == 0) reinterpret_cast<float2*>(dst)[n16 * 2] = reinterpret_cast<const float2*>(src)[n16 * 2];
             }
         }
-        if (want_keys && (uint32_t)lane < nvalid) a.keys[wbase + lane] = key;
+        if (want_keys && (uint32_t)lane < nfr) a.keys[wbase + lane] = key;
         __syncwarp();
-    }
-}
-
-// enqueue the lanes whose `inside` is set; flush when the queue could overflow on the next step
-template <int LAYOUT>
-__device__ __forceinline__ void enqueue(const ConvertArgs& a, WarpBlock<LAYOUT>& wb, uint32_t& qn, bool inside, uint32_t id,
-                                        int lane) {
-    const unsigned m = __ballot_sync(0xffffffffu, inside);
-    if (m) {
-        if (inside) wb.queue[qn + __popc(m & ((1u << lane) - 1u))] = id;
-        qn += __popc(m);
-        if (qn > kQueue - 32) {
-            flush_queue<LAYOUT>(a, wb, qn, lane);
-            qn = 0;
-        }
-    }
-}
-
-// warp-per-triangle coverage of candidates [c0, c1) of the triangle in `slot` (int64 edge functions)
-template <int LAYOUT>
-__device__ void raster_one(const ConvertArgs& a, WarpBlock<LAYOUT>& wb, uint32_t& qn, uint32_t slot, uint32_t c0, uint32_t c1,
-                           int lane) {
-    const TriRaster& tr = wb.rast[slot];
-    const uint32_t w = tr.w;
-    const float rcp = 1.0f / (float)w;
-    const long long C0 = tr.C[0], C1 = tr.C[1], C2 = tr.C[2];
-    const int A0 = tr.A[0], A1 = tr.A[1], A2 = tr.A[2], B0 = tr.B[0], B1 = tr.B[1], B2 = tr.B[2];
-    const unsigned incl = tr.incl;
-    const int bx = tr.x0, by = tr.y0;
-    for (uint32_t cb = c0; cb < c1; cb += 32) {
-        const uint32_t c = cb + lane;
-        bool inside = false;
-        uint32_t id = 0;
-        if (c < c1) {
-            uint32_t row = (uint32_t)((float)c * rcp);  // c < 2^24: exact in fp32, quotient off by at most 1
-            int col = (int)(c - row * w);
-            if (col < 0) { --row; col += (int)w; }
-            else if (col >= (int)w) { ++row; col -= (int)w; }
-            const int px = bx + col, py = by + (int)row;
-            const long long E0 = C0 + (long long)A0 * px + (long long)B0 * py;
-            const long long E1 = C1 + (long long)A1 * px + (long long)B1 * py;
-            const long long E2 = C2 + (long long)A2 * px + (long long)B2 * py;
-            inside = (E0 > 0 || (E0 == 0 && (incl & 1u))) && (E1 > 0 || (E1 == 0 && (incl & 2u))) &&
-                     (E2 > 0 || (E2 == 0 && (incl & 4u)));
-            id = (slot << 24) | ((uint32_t)py << 12) | (uint32_t)px;
-        }
-        enqueue<LAYOUT>(a, wb, qn, inside, id, lane);
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// the kernel
-// ------------------------------------------------------------------------------------------
-template <int LAYOUT>
-__global__ void __launch_bounds__(Cfg<LAYOUT>::kWarps * 32) __maxnreg__(Cfg<LAYOUT>::kMaxRegs) convert_kernel(const __grid_constant__ ConvertArgs a) {
-    using C = Cfg<LAYOUT>;
-    extern __shared__ __align__(128) unsigned char smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpBlock<LAYOUT>& wb = *reinterpret_cast<WarpBlock<LAYOUT>*>(smem + (size_t)warp * sizeof(WarpBlock<LAYOUT>));
-    const unsigned char* tri_bytes = reinterpret_cast<const unsigned char*>(a.tris);
-
-    if (lane == 0) {
-        mbar_init(&wb.bar, 1);
-        fence_barrier_init();
-    }
-    __syncwarp();
-    uint32_t phase = 0, qn = 0;
-
-    // ---- work units ---------------------------------------------------------------------------
-    uint32_t unit = 0;
-    if (lane == 0) unit = atomicAdd(SCHED(a, 0), 1u);
-    unit = __shfl_sync(0xffffffffu, unit, 0);
-    while (unit < a.n_units) {
-        const uint32_t t0 = unit * a.unit_tris;
-        const uint32_t ntri = min(a.unit_tris, a.tri_count - t0);
-        uint32_t next = 0;
-        if (lane == 0) {
-            const uint32_t bytes = ntri * kTriBytes;
-            fence_proxy_async();
-            mbar_arrive_expect_tx(&wb.bar, bytes);
-            tma_load_1d(wb.tri, tri_bytes + ((size_t)a.tri_first + t0) * kTriBytes, bytes, &wb.bar);
-            // claim the next unit now and pull its triangles into L2: both latencies overlap this unit
-            next = atomicAdd(SCHED(a, 0), 1u);
-            if (next < a.n_units) {
-                const uint32_t nt0 = next * a.unit_tris;
-                prefetch_l2(tri_bytes + ((size_t)a.tri_first + nt0) * kTriBytes, min(a.unit_tris, a.tri_count - nt0) * kTriBytes);
-            }
-        }
-        mbar_wait(&wb.bar, phase);
-        phase ^= 1;
-
-        // per-triangle stage: one lane per triangle
-        uint32_t cnt = 0;
-        if ((uint32_t)lane < ntri) cnt = setup_triangle<LAYOUT>(wb.tri + lane * 9, a.tri_first + t0 + lane, a, wb.rast[lane], wb.frag[lane]);
-
-        // classify: small (lane-per-triangle, int32), medium (warp-per-triangle), big (deferred)
-        int e0 = 0, e1 = 0, e2 = 0, a0 = 0, a1 = 0, a2 = 0, r0 = 0, r1 = 0, r2 = 0, w = 1, bx = 0, by = 0;
-        bool small = false;
-        if (cnt) {
-            const TriRaster& tr = wb.rast[lane];
-            w = tr.w; bx = tr.x0; by = tr.y0;
-            const int h = tr.h;
-            a0 = tr.A[0]; a1 = tr.A[1]; a2 = tr.A[2];
-            const int b0 = tr.B[0], b1 = tr.B[1], b2 = tr.B[2];
-            // E at the box origin, with the ownership bias folded in: inside <=> all E' >= 0
-            const long long E0 = tr.C[0] + (long long)a0 * bx + (long long)b0 * by - ((tr.incl & 1u) ? 0 : 1);
-            const long long E1 = tr.C[1] + (long long)a1 * bx + (long long)b1 * by - ((tr.incl & 2u) ? 0 : 1);
-            const long long E2 = tr.C[2] + (long long)a2 * bx + (long long)b2 * by - ((tr.incl & 4u) ? 0 : 1);
-            const long long lim = 0x7fffffffll;
-            const long long s0 = llabs(E0) + (long long)(w - 1) * abs(a0) + (long long)(h - 1) * abs(b0);
-            const long long s1 = llabs(E1) + (long long)(w - 1) * abs(a1) + (long long)(h - 1) * abs(b1);
-            const long long s2 = llabs(E2) + (long long)(w - 1) * abs(a2) + (long long)(h - 1) * abs(b2);
-            small = cnt <= kSmallCand && s0 < lim && s1 < lim && s2 < lim;
-            if (small) {
-                e0 = (int)E0; e1 = (int)E1; e2 = (int)E2;
-                r0 = b0 - (w - 1) * a0; r1 = b1 - (w - 1) * a1; r2 = b2 - (w - 1) * a2;  // step to the next row's first pixel
-            } else if (cnt > kBigCand) {  // defer: push chunks to the global queue
-                const uint32_t nch = (cnt + kChunkCand - 1) / kChunkCand;
-                uint32_t old = *reinterpret_cast<volatile uint32_t*>(SCHED(a, 2));
-                bool ok = false;
-                while (old + nch <= a.queue_cap) {
-                    const uint32_t prev = atomicCAS(SCHED(a, 2), old, old + nch);
-                    if (prev == old) { ok = true; break; }
-                    old = prev;
-                }
-                if (ok) {
-                    const uint32_t tg = a.tri_first + t0 + lane;
-                    for (uint32_t i = 0; i < nch; ++i) a.queue[old + i] = make_uint2(tg, i);
-                    __threadfence();
-                    cnt = 0;
-                }
-            }
-        }
-        __syncwarp();
-        // every chunk this unit defers is in the global queue now (pushers fenced): count the unit as
-        // "past set-up" so idle warps only wait for set-ups in flight, not for whole units
-        if (lane == 0) atomicAdd(SCHED(a, 1), 1u);
-
-        // small triangles: every lane walks its own pixel box in lock-step
-        {
-            uint32_t mine = small ? cnt : 0u;
-            uint32_t maxc = mine;
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, d));
-            int col = 0;
-            uint32_t id = ((uint32_t)lane << 24) | ((uint32_t)by << 12) | (uint32_t)bx;
-            const uint32_t idrow = (1u << 12) - (uint32_t)(w - 1);  // next row, first column
-            for (uint32_t it = 0; it < maxc; ++it) {
-                const bool inside = it < mine && (e0 | e1 | e2) >= 0;
-                enqueue<LAYOUT>(a, wb, qn, inside, id, lane);
-                if (++col == w) { col = 0; id += idrow; e0 += r0; e1 += r1; e2 += r2; }
-                else { ++id; e0 += a0; e1 += a1; e2 += a2; }
-            }
-        }
-        // medium triangles: the whole warp covers one triangle at a time
-        {
-            unsigned mm = __ballot_sync(0xffffffffu, cnt != 0 && !small);
-            while (mm) {
-                const int s = __ffs(mm) - 1;
-                mm &= mm - 1;
-                const uint32_t cs = __shfl_sync(0xffffffffu, cnt, s);
-                raster_one<LAYOUT>(a, wb, qn, (uint32_t)s, 0u, cs, lane);
-            }
-        }
-        flush_queue<LAYOUT>(a, wb, qn, lane);
-        qn = 0;
-        __syncwarp();
-        unit = __shfl_sync(0xffffffffu, next, 0);
-    }
-
-    // ---- drain: deferred big triangles, chunk by chunk, all warps ------------------------------
-    if (lane == 0) {
-        unsigned ns = 200;
-        while (ld_acquire_u32(SCHED(a, 1)) < a.n_units) { __nanosleep(ns); ns = min(ns * 2u, 2000u); }
-        __threadfence();
-    }
-    __syncwarp();
-    uint32_t tail = 0;
-    if (lane == 0) tail = ld_acquire_u32(SCHED(a, 2));
-    tail = __shfl_sync(0xffffffffu, tail, 0);
-    while (tail) {
-        uint32_t it = 0;
-        if (lane == 0) it = atomicAdd(SCHED(a, 3), 1u);
-        it = __shfl_sync(0xffffffffu, it, 0);
-        if (it >= tail) break;
-        const uint2 item = a.queue[it];
-        if (lane < 9) wb.tri[lane] = a.tris[(size_t)item.x * 9 + lane];
-        __syncwarp();
-        uint32_t c = 0;
-        if (lane == 0) c = setup_triangle<LAYOUT>(wb.tri, item.x, a, wb.rast[0], wb.frag[0]);
-        c = __shfl_sync(0xffffffffu, c, 0);
-        __syncwarp();
-        const uint32_t c0 = item.y * kChunkCand, c1 = min(c, c0 + kChunkCand);
-        raster_one<LAYOUT>(a, wb, qn, 0u, c0, c1, lane);
-        flush_queue<LAYOUT>(a, wb, qn, lane);
-        qn = 0;
-        __syncwarp();
-    }
-
-    // ---- last CTA out publishes the count and re-arms the scheduler for the next launch ---------
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const uint32_t done = atomicAdd(SCHED(a, 4), 1u);
-        if (done == gridDim.x - 1) {
-            __threadfence();
-            *a.total_out = *reinterpret_cast<volatile unsigned long long*>(a.counter);
-            *a.counter = 0ull;
-            *SCHED(a, 0) = 0; *SCHED(a, 1) = 0; *SCHED(a, 2) = 0; *SCHED(a, 3) = 0; *SCHED(a, 4) = 0;
-            __threadfence();
-        }
     }
 }
 
@@ -865,28 +954,39 @@ __global__ void ply_rows_kernel(const float4* __restrict__ rec, unsigned long lo
 // ------------------------------------------------------------------------------------------
 // launch wrappers used by m2s_api.cu
 // ------------------------------------------------------------------------------------------
-size_t convert_smem_bytes(int layout) {
+size_t raster_smem_bytes(int layout) {
     return layout == 0 ? sizeof(WarpBlock<0>) * Cfg<0>::kWarps : sizeof(WarpBlock<1>) * Cfg<1>::kWarps;
 }
+size_t fragment_smem_bytes(int layout) { return (size_t)(M2S_FRAG_THREADS / 32) * 32 * (layout == 0 ? Cfg<0>::kStride : Cfg<1>::kStride); }
 int convert_warps_per_cta(int layout) { return layout == 0 ? Cfg<0>::kWarps : Cfg<1>::kWarps; }
+size_t tri_frag_bytes(int layout) { return layout == 0 ? sizeof(TriFragT<Cfg<0>::kMaps>) : sizeof(TriFragT<Cfg<1>::kMaps>); }
 
-cudaError_t convert_configure(int layout, int* blocks_per_sm) {
+cudaError_t convert_configure(int layout, int* raster_blocks_per_sm, int* fragment_blocks_per_sm) {
     cudaError_t e;
-    const size_t smem = convert_smem_bytes(layout);
+    const size_t smem = raster_smem_bytes(layout), fsmem = fragment_smem_bytes(layout);
     if (layout == 0) {
-        e = cudaFuncSetAttribute(convert_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(raster_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, convert_kernel<0>, Cfg<0>::kWarps * 32, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(raster_blocks_per_sm, raster_kernel<0>, Cfg<0>::kWarps * 32, smem);
+        if (e != cudaSuccess) return e;
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(fragment_blocks_per_sm, fragment_kernel<0>, M2S_FRAG_THREADS, fsmem);
     }
-    e = cudaFuncSetAttribute(convert_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(raster_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, convert_kernel<1>, Cfg<1>::kWarps * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(raster_blocks_per_sm, raster_kernel<1>, Cfg<1>::kWarps * 32, smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(fragment_blocks_per_sm, fragment_kernel<1>, M2S_FRAG_THREADS, fsmem);
 }
 
-cudaError_t convert_launch(int layout, const ConvertArgs& args, int grid, cudaStream_t stream) {
-    const size_t smem = convert_smem_bytes(layout);
-    if (layout == 0) convert_kernel<0><<<grid, Cfg<0>::kWarps * 32, smem, stream>>>(args);
-    else convert_kernel<1><<<grid, Cfg<1>::kWarps * 32, smem, stream>>>(args);
+cudaError_t convert_launch(int layout, const ConvertArgs& args, int raster_grid, int fragment_grid, cudaStream_t stream) {
+    const size_t smem = raster_smem_bytes(layout), fsmem = fragment_smem_bytes(layout);
+    if (layout == 0) {
+        raster_kernel<0><<<raster_grid, Cfg<0>::kWarps * 32, smem, stream>>>(args);
+        fragment_kernel<0><<<fragment_grid, M2S_FRAG_THREADS, fsmem, stream>>>(args);
+    } else {
+        raster_kernel<1><<<raster_grid, Cfg<1>::kWarps * 32, smem, stream>>>(args);
+        fragment_kernel<1><<<fragment_grid, M2S_FRAG_THREADS, fsmem, stream>>>(args);
+    }
     return cudaGetLastError();
 }
 
