@@ -75,6 +75,9 @@ struct m2s_dscene {
     std::vector<void*> allocs;
 };
 
+static unsigned long long* g_trace = nullptr;  // debugging aid for M2S_TRACE builds (scripts/trace_raster.py)
+extern "C" __attribute__((visibility("default"))) void m2s_debug_set_trace(void* p) { g_trace = (unsigned long long*)p; }
+
 static m2s_status grow(m2s_ctx* ctx, void** p, size_t* have, size_t need) {
     if (*have >= need) return M2S_OK;
     if (*p) CUDA_TRY(cudaFreeAsync(*p, ctx->stream));
@@ -404,6 +407,7 @@ M2S_EXPORT m2s_status m2s_convert_enqueue(m2s_ctx* ctx, const m2s_dscene* s, con
     }
     a.queue = ctx->d_queue;
     a.queue_cap = ctx->queue_cap;
+    a.trace = g_trace;
     const int fgrid = ctx->sm_count * ctx->frag_blocks_per_sm[klayout];
     cudaError_t e = convert_launch(klayout, a, grid, fgrid, stream);
     if (e != cudaSuccess) { ctx->dirty = true; set_error(std::string("convert launch: ") + cudaGetErrorString(e)); return M2S_E_CUDA; }

@@ -70,6 +70,7 @@ struct ConvertArgs {
     uint32_t n_units;
     uint2* queue;                      // deferred big-triangle chunks: (triangle, chunk)
     uint32_t queue_cap;
+    unsigned long long* trace;         // M2S_TRACE builds only: 16 globaltimer stamps per raster warp
 };
 
 }  // namespace m2s

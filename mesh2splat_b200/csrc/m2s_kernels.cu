@@ -96,6 +96,12 @@ __device__ __forceinline__ void tma_store_1d(void* dst_gmem, const void* src_sme
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+#ifdef M2S_TRACE
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define STAMP(a, slot) do { if ((a).trace && lane == 0) (a).trace[((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * 16 + (slot)] = gtime(); } while (0)
+#else
+#define STAMP(a, slot) do { } while (0)
+#endif
 constexpr int kSchedStride = 32;  // scheduler words live on separate 128-byte lines
 #define SCHED(a, i) ((a).sched + (i) * kSchedStride)
 __device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
@@ -517,6 +523,7 @@ __global__ void __launch_bounds__(Cfg<LAYOUT>::kWarps * 32) __maxnreg__(Cfg<LAYO
     }
     __syncwarp();
     uint32_t phase = 0, qn = 0;
+    STAMP(a, 0);
 
     // ---- work units ---------------------------------------------------------------------------
     // the first unit of every warp is static (unit = global warp id): no atomic, and nobody can grab two
@@ -543,6 +550,7 @@ __global__ void __launch_bounds__(Cfg<LAYOUT>::kWarps * 32) __maxnreg__(Cfg<LAYO
         }
         mbar_wait(&wb.bar, phase);
         phase ^= 1;
+        STAMP(a, 1);
 
         // per-triangle stage: one lane per triangle
         uint32_t cnt = 0;
@@ -589,6 +597,7 @@ __global__ void __launch_bounds__(Cfg<LAYOUT>::kWarps * 32) __maxnreg__(Cfg<LAYO
                 }
             }
         }
+        STAMP(a, 2);
         __syncwarp();
         // every chunk this unit defers is in the global queue now (pushers fenced): count the unit as
         // "past set-up" so idle warps only wait for set-ups in flight, not for whole units
@@ -623,6 +632,7 @@ __global__ void __launch_bounds__(Cfg<LAYOUT>::kWarps * 32) __maxnreg__(Cfg<LAYO
                     else { f0 += a0; f1 += a1; f2 += a2; }
                 }
             }
+            STAMP(a, 3);
             const uint32_t nh = (uint32_t)__popcll(hits);
             uint32_t incl = nh;  // inclusive warp scan
 #pragma unroll
@@ -635,6 +645,7 @@ __global__ void __launch_bounds__(Cfg<LAYOUT>::kWarps * 32) __maxnreg__(Cfg<LAYO
                 unsigned long long base = 0;
                 if (lane == 0) base = atomicAdd(a.counter, (unsigned long long)total);
                 base = __shfl_sync(0xffffffffu, base, 0);
+                STAMP(a, 4);
                 unsigned long long idx = base + (incl - nh);
                 const uint32_t tg = a.tri_first + t0 + lane;
                 uint32_t pxy = ((uint32_t)by << 12) | (uint32_t)bx;
@@ -652,6 +663,7 @@ __global__ void __launch_bounds__(Cfg<LAYOUT>::kWarps * 32) __maxnreg__(Cfg<LAYO
                 }
             }
         }
+        STAMP(a, 5);
         // medium triangles: the whole warp covers one triangle at a time
         {
             unsigned mm = __ballot_sync(0xffffffffu, cnt != 0 && !small);
@@ -666,15 +678,17 @@ __global__ void __launch_bounds__(Cfg<LAYOUT>::kWarps * 32) __maxnreg__(Cfg<LAYO
         qn = 0;
         __syncwarp();
         unit = __shfl_sync(0xffffffffu, next, 0);
+        STAMP(a, 6);
     }
+    STAMP(a, 7);
 
     // ---- drain: deferred big triangles, chunk by chunk, all warps ------------------------------
     if (lane == 0) {
-        unsigned ns = 200;
-        while (ld_acquire_u32(SCHED(a, 1)) < a.n_units) { __nanosleep(ns); ns = min(ns * 2u, 2000u); }
-        __threadfence();
+        unsigned ns = 100;
+        while (ld_acquire_u32(SCHED(a, 1)) < a.n_units) { __nanosleep(ns); ns = min(ns * 2u, 1000u); }
     }
     __syncwarp();
+    STAMP(a, 8);
     uint32_t tail = 0;
     if (lane == 0) tail = ld_acquire_u32(SCHED(a, 2));
     tail = __shfl_sync(0xffffffffu, tail, 0);
@@ -702,9 +716,12 @@ __global__ void __launch_bounds__(Cfg<LAYOUT>::kWarps * 32) __maxnreg__(Cfg<LAYO
         __syncwarp();
     }
 
+    STAMP(a, 9);
     if (lane == 0) tma_store_wait_all();  // record stores are complete (not just read) before the kernel ends
     // ---- last CTA out publishes the count and re-arms the scheduler for the next launch ---------
+    STAMP(a, 10);
     __syncthreads();
+    STAMP(a, 11);
     if (threadIdx.x == 0) {
         __threadfence();
         const uint32_t done = atomicAdd(SCHED(a, 4), 1u);
@@ -728,6 +745,9 @@ __global__ void __launch_bounds__(M2S_FRAG_THREADS) fragment_kernel(const __grid
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* stage = smem + (size_t)warp * 32 * kStride;  // this warp's 32 records
+    // launched with programmatic stream serialisation: the CTAs of this grid are placed while the raster
+    // kernel drains; everything it wrote is visible after this wait
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const unsigned long long total = *reinterpret_cast<const volatile unsigned long long*>(a.total_out);
     const unsigned long long n = total < a.cap ? total : a.cap;
     const uint32_t* __restrict__ texb = a.tex_base;
@@ -980,14 +1000,30 @@ cudaError_t convert_configure(int layout, int* raster_blocks_per_sm, int* fragme
 
 cudaError_t convert_launch(int layout, const ConvertArgs& args, int raster_grid, int fragment_grid, cudaStream_t stream) {
     const size_t smem = raster_smem_bytes(layout), fsmem = fragment_smem_bytes(layout);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)fragment_grid);
+    cfg.blockDim = dim3(M2S_FRAG_THREADS);
+    cfg.dynamicSmemBytes = fsmem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // PDL: overlap this launch with the raster kernel's tail
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+#ifndef M2S_NO_PDL
+    cfg.numAttrs = 1;
+#else
+    cfg.numAttrs = 0;
+#endif
     if (layout == 0) {
         raster_kernel<0><<<raster_grid, Cfg<0>::kWarps * 32, smem, stream>>>(args);
-        fragment_kernel<0><<<fragment_grid, M2S_FRAG_THREADS, fsmem, stream>>>(args);
-    } else {
-        raster_kernel<1><<<raster_grid, Cfg<1>::kWarps * 32, smem, stream>>>(args);
-        fragment_kernel<1><<<fragment_grid, M2S_FRAG_THREADS, fsmem, stream>>>(args);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        return cudaLaunchKernelEx(&cfg, fragment_kernel<0>, args);
     }
-    return cudaGetLastError();
+    raster_kernel<1><<<raster_grid, Cfg<1>::kWarps * 32, smem, stream>>>(args);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return cudaLaunchKernelEx(&cfg, fragment_kernel<1>, args);
 }
 
 cudaError_t mip_down_launch(const uint32_t* src, uint32_t sw, uint32_t sh, uint32_t* dst, uint32_t dw, uint32_t dh,
