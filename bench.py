@@ -156,13 +156,13 @@ def run_reference(args):
     scene = synth.helmet_standin(2048)
     layout = LAYOUTS[args.layout]
     prep = oracle.Prepared(scene)
-    cores = oracle.max_threads()
+    cores = os.cpu_count() or oracle.max_threads()  # torchrun exports OMP_NUM_THREADS=1: ask for every core explicitly
     out = None
     for _ in range(max(1, min(args.warmup, 2))):
-        n, total, out = prep.convert(DENSITY, layout, out=out)
+        n, total, out = prep.convert(DENSITY, layout, out=out, threads=cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        n, total, out = prep.convert(DENSITY, layout, out=out)
+        n, total, out = prep.convert(DENSITY, layout, out=out, threads=cores)
     dt = (time.perf_counter() - t0) / args.steps
     val = n / dt / 1e6
     sample = f"full workload ({scene.triangle_count} triangles -> {n} gaussians) per step, {args.steps} steps"
@@ -211,17 +211,27 @@ def run_ours(args):
     out = torch.empty(cap_total * stride, dtype=torch.uint8, device=dev)
     d_total = torch.zeros(1, dtype=torch.int64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    gathered = torch.empty(world * cap_total * stride, dtype=torch.uint8, device=dev) if world > 1 else None
+    fused = world > 1 and args.gather == "fused"
+    gathered = torch.empty(world * cap_total * stride, dtype=torch.uint8, device=dev) if world > 1 and not fused else None
     counts = torch.zeros(world, dtype=torch.int64, device=dev) if world > 1 else None
-    final = torch.empty(cap_total * stride, dtype=torch.uint8, device=dev) if world > 1 else None
+    final = torch.empty(cap_total * stride, dtype=torch.uint8, device=dev) if world > 1 and not fused else None
+    pg = None
+    if fused:
+        from mesh2splat_b200.shard import PeerGather
+        pg = PeerGather(ctx, cap_total, stride, dist, torch)
 
     def step(timed_events=None):
         flush.zero_()  # evict L2 (126 MB) — untimed
         if timed_events is not None:
             timed_events[0].record(stream)
-        ctx.convert_enqueue(ds, params, out, cap_total, None, d_total, stream.cuda_stream)
         n_total = None
-        if world > 1:  # concatenate per-rank buffers on every rank: counts, then max-padded payload
+        if fused:  # records go straight into every rank's final buffer from the fragment kernel (NVLink peer stores)
+            pg.convert_enqueue(ds, params, stream.cuda_stream)
+            if timed_events is not None:
+                timed_events[1].record(stream)
+            return None
+        ctx.convert_enqueue(ds, params, out, cap_total, None, d_total, stream.cuda_stream)
+        if world > 1:  # NCCL baseline: concatenate per-rank buffers on every rank: counts, then max-padded payload
             dist.all_gather_into_tensor(counts, d_total)
             c = counts.cpu()
             mx = int(c.max())
@@ -252,12 +262,17 @@ def run_ours(args):
         dist.barrier()
     torch.cuda.synchronize(dev)
     ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+    if fused:
+        n_all = int(pg.total.item())
+        ctx.convert_enqueue(ds, params, out, cap_total, None, d_total, stream.cuda_stream)  # this rank's share, for the roofline
+        torch.cuda.synchronize(dev)
     n_local = int(d_total.item())
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-        n_all = int(n_total)
+        if not fused:
+            n_all = int(n_total)
     else:
         n_all = n_local
     clk = clocks.stop() if clocks else None
@@ -303,18 +318,24 @@ def run_ours(args):
         roofline = {"bound": "hbm", "kernel": "m2s::raster_kernel + m2s::fragment_kernel (the whole step)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": profiled_traffic(args.layout), "algorithmic_bytes": alg,
                     "kernel_ms": kernel_ms, "peak_source": peak_src}
-        # ---- CPU baseline on a bounded sample (the whole workload, a few repeats) ----
-        import oracle
-        prep = oracle.Prepared(scene)
-        o = None
-        n, _, o = prep.convert(DENSITY, layout, out=o)
-        reps = 3
-        t0 = time.perf_counter()
-        for _ in range(reps):
+        # ---- CPU baseline on a bounded sample (the whole workload, a few repeats); N = 1 only ----
+        cpu = None
+        if world == 1:
+            import oracle
+            prep = oracle.Prepared(scene)
+            o = None
             n, _, o = prep.convert(DENSITY, layout, out=o)
-        cdt = (time.perf_counter() - t0) / reps
-        cpu = {"value": n / cdt / 1e6, "unit": UNIT, "cores": oracle.max_threads(), "kind": "port",
-               "sample": f"full workload x{reps} ({scene.triangle_count} triangles -> {n} gaussians each)"}
+            reps = 3
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                n, _, o = prep.convert(DENSITY, layout, out=o)
+            cdt = (time.perf_counter() - t0) / reps
+            cpu = {"value": n / cdt / 1e6, "unit": UNIT, "cores": oracle.max_threads(), "kind": "port",
+                   "sample": f"full workload x{reps} ({scene.triangle_count} triangles -> {n} gaussians each)"}
+        if world > 1:  # bytes that must cross NVLink per GPU for "every rank holds the full buffer"
+            nv = (n_all - n_local) * stride
+            roofline["nvlink"] = {"ingress_bytes_per_gpu": int(nv), "peak_GBps": 770.0, "floor_ms": nv / 770e9 * 1e3,
+                                  "note": "measured peer-copy bandwidth per direction (B200_PROFILING.md); the gather cannot finish faster"}
         launches = 2 * args.steps  # raster_kernel + fragment_kernel per timed step (no memsets: the scheduler re-arms itself)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
@@ -322,7 +343,8 @@ def run_ours(args):
                 "config": {"workload": WORKLOAD, "density": DENSITY, "layout": args.layout, "record_bytes": stride,
                            "triangles": T, "gaussians": n_all, "textures": "3x2048^2 RGBA8 (+mips 1..4)",
                            "l2": "flushed between iterations (256 MiB memset, untimed)",
-                           "parallelism": f"triangle shards x{world}" + (" + NCCL all-gather (counts, padded payload)" if world > 1 else "")},
+                           "parallelism": f"triangle shards x{world}" + ((" + fused gather: peer stores into every rank's final buffer (NVLink)" if fused
+                                                                            else " + NCCL all-gather (counts, padded payload)") if world > 1 else "")},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu}
     if world > 1:
         dist.barrier()
@@ -340,6 +362,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layout", default="packed56", choices=sorted(LAYOUTS))
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="N>1: fused peer-store gather (default) or the NCCL all-gather baseline")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -177,6 +177,26 @@ m2s_status m2s_convert_host(m2s_ctx* ctx, const m2s_scene* scene, const m2s_para
                             void* h_out, uint64_t out_capacity, uint64_t* h_keys,
                             m2s_result* result);
 
+/* ---- multi-GPU: conversion fused with the gather ------------------------------------------------
+ * One process per GPU; rank r converts its own triangle range (params->first_triangle/triangle_count)
+ * and its fragment kernel stores the records straight into the final buffer of EVERY rank (peer
+ * memory over NVLink) at the rank-major global offset — the "single all-gather" of the conversion
+ * result without a separate collective pass or a host round trip.  Buffers come from any allocator
+ * that maps peer memory into each process (torch symmetric memory, cudaIpc*, cuMem*).
+ * xch[p]: rank p's exchange block, M2S_MAX_PEERS*4 uint64, zeroed once before first use.
+ * Every rank must make the same sequence of calls (an epoch counter pairs them up).  Layouts REF96 and
+ * PACKED56.  d_total_global (device, optional) receives the number of records in the final buffer
+ * once all ranks' records have landed; work enqueued after this call on `stream` sees the full buffer. */
+#define M2S_MAX_PEERS 8
+typedef struct m2s_peers {
+    uint32_t world, rank;
+    void* out[M2S_MAX_PEERS];
+    uint64_t* xch[M2S_MAX_PEERS];
+} m2s_peers;
+m2s_status m2s_convert_gather_enqueue(m2s_ctx* ctx, const m2s_dscene* scene, const m2s_params* params,
+                                      const m2s_peers* peers, uint64_t out_capacity, uint64_t* d_total_global,
+                                      void* stream);
+
 /* ---- outputs: replaces exportPly / savePlyVector -------------------------------------------- */
 /* ASCII header of format 0/1/2 for `count` vertices; returns bytes written (excl. NUL) or the
  * needed size if dst is too small. */

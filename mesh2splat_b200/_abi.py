@@ -51,6 +51,13 @@ class m2s_result(C.Structure):
                 ("device_ms", C.c_float)]
 
 
+MAX_PEERS = 8
+
+
+class m2s_peers(C.Structure):
+    _fields_ = [("world", C.c_uint32), ("rank", C.c_uint32), ("out", C.c_void_p * MAX_PEERS), ("xch", C.c_void_p * MAX_PEERS)]
+
+
 def make_params(resolution: int, layout: int = LAYOUT_REF96, gaussian_std: float = 0.65,
                 max_gaussians: int = 0, flags: int = 0, first_triangle: int = 0,
                 triangle_count: int = 0) -> m2s_params:

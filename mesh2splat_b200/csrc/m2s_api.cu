@@ -16,6 +16,8 @@ int convert_warps_per_cta(int layout);
 size_t tri_frag_bytes(int layout);
 cudaError_t convert_configure(int layout, int* raster_blocks_per_sm, int* fragment_blocks_per_sm);
 cudaError_t convert_launch(int layout, const ConvertArgs& args, int raster_grid, int fragment_grid, cudaStream_t stream);
+cudaError_t gather_wait_launch(const unsigned long long* xch, uint32_t world, unsigned long long epoch, unsigned long long gcap,
+                               unsigned long long* total_global, cudaStream_t stream);
 cudaError_t mip_down_launch(const uint32_t* src, uint32_t sw, uint32_t sh, uint32_t* dst, uint32_t dw, uint32_t dh,
                             cudaStream_t stream);
 cudaError_t ply_rows_launch(const void* ref96, unsigned long long count, const unsigned long long* d_count,
@@ -50,6 +52,7 @@ struct m2s_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int blocks_per_sm[2] = {0, 0};       // raster kernel (persistent)
     int frag_blocks_per_sm[2] = {0, 0};  // fragment kernel
+    unsigned long long epoch = 0;            // pairs up the ranks' calls of the fused gather
     bool dirty = true;                       // scheduler state needs a memset before the next launch
     // scratch owned by the context (grown on demand)
     void* d_scratch = nullptr;  size_t scratch_bytes = 0;   // REF96 staging for the .ply row layouts
@@ -343,12 +346,18 @@ static uint64_t effective_cap(const m2s_dscene* s, const m2s_params* p, uint64_t
     return std::min(cap, out_capacity);
 }
 
-M2S_EXPORT m2s_status m2s_convert_enqueue(m2s_ctx* ctx, const m2s_dscene* s, const m2s_params* p, void* d_out,
-                                          uint64_t out_capacity, uint64_t* d_keys, uint64_t* d_total, void* stream_) {
+static m2s_status convert_enqueue_impl(m2s_ctx* ctx, const m2s_dscene* s, const m2s_params* p, void* d_out, uint64_t out_capacity,
+                                       uint64_t* d_keys, uint64_t* d_total, void* stream_, const m2s_peers* peers) {
     if (!ctx || !s || !p) { set_error("m2s_convert: NULL argument"); return M2S_E_INVALID; }
     if (p->resolution < 1 || p->resolution > 4096) { set_error("m2s_convert: resolution must be in 1..4096"); return M2S_E_INVALID; }
     if (p->layout > M2S_LAYOUT_PLY_COMPRESSED) { set_error("m2s_convert: unknown layout"); return M2S_E_INVALID; }
-    if (!d_out && out_capacity) { set_error("m2s_convert: output buffer is NULL"); return M2S_E_INVALID; }
+    if (!peers && !d_out && out_capacity) { set_error("m2s_convert: output buffer is NULL"); return M2S_E_INVALID; }
+    if (peers) {
+        if (peers->world < 1 || peers->world > M2S_MAX_PEERS || peers->rank >= peers->world) { set_error("m2s_convert_gather: bad world/rank"); return M2S_E_INVALID; }
+        if (p->layout > M2S_LAYOUT_PACKED56) { set_error("m2s_convert_gather: layouts REF96 and PACKED56 only"); return M2S_E_INVALID; }
+        for (uint32_t r = 0; r < peers->world; ++r)
+            if (!peers->out[r] || !peers->xch[r] || (reinterpret_cast<uintptr_t>(peers->out[r]) & 15u)) { set_error("m2s_convert_gather: NULL or misaligned peer buffer"); return M2S_E_INVALID; }
+    }
     if (!(p->gaussian_std > 0.0f) && p->layout != M2S_LAYOUT_REF96) { set_error("m2s_convert: gaussian_std must be > 0"); return M2S_E_INVALID; }
     uint64_t first = std::min<uint64_t>(p->first_triangle, s->ntri);
     uint64_t count = p->triangle_count;
@@ -393,7 +402,8 @@ M2S_EXPORT m2s_status m2s_convert_enqueue(m2s_ctx* ctx, const m2s_dscene* s, con
     a.cap = cap;
     a.keys = (unsigned long long*)d_keys;
     a.counter = ctx->d_counter;
-    a.total_out = d_total ? (unsigned long long*)d_total : ctx->d_total;
+    // fused gather: the raster kernel's count stays local, the global total goes to d_total after the wait
+    a.total_out = (peers && peers->world > 1) ? ctx->d_total : (d_total ? (unsigned long long*)d_total : ctx->d_total);
     a.sched = ctx->d_sched;
     const int grid = ctx->sm_count * ctx->blocks_per_sm[klayout];
     {   // work-unit size: as large as 32 triangles, but small enough that every warp of the grid gets the
@@ -408,15 +418,37 @@ M2S_EXPORT m2s_status m2s_convert_enqueue(m2s_ctx* ctx, const m2s_dscene* s, con
     a.queue = ctx->d_queue;
     a.queue_cap = ctx->queue_cap;
     a.trace = g_trace;
+    if (peers && peers->world > 1) {
+        a.world = peers->world; a.rank = peers->rank;
+        for (uint32_t r = 0; r < peers->world; ++r) { a.peer_out[r] = (uint8_t*)peers->out[r]; a.peer_xch[r] = (unsigned long long*)peers->xch[r]; }
+        a.epoch = ++ctx->epoch;
+        a.gcap = out_capacity;
+    }
     const int fgrid = ctx->sm_count * ctx->frag_blocks_per_sm[klayout];
     cudaError_t e = convert_launch(klayout, a, grid, fgrid, stream);
     if (e != cudaSuccess) { ctx->dirty = true; set_error(std::string("convert launch: ") + cudaGetErrorString(e)); return M2S_E_CUDA; }
+    if (peers && peers->world > 1)
+        CUDA_TRY(gather_wait_launch((const unsigned long long*)peers->xch[peers->rank], peers->world, a.epoch, out_capacity,
+                                    (unsigned long long*)d_total, stream));
     if (ply_rows) {
         // the count is only known on the device here: the encoder reads it and stops at min(cap, total)
         const uint32_t fmt = p->layout - M2S_LAYOUT_PLY_STANDARD;
         CUDA_TRY(ply_rows_launch(ctx->d_scratch, cap, a.total_out, fmt, a.mult, d_out, stream));
     }
     return M2S_OK;
+}
+
+M2S_EXPORT m2s_status m2s_convert_enqueue(m2s_ctx* ctx, const m2s_dscene* s, const m2s_params* p, void* d_out,
+                                          uint64_t out_capacity, uint64_t* d_keys, uint64_t* d_total, void* stream_) {
+    return convert_enqueue_impl(ctx, s, p, d_out, out_capacity, d_keys, d_total, stream_, nullptr);
+}
+
+M2S_EXPORT m2s_status m2s_convert_gather_enqueue(m2s_ctx* ctx, const m2s_dscene* s, const m2s_params* p, const m2s_peers* peers,
+                                                 uint64_t out_capacity, uint64_t* d_total_global, void* stream_) {
+    if (!peers) { set_error("m2s_convert_gather: peers is NULL"); return M2S_E_INVALID; }
+    if (peers->world <= 1)  // degenerate: plain conversion into the local final buffer
+        return convert_enqueue_impl(ctx, s, p, peers->out[0], out_capacity, nullptr, d_total_global, stream_, nullptr);
+    return convert_enqueue_impl(ctx, s, p, nullptr, out_capacity, nullptr, d_total_global, stream_, peers);
 }
 
 M2S_EXPORT m2s_status m2s_convert(m2s_ctx* ctx, const m2s_dscene* s, const m2s_params* p, void* d_out, uint64_t out_capacity,

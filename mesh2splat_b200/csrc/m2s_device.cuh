@@ -5,6 +5,7 @@
 
 namespace m2s {
 
+constexpr int kMaxPeers = 8;             // GPUs of one NVSwitch domain
 constexpr int kMaxLevels = 5;            // levels 0..4 (GL_TEXTURE_MAX_LEVEL 4, glUtils.cpp:313)
 constexpr int kUnitTris = 32;            // max triangles per work unit (one lane per triangle)
 constexpr int kQueue = 512;              // fragment ids compacted per warp before a flush
@@ -71,6 +72,15 @@ struct ConvertArgs {
     uint2* queue;                      // deferred big-triangle chunks: (triangle, chunk)
     uint32_t queue_cap;
     unsigned long long* trace;         // M2S_TRACE builds only: 16 globaltimer stamps per raster warp
+    // multi-GPU fused gather (world <= 1: off).  peer_out[p] / peer_xch[p] are rank p's final buffer and
+    // exchange block mapped into this process (NVLink peer memory); every rank's fragment kernel stores its
+    // records into ALL final buffers at its global offset.  xch block: [kMaxPeers][4] u64 =
+    // {count, count_epoch, done_epoch, pad} per source rank.
+    uint32_t world, rank;
+    uint8_t* peer_out[kMaxPeers];
+    unsigned long long* peer_xch[kMaxPeers];
+    unsigned long long epoch;
+    unsigned long long gcap;           // capacity of the final buffers (records)
 };
 
 }  // namespace m2s

@@ -102,6 +102,14 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 #else
 #define STAMP(a, slot) do { } while (0)
 #endif
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 constexpr int kSchedStride = 32;  // scheduler words live on separate 128-byte lines
 #define SCHED(a, i) ((a).sched + (i) * kSchedStride)
 __device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
@@ -727,8 +735,17 @@ __global__ void __launch_bounds__(Cfg<LAYOUT>::kWarps * 32) __maxnreg__(Cfg<LAYO
         const uint32_t done = atomicAdd(SCHED(a, 4), 1u);
         if (done == gridDim.x - 1) {
             __threadfence();
-            *a.total_out = *reinterpret_cast<volatile unsigned long long*>(a.counter);
+            const unsigned long long tot = *reinterpret_cast<volatile unsigned long long*>(a.counter);
+            *a.total_out = tot;
             *a.counter = 0ull;
+            if (a.world > 1) {  // fused gather: tell every peer how many records this rank will write
+                const unsigned long long mine = tot < a.cap ? tot : a.cap;
+                for (uint32_t p = 0; p < a.world; ++p) {
+                    a.peer_xch[p][a.rank * 4 + 0] = mine;
+                    __threadfence_system();
+                    st_release_sys(a.peer_xch[p] + a.rank * 4 + 1, a.epoch);
+                }
+            }
             *SCHED(a, 0) = 0; *SCHED(a, 1) = 0; *SCHED(a, 2) = 0; *SCHED(a, 3) = 0; *SCHED(a, 4) = 0;
             __threadfence();
         }
@@ -750,6 +767,22 @@ __global__ void __launch_bounds__(M2S_FRAG_THREADS) fragment_kernel(const __grid
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const unsigned long long total = *reinterpret_cast<const volatile unsigned long long*>(a.total_out);
     const unsigned long long n = total < a.cap ? total : a.cap;
+    // fused gather: wait for every rank's count of this epoch, my records start after the lower ranks'
+    __shared__ unsigned long long s_goff;
+    unsigned long long goff = 0;
+    if (a.world > 1) {
+        if (threadIdx.x == 0) {
+            const unsigned long long* x = a.peer_xch[a.rank];
+            unsigned long long off = 0;
+            for (uint32_t r = 0; r < a.world; ++r) {
+                while (ld_acquire_sys(x + r * 4 + 1) != a.epoch) __nanosleep(100);
+                if (r < a.rank) off += *reinterpret_cast<const volatile unsigned long long*>(x + r * 4);
+            }
+            s_goff = off;
+        }
+        __syncthreads();
+        goff = s_goff;
+    }
     const uint32_t* __restrict__ texb = a.tex_base;
     const bool want_keys = a.keys != nullptr;
     const unsigned long long nwarps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
@@ -879,11 +912,11 @@ __global__ void __launch_bounds__(M2S_FRAG_THREADS) fragment_kernel(const __grid
             if (want_keys) key = ((unsigned long long)fid.x << 24) | (unsigned long long)fid.y;
         }
         __syncwarp();
-        // ---- the warp's records are one contiguous, 16-byte aligned span: straight vector copy ----
-        {
+        // ---- the warp's records are one contiguous span: straight vector copy -----------------------
+        if (a.world <= 1) {
             float4* dst = reinterpret_cast<float4*>(a.out + wbase * (unsigned long long)kStride);
             const float4* src = reinterpret_cast<const float4*>(stage);
-            const uint32_t n16 = nfr * kStride / 16;  // 32*stride is a multiple of 16; a short tail group too (stride*nfr%16==0 or 8)
+            const uint32_t n16 = nfr * kStride / 16;  // 32*stride is a multiple of 16; a short tail group may leave 8 bytes
 #pragma unroll
             for (int j = 0; j < (32 * kStride / 16 + 31) / 32; ++j) {
                 const uint32_t c = lane + 32 * j;
@@ -892,10 +925,50 @@ __global__ void __launch_bounds__(M2S_FRAG_THREADS) fragment_kernel(const __grid
             if ((nfr * kStride) & 8u) {  // odd number of 56-byte records: one trailing 8-byte piece
                 if (lane == 0) reinterpret_cast<float2*>(dst)[n16 * 2] = reinterpret_cast<const float2*>(src)[n16 * 2];
             }
+        } else {
+            // fused gather: the same span goes to the final buffer of EVERY rank (peer stores over NVLink)
+            const unsigned long long gbase = goff + wbase;
+            uint32_t nval = 0;
+            if (gbase < a.gcap) nval = (uint32_t)min((unsigned long long)nfr, a.gcap - gbase);
+            const uint32_t n8 = nval * kStride / 8;  // 8-byte pieces: the global offset may be odd (56-byte records)
+            const float2* src = reinterpret_cast<const float2*>(stage);
+            for (uint32_t p = 0; p < a.world; ++p) {
+                float2* dst = reinterpret_cast<float2*>(a.peer_out[p] + gbase * (unsigned long long)kStride);
+#pragma unroll
+                for (int j = 0; j < 32 * kStride / 8 / 32; ++j) {
+                    const uint32_t c = lane + 32 * j;
+                    if (c < n8) dst[c] = src[c];
+                }
+            }
         }
         if (want_keys && (uint32_t)lane < nfr) a.keys[wbase + lane] = key;
         __syncwarp();
     }
+    if (a.world > 1) {  // last CTA out tells every peer that this rank's records have landed
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t done = atomicAdd(SCHED(a, 6), 1u);
+            if (done == gridDim.x - 1) {
+                *SCHED(a, 6) = 0;
+                __threadfence_system();
+                for (uint32_t p = 0; p < a.world; ++p) st_release_sys(a.peer_xch[p] + a.rank * 4 + 2, a.epoch);
+            }
+        }
+    }
+}
+
+// waits until every rank's records of this epoch have landed in THIS rank's final buffer, publishes the
+// total; one thread — the data path never returns to the host
+__global__ void gather_wait_kernel(const unsigned long long* xch, uint32_t world, unsigned long long epoch,
+                                   unsigned long long gcap, unsigned long long* total_global) {
+    unsigned long long tot = 0;
+    for (uint32_t r = 0; r < world; ++r) {
+        while (ld_acquire_sys(xch + r * 4 + 2) != epoch) __nanosleep(200);
+        tot += *reinterpret_cast<const volatile unsigned long long*>(xch + r * 4);
+    }
+    if (total_global) *total_global = tot;
+    (void)gcap;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1024,6 +1097,12 @@ cudaError_t convert_launch(int layout, const ConvertArgs& args, int raster_grid,
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     return cudaLaunchKernelEx(&cfg, fragment_kernel<1>, args);
+}
+
+cudaError_t gather_wait_launch(const unsigned long long* xch, uint32_t world, unsigned long long epoch, unsigned long long gcap,
+                               unsigned long long* total_global, cudaStream_t stream) {
+    gather_wait_kernel<<<1, 1, 0, stream>>>(xch, world, epoch, gcap, total_global);
+    return cudaGetLastError();
 }
 
 cudaError_t mip_down_launch(const uint32_t* src, uint32_t sw, uint32_t sh, uint32_t* dst, uint32_t dw, uint32_t dh,

@@ -9,6 +9,11 @@ range on its own GPU, and the per-rank buffers are concatenated on every rank:
     payload  all_gather of max-count-padded buffers, then compaction to offsets (rank-major order)
 
 Works with any torch.distributed backend: NCCL on GPUs, gloo in the CPU tests.
+
+PeerGather is the B200-native form of the same step: the final buffer of every rank lives in
+symmetric (peer-mapped) memory and each rank's fragment kernel stores its records straight into all
+of them over NVLink at its rank-major offset (m2s_convert_gather_enqueue) — no collective call, no
+host round trip on the data path.
 """
 from __future__ import annotations
 
@@ -79,3 +84,55 @@ def all_gather_records(local, n_local: int, stride: int, dist, torch, out=None):
         out[off * stride:(off + c[r]) * stride] = gathered[r * mx * stride: r * mx * stride + c[r] * stride]
         off += c[r]
     return out[: total * stride], c
+
+
+class PeerGather:
+    """Final buffers + exchange blocks in torch symmetric memory, wired to m2s_convert_gather_enqueue.
+
+    Every rank constructs one (collectively), then calls convert() the same number of times."""
+
+    def __init__(self, ctx, capacity: int, stride: int, dist, torch):
+        import ctypes as C
+
+        import torch.distributed._symmetric_memory as symm
+
+        from . import _abi
+        self.ctx, self.capacity, self.stride, self.torch = ctx, int(capacity), int(stride), torch
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        if self.world > _abi.MAX_PEERS:
+            raise ValueError("PeerGather supports up to 8 ranks (one NVSwitch domain)")
+        dev = torch.device("cuda", ctx.device)
+        group = dist.group.WORLD
+        self.final = symm.empty(max(1, self.capacity) * self.stride, dtype=torch.uint8, device=dev)
+        self.xch = symm.empty(_abi.MAX_PEERS * 4, dtype=torch.int64, device=dev)
+        self.xch.zero_()
+        self.total = torch.zeros(1, dtype=torch.int64, device=dev)
+        torch.cuda.synchronize(dev)
+        try:
+            hf = symm.rendezvous(self.final, group)
+            hx = symm.rendezvous(self.xch, group)
+        except TypeError:  # older signature: group name
+            hf = symm.rendezvous(self.final, group.group_name)
+            hx = symm.rendezvous(self.xch, group.group_name)
+        self._handles = (hf, hx)
+        dist.barrier()  # every rank has zeroed its exchange block before anyone signals into it
+        self.peers = _abi.m2s_peers()
+        self.peers.world, self.peers.rank = self.world, self.rank
+        for r in range(self.world):
+            self.peers.out[r] = int(hf.buffer_ptrs[r])
+            self.peers.xch[r] = int(hx.buffer_ptrs[r])
+        self._C = C
+
+    def convert_enqueue(self, dscene, params, stream: int = 0) -> None:
+        from ._lib import check, lib
+        C = self._C
+        check(lib().m2s_convert_gather_enqueue(self.ctx.handle, dscene.handle, C.byref(params), C.byref(self.peers),
+                                               self.capacity, self.total.data_ptr(), stream or None))
+
+    def records(self, layout: int):
+        """(structured numpy view of the gathered records, count) — synchronises."""
+        from . import _abi
+        n = int(self.total.item())
+        n = min(n, self.capacity)
+        raw = self.final[: n * self.stride].cpu().numpy()
+        return raw.view(_abi.record_dtype(layout)), n
