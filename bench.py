@@ -222,6 +222,8 @@ def run_ours(args):
 
     def step(timed_events=None):
         flush.zero_()  # evict L2 (126 MB) — untimed
+        if fused:
+            pg.barrier()  # untimed device-side barrier: the ranks enter the timed step together (no host skew in it)
         if timed_events is not None:
             timed_events[0].record(stream)
         n_total = None

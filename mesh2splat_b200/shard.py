@@ -129,9 +129,14 @@ class PeerGather:
         check(lib().m2s_convert_gather_enqueue(self.ctx.handle, dscene.handle, C.byref(params), C.byref(self.peers),
                                                self.capacity, self.total.data_ptr(), stream or None))
 
+    def barrier(self) -> None:
+        """Device-side barrier across the ranks on the current torch stream (symmetric-memory signal pads)."""
+        self._handles[1].barrier()
+
     def records(self, layout: int):
         """(structured numpy view of the gathered records, count) — synchronises."""
         from . import _abi
+        self.torch.cuda.synchronize(self.final.device)  # the kernels may have run on the context's own stream
         n = int(self.total.item())
         n = min(n, self.capacity)
         raw = self.final[: n * self.stride].cpu().numpy()
