@@ -156,7 +156,8 @@ def run_reference(args):
     scene = synth.helmet_standin(2048)
     layout = LAYOUTS[args.layout]
     prep = oracle.Prepared(scene)
-    cores = os.cpu_count() or oracle.max_threads()  # torchrun exports OMP_NUM_THREADS=1: ask for every core explicitly
+    # torchrun exports OMP_NUM_THREADS=1: ask explicitly for every core this process may run on
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     out = None
     for _ in range(max(1, min(args.warmup, 2))):
         n, total, out = prep.convert(DENSITY, layout, out=out, threads=cores)

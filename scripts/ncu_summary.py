@@ -15,9 +15,10 @@ keys = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__b
         "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-        "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "lts__t_bytes.sum", "l1tex__t_bytes.sum",
+        "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "lts__t_bytes.sum", "l1tex__t_bytes.sum", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
         "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__inst_executed_op_global_atom.sum", "smsp__inst_executed_op_global_red.sum"]
-lines = [f"# ncu --set full --clock-control none: m2s::convert_kernel, layout {layout}", "",
+kname = d.get("Kernel Name", ("?", ""))[0]
+lines = [f"# ncu --set full --clock-control none: {kname}, layout {layout}", "",
          f"source report: {os.path.basename(rep)} (gpurun scratch; numbers below are per launch, cold-cache and serialised by ncu)", "",
          "| metric | value | unit |", "|---|---|---|"]
 for k in keys:
@@ -42,7 +43,7 @@ lines += ["", f"DRAM traffic per launch: {traffic/1e6:.2f} MB (read {num('dram__
           "the 126 MB L2 absorbs most of the record writes of one launch, so this is below the algorithmic bytes."]
 # per-source-region instruction split (needs the same build's .so)
 try:
-    sect = "convert_kernelILi0" if layout == "ref96" else "convert_kernelILi1"
+    sect = ("raster_kernel" if "raster" in kname else "fragment_kernel") + ("ILi0" if layout == "ref96" else "ILi1")
     by = subprocess.run([sys.executable, os.path.join(root, "scripts", "ncu_by_line.py"), rep, sect, "25"], capture_output=True, text=True).stdout
     lines += ["", "## hottest source lines (executed warp-instructions, stall samples)", "", "```", by.strip(), "```"]
 except Exception as e:  # noqa: BLE001
@@ -50,6 +51,9 @@ except Exception as e:  # noqa: BLE001
 open(out, "w").write("\n".join(lines) + "\n")
 tj = os.path.join(root, "profiles", "traffic.json")
 t = json.load(open(tj)) if os.path.exists(tj) else {}
-t[layout] = traffic
+key = layout + ("_raster" if "raster" in kname else "_fragment")
+t[key] = traffic
+if layout + "_raster" in t and layout + "_fragment" in t:
+    t[layout] = t[layout + "_raster"] + t[layout + "_fragment"]  # the whole step = both launches
 json.dump(t, open(tj, "w"), indent=1)
 print("wrote", out, "traffic", traffic)
