@@ -19,7 +19,8 @@ pytestmark = pytest.mark.gpu
 def run_both(ctx, scene, R, layout=LAYOUT_REF96, **kw):
     ds = ctx.upload(scene)
     out = ctx.convert(ds, R, layout, want_keys=True, **kw)
-    rec, keys, total = oracle.convert(scene, R, layout, want_keys=True, capacity=out.cap if out.cap else 1, **kw)
+    okw = {k: v for k, v in kw.items() if k != "capacity"}
+    rec, keys, total = oracle.convert(scene, R, layout, want_keys=True, capacity=out.cap if out.cap else 1, **okw)
     ds.free()
     return out, rec, keys, total
 
@@ -249,3 +250,84 @@ def test_helmet_standin_density_512_full_parity(gpu_ctx):
     assert 0.4e6 < out.total < 1.2e6
     out2 = check(gpu_ctx, s, 512, LAYOUT_PACKED56)
     assert out2.total == out.total
+
+
+# ---- CUDA per-triangle stage vs the REFERENCE's geometry shader (committed golden vectors) -------------
+def test_cuda_matches_reference_gs_golden_vectors(gpu_ctx):
+    """tests/golden/ref_shader_vectors.npz holds converterGS.glsl's own outputs (made by
+    tests/golden/make_golden.py from /root/reference).  One primitive per golden triangle with the golden
+    bbox; every gaussian the CUDA path emits for it must carry the reference's Scale and Quaternion bit for
+    bit, and the number of gaussians must equal the oracle's coverage for gl_Position = reference."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_shader_vectors.npz"))
+    tris = g["gs_tris"]
+    n = len(tris)
+    prims = [Primitive(i, 1, (1, 1, 1, 1), -1, -1, -1, tuple(float(v) for v in g["gs_bmin"][i]),
+                       tuple(float(v) for v in g["gs_bmax"][i])) for i in range(n)]
+    s = Scene(tris, prims, [])
+    R = 48
+    out, rec, keys, total = run_both(gpu_ctx, s, R, LAYOUT_REF96, flags=FLAG_UNCAPPED, capacity=n * R * R)
+    assert out.total == total
+    got, gk = out.numpy(), out.keys_numpy()
+    tri = (gk >> np.uint64(24)).astype(np.int64)
+    checked = 0
+    for i in np.unique(tri):
+        m = tri == i
+        sc = got["scale"][m][:, :3]
+        qt = got["rotation"][m]
+        assert np.array_equal(sc.view(np.uint32), np.tile(g["gs_scale"][i].view(np.uint32), (m.sum(), 1))), f"Scale, triangle {i}"
+        assert np.array_equal(qt.view(np.uint32), np.tile(g["gs_quat"][i].view(np.uint32), (m.sum(), 1))), f"Quaternion, triangle {i}"
+        checked += 1
+    assert checked >= n // 2, f"only {checked} of {n} golden triangles produced fragments"
+    assert_records_match(s, LAYOUT_REF96, got, gk, rec, keys)
+
+
+# ---- the other BASELINE configurations at full size: size-independent properties ------------------------
+def _keys_unique_and_in_range(keys, scene, R):
+    assert len(np.unique(keys)) == len(keys)
+    tri = keys >> np.uint64(24)
+    assert tri.max(initial=0) < scene.triangle_count
+    assert ((keys & np.uint64(0xfff)) < R).all() and (((keys >> np.uint64(12)) & np.uint64(0xfff)) < R).all()
+
+
+def test_config3_sponza_standin_reference_cap_and_uncapped(gpu_ctx):
+    """BASELINE config 3: multi-material, R=1024.  With the reference rule the 7 M cap is hit (count keeps
+    counting); uncapped, the total equals the oracle's and every fragment identity is unique."""
+    s = synth.sponza_standin(256)       # same geometry/primitives as the bench stand-in, smaller textures
+    ds = gpu_ctx.upload(s)
+    capped = gpu_ctx.convert(ds, 1024, LAYOUT_PACKED56)
+    assert capped.cap == 7_000_000
+    prep = oracle.Prepared(s)
+    _, total, _ = prep.convert(1024, LAYOUT_PACKED56, capacity=1)
+    assert capped.total == total
+    assert capped.overflow == (total > 7_000_000) and capped.written == min(total, 7_000_000)
+    un = gpu_ctx.convert(ds, 1024, LAYOUT_PACKED56, flags=FLAG_UNCAPPED, capacity=total + 16, want_keys=True)
+    assert un.total == total and un.written == total and not un.overflow
+    _keys_unique_and_in_range(un.keys_numpy(), s, 1024)
+    # every primitive contributes exactly what the oracle says (per-primitive coverage, bit-exact)
+    tri = (un.keys_numpy() >> np.uint64(24)).astype(np.int64)
+    firsts = np.array([p.first_triangle for p in s.primitives] + [s.triangle_count])
+    got = np.histogram(tri, bins=firsts)[0]
+    orec, okeys, _ = oracle.convert(s, 1024, LAYOUT_PACKED56, flags=FLAG_UNCAPPED, capacity=total + 16)
+    want = np.histogram((okeys >> np.uint64(24)).astype(np.int64), bins=firsts)[0]
+    assert np.array_equal(got, want)
+    assert np.array_equal(np.sort(un.keys_numpy()), np.sort(okeys))
+    ds.free()
+
+
+def test_config4_million_triangle_sphere(gpu_ctx):
+    """BASELINE config 4: 1 000 000 triangles, R=256 (most triangles are sub-pixel).  Total and the whole
+    fragment-identity set equal the oracle's; 8 contiguous shards partition it."""
+    s = synth.sphere_1m(256)
+    ds = gpu_ctx.upload(s)
+    out = gpu_ctx.convert(ds, 256, LAYOUT_PACKED56, want_keys=True)
+    orec, okeys, total = oracle.convert(s, 256, LAYOUT_PACKED56)
+    assert out.total == total and 50_000 < total < 400_000
+    assert np.array_equal(np.sort(out.keys_numpy()), np.sort(okeys))
+    from mesh2splat_b200.shard import plan_shards
+    parts = []
+    for first, count in plan_shards(s.triangle_count, 8):
+        o = gpu_ctx.convert(ds, 256, LAYOUT_PACKED56, first_triangle=first, triangle_count=count, want_keys=True)
+        parts.append(o.keys_numpy())
+    assert np.array_equal(np.sort(np.concatenate(parts)), np.sort(okeys))
+    ds.free()
