@@ -60,7 +60,6 @@ struct m2s_ctx {
     unsigned long long* d_keys = nullptr; size_t keys_bytes = 0;
     // intermediates between the raster and the fragment kernel
     void* d_ids = nullptr;      size_t ids_bytes = 0;       // uint2 per fragment
-    void* d_planes = nullptr;   size_t planes_bytes = 0;    // 144 B per triangle of the shard
     void* d_trifrag = nullptr;  size_t trifrag_bytes = 0;   // TriFragT per triangle of the shard
 };
 
@@ -175,7 +174,6 @@ M2S_EXPORT void m2s_ctx_destroy(m2s_ctx* c) {
     if (c->d_out) cudaFreeAsync(c->d_out, c->stream);
     if (c->d_keys) cudaFreeAsync(c->d_keys, c->stream);
     if (c->d_ids) cudaFreeAsync(c->d_ids, c->stream);
-    if (c->d_planes) cudaFreeAsync(c->d_planes, c->stream);
     if (c->d_trifrag) cudaFreeAsync(c->d_trifrag, c->stream);
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_sched); cudaFree(c->d_counter); cudaFree(c->d_total); cudaFree(c->d_queue);
@@ -376,7 +374,6 @@ static m2s_status convert_enqueue_impl(m2s_ctx* ctx, const m2s_dscene* s, const 
     if (reinterpret_cast<uintptr_t>(kout) & 15u) { set_error("m2s_convert: the output buffer must be 16-byte aligned"); return M2S_E_INVALID; }
     {   // scratch between the two kernels (grown on demand, kept by the context)
         m2s_status st = grow(ctx, &ctx->d_ids, &ctx->ids_bytes, std::max<uint64_t>(cap, 1) * sizeof(uint2));
-        if (st == M2S_OK) st = grow(ctx, &ctx->d_planes, &ctx->planes_bytes, std::max<uint64_t>(count, 1) * (size_t)kTriBytes);
         if (st == M2S_OK) st = grow(ctx, &ctx->d_trifrag, &ctx->trifrag_bytes, std::max<uint64_t>(count, 1) * tri_frag_bytes(klayout));
         if (st != M2S_OK) return st;
     }
@@ -396,7 +393,6 @@ static m2s_status convert_enqueue_impl(m2s_ctx* ctx, const m2s_dscene* s, const 
     a.half_R = (float)p->resolution * 0.5f;
     a.mult = p->gaussian_std / (float)p->resolution;
     a.frag_ids = (uint2*)ctx->d_ids;
-    a.tri_planes = (const float4*)ctx->d_planes;
     a.tri_frag = (unsigned char*)ctx->d_trifrag;
     a.out = (uint8_t*)kout;
     a.cap = cap;

@@ -54,9 +54,9 @@ struct ConvertArgs {
     uint32_t R;
     float half_R;
     float mult;  // sigma / R (SceneManager.cpp:668)
-    // intermediates between the two kernels (context-owned scratch, L2-resident at the sizes of interest)
+    // intermediates between the two kernels (context-owned scratch, L2-resident at the sizes of interest);
+    // the fragment kernel reads the vertices themselves from `tris`
     uint2* frag_ids;                   // {global triangle, y << 12 | x} per fragment; index = output record index
-    const float4* tri_planes;          // 9 float4 per triangle of the shard: attribute planes c0 | cx | cy
     unsigned char* tri_frag;           // one TriFragT per triangle of the shard
     uint8_t* out;
     unsigned long long cap;

@@ -99,7 +99,11 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 #ifdef M2S_TRACE
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define STAMP(a, slot) do { if ((a).trace && lane == 0) (a).trace[((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * 16 + (slot)] = gtime(); } while (0)
+#define STAMPV(a, slot, v) do { if ((a).trace && lane == 0) (a).trace[((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * 16 + (slot)] = (v); } while (0)
+#define TNOW() gtime()
 #else
+#define STAMPV(a, slot, v) do { } while (0)
+#define TNOW() 0ull
 #define STAMP(a, slot) do { } while (0)
 #endif
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
@@ -155,7 +159,7 @@ struct __align__(8) TexRef {  // 16 B — one map, resolved for one triangle
     unsigned short w0, h0, w1, h1;
 };
 template <int NMAPS>
-struct __align__(16) TriFragT {  // 64 + 16*NMAPS bytes
+struct __align__(16) TriFragT {  // 128 + 16*NMAPS bytes
     float quat[4];    // (w,x,y,z)
     float scale[3];   // raw (REF96) or log(scale * sigma/R)
     unsigned tri;     // global triangle index
@@ -163,6 +167,12 @@ struct __align__(16) TriFragT {  // 64 + 16*NMAPS bytes
     float frac[3];    // trilinear blend per map (0 => single level)
     unsigned meta;    // bits 0-2: map m has the same level sizes as map 0 (=> same footprint and weights);
                       // bits 4-15: x0, bits 16-27: y0 of the candidate pixel box
+    // exact barycentrics: lambda_k(px,py) = (E0_k + A_k (px-x0) + B_k (py-y0)) * inv_area  (GL 4.6 eq. 14.9, w = 1)
+    long long E0[3];
+    int A[3];
+    int B[3];
+    float inv_area;
+    unsigned pad;
     TexRef tex[NMAPS];
 };
 
@@ -330,29 +340,21 @@ __device__ __noinline__ uint32_t setup_triangle(const float4* __restrict__ t4, u
     tr.x0 = (unsigned short)x0; tr.y0 = (unsigned short)y0;
     tr.w = (unsigned short)(x1 - x0 + 1); tr.h = (unsigned short)(y1 - y0 + 1);
 
-    // Attribute plane equations, in place over the staged vertex data: attr(px,py) = c0 + cx*(px-x0) +
-    // cy*(py-y0), from the barycentric planes lambda_k = E_k / area2 (GL 4.6 14.6.1 eq. 14.9 with w = 1).
-    // Layout afterwards: t4[0..2] = c0 (12 attrs), t4[3..5] = cx, t4[6..8] = cy.
-    float dudx, dvdx, dudy, dvdy;
+    // barycentric state for the fragment kernel (exact integers, relative to the box origin) and the
+    // per-pixel steps of the mesh uv (constant per triangle: uv is affine in window space)
+    float dudx = 0.f, dvdx = 0.f, dudy = 0.f, dvdy = 0.f;
     {
-        float lam0[3], ldx[3], ldy[3];
+        const float uvx[3] = {q2.z, q5.z, q8.z}, uvy[3] = {q2.w, q5.w, q8.w};
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            lam0[k] = __ll2float_rn(tr.C[k] + (long long)Ak[k] * x0 + (long long)Bk[k] * y0) * ia;
-            ldx[k] = (float)Ak[k] * ia;
-            ldy[k] = (float)Bk[k] * ia;
+            tf.E0[k] = tr.C[k] + (long long)Ak[k] * x0 + (long long)Bk[k] * y0;
+            tf.A[k] = Ak[k]; tf.B[k] = Bk[k];
+            const float ca = (float)Ak[k] * ia, cb = (float)Bk[k] * ia;
+            dudx += uvx[k] * ca; dvdx += uvy[k] * ca;
+            dudy += uvx[k] * cb; dvdy += uvy[k] * cb;
         }
-        float4* w4 = const_cast<float4*>(t4);
-        const float4 q1 = t4[1], q4 = t4[4], q7 = t4[7];  // every input is in registers before the first store
-#define M2S_PLANE4(L, va, vb, vc) make_float4(L[0] * va.x + L[1] * vb.x + L[2] * vc.x, L[0] * va.y + L[1] * vb.y + L[2] * vc.y, \
-                                              L[0] * va.z + L[1] * vb.z + L[2] * vc.z, L[0] * va.w + L[1] * vb.w + L[2] * vc.w)
-        w4[0] = M2S_PLANE4(lam0, q0, q3, q6); w4[1] = M2S_PLANE4(lam0, q1, q4, q7); w4[2] = M2S_PLANE4(lam0, q2, q5, q8);
-        w4[3] = M2S_PLANE4(ldx, q0, q3, q6); w4[4] = M2S_PLANE4(ldx, q1, q4, q7);
-        w4[6] = M2S_PLANE4(ldy, q0, q3, q6); w4[7] = M2S_PLANE4(ldy, q1, q4, q7);
-        const float4 cxc = M2S_PLANE4(ldx, q2, q5, q8), cyc = M2S_PLANE4(ldy, q2, q5, q8);
-        w4[5] = cxc; w4[8] = cyc;
-#undef M2S_PLANE4
-        dudx = cxc.z; dvdx = cxc.w; dudy = cyc.z; dvdy = cyc.w;  // per-pixel steps of the mesh uv
+        tf.inv_area = ia;
+        tf.pad = 0;
     }
 
     // sampler state (GL 4.6 8.14): the steps of the mesh uv are constant per triangle, so lambda, the
@@ -587,21 +589,35 @@ __global__ void __launch_bounds__(Cfg<LAYOUT>::kWarps * 32) __maxnreg__(Cfg<LAYO
             if (small) {
                 e0 = (int)E0; e1 = (int)E1; e2 = (int)E2;
                 r0 = b0 - (w - 1) * a0; r1 = b1 - (w - 1) * a1; r2 = b2 - (w - 1) * a2;  // step to the next row's first pixel
-            } else if (cnt > kBigCand) {  // defer: push chunks to the global queue
-                const uint32_t nch = (cnt + kChunkCand - 1) / kChunkCand;
-                uint32_t old = *reinterpret_cast<volatile uint32_t*>(SCHED(a, 2));
-                bool ok = false;
-                while (old + nch <= a.queue_cap) {
-                    const uint32_t prev = atomicCAS(SCHED(a, 2), old, old + nch);
-                    if (prev == old) { ok = true; break; }
-                    old = prev;
-                }
-                if (ok) {
+            }
+        }
+        // big triangles: push their chunks to the global queue.  ONE atomicAdd per warp reserves the slots
+        // (a per-lane CAS loop collapses under contention: 15 k simultaneous pushers cost 19 ms)
+        {
+            const bool big = cnt > kBigCand && !small;
+            const uint32_t nch = big ? (cnt + kChunkCand - 1) / kChunkCand : 0u;
+            uint32_t incl = nch;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
+            }
+            const uint32_t wtotal = __shfl_sync(0xffffffffu, incl, 31);
+            if (wtotal) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(SCHED(a, 2), wtotal);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (big) {
+                    const uint32_t first = base + (incl - nch);
                     const uint32_t tg = a.tri_first + t0 + lane;
-                    for (uint32_t i = 0; i < nch; ++i) a.queue[old + i] = make_uint2(tg, i);
+                    if (first + nch <= a.queue_cap) {
+                        for (uint32_t i = 0; i < nch; ++i) a.queue[first + i] = make_uint2(tg, i);
+                        cnt = 0;
+                        deferred = true;
+                    } else {  // queue full: the in-range slots become no-ops, the triangle is rasterised here
+                        for (uint32_t i = first; i < min(first + nch, a.queue_cap); ++i) a.queue[i] = make_uint2(0xffffffffu, 0u);
+                    }
                     __threadfence();
-                    cnt = 0;
-                    deferred = true;
                 }
             }
         }
@@ -610,12 +626,11 @@ __global__ void __launch_bounds__(Cfg<LAYOUT>::kWarps * 32) __maxnreg__(Cfg<LAYO
         // every chunk this unit defers is in the global queue now (pushers fenced): count the unit as
         // "past set-up" so idle warps only wait for set-ups in flight, not for whole units
         if (lane == 0) atomicAdd(SCHED(a, 1), 1u);
-        // the unit's per-triangle records (plane equations + shading state) go to global memory for the
-        // fragment kernel: two TMA bulk stores straight out of this warp's shared-memory slice
+        // the unit's per-triangle records (barycentric + shading state) go to global memory for the fragment
+        // kernel: one TMA bulk store straight out of this warp's shared-memory slice
         if (__any_sync(0xffffffffu, cnt != 0 || deferred)) {
             if (lane == 0) {
                 fence_proxy_async();
-                tma_store_1d(const_cast<float4*>(a.tri_planes) + (size_t)t0 * 9, wb.tri, ntri * kTriBytes);
                 tma_store_1d(a.tri_frag + (size_t)t0 * sizeof(TriFragT<C::kMaps>), wb.frag, ntri * (uint32_t)sizeof(TriFragT<C::kMaps>));
                 tma_store_commit();
             }
@@ -699,17 +714,21 @@ __global__ void __launch_bounds__(Cfg<LAYOUT>::kWarps * 32) __maxnreg__(Cfg<LAYO
     STAMP(a, 8);
     uint32_t tail = 0;
     if (lane == 0) tail = ld_acquire_u32(SCHED(a, 2));
-    tail = __shfl_sync(0xffffffffu, tail, 0);
+    tail = min(__shfl_sync(0xffffffffu, tail, 0), a.queue_cap);
+    unsigned long long n_items = 0, t_setup = 0, t_rast = 0, t_load = 0;
     while (tail) {
+        const unsigned long long ta = TNOW();
         uint32_t it = 0;
         if (lane == 0) it = atomicAdd(SCHED(a, 3), 1u);
         it = __shfl_sync(0xffffffffu, it, 0);
         if (it >= tail) break;
         const uint2 item = a.queue[it];
+        if (item.x == 0xffffffffu) continue;  // slot of a push that did not fit
         if (lane == 0) tma_store_wait_read();
         __syncwarp();
         if (lane < 9) wb.tri[lane] = a.tris[(size_t)item.x * 9 + lane];
         __syncwarp();
+        const unsigned long long tb = TNOW();
         uint32_t c = 0;
         TriRaster tr;
         tr.w = 1; tr.h = 0; tr.x0 = 0; tr.y0 = 0; tr.incl = 0;
@@ -717,12 +736,16 @@ __global__ void __launch_bounds__(Cfg<LAYOUT>::kWarps * 32) __maxnreg__(Cfg<LAYO
         if (lane == 0) c = setup_triangle<LAYOUT>(wb.tri, item.x, a, tr, wb.frag[0]);
         c = __shfl_sync(0xffffffffu, c, 0);
         __syncwarp();
+        const unsigned long long tc = TNOW();
         const uint32_t c0 = item.y * kChunkCand, c1 = min(c, c0 + kChunkCand);
         raster_one<LAYOUT>(a, wb, qn, 0u, c0, c1, lane, tr);
         flush_ids<LAYOUT>(a, wb, qn, lane);
         qn = 0;
         __syncwarp();
+        const unsigned long long td = TNOW();
+        ++n_items; t_load += tb - ta; t_setup += tc - tb; t_rast += td - tc;
     }
+    STAMPV(a, 12, n_items); STAMPV(a, 13, t_load); STAMPV(a, 14, t_setup); STAMPV(a, 15, t_rast);
 
     STAMP(a, 9);
     if (lane == 0) tma_store_wait_all();  // record stores are complete (not just read) before the kernel ends
@@ -796,11 +819,14 @@ __global__ void __launch_bounds__(M2S_FRAG_THREADS) fragment_kernel(const __grid
             const int py = (fid.y >> 12) & 0xfff, px = fid.y & 0xfff;
             const TriFragT<C::kMaps> tf = *reinterpret_cast<const TriFragT<C::kMaps>*>(a.tri_frag + (size_t)tl * sizeof(TriFragT<C::kMaps>));
             const unsigned meta = tf.meta;
-            const float dx = u2f((uint32_t)(px - (int)((meta >> 4) & 0xfffu))), dy = u2f((uint32_t)(py - (int)((meta >> 16) & 0xfffu)));
-            const float4* __restrict__ v = a.tri_planes + (size_t)tl * 9;  // plane equations: c0 | cx | cy
+            const int dxi = px - (int)((meta >> 4) & 0xfffu), dyi = py - (int)((meta >> 16) & 0xfffu);
+            const float l0 = __ll2float_rn(tf.E0[0] + (long long)tf.A[0] * dxi + (long long)tf.B[0] * dyi) * tf.inv_area;
+            const float l1 = __ll2float_rn(tf.E0[1] + (long long)tf.A[1] * dxi + (long long)tf.B[1] * dyi) * tf.inv_area;
+            const float l2 = __ll2float_rn(tf.E0[2] + (long long)tf.A[2] * dxi + (long long)tf.B[2] * dyi) * tf.inv_area;
+            const float4* __restrict__ v = a.tris + (size_t)fid.x * 9;  // 3 x {pos3 nrm3 tan4 uv2}, L2-resident
             // uv first: the texel addresses depend on nothing else
-            const float4 c0c = __ldg(v + 2), cxc = __ldg(v + 5), cyc = __ldg(v + 8);
-            const float u = c0c.z + cxc.z * dx + cyc.z * dy, vv = c0c.w + cxc.w * dx + cyc.w * dy;
+            const float4 a2 = __ldg(v + 2), b2 = __ldg(v + 5), c2 = __ldg(v + 8);
+            const float u = l0 * a2.z + l1 * b2.z + l2 * c2.z, vv = l0 * a2.w + l1 * b2.w + l2 * c2.w;
 
             // ---- issue every texel load of every bound map back to back ----
             uint32_t tx[C::kMaps][8];
@@ -828,9 +854,9 @@ __global__ void __launch_bounds__(M2S_FRAG_THREADS) fragment_kernel(const __grid
                 tx[m][6] = two[m] ? __ldg(texb + (o1 + bl[m][1].i01)) : 0u; tx[m][7] = two[m] ? __ldg(texb + (o1 + bl[m][1].i11)) : 0u;
             }
             // ---- interpolate the remaining varyings while the loads are in flight ----
-            const float4 c0a = __ldg(v + 0), cxa = __ldg(v + 3), cya = __ldg(v + 6);
-            const float Px = c0a.x + cxa.x * dx + cya.x * dy, Py = c0a.y + cxa.y * dx + cya.y * dy,
-                        Pz = c0a.z + cxa.z * dx + cya.z * dy;
+            const float4 a0 = __ldg(v + 0), b0 = __ldg(v + 3), c0 = __ldg(v + 6);
+            const float Px = l0 * a0.x + l1 * b0.x + l2 * c0.x, Py = l0 * a0.y + l1 * b0.y + l2 * c0.y,
+                        Pz = l0 * a0.z + l1 * b0.z + l2 * c0.z;
             float* srec = reinterpret_cast<float*>(stage + lane * kStride);
 
             // colour (converterFS.glsl:55-62,99)
@@ -851,9 +877,9 @@ __global__ void __launch_bounds__(M2S_FRAG_THREADS) fragment_kernel(const __grid
             cr *= tf.factor[0]; cg *= tf.factor[1]; cb *= tf.factor[2]; ca *= tf.factor[3];
 
             if (LAYOUT == 0) {
-                const float Nx = c0a.w + cxa.w * dx + cya.w * dy;
-                const float4 c0b = __ldg(v + 1), cxb = __ldg(v + 4), cyb = __ldg(v + 7);
-                const float Ny = c0b.x + cxb.x * dx + cyb.x * dy, Nz = c0b.y + cxb.y * dx + cyb.y * dy;
+                const float Nx = l0 * a0.w + l1 * b0.w + l2 * c0.w;
+                const float4 a1 = __ldg(v + 1), b1 = __ldg(v + 4), c1 = __ldg(v + 7);
+                const float Ny = l0 * a1.x + l1 * b1.x + l2 * c1.x, Nz = l0 * a1.y + l1 * b1.y + l2 * c1.y;
                 float nx = Nx, ny = Ny, nz = Nz;
                 constexpr int MN = C::kMaps > 1 ? 1 : 0, MM = C::kMaps > 2 ? 2 : 0;
                 if (has[MN]) {  // :64-77 TBN
@@ -866,8 +892,8 @@ __global__ void __launch_bounds__(M2S_FRAG_THREADS) fragment_kernel(const __grid
                         my += f * (filt<1>(bl[MN][1], tx[MN][4], tx[MN][5], tx[MN][6], tx[MN][7]) - my);
                         mz += f * (filt<2>(bl[MN][1], tx[MN][4], tx[MN][5], tx[MN][6], tx[MN][7]) - mz);
                     }
-                    const float Tx = c0b.z + cxb.z * dx + cyb.z * dy, Ty = c0b.w + cxb.w * dx + cyb.w * dy;
-                    const float Tz = c0c.x + cxc.x * dx + cyc.x * dy, Tw = c0c.y + cxc.y * dx + cyc.y * dy;
+                    const float Tx = l0 * a1.z + l1 * b1.z + l2 * c1.z, Ty = l0 * a1.w + l1 * b1.w + l2 * c1.w;
+                    const float Tz = l0 * a2.x + l1 * b2.x + l2 * c2.x, Tw = l0 * a2.y + l1 * b2.y + l2 * c2.y;
                     float rx = mx * 2.0f - 1.0f, ry = my * 2.0f - 1.0f, rz = mz * 2.0f - 1.0f;
                     float inv = rsqrtf(rx * rx + ry * ry + rz * rz);
                     rx *= inv; ry *= inv; rz *= inv;

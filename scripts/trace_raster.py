@@ -8,7 +8,7 @@ layout = {"ref96": 0, "packed56": 1}[sys.argv[1] if len(sys.argv) > 1 else "pack
 R = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 which = sys.argv[3] if len(sys.argv) > 3 else "helmet"
 ctx = Context(0)
-scene = synth.helmet_standin(2048) if which == "helmet" else synth.unit_quad()
+scene = {"helmet": lambda: synth.helmet_standin(2048), "quad": synth.unit_quad, "dh": lambda: synth.damaged_helmet_standin(2048)}[which]()
 ds = ctx.upload(scene)
 nw = 148 * 16
 tr = torch.zeros(nw * 16, dtype=torch.int64, device="cuda")
@@ -26,3 +26,6 @@ for k, n in enumerate(names):
     if len(v):
         r = (v - t0) / 1e3
         print(f"{n:12s} n={len(v):5d}  min {r.min():7.2f}  p50 {np.median(r):7.2f}  p90 {np.percentile(r, 90):7.2f}  max {r.max():7.2f} us")
+it = t[:, 12]
+print("drain items/warp: mean %.1f max %d; per-item us: load %.2f setup %.2f raster+flush %.2f" % (
+    it.mean(), it.max(), t[:, 13].sum() / max(it.sum(), 1) / 1e3, t[:, 14].sum() / max(it.sum(), 1) / 1e3, t[:, 15].sum() / max(it.sum(), 1) / 1e3))
