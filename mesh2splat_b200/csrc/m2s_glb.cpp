@@ -14,8 +14,8 @@
 //   setupMeshBuffers  :468-576  per-primitive bbox = running union over primitives 0..k
 //   loadTextures + glUtils::generateTextures: RGBA8 images (tinygltf forces 4 channels,
 //                               thirdParty/tiny_gltf.h:2609)
-// No third-party code: own GLB/JSON reader, own inflate + PNG decoder.  JPEG images are NOT
-// supported yet (M2S_E_FORMAT) — see DESIGN.md.
+// No third-party code: own GLB/JSON reader, own inflate + PNG decoder, own baseline-JPEG decoder
+// (progressive JPEG is rejected with M2S_E_FORMAT).
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -324,9 +324,185 @@ Image decode_png(const uint8_t* d, size_t n) {
     return out;
 }
 
+
+// ---- JPEG (baseline sequential DCT, 8-bit, Huffman; 1 or 3 components, any sampling up to 2x2, restart
+// intervals) -> RGBA8.  Progressive / arithmetic / 12-bit files are rejected (M2S_E_FORMAT).  IDCT: separable
+// float reference form (exact to the DCT definition, rounded once); chroma upsampling: the 3:1 triangle
+// filter stb_image (tinygltf's decoder) and libjpeg use.  Decoders differ by +-1..2 code values in rounding,
+// inside the 2/255 colour tolerance the path states.
+struct JpegDecoder {
+    const uint8_t* p; const uint8_t* end;
+    struct Comp { int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0, dcpred = 0; std::vector<uint8_t> plane; int pw = 0, ph = 0; };
+    uint16_t qt[4][64]; bool have_qt[4] = {false, false, false, false};
+    struct HT { uint8_t bits[17]; uint8_t vals[256]; int mincode[17], maxcode[18], valptr[17]; bool ok = false; } dc[4], ac[4];
+    std::vector<Comp> comps; int W = 0, H = 0, restart = 0;
+    uint32_t bitbuf = 0; int bitcnt = 0; bool hit_marker = false;
+
+    static constexpr uint8_t zz[64] = {0,1,8,16,9,2,3,10,17,24,32,25,18,11,4,5,12,19,26,33,40,48,41,34,27,20,13,6,7,14,21,28,35,42,49,56,57,50,43,36,29,22,15,23,30,37,44,51,58,59,52,45,38,31,39,46,53,60,61,54,47,55,62,63};
+
+    int u8() { if (p >= end) throw FormatError("jpeg: truncated"); return *p++; }
+    int u16() { const int a = u8(); return (a << 8) | u8(); }
+    void build(HT& t) {
+        int code = 0, k = 0;
+        for (int l = 1; l <= 16; ++l) {
+            t.valptr[l] = k; t.mincode[l] = code;
+            code += t.bits[l]; k += t.bits[l];
+            t.maxcode[l] = t.bits[l] ? code - 1 : -1;
+            code <<= 1;
+        }
+        t.maxcode[17] = 0x7fffffff; t.ok = true;
+    }
+    int getbit() {
+        if (!bitcnt) {
+            int b = 0;
+            if (!hit_marker) {
+                if (p >= end) { hit_marker = true; }
+                else {
+                    b = *p++;
+                    if (b == 0xff) {
+                        const int b2 = p < end ? *p : 0xd9;
+                        if (b2 == 0) ++p;
+                        else { hit_marker = true; --p; b = 0; }
+                    }
+                }
+            }
+            bitbuf = (uint32_t)b; bitcnt = 8;
+        }
+        --bitcnt;
+        return (bitbuf >> bitcnt) & 1;
+    }
+    int getbits(int n) { int v = 0; while (n--) v = (v << 1) | getbit(); return v; }
+    int decode(const HT& t) {
+        int code = 0;
+        for (int l = 1; l <= 16; ++l) {
+            code = (code << 1) | getbit();
+            if (t.maxcode[l] >= 0 && code <= t.maxcode[l] && code >= t.mincode[l]) return t.vals[t.valptr[l] + code - t.mincode[l]];
+        }
+        throw FormatError("jpeg: bad huffman code");
+    }
+    static int extend(int v, int n) { return (n && v < (1 << (n - 1))) ? v - (1 << n) + 1 : v; }
+    void idct_store(const int* blk, const uint16_t* q, uint8_t* dst, int stride) {
+        static float C[8][8]; static bool init = false;
+        if (!init) { for (int x = 0; x < 8; ++x) for (int u = 0; u < 8; ++u) C[x][u] = (u ? 1.0f : 0.70710678f) * 0.5f * std::cos((2 * x + 1) * u * 3.14159265358979f / 16.0f); init = true; }
+        float f[64], t[64];
+        for (int i = 0; i < 64; ++i) f[zz[i]] = (float)(blk[i] * (int)q[i]);
+        for (int y = 0; y < 8; ++y) for (int x = 0; x < 8; ++x) { float s = 0; for (int u = 0; u < 8; ++u) s += C[x][u] * f[y * 8 + u]; t[y * 8 + x] = s; }
+        for (int x = 0; x < 8; ++x) for (int y = 0; y < 8; ++y) {
+            float s = 0; for (int v = 0; v < 8; ++v) s += C[y][v] * t[v * 8 + x];
+            const int o = (int)std::lrintf(s + 128.0f);
+            dst[y * stride + x] = (uint8_t)(o < 0 ? 0 : (o > 255 ? 255 : o));
+        }
+    }
+    Image run() {
+        if (u16() != 0xffd8) throw FormatError("jpeg: no SOI");
+        bool sos_done = false;
+        while (!sos_done) {
+            int m = u8();
+            if (m != 0xff) continue;
+            while ((m = u8()) == 0xff) {}
+            if (m == 0xd8 || m == 0x01 || (m >= 0xd0 && m <= 0xd7)) continue;
+            if (m == 0xd9) throw FormatError("jpeg: no image data");
+            const int len = u16();
+            const uint8_t* seg_end = p + len - 2;
+            if (len < 2 || seg_end > end) throw FormatError("jpeg: bad segment length");
+            if (m == 0xdb) {
+                while (p < seg_end) { const int pq = u8(); const int tq = pq & 15; if (tq > 3) throw FormatError("jpeg: bad DQT"); for (int i = 0; i < 64; ++i) qt[tq][i] = (uint16_t)((pq >> 4) ? u16() : u8()); have_qt[tq] = true; }
+            } else if (m == 0xc4) {
+                while (p < seg_end) {
+                    const int tc = u8(); const int th = tc & 15; if (th > 3) throw FormatError("jpeg: bad DHT");
+                    HT& t = (tc >> 4) ? ac[th] : dc[th];
+                    int n = 0; t.bits[0] = 0;
+                    for (int l = 1; l <= 16; ++l) { t.bits[l] = (uint8_t)u8(); n += t.bits[l]; }
+                    if (n > 256) throw FormatError("jpeg: bad DHT");
+                    for (int i = 0; i < n; ++i) t.vals[i] = (uint8_t)u8();
+                    build(t);
+                }
+            } else if (m == 0xc0 || m == 0xc1) {
+                if (u8() != 8) throw FormatError("jpeg: only 8-bit samples are supported");
+                H = u16(); W = u16();
+                const int nc = u8();
+                if (!W || !H || W > 32768 || H > 32768 || (nc != 1 && nc != 3)) throw FormatError("jpeg: unsupported frame");
+                comps.resize(nc);
+                for (auto& c : comps) { c.id = u8(); const int hv = u8(); c.h = hv >> 4; c.v = hv & 15; c.tq = u8(); if (c.h < 1 || c.h > 2 || c.v < 1 || c.v > 2 || c.tq > 3) throw FormatError("jpeg: unsupported sampling"); }
+            } else if (m == 0xc2 || (m >= 0xc3 && m <= 0xcf && m != 0xc4 && m != 0xc8 && m != 0xcc)) {
+                throw FormatError("jpeg: progressive / lossless / arithmetic JPEG is not supported");
+            } else if (m == 0xdd) { restart = u16(); }
+            else if (m == 0xda) {
+                const int ns = u8();
+                if (comps.empty() || ns != (int)comps.size()) throw FormatError("jpeg: unsupported scan");
+                for (int i = 0; i < ns; ++i) { const int id = u8(); const int t = u8(); bool f = false; for (auto& c : comps) if (c.id == id) { c.td = t >> 4; c.ta = t & 15; f = true; } if (!f) throw FormatError("jpeg: bad scan component"); }
+                p += 3;
+                sos_done = true;
+                continue;
+            }
+            p = seg_end;
+        }
+        int hmax = 1, vmax = 1;
+        for (auto& c : comps) { hmax = std::max(hmax, c.h); vmax = std::max(vmax, c.v); if (!have_qt[c.tq] || !dc[c.td].ok || !ac[c.ta].ok) throw FormatError("jpeg: missing table"); }
+        const int mcuw = 8 * hmax, mcuh = 8 * vmax, mx = (W + mcuw - 1) / mcuw, my = (H + mcuh - 1) / mcuh;
+        for (auto& c : comps) { c.pw = mx * c.h * 8; c.ph = my * c.v * 8; c.plane.assign((size_t)c.pw * c.ph, 0); }
+        int rst_left = restart;
+        for (int y = 0; y < my; ++y) for (int x = 0; x < mx; ++x) {
+            if (restart && rst_left == 0) {  // RSTn: byte-align, skip the marker, reset predictors
+                bitcnt = 0; hit_marker = false;
+                while (p + 1 < end && !(p[0] == 0xff && p[1] >= 0xd0 && p[1] <= 0xd7)) ++p;
+                if (p + 1 < end) p += 2;
+                for (auto& c : comps) c.dcpred = 0;
+                rst_left = restart;
+            }
+            for (auto& c : comps) for (int by = 0; by < c.v; ++by) for (int bx = 0; bx < c.h; ++bx) {
+                int blk[64] = {0};
+                const int t = decode(dc[c.td]);
+                c.dcpred += extend(getbits(t), t);
+                blk[0] = c.dcpred;
+                for (int k = 1; k < 64;) {
+                    const int rs = decode(ac[c.ta]); const int r = rs >> 4, sz = rs & 15;
+                    if (!sz) { if (r == 15) { k += 16; continue; } break; }
+                    k += r; if (k > 63) throw FormatError("jpeg: bad AC run");
+                    blk[k++] = extend(getbits(sz), sz);
+                }
+                idct_store(blk, qt[c.tq], c.plane.data() + ((size_t)(y * c.v + by) * 8) * c.pw + (size_t)(x * c.h + bx) * 8, c.pw);
+            }
+            if (restart) --rst_left;
+        }
+        // full-resolution sample of a (possibly 2x sub-sampled) component: 3:1 triangle filter along each
+        // sub-sampled axis, the "fancy upsampling" both stb_image (tinygltf's decoder) and libjpeg use
+        auto sample = [&](const Comp& c, int x, int y) -> float {
+            const int sx = hmax / c.h, sy = vmax / c.v;  // 1 or 2
+            const int cw = (W * c.h + hmax - 1) / hmax, ch = (H * c.v + vmax - 1) / vmax;  // valid extent of the plane
+            auto at = [&](int px, int py) { px = px < 0 ? 0 : (px >= cw ? cw - 1 : px); py = py < 0 ? 0 : (py >= ch ? ch - 1 : py); return (float)c.plane[(size_t)py * c.pw + px]; };
+            const int ix = sx == 2 ? x >> 1 : x, iy = sy == 2 ? y >> 1 : y;
+            const int nx = sx == 2 ? ((x & 1) ? ix + 1 : ix - 1) : ix, ny = sy == 2 ? ((y & 1) ? iy + 1 : iy - 1) : iy;
+            const float wx = sx == 2 ? 0.25f : 0.0f, wy = sy == 2 ? 0.25f : 0.0f;
+            const float top = at(ix, iy) * (1.0f - wx) + at(nx, iy) * wx, bot = at(ix, ny) * (1.0f - wx) + at(nx, ny) * wx;
+            return top * (1.0f - wy) + bot * wy;
+        };
+        Image out; out.w = (uint32_t)W; out.h = (uint32_t)H; out.rgba.resize((size_t)W * H * 4);
+        for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) {
+            uint8_t* o = &out.rgba[((size_t)y * W + x) * 4];
+            const float Y = sample(comps[0], x, y);
+            auto cl = [](float v) { const int i = (int)std::lrintf(v); return (uint8_t)(i < 0 ? 0 : (i > 255 ? 255 : i)); };
+            if (comps.size() == 1) { o[0] = o[1] = o[2] = cl(Y); }
+            else {
+                const float cb = sample(comps[1], x, y) - 128.0f, cr = sample(comps[2], x, y) - 128.0f;
+                o[0] = cl(Y + 1.402f * cr); o[1] = cl(Y - 0.344136f * cb - 0.714136f * cr); o[2] = cl(Y + 1.772f * cb);
+            }
+            o[3] = 255;
+        }
+        return out;
+    }
+};
+constexpr uint8_t JpegDecoder::zz[64];
+
+Image decode_jpeg(const uint8_t* d, size_t n) {
+    JpegDecoder dec;
+    dec.p = d; dec.end = d + n;
+    return dec.run();
+}
+
 Image decode_image(const uint8_t* d, size_t n) {
     if (n >= 8 && d[0] == 0x89 && d[1] == 'P') return decode_png(d, n);
-    if (n >= 3 && d[0] == 0xff && d[1] == 0xd8) throw FormatError("JPEG images are not supported by this loader yet");
+    if (n >= 3 && d[0] == 0xff && d[1] == 0xd8) return decode_jpeg(d, n);
     throw FormatError("unknown image format");
 }
 

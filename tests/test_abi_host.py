@@ -246,3 +246,62 @@ def test_glb_loader_errors(tmp_path):
     class _RC:  # loadModel prints and returns False on failure, like the reference (SceneManager.cpp:24-27)
         deviceScene = None
     assert SceneManager(_RC()).loadModel(str(bad)) is False
+
+
+def _glb_with_image(path, blob: bytes, mime: str):
+    """Single-triangle .glb whose baseColorTexture is `blob`."""
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32).tobytes()
+    views = [{"buffer": 0, "byteOffset": 0, "byteLength": len(pos)}, {"buffer": 0, "byteOffset": len(pos), "byteLength": len(blob)}]
+    gltf = {"asset": {"version": "2.0"}, "scenes": [{"nodes": [0]}], "nodes": [{"mesh": 0}],
+            "meshes": [{"primitives": [{"attributes": {"POSITION": 0}, "material": 0}]}],
+            "materials": [{"pbrMetallicRoughness": {"baseColorTexture": {"index": 0}}}],
+            "textures": [{"source": 0}], "images": [{"bufferView": 1, "mimeType": mime}],
+            "accessors": [{"bufferView": 0, "componentType": 5126, "count": 3, "type": "VEC3"}], "bufferViews": views}
+    binblob = pos + blob
+    binblob += b"\x00" * ((-len(binblob)) % 4)
+    gltf["buffers"] = [{"byteLength": len(binblob)}]
+    js = json.dumps(gltf).encode(); js += b" " * ((-len(js)) % 4)
+    with open(path, "wb") as f:
+        f.write(struct.pack("<4sII", b"glTF", 2, 12 + 8 + len(js) + 8 + len(binblob)))
+        f.write(struct.pack("<I4s", len(js), b"JSON")); f.write(js)
+        f.write(struct.pack("<I4s", len(binblob), b"BIN\x00")); f.write(binblob)
+
+
+@pytest.mark.parametrize("mode,subsampling,size", [("RGB", 0, (64, 48)), ("RGB", 2, (70, 37)), ("RGB", 1, (33, 65)), ("L", 0, (40, 24))])
+def test_glb_loader_decodes_baseline_jpeg(tmp_path, mode, subsampling, size):
+    """Own baseline-JPEG decoder vs Pillow (libjpeg) on smooth images: luma within 2 code values; chroma
+    differs only by the upsampling filter (ours: nearest), bounded on smooth content."""
+    import io
+    from PIL import Image
+    from mesh2splat_b200.gltf import load_glb
+    w, h = size
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    img = np.stack([128 + 100 * np.sin(xx / 9.0), 128 + 100 * np.cos(yy / 7.0), 128 + 60 * np.sin((xx + yy) / 11.0)], axis=-1)
+    img = np.clip(img, 0, 255).astype(np.uint8)
+    pil = Image.fromarray(img if mode == "RGB" else img[..., 0], mode)
+    buf = io.BytesIO()
+    kw = {"quality": 92} if mode == "L" else {"quality": 92, "subsampling": subsampling}
+    pil.save(buf, "JPEG", **kw)
+    want = np.asarray(Image.open(io.BytesIO(buf.getvalue())).convert("RGB")).astype(np.int32)
+    p = tmp_path / "j.glb"
+    _glb_with_image(str(p), buf.getvalue(), "image/jpeg")
+    s = load_glb(str(p))
+    got = s.textures[0]
+    assert got.shape == (h, w, 4) and np.all(got[..., 3] == 255)
+    d = np.abs(got[..., :3].astype(np.int32) - want)
+    if subsampling == 0:
+        assert d.max() <= 2, d.max()
+    else:
+        assert d.mean() < 1.0 and d.max() <= 6, (d.mean(), d.max())
+
+
+def test_glb_loader_rejects_progressive_jpeg(tmp_path):
+    import io
+    from PIL import Image
+    from mesh2splat_b200.gltf import load_glb
+    buf = io.BytesIO()
+    Image.fromarray(np.full((16, 16, 3), 90, np.uint8)).save(buf, "JPEG", progressive=True)
+    p = tmp_path / "p.glb"
+    _glb_with_image(str(p), buf.getvalue(), "image/jpeg")
+    with pytest.raises(ValueError, match="progressive"):
+        load_glb(str(p))
