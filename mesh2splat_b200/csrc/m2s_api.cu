@@ -388,7 +388,7 @@ static m2s_status convert_enqueue_impl(m2s_ctx* ctx, const m2s_dscene* s, const 
     a.tri_first = (uint32_t)first;
     a.tri_count = (uint32_t)count;
     a.ranges = s->d_ranges; a.nranges = s->nranges;
-    a.prims = s->d_prims; a.texs = s->d_texs; a.tex_base = s->d_arena; a.ntex = s->ntex;
+    a.prims = s->d_prims; a.nprims = s->nprims; a.texs = s->d_texs; a.tex_base = s->d_arena; a.ntex = s->ntex;
     a.R = p->resolution;
     a.half_R = (float)p->resolution * 0.5f;
     a.mult = p->gaussian_std / (float)p->resolution;

@@ -37,6 +37,9 @@ struct DPrim {
 };
 
 // sorted, disjoint triangle ranges -> primitive
+static_assert(sizeof(DPrim) == 56, "DPrim layout");
+
+// sorted, disjoint triangle ranges -> primitive
 struct DRange {
     uint32_t first, end, prim, pad;
 };
@@ -48,6 +51,7 @@ struct ConvertArgs {
     const DRange* ranges;
     uint32_t nranges;
     const DPrim* prims;
+    uint32_t nprims;
     const DTexture* texs;
     const uint32_t* tex_base;  // texture arena
     uint32_t ntex;

@@ -33,6 +33,7 @@
 // fixed-point snapping => coverage) is written with __f*_rn intrinsics in the operation order of
 // the oracle (and of GLM, which the reference's GLSL-as-C++ build uses), so coverage is bit-exact.
 // Per-fragment values may use FMA contraction and are compared with a tolerance.
+#include <cstdio>
 #include "m2s_device.cuh"
 
 // resident warps per SM / register cap per layout (warps are a multiple of 4: register allocation granularity)
@@ -206,27 +207,38 @@ struct __align__(128) WarpBlock {
     uint64_t bar;
 };
 
+// The scene's descriptor tables as the set-up sees them: in shared memory when they fit (each CTA copies
+// them once — 2368 warps chasing range -> primitive -> texture through the same few L2 lines cost ~1 us per
+// dependent step), else in global memory.
+struct Tables {
+    const DRange* ranges;
+    const DPrim* prims;
+    const DTexture* texs;
+    uint32_t nranges;
+};
+constexpr uint32_t kTableSmemBytes = 24 * 1024;
+
 // ------------------------------------------------------------------------------------------
 // per-triangle stage + rasteriser set-up.  t4: 9 float4 in shared memory.
 // Returns the number of candidate pixels (0 => nothing to rasterise).
 // ------------------------------------------------------------------------------------------
 template <int LAYOUT>
 __device__ __noinline__ uint32_t setup_triangle(const float4* __restrict__ t4, uint32_t tri_global, const ConvertArgs& a,
-                                   TriRaster& tr, TriFragT<Cfg<LAYOUT>::kMaps>& tf) {
+                                   const Tables& tb, TriRaster& tr, TriFragT<Cfg<LAYOUT>::kMaps>& tf) {
     using C = Cfg<LAYOUT>;
     tr.w = 0; tr.h = 0; tr.x0 = 0; tr.y0 = 0; tr.incl = 0; tr.inv_area = 0.f;
     tf.tri = tri_global;
     // triangle -> primitive (sorted disjoint ranges)
-    int lo = 0, hi = (int)a.nranges - 1, found = -1;
+    int lo = 0, hi = (int)tb.nranges - 1, found = -1;
     while (lo <= hi) {
         const int mid = (lo + hi) >> 1;
-        const DRange r = a.ranges[mid];
+        const DRange r = tb.ranges[mid];
         if (tri_global < r.first) hi = mid - 1;
         else if (tri_global >= r.end) lo = mid + 1;
         else { found = (int)r.prim; break; }
     }
     if (found < 0) return 0;
-    const DPrim pr = a.prims[found];
+    const DPrim pr = tb.prims[found];
 
     // vertex data: 3 x {pos3 nrm3 tan4 uv2} = 9 float4
     const float4 q0 = t4[0], q3 = t4[3], q6 = t4[6];
@@ -368,7 +380,7 @@ __device__ __noinline__ uint32_t setup_triangle(const float4* __restrict__ t4, u
         float frac = 0.f;
         const int ti = pr.tex[m];
         if (ti >= 0) {
-            const DTexture t = a.texs[ti];
+            const DTexture t = tb.texs[ti];
             const float W = (float)t.w[0], H = (float)t.h[0];
             const float axx = dudx * W, bxx = dvdx * H, ayy = dudy * W, byy = dvdy * H;
             const float rx = sqrtf(axx * axx + bxx * bxx), ry = sqrtf(ayy * ayy + byy * byy);
@@ -531,6 +543,29 @@ __global__ void __launch_bounds__(Cfg<LAYOUT>::kWarps * 32) __maxnreg__(Cfg<LAYO
         mbar_init(&wb.bar, 1);
         fence_barrier_init();
     }
+    // descriptor tables -> shared memory (once per CTA) when they fit
+    Tables tabs{a.ranges, a.prims, a.texs, a.nranges};
+    {
+        const uint32_t br = a.nranges * (uint32_t)sizeof(DRange), bp = a.nprims * (uint32_t)sizeof(DPrim), bt = a.ntex * (uint32_t)sizeof(DTexture);
+#ifdef M2S_NO_TABLES
+        if (false) {
+#else
+        if (br + bp + bt <= kTableSmemBytes) {  // uniform across the grid
+#endif
+            unsigned char* base = smem + (size_t)C::kWarps * sizeof(WarpBlock<LAYOUT>);
+            uint32_t* dst = reinterpret_cast<uint32_t*>(base);  // word-wise: the structs are 16, 56 and 48 bytes
+            const uint32_t* s0 = reinterpret_cast<const uint32_t*>(a.ranges);
+            const uint32_t* s1 = reinterpret_cast<const uint32_t*>(a.prims);
+            const uint32_t* s2 = reinterpret_cast<const uint32_t*>(a.texs);
+            const uint32_t n0 = br / 4, n1 = bp / 4, n2 = bt / 4;
+            for (uint32_t i = threadIdx.x; i < n0 + n1 + n2; i += blockDim.x)
+                dst[i] = i < n0 ? s0[i] : (i < n0 + n1 ? s1[i - n0] : s2[i - n0 - n1]);
+            tabs.ranges = reinterpret_cast<const DRange*>(base);
+            tabs.prims = reinterpret_cast<const DPrim*>(base + br);
+            tabs.texs = reinterpret_cast<const DTexture*>(base + br + bp);
+            __syncthreads();  // the only CTA-wide barrier before the end of the kernel
+        }
+    }
     __syncwarp();
     uint32_t phase = 0, qn = 0;
     STAMP(a, 0);
@@ -567,7 +602,7 @@ __global__ void __launch_bounds__(Cfg<LAYOUT>::kWarps * 32) __maxnreg__(Cfg<LAYO
         TriRaster tr;  // raster state stays with the lane that owns the triangle
         tr.w = 0; tr.h = 0; tr.x0 = 0; tr.y0 = 0; tr.incl = 0;
         tr.A[0] = tr.A[1] = tr.A[2] = tr.B[0] = tr.B[1] = tr.B[2] = 0; tr.C[0] = tr.C[1] = tr.C[2] = 0;
-        if ((uint32_t)lane < ntri) cnt = setup_triangle<LAYOUT>(wb.tri + lane * 9, a.tri_first + t0 + lane, a, tr, wb.frag[lane]);
+        if ((uint32_t)lane < ntri) cnt = setup_triangle<LAYOUT>(wb.tri + lane * 9, a.tri_first + t0 + lane, a, tabs, tr, wb.frag[lane]);
 
         // classify: small (lane-per-triangle, int32), medium (warp-per-triangle), big (deferred)
         int e0 = 0, e1 = 0, e2 = 0, a0 = 0, a1 = 0, a2 = 0, r0 = 0, r1 = 0, r2 = 0, w = 1, bx = 0, by = 0;
@@ -671,18 +706,22 @@ __global__ void __launch_bounds__(Cfg<LAYOUT>::kWarps * 32) __maxnreg__(Cfg<LAYO
                 STAMP(a, 4);
                 unsigned long long idx = base + (incl - nh);
                 const uint32_t tg = a.tri_first + t0 + lane;
-                uint32_t pxy = ((uint32_t)by << 12) | (uint32_t)bx;
-                const uint32_t pxyrow = (1u << 12) - (uint32_t)(w - 1);  // next row, first column
-                int col = 0;
-                uint32_t maxh = 64u - (uint32_t)__clzll((long long)hits);  // walk only up to the last hit
+                // walk 2 visits only the hits: bit b of the mask is candidate b = row*w + col; row = b/w by a
+                // 16.16 reciprocal (exact for b < 64, w <= 64)
+                const uint32_t inv = (65536u + (uint32_t)w - 1u) / (uint32_t)w;
+                uint32_t maxh = nh;
 #pragma unroll
                 for (int d = 16; d > 0; d >>= 1) maxh = max(maxh, __shfl_xor_sync(0xffffffffu, maxh, d));
+                unsigned long long m = hits;
                 for (uint32_t it = 0; it < maxh; ++it) {
-                    if ((hits >> it) & 1ull) {
-                        if (idx < a.cap) a.frag_ids[idx] = make_uint2(tg, pxy);  // converterFS.glsl:48-51 beyond the cap
+                    if (m) {
+                        const uint32_t b = (uint32_t)__ffsll((long long)m) - 1u;
+                        m &= m - 1ull;
+                        const uint32_t row = (b * inv) >> 16, col = b - row * (uint32_t)w;
+                        if (idx < a.cap)  // converterFS.glsl:48-51 beyond the cap
+                            a.frag_ids[idx] = make_uint2(tg, ((uint32_t)(by + (int)row) << 12) | (uint32_t)(bx + (int)col));
                         ++idx;
                     }
-                    if (++col == w) { col = 0; pxy += pxyrow; } else ++pxy;
                 }
             }
         }
@@ -733,7 +772,7 @@ __global__ void __launch_bounds__(Cfg<LAYOUT>::kWarps * 32) __maxnreg__(Cfg<LAYO
         TriRaster tr;
         tr.w = 1; tr.h = 0; tr.x0 = 0; tr.y0 = 0; tr.incl = 0;
         tr.A[0] = tr.A[1] = tr.A[2] = tr.B[0] = tr.B[1] = tr.B[2] = 0; tr.C[0] = tr.C[1] = tr.C[2] = 0;
-        if (lane == 0) c = setup_triangle<LAYOUT>(wb.tri, item.x, a, tr, wb.frag[0]);
+        if (lane == 0) c = setup_triangle<LAYOUT>(wb.tri, item.x, a, tabs, tr, wb.frag[0]);
         c = __shfl_sync(0xffffffffu, c, 0);
         __syncwarp();
         const unsigned long long tc = TNOW();
@@ -1074,7 +1113,7 @@ __global__ void ply_rows_kernel(const float4* __restrict__ rec, unsigned long lo
 // launch wrappers used by m2s_api.cu
 // ------------------------------------------------------------------------------------------
 size_t raster_smem_bytes(int layout) {
-    return layout == 0 ? sizeof(WarpBlock<0>) * Cfg<0>::kWarps : sizeof(WarpBlock<1>) * Cfg<1>::kWarps;
+    return (layout == 0 ? sizeof(WarpBlock<0>) * Cfg<0>::kWarps : sizeof(WarpBlock<1>) * Cfg<1>::kWarps) + kTableSmemBytes;
 }
 size_t fragment_smem_bytes(int layout) { return (size_t)(M2S_FRAG_THREADS / 32) * 32 * (layout == 0 ? Cfg<0>::kStride : Cfg<1>::kStride); }
 int convert_warps_per_cta(int layout) { return layout == 0 ? Cfg<0>::kWarps : Cfg<1>::kWarps; }

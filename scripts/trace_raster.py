@@ -20,12 +20,16 @@ for i in range(5):
 t = tr.cpu().numpy().reshape(nw, 16).astype(np.float64)
 t0 = t[:, 0][t[:, 0] > 0].min()
 names = ["start", "tma_done", "setup_done", "walk1_done", "atomic_done", "walk2_done", "unit_end", "units_done", "poll_done", "drain_done", "pre_sync", "post_sync"]
+if os.environ.get("TRACE_SETUP"):
+    names += ["s:prim_loaded", "s:quat_done", "s:scale_done", "s:raster_done"]
 print(f"{which} R={R} layout={layout}: device_ms={out.device_ms:.4f} total={out.total}")
 for k, n in enumerate(names):
     v = t[:, k]; v = v[v > 0]
     if len(v):
         r = (v - t0) / 1e3
         print(f"{n:12s} n={len(v):5d}  min {r.min():7.2f}  p50 {np.median(r):7.2f}  p90 {np.percentile(r, 90):7.2f}  max {r.max():7.2f} us")
+if os.environ.get("TRACE_SETUP"):
+    sys.exit(0)
 it = t[:, 12]
 print("drain items/warp: mean %.1f max %d; per-item us: load %.2f setup %.2f raster+flush %.2f" % (
     it.mean(), it.max(), t[:, 13].sum() / max(it.sum(), 1) / 1e3, t[:, 14].sum() / max(it.sum(), 1) / 1e3, t[:, 15].sum() / max(it.sum(), 1) / 1e3))
