@@ -156,8 +156,9 @@ def run_reference(args):
     scene = synth.helmet_standin(2048)
     layout = LAYOUTS[args.layout]
     prep = oracle.Prepared(scene)
-    # torchrun exports OMP_NUM_THREADS=1: ask explicitly for every core this process may run on
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    # torchrun exports OMP_NUM_THREADS=1, and more threads than usable cores is far slower than fewer
+    # (128 allowed / 64 usable ran 30x slower at 128): time the candidates, keep the fastest
+    cores = oracle.calibrate_threads(prep)
     out = None
     for _ in range(max(1, min(args.warmup, 2))):
         n, total, out = prep.convert(DENSITY, layout, out=out, threads=cores)
@@ -326,14 +327,15 @@ def run_ours(args):
         if world == 1:
             import oracle
             prep = oracle.Prepared(scene)
+            cores = oracle.calibrate_threads(prep)
             o = None
-            n, _, o = prep.convert(DENSITY, layout, out=o)
+            n, _, o = prep.convert(DENSITY, layout, out=o, threads=cores)
             reps = 3
             t0 = time.perf_counter()
             for _ in range(reps):
-                n, _, o = prep.convert(DENSITY, layout, out=o)
+                n, _, o = prep.convert(DENSITY, layout, out=o, threads=cores)
             cdt = (time.perf_counter() - t0) / reps
-            cpu = {"value": n / cdt / 1e6, "unit": UNIT, "cores": oracle.max_threads(), "kind": "port",
+            cpu = {"value": n / cdt / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"full workload x{reps} ({scene.triangle_count} triangles -> {n} gaussians each)"}
         if world > 1:  # bytes that must cross NVLink per GPU for "every rank holds the full buffer"
             nv = (n_all - n_local) * stride

@@ -16,6 +16,7 @@ import numpy as np
 
 from mesh2splat_b200 import _abi
 
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")  # idle OpenMP threads sleep instead of burning a CPU quota
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _lib = None
 _ref = None
@@ -91,6 +92,71 @@ def max_threads() -> int:
     return int(lib().orc_max_threads())
 
 
+_usable = None
+
+
+def usable_threads() -> int:
+    """Threads worth starting: the CPUs this process may run on, capped by the number of physical cores
+    among them and by the cgroup CPU quota.  (Measured on a GPU box: 128 hardware threads allowed, 64
+    of them usable -> 128 OpenMP threads ran the pass 30x slower than 64 did.)"""
+    global _usable
+    if _usable is not None:
+        return _usable
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        cpus = list(range(os.cpu_count() or 1))
+    n = len(cpus)
+    cores = set()
+    for c in cpus:
+        try:
+            with open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list") as f:
+                cores.add(f.read().strip())
+        except OSError:
+            cores.add(str(c))
+    n = min(n, max(1, len(cores)))
+    for path in ("/sys/fs/cgroup/cpu.max",):
+        try:
+            with open(path) as f:
+                quota, period = f.read().split()[:2]
+            if quota != "max":
+                n = min(n, max(1, int(int(quota) / int(period))))
+        except (OSError, ValueError):
+            pass
+    try:
+        with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f, open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as g:
+            q, per = int(f.read()), int(g.read())
+        if q > 0 and per > 0:
+            n = min(n, max(1, q // per))
+    except (OSError, ValueError):
+        pass
+    _usable = max(1, n)
+    return _usable
+
+
+def calibrate_threads(prep: "Prepared", resolution: int = 128, layout: int = _abi.LAYOUT_PACKED56) -> int:
+    """Thread count that runs the pass fastest on this host: usable_threads() and its neighbours are timed
+    on a small conversion (hyper-threads and container quotas make the best count a measurement, not a lookup)."""
+    import time
+    try:
+        allowed = len(os.sched_getaffinity(0))
+    except AttributeError:
+        allowed = os.cpu_count() or 1
+    base = usable_threads()
+    cand = sorted({max(1, base // 2), base, min(allowed, base * 2)})
+    best, best_t = base, float("inf")
+    out = None
+    for c in cand:
+        _, _, out = prep.convert(resolution, layout, out=out, threads=c)
+        t0 = time.perf_counter()
+        for _ in range(2):
+            _, _, out = prep.convert(resolution, layout, out=out, threads=c)
+        t = time.perf_counter() - t0
+        if t < best_t:
+            best, best_t = c, t
+    return best
+
+
 def convert(scene: _abi.Scene, resolution: int, layout: int = _abi.LAYOUT_REF96, gaussian_std: float = 0.65,
             max_gaussians: int = 0, flags: int = 0, first_triangle: int = 0, triangle_count: int = 0,
             capacity: int | None = None, want_keys: bool = True, threads: int = 0):
@@ -106,7 +172,7 @@ def convert(scene: _abi.Scene, resolution: int, layout: int = _abi.LAYOUT_REF96,
     keys = np.zeros(capacity, np.uint64) if want_keys else None
     total = C.c_uint64(0)
     n = lib().orc_convert(C.byref(cs), C.byref(p), out.ctypes.data, capacity,
-                          keys.ctypes.data if want_keys else None, C.byref(total), threads)
+                          keys.ctypes.data if want_keys else None, C.byref(total), threads or usable_threads())
     del keep
     rec = out[: n * stride].view(_abi.record_dtype(layout))
     return rec, (keys[:n] if want_keys else None), int(total.value)
@@ -133,7 +199,7 @@ class Prepared:
             out = np.empty(capacity * stride, np.uint8)
         total = C.c_uint64(0)
         n = lib().orc_convert_prepared(C.byref(self.cs), self.handle, C.byref(p), out.ctypes.data, capacity, None,
-                                       C.byref(total), threads)
+                                       C.byref(total), threads or usable_threads())
         return int(n), int(total.value), out
 
     def close(self):
