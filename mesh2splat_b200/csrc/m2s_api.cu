@@ -3,7 +3,9 @@
 // There is deliberately NO CPU compute path: without a CUDA device every entry point fails.
 #include <algorithm>
 #include <cmath>
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -50,6 +52,13 @@ struct m2s_ctx {
     uint32_t queue_cap = 1u << 20;
     unsigned long long* h_total = nullptr;   // pinned
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // convert_host pipeline: a second stream for the downloads, per-chunk counts and events
+    static constexpr int kMaxChunks = 8;
+    cudaStream_t stream2 = nullptr;
+    unsigned long long* d_chunk_tot = nullptr;   // [kMaxChunks]
+    unsigned long long* h_chunk_tot = nullptr;   // pinned + mapped: {count, tag} per chunk, written by the raster kernel
+    unsigned long long host_seq = 0;             // tag generator
+    cudaEvent_t ev_chunk[kMaxChunks] = {};
     int blocks_per_sm[2] = {0, 0};       // raster kernel (persistent)
     int frag_blocks_per_sm[2] = {0, 0};  // fragment kernel
     unsigned long long epoch = 0;            // pairs up the ranks' calls of the fused gather
@@ -158,6 +167,11 @@ M2S_EXPORT m2s_status m2s_ctx_create(int device, m2s_ctx** out) {
     CUDA_TRY(cudaMallocHost(&c->h_total, sizeof(unsigned long long)));
     CUDA_TRY(cudaEventCreate(&c->ev0));
     CUDA_TRY(cudaEventCreate(&c->ev1));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    CUDA_TRY(cudaMalloc(&c->d_chunk_tot, m2s_ctx::kMaxChunks * sizeof(unsigned long long)));
+    CUDA_TRY(cudaHostAlloc(&c->h_chunk_tot, 2 * m2s_ctx::kMaxChunks * sizeof(unsigned long long), cudaHostAllocMapped));
+    std::memset(c->h_chunk_tot, 0, 2 * m2s_ctx::kMaxChunks * sizeof(unsigned long long));
+    for (int i = 0; i < m2s_ctx::kMaxChunks; ++i) CUDA_TRY(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
     for (int l = 0; l < 2; ++l) {
         CUDA_TRY(convert_configure(l, &c->blocks_per_sm[l], &c->frag_blocks_per_sm[l]));
         if (c->blocks_per_sm[l] < 1 || c->frag_blocks_per_sm[l] < 1) { set_error("conversion kernel does not fit on this device"); return M2S_E_CUDA; }
@@ -178,7 +192,10 @@ M2S_EXPORT void m2s_ctx_destroy(m2s_ctx* c) {
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_sched); cudaFree(c->d_counter); cudaFree(c->d_total); cudaFree(c->d_queue);
     cudaFreeHost(c->h_total);
+    cudaFree(c->d_chunk_tot); cudaFreeHost(c->h_chunk_tot);
+    for (int i = 0; i < m2s_ctx::kMaxChunks; ++i) if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -223,7 +240,9 @@ M2S_EXPORT void m2s_scene_free(m2s_ctx* ctx, m2s_dscene* s) {
     delete s;
 }
 
-M2S_EXPORT m2s_status m2s_scene_upload(m2s_ctx* ctx, const m2s_scene* sc, m2s_dscene** out) {
+// first_tris < triangle_count: only that many triangles are copied here (the caller streams the rest into
+// d_tris itself, interleaved with its launches) and the stream is not synchronised.
+static m2s_status scene_upload_impl(m2s_ctx* ctx, const m2s_scene* sc, m2s_dscene** out, uint64_t first_tris, bool sync) {
     if (!ctx || !sc || !out) { set_error("m2s_scene_upload: NULL argument"); return M2S_E_INVALID; }
     *out = nullptr;
     if (sc->triangle_count && !sc->triangles) { set_error("m2s_scene_upload: triangles is NULL"); return M2S_E_INVALID; }
@@ -278,7 +297,7 @@ M2S_EXPORT m2s_status m2s_scene_upload(m2s_ctx* ctx, const m2s_scene* sc, m2s_ds
     d->ntri = sc->triangle_count;
     UP_TRY(dalloc((void**)&d->d_tris, sc->triangle_count * (size_t)kTriBytes));
     if (sc->triangle_count)
-        UP_TRY(cudaMemcpyAsync(d->d_tris, sc->triangles, sc->triangle_count * (size_t)kTriBytes, cudaMemcpyHostToDevice, ctx->stream));
+        UP_TRY(cudaMemcpyAsync(d->d_tris, sc->triangles, std::min<uint64_t>(first_tris, sc->triangle_count) * (size_t)kTriBytes, cudaMemcpyHostToDevice, ctx->stream));
     d->nranges = (uint32_t)ranges.size();
     UP_TRY(dalloc((void**)&d->d_ranges, ranges.size() * sizeof(DRange)));
     if (!ranges.empty())
@@ -318,10 +337,14 @@ M2S_EXPORT m2s_status m2s_scene_upload(m2s_ctx* ctx, const m2s_scene* sc, m2s_ds
     UP_TRY(dalloc((void**)&d->d_texs, d->h_texs.size() * sizeof(DTexture)));
     if (!d->h_texs.empty())
         UP_TRY(cudaMemcpyAsync(d->d_texs, d->h_texs.data(), d->h_texs.size() * sizeof(DTexture), cudaMemcpyHostToDevice, ctx->stream));
-    UP_TRY(cudaStreamSynchronize(ctx->stream));
+    if (sync) UP_TRY(cudaStreamSynchronize(ctx->stream));
 #undef UP_TRY
     *out = d;
     return M2S_OK;
+}
+
+M2S_EXPORT m2s_status m2s_scene_upload(m2s_ctx* ctx, const m2s_scene* sc, m2s_dscene** out) {
+    return scene_upload_impl(ctx, sc, out, UINT64_MAX, true);
 }
 
 M2S_EXPORT m2s_status m2s_scene_read_mip(m2s_ctx* ctx, const m2s_dscene* s, uint32_t texture, uint32_t level, uint8_t* dst,
@@ -345,7 +368,9 @@ static uint64_t effective_cap(const m2s_dscene* s, const m2s_params* p, uint64_t
 }
 
 static m2s_status convert_enqueue_impl(m2s_ctx* ctx, const m2s_dscene* s, const m2s_params* p, void* d_out, uint64_t out_capacity,
-                                       uint64_t* d_keys, uint64_t* d_total, void* stream_, const m2s_peers* peers) {
+                                       uint64_t* d_keys, uint64_t* d_total, void* stream_, const m2s_peers* peers,
+                                       const unsigned long long* prev_totals = nullptr, uint32_t nprev = 0,
+                                       unsigned long long* host_total = nullptr, unsigned long long host_tag = 0) {
     if (!ctx || !s || !p) { set_error("m2s_convert: NULL argument"); return M2S_E_INVALID; }
     if (p->resolution < 1 || p->resolution > 4096) { set_error("m2s_convert: resolution must be in 1..4096"); return M2S_E_INVALID; }
     if (p->layout > M2S_LAYOUT_PLY_COMPRESSED) { set_error("m2s_convert: unknown layout"); return M2S_E_INVALID; }
@@ -392,6 +417,7 @@ static m2s_status convert_enqueue_impl(m2s_ctx* ctx, const m2s_dscene* s, const 
     a.R = p->resolution;
     a.half_R = (float)p->resolution * 0.5f;
     a.mult = p->gaussian_std / (float)p->resolution;
+    a.log_sz = logf(1e-7f * a.mult);
     a.frag_ids = (uint2*)ctx->d_ids;
     a.tri_frag = (unsigned char*)ctx->d_trifrag;
     a.out = (uint8_t*)kout;
@@ -400,6 +426,10 @@ static m2s_status convert_enqueue_impl(m2s_ctx* ctx, const m2s_dscene* s, const 
     a.counter = ctx->d_counter;
     // fused gather: the raster kernel's count stays local, the global total goes to d_total after the wait
     a.total_out = (peers && peers->world > 1) ? ctx->d_total : (d_total ? (unsigned long long*)d_total : ctx->d_total);
+    a.prev_totals = prev_totals;
+    a.nprev = nprev;
+    a.host_total = host_total;
+    a.host_tag = host_tag;
     a.sched = ctx->d_sched;
     const int grid = ctx->sm_count * ctx->blocks_per_sm[klayout];
     {   // work-unit size: as large as 32 triangles, but small enough that every warp of the grid gets the
@@ -495,21 +525,120 @@ M2S_EXPORT m2s_status m2s_convert_host(m2s_ctx* ctx, const m2s_scene* sc, const 
     slim.primitives = prims.data();
     slim.textures = texs.data();
     slim.texture_count = (uint32_t)texs.size();
+    // Pipeline (REF96 / PACKED56, meshes large enough to split): the triangle range is cut into chunks; chunk c's
+    // records are appended after chunk c-1's on the device (fragment kernel: prev_totals) and start crossing
+    // PCIe on a second stream while chunk c+1 is still being uploaded and converted — H2D and D2H overlap.
+    uint64_t first = std::min<uint64_t>(p->first_triangle, sc->triangle_count);
+    uint64_t count = p->triangle_count;
+    if (count == 0 || first + count > sc->triangle_count) count = sc->triangle_count - first;
+    int nchunks = 1;
+    if (p->layout <= M2S_LAYOUT_PACKED56 && count >= 16384) {
+        nchunks = 4;
+        if (const char* e = std::getenv("M2S_HOST_CHUNKS")) nchunks = std::max(1, std::min(m2s_ctx::kMaxChunks, std::atoi(e)));
+    }
+    const uint64_t per = (count + nchunks - 1) / nchunks;
     m2s_dscene* ds = nullptr;
-    m2s_status st = m2s_scene_upload(ctx, &slim, &ds);
+    m2s_status st = scene_upload_impl(ctx, &slim, &ds, nchunks > 1 ? first + per : UINT64_MAX, nchunks == 1);
     if (st != M2S_OK) return st;
     st = grow(ctx, &ctx->d_out, &ctx->out_bytes, std::max<uint64_t>(out_capacity, 1) * stride);
     if (st == M2S_OK && h_keys) st = grow(ctx, (void**)&ctx->d_keys, &ctx->keys_bytes, std::max<uint64_t>(out_capacity, 1) * 8);
-    if (st != M2S_OK) { m2s_scene_free(ctx, ds); return st; }
+    if (st != M2S_OK) { cudaStreamSynchronize(ctx->stream); m2s_scene_free(ctx, ds); return st; }
     m2s_result r;
     std::memset(&r, 0, sizeof(r));
-    st = m2s_convert(ctx, ds, p, ctx->d_out, out_capacity, h_keys ? (uint64_t*)ctx->d_keys : nullptr, &r);
-    if (st == M2S_OK || st == M2S_E_CAPACITY) {
-        cudaError_t e = cudaSuccess;
-        if (r.written) e = cudaMemcpyAsync(h_out, ctx->d_out, r.written * stride, cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess && h_keys && r.written) e = cudaMemcpyAsync(h_keys, ctx->d_keys, r.written * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (nchunks == 1) {
+        st = m2s_convert(ctx, ds, p, ctx->d_out, out_capacity, h_keys ? (uint64_t*)ctx->d_keys : nullptr, &r);
+        if (st == M2S_OK || st == M2S_E_CAPACITY) {
+            cudaError_t e = cudaSuccess;
+            if (r.written) e = cudaMemcpyAsync(h_out, ctx->d_out, r.written * stride, cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess && h_keys && r.written) e = cudaMemcpyAsync(h_keys, ctx->d_keys, r.written * 8, cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) { set_error(std::string("convert_host download: ") + cudaGetErrorString(e)); st = M2S_E_CUDA; }
+        }
+    } else {
+        const uint64_t cap = effective_cap(ds, p, out_capacity);
+        auto bail = [&](const char* what, cudaError_t e) {
+            cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->stream2);
+            ctx->dirty = true;
+            set_error(std::string(what) + ": " + cudaGetErrorString(e));
+            m2s_scene_free(ctx, ds);
+            return M2S_E_CUDA;
+        };
+        static const bool host_trace = std::getenv("M2S_HOST_TRACE") != nullptr;  // debug: phase times on stderr
+        const auto t_start = std::chrono::steady_clock::now();
+        auto since = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_start).count(); };
+        cudaError_t e = cudaEventRecord(ctx->ev0, ctx->stream);
+        if (e != cudaSuccess) return bail("convert_host", e);
+        int launched = 0;
+        unsigned long long tags[m2s_ctx::kMaxChunks] = {};
+        for (int c = 0; c < nchunks; ++c) {
+            const uint64_t lo = first + (uint64_t)c * per, hi = std::min(first + count, lo + per);
+            if (lo >= hi) break;
+            if (c > 0) {
+                e = cudaMemcpyAsync(reinterpret_cast<unsigned char*>(ds->d_tris) + lo * (size_t)kTriBytes,
+                                    reinterpret_cast<const unsigned char*>(sc->triangles) + lo * (size_t)kTriBytes,
+                                    (hi - lo) * (size_t)kTriBytes, cudaMemcpyHostToDevice, ctx->stream);
+                if (e != cudaSuccess) return bail("convert_host upload", e);
+            }
+            m2s_params pc = *p;
+            pc.first_triangle = lo;
+            pc.triangle_count = hi - lo;
+            unsigned long long* h_dev = nullptr;  // device view of the mapped count slot
+            e = cudaHostGetDevicePointer((void**)&h_dev, ctx->h_chunk_tot + 2 * c, 0);
+            if (e != cudaSuccess) return bail("convert_host", e);
+            tags[c] = ++ctx->host_seq;
+            st = convert_enqueue_impl(ctx, ds, &pc, ctx->d_out, out_capacity, h_keys ? (uint64_t*)ctx->d_keys : nullptr,
+                                      (uint64_t*)(ctx->d_chunk_tot + c), ctx->stream, nullptr, ctx->d_chunk_tot, (uint32_t)c,
+                                      h_dev, tags[c]);
+            if (st != M2S_OK) { cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->stream2); m2s_scene_free(ctx, ds); return st; }
+            e = cudaEventRecord(ctx->ev_chunk[c], ctx->stream);
+            if (e != cudaSuccess) return bail("convert_host", e);
+            ++launched;
+        }
+        e = cudaEventRecord(ctx->ev1, ctx->stream);
+        if (e != cudaSuccess) return bail("convert_host", e);
+        uint64_t base = 0, written = 0;
+        if (host_trace) std::fprintf(stderr, "[m2s host] enqueued %d chunks at %.0f us\n", launched, since());
+        for (int c = 0; c < launched; ++c) {
+            // the count arrives (zero-copy) when the chunk's raster kernel ends; the download is enqueued behind
+            // the chunk's event while its fragment kernel still runs -> no host latency between kernel and copy
+            volatile unsigned long long* slot = ctx->h_chunk_tot + 2 * c;
+            for (;;) {
+                if (slot[1] == tags[c]) break;
+                const cudaError_t q = cudaEventQuery(ctx->ev_chunk[c]);
+                if (q == cudaSuccess) break;             // finished: the tag is there
+                if (q != cudaErrorNotReady) return bail("convert_host", q);
+            }
+            if (slot[1] != tags[c]) return bail("convert_host: count not published", cudaErrorUnknown);
+            const uint64_t tot = slot[0];
+            if (host_trace) std::fprintf(stderr, "[m2s host] chunk %d rasterised at %.0f us (%llu records)\n", c, since(), (unsigned long long)tot);
+            const uint64_t room = cap > base ? cap - base : 0, w = std::min(tot, room);
+            if (w) {
+                e = cudaStreamWaitEvent(ctx->stream2, ctx->ev_chunk[c], 0);
+                if (e == cudaSuccess)
+                    e = cudaMemcpyAsync(reinterpret_cast<unsigned char*>(h_out) + base * stride,
+                                        reinterpret_cast<const unsigned char*>(ctx->d_out) + base * stride, w * stride,
+                                        cudaMemcpyDeviceToHost, ctx->stream2);
+                if (e == cudaSuccess && h_keys)
+                    e = cudaMemcpyAsync(h_keys + base, ctx->d_keys + base, w * 8, cudaMemcpyDeviceToHost, ctx->stream2);
+                if (e != cudaSuccess) return bail("convert_host download", e);
+            }
+            base += tot;
+            written += w;
+        }
+        e = cudaStreamSynchronize(ctx->stream2);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) { set_error(std::string("convert_host download: ") + cudaGetErrorString(e)); st = M2S_E_CUDA; }
+        if (e != cudaSuccess) return bail("convert_host download", e);
+        if (host_trace) std::fprintf(stderr, "[m2s host] downloads done at %.0f us\n", since());
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        r.total = base; r.cap = cap; r.written = written; r.device_ms = ms;
+        st = M2S_OK;
+        if (base > cap) {
+            char buf[160];
+            std::snprintf(buf, sizeof(buf), "m2s_convert: %llu gaussians generated, capacity %llu", (unsigned long long)base, (unsigned long long)cap);
+            set_error(buf);
+            st = M2S_E_CAPACITY;
+        }
     }
     if (res) *res = r;
     m2s_scene_free(ctx, ds);

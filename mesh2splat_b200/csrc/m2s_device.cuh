@@ -58,6 +58,7 @@ struct ConvertArgs {
     uint32_t R;
     float half_R;
     float mult;  // sigma / R (SceneManager.cpp:668)
+    float log_sz;  // ln(1e-7 * mult): the constant third log-scale of the packed layout
     // intermediates between the two kernels (context-owned scratch, L2-resident at the sizes of interest);
     // the fragment kernel reads the vertices themselves from `tris`
     uint2* frag_ids;                   // {global triangle, y << 12 | x} per fragment; index = output record index
@@ -68,6 +69,10 @@ struct ConvertArgs {
     unsigned long long* counter;       // fragments generated (the reference's atomic counter); context-owned,
                                        // zero at launch, re-zeroed by the last CTA
     unsigned long long* total_out;     // receives the final count (last CTA out)
+    const unsigned long long* prev_totals;  // appended launches: counts of the earlier chunks (records start after them)
+    uint32_t nprev;
+    unsigned long long* host_total;    // optional, mapped pinned host memory: {count, tag} written by the raster kernel's
+    unsigned long long host_tag;       // last CTA so the host can size the download while the fragment kernel still runs
     // scheduling state (zero at launch, re-armed by the last CTA)
     uint32_t* sched;                   // 5 words, 128 B apart: unit counter, units past set-up, queue tail, queue head,
                                        // CTAs finished

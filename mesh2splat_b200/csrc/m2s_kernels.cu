@@ -306,9 +306,11 @@ __device__ __noinline__ uint32_t setup_triangle(const float4* __restrict__ t4, u
                        __fadd_rn(__fmul_rn(V0.z, i00), __fmul_rn(V1.z, i01))};
         const f3 Jv = {__fadd_rn(__fmul_rn(V0.x, i10), __fmul_rn(V1.x, i11)), __fadd_rn(__fmul_rn(V0.y, i10), __fmul_rn(V1.y, i11)),
                        __fadd_rn(__fmul_rn(V0.z, i10), __fmul_rn(V1.z, i11))};
+        // Scale and Quaternion are bit-identical to converterGS.glsl's (tests: golden GS vectors); only the
+        // log of the packed layout is the device's logf
         const float sx = len3(Ju), sy = len3(Jv), sz = 1e-7f;
         if (C::kLogScale) {  // parsers.cpp:497-499 log(scale * sigma/R)
-            tf.scale[0] = logf(__fmul_rn(sx, a.mult)); tf.scale[1] = logf(__fmul_rn(sy, a.mult)); tf.scale[2] = logf(__fmul_rn(sz, a.mult));
+            tf.scale[0] = logf(__fmul_rn(sx, a.mult)); tf.scale[1] = logf(__fmul_rn(sy, a.mult)); tf.scale[2] = a.log_sz;
         } else { tf.scale[0] = sx; tf.scale[1] = sy; tf.scale[2] = sz; }
     }
     tf.factor[0] = pr.factor[0]; tf.factor[1] = pr.factor[1]; tf.factor[2] = pr.factor[2]; tf.factor[3] = pr.factor[3];
@@ -383,8 +385,7 @@ __device__ __noinline__ uint32_t setup_triangle(const float4* __restrict__ t4, u
             const DTexture t = tb.texs[ti];
             const float W = (float)t.w[0], H = (float)t.h[0];
             const float axx = dudx * W, bxx = dvdx * H, ayy = dudy * W, byy = dvdy * H;
-            const float rx = sqrtf(axx * axx + bxx * bxx), ry = sqrtf(ayy * ayy + byy * byy);
-            const float lam = log2f(fmaxf(rx, ry));
+            const float lam = 0.5f * __log2f(fmaxf(axx * axx + bxx * bxx, ayy * ayy + byy * byy));  // log2 of the longer step
             const int q = (int)t.nlevels - 1;
             int l0 = 0;
             if (!(lam > 0.0f)) { l0 = 0; }                       // magnification: LINEAR on level 0
@@ -792,24 +793,64 @@ __global__ void __launch_bounds__(Cfg<LAYOUT>::kWarps * 32) __maxnreg__(Cfg<LAYO
     STAMP(a, 10);
     __syncthreads();
     STAMP(a, 11);
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const uint32_t done = atomicAdd(SCHED(a, 4), 1u);
-        if (done == gridDim.x - 1) {
+    if (warp == 0) {
+        uint32_t last = 0;
+        unsigned long long tot = 0;
+        if (lane == 0) {
             __threadfence();
-            const unsigned long long tot = *reinterpret_cast<volatile unsigned long long*>(a.counter);
-            *a.total_out = tot;
-            *a.counter = 0ull;
-            if (a.world > 1) {  // fused gather: tell every peer how many records this rank will write
-                const unsigned long long mine = tot < a.cap ? tot : a.cap;
-                for (uint32_t p = 0; p < a.world; ++p) {
-                    a.peer_xch[p][a.rank * 4 + 0] = mine;
+            const uint32_t done = atomicAdd(SCHED(a, 4), 1u);
+            if (done == gridDim.x - 1) {
+                __threadfence();
+                last = 1;
+                tot = *reinterpret_cast<volatile unsigned long long*>(a.counter);
+                *a.total_out = tot;
+                *a.counter = 0ull;
+                if (a.host_total) {  // zero-copy count for the host (PCIe posted write, ~1 us)
+                    *reinterpret_cast<volatile unsigned long long*>(a.host_total) = tot;
                     __threadfence_system();
-                    st_release_sys(a.peer_xch[p] + a.rank * 4 + 1, a.epoch);
+                    *reinterpret_cast<volatile unsigned long long*>(a.host_total + 1) = a.host_tag;
                 }
+                *SCHED(a, 0) = 0; *SCHED(a, 1) = 0; *SCHED(a, 2) = 0; *SCHED(a, 3) = 0; *SCHED(a, 4) = 0;
+                __threadfence();
             }
-            *SCHED(a, 0) = 0; *SCHED(a, 1) = 0; *SCHED(a, 2) = 0; *SCHED(a, 3) = 0; *SCHED(a, 4) = 0;
-            __threadfence();
+        }
+        if (a.world > 1) {  // fused gather: tell every peer how many records this rank will write, one lane per peer
+            last = __shfl_sync(0xffffffffu, last, 0);
+            tot = __shfl_sync(0xffffffffu, tot, 0);
+            if (last && (uint32_t)lane < a.world) {
+                const unsigned long long mine = tot < a.cap ? tot : a.cap;
+                a.peer_xch[lane][a.rank * 4 + 0] = mine;
+                __threadfence_system();
+                st_release_sys(a.peer_xch[lane] + a.rank * 4 + 1, a.epoch);
+            }
+        }
+    }
+}
+
+// A warp's staged records (shared memory, 16-byte aligned) -> one contiguous span of global memory at byte
+// offset `boff` of `dstbase`.  16-byte stores when the span starts 16-byte aligned (REF96 always; PACKED56
+// at even record offsets), else 8-byte stores (appended chunks / gathered ranks may start at an odd record).
+template <int STRIDE>
+__device__ __forceinline__ void copy_span(uint8_t* dstbase, unsigned long long boff, const unsigned char* stage, uint32_t nbytes, int lane) {
+    if ((boff & 15ull) == 0) {
+        float4* dst = reinterpret_cast<float4*>(dstbase + boff);
+        const float4* src = reinterpret_cast<const float4*>(stage);
+        const uint32_t n16 = nbytes / 16;
+#pragma unroll
+        for (int j = 0; j < (32 * STRIDE / 16 + 31) / 32; ++j) {
+            const uint32_t c = lane + 32 * j;
+            if (c < n16) dst[c] = src[c];
+        }
+        if ((nbytes & 8u) && lane == 0)  // odd number of 56-byte records: one trailing 8-byte piece
+            reinterpret_cast<float2*>(dst)[n16 * 2] = reinterpret_cast<const float2*>(src)[n16 * 2];
+    } else {
+        float2* dst = reinterpret_cast<float2*>(dstbase + boff);
+        const float2* src = reinterpret_cast<const float2*>(stage);
+        const uint32_t n8 = nbytes / 8;
+#pragma unroll
+        for (int j = 0; j < 32 * STRIDE / 8 / 32; ++j) {
+            const uint32_t c = lane + 32 * j;
+            if (c < n8) dst[c] = src[c];
         }
     }
 }
@@ -828,7 +869,12 @@ __global__ void __launch_bounds__(M2S_FRAG_THREADS) fragment_kernel(const __grid
     // kernel drains; everything it wrote is visible after this wait
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const unsigned long long total = *reinterpret_cast<const volatile unsigned long long*>(a.total_out);
-    const unsigned long long n = total < a.cap ? total : a.cap;
+    // appended launches (m2s_convert_host pipelines a scene in triangle chunks): this launch's records follow
+    // those of the earlier chunks; the cap applies to the running index, as the reference's counter does
+    unsigned long long base = 0;
+    for (uint32_t j = 0; j < a.nprev; ++j) base += *reinterpret_cast<const volatile unsigned long long*>(a.prev_totals + j);
+    const unsigned long long room = a.cap > base ? a.cap - base : 0ull;
+    const unsigned long long n = total < room ? total : room;
     // fused gather: wait for every rank's count of this epoch, my records start after the lower ranks'
     __shared__ unsigned long long s_goff;
     unsigned long long goff = 0;
@@ -964,13 +1010,13 @@ __global__ void __launch_bounds__(M2S_FRAG_THREADS) fragment_kernel(const __grid
                 s4[5] = make_float4(metal, rough, 0.0f, 1.0f);
             } else {
                 // parsers.cpp:484-499: SH0, opacity logit, log scale (per triangle)
-                const float kC0 = 0.28209479177387814f;  // SH_COEFF0, params.hpp:17
                 float2* s2 = reinterpret_cast<float2*>(srec);
                 s2[0] = make_float2(Px, Py);
                 s2[1] = make_float2(Pz, tf.quat[0]);
                 s2[2] = make_float2(tf.quat[1], tf.quat[2]);
                 s2[3] = make_float2(tf.quat[3], tf.scale[0]);
                 s2[4] = make_float2(tf.scale[1], tf.scale[2]);
+                const float kC0 = 0.28209479177387814f;  // SH_COEFF0, params.hpp:17
                 s2[5] = make_float2(__fdiv_rn(cr - 0.5f, kC0), __fdiv_rn(cg - 0.5f, kC0));
                 s2[6] = make_float2(__fdiv_rn(cb - 0.5f, kC0), inv_sigmoid(ca));
             }
@@ -979,34 +1025,21 @@ __global__ void __launch_bounds__(M2S_FRAG_THREADS) fragment_kernel(const __grid
         __syncwarp();
         // ---- the warp's records are one contiguous span: straight vector copy -----------------------
         if (a.world <= 1) {
-            float4* dst = reinterpret_cast<float4*>(a.out + wbase * (unsigned long long)kStride);
-            const float4* src = reinterpret_cast<const float4*>(stage);
-            const uint32_t n16 = nfr * kStride / 16;  // 32*stride is a multiple of 16; a short tail group may leave 8 bytes
-#pragma unroll
-            for (int j = 0; j < (32 * kStride / 16 + 31) / 32; ++j) {
-                const uint32_t c = lane + 32 * j;
-                if (c < n16) dst[c] = src[c];
-            }
-            if ((nfr * kStride) & 8u) {  // odd number of 56-byte records: one trailing 8-byte piece
-                if (lane == 0) reinterpret_cast<float2*>(dst)[n16 * 2] = reinterpret_cast<const float2*>(src)[n16 * 2];
-            }
+            copy_span<kStride>(a.out, (base + wbase) * (unsigned long long)kStride, stage, nfr * kStride, lane);
         } else {
             // fused gather: the same span goes to the final buffer of EVERY rank (peer stores over NVLink)
             const unsigned long long gbase = goff + wbase;
             uint32_t nval = 0;
             if (gbase < a.gcap) nval = (uint32_t)min((unsigned long long)nfr, a.gcap - gbase);
-            const uint32_t n8 = nval * kStride / 8;  // 8-byte pieces: the global offset may be odd (56-byte records)
-            const float2* src = reinterpret_cast<const float2*>(stage);
-            for (uint32_t p = 0; p < a.world; ++p) {
-                float2* dst = reinterpret_cast<float2*>(a.peer_out[p] + gbase * (unsigned long long)kStride);
-#pragma unroll
-                for (int j = 0; j < 32 * kStride / 8 / 32; ++j) {
-                    const uint32_t c = lane + 32 * j;
-                    if (c < n8) dst[c] = src[c];
-                }
+            // destinations are visited in a rotated order (by rank and by span) so that at any moment the
+            // grid's stores are spread over all peers' ingress ports instead of converging on peer 0
+            uint32_t p = (a.rank + 1u + (uint32_t)g) % a.world;
+            for (uint32_t i = 0; i < a.world; ++i) {
+                copy_span<kStride>(a.peer_out[p], gbase * (unsigned long long)kStride, stage, nval * kStride, lane);
+                p = p + 1 == a.world ? 0 : p + 1;
             }
         }
-        if (want_keys && (uint32_t)lane < nfr) a.keys[wbase + lane] = key;
+        if (want_keys && (uint32_t)lane < nfr) a.keys[base + wbase + lane] = key;
         __syncwarp();
     }
     if (a.world > 1) {  // last CTA out tells every peer that this rank's records have landed
@@ -1017,7 +1050,10 @@ __global__ void __launch_bounds__(M2S_FRAG_THREADS) fragment_kernel(const __grid
             if (done == gridDim.x - 1) {
                 *SCHED(a, 6) = 0;
                 __threadfence_system();
-                for (uint32_t p = 0; p < a.world; ++p) st_release_sys(a.peer_xch[p] + a.rank * 4 + 2, a.epoch);
+                for (uint32_t i = 0; i < a.world; ++i) {
+                    const uint32_t p = (a.rank + 1u + i) % a.world;
+                    st_release_sys(a.peer_xch[p] + a.rank * 4 + 2, a.epoch);
+                }
             }
         }
     }

@@ -210,6 +210,37 @@ def test_convert_host_matches_resident(gpu_ctx):
     assert_records_match(s, LAYOUT_REF96, rec, keys, want, wkeys)
 
 
+@pytest.mark.parametrize("layout", [LAYOUT_REF96, LAYOUT_PACKED56])
+def test_convert_host_pipelined_chunks(gpu_ctx, layout):
+    """Meshes of >= 16384 triangles go through m2s_convert_host in appended triangle chunks (H2D, kernels and
+    D2H overlapped): the result must be the same multiset as the oracle's single pass, keys included."""
+    tri = synth.displaced_sphere(101, 83, seed=11, amplitude=0.07)  # 16 766 triangles, odd chunk record offsets
+    s = Scene(tri, [Primitive(0, len(tri), (0.9, 0.8, 1.0, 1.0), 0, 1, 2)], synth.make_material_textures(256, 5))
+    s.compute_bboxes()
+    rec, keys, res = gpu_ctx.convert_host(s, 200, layout, flags=FLAG_UNCAPPED, want_keys=True)
+    want, wkeys, total = oracle.convert(s, 200, layout, flags=FLAG_UNCAPPED)
+    assert res.total == total and res.written == total
+    assert_records_match(s, layout, rec, keys, want, wkeys)
+
+
+def test_convert_host_pipelined_capacity(gpu_ctx):
+    """The cap applies to the running index across chunks: exactly `cap` records come back, the total keeps
+    counting (converterFS.glsl:46-51), status M2S_E_CAPACITY."""
+    tri = synth.displaced_sphere(101, 83, seed=11, amplitude=0.07)
+    s = Scene(tri, [Primitive(0, len(tri), (1, 1, 1, 1), 0, 1, 2)], synth.make_material_textures(64, 5))
+    s.compute_bboxes()
+    _, _, full = gpu_ctx.convert_host(s, 160, LAYOUT_PACKED56, flags=FLAG_UNCAPPED)
+    cap = full.total * 5 // 8 + 1  # ends inside the third of four chunks
+    rec, keys, res = gpu_ctx.convert_host(s, 160, LAYOUT_PACKED56, max_gaussians=cap, want_keys=True)
+    assert res.total == full.total and res.written == cap and len(rec) == cap
+    assert len(np.unique(keys)) == cap  # every stored record is a distinct fragment
+    want, wkeys, _ = oracle.convert(s, 160, LAYOUT_PACKED56, flags=FLAG_UNCAPPED)
+    order = np.argsort(wkeys)
+    pos = np.minimum(np.searchsorted(wkeys[order], keys), len(wkeys) - 1)
+    assert np.array_equal(wkeys[order][pos], keys)  # a subset of the uncapped result
+    assert_records_match(s, LAYOUT_PACKED56, rec, keys, want[order][pos], keys)
+
+
 def test_repeated_launches_rearm_the_scheduler(gpu_ctx):
     s = synth.unit_quad()
     ds = gpu_ctx.upload(s)
