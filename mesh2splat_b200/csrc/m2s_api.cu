@@ -58,6 +58,9 @@ struct m2s_ctx {
     unsigned long long* d_chunk_tot = nullptr;   // [kMaxChunks]
     unsigned long long* h_chunk_tot = nullptr;   // pinned + mapped: {count, tag} per chunk, written by the raster kernel
     unsigned long long host_seq = 0;             // tag generator
+    // file writer: two pinned staging buffers (download of block i overlaps the write of block i-1)
+    static constexpr size_t kStageBytes = 32u << 20;
+    unsigned char* h_stage[2] = {nullptr, nullptr};
     cudaEvent_t ev_chunk[kMaxChunks] = {};
     int blocks_per_sm[2] = {0, 0};       // raster kernel (persistent)
     int frag_blocks_per_sm[2] = {0, 0};  // fragment kernel
@@ -193,6 +196,7 @@ M2S_EXPORT void m2s_ctx_destroy(m2s_ctx* c) {
     cudaFree(c->d_sched); cudaFree(c->d_counter); cudaFree(c->d_total); cudaFree(c->d_queue);
     cudaFreeHost(c->h_total);
     cudaFree(c->d_chunk_tot); cudaFreeHost(c->h_chunk_tot);
+    for (int i = 0; i < 2; ++i) if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
     for (int i = 0; i < m2s_ctx::kMaxChunks; ++i) if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     if (c->stream2) cudaStreamDestroy(c->stream2);
@@ -502,29 +506,36 @@ M2S_EXPORT m2s_status m2s_convert(m2s_ctx* ctx, const m2s_dscene* s, const m2s_p
     return M2S_OK;
 }
 
+// Upload only the maps a layout consumes: PACKED56 carries neither normal nor metallic/roughness, the
+// standard .ply row no metallic/roughness — their texels would cross PCIe for nothing.
+struct SlimScene {
+    std::vector<m2s_primitive> prims;
+    std::vector<m2s_texture> texs;
+    m2s_scene scene;
+    SlimScene(const m2s_scene* sc, uint32_t layout) : prims(sc->primitives, sc->primitives + sc->primitive_count), scene(*sc) {
+        const bool need_normal = layout != M2S_LAYOUT_PACKED56;
+        const bool need_mr = layout == M2S_LAYOUT_REF96 || layout == M2S_LAYOUT_PLY_PBR || layout == M2S_LAYOUT_PLY_COMPRESSED;
+        std::vector<int32_t> remap(sc->texture_count, -1);
+        auto use = [&](int32_t& idx, bool needed) {
+            if (idx < 0 || !needed || (uint32_t)idx >= sc->texture_count) { if (idx >= 0 && (uint32_t)idx < sc->texture_count) idx = -1; return; }
+            if (remap[idx] < 0) { remap[idx] = (int32_t)texs.size(); texs.push_back(sc->textures[idx]); }
+            idx = remap[idx];
+        };
+        for (auto& pr : prims) { use(pr.albedo_texture, true); use(pr.normal_texture, need_normal); use(pr.metallic_roughness_texture, need_mr); }
+        scene.primitives = prims.data();
+        scene.textures = texs.data();
+        scene.texture_count = (uint32_t)texs.size();
+    }
+};
+
 M2S_EXPORT m2s_status m2s_convert_host(m2s_ctx* ctx, const m2s_scene* sc, const m2s_params* p, void* h_out, uint64_t out_capacity,
                                        uint64_t* h_keys, m2s_result* res) {
     if (!ctx || !sc || !p || (!h_out && out_capacity)) { set_error("m2s_convert_host: NULL argument"); return M2S_E_INVALID; }
     const uint32_t stride = m2s_record_stride(p->layout);
     if (!stride) { set_error("m2s_convert_host: unknown layout"); return M2S_E_INVALID; }
     CUDA_TRY(cudaSetDevice(ctx->device));
-    // Upload only the maps this layout consumes: PACKED56 carries neither normal nor metallic/roughness,
-    // the standard .ply row no metallic/roughness — their texels would cross PCIe for nothing.
-    const bool need_normal = p->layout != M2S_LAYOUT_PACKED56;
-    const bool need_mr = p->layout == M2S_LAYOUT_REF96 || p->layout == M2S_LAYOUT_PLY_PBR || p->layout == M2S_LAYOUT_PLY_COMPRESSED;
-    std::vector<m2s_primitive> prims(sc->primitives, sc->primitives + sc->primitive_count);
-    std::vector<m2s_texture> texs;
-    std::vector<int32_t> remap(sc->texture_count, -1);
-    auto use = [&](int32_t& idx, bool needed) {
-        if (idx < 0 || !needed || (uint32_t)idx >= sc->texture_count) { if (idx >= 0 && (uint32_t)idx < sc->texture_count) idx = -1; return; }
-        if (remap[idx] < 0) { remap[idx] = (int32_t)texs.size(); texs.push_back(sc->textures[idx]); }
-        idx = remap[idx];
-    };
-    for (auto& pr : prims) { use(pr.albedo_texture, true); use(pr.normal_texture, need_normal); use(pr.metallic_roughness_texture, need_mr); }
-    m2s_scene slim = *sc;
-    slim.primitives = prims.data();
-    slim.textures = texs.data();
-    slim.texture_count = (uint32_t)texs.size();
+    SlimScene slim_holder(sc, p->layout);
+    const m2s_scene& slim = slim_holder.scene;
     // Pipeline (REF96 / PACKED56, meshes large enough to split): the triangle range is cut into chunks; chunk c's
     // records are appended after chunk c-1's on the device (fragment kernel: prev_totals) and start crossing
     // PCIe on a second stream while chunk c+1 is still being uploaded and converted — H2D and D2H overlap.
@@ -644,6 +655,58 @@ M2S_EXPORT m2s_status m2s_convert_host(m2s_ctx* ctx, const m2s_scene* sc, const 
     m2s_scene_free(ctx, ds);
     return st;
 }
+
+// ---- scene -> .ply file: rows encoded on the GPU, streamed to disk through two pinned buffers -------------
+// (SceneManager::exportPly + parsers.cpp::savePlyVector write 4 bytes at a time from one thread)
+namespace m2s {
+m2s_status convert_scene_to_ply(m2s_ctx* ctx, const m2s_scene* sc, const m2s_params* p, const char* path, m2s_result* res) {
+    if (!ctx || !sc || !p || !path) { set_error("convert_scene_to_ply: NULL argument"); return M2S_E_INVALID; }
+    if (p->layout < M2S_LAYOUT_PLY_STANDARD || p->layout > M2S_LAYOUT_PLY_COMPRESSED) { set_error("convert_scene_to_ply: a .ply row layout is required"); return M2S_E_INVALID; }
+    const uint32_t format = p->layout - M2S_LAYOUT_PLY_STANDARD;
+    const uint32_t stride = m2s_record_stride(p->layout);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    SlimScene slim(sc, p->layout);
+    m2s_dscene* ds = nullptr;
+    m2s_status st = scene_upload_impl(ctx, &slim.scene, &ds, UINT64_MAX, false);
+    if (st != M2S_OK) return st;
+    const uint64_t cap = p->max_gaussians ? p->max_gaussians : m2s_reference_capacity(p->resolution, sc->primitive_count);
+    st = grow(ctx, &ctx->d_out, &ctx->out_bytes, std::max<uint64_t>(cap, 1) * stride);
+    if (st != M2S_OK) { cudaStreamSynchronize(ctx->stream); m2s_scene_free(ctx, ds); return st; }
+    m2s_result r;
+    std::memset(&r, 0, sizeof(r));
+    st = m2s_convert(ctx, ds, p, ctx->d_out, cap, nullptr, &r);  // synchronises; r.written rows are in d_out
+    m2s_scene_free(ctx, ds);
+    if (res) *res = r;
+    if (st != M2S_OK && st != M2S_E_CAPACITY) return st;
+    for (int i = 0; i < 2; ++i)
+        if (!ctx->h_stage[i]) CUDA_TRY(cudaMallocHost(&ctx->h_stage[i], m2s_ctx::kStageBytes));
+    FILE* f = std::fopen(path, "wb");
+    if (!f) { set_error(std::string("cannot open ") + path); return M2S_E_IO; }
+    char hdr[4096];
+    const size_t hn = m2s_ply_header(format, r.written, hdr, sizeof(hdr));
+    bool ok = std::fwrite(hdr, 1, hn, f) == hn;
+    const size_t rows_per_block = m2s_ctx::kStageBytes / stride;
+    const uint64_t nblocks = (r.written + rows_per_block - 1) / rows_per_block;
+    cudaError_t e = cudaSuccess;
+    auto block_bytes = [&](uint64_t b) { return (size_t)std::min<uint64_t>(rows_per_block, r.written - b * rows_per_block) * stride; };
+    for (uint64_t b = 0; b <= nblocks && ok && e == cudaSuccess; ++b) {
+        if (b < nblocks) {  // start the download of block b ...
+            e = cudaMemcpyAsync(ctx->h_stage[b & 1], reinterpret_cast<const unsigned char*>(ctx->d_out) + b * rows_per_block * stride,
+                                block_bytes(b), cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_chunk[b & 1], ctx->stream);
+        }
+        if (b > 0 && e == cudaSuccess) {  // ... and write block b-1 while it crosses PCIe
+            e = cudaEventSynchronize(ctx->ev_chunk[(b - 1) & 1]);
+            if (e == cudaSuccess) ok = std::fwrite(ctx->h_stage[(b - 1) & 1], 1, block_bytes(b - 1), f) == block_bytes(b - 1);
+        }
+    }
+    cudaStreamSynchronize(ctx->stream);
+    ok = (std::fclose(f) == 0) && ok;
+    if (e != cudaSuccess) { set_error(std::string("convert_scene_to_ply download: ") + cudaGetErrorString(e)); return M2S_E_CUDA; }
+    if (!ok) { set_error(std::string("short write to ") + path); return M2S_E_IO; }
+    return st;
+}
+}  // namespace m2s
 
 // ---- outputs ----------------------------------------------------------------------------------
 M2S_EXPORT m2s_status m2s_ply_encode(m2s_ctx* ctx, const void* d_ref96, uint64_t count, uint32_t format, float mult, void* d_rows,

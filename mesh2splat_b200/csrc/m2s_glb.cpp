@@ -32,6 +32,7 @@
 namespace m2s {
 void set_error(const std::string& msg);
 m2s_status write_ply_rows(const char* path, uint32_t format, const void* rows, uint64_t count);
+m2s_status convert_scene_to_ply(m2s_ctx* ctx, const m2s_scene* sc, const m2s_params* p, const char* path, m2s_result* res);
 }
 
 #define M2S_EXPORT extern "C" __attribute__((visibility("default")))
@@ -857,17 +858,11 @@ M2S_EXPORT m2s_status m2s_convert_file(m2s_ctx* ctx, const char* glb_path, uint3
     m2s_params_default(&p);
     p.resolution = resolution;
     p.gaussian_std = gaussian_std;
-    p.layout = M2S_LAYOUT_PLY_STANDARD + ply_format;  // rows are encoded on the GPU
-    const uint64_t cap = m2s_reference_capacity(resolution, hs->view.primitive_count);
-    const uint32_t stride = m2s_record_stride(p.layout);
-    std::vector<uint8_t> rows;
-    try { rows.resize((size_t)cap * stride); } catch (const std::bad_alloc&) { m2s_hscene_free(hs); m2s::set_error("out of memory"); return M2S_E_IO; }
+    p.layout = M2S_LAYOUT_PLY_STANDARD + ply_format;  // rows are encoded on the GPU and streamed to disk
     m2s_result r;
     std::memset(&r, 0, sizeof(r));
-    st = m2s_convert_host(ctx, &hs->view, &p, rows.data(), cap, nullptr, &r);
+    st = m2s::convert_scene_to_ply(ctx, &hs->view, &p, ply_path, &r);
     m2s_hscene_free(hs);
     if (result) *result = r;
-    if (st != M2S_OK && st != M2S_E_CAPACITY) return st;
-    const m2s_status wst = m2s::write_ply_rows(ply_path, ply_format, rows.data(), r.written);
-    return wst != M2S_OK ? wst : st;
+    return st;
 }

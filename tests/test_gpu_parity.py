@@ -241,6 +241,44 @@ def test_convert_host_pipelined_capacity(gpu_ctx):
     assert_records_match(s, LAYOUT_PACKED56, rec, keys, want[order][pos], keys)
 
 
+@pytest.mark.parametrize("fmt", [0, 1, 2])
+def test_convert_file_glb_to_ply(gpu_ctx, tmp_path, fmt):
+    """m2s_convert_file = loadModel -> ConversionPass::execute -> exportPly: the file must be the oracle's file
+    (same header bytes, same rows as a multiset; rows are ordered by atomic arrival in both)."""
+    from test_abi_host import _make_glb
+    from mesh2splat_b200.gltf import load_glb
+    glb, ply = tmp_path / "m.glb", tmp_path / f"m{fmt}.ply"
+    _make_glb(str(glb), two_prims=True)
+    R, std = 96, 0.65
+    res = gpu_ctx.convert_file(str(glb), R, str(ply), std, fmt)
+    s = load_glb(str(glb))
+    want, wkeys, total = oracle.convert(s, R, LAYOUT_REF96)
+    assert res.total == total and res.written == len(want) and total > 1000
+    ref = oracle.ply_bytes(want, fmt, float(np.float32(std) / np.float32(R)))
+    got = ply.read_bytes()
+    hdr = oracle.ply_header(fmt, len(want))
+    assert got[: len(hdr)] == hdr and len(got) == len(ref)
+    stride = {0: 248, 1: 76, 2: 48}[fmt]
+    g = np.frombuffer(got[len(hdr):], np.uint8).reshape(-1, stride)
+    w = np.frombuffer(ref[len(hdr):], np.uint8).reshape(-1, stride)
+    # identify rows by position (first 12 bytes: three floats, distinct per fragment within a primitive plane)
+    gp, wp = g[:, :12].copy().view(np.float32), w[:, :12].copy().view(np.float32)
+    go, wo = np.lexsort(np.round(gp * 4096).T), np.lexsort(np.round(wp * 4096).T)
+    assert np.allclose(gp[go], wp[wo], atol=2e-5)
+    G, W = g[go], w[wo]
+    if fmt == 2:  # pos f32x3 | rgba u8x4 | quat f32x4 | log-scale f32x3 | octahedral normal u8x2 | roughness, metallic u8
+        fcols = np.r_[0:12, 16:44]
+        bcols = np.r_[12:16, 44:48]
+        assert np.abs(G[:, bcols].astype(np.int16) - W[:, bcols].astype(np.int16)).max() <= 1  # one count of rounding slack
+    else:
+        fcols = np.r_[0:stride]
+    gf, wf = np.ascontiguousarray(G[:, fcols]).view(np.float32), np.ascontiguousarray(W[:, fcols]).view(np.float32)
+    fin = np.isfinite(wf)
+    assert np.array_equal(fin, np.isfinite(gf))
+    assert np.allclose(gf[fin], wf[fin], rtol=2e-4, atol=2e-4)
+    assert np.array_equal(gf[~fin], wf[~fin])  # opacity = +inf for alpha = 1
+
+
 def test_repeated_launches_rearm_the_scheduler(gpu_ctx):
     s = synth.unit_quad()
     ds = gpu_ctx.upload(s)
