@@ -540,6 +540,11 @@ __global__ void __launch_bounds__(Cfg<LAYOUT>::kWarps * 32) __maxnreg__(Cfg<LAYO
     WarpBlock<LAYOUT>& wb = *reinterpret_cast<WarpBlock<LAYOUT>*>(smem + (size_t)warp * sizeof(WarpBlock<LAYOUT>));
     const unsigned char* tri_bytes = reinterpret_cast<const unsigned char*>(a.tris);
 
+#ifdef M2S_EARLY_TRIGGER
+    // PDL early trigger (one fragment-kernel CTA per SM becomes resident beside this CTA and parks in
+    // griddepcontrol.wait).  Measured SLOWER (PACKED56 40.5 vs 39.8 us, REF96 62.4 vs 59.5 us): off.
+    asm volatile("griddepcontrol.launch_dependents;");
+#endif
     if (lane == 0) {
         mbar_init(&wb.bar, 1);
         fence_barrier_init();
