@@ -214,15 +214,15 @@ def run_ours(args):
     ds = ctx.upload(scene)
     T = scene.triangle_count
     # shard: contiguous ranges balanced by estimated candidate pixels (mesh2splat_b200/shard.py)
-    from mesh2splat_b200.shard import estimate_cost, plan_shards
+    from mesh2splat_b200.shard import estimate_cost, plan_work
     cost = estimate_cost(scene.triangles, scene.primitives[0].bbox_min, scene.primitives[0].bbox_max, DENSITY)
-    lo, cnt_ = plan_shards(T, world, cost)[rank]
+    lo, cnt_, row0, row1 = plan_work(T, world, DENSITY, cost)[rank]  # triangle ranges, or row bands for huge triangles
     hi = lo + cnt_
     cap_total = 6 * DENSITY * DENSITY
     # a dedicated (non-default) stream: everything timed is enqueued on it and the events are recorded on it
     stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)
-    params = _abi.make_params(DENSITY, layout, 0.65, 0, _abi.FLAG_UNCAPPED, lo, hi - lo)
+    params = _abi.make_params(DENSITY, layout, 0.65, 0, _abi.FLAG_UNCAPPED, lo, hi - lo, row0, row1)
     out = torch.empty(cap_total * stride, dtype=torch.uint8, device=dev)
     d_total = torch.zeros(1, dtype=torch.int64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)

@@ -117,6 +117,11 @@ typedef struct m2s_params {
      * per rank); triangle_count == 0 means "to the end" */
     uint64_t first_triangle;
     uint64_t triangle_count;
+    /* pixel-row band of the R x R grid this call rasterises: rows [row_begin, row_end); row_end == 0 means
+     * "to R".  Lets a multi-GPU plan split meshes made of a few huge triangles ("split very large
+     * triangles by pixel-row bands"): every rank takes all triangles but only its rows. */
+    uint32_t row_begin;
+    uint32_t row_end;
 } m2s_params;
 
 typedef struct m2s_result {

@@ -43,7 +43,8 @@ class m2s_scene(C.Structure):
 class m2s_params(C.Structure):
     _fields_ = [("resolution", C.c_uint32), ("gaussian_std", C.c_float),
                 ("max_gaussians", C.c_uint64), ("layout", C.c_uint32), ("flags", C.c_uint32),
-                ("first_triangle", C.c_uint64), ("triangle_count", C.c_uint64)]
+                ("first_triangle", C.c_uint64), ("triangle_count", C.c_uint64),
+                ("row_begin", C.c_uint32), ("row_end", C.c_uint32)]
 
 
 class m2s_result(C.Structure):
@@ -60,9 +61,9 @@ class m2s_peers(C.Structure):
 
 def make_params(resolution: int, layout: int = LAYOUT_REF96, gaussian_std: float = 0.65,
                 max_gaussians: int = 0, flags: int = 0, first_triangle: int = 0,
-                triangle_count: int = 0) -> m2s_params:
+                triangle_count: int = 0, row_begin: int = 0, row_end: int = 0) -> m2s_params:
     return m2s_params(int(resolution), float(gaussian_std), int(max_gaussians), int(layout),
-                      int(flags), int(first_triangle), int(triangle_count))
+                      int(flags), int(first_triangle), int(triangle_count), int(row_begin), int(row_end))
 
 
 def reference_capacity(resolution: int, primitive_count: int) -> int:

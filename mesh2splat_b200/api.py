@@ -123,7 +123,7 @@ class Context:
     def convert(self, dscene: DeviceScene, resolution: int, layout: int = _abi.LAYOUT_REF96,
                 gaussian_std: float = 0.65, max_gaussians: int = 0, flags: int = 0, first_triangle: int = 0,
                 triangle_count: int = 0, capacity: int | None = None, want_keys: bool = False,
-                out=None, keys=None, allow_overflow: bool = True) -> ConvertOutput:
+                out=None, keys=None, allow_overflow: bool = True, row_begin: int = 0, row_end: int = 0) -> ConvertOutput:
         torch = _torch()
         stride = _abi.STRIDES[layout]
         if capacity is None:
@@ -133,7 +133,8 @@ class Context:
             out = torch.empty(max(1, capacity) * stride, dtype=torch.uint8, device=dev)
         if want_keys and keys is None:
             keys = torch.empty(max(1, capacity), dtype=torch.int64, device=dev)
-        p = _abi.make_params(resolution, layout, gaussian_std, max_gaussians, flags, first_triangle, triangle_count)
+        p = _abi.make_params(resolution, layout, gaussian_std, max_gaussians, flags, first_triangle, triangle_count,
+                             row_begin, row_end)
         res = _abi.m2s_result()
         st = check(lib().m2s_convert(self.handle, dscene.handle, C.byref(p), out.data_ptr(), capacity,
                                      keys.data_ptr() if keys is not None else None, C.byref(res)),

@@ -419,6 +419,8 @@ static m2s_status convert_enqueue_impl(m2s_ctx* ctx, const m2s_dscene* s, const 
     a.ranges = s->d_ranges; a.nranges = s->nranges;
     a.prims = s->d_prims; a.nprims = s->nprims; a.texs = s->d_texs; a.tex_base = s->d_arena; a.ntex = s->ntex;
     a.R = p->resolution;
+    a.row_begin = std::min(p->row_begin, p->resolution);
+    a.row_end = (p->row_end == 0 || p->row_end > p->resolution) ? p->resolution : p->row_end;
     a.half_R = (float)p->resolution * 0.5f;
     a.mult = p->gaussian_std / (float)p->resolution;
     a.log_sz = logf(1e-7f * a.mult);

@@ -56,6 +56,7 @@ struct ConvertArgs {
     const uint32_t* tex_base;  // texture arena
     uint32_t ntex;
     uint32_t R;
+    uint32_t row_begin, row_end;  // pixel-row band [row_begin, row_end) of the R x R grid (whole grid: 0, R)
     float half_R;
     float mult;  // sigma / R (SceneManager.cpp:668)
     float log_sz;  // ln(1e-7 * mult): the constant third log-scale of the packed layout

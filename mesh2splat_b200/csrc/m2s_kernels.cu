@@ -349,7 +349,7 @@ __device__ __noinline__ uint32_t setup_triangle(const float4* __restrict__ t4, u
     const int ymin = min(Y[0], min(Y[1], Y[2])), ymax = max(Y[0], max(Y[1], Y[2]));
     const int R1 = (int)a.R - 1;
     const int x0 = max(0, (xmin + 127) >> 8), x1 = min(R1, (xmax - 128) >> 8);
-    const int y0 = max(0, (ymin + 127) >> 8), y1 = min(R1, (ymax - 128) >> 8);
+    const int y0 = max((int)a.row_begin, (ymin + 127) >> 8), y1 = min((int)a.row_end - 1, (ymax - 128) >> 8);  // row band
     if (x1 < x0 || y1 < y0) return 0;
     tr.x0 = (unsigned short)x0; tr.y0 = (unsigned short)y0;
     tr.w = (unsigned short)(x1 - x0 + 1); tr.h = (unsigned short)(y1 - y0 + 1);

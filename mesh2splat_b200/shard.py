@@ -39,6 +39,24 @@ def plan_shards(triangle_count: int, world: int, cost: np.ndarray | None = None)
     return [(int(cuts[r]), int(cuts[r + 1] - cuts[r])) for r in range(world)]
 
 
+def plan_work(triangle_count: int, world: int, resolution: int, cost: np.ndarray | None = None) -> list:
+    """Per-rank work item (first_triangle, triangle_count, row_begin, row_end) for m2s_params.
+
+    Normally contiguous triangle ranges balanced by `cost` (plan_shards).  When a few huge triangles dominate
+    — no cut of the triangle list can balance it, e.g. a 2-triangle quad on 8 GPUs — every rank takes ALL
+    triangles but only a band of pixel rows of the R x R grid ("split very large triangles by
+    pixel-row bands"); the per-triangle set-up is then replicated, which is cheap exactly when triangles are few."""
+    ranges = plan_shards(triangle_count, world, cost)
+    if world > 1 and cost is not None and triangle_count > 0:
+        c = np.maximum(np.asarray(cost, np.float64), 0.0)
+        cum = np.concatenate([[0.0], np.cumsum(c)])
+        worst = max(cum[a + n] - cum[a] for a, n in ranges)
+        if worst > 1.25 * cum[-1] / world and resolution >= world:  # triangle ranges cannot balance this scene
+            rows = [(resolution * r) // world for r in range(world + 1)]
+            return [(0, triangle_count, rows[r], rows[r + 1]) for r in range(world)]
+    return [(a, n, 0, 0) for a, n in ranges]
+
+
 def estimate_cost(triangles: np.ndarray, bbox_min, bbox_max, resolution: int) -> np.ndarray:
     """Per-triangle candidate-pixel estimate: area of the dominant-axis projection's bounding box on
     the R x R grid (+1 for the fixed per-triangle set-up)."""

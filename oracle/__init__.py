@@ -159,10 +159,11 @@ def calibrate_threads(prep: "Prepared", resolution: int = 128, layout: int = _ab
 
 def convert(scene: _abi.Scene, resolution: int, layout: int = _abi.LAYOUT_REF96, gaussian_std: float = 0.65,
             max_gaussians: int = 0, flags: int = 0, first_triangle: int = 0, triangle_count: int = 0,
-            capacity: int | None = None, want_keys: bool = True, threads: int = 0):
+            capacity: int | None = None, want_keys: bool = True, threads: int = 0, row_begin: int = 0, row_end: int = 0):
     """Whole pass on the CPU. Returns (records[structured], keys|None, total)."""
     cs, keep = scene.c_struct()
-    p = _abi.make_params(resolution, layout, gaussian_std, max_gaussians, flags, first_triangle, triangle_count)
+    p = _abi.make_params(resolution, layout, gaussian_std, max_gaussians, flags, first_triangle, triangle_count,
+                         row_begin, row_end)
     if capacity is None:
         capacity = max_gaussians if max_gaussians else (
             _abi.reference_capacity(resolution, len(scene.primitives)) if not (flags & _abi.FLAG_UNCAPPED)

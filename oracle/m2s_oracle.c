@@ -531,6 +531,8 @@ ORC_API uint64_t orc_convert_prepared(const m2s_scene* sc, const orc_prepared* p
     }
     if (cap > out_capacity) cap = out_capacity;
     const float mult = pr->gaussian_std / (float)R;
+    const uint32_t row_begin = pr->row_begin < R ? pr->row_begin : R;
+    const uint32_t row_end = (pr->row_end == 0 || pr->row_end > R) ? R : pr->row_end;
 #ifdef _OPENMP
     if (threads > 0) omp_set_num_threads(threads);
 #else
@@ -557,6 +559,10 @@ ORC_API uint64_t orc_convert_prepared(const m2s_scene* sc, const orc_prepared* p
         const m2s_primitive* P = &sc->primitives[c->prim];
         const float* tri = sc->triangles + (first + (uint64_t)t) * 36;
         if (!orc_triangle_setup(tri, P->bbox_min, P->bbox_max, R, &c->s)) continue;
+        /* pixel-row band of this call (m2s_params.row_begin/row_end; the whole grid by default) */
+        if (c->s.y0 < (int32_t)row_begin) c->s.y0 = (int32_t)row_begin;
+        if (c->s.y1 > (int32_t)row_end - 1) c->s.y1 = (int32_t)row_end - 1;
+        if (c->s.y1 < c->s.y0) continue;
         offs[t + 1] = count_fragments(&c->s);
         /* per-pixel steps of the mesh uv: d(uv)/dx = sum_k uv_k * A_k / area2, d/dy with B_k */
         float ia = 1.0f / (float)(c->s.area2 < 0 ? -c->s.area2 : c->s.area2);

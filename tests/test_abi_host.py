@@ -45,7 +45,7 @@ def test_struct_layouts_match_the_header():
     assert C.sizeof(_abi.m2s_texture) == 16
     assert C.sizeof(_abi.m2s_primitive) == 72
     assert C.sizeof(_abi.m2s_scene) == 48
-    assert C.sizeof(_abi.m2s_params) == 40
+    assert C.sizeof(_abi.m2s_params) == 48
     assert C.sizeof(_abi.m2s_result) == 32
     L = _lib.lib()
     for layout, stride in _abi.STRIDES.items():

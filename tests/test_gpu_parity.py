@@ -178,6 +178,31 @@ def test_shard_ranges_partition_the_output(gpu_ctx):
     ds.free()
 
 
+def test_row_bands_partition_the_output(gpu_ctx):
+    """m2s_params.row_begin/row_end: bands of pixel rows of the same triangles (huge and small) partition the
+    whole result; each band equals the oracle's band."""
+    a = synth.unit_quad()                       # 2 huge triangles (deferred, chunked) ...
+    b = synth.displaced_sphere(30, 16, seed=4)  # ... plus ~900 small ones
+    tri = np.vstack([a.triangles, b * np.float32(0.45) + np.float32(0.5)])
+    s = Scene(tri, [Primitive(0, len(tri), (1, 1, 1, 1), 0, -1, -1)], [synth.random_texture(64, 64, 3)])
+    s.compute_bboxes()
+    ds = gpu_ctx.upload(s)
+    R = 600
+    whole = gpu_ctx.convert(ds, R, LAYOUT_PACKED56, flags=FLAG_UNCAPPED, want_keys=True)
+    parts = []
+    for r0, r1 in [(0, 1), (1, 77), (77, 300), (300, 599), (599, 0)]:
+        o = gpu_ctx.convert(ds, R, LAYOUT_PACKED56, flags=FLAG_UNCAPPED, want_keys=True, row_begin=r0, row_end=r1)
+        k = o.keys_numpy()
+        rows = (k >> np.uint64(12)) & np.uint64(0xFFF)
+        assert rows.min() >= r0 and rows.max() < (r1 or R)
+        rec, keys, total = oracle.convert(s, R, LAYOUT_PACKED56, flags=FLAG_UNCAPPED, row_begin=r0, row_end=r1)
+        assert o.total == total
+        assert_records_match(s, LAYOUT_PACKED56, o.numpy(), k, rec, keys)
+        parts.append(k)
+    assert np.array_equal(np.sort(np.concatenate(parts)), np.sort(whole.keys_numpy()))
+    ds.free()
+
+
 @pytest.mark.parametrize("layout", [LAYOUT_PACKED56, LAYOUT_PLY_STANDARD, LAYOUT_PLY_PBR, LAYOUT_PLY_COMPRESSED])
 def test_other_layouts(gpu_ctx, layout):
     tri = synth.displaced_sphere(32, 16, seed=4)
@@ -277,6 +302,26 @@ def test_convert_file_glb_to_ply(gpu_ctx, tmp_path, fmt):
     assert np.array_equal(fin, np.isfinite(gf))
     assert np.allclose(gf[fin], wf[fin], rtol=2e-4, atol=2e-4)
     assert np.array_equal(gf[~fin], wf[~fin])  # opacity = +inf for alpha = 1
+
+
+def test_watertight_tiling_full_size(gpu_ctx):
+    """Size-independent coverage property at R = 2048: a Delaunay tiling of the unit square (~60 k triangles of
+    every shape, sub-pixel slivers to 100-pixel triangles) emits each of the 4 194 304 pixel centres exactly
+    once, and a second run produces bit-identical records (as a set)."""
+    from util import planar_triangulation
+    s = planar_triangulation(30000, seed=7)
+    R = 2048
+    ds = gpu_ctx.upload(s)
+    a = gpu_ctx.convert(ds, R, LAYOUT_PACKED56, flags=FLAG_UNCAPPED, capacity=R * R + 64, want_keys=True)
+    assert a.total == R * R
+    ka = a.keys_numpy()
+    assert len(np.unique(ka & np.uint64(0xFFFFFF))) == R * R
+    ra = a.numpy()[np.argsort(ka)].copy()
+    b = gpu_ctx.convert(ds, R, LAYOUT_PACKED56, flags=FLAG_UNCAPPED, capacity=R * R + 64, want_keys=True)
+    kb = b.keys_numpy()
+    assert np.array_equal(np.sort(ka), np.sort(kb))
+    assert ra.tobytes() == b.numpy()[np.argsort(kb)].tobytes()
+    ds.free()
 
 
 def test_repeated_launches_rearm_the_scheduler(gpu_ctx):

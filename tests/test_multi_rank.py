@@ -84,3 +84,36 @@ def test_plan_shards_properties():
     assert 8 <= sh[0][1] <= 12 and sh[0][1] + sh[1][1] == 100
     with pytest.raises(ValueError):
         plan_shards(10, 0)
+
+
+def test_plan_work_switches_to_row_bands_for_huge_triangles():
+    """A 2-triangle quad cannot be balanced by triangle ranges: plan_work hands every rank all triangles and a
+    band of pixel rows; the bands partition the grid and the per-band oracle outputs add up to the whole."""
+    sys.path.insert(0, ROOT)
+    import oracle
+    from mesh2splat_b200 import _abi, synth
+    from mesh2splat_b200.shard import estimate_cost, plan_work
+    s = synth.unit_quad()
+    R = 100
+    cost = estimate_cost(s.triangles, s.primitives[0].bbox_min, s.primitives[0].bbox_max, R)
+    assert plan_work(s.triangle_count, 2, R, cost) == [(0, 1, 0, 0), (1, 1, 0, 0)]  # two equal triangles, two ranks: ranges do
+    for world in (3, 8):
+        plan = plan_work(s.triangle_count, world, R, cost)
+        assert all(p[0] == 0 and p[1] == s.triangle_count for p in plan)
+        assert plan[0][2] == 0 and plan[-1][3] == R and all(plan[i][3] == plan[i + 1][2] for i in range(world - 1))
+        keys = []
+        for first, count, r0, r1 in plan:
+            rec, k, total = oracle.convert(s, R, _abi.LAYOUT_PACKED56, first_triangle=first, triangle_count=count,
+                                           row_begin=r0, row_end=r1)
+            rows = (k >> np.uint64(12)) & np.uint64(0xFFF)
+            assert total == len(k) == (r1 - r0) * R and rows.min() >= r0 and rows.max() < r1
+            keys.append(k)
+        whole, wk, wtotal = oracle.convert(s, R, _abi.LAYOUT_PACKED56)
+        assert np.array_equal(np.sort(np.concatenate(keys)), np.sort(wk))
+    # a mesh of many similar triangles keeps contiguous triangle ranges (whole grid: rows 0, 0)
+    tri = synth.displaced_sphere(24, 12, seed=2)
+    sp = _abi.Scene(tri, [_abi.Primitive(0, len(tri), (1, 1, 1, 1), -1, -1, -1)], [])
+    sp.compute_bboxes()
+    c2 = estimate_cost(sp.triangles, sp.primitives[0].bbox_min, sp.primitives[0].bbox_max, 64)
+    plan = plan_work(sp.triangle_count, 4, 64, c2)
+    assert all(p[2] == 0 and p[3] == 0 for p in plan) and sum(p[1] for p in plan) == sp.triangle_count

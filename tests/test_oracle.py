@@ -184,3 +184,15 @@ def test_oracle_thread_count_does_not_change_output():
     r1, k1, t1 = oracle.convert(s, 96, threads=1)
     r8, k8, t8 = oracle.convert(s, 96, threads=8)
     assert t1 == t8 and np.array_equal(k1, k8) and r1.tobytes() == r8.tobytes()
+
+
+@pytest.mark.parametrize("R,n", [(97, 300), (256, 5000)])
+def test_watertight_tiling_covers_every_pixel_exactly_once(R, n):
+    """GL 4.6 14.6.1: of two polygons sharing an edge exactly one produces the fragment (top-left rule here).
+    A Delaunay tiling of the unit square must therefore emit each of the R*R pixel centres exactly once."""
+    from util import planar_triangulation
+    s = planar_triangulation(n, seed=R)
+    rec, keys, total = oracle.convert(s, R, _abi.LAYOUT_REF96, flags=_abi.FLAG_UNCAPPED)
+    assert total == R * R
+    pix = keys & np.uint64(0xFFFFFF)
+    assert len(np.unique(pix)) == R * R

@@ -119,3 +119,21 @@ def png_bytes(img: np.ndarray) -> bytes:
 
     return (b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, ctype, 0, 0, 0))
             + chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))
+
+
+def planar_triangulation(n_points: int, seed: int) -> _abi.Scene:
+    """Delaunay triangulation of the unit square (4 corners + seeded random interior points), z = 0, uv = xy.
+    The triangles tile the square with shared edges, so a watertight rasteriser (top-left rule) must emit every
+    pixel centre of the R x R grid exactly once — a size-independent property of the coverage rules."""
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(seed)
+    pts = np.vstack([[[0, 0], [1, 0], [1, 1], [0, 1]], rng.random((n_points, 2))]).astype(np.float32)
+    tri = Delaunay(pts.astype(np.float64)).simplices
+    v = np.zeros((len(tri), 3, 12), np.float32)
+    v[:, :, 0:2] = pts[tri]
+    v[:, :, 5] = 1.0            # normal (0,0,1)
+    v[:, :, 6] = 1.0; v[:, :, 9] = 1.0   # tangent (1,0,0,1)
+    v[:, :, 10:12] = pts[tri]
+    s = _abi.Scene(v.reshape(len(tri), 36), [_abi.Primitive(0, len(tri), (1, 1, 1, 1), -1, -1, -1)], [])
+    s.compute_bboxes()
+    return s
