@@ -438,6 +438,7 @@ def test_config4_million_triangle_sphere(gpu_ctx):
     orec, okeys, total = oracle.convert(s, 256, LAYOUT_PACKED56)
     assert out.total == total and 50_000 < total < 400_000
     assert np.array_equal(np.sort(out.keys_numpy()), np.sort(okeys))
+    assert_records_match(s, LAYOUT_PACKED56, out.numpy(), out.keys_numpy(), orec, okeys)
     from mesh2splat_b200.shard import plan_shards
     parts = []
     for first, count in plan_shards(s.triangle_count, 8):
