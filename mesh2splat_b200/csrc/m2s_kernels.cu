@@ -2,37 +2,42 @@
 //
 // Two kernels on one stream replace the reference's geometry shader, fixed-function rasteriser,
 // fragment shader and SSBO atomic append (converter{GS,FS}.glsl, ConversionPass.cpp:114-116); the data
-// between them (8-byte fragment ids, 224-256 B per-triangle records) stays in the 126 MB L2.
+// between them (8-byte fragment ids, 144-176 B per-triangle records) stays in the 126 MB L2.  The second
+// kernel is launched with programmatic dependent launch.
 //
-// raster_kernel (persistent, one CTA per SM, every WARP an autonomous pipeline, no __syncthreads in the
-// steady state):
-//   claim a work unit (<= 32 consecutive triangles) from a global counter; claim the next one at once
-//     and prefetch its bytes into L2
+// raster_kernel (persistent, one CTA per SM, every WARP an autonomous pipeline; one __syncthreads after the
+// descriptor tables are copied to shared memory, none in the steady state):
+//   work unit = <= 32 consecutive triangles; a warp's first unit is static (global warp id), further ones
+//     are claimed from a global counter one unit ahead and their bytes prefetched into L2
 //   TMA (cp.async.bulk + mbarrier complete_tx) stages the unit's 144 B/triangle into shared memory
 //   per-triangle stage, one LANE per triangle (converterGS.glsl:326-443): longest edge, face normal,
 //     dominant axis, orthographic uv, quaternion, UV->3D Jacobian scale; rasteriser set-up: 24.8
-//     fixed-point window coords, int64 edge functions, top-left ownership bits, candidate pixel box;
-//     attribute plane equations in place over the staged vertices; the triangle's resolved sampler
-//     state (mip level pair, blend fraction, level offsets and sizes)
-//   the unit's records leave shared memory as two TMA bulk stores (cp.async.bulk.global.shared::cta)
+//     fixed-point window coords, int64 edge functions, top-left ownership bits, candidate pixel box
+//     (clamped to the call's pixel-row band); exact barycentric state (edge functions at the box origin,
+//     per-pixel steps, 1/area); the triangle's resolved sampler state (mip level pair, blend fraction,
+//     level offsets and sizes)
+//   the unit's per-triangle records leave shared memory as ONE TMA bulk store (cp.async.bulk.global.shared::cta)
 //   coverage, three regimes by candidate-pixel count:
-//     small  (<= 64, fits int32)  lane-per-triangle, lock-step incremental edge functions
+//     small  (<= 64, fits int32)  lane-per-triangle, lock-step incremental edge functions into a 64-bit
+//                                 hit mask; warp scan -> contiguous range per triangle; second pass over
+//                                 the set bits writes the ids (fragments leave TRIANGLE-MAJOR)
 //     medium (<= 1024)            warp-per-triangle, 32 candidates per step, int64 edge functions
-//     big                         pushed as 512-candidate chunks to a global queue and rasterised by
-//                                 ALL warps of the grid after the units are set up
-//     survivors are ballot-compacted into the warp's queue; one global atomicAdd per <= 512 fragments
-//     reserves the output range (the reference: one atomicCounterIncrement per fragment) and the ids
-//     are written coalesced.  Fragment i of the id list IS output record i.
+//     big                         pushed as 512-candidate chunks to a global queue (one atomicAdd per warp)
+//                                 and rasterised by ALL warps of the grid after the units are set up
+//     one global atomicAdd per unit (small) / per <= 512 fragments (medium, big) reserves the output range
+//     (the reference: one atomicCounterIncrement per fragment).  Fragment i of the id list IS output record i.
 // fragment_kernel (converterFS.glsl:44-104; lean registers, high occupancy, grid-stride):
-//   a warp takes 32 consecutive fragments: 2 FFMA per attribute from the plane equations, all texel
-//   loads of all bound maps issued back to back, trilinear filter on the FMA pipe (u8->f32 by
-//   PRMT+FADD), TBN normal, encode; the 32 records are transposed through shared memory and written as
-//   one contiguous, 16-byte-vectorised span.
+//   a warp takes 32 consecutive fragments: exact barycentrics from the int64 edge functions, attributes
+//   from the original vertices, all texel loads of all bound maps issued back to back, trilinear filter on
+//   the FMA pipe (u8->f32 by PRMT+FADD), TBN normal, encode; the 32 records are transposed through shared
+//   memory and written as one contiguous span (16-byte stores when aligned) — locally, or into every
+//   rank's final buffer over NVLink (fused multi-GPU gather), or after the earlier chunks' records
+//   (appended launches of the pipelined host path).
 //
-// Bit-exactness: every float operation that feeds a DECISION (edge ordering, dominant axis,
-// fixed-point snapping => coverage) is written with __f*_rn intrinsics in the operation order of
-// the oracle (and of GLM, which the reference's GLSL-as-C++ build uses), so coverage is bit-exact.
-// Per-fragment values may use FMA contraction and are compared with a tolerance.
+// Bit-exactness: every float operation of the per-triangle stage is written with __f*_rn intrinsics in the
+// operation order of the oracle (and of GLM, which the reference's GLSL-as-C++ build uses): coverage is
+// bit-exact and Scale/Quaternion match converterGS.glsl bit for bit.  Per-fragment values may use FMA
+// contraction and are compared with a tolerance.
 #include <cstdio>
 #include "m2s_device.cuh"
 
