@@ -177,7 +177,11 @@ m2s_status m2s_convert_enqueue(m2s_ctx* ctx, const m2s_dscene* scene, const m2s_
 m2s_status m2s_convert(m2s_ctx* ctx, const m2s_dscene* scene, const m2s_params* params,
                        void* d_out, uint64_t out_capacity, uint64_t* d_keys, m2s_result* result);
 /* Host-buffer form: upload scene, convert, download records (and keys if h_keys != NULL).
- * Everything a caller holding CPU data pays for. */
+ * Everything a caller holding CPU data pays for.  Only the maps the layout consumes are uploaded.  For
+ * REF96 / PACKED56 and >= 16384 triangles the call is pipelined: the triangle range is converted in
+ * chunks whose records are appended on the device, and each chunk's download overlaps the next chunk's
+ * upload and kernels (pass pinned host memory to benefit; M2S_HOST_CHUNKS=n overrides the chunk count,
+ * 1 = unpipelined).  The cap and the returned total behave as in one launch. */
 m2s_status m2s_convert_host(m2s_ctx* ctx, const m2s_scene* scene, const m2s_params* params,
                             void* h_out, uint64_t out_capacity, uint64_t* h_keys,
                             m2s_result* result);
@@ -225,6 +229,10 @@ const m2s_scene* m2s_hscene_view(const m2s_hscene* scene);
 const char* m2s_hscene_primitive_name(const m2s_hscene* scene, uint32_t primitive);
 void m2s_hscene_free(m2s_hscene* scene);
 
+/* loadModel -> ConversionPass::execute -> exportPly in one call (the batch loop of
+ * guiRendererConcreteMediator.cpp:146-193): capacity = the reference rule, .ply rows encoded on the GPU and
+ * streamed to disk through two pinned buffers.  ply_format as exportPly's exportFormat (0 standard,
+ * 1 PBR, 2 compressed; anything else = 0).  M2S_E_CAPACITY: the file holds the `cap` valid records. */
 m2s_status m2s_convert_file(m2s_ctx* ctx, const char* glb_path, uint32_t resolution,
                             float gaussian_std, uint32_t ply_format, const char* ply_path,
                             m2s_result* result);
