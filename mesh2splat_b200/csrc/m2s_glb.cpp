@@ -255,7 +255,8 @@ std::vector<uint8_t> inflate_zlib(const uint8_t* src, size_t n, size_t expected)
     return out;
 }
 
-// ---- PNG (8-bit, non-interlaced; gray / gray+alpha / rgb / rgba / palette [+tRNS]) -> RGBA8 -------
+// ---- PNG (every colour type and bit depth, Adam7 interlace, tRNS) -> RGBA8.  16-bit samples keep their high
+// byte; sub-byte gray is scaled to 0..255 (as stb_image, tinygltf's decoder, does) --------------------------
 struct Image { uint32_t w = 0, h = 0; std::vector<uint8_t> rgba; };
 uint32_t be32(const uint8_t* p) { return (uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3]; }
 
@@ -281,45 +282,88 @@ Image decode_png(const uint8_t* d, size_t n) {
         pos += 12 + (size_t)len;
     }
     if (!w || !h || w > 32768 || h > 32768) throw FormatError("png: bad dimensions");
-    if (depth != 8) throw FormatError("png: only 8-bit channels are supported");
-    if (interlace) throw FormatError("png: interlaced images are not supported");
     int ch;
     switch (ctype) { case 0: ch = 1; break; case 2: ch = 3; break; case 3: ch = 1; break; case 4: ch = 2; break; case 6: ch = 4; break;
                      default: throw FormatError("png: bad colour type"); }
-    const size_t stride = (size_t)w * ch;
-    std::vector<uint8_t> raw = inflate_zlib(idat.data(), idat.size(), (stride + 1) * h);
-    if (raw.size() < (stride + 1) * h) throw FormatError("png: not enough pixel data");
-    std::vector<uint8_t> img(stride * h);
-    std::vector<uint8_t> zero(stride, 0);
-    for (uint32_t y = 0; y < h; ++y) {
-        const uint8_t ft = raw[(stride + 1) * y];
-        const uint8_t* in = raw.data() + (stride + 1) * y + 1;
-        uint8_t* cur = img.data() + stride * y;
-        const uint8_t* up = y ? img.data() + stride * (y - 1) : zero.data();
-        for (size_t i = 0; i < stride; ++i) {
-            const int a = i >= (size_t)ch ? cur[i - ch] : 0, b = up[i], c = i >= (size_t)ch ? up[i - ch] : 0;
-            int pred = 0;
-            switch (ft) {
-                case 0: pred = 0; break; case 1: pred = a; break; case 2: pred = b; break; case 3: pred = (a + b) >> 1; break;
-                case 4: { const int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c);
-                          pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); break; }
-                default: throw FormatError("png: bad filter");
-            }
-            cur[i] = (uint8_t)(in[i] + pred);
-        }
+    const bool depth_ok = (ctype == 0 && (depth == 1 || depth == 2 || depth == 4 || depth == 8 || depth == 16)) ||
+                          (ctype == 3 && (depth == 1 || depth == 2 || depth == 4 || depth == 8)) ||
+                          ((ctype == 2 || ctype == 4 || ctype == 6) && (depth == 8 || depth == 16));
+    if (!depth_ok) throw FormatError("png: bad bit depth for the colour type");
+    if (interlace > 1) throw FormatError("png: bad interlace method");
+    const int bpp = ch * depth;                       // bits per pixel
+    const size_t fb = bpp >= 8 ? (size_t)bpp / 8 : 1;  // filter distance in bytes
+    auto row_bytes = [&](uint32_t pw) { return ((size_t)pw * bpp + 7) / 8; };
+    // the passes: one for a plain image, seven for Adam7 (x0, y0, dx, dy)
+    static const int adam7[7][4] = {{0, 0, 8, 8}, {4, 0, 8, 8}, {0, 4, 4, 8}, {2, 0, 4, 4}, {0, 2, 2, 4}, {1, 0, 2, 2}, {0, 1, 1, 2}};
+    static const int plain[1][4] = {{0, 0, 1, 1}};
+    const int (*passes)[4] = interlace ? adam7 : plain;
+    const int npass = interlace ? 7 : 1;
+    size_t expect = 0;
+    for (int k = 0; k < npass; ++k) {
+        const uint32_t x0 = passes[k][0], y0 = passes[k][1], dx = passes[k][2], dy = passes[k][3];
+        if (x0 >= w || y0 >= h) continue;
+        const uint32_t pw = (w - x0 + dx - 1) / dx, ph = (h - y0 + dy - 1) / dy;
+        expect += (row_bytes(pw) + 1) * ph;
     }
+    std::vector<uint8_t> raw = inflate_zlib(idat.data(), idat.size(), expect);
+    if (raw.size() < expect) throw FormatError("png: not enough pixel data");
     Image out; out.w = w; out.h = h; out.rgba.resize((size_t)w * h * 4);
-    for (size_t i = 0; i < (size_t)w * h; ++i) {
-        uint8_t* o = &out.rgba[i * 4];
-        const uint8_t* s = &img[i * ch];
-        switch (ctype) {
-            case 0: o[0] = o[1] = o[2] = s[0]; o[3] = (have_trns && trns.size() >= 2 && trns[1] == s[0]) ? 0 : 255; break;
-            case 2: o[0] = s[0]; o[1] = s[1]; o[2] = s[2];
-                    o[3] = (have_trns && trns.size() >= 6 && trns[1] == s[0] && trns[3] == s[1] && trns[5] == s[2]) ? 0 : 255; break;
-            case 3: { const size_t k = s[0]; if (k * 3 + 2 >= plte.size()) throw FormatError("png: palette index");
-                      o[0] = plte[k * 3]; o[1] = plte[k * 3 + 1]; o[2] = plte[k * 3 + 2]; o[3] = k < trns.size() ? trns[k] : 255; break; }
-            case 4: o[0] = o[1] = o[2] = s[0]; o[3] = s[1]; break;
-            case 6: o[0] = s[0]; o[1] = s[1]; o[2] = s[2]; o[3] = s[3]; break;
+    // sample k of an unfiltered row -> 8 bits: 16-bit samples keep their high byte, sub-byte GRAY samples are
+    // scaled to 0..255 (x255, x85, x17) as stb_image does; palette indices stay indices
+    const int gray_scale = (ctype == 0 && depth < 8) ? 255 / ((1 << depth) - 1) : 1;
+    auto sample = [&](const uint8_t* row, size_t k) -> uint32_t {
+        if (depth == 8) return row[k];
+        if (depth == 16) return row[2 * k];
+        const size_t bit = k * depth;
+        return (uint32_t)(row[bit >> 3] >> (8 - depth - (bit & 7))) & ((1u << depth) - 1u);
+    };
+    // colour key (tRNS of gray / rgb images): compared on the stored sample (16-bit: both bytes)
+    auto sample16 = [&](const uint8_t* row, size_t k) -> uint32_t {
+        return depth == 16 ? ((uint32_t)row[2 * k] << 8 | row[2 * k + 1]) : sample(row, k);
+    };
+    auto key16 = [&](size_t i) -> uint32_t { return (uint32_t)trns[2 * i] << 8 | trns[2 * i + 1]; };
+    size_t rp = 0;
+    std::vector<uint8_t> cur, prev;
+    for (int k = 0; k < npass; ++k) {
+        const uint32_t x0 = passes[k][0], y0 = passes[k][1], dx = passes[k][2], dy = passes[k][3];
+        if (x0 >= w || y0 >= h) continue;
+        const uint32_t pw = (w - x0 + dx - 1) / dx, ph = (h - y0 + dy - 1) / dy;
+        const size_t rb = row_bytes(pw);
+        cur.assign(rb, 0); prev.assign(rb, 0);
+        for (uint32_t y = 0; y < ph; ++y) {
+            const uint8_t ft = raw[rp];
+            const uint8_t* in = raw.data() + rp + 1;
+            rp += rb + 1;
+            for (size_t i = 0; i < rb; ++i) {
+                const int a = i >= fb ? cur[i - fb] : 0, b = prev[i], c = i >= fb ? prev[i - fb] : 0;
+                int pred = 0;
+                switch (ft) {
+                    case 0: pred = 0; break; case 1: pred = a; break; case 2: pred = b; break; case 3: pred = (a + b) >> 1; break;
+                    case 4: { const int pp = a + b - c, pa = std::abs(pp - a), pb = std::abs(pp - b), pc = std::abs(pp - c);
+                              pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); break; }
+                    default: throw FormatError("png: bad filter");
+                }
+                cur[i] = (uint8_t)(in[i] + pred);
+            }
+            uint8_t* orow = &out.rgba[((size_t)(y0 + y * dy) * w) * 4];
+            for (uint32_t x = 0; x < pw; ++x) {
+                uint8_t* o = orow + (size_t)(x0 + x * dx) * 4;
+                const size_t s0 = (size_t)x * ch;
+                switch (ctype) {
+                    case 0: { const uint32_t v = sample(cur.data(), s0);
+                              o[0] = o[1] = o[2] = (uint8_t)(v * gray_scale);
+                              o[3] = (have_trns && trns.size() >= 2 && key16(0) == sample16(cur.data(), s0)) ? 0 : 255; break; }
+                    case 2: o[0] = (uint8_t)sample(cur.data(), s0); o[1] = (uint8_t)sample(cur.data(), s0 + 1); o[2] = (uint8_t)sample(cur.data(), s0 + 2);
+                            o[3] = (have_trns && trns.size() >= 6 && key16(0) == sample16(cur.data(), s0) && key16(1) == sample16(cur.data(), s0 + 1) &&
+                                    key16(2) == sample16(cur.data(), s0 + 2)) ? 0 : 255; break;
+                    case 3: { const size_t idx = sample(cur.data(), s0); if (idx * 3 + 2 >= plte.size()) throw FormatError("png: palette index");
+                              o[0] = plte[idx * 3]; o[1] = plte[idx * 3 + 1]; o[2] = plte[idx * 3 + 2]; o[3] = idx < trns.size() ? trns[idx] : 255; break; }
+                    case 4: o[0] = o[1] = o[2] = (uint8_t)sample(cur.data(), s0); o[3] = (uint8_t)sample(cur.data(), s0 + 1); break;
+                    case 6: o[0] = (uint8_t)sample(cur.data(), s0); o[1] = (uint8_t)sample(cur.data(), s0 + 1); o[2] = (uint8_t)sample(cur.data(), s0 + 2);
+                            o[3] = (uint8_t)sample(cur.data(), s0 + 3); break;
+                }
+            }
+            std::swap(cur, prev);
         }
     }
     return out;

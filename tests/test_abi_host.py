@@ -295,6 +295,60 @@ def test_glb_loader_decodes_baseline_jpeg(tmp_path, mode, subsampling, size):
         assert d.mean() < 1.0 and d.max() <= 6, (d.mean(), d.max())
 
 
+_PNG_CASES = [(0, 1), (0, 2), (0, 4), (0, 8), (0, 16), (2, 8), (2, 16), (3, 1), (3, 2), (3, 4), (3, 8), (4, 8), (4, 16), (6, 8), (6, 16)]
+
+
+@pytest.mark.parametrize("interlace", [False, True])
+@pytest.mark.parametrize("ctype,depth", _PNG_CASES)
+def test_glb_loader_decodes_every_png_type(tmp_path, ctype, depth, interlace):
+    """Every PNG colour type / bit depth, plain and Adam7, all five filters, tRNS (palette alpha and colour key):
+    the expected RGBA8 is computed from the source samples (16-bit -> high byte; sub-byte gray scaled to 0..255,
+    as stb_image — tinygltf's decoder in the reference — does)."""
+    from mesh2splat_b200.gltf import load_glb
+    from util import png_encode
+    rng = np.random.default_rng(ctype * 100 + depth)
+    w, h = 13, 11                        # not multiples of 8: exercises partial bytes and short Adam7 passes
+    ch = {0: 1, 2: 3, 3: 1, 4: 2, 6: 4}[ctype]
+    smp = rng.integers(0, 1 << depth, size=(h, w, ch), dtype=np.int64)
+    plte = trns = None
+    to8 = (lambda v: v >> 8) if depth == 16 else (lambda v: v)
+    want = np.zeros((h, w, 4), np.int64)
+    if ctype == 3:
+        n = 1 << depth
+        pal = rng.integers(0, 256, size=(n, 3), dtype=np.int64)
+        alpha = rng.integers(0, 256, size=(max(1, n // 2),), dtype=np.int64)   # tRNS shorter than the palette: rest opaque
+        plte, trns = pal.astype(np.uint8).tobytes(), alpha.astype(np.uint8).tobytes()
+        idx = smp[..., 0]
+        want[..., :3] = pal[idx]
+        want[..., 3] = np.where(idx < len(alpha), alpha[np.minimum(idx, len(alpha) - 1)], 255)
+    elif ctype == 0:
+        key = int(smp[2, 3, 0])
+        trns = int(key).to_bytes(2, "big")
+        scale = 255 // ((1 << depth) - 1) if depth < 8 else 1
+        want[..., :3] = (to8(smp[..., :1]) * scale)
+        want[..., 3] = np.where(smp[..., 0] == key, 0, 255)
+    elif ctype == 2:
+        key = smp[4, 5]
+        trns = b"".join(int(v).to_bytes(2, "big") for v in key)
+        want[..., :3] = to8(smp)
+        want[..., 3] = np.where(np.all(smp == key, axis=-1), 0, 255)
+    elif ctype == 4:
+        want[..., :3] = to8(smp[..., :1]); want[..., 3] = to8(smp[..., 1])
+    else:
+        want[...] = to8(smp)
+    blob = png_encode(smp, ctype, depth, interlace, plte, trns)
+    p = tmp_path / "p.glb"
+    _glb_with_image(str(p), blob, "image/png")
+    got = load_glb(str(p)).textures[0]
+    assert got.shape == (h, w, 4)
+    assert np.array_equal(got.astype(np.int64), want)
+    if ctype in (0, 2, 6) and depth == 8 or ctype == 3:     # cross-check the test's own encoder against Pillow
+        import io
+        from PIL import Image
+        pil = np.asarray(Image.open(io.BytesIO(blob)).convert("RGBA")).astype(np.int64)
+        assert np.array_equal(pil, want)
+
+
 def test_glb_loader_rejects_progressive_jpeg(tmp_path):
     import io
     from PIL import Image

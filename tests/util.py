@@ -137,3 +137,70 @@ def planar_triangulation(n_points: int, seed: int) -> _abi.Scene:
     s = _abi.Scene(v.reshape(len(tri), 36), [_abi.Primitive(0, len(tri), (1, 1, 1, 1), -1, -1, -1)], [])
     s.compute_bboxes()
     return s
+
+
+def png_encode(samples: np.ndarray, ctype: int, depth: int, interlace: bool = False, plte: bytes | None = None,
+               trns: bytes | None = None) -> bytes:
+    """General PNG writer for loader tests.  samples: (h, w, channels) integers < 2**depth (channels: 1 gray/palette,
+    2 gray+alpha, 3 rgb, 4 rgba).  Rows cycle through the five filter types; Adam7 when interlace."""
+    import struct
+    import zlib
+    smp = np.asarray(samples)
+    h, w, ch = smp.shape
+    assert ch == {0: 1, 2: 3, 3: 1, 4: 2, 6: 4}[ctype]
+
+    def pack_row(row):  # (pw, ch) -> bytes
+        flat = row.reshape(-1).astype(np.uint32)
+        if depth == 8:
+            return flat.astype(np.uint8).tobytes()
+        if depth == 16:
+            return flat.astype(">u2").tobytes()
+        bits = np.zeros(len(flat) * depth, np.uint8)
+        for b in range(depth):
+            bits[b::depth] = (flat >> (depth - 1 - b)) & 1
+        return np.packbits(bits).tobytes()
+
+    fb = max(1, ch * depth // 8)
+
+    def filt(rows):  # list of bytes -> filtered stream
+        out = bytearray()
+        prev = bytes(len(rows[0])) if rows else b""
+        for y, r in enumerate(rows):
+            ft = y % 5
+            cur = bytearray(len(r))
+            for i in range(len(r)):
+                a = r[i - fb] if i >= fb else 0
+                b = prev[i]
+                c = prev[i - fb] if i >= fb else 0
+                if ft == 0: pred = 0
+                elif ft == 1: pred = a
+                elif ft == 2: pred = b
+                elif ft == 3: pred = (a + b) >> 1
+                else:
+                    pp = a + b - c
+                    pa, pb, pc = abs(pp - a), abs(pp - b), abs(pp - c)
+                    pred = a if (pa <= pb and pa <= pc) else (b if pb <= pc else c)
+                cur[i] = (r[i] - pred) & 0xff
+            out.append(ft); out += cur
+            prev = r
+        return bytes(out)
+
+    passes = [(0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2)] if interlace else [(0, 0, 1, 1)]
+    raw = b""
+    for x0, y0, dx, dy in passes:
+        sub = smp[y0::dy, x0::dx]
+        if sub.shape[0] == 0 or sub.shape[1] == 0:
+            continue
+        raw += filt([pack_row(sub[y]) for y in range(sub.shape[0])])
+
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xffffffff)
+
+    out = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, 1 if interlace else 0))
+    if plte is not None:
+        out += chunk(b"PLTE", plte)
+    if trns is not None:
+        out += chunk(b"tRNS", trns)
+    half = len(raw) // 2 or 1
+    z = zlib.compress(raw, 6)
+    return out + chunk(b"IDAT", z[:half]) + chunk(b"IDAT", z[half:]) + chunk(b"IEND", b"")
