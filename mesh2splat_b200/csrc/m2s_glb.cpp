@@ -14,8 +14,8 @@
 //   setupMeshBuffers  :468-576  per-primitive bbox = running union over primitives 0..k
 //   loadTextures + glUtils::generateTextures: RGBA8 images (tinygltf forces 4 channels,
 //                               thirdParty/tiny_gltf.h:2609)
-// No third-party code: own GLB/JSON reader, own inflate + PNG decoder, own baseline-JPEG decoder
-// (progressive JPEG is rejected with M2S_E_FORMAT).
+// No third-party code: own GLB/JSON reader, own inflate + PNG decoder (every colour type / depth, Adam7), own
+// JPEG decoder (baseline + progressive Huffman; arithmetic / lossless / 12-bit are rejected with M2S_E_FORMAT).
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -370,14 +370,16 @@ Image decode_png(const uint8_t* d, size_t n) {
 }
 
 
-// ---- JPEG (baseline sequential DCT, 8-bit, Huffman; 1 or 3 components, any sampling up to 2x2, restart
-// intervals) -> RGBA8.  Progressive / arithmetic / 12-bit files are rejected (M2S_E_FORMAT).  IDCT: separable
+// ---- JPEG (baseline, extended-sequential and PROGRESSIVE DCT, 8-bit, Huffman; 1 or 3 components, any sampling
+// up to 2x2, restart intervals, interleaved and per-component scans) -> RGBA8.  Arithmetic / lossless / 12-bit
+// files are rejected (M2S_E_FORMAT).  IDCT: separable
 // float reference form (exact to the DCT definition, rounded once); chroma upsampling: the 3:1 triangle
 // filter stb_image (tinygltf's decoder) and libjpeg use.  Decoders differ by +-1..2 code values in rounding,
 // inside the 2/255 colour tolerance the path states.
 struct JpegDecoder {
     const uint8_t* p; const uint8_t* end;
-    struct Comp { int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0, dcpred = 0; std::vector<uint8_t> plane; int pw = 0, ph = 0; };
+    struct Comp { int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0, dcpred = 0; std::vector<uint8_t> plane; int pw = 0, ph = 0;
+                  int bw = 0, bh = 0, vbw = 0, vbh = 0; std::vector<short> coef; };  // coefficients in NATURAL order
     uint16_t qt[4][64]; bool have_qt[4] = {false, false, false, false};
     struct HT { uint8_t bits[17]; uint8_t vals[256]; int mincode[17], maxcode[18], valptr[17]; bool ok = false; } dc[4], ac[4];
     std::vector<Comp> comps; int W = 0, H = 0, restart = 0;
@@ -426,11 +428,11 @@ struct JpegDecoder {
         throw FormatError("jpeg: bad huffman code");
     }
     static int extend(int v, int n) { return (n && v < (1 << (n - 1))) ? v - (1 << n) + 1 : v; }
-    void idct_store(const int* blk, const uint16_t* q, uint8_t* dst, int stride) {
+    void idct_store(const short* blk, const uint16_t* q, uint8_t* dst, int stride) {
         static float C[8][8]; static bool init = false;
         if (!init) { for (int x = 0; x < 8; ++x) for (int u = 0; u < 8; ++u) C[x][u] = (u ? 1.0f : 0.70710678f) * 0.5f * std::cos((2 * x + 1) * u * 3.14159265358979f / 16.0f); init = true; }
         float f[64], t[64];
-        for (int i = 0; i < 64; ++i) f[zz[i]] = (float)(blk[i] * (int)q[i]);
+        for (int i = 0; i < 64; ++i) f[zz[i]] = (float)((int)blk[zz[i]] * (int)q[i]);  // DQT is stored in zig-zag order
         for (int y = 0; y < 8; ++y) for (int x = 0; x < 8; ++x) { float s = 0; for (int u = 0; u < 8; ++u) s += C[x][u] * f[y * 8 + u]; t[y * 8 + x] = s; }
         for (int x = 0; x < 8; ++x) for (int y = 0; y < 8; ++y) {
             float s = 0; for (int v = 0; v < 8; ++v) s += C[y][v] * t[v * 8 + x];
@@ -438,15 +440,124 @@ struct JpegDecoder {
             dst[y * stride + x] = (uint8_t)(o < 0 ? 0 : (o > 255 ? 255 : o));
         }
     }
+    // ---- entropy decoding into coefficient arrays (all scans), then dequantise + IDCT ----------------
+    bool progressive = false;
+    int hmax = 1, vmax = 1, mx = 0, my = 0;
+    int eobrun = 0;
+    void frame_setup() {
+        hmax = vmax = 1;
+        for (auto& c : comps) { hmax = std::max(hmax, c.h); vmax = std::max(vmax, c.v); }
+        const int mcuw = 8 * hmax, mcuh = 8 * vmax;
+        mx = (W + mcuw - 1) / mcuw; my = (H + mcuh - 1) / mcuh;
+        for (auto& c : comps) {
+            c.bw = mx * c.h; c.bh = my * c.v;                      // blocks incl. MCU padding
+            c.vbw = ((W * c.h + hmax - 1) / hmax + 7) / 8;          // blocks a non-interleaved scan visits
+            c.vbh = ((H * c.v + vmax - 1) / vmax + 7) / 8;
+            c.pw = c.bw * 8; c.ph = c.bh * 8;
+            c.coef.assign((size_t)c.bw * c.bh * 64, 0);
+        }
+    }
+    void restart_point() {  // RSTn: byte-align, skip the marker, reset predictors and the EOB run
+        bitcnt = 0; hit_marker = false;
+        while (p + 1 < end && !(p[0] == 0xff && p[1] >= 0xd0 && p[1] <= 0xd7)) {
+            if (p[0] == 0xff && p[1] != 0 && p[1] != 0xff) { hit_marker = true; return; }  // some other marker: scan is over
+            ++p;
+        }
+        if (p + 1 < end) p += 2;
+        for (auto& c : comps) c.dcpred = 0;
+        eobrun = 0;
+    }
+    // one 8x8 block of one scan (T.81 F.2.2 sequential, G.1.2 progressive); coefficients in natural order
+    void decode_block(Comp& c, short* blk, int Ss, int Se, int Ah, int Al) {
+        if (!progressive) {
+            const int t = decode(dc[c.td]);
+            c.dcpred += extend(getbits(t), t);
+            blk[0] = (short)c.dcpred;
+            for (int k = 1; k < 64;) {
+                const int rs = decode(ac[c.ta]); const int r = rs >> 4, sz = rs & 15;
+                if (!sz) { if (r == 15) { k += 16; continue; } break; }
+                k += r; if (k > 63) throw FormatError("jpeg: bad AC run");
+                blk[zz[k++]] = (short)extend(getbits(sz), sz);
+            }
+            return;
+        }
+        if (Ss == 0) {  // DC scan
+            if (Ah == 0) { const int t = decode(dc[c.td]); c.dcpred += extend(getbits(t), t); blk[0] = (short)(c.dcpred * (1 << Al)); }
+            else if (getbit()) blk[0] = (short)(blk[0] | (1 << Al));
+            return;
+        }
+        const int p1 = 1 << Al, m1 = -(1 << Al);
+        if (Ah == 0) {  // AC, first pass of this band
+            if (eobrun > 0) { --eobrun; return; }
+            for (int k = Ss; k <= Se;) {
+                const int rs = decode(ac[c.ta]); const int r = rs >> 4, sz = rs & 15;
+                if (sz == 0) {
+                    if (r < 15) { eobrun = (1 << r) - 1; if (r) eobrun += getbits(r); break; }
+                    k += 16;
+                } else {
+                    k += r; if (k > Se) throw FormatError("jpeg: bad AC run");
+                    blk[zz[k++]] = (short)(extend(getbits(sz), sz) * p1);
+                }
+            }
+            return;
+        }
+        // AC refinement: one more bit for the coefficients already non-zero, new +-1 coefficients in between
+        auto refine = [&](short& v) { if (getbit() && (v & p1) == 0) v = (short)(v + (v >= 0 ? p1 : m1)); };
+        int k = Ss;
+        if (eobrun == 0) {
+            for (; k <= Se; ++k) {
+                const int rs = decode(ac[c.ta]); int r = rs >> 4; const int sz = rs & 15;
+                int val = 0;
+                if (sz) { if (sz != 1) throw FormatError("jpeg: bad refinement code"); val = getbit() ? p1 : m1; }
+                else if (r != 15) { eobrun = 1 << r; if (r) eobrun += getbits(r); break; }
+                // skip r still-zero coefficients, refining the non-zero ones passed on the way
+                for (; k <= Se; ++k) {
+                    short& v = blk[zz[k]];
+                    if (v != 0) refine(v);
+                    else if (--r < 0) break;
+                }
+                if (val && k <= Se) blk[zz[k]] = (short)val;
+            }
+        }
+        if (eobrun > 0) {
+            for (; k <= Se; ++k) { short& v = blk[zz[k]]; if (v != 0) refine(v); }
+            --eobrun;
+        }
+    }
+    void decode_scan(const std::vector<int>& sc, int Ss, int Se, int Ah, int Al) {
+        bitcnt = 0; hit_marker = false; eobrun = 0;
+        for (auto& c : comps) c.dcpred = 0;
+        int rst_left = restart;
+        auto tick = [&]() { if (restart && --rst_left == 0) { restart_point(); rst_left = restart; } };
+        if (sc.size() == 1) {  // non-interleaved: the component's own block grid
+            Comp& c = comps[sc[0]];
+            const int nb = c.vbw * c.vbh;
+            for (int i = 0; i < nb; ++i) {
+                const int bx = i % c.vbw, by = i / c.vbw;
+                decode_block(c, &c.coef[((size_t)by * c.bw + bx) * 64], Ss, Se, Ah, Al);
+                if (i + 1 < nb) tick();
+            }
+        } else {
+            for (int y = 0; y < my; ++y) for (int x = 0; x < mx; ++x) {
+                for (int ci : sc) { Comp& c = comps[ci];
+                    for (int by = 0; by < c.v; ++by) for (int bx = 0; bx < c.h; ++bx)
+                        decode_block(c, &c.coef[((size_t)(y * c.v + by) * c.bw + (x * c.h + bx)) * 64], Ss, Se, Ah, Al);
+                }
+                if (!(y == my - 1 && x == mx - 1)) tick();
+            }
+        }
+        // the scan's entropy-coded segment ends at the next marker that is not RSTn / stuffed 0xFF00
+        while (p + 1 < end && !(p[0] == 0xff && p[1] != 0 && p[1] != 0xff && !(p[1] >= 0xd0 && p[1] <= 0xd7))) ++p;
+    }
     Image run() {
         if (u16() != 0xffd8) throw FormatError("jpeg: no SOI");
-        bool sos_done = false;
-        while (!sos_done) {
+        bool eoi = false, have_scan = false;
+        while (!eoi && p < end) {
             int m = u8();
             if (m != 0xff) continue;
             while ((m = u8()) == 0xff) {}
-            if (m == 0xd8 || m == 0x01 || (m >= 0xd0 && m <= 0xd7)) continue;
-            if (m == 0xd9) throw FormatError("jpeg: no image data");
+            if (m == 0xd8 || m == 0x01 || m == 0x00 || (m >= 0xd0 && m <= 0xd7)) continue;
+            if (m == 0xd9) { eoi = true; break; }
             const int len = u16();
             const uint8_t* seg_end = p + len - 2;
             if (len < 2 || seg_end > end) throw FormatError("jpeg: bad segment length");
@@ -462,53 +573,53 @@ struct JpegDecoder {
                     for (int i = 0; i < n; ++i) t.vals[i] = (uint8_t)u8();
                     build(t);
                 }
-            } else if (m == 0xc0 || m == 0xc1) {
+            } else if (m == 0xc0 || m == 0xc1 || m == 0xc2) {
+                if (!comps.empty()) throw FormatError("jpeg: more than one frame");
+                progressive = m == 0xc2;
                 if (u8() != 8) throw FormatError("jpeg: only 8-bit samples are supported");
                 H = u16(); W = u16();
                 const int nc = u8();
                 if (!W || !H || W > 32768 || H > 32768 || (nc != 1 && nc != 3)) throw FormatError("jpeg: unsupported frame");
                 comps.resize(nc);
                 for (auto& c : comps) { c.id = u8(); const int hv = u8(); c.h = hv >> 4; c.v = hv & 15; c.tq = u8(); if (c.h < 1 || c.h > 2 || c.v < 1 || c.v > 2 || c.tq > 3) throw FormatError("jpeg: unsupported sampling"); }
-            } else if (m == 0xc2 || (m >= 0xc3 && m <= 0xcf && m != 0xc4 && m != 0xc8 && m != 0xcc)) {
-                throw FormatError("jpeg: progressive / lossless / arithmetic JPEG is not supported");
+                if (nc == 1) { comps[0].h = comps[0].v = 1; }  // a single component is never sub-sampled (T.81 A.2.2)
+                frame_setup();
+            } else if (m >= 0xc3 && m <= 0xcf && m != 0xc4 && m != 0xc8 && m != 0xcc) {
+                throw FormatError("jpeg: lossless / hierarchical / arithmetic JPEG is not supported");
             } else if (m == 0xdd) { restart = u16(); }
             else if (m == 0xda) {
                 const int ns = u8();
-                if (comps.empty() || ns != (int)comps.size()) throw FormatError("jpeg: unsupported scan");
-                for (int i = 0; i < ns; ++i) { const int id = u8(); const int t = u8(); bool f = false; for (auto& c : comps) if (c.id == id) { c.td = t >> 4; c.ta = t & 15; f = true; } if (!f) throw FormatError("jpeg: bad scan component"); }
-                p += 3;
-                sos_done = true;
+                if (comps.empty() || ns < 1 || ns > (int)comps.size()) throw FormatError("jpeg: unsupported scan");
+                std::vector<int> sc;
+                for (int i = 0; i < ns; ++i) {
+                    const int id = u8(); const int t = u8(); int found = -1;
+                    for (size_t ci = 0; ci < comps.size(); ++ci) if (comps[ci].id == id) found = (int)ci;
+                    if (found < 0) throw FormatError("jpeg: bad scan component");
+                    comps[found].td = t >> 4; comps[found].ta = t & 15; sc.push_back(found);
+                }
+                const int Ss = u8(), Se = u8(), AhAl = u8();
+                const int Ah = AhAl >> 4, Al = AhAl & 15;
+                if (progressive) {
+                    if (Ss > Se || Se > 63 || (Ss == 0 && Se != 0) || (Ss != 0 && ns != 1) || Al > 13) throw FormatError("jpeg: bad progressive scan");
+                } else if (ns != (int)comps.size() && comps.size() != 1 && ns != 1) throw FormatError("jpeg: unsupported scan");
+                for (int ci : sc) {
+                    const Comp& c = comps[ci];
+                    if ((!progressive || Ss == 0) && !(progressive && Ah) && !dc[c.td].ok) throw FormatError("jpeg: missing DC table");
+                    if ((!progressive || Ss != 0) && !ac[c.ta].ok) throw FormatError("jpeg: missing AC table");
+                }
+                p = seg_end;
+                decode_scan(sc, progressive ? Ss : 0, progressive ? Se : 63, progressive ? Ah : 0, progressive ? Al : 0);
+                have_scan = true;
                 continue;
             }
             p = seg_end;
         }
-        int hmax = 1, vmax = 1;
-        for (auto& c : comps) { hmax = std::max(hmax, c.h); vmax = std::max(vmax, c.v); if (!have_qt[c.tq] || !dc[c.td].ok || !ac[c.ta].ok) throw FormatError("jpeg: missing table"); }
-        const int mcuw = 8 * hmax, mcuh = 8 * vmax, mx = (W + mcuw - 1) / mcuw, my = (H + mcuh - 1) / mcuh;
-        for (auto& c : comps) { c.pw = mx * c.h * 8; c.ph = my * c.v * 8; c.plane.assign((size_t)c.pw * c.ph, 0); }
-        int rst_left = restart;
-        for (int y = 0; y < my; ++y) for (int x = 0; x < mx; ++x) {
-            if (restart && rst_left == 0) {  // RSTn: byte-align, skip the marker, reset predictors
-                bitcnt = 0; hit_marker = false;
-                while (p + 1 < end && !(p[0] == 0xff && p[1] >= 0xd0 && p[1] <= 0xd7)) ++p;
-                if (p + 1 < end) p += 2;
-                for (auto& c : comps) c.dcpred = 0;
-                rst_left = restart;
-            }
-            for (auto& c : comps) for (int by = 0; by < c.v; ++by) for (int bx = 0; bx < c.h; ++bx) {
-                int blk[64] = {0};
-                const int t = decode(dc[c.td]);
-                c.dcpred += extend(getbits(t), t);
-                blk[0] = c.dcpred;
-                for (int k = 1; k < 64;) {
-                    const int rs = decode(ac[c.ta]); const int r = rs >> 4, sz = rs & 15;
-                    if (!sz) { if (r == 15) { k += 16; continue; } break; }
-                    k += r; if (k > 63) throw FormatError("jpeg: bad AC run");
-                    blk[k++] = extend(getbits(sz), sz);
-                }
-                idct_store(blk, qt[c.tq], c.plane.data() + ((size_t)(y * c.v + by) * 8) * c.pw + (size_t)(x * c.h + bx) * 8, c.pw);
-            }
-            if (restart) --rst_left;
+        if (comps.empty() || !have_scan) throw FormatError("jpeg: no image data");
+        for (auto& c : comps) {
+            if (!have_qt[c.tq]) throw FormatError("jpeg: missing quantisation table");
+            c.plane.assign((size_t)c.pw * c.ph, 0);
+            for (int by = 0; by < c.bh; ++by) for (int bx = 0; bx < c.bw; ++bx)
+                idct_store(&c.coef[((size_t)by * c.bw + bx) * 64], qt[c.tq], c.plane.data() + ((size_t)by * 8) * c.pw + (size_t)bx * 8, c.pw);
         }
         // full-resolution sample of a (possibly 2x sub-sampled) component: 3:1 triangle filter along each
         // sub-sampled axis, the "fancy upsampling" both stb_image (tinygltf's decoder) and libjpeg use

@@ -349,13 +349,55 @@ def test_glb_loader_decodes_every_png_type(tmp_path, ctype, depth, interlace):
         assert np.array_equal(pil, want)
 
 
-def test_glb_loader_rejects_progressive_jpeg(tmp_path):
+@pytest.mark.parametrize("mode,subsampling,size,restart", [("RGB", 0, (64, 48), 0), ("RGB", 2, (70, 37), 0), ("RGB", 1, (33, 65), 0),
+                                                          ("L", 0, (40, 24), 0), ("RGB", 2, (129, 95), 3), ("RGB", 0, (17, 9), 0)])
+@pytest.mark.parametrize("quality", [35, 92])
+def test_glb_loader_decodes_progressive_jpeg(tmp_path, mode, subsampling, size, restart, quality):
+    """Progressive JPEG (spectral selection + successive approximation, per-component AC scans, EOB runs,
+    refinement passes; stb_image — the reference's decoder — reads these too): same bounds vs Pillow/libjpeg
+    as the baseline decoder, and bit-identical to OUR decoding of the same picture saved as baseline when the
+    coefficients are the same (libjpeg quantises before choosing the scan script)."""
+    import io
+    from PIL import Image
+    from mesh2splat_b200.gltf import load_glb
+    w, h = size
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    rng = np.random.default_rng(w * h)
+    img = np.stack([128 + 100 * np.sin(xx / 9.0), 128 + 100 * np.cos(yy / 7.0), 128 + 60 * np.sin((xx + yy) / 11.0)], axis=-1)
+    img = np.clip(img + rng.normal(0, 6, img.shape), 0, 255).astype(np.uint8)   # noise: many non-zero AC coefficients
+    pil = Image.fromarray(img if mode == "RGB" else img[..., 0], mode)
+    kw = {"quality": quality} if mode == "L" else {"quality": quality, "subsampling": subsampling}
+    if restart:
+        kw["restart_marker_rows"] = restart
+    outs = {}
+    for prog in (True, False):
+        buf = io.BytesIO()
+        pil.save(buf, "JPEG", progressive=prog, **kw)
+        if prog:
+            assert b"\xff\xc2" in buf.getvalue()
+            want = np.asarray(Image.open(io.BytesIO(buf.getvalue())).convert("RGB")).astype(np.int32)
+        p = tmp_path / f"j{int(prog)}.glb"
+        _glb_with_image(str(p), buf.getvalue(), "image/jpeg")
+        outs[prog] = load_glb(str(p)).textures[0]
+    got = outs[True]
+    assert got.shape == (h, w, 4) and np.all(got[..., 3] == 255)
+    assert np.array_equal(got, outs[False])          # same coefficients, whatever the scan script
+    d = np.abs(got[..., :3].astype(np.int32) - want)
+    if subsampling == 0 or mode == "L":   # IDCT / colour-conversion rounding only (libjpeg: integer islow; ours: float)
+        assert d.max() <= 3 and d.mean() < 0.6, (d.max(), d.mean())
+    else:                                  # + chroma upsampling differences on noisy content
+        assert d.mean() < 1.5 and d.max() <= 12, (d.mean(), d.max())
+
+
+def test_glb_loader_rejects_arithmetic_jpeg(tmp_path):
+    """Arithmetic-coded frames (SOF9..SOF11) are rejected loudly, not mis-decoded."""
     import io
     from PIL import Image
     from mesh2splat_b200.gltf import load_glb
     buf = io.BytesIO()
-    Image.fromarray(np.full((16, 16, 3), 90, np.uint8)).save(buf, "JPEG", progressive=True)
+    Image.fromarray(np.full((16, 16, 3), 90, np.uint8)).save(buf, "JPEG")
+    blob = buf.getvalue().replace(b"\xff\xc0", b"\xff\xc9", 1)
     p = tmp_path / "p.glb"
-    _glb_with_image(str(p), buf.getvalue(), "image/jpeg")
-    with pytest.raises(ValueError, match="progressive"):
+    _glb_with_image(str(p), blob, "image/jpeg")
+    with pytest.raises(ValueError, match="arithmetic"):
         load_glb(str(p))
