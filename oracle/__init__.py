@@ -88,6 +88,32 @@ def ref_lib():
     return _ref
 
 
+_refply = None
+
+
+def ref_ply_lib():
+    """The reference's own .ply writer (oracle/_ref/libm2s_refply.so), or None if it was never built."""
+    global _refply
+    if _refply is None:
+        path = os.path.join(_HERE, "_ref", "libm2s_refply.so")
+        if not os.path.exists(path):
+            return None
+        _refply = C.CDLL(path)
+        _refply.ref_save_ply.restype = C.c_int
+        _refply.ref_save_ply.argtypes = [C.c_char_p, C.c_void_p, C.c_uint64, C.c_uint, C.c_float]
+    return _refply
+
+
+def ref_save_ply(path: str, ref96: np.ndarray, fmt: int, mult: float) -> bool:
+    """parsers::savePlyVector of the reference on REF96 records; False if the library is unavailable."""
+    r = ref_ply_lib()
+    if r is None:
+        return False
+    flat = np.ascontiguousarray(ref96).view(np.float32).reshape(-1, 24)
+    r.ref_save_ply(str(path).encode(), flat.ctypes.data, len(flat), fmt, mult)
+    return True
+
+
 def max_threads() -> int:
     return int(lib().orc_max_threads())
 

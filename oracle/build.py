@@ -114,8 +114,40 @@ def build_ref(force: bool = False) -> str | None:
     return out
 
 
+_STUBS = {
+    "crtdbg.h": "/* empty stand-in: the reference includes <crtdbg.h> (MSVC debug CRT) */\n",
+    "windows.h": ("/* stand-in for <windows.h> on Linux: the .ply writer uses nothing from it */\n#pragma once\n"
+                  "typedef unsigned long DWORD; typedef char* LPSTR; typedef void* HMODULE;\n#ifndef MAX_PATH\n#define MAX_PATH 260\n#endif\n"
+                  "static inline DWORD GetModuleFileNameA(HMODULE, LPSTR buf, DWORD n) { if (n) buf[0] = 0; return 0; }\n"),
+    "compat.h": "/* forced include: MSVC lets the reference call isnan() unqualified */\n#include <cmath>\nusing std::isnan;\n",
+}
+
+
+def build_ref_ply(force: bool = False) -> str | None:
+    """The reference's own .ply writer (src/parsers/parsers.cpp + src/utils/utils.cpp, compiled where they lie)."""
+    srcs = [os.path.join(REF, "src", "parsers", "parsers.cpp"), os.path.join(REF, "src", "utils", "utils.cpp")]
+    out = os.path.join(REF_OUT, "libm2s_refply.so")
+    if not all(os.path.exists(x) for x in srcs):
+        return out if os.path.exists(out) else None
+    harness = os.path.join(HERE, "ref_ply_harness.cpp")
+    if not force and _newer(out, *srcs, harness, __file__):
+        return out
+    stubs = os.path.join(REF_OUT, "stubs")
+    os.makedirs(stubs, exist_ok=True)
+    for name, text in _STUBS.items():
+        with open(os.path.join(stubs, name), "w") as f:
+            f.write(text)
+    tp = os.path.join(REF, "thirdParty")
+    inc = ["-I", stubs, "-I", os.path.join(REF, "src"), "-I", os.path.join(REF, "src", "utils"), "-I", tp, "-I", os.path.join(tp, "glm"),
+           "-I", os.path.join(tp, "glew", "include"), "-I", os.path.join(tp, "GLFW", "include"), "-I", os.path.join(tp, "imgui"),
+           "-I", os.path.join(tp, "imgui", "backends")]
+    _run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-w", "-ffp-contract=off", "-DGLEW_NO_GLU", "-include", os.path.join(stubs, "compat.h"),
+          *inc, "-o", out, *srcs, harness, "-lstdc++fs"])
+    return out
+
+
 def build_all(force: bool = False) -> dict:
-    return {"oracle": build_oracle(force), "ref": build_ref(force)}
+    return {"oracle": build_oracle(force), "ref": build_ref(force), "ref_ply": build_ref_ply(force)}
 
 
 if __name__ == "__main__":

@@ -93,6 +93,39 @@ def main():
                         fs_varyings=vary, fs_texels=tex, fs_flags=flags, fs_factor=factor, fs_counter_start=start,
                         fs_max_gaussians=maxg, fs_rec=rec, fs_written=written, fs_counter_after=after)
     print("wrote", out, os.path.getsize(out), "bytes")
+    ply_vectors(rng)
+
+
+def ply_vectors(rng):
+    """ref_ply_vectors.npz: REF96 records -> the bytes the REFERENCE's own parsers::savePlyVector writes
+    (src/parsers/parsers.cpp + src/utils/utils.cpp compiled where they lie, oracle/_ref/libm2s_refply.so)."""
+    import tempfile
+    if oracle.ref_ply_lib() is None:
+        raise SystemExit("oracle/_ref/libm2s_refply.so is not built (no /root/reference here)")
+    n = 200
+    rec = np.zeros((n, 24), np.float32)
+    rec[:, 0:3] = rng.normal(size=(n, 3)) * 3                      # position
+    rec[:, 3] = 1.0
+    rec[:, 4:8] = rng.random((n, 4))                               # colour
+    rec[:, 8:10] = np.exp(rng.normal(size=(n, 2)) * 2 - 3); rec[:, 10] = 1e-7   # raw scale
+    nrm = rng.normal(size=(n, 3)); rec[:, 12:15] = nrm / np.linalg.norm(nrm, axis=1, keepdims=True)
+    q = rng.normal(size=(n, 4)); rec[:, 16:20] = q / np.linalg.norm(q, axis=1, keepdims=True)
+    rec[:, 20:22] = rng.random((n, 2)); rec[:, 23] = 1.0          # pbr
+    # edge cases: alpha 1 (opacity +inf) and 0, colours outside [0,1], zero scale, axis normals, unnormalised normal
+    rec[0, 7] = 1.0; rec[1, 7] = 0.0; rec[2, 4:7] = (1.5, -0.25, 0.5); rec[3, 8:10] = 0.0
+    rec[4, 12:15] = (0, 0, 1); rec[5, 12:15] = (0, 0, -1); rec[6, 12:15] = (-1, 0, 0); rec[7, 12:15] = (3.0, 0.5, -2.0)
+    rec[8, 9] = rec[8, 8]; rec[9, 20:22] = (1.7, -0.3)
+    rec = rec.astype(np.float32)
+    mult = np.float32(0.65) / np.float32(512)
+    files = {}
+    with tempfile.TemporaryDirectory() as d:
+        for fmt in (0, 1, 2, 9):
+            path = os.path.join(d, f"ref{fmt}.ply")
+            oracle.ref_save_ply(path, rec, fmt, float(mult))
+            files[f"ply_format_{fmt}"] = np.frombuffer(open(path, "rb").read(), np.uint8)
+    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_ply_vectors.npz")
+    np.savez_compressed(out, records=rec, scale_multiplier=np.float32(mult), **files)
+    print("wrote", out, os.path.getsize(out), "bytes")
 
 
 if __name__ == "__main__":

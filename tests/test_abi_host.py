@@ -119,6 +119,17 @@ def test_ply_writer_is_byte_identical_to_the_restated_savePlyVector(tmp_path, fm
     assert hdr.count("property") == {0: 62, 1: 19, 2: 18}[eff]
 
 
+@pytest.mark.parametrize("fmt", [0, 1, 2, 9])
+def test_ply_writer_matches_reference_savePlyVector_golden(tmp_path, fmt):
+    """m2s_ply_write vs the files the reference's own parsers::savePlyVector wrote (tests/golden/ref_ply_vectors.npz)."""
+    from mesh2splat_b200.api import ply_write
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_ply_vectors.npz"))
+    rec = g["records"].view(_abi.record_dtype(_abi.LAYOUT_REF96)).reshape(-1)
+    path = tmp_path / f"g{fmt}.ply"
+    ply_write(str(path), rec, fmt, float(g["scale_multiplier"]))
+    assert path.read_bytes() == g[f"ply_format_{fmt}"].tobytes()
+
+
 # ---- .glb loader ------------------------------------------------------------------------------------
 def _make_glb(path, *, indexed=True, with_normals=True, with_tangents=True, with_uv=True, with_texture=True,
               matrix=None, trs=None, two_prims=False):

@@ -196,3 +196,36 @@ def test_watertight_tiling_covers_every_pixel_exactly_once(R, n):
     assert total == R * R
     pix = keys & np.uint64(0xFFFFFF)
     assert len(np.unique(pix)) == R * R
+
+
+# ---- export arithmetic pinned to the reference's own writer ---------------------------------------------------
+def _ply_golden():
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_ply_vectors.npz"))
+
+
+@pytest.mark.parametrize("fmt", [0, 1, 2, 9])
+def test_ply_bytes_match_reference_savePlyVector_golden(fmt):
+    """tests/golden/ref_ply_vectors.npz holds the files the REFERENCE's parsers::savePlyVector wrote for 200
+    records (parsers.cpp + utils.cpp compiled from /root/reference by oracle/build.py; make_golden.py).  The
+    restatement must reproduce them byte for byte — header, field order, SH0, logit (+inf), log-scale, the
+    compressed format's octahedral normal and byte packing, and the default branch for unknown formats."""
+    g = _ply_golden()
+    rec = g["records"].view(_abi.record_dtype(LAYOUT_REF96)).reshape(-1)
+    got = oracle.ply_bytes(rec, fmt, float(g["scale_multiplier"]))
+    want = g[f"ply_format_{fmt}"].tobytes()
+    assert len(got) == len(want)
+    assert got == want
+
+
+def test_ply_bytes_match_live_reference_writer(tmp_path):
+    """Same check against the reference library itself when it is built here (fresh random records)."""
+    if oracle.ref_ply_lib() is None:
+        pytest.skip("oracle/_ref/libm2s_refply.so not built (no /root/reference on this machine)")
+    rng = np.random.default_rng(77)
+    rec = rng.random((500, 24)).astype(np.float32)
+    rec[:, 8:11] *= np.float32(0.01); rec[:50, 7] = 1.0
+    mult = float(np.float32(0.65) / np.float32(300))
+    for fmt in (0, 1, 2):
+        path = tmp_path / f"live{fmt}.ply"
+        assert oracle.ref_save_ply(str(path), rec, fmt, mult)
+        assert path.read_bytes() == oracle.ply_bytes(rec.view(_abi.record_dtype(LAYOUT_REF96)).reshape(-1), fmt, mult)
