@@ -428,16 +428,57 @@ struct JpegDecoder {
         throw FormatError("jpeg: bad huffman code");
     }
     static int extend(int v, int n) { return (n && v < (1 << (n - 1))) ? v - (1 << n) + 1 : v; }
+    // Inverse DCT in the fixed-point form stb_image v2.29 (tinygltf's decoder in the reference) uses, so that decoded
+    // texels match the reference bit for bit: the Loeffler-Ligtenberg-Moschytz factorisation with 12-bit constants;
+    // columns first (result kept with 2 extra bits: +512 >> 10), then rows (+65536 + (128 << 17)) >> 17, clamped.
+    static int fx(double v) { return (int)(v * 4096.0 + 0.5); }
+    struct Lane { int s[8]; };
+    static void lane_idct(const int* in, int stride, int out[8]) {  // one 8-point pass; outputs are sums/differences x_k +- t_k
+        const int s0 = in[0], s1 = in[stride], s2 = in[2 * stride], s3 = in[3 * stride], s4 = in[4 * stride], s5 = in[5 * stride],
+                  s6 = in[6 * stride], s7 = in[7 * stride];
+        // even part
+        const int pe = (s2 + s6) * fx(0.5411961);
+        const int e2 = pe + s6 * fx(-1.847759065), e3 = pe + s2 * fx(0.765366865);
+        const int e0 = (s0 + s4) * 4096, e1 = (s0 - s4) * 4096;
+        const int x0 = e0 + e3, x3 = e0 - e3, x1 = e1 + e2, x2 = e1 - e2;
+        // odd part
+        const int q3 = s7 + s3, q4 = s5 + s1, q1 = s7 + s1, q2 = s5 + s3;
+        const int q5 = (q3 + q4) * fx(1.175875602);
+        const int r1 = q5 + q1 * fx(-0.899976223), r2 = q5 + q2 * fx(-2.562915447);
+        const int r3 = q3 * fx(-1.961570560), r4 = q4 * fx(-0.390180644);
+        const int t3 = s1 * fx(1.501321110) + r1 + r4, t2 = s3 * fx(3.072711026) + r2 + r3;
+        const int t1 = s5 * fx(2.053119869) + r2 + r4, t0 = s7 * fx(0.298631336) + r1 + r3;
+        out[0] = x0; out[1] = x1; out[2] = x2; out[3] = x3; out[4] = t0; out[5] = t1; out[6] = t2; out[7] = t3;
+    }
     void idct_store(const short* blk, const uint16_t* q, uint8_t* dst, int stride) {
-        static float C[8][8]; static bool init = false;
-        if (!init) { for (int x = 0; x < 8; ++x) for (int u = 0; u < 8; ++u) C[x][u] = (u ? 1.0f : 0.70710678f) * 0.5f * std::cos((2 * x + 1) * u * 3.14159265358979f / 16.0f); init = true; }
-        float f[64], t[64];
-        for (int i = 0; i < 64; ++i) f[zz[i]] = (float)((int)blk[zz[i]] * (int)q[i]);  // DQT is stored in zig-zag order
-        for (int y = 0; y < 8; ++y) for (int x = 0; x < 8; ++x) { float s = 0; for (int u = 0; u < 8; ++u) s += C[x][u] * f[y * 8 + u]; t[y * 8 + x] = s; }
-        for (int x = 0; x < 8; ++x) for (int y = 0; y < 8; ++y) {
-            float s = 0; for (int v = 0; v < 8; ++v) s += C[y][v] * t[v * 8 + x];
-            const int o = (int)std::lrintf(s + 128.0f);
-            dst[y * stride + x] = (uint8_t)(o < 0 ? 0 : (o > 255 ? 255 : o));
+        int d[64], v[64];
+        for (int i = 0; i < 64; ++i) d[zz[i]] = (int)(short)((int)blk[zz[i]] * (int)q[i]);  // DQT is stored in zig-zag order; 16-bit product
+        for (int c = 0; c < 8; ++c) {  // columns
+            const int* col = d + c;
+            if (!(col[8] | col[16] | col[24] | col[32] | col[40] | col[48] | col[56])) {
+                const int dc = col[0] * 4;
+                for (int r = 0; r < 8; ++r) v[r * 8 + c] = dc;
+                continue;
+            }
+            int o[8];
+            lane_idct(col, 8, o);
+            const int x0 = o[0] + 512, x1 = o[1] + 512, x2 = o[2] + 512, x3 = o[3] + 512;
+            v[0 * 8 + c] = (x0 + o[7]) >> 10; v[7 * 8 + c] = (x0 - o[7]) >> 10;
+            v[1 * 8 + c] = (x1 + o[6]) >> 10; v[6 * 8 + c] = (x1 - o[6]) >> 10;
+            v[2 * 8 + c] = (x2 + o[5]) >> 10; v[5 * 8 + c] = (x2 - o[5]) >> 10;
+            v[3 * 8 + c] = (x3 + o[4]) >> 10; v[4 * 8 + c] = (x3 - o[4]) >> 10;
+        }
+        auto clamp8 = [](int x) { return (uint8_t)(x < 0 ? 0 : (x > 255 ? 255 : x)); };
+        for (int r = 0; r < 8; ++r) {  // rows
+            int o[8];
+            lane_idct(v + r * 8, 1, o);
+            const int bias = 65536 + (128 << 17);
+            const int x0 = o[0] + bias, x1 = o[1] + bias, x2 = o[2] + bias, x3 = o[3] + bias;
+            uint8_t* row = dst + r * stride;
+            row[0] = clamp8((x0 + o[7]) >> 17); row[7] = clamp8((x0 - o[7]) >> 17);
+            row[1] = clamp8((x1 + o[6]) >> 17); row[6] = clamp8((x1 - o[6]) >> 17);
+            row[2] = clamp8((x2 + o[5]) >> 17); row[5] = clamp8((x2 - o[5]) >> 17);
+            row[3] = clamp8((x3 + o[4]) >> 17); row[4] = clamp8((x3 - o[4]) >> 17);
         }
     }
     // ---- entropy decoding into coefficient arrays (all scans), then dequantise + IDCT ----------------
@@ -621,29 +662,68 @@ struct JpegDecoder {
             for (int by = 0; by < c.bh; ++by) for (int bx = 0; bx < c.bw; ++bx)
                 idct_store(&c.coef[((size_t)by * c.bw + bx) * 64], qt[c.tq], c.plane.data() + ((size_t)by * 8) * c.pw + (size_t)bx * 8, c.pw);
         }
-        // full-resolution sample of a (possibly 2x sub-sampled) component: 3:1 triangle filter along each
-        // sub-sampled axis, the "fancy upsampling" both stb_image (tinygltf's decoder) and libjpeg use
-        auto sample = [&](const Comp& c, int x, int y) -> float {
-            const int sx = hmax / c.h, sy = vmax / c.v;  // 1 or 2
-            const int cw = (W * c.h + hmax - 1) / hmax, ch = (H * c.v + vmax - 1) / vmax;  // valid extent of the plane
-            auto at = [&](int px, int py) { px = px < 0 ? 0 : (px >= cw ? cw - 1 : px); py = py < 0 ? 0 : (py >= ch ? ch - 1 : py); return (float)c.plane[(size_t)py * c.pw + px]; };
-            const int ix = sx == 2 ? x >> 1 : x, iy = sy == 2 ? y >> 1 : y;
-            const int nx = sx == 2 ? ((x & 1) ? ix + 1 : ix - 1) : ix, ny = sy == 2 ? ((y & 1) ? iy + 1 : iy - 1) : iy;
-            const float wx = sx == 2 ? 0.25f : 0.0f, wy = sy == 2 ? 0.25f : 0.0f;
-            const float top = at(ix, iy) * (1.0f - wx) + at(nx, iy) * wx, bot = at(ix, ny) * (1.0f - wx) + at(nx, ny) * wx;
-            return top * (1.0f - wy) + bot * wy;
-        };
+        // Chroma upsampling and colour conversion, again in stb_image's integer form (bit-identical texels):
+        //   2x horizontally: out[2i] = (3 c[i] + c[i-1] + 2) >> 2, out[2i+1] = (3 c[i] + c[i+1] + 2) >> 2, ends copied
+        //   2x vertically:   (3 near + far + 2) >> 2 with near = row y>>1, far = the row above (even y) / below (odd y)
+        //   2x both:         t[i] = 3 near[i] + far[i];  out[2i-1] = (3 t[i-1] + t[i] + 8) >> 4, out[2i] = (3 t[i] + t[i-1] + 8) >> 4
+        //   anything else:   nearest sample
+        // rows/columns outside the component's valid extent (not the MCU padding) are clamped.
+        std::vector<std::vector<uint8_t>> line(comps.size(), std::vector<uint8_t>((size_t)W + 8));
         Image out; out.w = (uint32_t)W; out.h = (uint32_t)H; out.rgba.resize((size_t)W * H * 4);
-        for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) {
-            uint8_t* o = &out.rgba[((size_t)y * W + x) * 4];
-            const float Y = sample(comps[0], x, y);
-            auto cl = [](float v) { const int i = (int)std::lrintf(v); return (uint8_t)(i < 0 ? 0 : (i > 255 ? 255 : i)); };
-            if (comps.size() == 1) { o[0] = o[1] = o[2] = cl(Y); }
-            else {
-                const float cb = sample(comps[1], x, y) - 128.0f, cr = sample(comps[2], x, y) - 128.0f;
-                o[0] = cl(Y + 1.402f * cr); o[1] = cl(Y - 0.344136f * cb - 0.714136f * cr); o[2] = cl(Y + 1.772f * cb);
+        for (int y = 0; y < H; ++y) {
+            for (size_t ci = 0; ci < comps.size(); ++ci) {
+                const Comp& c = comps[ci];
+                const int sx = hmax / c.h, sy = vmax / c.v;
+                const int cw = (W * c.h + hmax - 1) / hmax, chh = (H * c.v + vmax - 1) / vmax;  // valid extent of the plane
+                uint8_t* o = line[ci].data();
+                auto rowp = [&](int r) { r = r < 0 ? 0 : (r >= chh ? chh - 1 : r); return c.plane.data() + (size_t)r * c.pw; };
+                if (sx == 1 && sy == 1) { std::memcpy(o, rowp(y), (size_t)W); continue; }
+                const int ny = sy == 2 ? (y >> 1) : (sy == 1 ? y : y / sy);
+                const uint8_t* near = rowp(ny);
+                const uint8_t* far = sy == 2 ? rowp((y & 1) ? ny + 1 : ny - 1) : near;
+                if (sx == 1 && sy == 2) {
+                    for (int i = 0; i < cw && i < W; ++i) o[i] = (uint8_t)((3 * near[i] + far[i] + 2) >> 2);
+                } else if (sx == 2 && sy == 1) {
+                    if (cw == 1) { o[0] = o[1] = near[0]; }
+                    else {
+                        o[0] = near[0]; o[1] = (uint8_t)((near[0] * 3 + near[1] + 2) >> 2);
+                        int i = 1;
+                        for (; i < cw - 1; ++i) { const int n = 3 * near[i] + 2; o[2 * i] = (uint8_t)((n + near[i - 1]) >> 2); o[2 * i + 1] = (uint8_t)((n + near[i + 1]) >> 2); }
+                        o[2 * i] = (uint8_t)((near[cw - 2] * 3 + near[cw - 1] + 2) >> 2); o[2 * i + 1] = near[cw - 1];
+                    }
+                } else if (sx == 2 && sy == 2) {
+                    if (cw == 1) { o[0] = o[1] = (uint8_t)((3 * near[0] + far[0] + 2) >> 2); }
+                    else {
+                        int t1 = 3 * near[0] + far[0];
+                        o[0] = (uint8_t)((t1 + 2) >> 2);
+                        for (int i = 1; i < cw; ++i) {
+                            const int t0 = t1;
+                            t1 = 3 * near[i] + far[i];
+                            o[2 * i - 1] = (uint8_t)((3 * t0 + t1 + 8) >> 4);
+                            o[2 * i] = (uint8_t)((3 * t1 + t0 + 8) >> 4);
+                        }
+                        o[2 * cw - 1] = (uint8_t)((t1 + 2) >> 2);
+                    }
+                } else {
+                    for (int x = 0; x < W; ++x) o[x] = near[std::min(x / sx, cw - 1)];
+                }
             }
-            o[3] = 255;
+            uint8_t* orow = &out.rgba[(size_t)y * W * 4];
+            if (comps.size() == 1) {
+                for (int x = 0; x < W; ++x) { orow[4 * x] = orow[4 * x + 1] = orow[4 * x + 2] = line[0][x]; orow[4 * x + 3] = 255; }
+            } else {
+                // YCbCr -> RGB with 20 fractional bits; constants are 12-bit values shifted by 8
+                auto f2f = [](float v) { return ((int)(v * 4096.0f + 0.5f)) << 8; };
+                auto clamp8 = [](int v) { return (uint8_t)((unsigned)v > 255 ? (v < 0 ? 0 : 255) : v); };
+                for (int x = 0; x < W; ++x) {
+                    const int yf = (line[0][x] << 20) + (1 << 19);
+                    const int cb = line[1][x] - 128, cr = line[2][x] - 128;
+                    const int r = yf + cr * f2f(1.40200f);
+                    const int g = yf + cr * -f2f(0.71414f) + (int)((unsigned)(cb * -f2f(0.34414f)) & 0xffff0000u);
+                    const int b = yf + cb * f2f(1.77200f);
+                    orow[4 * x] = clamp8(r >> 20); orow[4 * x + 1] = clamp8(g >> 20); orow[4 * x + 2] = clamp8(b >> 20); orow[4 * x + 3] = 255;
+                }
+            }
         }
         return out;
     }
@@ -681,9 +761,12 @@ V3 operator*(V3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
 V3 cross(V3 a, V3 b) { return {a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y}; }
 float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 V3 normalize(V3 a) { const float inv = 1.0f / std::sqrt(dot(a, a)); return a * inv; }
+// glm::vec3(worldTransform * glm::vec4(p, 1)) in GLM 1.0.1's operation order (type_mat4x4.inl operator*(mat4, vec4)):
+// (m0*x + m1*y) + (m2*z + m3*w) — pairwise, not left to right; checked bit for bit against the reference's own
+// parser (oracle/_ref/libm2s_refloader.so, tests/test_oracle.py)
 V3 xform_point(const M4& M, V3 p) {
-    return {M.m[0][0] * p.x + M.m[1][0] * p.y + M.m[2][0] * p.z + M.m[3][0], M.m[0][1] * p.x + M.m[1][1] * p.y + M.m[2][1] * p.z + M.m[3][1],
-            M.m[0][2] * p.x + M.m[1][2] * p.y + M.m[2][2] * p.z + M.m[3][2]};
+    auto row = [&](int r) { return (M.m[0][r] * p.x + M.m[1][r] * p.y) + (M.m[2][r] * p.z + M.m[3][r] * 1.0f); };
+    return {row(0), row(1), row(2)};
 }
 struct M3 { float m[3][3]; };
 V3 mul3(const M3& M, V3 p) {
@@ -691,15 +774,25 @@ V3 mul3(const M3& M, V3 p) {
             M.m[0][2] * p.x + M.m[1][2] * p.y + M.m[2][2] * p.z};
 }
 M3 upper3(const M4& M) { M3 r; for (int c = 0; c < 3; ++c) for (int row = 0; row < 3; ++row) r.m[c][row] = M.m[c][row]; return r; }
-M3 inverse_transpose(const M3& a) {  // transpose(inverse(a)) = cofactor matrix / det
-    const float (*m)[3] = a.m;
-    const float c00 = m[1][1] * m[2][2] - m[2][1] * m[1][2], c01 = m[1][2] * m[2][0] - m[1][0] * m[2][2], c02 = m[1][0] * m[2][1] - m[1][1] * m[2][0];
-    const float det = m[0][0] * c00 + m[0][1] * c01 + m[0][2] * c02;
+// glm::transpose(glm::inverse(mat3)) with GLM 1.0.1's cofactors and determinant expansion (func_matrix.inl,
+// compute_inverse<3,3>), so that normals match the reference bit for bit
+M3 inverse_transpose(const M3& a) {
+    const float (*m)[3] = a.m;  // m[column][row]
+    const float det = +m[0][0] * (m[1][1] * m[2][2] - m[2][1] * m[1][2]) - m[1][0] * (m[0][1] * m[2][2] - m[2][1] * m[0][2]) +
+                      m[2][0] * (m[0][1] * m[1][2] - m[1][1] * m[0][2]);
     const float id = 1.0f / det;
+    float inv[3][3];  // inv[column][row]
+    inv[0][0] = +(m[1][1] * m[2][2] - m[2][1] * m[1][2]) * id;
+    inv[1][0] = -(m[1][0] * m[2][2] - m[2][0] * m[1][2]) * id;
+    inv[2][0] = +(m[1][0] * m[2][1] - m[2][0] * m[1][1]) * id;
+    inv[0][1] = -(m[0][1] * m[2][2] - m[2][1] * m[0][2]) * id;
+    inv[1][1] = +(m[0][0] * m[2][2] - m[2][0] * m[0][2]) * id;
+    inv[2][1] = -(m[0][0] * m[2][1] - m[2][0] * m[0][1]) * id;
+    inv[0][2] = +(m[0][1] * m[1][2] - m[1][1] * m[0][2]) * id;
+    inv[1][2] = -(m[0][0] * m[1][2] - m[1][0] * m[0][2]) * id;
+    inv[2][2] = +(m[0][0] * m[1][1] - m[1][0] * m[0][1]) * id;
     M3 r;
-    r.m[0][0] = c00 * id; r.m[0][1] = c01 * id; r.m[0][2] = c02 * id;
-    r.m[1][0] = (m[2][1] * m[0][2] - m[0][1] * m[2][2]) * id; r.m[1][1] = (m[0][0] * m[2][2] - m[2][0] * m[0][2]) * id; r.m[1][2] = (m[2][0] * m[0][1] - m[0][0] * m[2][1]) * id;
-    r.m[2][0] = (m[0][1] * m[1][2] - m[1][1] * m[0][2]) * id; r.m[2][1] = (m[1][0] * m[0][2] - m[0][0] * m[1][2]) * id; r.m[2][2] = (m[0][0] * m[1][1] - m[1][0] * m[0][1]) * id;
+    for (int c = 0; c < 3; ++c) for (int row = 0; row < 3; ++row) r.m[c][row] = inv[row][c];
     return r;
 }
 M4 trs(const JValue& node) {

@@ -114,6 +114,71 @@ def ref_save_ply(path: str, ref96: np.ndarray, fmt: int, mult: float) -> bool:
     return True
 
 
+_refloader = None
+
+
+def ref_loader_lib():
+    """The reference's own .glb parser (oracle/_ref/libm2s_refloader.so), or None if it was never built."""
+    global _refloader
+    if _refloader is None:
+        path = os.path.join(_HERE, "_ref", "libm2s_refloader.so")
+        if not os.path.exists(path):
+            return None
+        L = C.CDLL(path)
+        L.ref_glb_parse.restype = C.c_void_p
+        L.ref_glb_parse.argtypes = [C.c_char_p]
+        for f in ("ref_glb_ok", "ref_glb_mesh_count"):
+            getattr(L, f).restype = C.c_int
+            getattr(L, f).argtypes = [C.c_void_p]
+        L.ref_glb_mesh_name.restype = C.c_char_p
+        L.ref_glb_mesh_name.argtypes = [C.c_void_p, C.c_int]
+        L.ref_glb_face_count.restype = C.c_int
+        L.ref_glb_face_count.argtypes = [C.c_void_p, C.c_int]
+        L.ref_glb_faces.restype = None
+        L.ref_glb_faces.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_glb_base_color.restype = None
+        L.ref_glb_base_color.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_glb_texture.restype = C.c_uint64
+        L.ref_glb_texture.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                      C.POINTER(C.POINTER(C.c_ubyte))]
+        L.ref_glb_free.restype = None
+        L.ref_glb_free.argtypes = [C.c_void_p]
+        _refloader = L
+    return _refloader
+
+
+def ref_load_glb(path: str):
+    """SceneManager::parseGltfFile of the reference (tinygltf + stb_image).  Returns None if the library is
+    unavailable, else (ok, meshes) with meshes = [{name, faces (n,36) float32 as 3 x {pos3 nrm3 tan4 uv2},
+    base_color (4,), textures: {0|1|2: uint8 array (h, w, channels)}}]."""
+    L = ref_loader_lib()
+    if L is None:
+        return None
+    h = L.ref_glb_parse(str(path).encode())
+    try:
+        meshes = []
+        for i in range(L.ref_glb_mesh_count(h)):
+            n = L.ref_glb_face_count(h, i)
+            faces = np.zeros((n, 36), np.float32)
+            if n:
+                L.ref_glb_faces(h, i, faces.ctypes.data)
+            bc = np.zeros(4, np.float32)
+            L.ref_glb_base_color(h, i, bc.ctypes.data)
+            tex = {}
+            for which in range(3):
+                w, hh, ch = C.c_int(0), C.c_int(0), C.c_int(0)
+                data = C.POINTER(C.c_ubyte)()
+                nbytes = L.ref_glb_texture(h, i, which, C.byref(w), C.byref(hh), C.byref(ch), C.byref(data))
+                if nbytes:
+                    arr = np.ctypeslib.as_array(data, shape=(int(nbytes),)).copy()
+                    per = int(nbytes) // max(1, w.value * hh.value)
+                    tex[which] = arr.reshape(hh.value, w.value, per) if per * w.value * hh.value == nbytes else arr
+            meshes.append({"name": L.ref_glb_mesh_name(h, i).decode("utf-8", "replace"), "faces": faces, "base_color": bc, "textures": tex})
+        return bool(L.ref_glb_ok(h)), meshes
+    finally:
+        L.ref_glb_free(h)
+
+
 def max_threads() -> int:
     return int(lib().orc_max_threads())
 

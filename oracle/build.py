@@ -146,8 +146,54 @@ def build_ref_ply(force: bool = False) -> str | None:
     return out
 
 
+def _ref_includes(stubs: str) -> list:
+    tp = os.path.join(REF, "thirdParty")
+    return ["-I", stubs, "-I", os.path.join(REF, "src"), "-I", os.path.join(REF, "src", "utils"), "-I", tp, "-I", os.path.join(tp, "glm"),
+            "-I", os.path.join(tp, "glew", "include"), "-I", os.path.join(tp, "GLFW", "include"), "-I", os.path.join(tp, "imgui"),
+            "-I", os.path.join(tp, "imgui", "backends"), "-I", os.path.join(tp, "xatlas"), "-I", os.path.join(tp, "ImGuiFileDialog"),
+            "-I", os.path.join(tp, "imguizmo")]
+
+
+def build_ref_loader(force: bool = False) -> str | None:
+    """The reference's own .glb parser: SceneManager::parseGltfFile with tinygltf + stb_image (compiled where they lie)."""
+    srcs = [os.path.join(REF, "src", "utils", "SceneManager.cpp"), os.path.join(REF, "src", "utils", "utils.cpp"),
+            os.path.join(REF, "src", "parsers", "parsers.cpp")]
+    out = os.path.join(REF_OUT, "libm2s_refloader.so")
+    if not all(os.path.exists(x) for x in srcs):
+        return out if os.path.exists(out) else None
+    harness = os.path.join(HERE, "ref_loader_harness.cpp")
+    if not force and _newer(out, *srcs, harness, __file__):
+        return out
+    stubs = os.path.join(REF_OUT, "stubs")
+    os.makedirs(stubs, exist_ok=True)
+    for name, text in _STUBS.items():
+        with open(os.path.join(stubs, name), "w") as f:
+            f.write(text)
+    flags = ["-std=c++17", "-O1", "-fPIC", "-w", "-ffp-contract=off", "-DGLEW_NO_GLU", "-include", os.path.join(stubs, "compat.h"), *_ref_includes(stubs)]
+    objs = []
+    for src in srcs + [harness]:
+        obj = os.path.join(REF_OUT, "ld_" + os.path.splitext(os.path.basename(src))[0] + ".o")
+        _run(["g++", *flags, "-c", src, "-o", obj])
+        objs.append(obj)
+    # the GLEW entry points SceneManager.cpp references are data symbols of glew.c (only a Windows .lib is vendored):
+    # null pointers, generated from the object file's undefined symbols — the GL half is never called
+    und = subprocess.run(["nm", "-u", *objs], capture_output=True, text=True).stdout
+    glew = sorted({w for line in und.splitlines() for w in line.split() if w.startswith("__glew")})
+    gl_null = os.path.join(REF_OUT, "glew_null.c")
+    with open(gl_null, "w") as f:
+        f.write("/* generated by oracle/build.py: null GLEW entry points (never called) */\n")
+        for g in glew:
+            f.write(f"void* {g} = 0;\n")
+    gl_obj = os.path.join(REF_OUT, "ld_glew_null.o")
+    _run(["gcc", "-fPIC", "-c", gl_null, "-o", gl_obj])
+    _run(["g++", "-shared", "-o", out, *objs, gl_obj, "-lstdc++fs"])
+    for o in objs + [gl_obj]:
+        os.remove(o)
+    return out
+
+
 def build_all(force: bool = False) -> dict:
-    return {"oracle": build_oracle(force), "ref": build_ref(force), "ref_ply": build_ref_ply(force)}
+    return {"oracle": build_oracle(force), "ref": build_ref(force), "ref_ply": build_ref_ply(force), "ref_loader": build_ref_loader(force)}
 
 
 if __name__ == "__main__":

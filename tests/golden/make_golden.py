@@ -94,6 +94,7 @@ def main():
                         fs_max_gaussians=maxg, fs_rec=rec, fs_written=written, fs_counter_after=after)
     print("wrote", out, os.path.getsize(out), "bytes")
     ply_vectors(rng)
+    loader_vectors()
 
 
 def ply_vectors(rng):
@@ -126,6 +127,94 @@ def ply_vectors(rng):
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_ply_vectors.npz")
     np.savez_compressed(out, records=rec, scale_multiplier=np.float32(mult), **files)
     print("wrote", out, os.path.getsize(out), "bytes")
+
+
+def loader_vectors():
+    """ref_loader_vectors.npz: small .glb files (geometry variants, node transforms, PNG / JPEG images) and what the
+    REFERENCE's own parser — SceneManager::parseGltfFile with tinygltf + stb_image, compiled where they lie
+    (oracle/_ref/libm2s_refloader.so) — makes of them: faces (pos, normal, tangent, uv), base colour, decoded images."""
+    import io
+    import tempfile
+    from PIL import Image
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_abi_host import _glb_with_image, _make_glb
+    from util import png_encode
+    if oracle.ref_loader_lib() is None:
+        raise SystemExit("oracle/_ref/libm2s_refloader.so is not built (no /root/reference here)")
+    rng = np.random.default_rng(424242)
+    store = {}
+    names = []
+
+    def add(name, path):
+        ok, meshes = oracle.ref_load_glb(path)
+        assert ok and meshes, name
+        names.append(name)
+        store[f"{name}/glb"] = np.frombuffer(open(path, "rb").read(), np.uint8)
+        store[f"{name}/faces"] = np.vstack([m["faces"] for m in meshes])
+        store[f"{name}/mesh_faces"] = np.array([len(m["faces"]) for m in meshes], np.int64)
+        store[f"{name}/mesh_names"] = np.array([m["name"] for m in meshes])
+        store[f"{name}/base_color"] = np.stack([m["base_color"] for m in meshes])
+        for which, t in meshes[0]["textures"].items():
+            if t.ndim == 3 and t.shape[2] == 4:       # 8-bit RGBA (16-bit PNGs come back as 8 bytes per pixel: not compared)
+                store[f"{name}/tex{which}"] = t
+
+    def rnd_mat():
+        M = np.eye(4, dtype=np.float32); M[:3, :3] = rng.normal(size=(3, 3)); M[:3, 3] = rng.normal(size=3) * 5
+        return M
+
+    with tempfile.TemporaryDirectory() as d:
+        k = 0
+        for indexed in (True, False):
+            for with_normals in (True, False):
+                for with_tangents in (True, False):
+                    for xf in ("none", "matrix", "trs"):
+                        kw = dict(indexed=indexed, with_normals=with_normals, with_tangents=with_tangents, two_prims=(k % 4 == 0),
+                                  with_uv=(k % 5 != 4), with_texture=(k % 3 == 0))
+                        if xf == "matrix":
+                            kw["matrix"] = rnd_mat()
+                        elif xf == "trs":
+                            q = rng.normal(size=4); q /= np.linalg.norm(q)
+                            kw["trs"] = ([float(v) for v in rng.normal(size=3) * 3], [float(v) for v in q], [float(v) for v in rng.random(3) * 3 + 0.1])
+                        path = os.path.join(d, f"g{k}.glb")
+                        _make_glb(path, **kw)
+                        add(f"geom{k:02d}", path)
+                        k += 1
+        # images: every 8-bit-or-less PNG type (plain + Adam7), JPEG baseline/progressive x subsampling, gray
+        for ctype, depth in [(0, 1), (0, 2), (0, 4), (0, 8), (2, 8), (3, 1), (3, 2), (3, 4), (3, 8), (4, 8), (6, 8)]:
+            ch = {0: 1, 2: 3, 3: 1, 4: 2, 6: 4}[ctype]
+            smp = rng.integers(0, 1 << depth, size=(11, 13, ch))
+            plte = trns = None
+            if ctype == 3:
+                n = 1 << depth
+                plte = rng.integers(0, 256, size=(n, 3), dtype=np.uint8).tobytes()
+                trns = rng.integers(0, 256, size=(max(1, n // 2),), dtype=np.uint8).tobytes()
+            if ctype == 0:
+                trns = int(smp[2, 3, 0]).to_bytes(2, "big")
+            if ctype == 2:
+                trns = b"".join(int(v).to_bytes(2, "big") for v in smp[4, 5])
+            for il in (False, True):
+                path = os.path.join(d, "p.glb")
+                _glb_with_image(path, png_encode(smp, ctype, depth, il, plte, trns), "image/png")
+                add(f"png_c{ctype}_d{depth}_i{int(il)}", path)
+        for (w, h) in [(64, 48), (37, 70), (17, 9), (1, 1)]:
+            yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+            img = np.stack([128 + 100 * np.sin(xx / 9), 128 + 100 * np.cos(yy / 7), 128 + 60 * np.sin((xx + yy) / 11)], axis=-1)
+            img = np.clip(img + rng.normal(0, 12, img.shape), 0, 255).astype(np.uint8)
+            for prog in (False, True):
+                for ss in (0, 1, 2):
+                    b = io.BytesIO()
+                    Image.fromarray(img).save(b, "JPEG", quality=80, subsampling=ss, progressive=prog)
+                    path = os.path.join(d, "j.glb")
+                    _glb_with_image(path, b.getvalue(), "image/jpeg")
+                    add(f"jpeg_{w}x{h}_p{int(prog)}_s{ss}", path)
+            b = io.BytesIO()
+            Image.fromarray(img[..., 0]).save(b, "JPEG", quality=80)
+            path = os.path.join(d, "j.glb")
+            _glb_with_image(path, b.getvalue(), "image/jpeg")
+            add(f"jpeg_{w}x{h}_gray", path)
+    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_loader_vectors.npz")
+    np.savez_compressed(out, names=np.array(names), **store)
+    print("wrote", out, os.path.getsize(out), "bytes,", len(names), "cases")
 
 
 if __name__ == "__main__":

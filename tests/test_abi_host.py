@@ -278,10 +278,46 @@ def _glb_with_image(path, blob: bytes, mime: str):
         f.write(struct.pack("<I4s", len(binblob), b"BIN\x00")); f.write(binblob)
 
 
+def _loader_golden():
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_loader_vectors.npz"))
+
+
+def test_glb_loader_matches_the_reference_parser_golden(tmp_path):
+    """tests/golden/ref_loader_vectors.npz: 74 small .glb files and what the REFERENCE's own parser made of them
+    (SceneManager::parseGltfFile + tinygltf + stb_image compiled from /root/reference; make_golden.py).
+    m2s_glb_load must reproduce it BIT FOR BIT: world-space positions, normals (normal matrix or flat fallback),
+    tangents (transformed or per-face fallback), uvs, primitive names and skipping rules, base colour, and every
+    decoded texel (all <= 8-bit PNG types incl. Adam7, baseline and progressive JPEG in 4:4:4 / 4:2:2 / 4:2:0)."""
+    from mesh2splat_b200.gltf import load_glb
+    g = _loader_golden()
+    checked_tex = 0
+    for name in g["names"]:
+        name = str(name)
+        p = tmp_path / "case.glb"
+        p.write_bytes(g[f"{name}/glb"].tobytes())
+        s = load_glb(str(p))
+        want = g[f"{name}/faces"]
+        assert s.triangles.shape == want.shape, name
+        assert np.array_equal(s.triangles.view(np.uint32), want.view(np.uint32)), f"{name}: triangle data differs"
+        assert [pr.name for pr in s.primitives] == [str(x) for x in g[f"{name}/mesh_names"]], name
+        assert [pr.triangle_count for pr in s.primitives] == list(g[f"{name}/mesh_faces"]), name
+        for pr, bc in zip(s.primitives, g[f"{name}/base_color"]):
+            assert np.array_equal(np.asarray(pr.base_color_factor, np.float32), bc), name
+        pr0 = s.primitives[0]
+        for which, idx in ((0, pr0.albedo_texture), (1, pr0.normal_texture), (2, pr0.metallic_roughness_texture)):
+            key = f"{name}/tex{which}"
+            if key in g.files:
+                assert idx >= 0, name
+                assert np.array_equal(s.textures[idx], g[key]), f"{name}: texture {which} differs from stb_image's decode"
+                checked_tex += 1
+    assert checked_tex >= 60
+
+
 @pytest.mark.parametrize("mode,subsampling,size", [("RGB", 0, (64, 48)), ("RGB", 2, (70, 37)), ("RGB", 1, (33, 65)), ("L", 0, (40, 24))])
 def test_glb_loader_decodes_baseline_jpeg(tmp_path, mode, subsampling, size):
-    """Own baseline-JPEG decoder vs Pillow (libjpeg) on smooth images: luma within 2 code values; chroma
-    differs only by the upsampling filter (ours: nearest), bounded on smooth content."""
+    """Sanity bound of the own JPEG decoder against Pillow (libjpeg) on smooth images.  The decoder follows
+    stb_image's arithmetic (the reference's decoder; bit-exactness against it is what tests/test_oracle.py checks
+    with golden files); libjpeg rounds its IDCT and 4:2:2 upsampling slightly differently."""
     import io
     from PIL import Image
     from mesh2splat_b200.gltf import load_glb
@@ -301,9 +337,9 @@ def test_glb_loader_decodes_baseline_jpeg(tmp_path, mode, subsampling, size):
     assert got.shape == (h, w, 4) and np.all(got[..., 3] == 255)
     d = np.abs(got[..., :3].astype(np.int32) - want)
     if subsampling == 0:
-        assert d.max() <= 2, d.max()
+        assert d.max() <= 3, d.max()
     else:
-        assert d.mean() < 1.0 and d.max() <= 6, (d.mean(), d.max())
+        assert d.mean() < 1.0 and d.max() <= 12, (d.mean(), d.max())
 
 
 _PNG_CASES = [(0, 1), (0, 2), (0, 4), (0, 8), (0, 16), (2, 8), (2, 16), (3, 1), (3, 2), (3, 4), (3, 8), (4, 8), (4, 16), (6, 8), (6, 16)]
@@ -394,10 +430,10 @@ def test_glb_loader_decodes_progressive_jpeg(tmp_path, mode, subsampling, size, 
     assert got.shape == (h, w, 4) and np.all(got[..., 3] == 255)
     assert np.array_equal(got, outs[False])          # same coefficients, whatever the scan script
     d = np.abs(got[..., :3].astype(np.int32) - want)
-    if subsampling == 0 or mode == "L":   # IDCT / colour-conversion rounding only (libjpeg: integer islow; ours: float)
-        assert d.max() <= 3 and d.mean() < 0.6, (d.max(), d.mean())
+    if subsampling == 0 or mode == "L":   # IDCT / colour-conversion rounding only (libjpeg islow vs stb's fixed point)
+        assert d.max() <= 4 and d.mean() < 0.6, (d.max(), d.mean())
     else:                                  # + chroma upsampling differences on noisy content
-        assert d.mean() < 1.5 and d.max() <= 12, (d.mean(), d.max())
+        assert d.mean() < 1.5 and d.max() <= 16, (d.mean(), d.max())
 
 
 def test_glb_loader_rejects_arithmetic_jpeg(tmp_path):

@@ -229,3 +229,29 @@ def test_ply_bytes_match_live_reference_writer(tmp_path):
         path = tmp_path / f"live{fmt}.ply"
         assert oracle.ref_save_ply(str(path), rec, fmt, mult)
         assert path.read_bytes() == oracle.ply_bytes(rec.view(_abi.record_dtype(LAYOUT_REF96)).reshape(-1), fmt, mult)
+
+
+def test_loader_matches_live_reference_parser(tmp_path):
+    """Fresh random node transforms / attribute combinations through the reference's own parser (when it is built
+    here) and through m2s_glb_load: bit-identical triangle data."""
+    if oracle.ref_loader_lib() is None:
+        pytest.skip("oracle/_ref/libm2s_refloader.so not built (no /root/reference on this machine)")
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_abi_host import _make_glb
+    from mesh2splat_b200.gltf import load_glb
+    rng = np.random.default_rng(99)
+    for k in range(24):
+        if k % 2 == 0:
+            M = np.eye(4, dtype=np.float32); M[:3, :3] = rng.normal(size=(3, 3)); M[:3, 3] = rng.normal(size=3) * 5
+            kw = dict(matrix=M)
+        else:
+            q = rng.normal(size=4); q /= np.linalg.norm(q)
+            kw = dict(trs=([float(v) for v in rng.normal(size=3)], [float(v) for v in q], [float(v) for v in rng.random(3) * 2 + 0.2]))
+        kw.update(with_normals=bool(k % 3), with_tangents=bool(k % 5), indexed=bool(k % 4))
+        p = tmp_path / f"c{k}.glb"
+        _make_glb(str(p), **kw)
+        ok, meshes = oracle.ref_load_glb(str(p))
+        s = load_glb(str(p))
+        want = np.vstack([m["faces"] for m in meshes])
+        assert ok and np.array_equal(want.view(np.uint32), s.triangles.view(np.uint32)), k
