@@ -418,11 +418,11 @@ struct JpegDecoder {
         --bitcnt;
         return (bitbuf >> bitcnt) & 1;
     }
-    int getbits(int n) { int v = 0; while (n--) v = (v << 1) | getbit(); return v; }
+    int getbits(int n) { uint32_t v = 0; while (n-- > 0) v = (v << 1) | (uint32_t)getbit(); return (int)v; }
     int decode(const HT& t) {
         int code = 0;
         for (int l = 1; l <= 16; ++l) {
-            code = (code << 1) | getbit();
+            code = (int)(((uint32_t)code << 1) | (uint32_t)getbit());
             if (t.maxcode[l] >= 0 && code <= t.maxcode[l] && code >= t.mincode[l]) return t.vals[t.valptr[l] + code - t.mincode[l]];
         }
         throw FormatError("jpeg: bad huffman code");
@@ -434,21 +434,24 @@ struct JpegDecoder {
     static int fx(double v) { return (int)(v * 4096.0 + 0.5); }
     struct Lane { int s[8]; };
     static void lane_idct(const int* in, int stride, int out[8]) {  // one 8-point pass; outputs are sums/differences x_k +- t_k
-        const int s0 = in[0], s1 = in[stride], s2 = in[2 * stride], s3 = in[3 * stride], s4 = in[4 * stride], s5 = in[5 * stride],
-                  s6 = in[6 * stride], s7 = in[7 * stride];
+        // two's-complement wrap-around arithmetic (unsigned): identical to int for every valid stream, defined for garbage
+        typedef uint32_t U;
+        const U s0 = (U)in[0], s1 = (U)in[stride], s2 = (U)in[2 * stride], s3 = (U)in[3 * stride], s4 = (U)in[4 * stride],
+                s5 = (U)in[5 * stride], s6 = (U)in[6 * stride], s7 = (U)in[7 * stride];
+        auto k = [](double v) { return (U)fx(v); };
         // even part
-        const int pe = (s2 + s6) * fx(0.5411961);
-        const int e2 = pe + s6 * fx(-1.847759065), e3 = pe + s2 * fx(0.765366865);
-        const int e0 = (s0 + s4) * 4096, e1 = (s0 - s4) * 4096;
-        const int x0 = e0 + e3, x3 = e0 - e3, x1 = e1 + e2, x2 = e1 - e2;
+        const U pe = (s2 + s6) * k(0.5411961);
+        const U e2 = pe + s6 * k(-1.847759065), e3 = pe + s2 * k(0.765366865);
+        const U e0 = (s0 + s4) * 4096u, e1 = (s0 - s4) * 4096u;
+        const U x0 = e0 + e3, x3 = e0 - e3, x1 = e1 + e2, x2 = e1 - e2;
         // odd part
-        const int q3 = s7 + s3, q4 = s5 + s1, q1 = s7 + s1, q2 = s5 + s3;
-        const int q5 = (q3 + q4) * fx(1.175875602);
-        const int r1 = q5 + q1 * fx(-0.899976223), r2 = q5 + q2 * fx(-2.562915447);
-        const int r3 = q3 * fx(-1.961570560), r4 = q4 * fx(-0.390180644);
-        const int t3 = s1 * fx(1.501321110) + r1 + r4, t2 = s3 * fx(3.072711026) + r2 + r3;
-        const int t1 = s5 * fx(2.053119869) + r2 + r4, t0 = s7 * fx(0.298631336) + r1 + r3;
-        out[0] = x0; out[1] = x1; out[2] = x2; out[3] = x3; out[4] = t0; out[5] = t1; out[6] = t2; out[7] = t3;
+        const U q3 = s7 + s3, q4 = s5 + s1, q1 = s7 + s1, q2 = s5 + s3;
+        const U q5 = (q3 + q4) * k(1.175875602);
+        const U r1 = q5 + q1 * k(-0.899976223), r2 = q5 + q2 * k(-2.562915447);
+        const U r3 = q3 * k(-1.961570560), r4 = q4 * k(-0.390180644);
+        const U t3 = s1 * k(1.501321110) + r1 + r4, t2 = s3 * k(3.072711026) + r2 + r3;
+        const U t1 = s5 * k(2.053119869) + r2 + r4, t0 = s7 * k(0.298631336) + r1 + r3;
+        out[0] = (int)x0; out[1] = (int)x1; out[2] = (int)x2; out[3] = (int)x3; out[4] = (int)t0; out[5] = (int)t1; out[6] = (int)t2; out[7] = (int)t3;
     }
     void idct_store(const short* blk, const uint16_t* q, uint8_t* dst, int stride) {
         int d[64], v[64];
@@ -456,29 +459,33 @@ struct JpegDecoder {
         for (int c = 0; c < 8; ++c) {  // columns
             const int* col = d + c;
             if (!(col[8] | col[16] | col[24] | col[32] | col[40] | col[48] | col[56])) {
-                const int dc = col[0] * 4;
+                const int dc = (int)((uint32_t)col[0] * 4u);
                 for (int r = 0; r < 8; ++r) v[r * 8 + c] = dc;
                 continue;
             }
             int o[8];
             lane_idct(col, 8, o);
-            const int x0 = o[0] + 512, x1 = o[1] + 512, x2 = o[2] + 512, x3 = o[3] + 512;
-            v[0 * 8 + c] = (x0 + o[7]) >> 10; v[7 * 8 + c] = (x0 - o[7]) >> 10;
-            v[1 * 8 + c] = (x1 + o[6]) >> 10; v[6 * 8 + c] = (x1 - o[6]) >> 10;
-            v[2 * 8 + c] = (x2 + o[5]) >> 10; v[5 * 8 + c] = (x2 - o[5]) >> 10;
-            v[3 * 8 + c] = (x3 + o[4]) >> 10; v[4 * 8 + c] = (x3 - o[4]) >> 10;
+            auto add = [](int a, int b2) { return (int)((uint32_t)a + (uint32_t)b2); };
+            auto sub = [](int a, int b2) { return (int)((uint32_t)a - (uint32_t)b2); };
+            const int x0 = add(o[0], 512), x1 = add(o[1], 512), x2 = add(o[2], 512), x3 = add(o[3], 512);
+            v[0 * 8 + c] = add(x0, o[7]) >> 10; v[7 * 8 + c] = sub(x0, o[7]) >> 10;
+            v[1 * 8 + c] = add(x1, o[6]) >> 10; v[6 * 8 + c] = sub(x1, o[6]) >> 10;
+            v[2 * 8 + c] = add(x2, o[5]) >> 10; v[5 * 8 + c] = sub(x2, o[5]) >> 10;
+            v[3 * 8 + c] = add(x3, o[4]) >> 10; v[4 * 8 + c] = sub(x3, o[4]) >> 10;
         }
         auto clamp8 = [](int x) { return (uint8_t)(x < 0 ? 0 : (x > 255 ? 255 : x)); };
         for (int r = 0; r < 8; ++r) {  // rows
             int o[8];
             lane_idct(v + r * 8, 1, o);
+            auto add = [](int a, int b2) { return (int)((uint32_t)a + (uint32_t)b2); };
+            auto sub = [](int a, int b2) { return (int)((uint32_t)a - (uint32_t)b2); };
             const int bias = 65536 + (128 << 17);
-            const int x0 = o[0] + bias, x1 = o[1] + bias, x2 = o[2] + bias, x3 = o[3] + bias;
+            const int x0 = add(o[0], bias), x1 = add(o[1], bias), x2 = add(o[2], bias), x3 = add(o[3], bias);
             uint8_t* row = dst + r * stride;
-            row[0] = clamp8((x0 + o[7]) >> 17); row[7] = clamp8((x0 - o[7]) >> 17);
-            row[1] = clamp8((x1 + o[6]) >> 17); row[6] = clamp8((x1 - o[6]) >> 17);
-            row[2] = clamp8((x2 + o[5]) >> 17); row[5] = clamp8((x2 - o[5]) >> 17);
-            row[3] = clamp8((x3 + o[4]) >> 17); row[4] = clamp8((x3 - o[4]) >> 17);
+            row[0] = clamp8(add(x0, o[7]) >> 17); row[7] = clamp8(sub(x0, o[7]) >> 17);
+            row[1] = clamp8(add(x1, o[6]) >> 17); row[6] = clamp8(sub(x1, o[6]) >> 17);
+            row[2] = clamp8(add(x2, o[5]) >> 17); row[5] = clamp8(sub(x2, o[5]) >> 17);
+            row[3] = clamp8(add(x3, o[4]) >> 17); row[4] = clamp8(sub(x3, o[4]) >> 17);
         }
     }
     // ---- entropy decoding into coefficient arrays (all scans), then dequantise + IDCT ----------------
@@ -512,6 +519,7 @@ struct JpegDecoder {
     void decode_block(Comp& c, short* blk, int Ss, int Se, int Ah, int Al) {
         if (!progressive) {
             const int t = decode(dc[c.td]);
+            if (t > 15) throw FormatError("jpeg: bad DC size");
             c.dcpred += extend(getbits(t), t);
             blk[0] = (short)c.dcpred;
             for (int k = 1; k < 64;) {
@@ -523,7 +531,12 @@ struct JpegDecoder {
             return;
         }
         if (Ss == 0) {  // DC scan
-            if (Ah == 0) { const int t = decode(dc[c.td]); c.dcpred += extend(getbits(t), t); blk[0] = (short)(c.dcpred * (1 << Al)); }
+            if (Ah == 0) {
+                const int t = decode(dc[c.td]);
+                if (t > 15) throw FormatError("jpeg: bad DC size");
+                c.dcpred += extend(getbits(t), t);
+                blk[0] = (short)((uint32_t)c.dcpred * (1u << Al));
+            }
             else if (getbit()) blk[0] = (short)(blk[0] | (1 << Al));
             return;
         }
@@ -636,6 +649,8 @@ struct JpegDecoder {
                     const int id = u8(); const int t = u8(); int found = -1;
                     for (size_t ci = 0; ci < comps.size(); ++ci) if (comps[ci].id == id) found = (int)ci;
                     if (found < 0) throw FormatError("jpeg: bad scan component");
+                    if ((t >> 4) > 3 || (t & 15) > 3) throw FormatError("jpeg: bad table selector");
+                    for (int prev : sc) if (prev == found) throw FormatError("jpeg: component listed twice in a scan");
                     comps[found].td = t >> 4; comps[found].ta = t & 15; sc.push_back(found);
                 }
                 const int Ss = u8(), Se = u8(), AhAl = u8();
