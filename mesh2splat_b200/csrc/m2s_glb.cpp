@@ -869,11 +869,18 @@ AccessorView accessor(const Glb& g, int index) {
 }
 
 // getBufferData<T> (SceneManager.cpp:50-61): tightly packed float arrays, stride ignored
-const float* float_array(const Glb& g, int acc, int comps, size_t* count) {
+// `holder` receives an aligned copy when the data does not start on a 4-byte boundary (invalid glTF, but the bytes
+// are still read the way the reference's reinterpret_cast would read them on x86)
+const float* float_array(const Glb& g, int acc, int comps, size_t* count, std::vector<float>& holder) {
     const AccessorView v = accessor(g, acc);
     if (v.componentType != 5126) throw FormatError("vertex attribute is not FLOAT (normalised integer attributes unsupported, as in the reference)");
     if (v.count * comps * sizeof(float) > v.avail) throw FormatError("vertex attribute exceeds the BIN chunk");
     *count = v.count;
+    if (reinterpret_cast<uintptr_t>(v.data) & 3u) {
+        holder.resize(v.count * comps);
+        std::memcpy(holder.data(), v.data, holder.size() * sizeof(float));
+        return holder.data();
+    }
     return reinterpret_cast<const float*>(v.data);
 }
 
@@ -1006,7 +1013,8 @@ M2S_EXPORT m2s_status m2s_glb_load(const char* path, int cumulative_bbox, m2s_hs
                 const std::string name = base + "_" + std::to_string(meshCounter++);
 
                 size_t nverts = 0;
-                const float* pos = float_array(g, attrs->get("POSITION")->as_int(-1), 3, &nverts);
+                std::vector<float> hold_pos, hold_nrm, hold_uv, hold_tan;
+                const float* pos = float_array(g, attrs->get("POSITION")->as_int(-1), 3, &nverts, hold_pos);
                 std::vector<uint32_t> indices;
                 const int ia = pr.get_int("indices", -1);
                 if (ia >= 0) {
@@ -1025,11 +1033,11 @@ M2S_EXPORT m2s_status m2s_glb_load(const char* path, int cumulative_bbox, m2s_hs
                 for (uint32_t ix : indices) if (ix >= nverts) throw FormatError("vertex index out of range");
 
                 size_t cnt = 0;
-                const float* nrm = attrs->get("NORMAL") ? float_array(g, attrs->get("NORMAL")->as_int(-1), 3, &cnt) : nullptr;
+                const float* nrm = attrs->get("NORMAL") ? float_array(g, attrs->get("NORMAL")->as_int(-1), 3, &cnt, hold_nrm) : nullptr;
                 if (nrm && cnt < nverts) throw FormatError("NORMAL accessor shorter than POSITION");
-                const float* uvs = attrs->get("TEXCOORD_0") ? float_array(g, attrs->get("TEXCOORD_0")->as_int(-1), 2, &cnt) : nullptr;
+                const float* uvs = attrs->get("TEXCOORD_0") ? float_array(g, attrs->get("TEXCOORD_0")->as_int(-1), 2, &cnt, hold_uv) : nullptr;
                 if (uvs && cnt < nverts) throw FormatError("TEXCOORD_0 accessor shorter than POSITION");
-                const float* tan = attrs->get("TANGENT") ? float_array(g, attrs->get("TANGENT")->as_int(-1), 4, &cnt) : nullptr;
+                const float* tan = attrs->get("TANGENT") ? float_array(g, attrs->get("TANGENT")->as_int(-1), 4, &cnt, hold_tan) : nullptr;
                 if (tan && cnt < nverts) throw FormatError("TANGENT accessor shorter than POSITION");
 
                 m2s_primitive P;
