@@ -57,6 +57,20 @@ def plan_work(triangle_count: int, world: int, resolution: int, cost: np.ndarray
     return [(a, n, 0, 0) for a, n in ranges]
 
 
+def choose_strategy(t_single_us: float, n_records: int, stride: int, world: int, fixed_us: float = 35.0,
+                    nvlink_gb_s: float = 770.0) -> str:
+    """"shard" or "replicate" for a conversion whose result every rank must hold.
+
+    Sharding costs t_single/world of compute, the fixed multi-GPU overhead (count exchange, done flags, rank skew:
+    ~35 us measured) and at least (world-1)/world * n_records * stride bytes of NVLink ingress per GPU; replicating
+    costs t_single and no traffic.  Output-heavy scenes (BASELINE config 2: 36 MB of records from a 40 us
+    conversion) replicate; triangle-heavy ones (config 4: 9.5 MB from 123 us) shard."""
+    if world <= 1:
+        return "replicate"
+    ingress_us = (world - 1) / world * n_records * stride / (nvlink_gb_s * 1e3)
+    return "shard" if t_single_us / world + fixed_us + ingress_us < t_single_us else "replicate"
+
+
 def estimate_cost(triangles: np.ndarray, bbox_min, bbox_max, resolution: int) -> np.ndarray:
     """Per-triangle candidate-pixel estimate: area of the dominant-axis projection's bounding box on
     the R x R grid (+1 for the fixed per-triangle set-up)."""

@@ -117,3 +117,12 @@ def test_plan_work_switches_to_row_bands_for_huge_triangles():
     c2 = estimate_cost(sp.triangles, sp.primitives[0].bbox_min, sp.primitives[0].bbox_max, 64)
     plan = plan_work(sp.triangle_count, 4, 64, c2)
     assert all(p[2] == 0 and p[3] == 0 for p in plan) and sum(p[1] for p in plan) == sp.triangle_count
+
+
+def test_choose_strategy_on_the_measured_configs():
+    sys.path.insert(0, ROOT)
+    from mesh2splat_b200.shard import choose_strategy
+    for g in (2, 4, 8):
+        assert choose_strategy(39.9, 643438, 56, g) == "replicate"      # config 2: the gather alone costs 23-43 us
+        assert choose_strategy(122.7, 169183, 56, g) == "shard"         # config 4: 1 M triangles, 9.5 MB of records
+    assert choose_strategy(122.7, 169183, 56, 1) == "replicate"
