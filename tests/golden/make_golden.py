@@ -157,6 +157,12 @@ def loader_vectors():
         for which, t in meshes[0]["textures"].items():
             if t.ndim == 3 and t.shape[2] == 4:       # 8-bit RGBA (16-bit PNGs come back as 8 bytes per pixel: not compared)
                 store[f"{name}/tex{which}"] = t
+        # per-primitive texture presence (3 flags) for the multi-mesh cases
+        store[f"{name}/tex_present"] = np.array([[int(w in m["textures"]) for w in range(3)] for m in meshes], np.int64)
+        for mi, m in enumerate(meshes[1:], start=1):
+            for which, t in m["textures"].items():
+                if t.ndim == 3 and t.shape[2] == 4:
+                    store[f"{name}/m{mi}tex{which}"] = t
 
     def rnd_mat():
         M = np.eye(4, dtype=np.float32); M[:3, :3] = rng.normal(size=(3, 3)); M[:3, 3] = rng.normal(size=3) * 5
@@ -212,6 +218,15 @@ def loader_vectors():
             path = os.path.join(d, "j.glb")
             _glb_with_image(path, b.getvalue(), "image/jpeg")
             add(f"jpeg_{w}x{h}_gray", path)
+        # random multi-mesh scene graphs (nested matrix / TRS nodes, instancing, several materials sharing images,
+        # u8 / u16 / u32 / no indices, skipped LINES and POSITION-less primitives, two scenes)
+        from util import make_complex_glb
+        for seed in range(40):
+            path = os.path.join(d, "c.glb")
+            make_complex_glb(path, 1000 + seed)
+            ok, meshes = oracle.ref_load_glb(path)
+            if ok and meshes:
+                add(f"graph{seed:02d}", path)
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_loader_vectors.npz")
     np.savez_compressed(out, names=np.array(names), **store)
     print("wrote", out, os.path.getsize(out), "bytes,", len(names), "cases")

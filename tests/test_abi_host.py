@@ -283,7 +283,8 @@ def _loader_golden():
 
 
 def test_glb_loader_matches_the_reference_parser_golden(tmp_path):
-    """tests/golden/ref_loader_vectors.npz: 74 small .glb files and what the REFERENCE's own parser made of them
+    """tests/golden/ref_loader_vectors.npz: 110+ small .glb files (geometry variants, every image type, 40 random
+    multi-mesh scene graphs) and what the REFERENCE's own parser made of them
     (SceneManager::parseGltfFile + tinygltf + stb_image compiled from /root/reference; make_golden.py).
     m2s_glb_load must reproduce it BIT FOR BIT: world-space positions, normals (normal matrix or flat fallback),
     tangents (transformed or per-face fallback), uvs, primitive names and skipping rules, base colour, and every
@@ -303,14 +304,17 @@ def test_glb_loader_matches_the_reference_parser_golden(tmp_path):
         assert [pr.triangle_count for pr in s.primitives] == list(g[f"{name}/mesh_faces"]), name
         for pr, bc in zip(s.primitives, g[f"{name}/base_color"]):
             assert np.array_equal(np.asarray(pr.base_color_factor, np.float32), bc), name
-        pr0 = s.primitives[0]
-        for which, idx in ((0, pr0.albedo_texture), (1, pr0.normal_texture), (2, pr0.metallic_roughness_texture)):
-            key = f"{name}/tex{which}"
-            if key in g.files:
-                assert idx >= 0, name
-                assert np.array_equal(s.textures[idx], g[key]), f"{name}: texture {which} differs from stb_image's decode"
-                checked_tex += 1
-    assert checked_tex >= 60
+        present = g[f"{name}/tex_present"] if f"{name}/tex_present" in g.files else None
+        for mi, pr in enumerate(s.primitives):
+            for which, idx in ((0, pr.albedo_texture), (1, pr.normal_texture), (2, pr.metallic_roughness_texture)):
+                if present is not None:
+                    assert (idx >= 0) == bool(present[mi][which]), f"{name}: primitive {mi} texture slot {which}"
+                key = f"{name}/tex{which}" if mi == 0 else f"{name}/m{mi}tex{which}"
+                if key in g.files:
+                    assert idx >= 0, name
+                    assert np.array_equal(s.textures[idx], g[key]), f"{name}: primitive {mi} texture {which} differs from stb_image's decode"
+                    checked_tex += 1
+    assert checked_tex >= 150
 
 
 @pytest.mark.parametrize("mode,subsampling,size", [("RGB", 0, (64, 48)), ("RGB", 2, (70, 37)), ("RGB", 1, (33, 65)), ("L", 0, (40, 24))])

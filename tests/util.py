@@ -204,3 +204,115 @@ def png_encode(samples: np.ndarray, ctype: int, depth: int, interlace: bool = Fa
     half = len(raw) // 2 or 1
     z = zlib.compress(raw, 6)
     return out + chunk(b"IDAT", z[:half]) + chunk(b"IDAT", z[half:]) + chunk(b"IEND", b"")
+
+
+def make_complex_glb(path: str, seed: int) -> None:
+    """Random multi-mesh .glb for differential loader tests: node hierarchy up to depth 3 mixing `matrix` and TRS
+    nodes, 2-4 meshes of 1-3 primitives (index types u8 / u16 / u32 / none; optional NORMAL / TANGENT / TEXCOORD_0;
+    a LINES primitive and a POSITION-less one that must be skipped), several materials sharing images, a primitive
+    without a material, a mesh instanced by two nodes, an unnamed mesh, optionally two scenes with `scene` set."""
+    import json
+    import struct
+    rng = np.random.default_rng(seed)
+    blobs, views, accessors = [], [], []
+
+    def add_view(b):
+        off = sum(len(x) for x in blobs)
+        blobs.append(b + b"\x00" * ((-len(b)) % 4))
+        views.append({"buffer": 0, "byteOffset": off, "byteLength": len(b)})
+        return len(views) - 1
+
+    def add_acc(arr, ctype, typ):
+        accessors.append({"bufferView": add_view(np.ascontiguousarray(arr).tobytes()), "componentType": ctype, "count": len(arr), "type": typ})
+        return len(accessors) - 1
+
+    nimg = int(rng.integers(1, 4))
+    images = []
+    for i in range(nimg):
+        w, h = int(rng.integers(2, 9)), int(rng.integers(2, 9))
+        ch = int(rng.choice([3, 4]))
+        images.append({"bufferView": add_view(png_bytes(rng.integers(0, 256, size=(h, w, ch), dtype=np.uint8))), "mimeType": "image/png"})
+    textures = [{"source": int(rng.integers(0, nimg))} for _ in range(int(rng.integers(1, 5)))]
+    materials = []
+    for m in range(int(rng.integers(1, 4))):
+        pbr = {}
+        if rng.random() < 0.8: pbr["baseColorFactor"] = [float(v) for v in rng.random(4)]
+        if rng.random() < 0.7: pbr["baseColorTexture"] = {"index": int(rng.integers(0, len(textures)))}
+        if rng.random() < 0.5: pbr["metallicRoughnessTexture"] = {"index": int(rng.integers(0, len(textures)))}
+        mat = {"name": f"mat{m}", "pbrMetallicRoughness": pbr}
+        if rng.random() < 0.5: mat["normalTexture"] = {"index": int(rng.integers(0, len(textures))), "scale": 1.5}
+        if rng.random() < 0.2: del mat["pbrMetallicRoughness"]
+        materials.append(mat)
+    meshes = []
+    for mi in range(int(rng.integers(2, 5))):
+        prims = []
+        for pi in range(int(rng.integers(1, 4))):
+            nv = int(rng.integers(3, 12))
+            pos = (rng.normal(size=(nv, 3)) * 2).astype(np.float32)
+            attrs = {"POSITION": add_acc(pos, 5126, "VEC3")}
+            if rng.random() < 0.6:
+                n = rng.normal(size=(nv, 3)); attrs["NORMAL"] = add_acc((n / np.linalg.norm(n, axis=1, keepdims=True)).astype(np.float32), 5126, "VEC3")
+            if rng.random() < 0.5:
+                t = rng.normal(size=(nv, 3)); t /= np.linalg.norm(t, axis=1, keepdims=True)
+                attrs["TANGENT"] = add_acc(np.concatenate([t, np.where(rng.random((nv, 1)) < 0.5, -1.0, 1.0)], axis=1).astype(np.float32), 5126, "VEC4")
+            if rng.random() < 0.7:
+                attrs["TEXCOORD_0"] = add_acc(rng.random((nv, 2)).astype(np.float32), 5126, "VEC2")
+            prim = {"attributes": attrs}
+            kind = int(rng.integers(0, 4))
+            ntri = int(rng.integers(1, 6))
+            if kind < 3:
+                idx = rng.integers(0, nv, size=ntri * 3)
+                dt, ct = [(np.uint8, 5121), (np.uint16, 5123), (np.uint32, 5125)][kind]
+                prim["indices"] = add_acc(idx.astype(dt), ct, "SCALAR")
+            elif nv % 3:   # non-indexed needs a multiple of 3 vertices, else the reference skips the primitive: keep both cases
+                if rng.random() < 0.5:
+                    prim["attributes"]["POSITION"] = add_acc(pos[: nv - nv % 3], 5126, "VEC3")
+                    for k in ("NORMAL", "TANGENT", "TEXCOORD_0"):
+                        prim["attributes"].pop(k, None)
+            if rng.random() < 0.8: prim["material"] = int(rng.integers(0, len(materials)))
+            if rng.random() < 0.15: prim["mode"] = 1
+            if rng.random() < 0.1: del prim["attributes"]["POSITION"]
+            prims.append(prim)
+        mesh = {"primitives": prims}
+        if rng.random() < 0.8: mesh["name"] = f"part{mi}"
+        meshes.append(mesh)
+
+    def xform(node):
+        r = rng.random()
+        if r < 0.35:
+            M = np.eye(4, dtype=np.float32); M[:3, :3] = rng.normal(size=(3, 3)); M[:3, 3] = rng.normal(size=3) * 3
+            node["matrix"] = [float(v) for v in M.T.reshape(-1)]
+        elif r < 0.8:
+            if rng.random() < 0.8: node["translation"] = [float(v) for v in rng.normal(size=3) * 2]
+            if rng.random() < 0.8:
+                q = rng.normal(size=4); node["rotation"] = [float(v) for v in q / np.linalg.norm(q)]
+            if rng.random() < 0.8: node["scale"] = [float(v) for v in rng.random(3) * 2 + 0.2]
+
+    nodes = []
+    def add_node(depth):
+        node = {}
+        xform(node)
+        if rng.random() < 0.7: node["mesh"] = int(rng.integers(0, len(meshes)))
+        nodes.append(node)
+        me = len(nodes) - 1
+        if depth < 3:
+            kids = [add_node(depth + 1) for _ in range(int(rng.integers(0, 3)))]
+            if kids: nodes[me]["children"] = kids
+        return me
+    roots = [add_node(1) for _ in range(int(rng.integers(1, 3)))]
+    scenes = [{"nodes": roots}]
+    gltf = {"asset": {"version": "2.0"}, "scenes": scenes, "nodes": nodes, "meshes": meshes, "materials": materials,
+            "textures": textures, "images": images, "bufferViews": views, "accessors": accessors}
+    if rng.random() < 0.3:
+        other = add_node(1)
+        gltf["scenes"] = [{"nodes": [other]}, {"nodes": roots}]
+        gltf["scene"] = 1
+    elif rng.random() < 0.7:
+        gltf["scene"] = 0
+    binblob = b"".join(blobs)
+    gltf["buffers"] = [{"byteLength": len(binblob)}]
+    js = json.dumps(gltf).encode(); js += b" " * ((-len(js)) % 4)
+    with open(path, "wb") as f:
+        f.write(struct.pack("<4sII", b"glTF", 2, 12 + 8 + len(js) + 8 + len(binblob)))
+        f.write(struct.pack("<I4s", len(js), b"JSON")); f.write(js)
+        f.write(struct.pack("<I4s", len(binblob), b"BIN\x00")); f.write(binblob)
