@@ -227,8 +227,16 @@ constexpr uint32_t kTableSmemBytes = 24 * 1024;
 // per-triangle stage + rasteriser set-up.  t4: 9 float4 in shared memory.
 // Returns the number of candidate pixels (0 => nothing to rasterise).
 // ------------------------------------------------------------------------------------------
+// M2S_INLINE_SETUP (tuning build, off): inline the per-triangle stage into the unit loop — the raster state then lives
+// in registers instead of going through local memory (the default build shows 36 STL / 28 LDL around the call) — and
+// keep one out-of-line copy for the drain path.  Inlined at both sites it was 90 KB of code, hence the split.
+#ifdef M2S_INLINE_SETUP
+#define M2S_SETUP_QUAL __forceinline__
+#else
+#define M2S_SETUP_QUAL __noinline__
+#endif
 template <int LAYOUT>
-__device__ __noinline__ uint32_t setup_triangle(const float4* __restrict__ t4, uint32_t tri_global, const ConvertArgs& a,
+__device__ M2S_SETUP_QUAL uint32_t setup_triangle(const float4* __restrict__ t4, uint32_t tri_global, const ConvertArgs& a,
                                    const Tables& tb, TriRaster& tr, TriFragT<Cfg<LAYOUT>::kMaps>& tf) {
     using C = Cfg<LAYOUT>;
     tr.w = 0; tr.h = 0; tr.x0 = 0; tr.y0 = 0; tr.incl = 0; tr.inv_area = 0.f;
@@ -410,6 +418,16 @@ __device__ __noinline__ uint32_t setup_triangle(const float4* __restrict__ t4, u
     tf.meta = share | ((unsigned)x0 << 4) | ((unsigned)y0 << 16);
     return (uint32_t)tr.w * (uint32_t)tr.h;
 }
+#ifdef M2S_INLINE_SETUP
+template <int LAYOUT>
+__device__ __noinline__ uint32_t setup_triangle_outofline(const float4* __restrict__ t4, uint32_t tri_global, const ConvertArgs& a,
+                                                          const Tables& tb, TriRaster& tr, TriFragT<Cfg<LAYOUT>::kMaps>& tf) {
+    return setup_triangle<LAYOUT>(t4, tri_global, a, tb, tr, tf);
+}
+#define M2S_SETUP_DRAIN setup_triangle_outofline
+#else
+#define M2S_SETUP_DRAIN setup_triangle
+#endif
 
 // ------------------------------------------------------------------------------------------
 // sampler: RGBA8 unorm, REPEAT, bilinear within a level, linear between levels
@@ -783,7 +801,7 @@ __global__ void __launch_bounds__(Cfg<LAYOUT>::kWarps * 32) __maxnreg__(Cfg<LAYO
         TriRaster tr;
         tr.w = 1; tr.h = 0; tr.x0 = 0; tr.y0 = 0; tr.incl = 0;
         tr.A[0] = tr.A[1] = tr.A[2] = tr.B[0] = tr.B[1] = tr.B[2] = 0; tr.C[0] = tr.C[1] = tr.C[2] = 0;
-        if (lane == 0) c = setup_triangle<LAYOUT>(wb.tri, item.x, a, tabs, tr, wb.frag[0]);
+        if (lane == 0) c = M2S_SETUP_DRAIN<LAYOUT>(wb.tri, item.x, a, tabs, tr, wb.frag[0]);
         c = __shfl_sync(0xffffffffu, c, 0);
         __syncwarp();
         const unsigned long long tc = TNOW();
