@@ -464,3 +464,28 @@ def test_glb_loader_survives_corrupt_files():
     import fuzz_loader
     ok, msg = fuzz_loader.run(0, 600)
     assert ok, msg
+
+
+def test_every_entry_point_rejects_null_arguments_with_a_status():
+    """Error behaviour of the boundary: integer status + thread-local message, never a crash (the reference prints
+    to std::cerr and carries on, or exit(1)s — SURVEY 8b)."""
+    from mesh2splat_b200 import _lib
+    L = _lib.lib()
+    INV = _abi.M2S_E_INVALID
+    assert L.m2s_ply_write(None, None, 0, 0, C.c_float(1.0)) == INV
+    assert L.m2s_ply_write(b"/tmp/never_written.ply", None, 5, 0, C.c_float(1.0)) == INV
+    small = C.create_string_buffer(16)
+    need = L.m2s_ply_header(0, 10, small, 16)
+    assert need > 16 and L.m2s_ply_header(0, 10, None, 0) == need   # returns the size needed, writes at most cap bytes
+    h = C.c_void_p(0)
+    assert L.m2s_glb_load(None, 1, C.byref(h)) == INV and L.m2s_glb_load(b"/nonexistent.glb", 1, None) == INV
+    assert not L.m2s_hscene_view(None) and L.m2s_hscene_primitive_name(None, 0) == b""
+    L.m2s_hscene_free(None); L.m2s_ctx_destroy(None); L.m2s_scene_free(None, None)
+    assert L.m2s_record_stride(99) == 0 and L.m2s_status_string(99) == b"unknown"
+    assert L.m2s_compute_bboxes(None, None, 3, 1) == INV
+    assert L.m2s_ctx_create(0, None) == INV
+    assert L.m2s_convert(None, None, None, None, 0, None, None) == INV
+    assert L.m2s_convert_host(None, None, None, None, 0, None, None) == INV
+    assert L.m2s_convert_file(None, None, 64, C.c_float(0.65), 0, None, None) == INV
+    assert L.m2s_scene_upload(None, None, None) == INV
+    assert b"NULL" in L.m2s_last_error()
