@@ -930,6 +930,19 @@ __global__ void __launch_bounds__(M2S_FRAG_THREADS) fragment_kernel(const __grid
             const uint2 fid = __ldg(a.frag_ids + wbase + lane);
             const uint32_t tl = fid.x - a.tri_first;
             const int py = (fid.y >> 12) & 0xfff, px = fid.y & 0xfff;
+#ifdef M2S_FRAG_PREFETCH
+            // Tuning build (off): the stall samples of this kernel sit on four serial load waits — fragment id ->
+            // triangle record -> vertices -> texels (profiles/r01_fragment_kernel_*.md: 14.8 + 13.2 + 16.6 + 10.3 % of
+            // the samples).  Pull the position vertices (read last, after the texel loads were issued) into L1 as soon
+            // as the triangle is known, and the next iteration's fragment ids while this one is shaded.
+            {
+                const float4* pv = a.tris + (size_t)fid.x * 9;
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(pv));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(pv + 3));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(pv + 6));
+                if ((g + nwarps) * 32 < n) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.frag_ids + (g + nwarps) * 32 + lane));
+            }
+#endif
             const TriFragT<C::kMaps> tf = *reinterpret_cast<const TriFragT<C::kMaps>*>(a.tri_frag + (size_t)tl * sizeof(TriFragT<C::kMaps>));
             const unsigned meta = tf.meta;
             const int dxi = px - (int)((meta >> 4) & 0xfffu), dyi = py - (int)((meta >> 16) & 0xfffu);
