@@ -39,6 +39,7 @@ from mesh2splat_b200 import _abi, synth  # noqa: E402
 
 DENSITY = 512
 WORKLOAD = "helmet_standin"  # BASELINE.json configs[1] (SciFiHelmet.glb stand-in)
+WORKLOAD_DEFAULT = WORKLOAD
 # workload -> (scene factory, BASELINE density); only the default is the judged bench line
 WORKLOADS = {"helmet_standin": (lambda: synth.helmet_standin(2048), 512),
              "sphere_1m": (lambda: synth.sphere_1m(2048), 256),
@@ -79,6 +80,27 @@ def profiled_traffic(layout_name: str):
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             return json.load(f).get(layout_name)
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def profiled_launch_shares():
+    """Share of the step per kernel from the committed ncu launch list of this same command (serialised, cold cache):
+    the full-size launches only (the later, shorter ones belong to the pipelined e2e leg).  None if unavailable."""
+    try:
+        import csv
+        with open(os.path.join(ROOT, "profiles", "r01_launches_bench.csv")) as f:
+            rows = [r for r in csv.reader(f) if len(r) > 5]
+        hdr = rows[0]
+        ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+        seq = [(r[ki], float(r[vi].replace(",", "")) / 1e3) for r in rows[1:] if "raster_kernel" in r[ki] or "fragment_kernel" in r[ki]]
+        ras = [v for k, v in seq[:12] if "raster_kernel" in k]
+        frag = [v for k, v in seq[:12] if "fragment_kernel" in k]
+        if not ras or not frag:
+            return None
+        a, b = sum(ras) / len(ras), sum(frag) / len(frag)
+        return {"raster_kernel_us": round(a, 2), "fragment_kernel_us": round(b, 2), "raster_share": round(a / (a + b), 3),
+                "fragment_share": round(b / (a + b), 3), "source": "profiles/r01_launches_bench.csv (ncu, serialised, cold cache, PACKED56)"}
     except Exception:  # noqa: BLE001
         return None
 
@@ -335,6 +357,8 @@ def run_ours(args):
         roofline = {"bound": "hbm", "kernel": "m2s::raster_kernel + m2s::fragment_kernel (the whole step)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": profiled_traffic(args.layout), "algorithmic_bytes": alg,
                     "kernel_ms": kernel_ms, "peak_source": peak_src}
+        if args.layout == "packed56" and args.workload == WORKLOAD_DEFAULT:
+            roofline["launch_shares"] = profiled_launch_shares()
         # ---- CPU baseline on a bounded sample (the whole workload, a few repeats); N = 1 only ----
         cpu = None
         if world == 1:
