@@ -1,7 +1,6 @@
 """Mutation fuzz of m2s_glb_load: corrupt golden .glb fixtures (bit flips, truncation, length-field edits) and load
 them in a child process; any crash (signal) is reported with the seed that reproduces it."""
-import os, subprocess, sys, tempfile
-import numpy as np
+import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CHILD = r'''
 import sys, numpy as np

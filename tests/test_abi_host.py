@@ -458,7 +458,6 @@ def test_glb_loader_survives_corrupt_files():
     """600 deterministic mutants (bit flips, truncations, clobbered length fields, byte swaps) of the golden .glb
     files, loaded in a child process: every one must end in a status code — never a crash.  (scripts/fuzz_loader.py
     runs the same mutation engine at scale; the decoder was also run under ASan/UBSan on 40 k mutants.)"""
-    import subprocess
     import sys
     sys.path.insert(0, os.path.join(ROOT, "scripts"))
     import fuzz_loader
