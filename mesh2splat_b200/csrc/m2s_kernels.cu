@@ -518,8 +518,13 @@ __device__ __forceinline__ void enqueue(const ConvertArgs& a, WarpBlock<LAYOUT>&
 }
 
 // warp-per-triangle coverage of candidates [c0, c1) of the triangle in `slot` (int64 edge functions)
+#ifdef M2S_INLINE_RASTER  // tuning build (off): with the set-up inlined too, the raster state never needs an address
+#define M2S_RASTER_QUAL __forceinline__
+#else
+#define M2S_RASTER_QUAL
+#endif
 template <int LAYOUT>
-__device__ void raster_one(const ConvertArgs& a, WarpBlock<LAYOUT>& wb, uint32_t& qn, uint32_t slot, uint32_t c0, uint32_t c1,
+__device__ M2S_RASTER_QUAL void raster_one(const ConvertArgs& a, WarpBlock<LAYOUT>& wb, uint32_t& qn, uint32_t slot, uint32_t c0, uint32_t c1,
                            int lane, const TriRaster& mine) {
     // the raster state lives in the registers of lane `slot`: broadcast it
     const unsigned full = 0xffffffffu;
