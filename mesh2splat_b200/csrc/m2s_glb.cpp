@@ -65,6 +65,15 @@ struct JValue {
     int as_int(int dflt) const { return type == Number ? (int)num : dflt; }
     double as_num(double dflt) const { return type == Number ? num : dflt; }
     int get_int(const char* key, int dflt) const { const JValue* v = get(key); return v ? v->as_int(dflt) : dflt; }
+    // byte offsets / lengths / element counts: non-negative integers below 2^53, anything else is malformed
+    // (a negative double cast to size_t wraps and defeats every later range check)
+    uint64_t get_size(const char* key, uint64_t dflt) const {
+        const JValue* v = get(key);
+        if (!v) return dflt;
+        if (v->type != Number || !(v->num >= 0.0) || v->num > 9007199254740992.0 || v->num != std::floor(v->num))
+            throw FormatError(std::string("'") + key + "' is not a non-negative integer");
+        return (uint64_t)v->num;
+    }
     std::string get_str(const char* key) const { const JValue* v = get(key); return (v && v->type == String) ? v->str : std::string(); }
     size_t size() const { return type == Array ? arr.size() : 0; }
 };
@@ -928,11 +937,12 @@ AccessorView accessor(const Glb& g, int index) {
     if (!bvs || bv < 0 || (size_t)bv >= bvs->size()) throw FormatError("accessor without bufferView (sparse accessors unsupported)");
     const JValue& v = bvs->arr[bv];
     if (v.get_int("buffer", 0) != 0) throw FormatError("only the GLB-embedded buffer 0 is supported");
-    const size_t off = (size_t)v.get_int("byteOffset", 0) + (size_t)a.get_int("byteOffset", 0);
-    if (off > g.bin_size) throw FormatError("accessor offset beyond the BIN chunk");
+    const uint64_t off_v = v.get_size("byteOffset", 0), off_a = a.get_size("byteOffset", 0);
+    if (off_v > g.bin_size || off_a > g.bin_size - off_v) throw FormatError("accessor offset beyond the BIN chunk");
+    const size_t off = (size_t)(off_v + off_a);
     AccessorView r;
     r.data = g.bin + off; r.avail = g.bin_size - off;
-    r.count = (size_t)a.get_int("count", 0);
+    r.count = (size_t)a.get_size("count", 0);
     r.componentType = a.get_int("componentType", 0);
     r.type = a.get_str("type");
     return r;
@@ -944,7 +954,7 @@ AccessorView accessor(const Glb& g, int index) {
 const float* float_array(const Glb& g, int acc, int comps, size_t* count, std::vector<float>& holder) {
     const AccessorView v = accessor(g, acc);
     if (v.componentType != 5126) throw FormatError("vertex attribute is not FLOAT (normalised integer attributes unsupported, as in the reference)");
-    if (v.count * comps * sizeof(float) > v.avail) throw FormatError("vertex attribute exceeds the BIN chunk");
+    if (v.count > v.avail / (comps * sizeof(float))) throw FormatError("vertex attribute exceeds the BIN chunk");
     *count = v.count;
     if (reinterpret_cast<uintptr_t>(v.data) & 3u) {
         holder.resize(v.count * comps);
@@ -1059,8 +1069,8 @@ M2S_EXPORT m2s_status m2s_glb_load(const char* path, int cumulative_bbox, m2s_hs
             const JValue* bvs = g.json.get("bufferViews");
             if (bv < 0 || !bvs || (size_t)bv >= bvs->size()) throw FormatError("image without bufferView (external uri images unsupported in .glb)");
             const JValue& v = bvs->arr[bv];
-            const size_t off = (size_t)v.get_int("byteOffset", 0), len = (size_t)v.get_int("byteLength", 0);
-            if (off + len > g.bin_size) throw FormatError("image exceeds the BIN chunk");
+            const uint64_t off = v.get_size("byteOffset", 0), len = v.get_size("byteLength", 0);
+            if (off > g.bin_size || len > g.bin_size - off) throw FormatError("image exceeds the BIN chunk");
             sl.data = g.bin + off; sl.len = len;
         };
         {
@@ -1150,10 +1160,10 @@ M2S_EXPORT m2s_status m2s_glb_load(const char* path, int cumulative_bbox, m2s_hs
                 const int ia = pr.get_int("indices", -1);
                 if (ia >= 0) {
                     const AccessorView iv = accessor(g, ia);
-                    indices.resize(iv.count);
                     const size_t es = iv.componentType == 5123 ? 2 : (iv.componentType == 5125 ? 4 : (iv.componentType == 5121 ? 1 : 0));
                     if (!es) continue;  // unsupported index type: primitive skipped (:336-339)
-                    if (iv.count * es > iv.avail) throw FormatError("index accessor exceeds the BIN chunk");
+                    if (iv.count > iv.avail / es) throw FormatError("index accessor exceeds the BIN chunk");
+                    indices.resize(iv.count);  // only after the count is known to fit the BIN chunk
                     for (size_t i = 0; i < iv.count; ++i) {
                         if (es == 2) { uint16_t v; std::memcpy(&v, iv.data + 2 * i, 2); indices[i] = v; }
                         else if (es == 4) { uint32_t v; std::memcpy(&v, iv.data + 4 * i, 4); indices[i] = v; }
@@ -1237,6 +1247,9 @@ M2S_EXPORT m2s_status m2s_glb_load(const char* path, int cumulative_bbox, m2s_hs
     } catch (const std::bad_alloc&) {
         m2s::set_error("Failed to load glTF: out of memory");
         return M2S_E_IO;
+    } catch (const std::exception& e) {  // nothing may cross the extern "C" boundary
+        m2s::set_error(std::string("Failed to load glTF: ") + e.what());
+        return M2S_E_FORMAT;
     }
     hs->view.triangles = hs->triangles.data();
     hs->view.triangle_count = hs->triangles.size() / M2S_FLOATS_PER_TRIANGLE;
@@ -1263,7 +1276,12 @@ M2S_EXPORT m2s_status m2s_convert_file(m2s_ctx* ctx, const char* glb_path, uint3
     p.layout = M2S_LAYOUT_PLY_STANDARD + ply_format;  // rows are encoded on the GPU and streamed to disk
     m2s_result r;
     std::memset(&r, 0, sizeof(r));
-    st = m2s::convert_scene_to_ply(ctx, &hs->view, &p, ply_path, &r);
+    try {
+        st = m2s::convert_scene_to_ply(ctx, &hs->view, &p, ply_path, &r);
+    } catch (const std::exception& e) {  // nothing may cross the extern "C" boundary
+        m2s::set_error(std::string("m2s_convert_file: ") + e.what());
+        st = M2S_E_IO;
+    }
     m2s_hscene_free(hs);
     if (result) *result = r;
     return st;

@@ -14,7 +14,7 @@ d = tempfile.mkdtemp()
 for seed in range(seed0, seed0 + count):
     rng = np.random.default_rng(seed)
     blob = bytearray(g[names[seed %% len(names)] + "/glb"].tobytes())
-    kind = seed %% 4
+    kind = seed %% 5
     if kind == 0:
         for _ in range(int(rng.integers(1, 8))):
             blob[int(rng.integers(0, len(blob)))] ^= 1 << int(rng.integers(0, 8))
@@ -23,6 +23,20 @@ for seed in range(seed0, seed0 + count):
     elif kind == 2:
         i = int(rng.integers(0, max(1, len(blob) - 4)))
         blob[i:i + 4] = int(rng.integers(0, 2**32)).to_bytes(4, "little")
+    elif kind == 4:
+        # JSON-level: replace one numeric literal of the JSON chunk by a hostile value (negative, huge, fractional);
+        # keeps the chunk length by padding/truncating with spaces when possible (ADVICE r1: negative byteOffset)
+        import re, struct
+        jlen = struct.unpack_from("<I", blob, 12)[0]
+        js = bytes(blob[20:20 + jlen])
+        nums = list(re.finditer(rb"(?<=[:\[,\s])-?\d+(\.\d+)?", js))
+        if nums:
+            m = nums[int(rng.integers(0, len(nums)))]
+            bad = [b"-1", b"-3", b"-1000000", b"2147483648", b"1e300", b"0.5", b"-0.5", b"1099511627776"][int(rng.integers(0, 8))]
+            js2 = js[:m.start()] + bad + js[m.end():]
+            js2 += b" " * ((-len(js2)) %% 4)
+            rest = bytes(blob[20 + jlen:])
+            blob = bytearray(struct.pack("<4sII", b"glTF", 2, 20 + len(js2) + len(rest)) + struct.pack("<I4s", len(js2), b"JSON") + js2 + rest)
     else:
         i = int(rng.integers(0, len(blob))); j = int(rng.integers(0, len(blob)))
         blob[i], blob[j] = blob[j], blob[i]

@@ -259,6 +259,61 @@ def test_glb_loader_errors(tmp_path):
     assert SceneManager(_RC()).loadModel(str(bad)) is False
 
 
+def _rewrite_glb_json(src: str, dst: str, edit) -> None:
+    """Re-serialise a .glb after `edit(gltf_dict)` changed its JSON chunk (BIN chunk untouched)."""
+    raw = open(src, "rb").read()
+    jlen = struct.unpack_from("<I", raw, 12)[0]
+    g = json.loads(raw[20:20 + jlen])
+    edit(g)
+    js = json.dumps(g).encode(); js += b" " * ((-len(js)) % 4)
+    rest = raw[20 + jlen:]
+    with open(dst, "wb") as f:
+        f.write(struct.pack("<4sII", b"glTF", 2, 12 + 8 + len(js) + len(rest)))
+        f.write(struct.pack("<I4s", len(js), b"JSON")); f.write(js); f.write(rest)
+
+
+_HOSTILE = [-1, -3, -1000000, 2**31, 2**40, 2**63, 1e300, 0.5, -0.5]
+
+
+def test_glb_loader_rejects_hostile_sizes(tmp_path):
+    """negative / huge / fractional byteOffset, byteLength and count must come back as a format error —
+    not wrap through size_t into an out-of-bounds read, not throw std::length_error across the C boundary.
+    Loaded in a child process so that a crash is a test failure, not the end of the test run."""
+    import subprocess
+    import sys as _sys
+    base = tmp_path / "base.glb"
+    _make_glb(str(base))
+    cases = []
+    for i, bad in enumerate(_HOSTILE):
+        def e_img_off(g, bad=bad): g["bufferViews"][g["images"][0]["bufferView"]]["byteOffset"] = bad
+        def e_img_len(g, bad=bad): g["bufferViews"][g["images"][0]["bufferView"]]["byteLength"] = bad
+        def e_img_wrap(g, bad=bad):
+            v = g["bufferViews"][g["images"][0]["bufferView"]]
+            v["byteOffset"] = -1000000; v["byteLength"] = 1000016
+        def e_idx_count(g, bad=bad): g["accessors"][g["meshes"][0]["primitives"][0]["indices"]]["count"] = bad
+        def e_pos_count(g, bad=bad): g["accessors"][g["meshes"][0]["primitives"][0]["attributes"]["POSITION"]]["count"] = bad
+        def e_acc_off(g, bad=bad): g["accessors"][g["meshes"][0]["primitives"][0]["attributes"]["POSITION"]]["byteOffset"] = bad
+        def e_view_off(g, bad=bad): g["bufferViews"][0]["byteOffset"] = bad
+        for j, ed in enumerate((e_img_off, e_img_len, e_img_wrap, e_idx_count, e_pos_count, e_acc_off, e_view_off)):
+            p = tmp_path / f"h_{i}_{j}.glb"
+            _rewrite_glb_json(str(base), str(p), ed)
+            cases.append(str(p))
+    child = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from mesh2splat_b200.gltf import load_glb\n"
+        "n = 0\n"
+        "for p in sys.argv[1:]:\n"
+        "    try:\n"
+        "        load_glb(p)\n"
+        "    except ValueError:\n"
+        "        n += 1\n"
+        "print('rejected', n, 'of', len(sys.argv) - 1)\n"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([_sys.executable, "-c", child, *cases], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, f"loader crashed (rc {r.returncode}): {r.stderr[-400:]}"
+    assert r.stdout.strip() == f"rejected {len(cases)} of {len(cases)}", r.stdout
+
+
 def _glb_with_image(path, blob: bytes, mime: str):
     """Single-triangle .glb whose baseColorTexture is `blob`."""
     pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32).tobytes()
