@@ -48,8 +48,7 @@ struct m2s_ctx {
     uint32_t* d_sched = nullptr;             // 8 x 128 B (one scheduler word per cache line)
     unsigned long long* d_counter = nullptr; // running fragment counter
     unsigned long long* d_total = nullptr;   // published count
-    uint2* d_queue = nullptr;
-    uint32_t queue_cap = 1u << 20;
+    uint32_t* d_nitems = nullptr;            // work items queued by the last raster launch
     unsigned long long* h_total = nullptr;   // pinned
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // convert_host pipeline: a second stream for the downloads, per-chunk counts and events
@@ -62,17 +61,18 @@ struct m2s_ctx {
     static constexpr size_t kStageBytes = 32u << 20;
     unsigned char* h_stage[2] = {nullptr, nullptr};
     cudaEvent_t ev_chunk[kMaxChunks] = {};
-    int blocks_per_sm[2] = {0, 0};       // raster kernel (persistent)
-    int frag_blocks_per_sm[2] = {0, 0};  // fragment kernel
+    static constexpr int kLayouts = 5;
+    int blocks_per_sm[kLayouts] = {};       // raster kernel (persistent)
+    int frag_blocks_per_sm[kLayouts] = {};  // fragment kernel
     unsigned long long epoch = 0;            // pairs up the ranks' calls of the fused gather
     bool dirty = true;                       // scheduler state needs a memset before the next launch
     // scratch owned by the context (grown on demand)
-    void* d_scratch = nullptr;  size_t scratch_bytes = 0;   // REF96 staging for the .ply row layouts
     void* d_out = nullptr;      size_t out_bytes = 0;       // convert_host output
     unsigned long long* d_keys = nullptr; size_t keys_bytes = 0;
     // intermediates between the raster and the fragment kernel
-    void* d_ids = nullptr;      size_t ids_bytes = 0;       // uint2 per fragment
-    void* d_trifrag = nullptr;  size_t trifrag_bytes = 0;   // TriFragT per triangle of the shard
+    void* d_trifrag = nullptr;  size_t trifrag_bytes = 0;   // TriRec per triangle of the shard
+    void* d_units = nullptr;    size_t units_bytes = 0;     // UnitDesc per work unit
+    void* d_items = nullptr;    size_t items_bytes = 0;     // FragItem queue
 };
 
 struct m2s_dscene {
@@ -92,12 +92,16 @@ struct m2s_dscene {
 static unsigned long long* g_trace = nullptr;  // debugging aid for M2S_TRACE builds (scripts/trace_raster.py)
 extern "C" __attribute__((visibility("default"))) void m2s_debug_set_trace(void* p) { g_trace = (unsigned long long*)p; }
 
-static m2s_status grow(m2s_ctx* ctx, void** p, size_t* have, size_t need) {
+// Context scratch grows on the stream that will USE it: the free of the old block is ordered after the kernels
+// already enqueued there, the new block is ready before the next one.  (A caller that alternates between streams
+// without synchronising them must not share one context: documented in m2s.h.)
+static m2s_status grow(m2s_ctx* ctx, void** p, size_t* have, size_t need, cudaStream_t stream = nullptr) {
     if (*have >= need) return M2S_OK;
-    if (*p) CUDA_TRY(cudaFreeAsync(*p, ctx->stream));
+    if (!stream) stream = ctx->stream;
+    if (*p) CUDA_TRY(cudaFreeAsync(*p, stream));
     *p = nullptr; *have = 0;
-    CUDA_TRY(cudaMallocAsync(p, need, ctx->stream));
-    *have = need;
+    CUDA_TRY(cudaMallocAsync(p, need + need / 4, stream));  // 25 % head room: density sweeps do not reallocate at every step
+    *have = need + need / 4;
     return M2S_OK;
 }
 
@@ -166,7 +170,7 @@ M2S_EXPORT m2s_status m2s_ctx_create(int device, m2s_ctx** out) {
     CUDA_TRY(cudaMalloc(&c->d_sched, 8 * 128));
     CUDA_TRY(cudaMalloc(&c->d_counter, sizeof(unsigned long long)));
     CUDA_TRY(cudaMalloc(&c->d_total, sizeof(unsigned long long)));
-    CUDA_TRY(cudaMalloc(&c->d_queue, (size_t)c->queue_cap * sizeof(uint2)));
+    CUDA_TRY(cudaMalloc(&c->d_nitems, sizeof(uint32_t)));
     CUDA_TRY(cudaMallocHost(&c->h_total, sizeof(unsigned long long)));
     CUDA_TRY(cudaEventCreate(&c->ev0));
     CUDA_TRY(cudaEventCreate(&c->ev1));
@@ -175,7 +179,7 @@ M2S_EXPORT m2s_status m2s_ctx_create(int device, m2s_ctx** out) {
     CUDA_TRY(cudaHostAlloc(&c->h_chunk_tot, 2 * m2s_ctx::kMaxChunks * sizeof(unsigned long long), cudaHostAllocMapped));
     std::memset(c->h_chunk_tot, 0, 2 * m2s_ctx::kMaxChunks * sizeof(unsigned long long));
     for (int i = 0; i < m2s_ctx::kMaxChunks; ++i) CUDA_TRY(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
-    for (int l = 0; l < 2; ++l) {
+    for (int l = 0; l < m2s_ctx::kLayouts; ++l) {
         CUDA_TRY(convert_configure(l, &c->blocks_per_sm[l], &c->frag_blocks_per_sm[l]));
         if (c->blocks_per_sm[l] < 1 || c->frag_blocks_per_sm[l] < 1) { set_error("conversion kernel does not fit on this device"); return M2S_E_CUDA; }
     }
@@ -187,13 +191,13 @@ M2S_EXPORT void m2s_ctx_destroy(m2s_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    if (c->d_scratch) cudaFreeAsync(c->d_scratch, c->stream);
     if (c->d_out) cudaFreeAsync(c->d_out, c->stream);
     if (c->d_keys) cudaFreeAsync(c->d_keys, c->stream);
-    if (c->d_ids) cudaFreeAsync(c->d_ids, c->stream);
     if (c->d_trifrag) cudaFreeAsync(c->d_trifrag, c->stream);
+    if (c->d_units) cudaFreeAsync(c->d_units, c->stream);
+    if (c->d_items) cudaFreeAsync(c->d_items, c->stream);
     cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_sched); cudaFree(c->d_counter); cudaFree(c->d_total); cudaFree(c->d_queue);
+    cudaFree(c->d_sched); cudaFree(c->d_counter); cudaFree(c->d_total); cudaFree(c->d_nitems);
     cudaFreeHost(c->h_total);
     cudaFree(c->d_chunk_tot); cudaFreeHost(c->h_chunk_tot);
     for (int i = 0; i < 2; ++i) if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
@@ -392,18 +396,28 @@ static m2s_status convert_enqueue_impl(m2s_ctx* ctx, const m2s_dscene* s, const 
     CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : ctx->stream;
     const uint64_t cap = effective_cap(s, p, out_capacity);
-    const bool ply_rows = p->layout >= M2S_LAYOUT_PLY_STANDARD;
-    const int klayout = ply_rows ? 0 : (int)p->layout;
+    const int klayout = (int)p->layout;  // every layout, the .ply rows included, is written by the fragment kernel itself
     void* kout = d_out;
-    if (ply_rows) {  // REF96 into scratch, then the row encoder
-        m2s_status st = grow(ctx, &ctx->d_scratch, &ctx->scratch_bytes, std::max<uint64_t>(cap, 1) * 96);
-        if (st != M2S_OK) return st;
-        kout = ctx->d_scratch;
-    }
     if (reinterpret_cast<uintptr_t>(kout) & 15u) { set_error("m2s_convert: the output buffer must be 16-byte aligned"); return M2S_E_INVALID; }
+    const int grid = ctx->sm_count * ctx->blocks_per_sm[klayout];
+    // work-unit size: as large as 32 triangles, but small enough that every warp of the grid gets the
+    // same number of units (a 70 k-triangle mesh is only ~1 unit of 32 per resident warp)
+    uint64_t unit_tris, n_units;
+    {
+        const uint64_t warps = (uint64_t)grid * convert_warps_per_cta(klayout);
+        const uint64_t rounds = std::max<uint64_t>(1, (count + warps * kUnitTris - 1) / (warps * kUnitTris));
+        unit_tris = (count + warps * rounds - 1) / (warps * rounds);
+        unit_tris = std::min<uint64_t>(std::max<uint64_t>(unit_tris, 1), kUnitTris);
+        n_units = (count + unit_tris - 1) / unit_tris;
+    }
+    // item queue: an item takes a slot only if it starts below the cap, and live items cover disjoint output
+    // ranges: at most one end-of-unit item per unit, cap/32 items closed by 32 non-empty blocks, cap/1024 closed by
+    // their fragment count, cap/2048 pieces of oversized blocks — the queue cannot overflow
+    const uint64_t queue_cap = std::min<uint64_t>(n_units + cap / 32 + cap / kFlushFrags + cap / kItemMaxFrags + 64, 0x7fffffffu);
     {   // scratch between the two kernels (grown on demand, kept by the context)
-        m2s_status st = grow(ctx, &ctx->d_ids, &ctx->ids_bytes, std::max<uint64_t>(cap, 1) * sizeof(uint2));
-        if (st == M2S_OK) st = grow(ctx, &ctx->d_trifrag, &ctx->trifrag_bytes, std::max<uint64_t>(count, 1) * tri_frag_bytes(klayout));
+        m2s_status st = grow(ctx, &ctx->d_trifrag, &ctx->trifrag_bytes, std::max<uint64_t>(count, 1) * tri_frag_bytes(klayout), stream);
+        if (st == M2S_OK) st = grow(ctx, &ctx->d_units, &ctx->units_bytes, std::max<uint64_t>(n_units, 1) * sizeof(UnitDesc), stream);
+        if (st == M2S_OK) st = grow(ctx, &ctx->d_items, &ctx->items_bytes, queue_cap * sizeof(FragItem), stream);
         if (st != M2S_OK) return st;
     }
     if (ctx->dirty) {
@@ -424,8 +438,11 @@ static m2s_status convert_enqueue_impl(m2s_ctx* ctx, const m2s_dscene* s, const 
     a.half_R = (float)p->resolution * 0.5f;
     a.mult = p->gaussian_std / (float)p->resolution;
     a.log_sz = logf(1e-7f * a.mult);
-    a.frag_ids = (uint2*)ctx->d_ids;
     a.tri_frag = (unsigned char*)ctx->d_trifrag;
+    a.unit_desc = (UnitDesc*)ctx->d_units;
+    a.items = (FragItem*)ctx->d_items;
+    a.queue_cap = (uint32_t)queue_cap;
+    a.n_items_out = ctx->d_nitems;
     a.out = (uint8_t*)kout;
     a.cap = cap;
     a.keys = (unsigned long long*)d_keys;
@@ -437,18 +454,8 @@ static m2s_status convert_enqueue_impl(m2s_ctx* ctx, const m2s_dscene* s, const 
     a.host_total = host_total;
     a.host_tag = host_tag;
     a.sched = ctx->d_sched;
-    const int grid = ctx->sm_count * ctx->blocks_per_sm[klayout];
-    {   // work-unit size: as large as 32 triangles, but small enough that every warp of the grid gets the
-        // same number of units (a 70 k-triangle mesh is only ~1 unit of 32 per resident warp)
-        const uint64_t warps = (uint64_t)grid * convert_warps_per_cta(klayout);
-        const uint64_t rounds = std::max<uint64_t>(1, (count + warps * kUnitTris - 1) / (warps * kUnitTris));
-        uint64_t unit = (count + warps * rounds - 1) / (warps * rounds);
-        unit = std::min<uint64_t>(std::max<uint64_t>(unit, 1), kUnitTris);
-        a.unit_tris = (uint32_t)unit;
-        a.n_units = (uint32_t)((count + unit - 1) / unit);
-    }
-    a.queue = ctx->d_queue;
-    a.queue_cap = ctx->queue_cap;
+    a.unit_tris = (uint32_t)unit_tris;
+    a.n_units = (uint32_t)n_units;
     a.trace = g_trace;
     if (peers && peers->world > 1) {
         a.world = peers->world; a.rank = peers->rank;
@@ -462,11 +469,6 @@ static m2s_status convert_enqueue_impl(m2s_ctx* ctx, const m2s_dscene* s, const 
     if (peers && peers->world > 1)
         CUDA_TRY(gather_wait_launch((const unsigned long long*)peers->xch[peers->rank], peers->world, a.epoch, out_capacity,
                                     (unsigned long long*)d_total, stream));
-    if (ply_rows) {
-        // the count is only known on the device here: the encoder reads it and stops at min(cap, total)
-        const uint32_t fmt = p->layout - M2S_LAYOUT_PLY_STANDARD;
-        CUDA_TRY(ply_rows_launch(ctx->d_scratch, cap, a.total_out, fmt, a.mult, d_out, stream));
-    }
     return M2S_OK;
 }
 

@@ -8,12 +8,37 @@ namespace m2s {
 constexpr int kMaxPeers = 8;             // GPUs of one NVSwitch domain
 constexpr int kMaxLevels = 5;            // levels 0..4 (GL_TEXTURE_MAX_LEVEL 4, glUtils.cpp:313)
 constexpr int kUnitTris = 32;            // max triangles per work unit (one lane per triangle)
-constexpr int kQueue = 512;              // fragment ids compacted per warp before a flush
 constexpr int kTriBytes = 144;           // 36 floats
-constexpr uint32_t kSmallCand = 64;      // <= this many candidate pixels: lane-per-triangle raster
-constexpr uint32_t kBigCand = 1024;      // > this many: deferred, split into chunks over all warps
-constexpr uint32_t kChunkCand = 512;     // candidates per deferred work item
+constexpr uint32_t kSmallCand = 64;      // <= this many candidate pixels (and <= 32 rows): coverage as a 64-bit mask
+constexpr int kItemBlocks = 32;          // row blocks (<= 32 pixel rows of one triangle) per fragment work item
+constexpr uint32_t kFlushFrags = 1024;   // a warp's pending row blocks become one item once they hold this many fragments
+constexpr uint32_t kItemMaxFrags = 2048; // a single row block with more fragments is cut into items of this size
 constexpr float kGuard = 8192.0f;        // window-coordinate guard band (|xw| beyond -> triangle dropped)
+
+// ---- raster_kernel -> fragment_kernel interface (context-owned scratch, L2-resident at the sizes of interest) ----
+// The raster kernel only COUNTS: per triangle it leaves a record (TriRec, m2s_kernels.cu) holding the exact edge
+// functions, the shading constants and — for small triangles — the 64-bit coverage mask of the candidate box; the
+// fragment kernel enumerates the covered pixels itself (mask rows / exact row spans, m2s_span.cuh).
+// Work of the fragment kernel = n_units "unit items" (the small triangles of one work unit, UnitDesc) followed by
+// the queued FragItems (row blocks of the larger triangles of one unit).
+struct UnitDesc {               // 16 B per work unit
+    unsigned long long first;   // output index (this launch) of the unit's first small-triangle fragment
+    uint32_t total;             // fragments of the unit's small triangles (triangle-major, TriRec::first = prefix)
+    uint32_t pad;
+};
+struct BlockRef {               // <= 32 consecutive pixel rows of one triangle
+    uint32_t prefix;            // fragments of the item before this block
+    uint32_t ref;               // slot in the unit (5 bits) | first row relative to the box (12) << 5 | rows (6) << 17
+};
+struct FragItem {               // 288 B
+    unsigned long long first;   // output index (this launch) of fragment 0 of the item
+    uint32_t unit;              // work unit the blocks' triangles belong to
+    uint32_t nblocks;
+    uint32_t frag_begin, frag_end;  // fragments [frag_begin, frag_end) of the item are this item's work
+    uint32_t pad[2];
+    BlockRef blocks[kItemBlocks];
+};
+static_assert(sizeof(FragItem) == 288, "FragItem layout");
 
 // RGBA8 mip chain of one texture inside the texture arena (one allocation for all textures).
 // Levels are pitch-linear, tightly packed, row 0 first; off[] are TEXEL offsets from the arena base.
@@ -36,7 +61,6 @@ struct DPrim {
     int pad;
 };
 
-// sorted, disjoint triangle ranges -> primitive
 static_assert(sizeof(DPrim) == 56, "DPrim layout");
 
 // sorted, disjoint triangle ranges -> primitive
@@ -62,8 +86,11 @@ struct ConvertArgs {
     float log_sz;  // ln(1e-7 * mult): the constant third log-scale of the packed layout
     // intermediates between the two kernels (context-owned scratch, L2-resident at the sizes of interest);
     // the fragment kernel reads the vertices themselves from `tris`
-    uint2* frag_ids;                   // {global triangle, y << 12 | x} per fragment; index = output record index
-    unsigned char* tri_frag;           // one TriFragT per triangle of the shard
+    unsigned char* tri_frag;           // one TriRec per triangle of the shard
+    UnitDesc* unit_desc;               // [n_units]
+    FragItem* items;                   // [queue_cap]
+    uint32_t queue_cap;
+    uint32_t* n_items_out;             // items queued by this launch (published by the raster kernel's last CTA)
     uint8_t* out;
     unsigned long long cap;
     unsigned long long* keys;          // optional
@@ -75,12 +102,10 @@ struct ConvertArgs {
     unsigned long long* host_total;    // optional, mapped pinned host memory: {count, tag} written by the raster kernel's
     unsigned long long host_tag;       // last CTA so the host can size the download while the fragment kernel still runs
     // scheduling state (zero at launch, re-armed by the last CTA)
-    uint32_t* sched;                   // 5 words, 128 B apart: unit counter, units past set-up, queue tail, queue head,
-                                       // CTAs finished
+    uint32_t* sched;                   // words 128 B apart: 0 unit counter, 2 item-queue tail, 4 raster CTAs finished,
+                                       // 6 fragment CTAs finished (fused gather)
     uint32_t unit_tris;                // triangles per work unit (<= 32), chosen by the host for balance
     uint32_t n_units;
-    uint2* queue;                      // deferred big-triangle chunks: (triangle, chunk)
-    uint32_t queue_cap;
     unsigned long long* trace;         // M2S_TRACE builds only: 16 globaltimer stamps per raster warp
     // multi-GPU fused gather (world <= 1: off).  peer_out[p] / peer_xch[p] are rank p's final buffer and
     // exchange block mapped into this process (NVLink peer memory); every rank's fragment kernel stores its

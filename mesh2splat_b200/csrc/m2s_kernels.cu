@@ -1,57 +1,58 @@
 // m2s_kernels.cu — the conversion pass as hand-written sm_100a CUDA.
 //
-// Two kernels on one stream replace the reference's geometry shader, fixed-function rasteriser,
-// fragment shader and SSBO atomic append (converter{GS,FS}.glsl, ConversionPass.cpp:114-116); the data
-// between them (8-byte fragment ids, 144-176 B per-triangle records) stays in the 126 MB L2.  The second
-// kernel is launched with programmatic dependent launch.
+// Two kernels on one stream replace the reference's geometry shader, fixed-function rasteriser, fragment shader
+// and SSBO atomic append (converter{GS,FS}.glsl, ConversionPass.cpp:114-116).  The second kernel is launched with
+// programmatic dependent launch.  What crosses between them is small and stays in the 126 MB L2: one 144-176 B
+// record per triangle, 16 B per work unit, 288 B per queued work item — never anything per fragment.
 //
-// raster_kernel (persistent, one CTA per SM, every WARP an autonomous pipeline; one __syncthreads after the
-// descriptor tables are copied to shared memory, none in the steady state):
-//   work unit = <= 32 consecutive triangles; a warp's first unit is static (global warp id), further ones
-//     are claimed from a global counter one unit ahead and their bytes prefetched into L2
+// raster_kernel — per-TRIANGLE work: set-up and COUNTING (persistent, one CTA per SM, every warp an autonomous
+// pipeline; one __syncthreads after the descriptor tables are copied to shared memory, none in the steady state)
+//   work unit = <= 32 consecutive triangles; a warp's first unit is static (global warp id), further ones are
+//     claimed from a global counter; the next unit's triangles are in flight (TMA) while this one is processed
 //   TMA (cp.async.bulk + mbarrier complete_tx) stages the unit's 144 B/triangle into shared memory
-//   per-triangle stage, one LANE per triangle (converterGS.glsl:326-443): longest edge, face normal,
-//     dominant axis, orthographic uv, quaternion, UV->3D Jacobian scale; rasteriser set-up: 24.8
-//     fixed-point window coords, int64 edge functions, top-left ownership bits, candidate pixel box
-//     (clamped to the call's pixel-row band); exact barycentric state (edge functions at the box origin,
-//     per-pixel steps, 1/area); the triangle's resolved sampler state (mip level pair, blend fraction,
-//     level offsets and sizes)
-//   the unit's per-triangle records leave shared memory as ONE TMA bulk store (cp.async.bulk.global.shared::cta)
-//   coverage, three regimes by candidate-pixel count:
-//     small  (<= 64, fits int32)  lane-per-triangle, lock-step incremental edge functions into a 64-bit
-//                                 hit mask; warp scan -> contiguous range per triangle; second pass over
-//                                 the set bits writes the ids (fragments leave TRIANGLE-MAJOR)
-//     medium (<= 1024)            warp-per-triangle, 32 candidates per step, int64 edge functions
-//     big                         pushed as 512-candidate chunks to a global queue (one atomicAdd per warp)
-//                                 and rasterised by ALL warps of the grid after the units are set up
-//     one global atomicAdd per unit (small) / per <= 512 fragments (medium, big) reserves the output range
-//     (the reference: one atomicCounterIncrement per fragment).  Fragment i of the id list IS output record i.
-// fragment_kernel (converterFS.glsl:44-104; lean registers, high occupancy, grid-stride):
-//   a warp takes 32 consecutive fragments: exact barycentrics from the int64 edge functions, attributes
-//   from the original vertices, all texel loads of all bound maps issued back to back, trilinear filter on
-//   the FMA pipe (u8->f32 by PRMT+FADD), TBN normal, encode; the 32 records are transposed through shared
-//   memory and written as one contiguous span (16-byte stores when aligned) — locally, or into every
-//   rank's final buffer over NVLink (fused multi-GPU gather), or after the earlier chunks' records
-//   (appended launches of the pipelined host path).
+//   per-triangle stage, one LANE per triangle (converterGS.glsl:326-443): longest edge, face normal, dominant
+//     axis, orthographic uv, quaternion, UV->3D Jacobian scale; rasteriser set-up: 24.8 fixed-point window
+//     coords, int64 edge functions, top-left ownership bits, candidate pixel box (clamped to the call's
+//     pixel-row band); the triangle's resolved sampler state (mip level pair, blend fraction, level offsets)
+//   coverage is only COUNTED here:
+//     small triangles (box <= 64 pixels, <= 32 rows, int32-safe): lane-per-triangle lock-step walk of the box
+//       with incremental edge functions -> 64-bit coverage mask, stored in the record; a warp scan gives every
+//       triangle its offset inside the unit; ONE global atomicAdd per unit reserves the output range
+//       (the reference: one atomicCounterIncrement per fragment)
+//     all other triangles: lane-per-ROW exact interval (m2s_span.cuh: three estimated divisions + exact int64
+//       fix-up) -> fragments per block of 32 rows; blocks are batched into work items (<= 32 blocks or
+//       >= 1024 fragments; one atomicAdd reserves the item's output range), a block of more than 2048
+//       fragments is cut into several items — a 2-triangle quad at R = 2048 becomes 4096 items for the
+//       whole GPU, while its raster work is 128 warp steps
+//   the unit's records leave shared memory as ONE TMA bulk store (cp.async.bulk.global.shared::cta)
+// fragment_kernel — per-FRAGMENT work (converterFS.glsl:44-104); a CTA of 4 warps takes one work item:
+//   TMA stages the unit's records and its 144 B/triangle vertices into shared memory (one mbarrier), every
+//   warp rebuilds the row spans of its share of the item's blocks (mask rows / m2s_span.cuh) into a prefix
+//   table; then a warp takes 32 consecutive fragments = 32 consecutive output records: two 5-step searches
+//   (block by shuffle, row in shared memory) give (triangle, x, y); exact barycentrics from the int64 edge
+//   functions, attributes from the staged vertices, all texel loads of all bound maps issued back to back,
+//   trilinear filter on the FMA pipe (u8->f32 by PRMT+FADD), TBN normal, encode (REF96 / PACKED56 / the three
+//   .ply row formats directly); the 32 records are transposed through shared memory and written as one
+//   contiguous span (16-byte stores when aligned) — locally, or into every rank's final buffer over NVLink
+//   (fused multi-GPU gather), or after the earlier chunks' records (appended launches of the host path).
 //
 // Bit-exactness: every float operation of the per-triangle stage is written with __f*_rn intrinsics in the
 // operation order of the oracle (and of GLM, which the reference's GLSL-as-C++ build uses): coverage is
 // bit-exact and Scale/Quaternion match converterGS.glsl bit for bit.  Per-fragment values may use FMA
-// contraction and are compared with a tolerance.
+// contraction / fast reciprocals and are compared with a tolerance.
 #include <cstdio>
 #include "m2s_device.cuh"
+#include "m2s_span.cuh"
 
-// resident warps per SM / register cap per layout (warps are a multiple of 4: register allocation granularity)
-#ifndef M2S_WARPS_REF96
-#define M2S_WARPS_REF96 16
-#define M2S_REGS_REF96 128
+// resident raster warps per SM / register cap per raster kind (warps are a multiple of 4: register allocation granularity)
+#ifndef M2S_RASTER_WARPS
+#define M2S_RASTER_WARPS 16
 #endif
-#ifndef M2S_WARPS_PACKED56
-#define M2S_WARPS_PACKED56 16
-#define M2S_REGS_PACKED56 128
+#ifndef M2S_RASTER_REGS
+#define M2S_RASTER_REGS 128
 #endif
-#ifndef M2S_FRAG_THREADS
-#define M2S_FRAG_THREADS 256
+#ifndef M2S_FRAG_WARPS
+#define M2S_FRAG_WARPS 4
 #endif
 
 namespace m2s {
@@ -150,65 +151,53 @@ __device__ __forceinline__ f3 cross3(f3 x, f3 y) {
 }
 
 // ------------------------------------------------------------------------------------------
-// per-warp shared-memory records
+// per-triangle record: everything the fragment kernel needs besides the vertices
 // ------------------------------------------------------------------------------------------
-struct __align__(16) TriRaster {  // 64 B — sign-normalised edge functions E_k(i,j) = A_k i + B_k j + C_k
-    long long C[3];
-    int A[3];
-    int B[3];
-    unsigned short x0, y0, w, h;  // candidate pixel box
-    float inv_area;
-    unsigned incl;                // bit k: edge k owns its E == 0 samples (top-left rule)
-};
 struct __align__(8) TexRef {  // 16 B — one map, resolved for one triangle
     uint32_t off0, off1;          // texel offsets of the two mip levels in the arena; off0 == ~0u: no map
     unsigned short w0, h0, w1, h1;
 };
 template <int NMAPS>
-struct __align__(16) TriFragT {  // 128 + 16*NMAPS bytes
-    float quat[4];    // (w,x,y,z)
-    float scale[3];   // raw (REF96) or log(scale * sigma/R)
-    unsigned tri;     // global triangle index
-    float factor[4];  // u_materialFactor
-    float frac[3];    // trilinear blend per map (0 => single level)
-    unsigned meta;    // bits 0-2: map m has the same level sizes as map 0 (=> same footprint and weights);
-                      // bits 4-15: x0, bits 16-27: y0 of the candidate pixel box
-    // exact barycentrics: lambda_k(px,py) = (E0_k + A_k (px-x0) + B_k (py-y0)) * inv_area  (GL 4.6 eq. 14.9, w = 1)
-    long long E0[3];
+struct __align__(16) TriRec {     // 144 B (1 map) / 176 B (3 maps)
+    // exact barycentrics: lambda_k(x,y) = (E0_k + A_k (x-x0) + B_k (y-y0)) * inv_area  (GL 4.6 eq. 14.9, w = 1);
+    // coverage: E0_k - (edge k owns its zero set ? 0 : 1) >= 0
+    long long E0[3];              // edge functions at the centre of pixel (x0, y0), the box origin
+    unsigned long long hits;      // small triangles: coverage mask of the w x h box, bit = row * w + column
     int A[3];
     int B[3];
     float inv_area;
-    unsigned pad;
+    unsigned box;                 // w (13 bits) | h (13) << 13 | ownership bits (3) << 26 | small (1) << 29; 0: nothing to emit
+    float quat[4];                // (w,x,y,z)
+    float factor[4];              // u_materialFactor
+    float scale[2];               // raw (REF96) or log(scale * sigma/R); the third component is a constant
+    unsigned meta;                // bits 0-2: map m has the same level sizes as map 0 (=> same footprint and weights);
+                                  // bits 4-15: x0, bits 16-27: y0 of the candidate pixel box
+    unsigned first;               // fragments of the unit's small triangles before this one
+    float frac[NMAPS];            // trilinear blend per map (0 => single level)
     TexRef tex[NMAPS];
 };
+static_assert(sizeof(TriRec<1>) == 144 && sizeof(TriRec<3>) == 176, "TriRec layout");
+constexpr unsigned kBoxSmall = 1u << 29;
 
-template <int LAYOUT>
-struct Cfg;
-template <>
-struct Cfg<0> {  // REF96
-    static constexpr int kStride = 96;
-    static constexpr int kPitch = 96;   // = stride: the warp's 32 records are one contiguous 3 KB span
-    static constexpr int kMaps = 3;
-    static constexpr bool kLogScale = false;
-    // warps are allocated registers in groups of 4, so the warp count is a multiple of 4
-    static constexpr int kWarps = M2S_WARPS_REF96;
-    static constexpr int kMaxRegs = M2S_REGS_REF96;   // warps * 32 * regs <= 64 K registers
-};
-template <>
-struct Cfg<1> {  // PACKED56
-    static constexpr int kStride = 56;
-    static constexpr int kPitch = 56;
-    static constexpr int kMaps = 1;
-    static constexpr bool kLogScale = true;
-    static constexpr int kWarps = M2S_WARPS_PACKED56;
-    static constexpr int kMaxRegs = M2S_REGS_PACKED56;
-};
+// raster kinds: what the per-triangle stage has to prepare (maps to resolve, raw or log scale)
+template <int RK> struct RCfg;
+template <> struct RCfg<0> { static constexpr int kMaps = 3; static constexpr bool kLogScale = false; };  // REF96
+template <> struct RCfg<1> { static constexpr int kMaps = 1; static constexpr bool kLogScale = true; };   // PACKED56
+template <> struct RCfg<2> { static constexpr int kMaps = 3; static constexpr bool kLogScale = true; };   // .ply rows
 
-template <int LAYOUT>
+// output layouts (m2s_layout)
+template <int LAYOUT> struct Cfg;
+template <> struct Cfg<0> { static constexpr int kStride = 96, kRK = 0; };   // REF96
+template <> struct Cfg<1> { static constexpr int kStride = 56, kRK = 1; };   // PACKED56
+template <> struct Cfg<2> { static constexpr int kStride = 248, kRK = 2; };  // PLY_STANDARD (parsers.cpp:431-514)
+template <> struct Cfg<3> { static constexpr int kStride = 76, kRK = 2; };   // PLY_PBR      (parsers.cpp:232-316)
+template <> struct Cfg<4> { static constexpr int kStride = 48, kRK = 2; };   // PLY_COMPRESSED (parsers.cpp:339-428)
+
+template <int RK>
 struct __align__(128) WarpBlock {
-    float4 tri[kUnitTris * 9];                   // 4608 B, TMA destination
-    TriFragT<Cfg<LAYOUT>::kMaps> frag[kUnitTris];
-    uint32_t queue[kQueue];                      // 2048 B: slot << 24 | y << 12 | x
+    float4 tri[kUnitTris * 9];                    // 4608 B, TMA destination
+    TriRec<RCfg<RK>::kMaps> rec[kUnitTris];       // TMA source
+    BlockRef pend[kItemBlocks];                   // row blocks waiting to become a work item
     uint64_t bar;
 };
 
@@ -223,24 +212,22 @@ struct Tables {
 };
 constexpr uint32_t kTableSmemBytes = 24 * 1024;
 
+// what the raster kernel itself keeps of a triangle after the set-up (registers of the owning lane)
+struct TriSetup {
+    long long E0[3];
+    int A[3], B[3];
+    int w, h;
+    unsigned incl;
+};
+
 // ------------------------------------------------------------------------------------------
 // per-triangle stage + rasteriser set-up.  t4: 9 float4 in shared memory.
 // Returns the number of candidate pixels (0 => nothing to rasterise).
 // ------------------------------------------------------------------------------------------
-// M2S_INLINE_SETUP (tuning build, off): inline the per-triangle stage into the unit loop — the raster state then lives
-// in registers instead of going through local memory (the default build shows 36 STL / 28 LDL around the call) — and
-// keep one out-of-line copy for the drain path.  Inlined at both sites it was 90 KB of code, hence the split.
-#ifdef M2S_INLINE_SETUP
-#define M2S_SETUP_QUAL __forceinline__
-#else
-#define M2S_SETUP_QUAL __noinline__
-#endif
-template <int LAYOUT>
-__device__ M2S_SETUP_QUAL uint32_t setup_triangle(const float4* __restrict__ t4, uint32_t tri_global, const ConvertArgs& a,
-                                   const Tables& tb, TriRaster& tr, TriFragT<Cfg<LAYOUT>::kMaps>& tf) {
-    using C = Cfg<LAYOUT>;
-    tr.w = 0; tr.h = 0; tr.x0 = 0; tr.y0 = 0; tr.incl = 0; tr.inv_area = 0.f;
-    tf.tri = tri_global;
+template <int RK>
+__device__ __forceinline__ uint32_t setup_triangle(const float4* __restrict__ t4, uint32_t tri_global, const ConvertArgs& a,
+                                                   const Tables& tb, TriSetup& ts, TriRec<RCfg<RK>::kMaps>& tf) {
+    using C = RCfg<RK>;
     // triangle -> primitive (sorted disjoint ranges)
     int lo = 0, hi = (int)tb.nranges - 1, found = -1;
     while (lo <= hi) {
@@ -282,6 +269,54 @@ __device__ M2S_SETUP_QUAL uint32_t setup_triangle(const float4* __restrict__ t4,
         ou[2] = __fdiv_rn(__fsub_rn(pa2, mina), range); ov[2] = __fdiv_rn(__fsub_rn(pb2, minb), range);
     }
 
+    // rasteriser set-up first: gl_Position = ouv*2-1 (:439), viewport R x R, 8 sub-pixel bits.  A triangle that
+    // cannot emit a fragment leaves here, before the quaternion / Jacobian / sampler arithmetic
+    int X[3], Y[3];
+    bool valid = true;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float ndx = __fsub_rn(__fmul_rn(ou[k], 2.0f), 1.0f), ndy = __fsub_rn(__fmul_rn(ov[k], 2.0f), 1.0f);
+        const float xw = __fadd_rn(__fmul_rn(ndx, a.half_R), a.half_R), yw = __fadd_rn(__fmul_rn(ndy, a.half_R), a.half_R);
+        if (!(fabsf(xw) <= kGuard) || !(fabsf(yw) <= kGuard)) valid = false;  // also rejects NaN
+        X[k] = __float2int_rn(__fmul_rn(xw, 256.0f));
+        Y[k] = __float2int_rn(__fmul_rn(yw, 256.0f));
+    }
+    if (!valid) return 0;
+    const long long area2 = (long long)(X[1] - X[0]) * (Y[2] - Y[0]) - (long long)(X[2] - X[0]) * (Y[1] - Y[0]);
+    if (area2 == 0) return 0;
+    const int xmin = min(X[0], min(X[1], X[2])), xmax = max(X[0], max(X[1], X[2]));
+    const int ymin = min(Y[0], min(Y[1], Y[2])), ymax = max(Y[0], max(Y[1], Y[2]));
+    const int R1 = (int)a.R - 1;
+    const int x0 = max(0, (xmin + 127) >> 8), x1 = min(R1, (xmax - 128) >> 8);
+    const int y0 = max((int)a.row_begin, (ymin + 127) >> 8), y1 = min((int)a.row_end - 1, (ymax - 128) >> 8);  // row band
+    if (x1 < x0 || y1 < y0) return 0;
+    const int sg = area2 < 0 ? -1 : 1;
+    unsigned incl = 0;
+    const float ia = 1.0f / __ll2float_rn(area2 < 0 ? -area2 : area2);
+    // edge functions E_k(i,j) = A_k i + B_k j + C_k at pixel centres, sign-normalised; kept relative to the box
+    // origin; the per-pixel steps of the mesh uv (constant per triangle: uv is affine in window space)
+    float dudx = 0.f, dvdx = 0.f, dudy = 0.f, dvdy = 0.f;
+    {
+        const float uvx[3] = {q2.z, q5.z, q8.z}, uvy[3] = {q2.w, q5.w, q8.w};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int va = (k + 1) % 3, vb = (k + 2) % 3;
+            const int dx = X[vb] - X[va], dy = Y[vb] - Y[va];
+            const int A = sg * (-dy * 256), B = sg * (dx * 256);
+            const long long Ck = (long long)sg * ((long long)dx * (128 - Y[va]) - (long long)dy * (128 - X[va]));
+            if (A > 0 || (A == 0 && B > 0)) incl |= 1u << k;
+            const long long E0 = Ck + (long long)A * x0 + (long long)B * y0;
+            ts.E0[k] = E0; ts.A[k] = A; ts.B[k] = B;
+            tf.E0[k] = E0; tf.A[k] = A; tf.B[k] = B;
+            const float ca = (float)A * ia, cb = (float)B * ia;
+            dudx += uvx[k] * ca; dvdx += uvy[k] * ca;
+            dudy += uvx[k] * cb; dvdy += uvy[k] * cb;
+        }
+    }
+    ts.incl = incl;
+    ts.w = x1 - x0 + 1; ts.h = y1 - y0 + 1;
+    tf.inv_area = ia;
+
     // :399-407 rotation -> quaternion (w,x,y,z), quat_cast :131-183
     {
         const f3 xA = e1, yA = norm3(cross3(n, xA)), zA = n;
@@ -320,74 +355,19 @@ __device__ M2S_SETUP_QUAL uint32_t setup_triangle(const float4* __restrict__ t4,
         const f3 Jv = {__fadd_rn(__fmul_rn(V0.x, i10), __fmul_rn(V1.x, i11)), __fadd_rn(__fmul_rn(V0.y, i10), __fmul_rn(V1.y, i11)),
                        __fadd_rn(__fmul_rn(V0.z, i10), __fmul_rn(V1.z, i11))};
         // Scale and Quaternion are bit-identical to converterGS.glsl's (tests: golden GS vectors); only the
-        // log of the packed layout is the device's logf
-        const float sx = len3(Ju), sy = len3(Jv), sz = 1e-7f;
+        // log of the packed / .ply layouts is the device's logf
+        const float sx = len3(Ju), sy = len3(Jv);
         if (C::kLogScale) {  // parsers.cpp:497-499 log(scale * sigma/R)
-            tf.scale[0] = logf(__fmul_rn(sx, a.mult)); tf.scale[1] = logf(__fmul_rn(sy, a.mult)); tf.scale[2] = a.log_sz;
-        } else { tf.scale[0] = sx; tf.scale[1] = sy; tf.scale[2] = sz; }
+            tf.scale[0] = logf(__fmul_rn(sx, a.mult)); tf.scale[1] = logf(__fmul_rn(sy, a.mult));
+        } else { tf.scale[0] = sx; tf.scale[1] = sy; }
     }
     tf.factor[0] = pr.factor[0]; tf.factor[1] = pr.factor[1]; tf.factor[2] = pr.factor[2]; tf.factor[3] = pr.factor[3];
-
-    // rasteriser set-up: gl_Position = ouv*2-1 (:439), viewport R x R, 8 sub-pixel bits
-    int X[3], Y[3];
-    bool valid = true;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const float ndx = __fsub_rn(__fmul_rn(ou[k], 2.0f), 1.0f), ndy = __fsub_rn(__fmul_rn(ov[k], 2.0f), 1.0f);
-        const float xw = __fadd_rn(__fmul_rn(ndx, a.half_R), a.half_R), yw = __fadd_rn(__fmul_rn(ndy, a.half_R), a.half_R);
-        if (!(fabsf(xw) <= kGuard) || !(fabsf(yw) <= kGuard)) valid = false;  // also rejects NaN
-        X[k] = __float2int_rn(__fmul_rn(xw, 256.0f));
-        Y[k] = __float2int_rn(__fmul_rn(yw, 256.0f));
-    }
-    if (!valid) return 0;
-    const long long area2 = (long long)(X[1] - X[0]) * (Y[2] - Y[0]) - (long long)(X[2] - X[0]) * (Y[1] - Y[0]);
-    if (area2 == 0) return 0;
-    const int sg = area2 < 0 ? -1 : 1;
-    unsigned incl = 0;
-    int Ak[3], Bk[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const int va = (k + 1) % 3, vb = (k + 2) % 3;
-        const int dx = X[vb] - X[va], dy = Y[vb] - Y[va];
-        const int A = sg * (-dy * 256), B = sg * (dx * 256);
-        tr.A[k] = Ak[k] = A;
-        tr.B[k] = Bk[k] = B;
-        tr.C[k] = (long long)sg * ((long long)dx * (128 - Y[va]) - (long long)dy * (128 - X[va]));
-        if (A > 0 || (A == 0 && B > 0)) incl |= 1u << k;
-    }
-    tr.incl = incl;
-    const float ia = 1.0f / __ll2float_rn(area2 < 0 ? -area2 : area2);
-    tr.inv_area = ia;
-    const int xmin = min(X[0], min(X[1], X[2])), xmax = max(X[0], max(X[1], X[2]));
-    const int ymin = min(Y[0], min(Y[1], Y[2])), ymax = max(Y[0], max(Y[1], Y[2]));
-    const int R1 = (int)a.R - 1;
-    const int x0 = max(0, (xmin + 127) >> 8), x1 = min(R1, (xmax - 128) >> 8);
-    const int y0 = max((int)a.row_begin, (ymin + 127) >> 8), y1 = min((int)a.row_end - 1, (ymax - 128) >> 8);  // row band
-    if (x1 < x0 || y1 < y0) return 0;
-    tr.x0 = (unsigned short)x0; tr.y0 = (unsigned short)y0;
-    tr.w = (unsigned short)(x1 - x0 + 1); tr.h = (unsigned short)(y1 - y0 + 1);
-
-    // barycentric state for the fragment kernel (exact integers, relative to the box origin) and the
-    // per-pixel steps of the mesh uv (constant per triangle: uv is affine in window space)
-    float dudx = 0.f, dvdx = 0.f, dudy = 0.f, dvdy = 0.f;
-    {
-        const float uvx[3] = {q2.z, q5.z, q8.z}, uvy[3] = {q2.w, q5.w, q8.w};
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            tf.E0[k] = tr.C[k] + (long long)Ak[k] * x0 + (long long)Bk[k] * y0;
-            tf.A[k] = Ak[k]; tf.B[k] = Bk[k];
-            const float ca = (float)Ak[k] * ia, cb = (float)Bk[k] * ia;
-            dudx += uvx[k] * ca; dvdx += uvy[k] * ca;
-            dudy += uvx[k] * cb; dvdy += uvy[k] * cb;
-        }
-        tf.inv_area = ia;
-        tf.pad = 0;
-    }
 
     // sampler state (GL 4.6 8.14): the steps of the mesh uv are constant per triangle, so lambda, the
     // level pair and the blend fraction are too
     unsigned share = 0;
     TexRef ref0;
+    float frac0 = 0.f;
 #pragma unroll
     for (int m = 0; m < C::kMaps; ++m) {
         TexRef ref;
@@ -395,7 +375,7 @@ __device__ M2S_SETUP_QUAL uint32_t setup_triangle(const float4* __restrict__ t4,
         float frac = 0.f;
         const int ti = pr.tex[m];
         if (ti >= 0) {
-            const DTexture t = tb.texs[ti];
+            const DTexture& t = tb.texs[ti];  // indexed in place (a local copy indexed by level would live in local memory)
             const float W = (float)t.w[0], H = (float)t.h[0];
             const float axx = dudx * W, bxx = dvdx * H, ayy = dudy * W, byy = dvdy * H;
             const float lam = 0.5f * __log2f(fmaxf(axx * axx + bxx * bxx, ayy * ayy + byy * byy));  // log2 of the longer step
@@ -408,26 +388,16 @@ __device__ M2S_SETUP_QUAL uint32_t setup_triangle(const float4* __restrict__ t4,
             ref.off0 = t.off[l0]; ref.off1 = t.off[l1];
             ref.w0 = t.w[l0]; ref.h0 = t.h[l0]; ref.w1 = t.w[l1]; ref.h1 = t.h[l1];
         }
-        if (m == 0) ref0 = ref;
+        if (m == 0) { ref0 = ref; frac0 = frac; }
         else if (ti >= 0 && ref0.off0 != 0xffffffffu && ref.w0 == ref0.w0 && ref.h0 == ref0.h0 && ref.w1 == ref0.w1 &&
-                 ref.h1 == ref0.h1 && frac == tf.frac[0])
+                 ref.h1 == ref0.h1 && frac == frac0)
             share |= 1u << m;
         tf.tex[m] = ref;
         tf.frac[m] = frac;
     }
     tf.meta = share | ((unsigned)x0 << 4) | ((unsigned)y0 << 16);
-    return (uint32_t)tr.w * (uint32_t)tr.h;
+    return (uint32_t)ts.w * (uint32_t)ts.h;
 }
-#ifdef M2S_INLINE_SETUP
-template <int LAYOUT>
-__device__ __noinline__ uint32_t setup_triangle_outofline(const float4* __restrict__ t4, uint32_t tri_global, const ConvertArgs& a,
-                                                          const Tables& tb, TriRaster& tr, TriFragT<Cfg<LAYOUT>::kMaps>& tf) {
-    return setup_triangle<LAYOUT>(t4, tri_global, a, tb, tr, tf);
-}
-#define M2S_SETUP_DRAIN setup_triangle_outofline
-#else
-#define M2S_SETUP_DRAIN setup_triangle
-#endif
 
 // ------------------------------------------------------------------------------------------
 // sampler: RGBA8 unorm, REPEAT, bilinear within a level, linear between levels
@@ -484,109 +454,111 @@ __device__ __forceinline__ float inv_sigmoid(float a) {  // utils.hpp:270
 }
 
 // ------------------------------------------------------------------------------------------
-// flush: reserve the output range and write the warp's fragment ids (coalesced)
+// raster_kernel helpers: work items of the fragment kernel
 // ------------------------------------------------------------------------------------------
-template <int LAYOUT>
-__device__ __forceinline__ void flush_ids(const ConvertArgs& a, WarpBlock<LAYOUT>& wb, uint32_t qn, int lane) {
-    if (qn == 0) return;
-    __syncwarp();
+__device__ __forceinline__ uint32_t block_ref(uint32_t slot, uint32_t row_begin, uint32_t nrows) {
+    return slot | (row_begin << 5) | (nrows << 17);
+}
+
+// the warp's pending row blocks become ONE work item: reserve its output range and a queue slot
+template <int RK>
+__device__ __forceinline__ void flush_blocks(const ConvertArgs& a, WarpBlock<RK>& wb, uint32_t unit, uint32_t& npend, uint32_t& pend_total,
+                                             int lane) {
+    if (npend == 0) return;
+    __syncwarp();  // lane 0's pend[] writes are visible to the warp
+    // converterFS.glsl:48-51: the counter keeps counting, but an item that starts beyond the cap emits nothing and
+    // takes no queue slot (so the queue can be sized from the cap: live items cover disjoint ranges below it)
     unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(a.counter, (unsigned long long)qn);
+    uint32_t slot = 0xffffffffu;
+    if (lane == 0) {
+        base = atomicAdd(a.counter, (unsigned long long)pend_total);
+        if (base < a.cap) slot = atomicAdd(SCHED(a, 2), 1u);
+    }
     base = __shfl_sync(0xffffffffu, base, 0);
-    for (uint32_t i = lane; i < qn; i += 32) {
-        const uint32_t id = wb.queue[i];
-        const unsigned long long idx = base + i;
-        if (idx < a.cap)  // converterFS.glsl:48-51: the counter keeps counting, records beyond the cap are dropped
-            a.frag_ids[idx] = make_uint2(wb.frag[id >> 24].tri, id & 0xffffffu);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (slot < a.queue_cap) {
+        FragItem* it = a.items + slot;
+        if (lane == 0) {
+            it->first = base; it->unit = unit; it->nblocks = npend;
+            it->frag_begin = 0; it->frag_end = pend_total;
+        }
+        if ((uint32_t)lane < npend) it->blocks[lane] = wb.pend[lane];
     }
     __syncwarp();
+    npend = 0; pend_total = 0;
 }
 
-// enqueue the lanes whose `inside` is set; flush when the queue could overflow on the next step
-template <int LAYOUT>
-__device__ __forceinline__ void enqueue(const ConvertArgs& a, WarpBlock<LAYOUT>& wb, uint32_t& qn, bool inside, uint32_t id,
-                                        int lane) {
-    const unsigned m = __ballot_sync(0xffffffffu, inside);
-    if (m) {
-        if (inside) wb.queue[qn + __popc(m & ((1u << lane) - 1u))] = id;
-        qn += __popc(m);
-        if (qn > kQueue - 32) {
-            flush_ids<LAYOUT>(a, wb, qn, lane);
-            qn = 0;
+// a row block of triangle `slot` holding `bt` fragments
+template <int RK>
+__device__ __forceinline__ void push_block(const ConvertArgs& a, WarpBlock<RK>& wb, uint32_t unit, uint32_t& npend, uint32_t& pend_total,
+                                           uint32_t slot, uint32_t row_begin, uint32_t nrows, uint32_t bt, int lane) {
+    const uint32_t ref = block_ref(slot, row_begin, nrows);
+    if (bt > kItemMaxFrags) {  // a block of a huge triangle: several single-block items, each a fragment sub-range
+        unsigned long long base = 0;
+        uint32_t first = 0, nit = 0;
+        if (lane == 0) {
+            base = atomicAdd(a.counter, (unsigned long long)bt);
+            if (base < a.cap) {  // only the items that start below the cap exist
+                const unsigned long long live = min((unsigned long long)bt, a.cap - base);
+                nit = (uint32_t)((live + kItemMaxFrags - 1) / kItemMaxFrags);
+                first = atomicAdd(SCHED(a, 2), nit);
+            }
         }
-    }
-}
-
-// warp-per-triangle coverage of candidates [c0, c1) of the triangle in `slot` (int64 edge functions)
-#ifdef M2S_INLINE_RASTER  // tuning build (off): with the set-up inlined too, the raster state never needs an address
-#define M2S_RASTER_QUAL __forceinline__
-#else
-#define M2S_RASTER_QUAL
-#endif
-template <int LAYOUT>
-__device__ M2S_RASTER_QUAL void raster_one(const ConvertArgs& a, WarpBlock<LAYOUT>& wb, uint32_t& qn, uint32_t slot, uint32_t c0, uint32_t c1,
-                           int lane, const TriRaster& mine) {
-    // the raster state lives in the registers of lane `slot`: broadcast it
-    const unsigned full = 0xffffffffu;
-    const int src = (int)slot;
-    const uint32_t w = __shfl_sync(full, (uint32_t)mine.w, src);
-    const float rcp = 1.0f / (float)w;
-    const long long C0 = __shfl_sync(full, mine.C[0], src), C1 = __shfl_sync(full, mine.C[1], src), C2 = __shfl_sync(full, mine.C[2], src);
-    const int A0 = __shfl_sync(full, mine.A[0], src), A1 = __shfl_sync(full, mine.A[1], src), A2 = __shfl_sync(full, mine.A[2], src);
-    const int B0 = __shfl_sync(full, mine.B[0], src), B1 = __shfl_sync(full, mine.B[1], src), B2 = __shfl_sync(full, mine.B[2], src);
-    const unsigned incl = __shfl_sync(full, mine.incl, src);
-    const int bx = __shfl_sync(full, (int)mine.x0, src), by = __shfl_sync(full, (int)mine.y0, src);
-    for (uint32_t cb = c0; cb < c1; cb += 32) {
-        const uint32_t c = cb + lane;
-        bool inside = false;
-        uint32_t id = 0;
-        if (c < c1) {
-            uint32_t row = (uint32_t)((float)c * rcp);  // c < 2^24: exact in fp32, quotient off by at most 1
-            int col = (int)(c - row * w);
-            if (col < 0) { --row; col += (int)w; }
-            else if (col >= (int)w) { ++row; col -= (int)w; }
-            const int px = bx + col, py = by + (int)row;
-            const long long E0 = C0 + (long long)A0 * px + (long long)B0 * py;
-            const long long E1 = C1 + (long long)A1 * px + (long long)B1 * py;
-            const long long E2 = C2 + (long long)A2 * px + (long long)B2 * py;
-            inside = (E0 > 0 || (E0 == 0 && (incl & 1u))) && (E1 > 0 || (E1 == 0 && (incl & 2u))) &&
-                     (E2 > 0 || (E2 == 0 && (incl & 4u)));
-            id = (slot << 24) | ((uint32_t)py << 12) | (uint32_t)px;
+        base = __shfl_sync(0xffffffffu, base, 0);
+        first = __shfl_sync(0xffffffffu, first, 0);
+        nit = __shfl_sync(0xffffffffu, nit, 0);
+        for (uint32_t i = lane; i < nit; i += 32) {
+            if (first + i >= a.queue_cap) break;
+            FragItem* it = a.items + first + i;
+            const uint32_t fb = i * kItemMaxFrags;
+            it->first = base; it->unit = unit; it->nblocks = 1u;
+            it->frag_begin = fb; it->frag_end = min(bt, fb + kItemMaxFrags);
+            it->blocks[0].prefix = 0; it->blocks[0].ref = ref;
         }
-        enqueue<LAYOUT>(a, wb, qn, inside, id, lane);
+        return;
     }
+    if (lane == 0) { wb.pend[npend].prefix = pend_total; wb.pend[npend].ref = ref; }
+    ++npend;
+    pend_total += bt;
+    if (npend == kItemBlocks || pend_total >= kFlushFrags) flush_blocks<RK>(a, wb, unit, npend, pend_total, lane);
 }
 
 // ------------------------------------------------------------------------------------------
-// the kernel
+// raster_kernel
 // ------------------------------------------------------------------------------------------
-template <int LAYOUT>
-__global__ void __launch_bounds__(Cfg<LAYOUT>::kWarps * 32) __maxnreg__(Cfg<LAYOUT>::kMaxRegs) raster_kernel(const __grid_constant__ ConvertArgs a) {
-    using C = Cfg<LAYOUT>;
+template <int RK>
+__global__ void __launch_bounds__(M2S_RASTER_WARPS * 32, 1) raster_kernel(const __grid_constant__ ConvertArgs a) {
+    using C = RCfg<RK>;
+    using Rec = TriRec<C::kMaps>;
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpBlock<LAYOUT>& wb = *reinterpret_cast<WarpBlock<LAYOUT>*>(smem + (size_t)warp * sizeof(WarpBlock<LAYOUT>));
+    WarpBlock<RK>& wb = *reinterpret_cast<WarpBlock<RK>*>(smem + (size_t)warp * sizeof(WarpBlock<RK>));
     const unsigned char* tri_bytes = reinterpret_cast<const unsigned char*>(a.tris);
 
-#ifdef M2S_EARLY_TRIGGER
-    // PDL early trigger (one fragment-kernel CTA per SM becomes resident beside this CTA and parks in
-    // griddepcontrol.wait).  Measured SLOWER (PACKED56 40.5 vs 39.8 us, REF96 62.4 vs 59.5 us): off.
-    asm volatile("griddepcontrol.launch_dependents;");
-#endif
     if (lane == 0) {
         mbar_init(&wb.bar, 1);
         fence_barrier_init();
     }
+    __syncwarp();
+    // the first unit of every warp is static (unit = global warp id): no atomic, and nobody can grab two units
+    // while a neighbour gets none; its triangles start moving before the descriptor tables are copied
+    const uint32_t nwarps_total = gridDim.x * (blockDim.x >> 5);
+    uint32_t unit = blockIdx.x + gridDim.x * warp;  // warp w of every CTA before warp w+1 of any: SMs fill evenly
+    auto issue_load = [&](uint32_t u) {  // lane 0 only
+        const uint32_t t0 = u * a.unit_tris;
+        const uint32_t bytes = min(a.unit_tris, a.tri_count - t0) * kTriBytes;
+        fence_proxy_async();
+        mbar_arrive_expect_tx(&wb.bar, bytes);
+        tma_load_1d(wb.tri, tri_bytes + ((size_t)a.tri_first + t0) * kTriBytes, bytes, &wb.bar);
+    };
+    if (lane == 0 && unit < a.n_units) issue_load(unit);
+
     // descriptor tables -> shared memory (once per CTA) when they fit
     Tables tabs{a.ranges, a.prims, a.texs, a.nranges};
     {
         const uint32_t br = a.nranges * (uint32_t)sizeof(DRange), bp = a.nprims * (uint32_t)sizeof(DPrim), bt = a.ntex * (uint32_t)sizeof(DTexture);
-#ifdef M2S_NO_TABLES
-        if (false) {
-#else
         if (br + bp + bt <= kTableSmemBytes) {  // uniform across the grid
-#endif
-            unsigned char* base = smem + (size_t)C::kWarps * sizeof(WarpBlock<LAYOUT>);
+            unsigned char* base = smem + (size_t)M2S_RASTER_WARPS * sizeof(WarpBlock<RK>);
             uint32_t* dst = reinterpret_cast<uint32_t*>(base);  // word-wise: the structs are 16, 56 and 48 bytes
             const uint32_t* s0 = reinterpret_cast<const uint32_t*>(a.ranges);
             const uint32_t* s1 = reinterpret_cast<const uint32_t*>(a.prims);
@@ -600,232 +572,137 @@ __global__ void __launch_bounds__(Cfg<LAYOUT>::kWarps * 32) __maxnreg__(Cfg<LAYO
             __syncthreads();  // the only CTA-wide barrier before the end of the kernel
         }
     }
-    __syncwarp();
-    uint32_t phase = 0, qn = 0;
+    uint32_t phase = 0;
     STAMP(a, 0);
 
-    // ---- work units ---------------------------------------------------------------------------
-    // the first unit of every warp is static (unit = global warp id): no atomic, and nobody can grab two
-    // units while a neighbour gets none; further units are claimed dynamically one unit ahead
-    const uint32_t nwarps_total = gridDim.x * (blockDim.x >> 5);
-    uint32_t unit = blockIdx.x + gridDim.x * warp;  // warp w of every CTA before warp w+1 of any: SMs fill evenly
     while (unit < a.n_units) {
         const uint32_t t0 = unit * a.unit_tris;
         const uint32_t ntri = min(a.unit_tris, a.tri_count - t0);
         uint32_t next = 0xffffffffu;
         if (lane == 0) {
-            const uint32_t bytes = ntri * kTriBytes;
-            tma_store_wait_read();  // the previous unit's record stores have finished reading this slice
-            fence_proxy_async();
-            mbar_arrive_expect_tx(&wb.bar, bytes);
-            tma_load_1d(wb.tri, tri_bytes + ((size_t)a.tri_first + t0) * kTriBytes, bytes, &wb.bar);
-            if (a.n_units > nwarps_total) {  // more units than warps: claim the next one now, pull its bytes into L2
-                next = nwarps_total + atomicAdd(SCHED(a, 0), 1u);
-                if (next < a.n_units) {
-                    const uint32_t nt0 = next * a.unit_tris;
-                    prefetch_l2(tri_bytes + ((size_t)a.tri_first + nt0) * kTriBytes, min(a.unit_tris, a.tri_count - nt0) * kTriBytes);
-                }
-            }
+            if (a.n_units > nwarps_total) next = nwarps_total + atomicAdd(SCHED(a, 0), 1u);  // needed only after the set-up
+            tma_store_wait_read();  // the previous unit's record store has finished reading wb.rec
         }
         mbar_wait(&wb.bar, phase);
         phase ^= 1;
+        __syncwarp();
         STAMP(a, 1);
 
-        // per-triangle stage: one lane per triangle
+        // ---- per-triangle stage: one lane per triangle ----
         uint32_t cnt = 0;
-        TriRaster tr;  // raster state stays with the lane that owns the triangle
-        tr.w = 0; tr.h = 0; tr.x0 = 0; tr.y0 = 0; tr.incl = 0;
-        tr.A[0] = tr.A[1] = tr.A[2] = tr.B[0] = tr.B[1] = tr.B[2] = 0; tr.C[0] = tr.C[1] = tr.C[2] = 0;
-        if ((uint32_t)lane < ntri) cnt = setup_triangle<LAYOUT>(wb.tri + lane * 9, a.tri_first + t0 + lane, a, tabs, tr, wb.frag[lane]);
+        TriSetup ts;
+        ts.w = 1; ts.h = 0; ts.incl = 0;
+        ts.A[0] = ts.A[1] = ts.A[2] = ts.B[0] = ts.B[1] = ts.B[2] = 0; ts.E0[0] = ts.E0[1] = ts.E0[2] = 0;
+        Rec& myrec = wb.rec[lane];
+        if ((uint32_t)lane < ntri) cnt = setup_triangle<RK>(wb.tri + lane * 9, a.tri_first + t0 + lane, a, tabs, ts, myrec);
+        __syncwarp();
+        STAMP(a, 2);
+        // the triangle staging area is dead now: the next unit's triangles can fly in while this one is counted
+        next = __shfl_sync(0xffffffffu, next, 0);
+        if (lane == 0 && next < a.n_units) issue_load(next);
 
-        // classify: small (lane-per-triangle, int32), medium (warp-per-triangle), big (deferred)
-        int e0 = 0, e1 = 0, e2 = 0, a0 = 0, a1 = 0, a2 = 0, r0 = 0, r1 = 0, r2 = 0, w = 1, bx = 0, by = 0;
-        bool small = false, deferred = false;
+        // ---- small triangles: lane-per-triangle lock-step walk of the candidate box -> coverage mask ----
+        int e0 = 0, e1 = 0, e2 = 0, a0 = 0, a1 = 0, a2 = 0, r0 = 0, r1 = 0, r2 = 0, w = 1;
+        bool small = false;
         if (cnt) {
-            w = tr.w; bx = tr.x0; by = tr.y0;
-            const int h = tr.h;
-            a0 = tr.A[0]; a1 = tr.A[1]; a2 = tr.A[2];
-            const int b0 = tr.B[0], b1 = tr.B[1], b2 = tr.B[2];
+            w = ts.w;
+            const int h = ts.h;
+            a0 = ts.A[0]; a1 = ts.A[1]; a2 = ts.A[2];
+            const int b0 = ts.B[0], b1 = ts.B[1], b2 = ts.B[2];
             // E at the box origin, with the ownership bias folded in: inside <=> all E' >= 0
-            const long long E0 = tr.C[0] + (long long)a0 * bx + (long long)b0 * by - ((tr.incl & 1u) ? 0 : 1);
-            const long long E1 = tr.C[1] + (long long)a1 * bx + (long long)b1 * by - ((tr.incl & 2u) ? 0 : 1);
-            const long long E2 = tr.C[2] + (long long)a2 * bx + (long long)b2 * by - ((tr.incl & 4u) ? 0 : 1);
+            const long long E0 = ts.E0[0] - ((ts.incl & 1u) ? 0 : 1);
+            const long long E1 = ts.E0[1] - ((ts.incl & 2u) ? 0 : 1);
+            const long long E2 = ts.E0[2] - ((ts.incl & 4u) ? 0 : 1);
             const long long lim = 0x7fffffffll;
             const long long s0 = llabs(E0) + (long long)(w - 1) * abs(a0) + (long long)(h - 1) * abs(b0);
             const long long s1 = llabs(E1) + (long long)(w - 1) * abs(a1) + (long long)(h - 1) * abs(b1);
             const long long s2 = llabs(E2) + (long long)(w - 1) * abs(a2) + (long long)(h - 1) * abs(b2);
-            small = cnt <= kSmallCand && s0 < lim && s1 < lim && s2 < lim;
+            small = cnt <= kSmallCand && h <= 32 && s0 < lim && s1 < lim && s2 < lim;
             if (small) {
                 e0 = (int)E0; e1 = (int)E1; e2 = (int)E2;
                 r0 = b0 - (w - 1) * a0; r1 = b1 - (w - 1) * a1; r2 = b2 - (w - 1) * a2;  // step to the next row's first pixel
             }
         }
-        // big triangles: push their chunks to the global queue.  ONE atomicAdd per warp reserves the slots
-        // (a per-lane CAS loop collapses under contention: 15 k simultaneous pushers cost 19 ms)
+        unsigned long long hits = 0;
         {
-            const bool big = cnt > kBigCand && !small;
-            const uint32_t nch = big ? (cnt + kChunkCand - 1) / kChunkCand : 0u;
-            uint32_t incl = nch;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += v;
-            }
-            const uint32_t wtotal = __shfl_sync(0xffffffffu, incl, 31);
-            if (wtotal) {
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(SCHED(a, 2), wtotal);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (big) {
-                    const uint32_t first = base + (incl - nch);
-                    const uint32_t tg = a.tri_first + t0 + lane;
-                    if (first + nch <= a.queue_cap) {
-                        for (uint32_t i = 0; i < nch; ++i) a.queue[first + i] = make_uint2(tg, i);
-                        cnt = 0;
-                        deferred = true;
-                    } else {  // queue full: the in-range slots become no-ops, the triangle is rasterised here
-                        for (uint32_t i = first; i < min(first + nch, a.queue_cap); ++i) a.queue[i] = make_uint2(0xffffffffu, 0u);
-                    }
-                    __threadfence();
-                }
+            const uint32_t mine = small ? cnt : 0u;
+            const uint32_t maxc = __reduce_max_sync(0xffffffffu, mine);
+            int col = 0, f0 = e0, f1 = e1, f2 = e2;
+            for (uint32_t it = 0; it < maxc; ++it) {
+                const bool inside = it < mine && (f0 | f1 | f2) >= 0;
+                hits |= (unsigned long long)inside << it;
+                if (++col == w) { col = 0; f0 += r0; f1 += r1; f2 += r2; }
+                else { f0 += a0; f1 += a1; f2 += a2; }
             }
         }
-        STAMP(a, 2);
+        STAMP(a, 3);
+        const uint32_t nh = (uint32_t)__popcll(hits);
+        uint32_t incl_scan = nh;  // inclusive warp scan
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl_scan, d);
+            if (lane >= d) incl_scan += v;
+        }
+        const uint32_t total_small = __shfl_sync(0xffffffffu, incl_scan, 31);
+        // ONE atomicAdd per unit reserves the output range of its small triangles (the reference: one
+        // atomicCounterIncrement per fragment); the result is only needed for the unit descriptor at the end
+        unsigned long long ubase = 0;
+        if (lane == 0 && total_small) ubase = atomicAdd(a.counter, (unsigned long long)total_small);
+        if ((uint32_t)lane < ntri) {
+            myrec.hits = hits;
+            myrec.first = incl_scan - nh;
+            myrec.box = cnt ? ((unsigned)ts.w | ((unsigned)ts.h << 13) | (ts.incl << 26) | (small ? kBoxSmall : 0u)) : 0u;
+        }
         __syncwarp();
-        // every chunk this unit defers is in the global queue now (pushers fenced): count the unit as
-        // "past set-up" so idle warps only wait for set-ups in flight, not for whole units
-        if (lane == 0) atomicAdd(SCHED(a, 1), 1u);
-        // the unit's per-triangle records (barycentric + shading state) go to global memory for the fragment
-        // kernel: one TMA bulk store straight out of this warp's shared-memory slice
-        if (__any_sync(0xffffffffu, cnt != 0 || deferred)) {
+        STAMP(a, 4);
+
+        // ---- all other triangles: the warp counts one triangle at a time, one lane per pixel row ----
+        uint32_t npend = 0, pend_total = 0;
+        unsigned gm = __ballot_sync(0xffffffffu, cnt != 0 && !small);
+        while (gm) {
+            const int s = __ffs(gm) - 1;
+            gm &= gm - 1;
+            const Rec& r = wb.rec[s];  // broadcast reads
+            const unsigned box = r.box;
+            RowState rs;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                rs.E[k] = r.E0[k] - (((box >> (26 + k)) & 1u) ? 0 : 1);
+                rs.A[k] = r.A[k]; rs.B[k] = r.B[k];
+            }
+            rs.w = (int)(box & 0x1fffu);
+            const int h = (int)((box >> 13) & 0x1fffu);
+            for (int rb = 0; rb < h; rb += 32) {
+                const int yrel = rb + lane;
+                int xl;
+                const uint32_t n = yrel < h ? span_row(rs, yrel, xl) : 0u;
+                const uint32_t bt = __reduce_add_sync(0xffffffffu, n);
+                if (bt) push_block<RK>(a, wb, unit, npend, pend_total, (uint32_t)s, (uint32_t)rb, (uint32_t)min(32, h - rb), bt, lane);
+            }
+        }
+        flush_blocks<RK>(a, wb, unit, npend, pend_total, lane);
+        STAMP(a, 5);
+
+        // ---- the unit's records go to global memory for the fragment kernel: one TMA bulk store straight out of
+        // this warp's shared-memory slice (every writer fences its generic-proxy writes, then the barrier) ----
+        const bool any = __any_sync(0xffffffffu, cnt != 0);
+        if (any) {
+            fence_proxy_async();
+            __syncwarp();
             if (lane == 0) {
-                fence_proxy_async();
-                tma_store_1d(a.tri_frag + (size_t)t0 * sizeof(TriFragT<C::kMaps>), wb.frag, ntri * (uint32_t)sizeof(TriFragT<C::kMaps>));
+                tma_store_1d(a.tri_frag + (size_t)t0 * sizeof(Rec), wb.rec, ntri * (uint32_t)sizeof(Rec));
                 tma_store_commit();
             }
         }
-
-        // small triangles: every lane walks its own pixel box in lock-step, twice.  Walk 1 records the
-        // covered candidates in a 64-bit mask (no ballots, no stores); a warp scan of the hit counts gives
-        // every triangle a contiguous output range; walk 2 writes the ids there.  Fragments therefore
-        // leave TRIANGLE-MAJOR, which is what keeps the fragment kernel's record and texel loads coherent.
-        {
-            const uint32_t mine = small ? cnt : 0u;
-            uint32_t maxc = mine;
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, d));
-            unsigned long long hits = 0;
-            {
-                int col = 0, f0 = e0, f1 = e1, f2 = e2;
-                for (uint32_t it = 0; it < maxc; ++it) {
-                    const bool inside = it < mine && (f0 | f1 | f2) >= 0;
-                    hits |= (unsigned long long)inside << it;
-                    if (++col == w) { col = 0; f0 += r0; f1 += r1; f2 += r2; }
-                    else { f0 += a0; f1 += a1; f2 += a2; }
-                }
-            }
-            STAMP(a, 3);
-            const uint32_t nh = (uint32_t)__popcll(hits);
-            uint32_t incl = nh;  // inclusive warp scan
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += v;
-            }
-            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-            if (total) {
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(a.counter, (unsigned long long)total);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                STAMP(a, 4);
-                unsigned long long idx = base + (incl - nh);
-                const uint32_t tg = a.tri_first + t0 + lane;
-                // walk 2 visits only the hits: bit b of the mask is candidate b = row*w + col; row = b/w by a
-                // 16.16 reciprocal (exact for b < 64, w <= 64)
-                const uint32_t inv = (65536u + (uint32_t)w - 1u) / (uint32_t)w;
-                uint32_t maxh = nh;
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) maxh = max(maxh, __shfl_xor_sync(0xffffffffu, maxh, d));
-                unsigned long long m = hits;
-                for (uint32_t it = 0; it < maxh; ++it) {
-                    if (m) {
-                        const uint32_t b = (uint32_t)__ffsll((long long)m) - 1u;
-                        m &= m - 1ull;
-                        const uint32_t row = (b * inv) >> 16, col = b - row * (uint32_t)w;
-                        if (idx < a.cap)  // converterFS.glsl:48-51 beyond the cap
-                            a.frag_ids[idx] = make_uint2(tg, ((uint32_t)(by + (int)row) << 12) | (uint32_t)(bx + (int)col));
-                        ++idx;
-                    }
-                }
-            }
-        }
-        STAMP(a, 5);
-        // medium triangles: the whole warp covers one triangle at a time
-        {
-            unsigned mm = __ballot_sync(0xffffffffu, cnt != 0 && !small);
-            while (mm) {
-                const int s = __ffs(mm) - 1;
-                mm &= mm - 1;
-                const uint32_t cs = __shfl_sync(0xffffffffu, cnt, s);
-                raster_one<LAYOUT>(a, wb, qn, (uint32_t)s, 0u, cs, lane, tr);
-            }
-        }
-        flush_ids<LAYOUT>(a, wb, qn, lane);
-        qn = 0;
-        __syncwarp();
-        unit = __shfl_sync(0xffffffffu, next, 0);
+        if (lane == 0)  // UnitDesc {first, total, pad}
+            *reinterpret_cast<uint4*>(a.unit_desc + unit) = make_uint4((uint32_t)ubase, (uint32_t)(ubase >> 32), total_small, 0u);
+        unit = next;
         STAMP(a, 6);
     }
     STAMP(a, 7);
-
-    // ---- drain: deferred big triangles, chunk by chunk, all warps ------------------------------
-    if (lane == 0) {
-        unsigned ns = 100;
-        while (ld_acquire_u32(SCHED(a, 1)) < a.n_units) { __nanosleep(ns); ns = min(ns * 2u, 1000u); }
-    }
-    __syncwarp();
-    STAMP(a, 8);
-    uint32_t tail = 0;
-    if (lane == 0) tail = ld_acquire_u32(SCHED(a, 2));
-    tail = min(__shfl_sync(0xffffffffu, tail, 0), a.queue_cap);
-    unsigned long long n_items = 0, t_setup = 0, t_rast = 0, t_load = 0;
-    while (tail) {
-        const unsigned long long ta = TNOW();
-        uint32_t it = 0;
-        if (lane == 0) it = atomicAdd(SCHED(a, 3), 1u);
-        it = __shfl_sync(0xffffffffu, it, 0);
-        if (it >= tail) break;
-        const uint2 item = a.queue[it];
-        if (item.x == 0xffffffffu) continue;  // slot of a push that did not fit
-        if (lane == 0) tma_store_wait_read();
-        __syncwarp();
-        if (lane < 9) wb.tri[lane] = a.tris[(size_t)item.x * 9 + lane];
-        __syncwarp();
-        const unsigned long long tb = TNOW();
-        uint32_t c = 0;
-        TriRaster tr;
-        tr.w = 1; tr.h = 0; tr.x0 = 0; tr.y0 = 0; tr.incl = 0;
-        tr.A[0] = tr.A[1] = tr.A[2] = tr.B[0] = tr.B[1] = tr.B[2] = 0; tr.C[0] = tr.C[1] = tr.C[2] = 0;
-        if (lane == 0) c = M2S_SETUP_DRAIN<LAYOUT>(wb.tri, item.x, a, tabs, tr, wb.frag[0]);
-        c = __shfl_sync(0xffffffffu, c, 0);
-        __syncwarp();
-        const unsigned long long tc = TNOW();
-        const uint32_t c0 = item.y * kChunkCand, c1 = min(c, c0 + kChunkCand);
-        raster_one<LAYOUT>(a, wb, qn, 0u, c0, c1, lane, tr);
-        flush_ids<LAYOUT>(a, wb, qn, lane);
-        qn = 0;
-        __syncwarp();
-        const unsigned long long td = TNOW();
-        ++n_items; t_load += tb - ta; t_setup += tc - tb; t_rast += td - tc;
-    }
-    STAMPV(a, 12, n_items); STAMPV(a, 13, t_load); STAMPV(a, 14, t_setup); STAMPV(a, 15, t_rast);
-
-    STAMP(a, 9);
     if (lane == 0) tma_store_wait_all();  // record stores are complete (not just read) before the kernel ends
-    // ---- last CTA out publishes the count and re-arms the scheduler for the next launch ---------
-    STAMP(a, 10);
+    // ---- last CTA out publishes the counts and re-arms the scheduler for the next launch ---------
     __syncthreads();
-    STAMP(a, 11);
     if (warp == 0) {
         uint32_t last = 0;
         unsigned long long tot = 0;
@@ -837,13 +714,14 @@ __global__ void __launch_bounds__(Cfg<LAYOUT>::kWarps * 32) __maxnreg__(Cfg<LAYO
                 last = 1;
                 tot = *reinterpret_cast<volatile unsigned long long*>(a.counter);
                 *a.total_out = tot;
+                *a.n_items_out = *reinterpret_cast<volatile uint32_t*>(SCHED(a, 2));
                 *a.counter = 0ull;
                 if (a.host_total) {  // zero-copy count for the host (PCIe posted write, ~1 us)
                     *reinterpret_cast<volatile unsigned long long*>(a.host_total) = tot;
                     __threadfence_system();
                     *reinterpret_cast<volatile unsigned long long*>(a.host_total + 1) = a.host_tag;
                 }
-                *SCHED(a, 0) = 0; *SCHED(a, 1) = 0; *SCHED(a, 2) = 0; *SCHED(a, 3) = 0; *SCHED(a, 4) = 0;
+                *SCHED(a, 0) = 0; *SCHED(a, 2) = 0; *SCHED(a, 4) = 0;
                 __threadfence();
             }
         }
@@ -861,55 +739,263 @@ __global__ void __launch_bounds__(Cfg<LAYOUT>::kWarps * 32) __maxnreg__(Cfg<LAYO
 }
 
 // A warp's staged records (shared memory, 16-byte aligned) -> one contiguous span of global memory at byte
-// offset `boff` of `dstbase`.  16-byte stores when the span starts 16-byte aligned (REF96 always; PACKED56
-// at even record offsets), else 8-byte stores (appended chunks / gathered ranks may start at an odd record).
+// offset `boff` of `dstbase`.  The widest store the destination alignment allows: 16-byte when the span starts
+// 16-byte aligned (REF96 always; PACKED56 at even record offsets), else 8-byte (strides that are multiples of 8)
+// or 4-byte pieces (the 76-byte .ply row); a sub-vector tail is copied word-wise.
 template <int STRIDE>
 __device__ __forceinline__ void copy_span(uint8_t* dstbase, unsigned long long boff, const unsigned char* stage, uint32_t nbytes, int lane) {
+    static_assert(STRIDE % 4 == 0, "record strides are multiples of 4");
+    const uint32_t nw = nbytes / 4;
+    uint32_t done = 0;  // words copied by the vector body
     if ((boff & 15ull) == 0) {
         float4* dst = reinterpret_cast<float4*>(dstbase + boff);
         const float4* src = reinterpret_cast<const float4*>(stage);
-        const uint32_t n16 = nbytes / 16;
+        const uint32_t n16 = nw / 4;
 #pragma unroll
         for (int j = 0; j < (32 * STRIDE / 16 + 31) / 32; ++j) {
             const uint32_t c = lane + 32 * j;
             if (c < n16) dst[c] = src[c];
         }
-        if ((nbytes & 8u) && lane == 0)  // odd number of 56-byte records: one trailing 8-byte piece
-            reinterpret_cast<float2*>(dst)[n16 * 2] = reinterpret_cast<const float2*>(src)[n16 * 2];
-    } else {
+        done = n16 * 4;
+    } else if ((boff & 7ull) == 0) {
         float2* dst = reinterpret_cast<float2*>(dstbase + boff);
         const float2* src = reinterpret_cast<const float2*>(stage);
-        const uint32_t n8 = nbytes / 8;
+        const uint32_t n8 = nw / 2;
 #pragma unroll
-        for (int j = 0; j < 32 * STRIDE / 8 / 32; ++j) {
+        for (int j = 0; j < (32 * STRIDE / 8 + 31) / 32; ++j) {
             const uint32_t c = lane + 32 * j;
             if (c < n8) dst[c] = src[c];
         }
+        done = n8 * 2;
+    } else {
+        uint32_t* dst = reinterpret_cast<uint32_t*>(dstbase + boff);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(stage);
+#pragma unroll
+        for (int j = 0; j < STRIDE / 4; ++j) {
+            const uint32_t c = lane + 32 * j;
+            if (c < nw) dst[c] = src[c];
+        }
+        done = nw;
     }
+    if (done + lane < nw)  // at most 3 trailing words
+        reinterpret_cast<uint32_t*>(dstbase + boff)[done + lane] = reinterpret_cast<const uint32_t*>(stage)[done + lane];
 }
 
 // ------------------------------------------------------------------------------------------
-// fragment stage: one warp = 32 consecutive fragments = 32 consecutive output records
+// fragment_kernel: one CTA = one work item; one warp step = 32 consecutive fragments = 32 consecutive records
 // ------------------------------------------------------------------------------------------
+constexpr int kFragWarps = M2S_FRAG_WARPS;
+constexpr int kFragThreads = kFragWarps * 32;
+constexpr uint32_t kSpanWords = kItemBlocks * 32;  // one word per pixel row of every block: prefix << 12 | first column
+
 template <int LAYOUT>
-__global__ void __launch_bounds__(M2S_FRAG_THREADS) fragment_kernel(const __grid_constant__ ConvertArgs a) {
-    using C = Cfg<LAYOUT>;
-    constexpr int kStride = C::kStride;
+struct FragSmem {
+    using Rec = TriRec<RCfg<Cfg<LAYOUT>::kRK>::kMaps>;
+    static constexpr size_t kRecOff = 0;
+    static constexpr size_t kTriOff = kRecOff + kUnitTris * sizeof(Rec);
+    static constexpr size_t kSpanOff = kTriOff + kUnitTris * kTriBytes;
+    static constexpr size_t kStageOff = kSpanOff + kSpanWords * 4;
+    static constexpr size_t kBytes = kStageOff + (size_t)kFragWarps * 32 * Cfg<LAYOUT>::kStride;
+};
+
+__device__ __forceinline__ float inv_sigmoid_fast(float a) {  // utils.hpp:270; alpha = 1 -> +inf as in the reference
+    a = fminf(fmaxf(a, 0.0f), 1.0f);
+    return -__logf(__frcp_rn(a + 1e-8f) - 1.0f);
+}
+__device__ __forceinline__ unsigned char to_byte(float v) {
+    v = fminf(fmaxf(v, 0.0f), 1.0f);
+    return (unsigned char)roundf(v * 255.0f);
+}
+
+// One fragment: triangle `slot` of the staged unit, pixel (dx, dy) relative to the triangle's box origin.
+template <int LAYOUT>
+__device__ __forceinline__ void shade(const ConvertArgs& a, const typename FragSmem<LAYOUT>::Rec& tf, const float4* __restrict__ v,
+                                      int dxi, int dyi, const uint32_t* __restrict__ texb, unsigned char* __restrict__ srec_bytes) {
+    constexpr int kMaps = RCfg<Cfg<LAYOUT>::kRK>::kMaps;
+    const float ia = tf.inv_area;
+    const float l0 = __ll2float_rn(tf.E0[0] + (long long)tf.A[0] * dxi + (long long)tf.B[0] * dyi) * ia;
+    const float l1 = __ll2float_rn(tf.E0[1] + (long long)tf.A[1] * dxi + (long long)tf.B[1] * dyi) * ia;
+    const float l2 = __ll2float_rn(tf.E0[2] + (long long)tf.A[2] * dxi + (long long)tf.B[2] * dyi) * ia;
+    // vertices: 3 x {pos3 nrm3 tan4 uv2} = 9 float4 in shared memory; uv first: the texel addresses depend on nothing else
+    const float4 a2 = v[2], b2 = v[5], c2 = v[8];
+    const float u = l0 * a2.z + l1 * b2.z + l2 * c2.z, vv = l0 * a2.w + l1 * b2.w + l2 * c2.w;
+    const unsigned meta = tf.meta;
+
+    // ---- issue every texel load of every bound map back to back ----
+    uint32_t tx[kMaps][8];
+    Bilin bl[kMaps][2];
+    bool has[kMaps], two[kMaps];
+    uint32_t offs0[kMaps], offs1[kMaps];
+#pragma unroll
+    for (int m = 0; m < kMaps; ++m) {
+        const TexRef ref = tf.tex[m];
+        has[m] = ref.off0 != 0xffffffffu;
+        two[m] = has[m] && tf.frac[m] > 0.0f;
+        offs0[m] = has[m] ? ref.off0 : 0u;
+        offs1[m] = ref.off1;
+        if (m == 0 || !((meta >> m) & 1u)) {
+            bl[m][0] = bilin_setup(ref.w0, ref.h0, u, vv);
+            bl[m][1] = bilin_setup(ref.w1, ref.h1, u, vv);
+        } else { bl[m][0] = bl[0][0]; bl[m][1] = bl[0][1]; }
+    }
+#pragma unroll
+    for (int m = 0; m < kMaps; ++m) {
+        const uint32_t o0 = offs0[m], o1 = offs1[m];  // uniform base + 32-bit texel index
+        tx[m][0] = has[m] ? __ldg(texb + (o0 + bl[m][0].i00)) : 0u; tx[m][1] = has[m] ? __ldg(texb + (o0 + bl[m][0].i10)) : 0u;
+        tx[m][2] = has[m] ? __ldg(texb + (o0 + bl[m][0].i01)) : 0u; tx[m][3] = has[m] ? __ldg(texb + (o0 + bl[m][0].i11)) : 0u;
+        tx[m][4] = two[m] ? __ldg(texb + (o1 + bl[m][1].i00)) : 0u; tx[m][5] = two[m] ? __ldg(texb + (o1 + bl[m][1].i10)) : 0u;
+        tx[m][6] = two[m] ? __ldg(texb + (o1 + bl[m][1].i01)) : 0u; tx[m][7] = two[m] ? __ldg(texb + (o1 + bl[m][1].i11)) : 0u;
+    }
+    // ---- interpolate the remaining varyings while the loads are in flight ----
+    const float4 a0 = v[0], b0 = v[3], c0 = v[6];
+    const float Px = l0 * a0.x + l1 * b0.x + l2 * c0.x, Py = l0 * a0.y + l1 * b0.y + l2 * c0.y,
+                Pz = l0 * a0.z + l1 * b0.z + l2 * c0.z;
+
+    // colour (converterFS.glsl:55-62,99)
+    float cr = 1.f, cg = 1.f, cb = 1.f, ca = 1.f;
+    if (has[0]) {
+        const float f = tf.frac[0];
+        cr = filt<0>(bl[0][0], tx[0][0], tx[0][1], tx[0][2], tx[0][3]);
+        cg = filt<1>(bl[0][0], tx[0][0], tx[0][1], tx[0][2], tx[0][3]);
+        cb = filt<2>(bl[0][0], tx[0][0], tx[0][1], tx[0][2], tx[0][3]);
+        ca = filt<3>(bl[0][0], tx[0][0], tx[0][1], tx[0][2], tx[0][3]);
+        if (two[0]) {
+            cr += f * (filt<0>(bl[0][1], tx[0][4], tx[0][5], tx[0][6], tx[0][7]) - cr);
+            cg += f * (filt<1>(bl[0][1], tx[0][4], tx[0][5], tx[0][6], tx[0][7]) - cg);
+            cb += f * (filt<2>(bl[0][1], tx[0][4], tx[0][5], tx[0][6], tx[0][7]) - cb);
+            ca += f * (filt<3>(bl[0][1], tx[0][4], tx[0][5], tx[0][6], tx[0][7]) - ca);
+        }
+    }
+    cr *= tf.factor[0]; cg *= tf.factor[1]; cb *= tf.factor[2]; ca *= tf.factor[3];
+    const float kInvC0 = 1.0f / 0.28209479177387814f;  // SH_COEFF0, params.hpp:17 (parsers.cpp:484-486)
+
+    if (LAYOUT == 1) {
+        // parsers.cpp:484-499: SH0, opacity logit, log scale (per triangle)
+        float2* s2 = reinterpret_cast<float2*>(srec_bytes);
+        s2[0] = make_float2(Px, Py);
+        s2[1] = make_float2(Pz, tf.quat[0]);
+        s2[2] = make_float2(tf.quat[1], tf.quat[2]);
+        s2[3] = make_float2(tf.quat[3], tf.scale[0]);
+        s2[4] = make_float2(tf.scale[1], a.log_sz);
+        s2[5] = make_float2((cr - 0.5f) * kInvC0, (cg - 0.5f) * kInvC0);
+        s2[6] = make_float2((cb - 0.5f) * kInvC0, inv_sigmoid_fast(ca));
+        return;
+    }
+    // ---- every other layout carries the shading normal; PBR values where the layout has them ----
+    constexpr int MN = kMaps > 1 ? 1 : 0, MM = kMaps > 2 ? 2 : 0;
+    const float Nx = l0 * a0.w + l1 * b0.w + l2 * c0.w;
+    const float4 a1 = v[1], b1 = v[4], c1 = v[7];
+    const float Ny = l0 * a1.x + l1 * b1.x + l2 * c1.x, Nz = l0 * a1.y + l1 * b1.y + l2 * c1.y;
+    float nx = Nx, ny = Ny, nz = Nz;
+    if (has[MN]) {  // :64-77 TBN
+        const float f = tf.frac[MN];
+        float mx = filt<0>(bl[MN][0], tx[MN][0], tx[MN][1], tx[MN][2], tx[MN][3]);
+        float my = filt<1>(bl[MN][0], tx[MN][0], tx[MN][1], tx[MN][2], tx[MN][3]);
+        float mz = filt<2>(bl[MN][0], tx[MN][0], tx[MN][1], tx[MN][2], tx[MN][3]);
+        if (two[MN]) {
+            mx += f * (filt<0>(bl[MN][1], tx[MN][4], tx[MN][5], tx[MN][6], tx[MN][7]) - mx);
+            my += f * (filt<1>(bl[MN][1], tx[MN][4], tx[MN][5], tx[MN][6], tx[MN][7]) - my);
+            mz += f * (filt<2>(bl[MN][1], tx[MN][4], tx[MN][5], tx[MN][6], tx[MN][7]) - mz);
+        }
+        const float Tx = l0 * a1.z + l1 * b1.z + l2 * c1.z, Ty = l0 * a1.w + l1 * b1.w + l2 * c1.w;
+        const float Tz = l0 * a2.x + l1 * b2.x + l2 * c2.x, Tw = l0 * a2.y + l1 * b2.y + l2 * c2.y;
+        float rx = mx * 2.0f - 1.0f, ry = my * 2.0f - 1.0f, rz = mz * 2.0f - 1.0f;
+        float inv = rsqrtf(rx * rx + ry * ry + rz * rz);
+        rx *= inv; ry *= inv; rz *= inv;
+        float bx = Ny * Tz - Ty * Nz, by = Nz * Tx - Tz * Nx, bz = Nx * Ty - Tx * Ny;  // cross(N,T)
+        inv = Tw * rsqrtf(bx * bx + by * by + bz * bz);
+        bx *= inv; by *= inv; bz *= inv;
+        inv = rsqrtf(Nx * Nx + Ny * Ny + Nz * Nz);
+        const float ox = Tx * rx + bx * ry + Nx * inv * rz, oy = Ty * rx + by * ry + Ny * inv * rz,
+                    oz = Tz * rx + bz * ry + Nz * inv * rz;
+        inv = rsqrtf(ox * ox + oy * oy + oz * oz);
+        nx = ox * inv; ny = oy * inv; nz = oz * inv;
+    }
+    float metal = 0.1f, rough = 0.5f;  // :83-95 (.bg)
+    if (LAYOUT != 2 && has[MM]) {      // the standard .ply row carries no PBR values
+        const float f = tf.frac[MM];
+        rough = filt<1>(bl[MM][0], tx[MM][0], tx[MM][1], tx[MM][2], tx[MM][3]);
+        metal = filt<2>(bl[MM][0], tx[MM][0], tx[MM][1], tx[MM][2], tx[MM][3]);
+        if (two[MM]) {
+            rough += f * (filt<1>(bl[MM][1], tx[MM][4], tx[MM][5], tx[MM][6], tx[MM][7]) - rough);
+            metal += f * (filt<2>(bl[MM][1], tx[MM][4], tx[MM][5], tx[MM][6], tx[MM][7]) - metal);
+        }
+    }
+    if (LAYOUT == 0) {
+        float4* s4 = reinterpret_cast<float4*>(srec_bytes);
+        s4[0] = make_float4(Px, Py, Pz, 1.0f);
+        s4[1] = make_float4(cr, cg, cb, ca);
+        s4[2] = make_float4(tf.scale[0], tf.scale[1], 1e-7f, 0.0f);
+        s4[3] = make_float4(nx, ny, nz, 0.0f);
+        s4[4] = make_float4(tf.quat[0], tf.quat[1], tf.quat[2], tf.quat[3]);
+        s4[5] = make_float4(metal, rough, 0.0f, 1.0f);
+    } else if (LAYOUT == 2) {  // parsers.cpp:431-514: xyz n f_dc f_rest(45 x 0) opacity scale rot — 62 floats, 8-byte aligned rows
+        float2* s2 = reinterpret_cast<float2*>(srec_bytes);
+        s2[0] = make_float2(Px, Py); s2[1] = make_float2(Pz, nx); s2[2] = make_float2(ny, nz);
+        s2[3] = make_float2((cr - 0.5f) * kInvC0, (cg - 0.5f) * kInvC0);
+        s2[4] = make_float2((cb - 0.5f) * kInvC0, 0.0f);
+#pragma unroll
+        for (int k = 5; k < 27; ++k) s2[k] = make_float2(0.0f, 0.0f);
+        s2[27] = make_float2(inv_sigmoid_fast(ca), tf.scale[0]);
+        s2[28] = make_float2(tf.scale[1], a.log_sz);
+        s2[29] = make_float2(tf.quat[0], tf.quat[1]);
+        s2[30] = make_float2(tf.quat[2], tf.quat[3]);
+    } else if (LAYOUT == 3) {  // parsers.cpp:232-316: 19 floats, 4-byte aligned rows
+        float* f = reinterpret_cast<float*>(srec_bytes);
+        f[0] = Px; f[1] = Py; f[2] = Pz; f[3] = nx; f[4] = ny; f[5] = nz;
+        f[6] = (cr - 0.5f) * kInvC0; f[7] = (cg - 0.5f) * kInvC0; f[8] = (cb - 0.5f) * kInvC0;
+        f[9] = metal; f[10] = rough; f[11] = inv_sigmoid_fast(ca);
+        f[12] = tf.scale[0]; f[13] = tf.scale[1]; f[14] = a.log_sz;
+        f[15] = tf.quat[0]; f[16] = tf.quat[1]; f[17] = tf.quat[2]; f[18] = tf.quat[3];
+    } else {                   // parsers.cpp:339-428: 48-byte rows
+        float* f = reinterpret_cast<float*>(srec_bytes);
+        unsigned char* p = srec_bytes;
+        f[0] = Px; f[1] = Py; f[2] = Pz;
+        *reinterpret_cast<uchar4*>(p + 12) = make_uchar4(to_byte(cr), to_byte(cg), to_byte(cb), to_byte(ca));
+        f[4] = tf.quat[0]; f[5] = tf.quat[1]; f[6] = tf.quat[2]; f[7] = tf.quat[3];
+        f[8] = tf.scale[0]; f[9] = tf.scale[1]; f[10] = fminf(tf.scale[0], tf.scale[1]);  // log(min(sx,sy) * mult): log is monotonic
+        // octahedral normal (parsers.cpp:318-337)
+        const float s = fabsf(nx) + fabsf(ny) + fabsf(nz) + 1e-8f;
+        const float ox = nx / s, oy = ny / s, oz = nz / s;
+        float rx, ry;
+        if (oz >= 0.0f) { rx = ox; ry = oy; }
+        else {
+            const float m = (ox >= 0.0f && oy >= 0.0f) ? 1.0f : -1.0f;
+            rx = (1.0f - fabsf(oy)) * m; ry = (1.0f - fabsf(ox)) * m;
+        }
+        const float qx = fminf(fmaxf(roundf((rx * 0.5f + 0.5f) * 255.0f), 0.0f), 255.0f);
+        const float qy = fminf(fmaxf(roundf((ry * 0.5f + 0.5f) * 255.0f), 0.0f), 255.0f);
+        *reinterpret_cast<uchar4*>(p + 44) = make_uchar4((unsigned char)qx, (unsigned char)qy, to_byte(rough), to_byte(metal));
+    }
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(kFragThreads) fragment_kernel(const __grid_constant__ ConvertArgs a) {
+    using S = FragSmem<LAYOUT>;
+    using Rec = typename S::Rec;
+    constexpr int kStride = Cfg<LAYOUT>::kStride;
     extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    __shared__ unsigned long long s_goff;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char* stage = smem + (size_t)warp * 32 * kStride;  // this warp's 32 records
+    const Rec* recs = reinterpret_cast<const Rec*>(smem + S::kRecOff);
+    const float4* tris = reinterpret_cast<const float4*>(smem + S::kTriOff);
+    uint32_t* span = reinterpret_cast<uint32_t*>(smem + S::kSpanOff);
+    unsigned char* stage = smem + S::kStageOff + (size_t)warp * 32 * kStride;  // this warp's 32 records
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
     // launched with programmatic stream serialisation: the CTAs of this grid are placed while the raster
     // kernel drains; everything it wrote is visible after this wait
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    const unsigned long long total = *reinterpret_cast<const volatile unsigned long long*>(a.total_out);
     // appended launches (m2s_convert_host pipelines a scene in triangle chunks): this launch's records follow
     // those of the earlier chunks; the cap applies to the running index, as the reference's counter does
     unsigned long long base = 0;
     for (uint32_t j = 0; j < a.nprev; ++j) base += *reinterpret_cast<const volatile unsigned long long*>(a.prev_totals + j);
     const unsigned long long room = a.cap > base ? a.cap - base : 0ull;
-    const unsigned long long n = total < room ? total : room;
     // fused gather: wait for every rank's count of this epoch, my records start after the lower ranks'
-    __shared__ unsigned long long s_goff;
     unsigned long long goff = 0;
     if (a.world > 1) {
         if (threadIdx.x == 0) {
@@ -924,169 +1010,146 @@ __global__ void __launch_bounds__(M2S_FRAG_THREADS) fragment_kernel(const __grid
         __syncthreads();
         goff = s_goff;
     }
+    const uint32_t nq = min(*reinterpret_cast<const volatile uint32_t*>(a.n_items_out), a.queue_cap);
+    const uint32_t nitems = a.n_units + nq;
     const uint32_t* __restrict__ texb = a.tex_base;
     const bool want_keys = a.keys != nullptr;
-    const unsigned long long nwarps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
-    for (unsigned long long g = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + warp; g * 32 < n; g += nwarps) {
-        const unsigned long long wbase = g * 32;
-        const uint32_t nfr = (uint32_t)min(32ull, n - wbase);
-        unsigned long long key = 0;
-        if ((uint32_t)lane < nfr) {
-            const uint2 fid = __ldg(a.frag_ids + wbase + lane);
-            const uint32_t tl = fid.x - a.tri_first;
-            const int py = (fid.y >> 12) & 0xfff, px = fid.y & 0xfff;
-#ifdef M2S_FRAG_PREFETCH
-            // Tuning build (off): the stall samples of this kernel sit on four serial load waits — fragment id ->
-            // triangle record -> vertices -> texels (profiles/r01_fragment_kernel_*.md: 14.8 + 13.2 + 16.6 + 10.3 % of
-            // the samples).  Pull the position vertices (read last, after the texel loads were issued) into L1 as soon
-            // as the triangle is known, and the next iteration's fragment ids while this one is shaded.
-            {
-                const float4* pv = a.tris + (size_t)fid.x * 9;
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(pv));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(pv + 3));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(pv + 6));
-                if ((g + nwarps) * 32 < n) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.frag_ids + (g + nwarps) * 32 + lane));
-            }
-#endif
-            const TriFragT<C::kMaps> tf = *reinterpret_cast<const TriFragT<C::kMaps>*>(a.tri_frag + (size_t)tl * sizeof(TriFragT<C::kMaps>));
-            const unsigned meta = tf.meta;
-            const int dxi = px - (int)((meta >> 4) & 0xfffu), dyi = py - (int)((meta >> 16) & 0xfffu);
-            const float l0 = __ll2float_rn(tf.E0[0] + (long long)tf.A[0] * dxi + (long long)tf.B[0] * dyi) * tf.inv_area;
-            const float l1 = __ll2float_rn(tf.E0[1] + (long long)tf.A[1] * dxi + (long long)tf.B[1] * dyi) * tf.inv_area;
-            const float l2 = __ll2float_rn(tf.E0[2] + (long long)tf.A[2] * dxi + (long long)tf.B[2] * dyi) * tf.inv_area;
-            const float4* __restrict__ v = a.tris + (size_t)fid.x * 9;  // 3 x {pos3 nrm3 tan4 uv2}, L2-resident
-            // uv first: the texel addresses depend on nothing else
-            const float4 a2 = __ldg(v + 2), b2 = __ldg(v + 5), c2 = __ldg(v + 8);
-            const float u = l0 * a2.z + l1 * b2.z + l2 * c2.z, vv = l0 * a2.w + l1 * b2.w + l2 * c2.w;
+    uint32_t phase = 0;
 
-            // ---- issue every texel load of every bound map back to back ----
-            uint32_t tx[C::kMaps][8];
-            Bilin bl[C::kMaps][2];
-            bool has[C::kMaps], two[C::kMaps];
-            uint32_t offs0[C::kMaps], offs1[C::kMaps];
-#pragma unroll
-            for (int m = 0; m < C::kMaps; ++m) {
-                const TexRef ref = tf.tex[m];
-                has[m] = ref.off0 != 0xffffffffu;
-                two[m] = has[m] && tf.frac[m] > 0.0f;
-                offs0[m] = has[m] ? ref.off0 : 0u;
-                offs1[m] = ref.off1;
-                if (m == 0 || !((meta >> m) & 1u)) {
-                    bl[m][0] = bilin_setup(ref.w0, ref.h0, u, vv);
-                    bl[m][1] = bilin_setup(ref.w1, ref.h1, u, vv);
-                } else { bl[m][0] = bl[0][0]; bl[m][1] = bl[0][1]; }
-            }
-#pragma unroll
-            for (int m = 0; m < C::kMaps; ++m) {
-                const uint32_t o0 = offs0[m], o1 = offs1[m];  // uniform base + 32-bit texel index
-                tx[m][0] = has[m] ? __ldg(texb + (o0 + bl[m][0].i00)) : 0u; tx[m][1] = has[m] ? __ldg(texb + (o0 + bl[m][0].i10)) : 0u;
-                tx[m][2] = has[m] ? __ldg(texb + (o0 + bl[m][0].i01)) : 0u; tx[m][3] = has[m] ? __ldg(texb + (o0 + bl[m][0].i11)) : 0u;
-                tx[m][4] = two[m] ? __ldg(texb + (o1 + bl[m][1].i00)) : 0u; tx[m][5] = two[m] ? __ldg(texb + (o1 + bl[m][1].i10)) : 0u;
-                tx[m][6] = two[m] ? __ldg(texb + (o1 + bl[m][1].i01)) : 0u; tx[m][7] = two[m] ? __ldg(texb + (o1 + bl[m][1].i11)) : 0u;
-            }
-            // ---- interpolate the remaining varyings while the loads are in flight ----
-            const float4 a0 = __ldg(v + 0), b0 = __ldg(v + 3), c0 = __ldg(v + 6);
-            const float Px = l0 * a0.x + l1 * b0.x + l2 * c0.x, Py = l0 * a0.y + l1 * b0.y + l2 * c0.y,
-                        Pz = l0 * a0.z + l1 * b0.z + l2 * c0.z;
-            float* srec = reinterpret_cast<float*>(stage + lane * kStride);
-
-            // colour (converterFS.glsl:55-62,99)
-            float cr = 1.f, cg = 1.f, cb = 1.f, ca = 1.f;
-            if (has[0]) {
-                const float f = tf.frac[0];
-                cr = filt<0>(bl[0][0], tx[0][0], tx[0][1], tx[0][2], tx[0][3]);
-                cg = filt<1>(bl[0][0], tx[0][0], tx[0][1], tx[0][2], tx[0][3]);
-                cb = filt<2>(bl[0][0], tx[0][0], tx[0][1], tx[0][2], tx[0][3]);
-                ca = filt<3>(bl[0][0], tx[0][0], tx[0][1], tx[0][2], tx[0][3]);
-                if (two[0]) {
-                    cr += f * (filt<0>(bl[0][1], tx[0][4], tx[0][5], tx[0][6], tx[0][7]) - cr);
-                    cg += f * (filt<1>(bl[0][1], tx[0][4], tx[0][5], tx[0][6], tx[0][7]) - cg);
-                    cb += f * (filt<2>(bl[0][1], tx[0][4], tx[0][5], tx[0][6], tx[0][7]) - cb);
-                    ca += f * (filt<3>(bl[0][1], tx[0][4], tx[0][5], tx[0][6], tx[0][7]) - ca);
-                }
-            }
-            cr *= tf.factor[0]; cg *= tf.factor[1]; cb *= tf.factor[2]; ca *= tf.factor[3];
-
-            if (LAYOUT == 0) {
-                const float Nx = l0 * a0.w + l1 * b0.w + l2 * c0.w;
-                const float4 a1 = __ldg(v + 1), b1 = __ldg(v + 4), c1 = __ldg(v + 7);
-                const float Ny = l0 * a1.x + l1 * b1.x + l2 * c1.x, Nz = l0 * a1.y + l1 * b1.y + l2 * c1.y;
-                float nx = Nx, ny = Ny, nz = Nz;
-                constexpr int MN = C::kMaps > 1 ? 1 : 0, MM = C::kMaps > 2 ? 2 : 0;
-                if (has[MN]) {  // :64-77 TBN
-                    const float f = tf.frac[MN];
-                    float mx = filt<0>(bl[MN][0], tx[MN][0], tx[MN][1], tx[MN][2], tx[MN][3]);
-                    float my = filt<1>(bl[MN][0], tx[MN][0], tx[MN][1], tx[MN][2], tx[MN][3]);
-                    float mz = filt<2>(bl[MN][0], tx[MN][0], tx[MN][1], tx[MN][2], tx[MN][3]);
-                    if (two[MN]) {
-                        mx += f * (filt<0>(bl[MN][1], tx[MN][4], tx[MN][5], tx[MN][6], tx[MN][7]) - mx);
-                        my += f * (filt<1>(bl[MN][1], tx[MN][4], tx[MN][5], tx[MN][6], tx[MN][7]) - my);
-                        mz += f * (filt<2>(bl[MN][1], tx[MN][4], tx[MN][5], tx[MN][6], tx[MN][7]) - mz);
-                    }
-                    const float Tx = l0 * a1.z + l1 * b1.z + l2 * c1.z, Ty = l0 * a1.w + l1 * b1.w + l2 * c1.w;
-                    const float Tz = l0 * a2.x + l1 * b2.x + l2 * c2.x, Tw = l0 * a2.y + l1 * b2.y + l2 * c2.y;
-                    float rx = mx * 2.0f - 1.0f, ry = my * 2.0f - 1.0f, rz = mz * 2.0f - 1.0f;
-                    float inv = rsqrtf(rx * rx + ry * ry + rz * rz);
-                    rx *= inv; ry *= inv; rz *= inv;
-                    float bx = Ny * Tz - Ty * Nz, by = Nz * Tx - Tz * Nx, bz = Nx * Ty - Tx * Ny;  // cross(N,T)
-                    inv = Tw * rsqrtf(bx * bx + by * by + bz * bz);
-                    bx *= inv; by *= inv; bz *= inv;
-                    inv = rsqrtf(Nx * Nx + Ny * Ny + Nz * Nz);
-                    const float ox = Tx * rx + bx * ry + Nx * inv * rz, oy = Ty * rx + by * ry + Ny * inv * rz,
-                                oz = Tz * rx + bz * ry + Nz * inv * rz;
-                    inv = rsqrtf(ox * ox + oy * oy + oz * oz);
-                    nx = ox * inv; ny = oy * inv; nz = oz * inv;
-                }
-                float metal = 0.1f, rough = 0.5f;  // :83-95 (.bg)
-                if (has[MM]) {
-                    const float f = tf.frac[MM];
-                    rough = filt<1>(bl[MM][0], tx[MM][0], tx[MM][1], tx[MM][2], tx[MM][3]);
-                    metal = filt<2>(bl[MM][0], tx[MM][0], tx[MM][1], tx[MM][2], tx[MM][3]);
-                    if (two[MM]) {
-                        rough += f * (filt<1>(bl[MM][1], tx[MM][4], tx[MM][5], tx[MM][6], tx[MM][7]) - rough);
-                        metal += f * (filt<2>(bl[MM][1], tx[MM][4], tx[MM][5], tx[MM][6], tx[MM][7]) - metal);
-                    }
-                }
-                float4* s4 = reinterpret_cast<float4*>(srec);
-                s4[0] = make_float4(Px, Py, Pz, 1.0f);
-                s4[1] = make_float4(cr, cg, cb, ca);
-                s4[2] = make_float4(tf.scale[0], tf.scale[1], tf.scale[2], 0.0f);
-                s4[3] = make_float4(nx, ny, nz, 0.0f);
-                s4[4] = make_float4(tf.quat[0], tf.quat[1], tf.quat[2], tf.quat[3]);
-                s4[5] = make_float4(metal, rough, 0.0f, 1.0f);
-            } else {
-                // parsers.cpp:484-499: SH0, opacity logit, log scale (per triangle)
-                float2* s2 = reinterpret_cast<float2*>(srec);
-                s2[0] = make_float2(Px, Py);
-                s2[1] = make_float2(Pz, tf.quat[0]);
-                s2[2] = make_float2(tf.quat[1], tf.quat[2]);
-                s2[3] = make_float2(tf.quat[3], tf.scale[0]);
-                s2[4] = make_float2(tf.scale[1], tf.scale[2]);
-                const float kC0 = 0.28209479177387814f;  // SH_COEFF0, params.hpp:17
-                s2[5] = make_float2(__fdiv_rn(cr - 0.5f, kC0), __fdiv_rn(cg - 0.5f, kC0));
-                s2[6] = make_float2(__fdiv_rn(cb - 0.5f, kC0), inv_sigmoid(ca));
-            }
-            if (want_keys) key = ((unsigned long long)fid.x << 24) | (unsigned long long)fid.y;
-        }
-        __syncwarp();
-        // ---- the warp's records are one contiguous span: straight vector copy -----------------------
-        if (a.world <= 1) {
-            copy_span<kStride>(a.out, (base + wbase) * (unsigned long long)kStride, stage, nfr * kStride, lane);
+    for (uint32_t it = blockIdx.x; it < nitems; it += gridDim.x) {
+        // ---- the item: a unit's small triangles (implicit: one block per triangle) or queued row blocks ----
+        unsigned long long first;
+        uint32_t unit, nblocks, fb, fe;
+        uint32_t bprefix = 0xffffffffu, bref = 0;  // lane b: block b of the item
+        const bool unit_item = it < a.n_units;
+        if (unit_item) {
+            unit = it;
+            const uint4 d = __ldg(reinterpret_cast<const uint4*>(a.unit_desc + unit));
+            first = (unsigned long long)d.x | ((unsigned long long)d.y << 32);
+            fb = 0; fe = d.z;
+            nblocks = min(a.unit_tris, a.tri_count - unit * a.unit_tris);
         } else {
-            // fused gather: the same span goes to the final buffer of EVERY rank (peer stores over NVLink)
-            const unsigned long long gbase = goff + wbase;
-            uint32_t nval = 0;
-            if (gbase < a.gcap) nval = (uint32_t)min((unsigned long long)nfr, a.gcap - gbase);
-            // destinations are visited in a rotated order (by rank and by span) so that at any moment the
-            // grid's stores are spread over all peers' ingress ports instead of converging on peer 0
-            uint32_t p = (a.rank + 1u + (uint32_t)g) % a.world;
-            for (uint32_t i = 0; i < a.world; ++i) {
-                copy_span<kStride>(a.peer_out[p], gbase * (unsigned long long)kStride, stage, nval * kStride, lane);
-                p = p + 1 == a.world ? 0 : p + 1;
+            const FragItem* q = a.items + (it - a.n_units);
+            const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(q));
+            const uint2 h1 = __ldg(reinterpret_cast<const uint2*>(q) + 2);
+            first = (unsigned long long)h0.x | ((unsigned long long)h0.y << 32);
+            unit = h0.z; nblocks = h0.w; fb = h1.x; fe = h1.y;
+            if ((uint32_t)lane < nblocks) {
+                const uint2 b = __ldg(reinterpret_cast<const uint2*>(q->blocks + lane));
+                bprefix = b.x; bref = b.y;
             }
         }
-        if (want_keys && (uint32_t)lane < nfr) a.keys[base + wbase + lane] = key;
-        __syncwarp();
+        if (fe <= fb || first + fb >= room) continue;  // uniform over the CTA: nothing to emit
+        const uint32_t t0 = unit * a.unit_tris;
+        const uint32_t ntri = min(a.unit_tris, a.tri_count - t0);
+        if (threadIdx.x == 0) {  // stage the unit's records and vertices: two TMA bulk copies, one mbarrier
+            const uint32_t rb = ntri * (uint32_t)sizeof(Rec), tb = ntri * (uint32_t)kTriBytes;
+            fence_proxy_async();
+            mbar_arrive_expect_tx(&bar, rb + tb);
+            tma_load_1d(smem + S::kRecOff, a.tri_frag + (size_t)t0 * sizeof(Rec), rb, &bar);
+            tma_load_1d(smem + S::kTriOff, reinterpret_cast<const unsigned char*>(a.tris) + ((size_t)a.tri_first + t0) * kTriBytes, tb, &bar);
+        }
+        mbar_wait(&bar, phase);
+        phase ^= 1;
+        if (unit_item && (uint32_t)lane < nblocks) {  // block b = triangle b: its rows are the rows of the coverage mask
+            const unsigned box = recs[lane].box;
+            const uint32_t rows = (box & kBoxSmall) ? ((box >> 13) & 0x1fffu) : 0u;
+            bprefix = recs[lane].first;
+            bref = (uint32_t)lane | (rows << 17);
+        }
+        // ---- row spans of the item's blocks: prefix << 12 | first column, one word per row ----
+        for (uint32_t b = warp; b < nblocks; b += kFragWarps) {
+            const uint32_t ref = __shfl_sync(0xffffffffu, bref, (int)b), bp = __shfl_sync(0xffffffffu, bprefix, (int)b);
+            const uint32_t slot = ref & 31u, row_begin = (ref >> 5) & 0xfffu, nrows = (ref >> 17) & 63u;
+            const Rec& r = recs[slot];
+            const unsigned box = r.box;
+            const int w = (int)(box & 0x1fffu);
+            uint32_t n = 0;
+            int xl = 0;
+            if ((uint32_t)lane < nrows) {
+                if (box & kBoxSmall) {
+                    const unsigned long long rowmask = w >= 64 ? ~0ull : ((1ull << w) - 1ull);
+                    const unsigned long long bits = (r.hits >> (lane * w)) & rowmask;  // lane < h, h * w <= 64
+                    n = (uint32_t)__popcll(bits);
+                    xl = bits ? __ffsll((long long)bits) - 1 : 0;
+                } else {
+                    RowState rs;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        rs.E[k] = r.E0[k] - (((box >> (26 + k)) & 1u) ? 0 : 1);
+                        rs.A[k] = r.A[k]; rs.B[k] = r.B[k];
+                    }
+                    rs.w = w;
+                    n = span_row(rs, (int)(row_begin + lane), xl);
+                }
+            }
+            uint32_t incl = n;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            span[b * 32 + lane] = ((bp + incl - n) << 12) | (uint32_t)xl;  // rows past the block: prefix = block end
+        }
+        __syncthreads();
+
+        // ---- 32 consecutive fragments per warp step ----
+        const uint32_t nfrag = fe - fb;
+        for (uint32_t g = warp; g * 32 < nfrag; g += kFragWarps) {
+            const uint32_t j0 = fb + g * 32;
+            const uint32_t nfr = min(32u, fe - j0);
+            const uint32_t j = j0 + min((uint32_t)lane, nfr - 1);  // idle lanes shadow the last fragment
+            // block: the last one whose prefix is <= j (blocks without fragments share their successor's prefix)
+            uint32_t b = 0;
+#pragma unroll
+            for (int stp = 16; stp > 0; stp >>= 1) {
+                const uint32_t c = b + stp;
+                const uint32_t pv = __shfl_sync(0xffffffffu, bprefix, (int)(c & 31u));
+                if (c < nblocks && pv <= j) b = c;
+            }
+            const uint32_t ref = __shfl_sync(0xffffffffu, bref, (int)b);
+            const uint32_t slot = ref & 31u, row_begin = (ref >> 5) & 0xfffu;
+            // row: the last one whose prefix is <= j
+            const uint32_t* sp = span + b * 32;
+            uint32_t r = 0;
+#pragma unroll
+            for (int stp = 16; stp > 0; stp >>= 1) {
+                const uint32_t c = r + stp;
+                if ((sp[c] >> 12) <= j) r = c;
+            }
+            const uint32_t sw = sp[r];
+            const int dxi = (int)((sw & 0xfffu) + (j - (sw >> 12))), dyi = (int)(row_begin + r);
+            const Rec& tf = recs[slot];
+            if ((uint32_t)lane < nfr) shade<LAYOUT>(a, tf, tris + slot * 9, dxi, dyi, texb, stage + lane * kStride);
+            __syncwarp();
+            // ---- the warp's records are one contiguous span: straight vector copy -----------------------
+            const unsigned long long idx0 = first + j0;  // index within this launch
+            uint32_t nval = 0;
+            if (idx0 < room) nval = (uint32_t)min((unsigned long long)nfr, room - idx0);
+            if (a.world <= 1) {
+                copy_span<kStride>(a.out, (base + idx0) * (unsigned long long)kStride, stage, nval * kStride, lane);
+            } else {
+                // fused gather: the same span goes to the final buffer of EVERY rank (peer stores over NVLink)
+                const unsigned long long gbase = goff + idx0;
+                uint32_t gval = 0;
+                if (gbase < a.gcap) gval = (uint32_t)min((unsigned long long)nval, a.gcap - gbase);
+                // destinations are visited in a rotated order (by rank and by span) so that at any moment the
+                // grid's stores are spread over all peers' ingress ports instead of converging on peer 0
+                uint32_t p = (a.rank + 1u + it + g) % a.world;
+                for (uint32_t i = 0; i < a.world; ++i) {
+                    copy_span<kStride>(a.peer_out[p], gbase * (unsigned long long)kStride, stage, gval * kStride, lane);
+                    p = p + 1 == a.world ? 0 : p + 1;
+                }
+            }
+            if (want_keys && (uint32_t)lane < nval) {  // fragment identity: triangle << 24 | y << 12 | x
+                const unsigned meta = tf.meta;
+                const unsigned long long tg = a.tri_first + t0 + slot;
+                a.keys[base + idx0 + lane] = (tg << 24) | ((unsigned long long)(((meta >> 16) & 0xfffu) + (unsigned)dyi) << 12) |
+                                             (unsigned long long)(((meta >> 4) & 0xfffu) + (unsigned)dxi);
+            }
+            __syncwarp();
+        }
+        __syncthreads();  // the next item's TMA overwrites the staged unit and the span table
     }
     if (a.world > 1) {  // last CTA out tells every peer that this rank's records have landed
         __threadfence_system();
@@ -1140,10 +1203,6 @@ __global__ void mip_down_kernel(const uint32_t* __restrict__ src, uint32_t sw, u
 // ------------------------------------------------------------------------------------------
 // .ply body rows from REF96 records (parsers.cpp:232-316,339-428,431-514)
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned char to_byte(float v) {
-    v = fminf(fmaxf(v, 0.0f), 1.0f);
-    return (unsigned char)roundf(v * 255.0f);
-}
 __global__ void ply_rows_kernel(const float4* __restrict__ rec, unsigned long long count,
                                 const unsigned long long* __restrict__ d_count, uint32_t format, float mult,
                                 unsigned char* __restrict__ rows) {
@@ -1194,35 +1253,67 @@ __global__ void ply_rows_kernel(const float4* __restrict__ rec, unsigned long lo
 // ------------------------------------------------------------------------------------------
 // launch wrappers used by m2s_api.cu
 // ------------------------------------------------------------------------------------------
+static int raster_kind(int layout) { return layout == 0 ? 0 : (layout == 1 ? 1 : 2); }
 size_t raster_smem_bytes(int layout) {
-    return (layout == 0 ? sizeof(WarpBlock<0>) * Cfg<0>::kWarps : sizeof(WarpBlock<1>) * Cfg<1>::kWarps) + kTableSmemBytes;
+    const int rk = raster_kind(layout);
+    const size_t wb = rk == 0 ? sizeof(WarpBlock<0>) : (rk == 1 ? sizeof(WarpBlock<1>) : sizeof(WarpBlock<2>));
+    return wb * M2S_RASTER_WARPS + kTableSmemBytes;
 }
-size_t fragment_smem_bytes(int layout) { return (size_t)(M2S_FRAG_THREADS / 32) * 32 * (layout == 0 ? Cfg<0>::kStride : Cfg<1>::kStride); }
-int convert_warps_per_cta(int layout) { return layout == 0 ? Cfg<0>::kWarps : Cfg<1>::kWarps; }
-size_t tri_frag_bytes(int layout) { return layout == 0 ? sizeof(TriFragT<Cfg<0>::kMaps>) : sizeof(TriFragT<Cfg<1>::kMaps>); }
+size_t fragment_smem_bytes(int layout) {
+    switch (layout) {
+        case 0: return FragSmem<0>::kBytes;
+        case 1: return FragSmem<1>::kBytes;
+        case 2: return FragSmem<2>::kBytes;
+        case 3: return FragSmem<3>::kBytes;
+        default: return FragSmem<4>::kBytes;
+    }
+}
+int convert_warps_per_cta(int) { return M2S_RASTER_WARPS; }
+size_t tri_frag_bytes(int layout) { return raster_kind(layout) == 1 ? sizeof(TriRec<1>) : sizeof(TriRec<3>); }
+
+template <int RK>
+static cudaError_t configure_raster(size_t smem, int* blocks) {
+    cudaError_t e = cudaFuncSetAttribute(raster_kernel<RK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, raster_kernel<RK>, M2S_RASTER_WARPS * 32, smem);
+}
+template <int L>
+static cudaError_t configure_fragment(size_t smem, int* blocks) {
+    cudaError_t e = cudaFuncSetAttribute(fragment_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, fragment_kernel<L>, kFragThreads, smem);
+}
 
 cudaError_t convert_configure(int layout, int* raster_blocks_per_sm, int* fragment_blocks_per_sm) {
-    cudaError_t e;
     const size_t smem = raster_smem_bytes(layout), fsmem = fragment_smem_bytes(layout);
-    if (layout == 0) {
-        e = cudaFuncSetAttribute(raster_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(raster_blocks_per_sm, raster_kernel<0>, Cfg<0>::kWarps * 32, smem);
-        if (e != cudaSuccess) return e;
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(fragment_blocks_per_sm, fragment_kernel<0>, M2S_FRAG_THREADS, fsmem);
+    cudaError_t e;
+    switch (raster_kind(layout)) {
+        case 0: e = configure_raster<0>(smem, raster_blocks_per_sm); break;
+        case 1: e = configure_raster<1>(smem, raster_blocks_per_sm); break;
+        default: e = configure_raster<2>(smem, raster_blocks_per_sm); break;
     }
-    e = cudaFuncSetAttribute(raster_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(raster_blocks_per_sm, raster_kernel<1>, Cfg<1>::kWarps * 32, smem);
-    if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(fragment_blocks_per_sm, fragment_kernel<1>, M2S_FRAG_THREADS, fsmem);
+    switch (layout) {
+        case 0: return configure_fragment<0>(fsmem, fragment_blocks_per_sm);
+        case 1: return configure_fragment<1>(fsmem, fragment_blocks_per_sm);
+        case 2: return configure_fragment<2>(fsmem, fragment_blocks_per_sm);
+        case 3: return configure_fragment<3>(fsmem, fragment_blocks_per_sm);
+        default: return configure_fragment<4>(fsmem, fragment_blocks_per_sm);
+    }
 }
 
 cudaError_t convert_launch(int layout, const ConvertArgs& args, int raster_grid, int fragment_grid, cudaStream_t stream) {
     const size_t smem = raster_smem_bytes(layout), fsmem = fragment_smem_bytes(layout);
+    switch (raster_kind(layout)) {
+        case 0: raster_kernel<0><<<raster_grid, M2S_RASTER_WARPS * 32, smem, stream>>>(args); break;
+        case 1: raster_kernel<1><<<raster_grid, M2S_RASTER_WARPS * 32, smem, stream>>>(args); break;
+        default: raster_kernel<2><<<raster_grid, M2S_RASTER_WARPS * 32, smem, stream>>>(args); break;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)fragment_grid);
-    cfg.blockDim = dim3(M2S_FRAG_THREADS);
+    cfg.blockDim = dim3(kFragThreads);
     cfg.dynamicSmemBytes = fsmem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -1234,16 +1325,13 @@ cudaError_t convert_launch(int layout, const ConvertArgs& args, int raster_grid,
 #else
     cfg.numAttrs = 0;
 #endif
-    if (layout == 0) {
-        raster_kernel<0><<<raster_grid, Cfg<0>::kWarps * 32, smem, stream>>>(args);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-        return cudaLaunchKernelEx(&cfg, fragment_kernel<0>, args);
+    switch (layout) {
+        case 0: return cudaLaunchKernelEx(&cfg, fragment_kernel<0>, args);
+        case 1: return cudaLaunchKernelEx(&cfg, fragment_kernel<1>, args);
+        case 2: return cudaLaunchKernelEx(&cfg, fragment_kernel<2>, args);
+        case 3: return cudaLaunchKernelEx(&cfg, fragment_kernel<3>, args);
+        default: return cudaLaunchKernelEx(&cfg, fragment_kernel<4>, args);
     }
-    raster_kernel<1><<<raster_grid, Cfg<1>::kWarps * 32, smem, stream>>>(args);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    return cudaLaunchKernelEx(&cfg, fragment_kernel<1>, args);
 }
 
 cudaError_t gather_wait_launch(const unsigned long long* xch, uint32_t world, unsigned long long epoch, unsigned long long gcap,
