@@ -159,6 +159,16 @@ m2s_status m2s_compute_bboxes(const float* triangles, m2s_primitive* primitives,
 /* Copies triangles + primitive table + textures to the device and builds mip levels 1..4
  * (2x2 box, round-to-nearest) on the GPU.  Host pointers may be pageable. */
 m2s_status m2s_scene_upload(m2s_ctx* ctx, const m2s_scene* scene, m2s_dscene** out);
+/* One shard of a scene (multi-GPU: one contiguous triangle range per rank): copies the triangles
+ * [first_triangle, first_triangle + triangle_count) to their global positions and, of the maps `layout` consumes, only
+ * the texture rows those triangles can sample (16-row groups incl. their mip rows, REPEAT wrap and all five levels'
+ * footprints considered).  Converting any triangle outside the range with the returned scene is undefined. */
+m2s_status m2s_scene_upload_range(m2s_ctx* ctx, const m2s_scene* scene, uint32_t layout, uint64_t first_triangle,
+                                  uint64_t triangle_count, m2s_dscene** out);
+/* Payload bytes copied host -> device for this scene so far (triangles + texture rows); accounting for benchmarks. */
+uint64_t m2s_scene_h2d_bytes(const m2s_dscene* scene);
+/* The enqueue stream of the last conversion that used the scene must be idle (scratch and scene memory are
+ * stream-ordered allocations of the context stream). */
 void m2s_scene_free(m2s_ctx* ctx, m2s_dscene* scene);
 /* Copies one generated mip level (RGBA8, tightly packed) back to the host; for parity tests. */
 m2s_status m2s_scene_read_mip(m2s_ctx* ctx, const m2s_dscene* scene, uint32_t texture,
@@ -176,12 +186,17 @@ m2s_status m2s_convert_enqueue(m2s_ctx* ctx, const m2s_dscene* scene, const m2s_
  * ConversionPass.cpp:54-59).  Returns M2S_E_CAPACITY if total > cap (records up to cap are valid). */
 m2s_status m2s_convert(m2s_ctx* ctx, const m2s_dscene* scene, const m2s_params* params,
                        void* d_out, uint64_t out_capacity, uint64_t* d_keys, m2s_result* result);
+/* Measurement aid (not part of the reference's surface): one conversion on the context stream with an event between
+ * the two kernels (which then do not overlap) — the per-kernel times of the step, for bench.py's roofline. */
+m2s_status m2s_convert_timed(m2s_ctx* ctx, const m2s_dscene* scene, const m2s_params* params,
+                             void* d_out, uint64_t out_capacity, float* raster_ms, float* fragment_ms);
 /* Host-buffer form: upload scene, convert, download records (and keys if h_keys != NULL).
- * Everything a caller holding CPU data pays for.  Only the maps the layout consumes are uploaded.  For
- * REF96 / PACKED56 and >= 16384 triangles the call is pipelined: the triangle range is converted in
- * chunks whose records are appended on the device, and each chunk's download overlaps the next chunk's
- * upload and kernels (pass pinned host memory to benefit; M2S_HOST_CHUNKS=n overrides the chunk count,
- * 1 = unpipelined).  The cap and the returned total behave as in one launch. */
+ * Everything a caller holding CPU data pays for.  Only the maps the layout consumes are uploaded, and of those only
+ * the texture rows the converted triangle range can sample.  With >= 16384 triangles the call is pipelined: the
+ * triangle range is converted in chunks (each bringing its triangles and texture rows with it) whose records are
+ * appended on the device, and each chunk's download overlaps the next chunk's upload and kernels (pass pinned host
+ * memory to benefit; M2S_HOST_CHUNKS=n overrides the chunk count, 1 = unpipelined).  The cap and the returned total
+ * behave as in one launch. */
 m2s_status m2s_convert_host(m2s_ctx* ctx, const m2s_scene* scene, const m2s_params* params,
                             void* h_out, uint64_t out_capacity, uint64_t* h_keys,
                             m2s_result* result);

@@ -15,8 +15,8 @@ _lib = None
 SYMBOLS = [
     "m2s_version", "m2s_last_error", "m2s_status_string", "m2s_record_stride", "m2s_reference_capacity",
     "m2s_params_default", "m2s_ctx_create", "m2s_ctx_destroy", "m2s_ctx_device", "m2s_ctx_sm_count",
-    "m2s_compute_bboxes", "m2s_scene_upload", "m2s_scene_free", "m2s_scene_read_mip",
-    "m2s_convert_enqueue", "m2s_convert", "m2s_convert_host", "m2s_convert_gather_enqueue",
+    "m2s_compute_bboxes", "m2s_scene_upload", "m2s_scene_upload_range", "m2s_scene_h2d_bytes", "m2s_scene_free", "m2s_scene_read_mip",
+    "m2s_convert_enqueue", "m2s_convert", "m2s_convert_timed", "m2s_convert_host", "m2s_convert_gather_enqueue",
     "m2s_ply_header", "m2s_ply_encode", "m2s_ply_write", "m2s_convert_file",
     "m2s_glb_load", "m2s_hscene_view", "m2s_hscene_primitive_name", "m2s_hscene_free",
 ]
@@ -64,6 +64,10 @@ def lib() -> C.CDLL:
     L.m2s_compute_bboxes.argtypes = [vp, C.POINTER(_abi.m2s_primitive), u32, i32]
     L.m2s_scene_upload.restype = i32
     L.m2s_scene_upload.argtypes = [vp, C.POINTER(_abi.m2s_scene), C.POINTER(vp)]
+    L.m2s_scene_upload_range.restype = i32
+    L.m2s_scene_upload_range.argtypes = [vp, C.POINTER(_abi.m2s_scene), u32, u64, u64, C.POINTER(vp)]
+    L.m2s_scene_h2d_bytes.restype = u64
+    L.m2s_scene_h2d_bytes.argtypes = [vp]
     L.m2s_scene_free.restype = None
     L.m2s_scene_free.argtypes = [vp, vp]
     L.m2s_scene_read_mip.restype = i32
@@ -74,6 +78,8 @@ def lib() -> C.CDLL:
     L.m2s_convert_gather_enqueue.argtypes = [vp, vp, C.POINTER(_abi.m2s_params), C.POINTER(_abi.m2s_peers), u64, vp, vp]
     L.m2s_convert.restype = i32
     L.m2s_convert.argtypes = [vp, vp, C.POINTER(_abi.m2s_params), vp, u64, vp, C.POINTER(_abi.m2s_result)]
+    L.m2s_convert_timed.restype = i32
+    L.m2s_convert_timed.argtypes = [vp, vp, C.POINTER(_abi.m2s_params), vp, u64, C.POINTER(f32), C.POINTER(f32)]
     L.m2s_convert_host.restype = i32
     L.m2s_convert_host.argtypes = [vp, C.POINTER(_abi.m2s_scene), C.POINTER(_abi.m2s_params), vp, u64, vp,
                                    C.POINTER(_abi.m2s_result)]

@@ -45,6 +45,9 @@ class DeviceScene:
                                        C.byref(ow), C.byref(oh)))
         return buf.reshape(-1)[: ow.value * oh.value * 4].reshape(oh.value, ow.value, 4).copy()
 
+    def h2d_bytes(self) -> int:
+        return int(lib().m2s_scene_h2d_bytes(self.handle))
+
     def free(self):
         if self.handle:
             lib().m2s_scene_free(self.ctx.handle, self.handle)
@@ -112,6 +115,14 @@ class Context:
         del keep
         return DeviceScene(self, h.value, scene)
 
+    def upload_range(self, scene: _abi.Scene, layout: int, first_triangle: int, triangle_count: int, c_scene=None) -> DeviceScene:
+        """One shard (m2s_scene_upload_range): the triangle range at its global indices + only the texture rows it samples."""
+        cs, keep = c_scene if c_scene is not None else scene.c_struct()
+        h = C.c_void_p(0)
+        check(lib().m2s_scene_upload_range(self.handle, C.byref(cs), layout, first_triangle, triangle_count, C.byref(h)))
+        del keep
+        return DeviceScene(self, h.value, scene)
+
     # ---- the hot path ----
     def default_capacity(self, dscene: DeviceScene, resolution: int, max_gaussians: int, flags: int) -> int:
         if max_gaussians:
@@ -148,6 +159,12 @@ class Context:
         check(lib().m2s_convert_enqueue(self.handle, dscene.handle, C.byref(params), out.data_ptr(), capacity,
                                         keys.data_ptr() if keys is not None else None,
                                         total.data_ptr() if total is not None else None, stream or None))
+
+    def convert_timed(self, dscene: DeviceScene, params: _abi.m2s_params, out, capacity: int):
+        """One conversion with an event between the two kernels (they do not overlap): (raster_ms, fragment_ms)."""
+        a, b = C.c_float(0), C.c_float(0)
+        check(lib().m2s_convert_timed(self.handle, dscene.handle, C.byref(params), out.data_ptr(), capacity, C.byref(a), C.byref(b)))
+        return float(a.value), float(b.value)
 
     def convert_host(self, scene: _abi.Scene, resolution: int, layout: int = _abi.LAYOUT_REF96,
                      gaussian_std: float = 0.65, max_gaussians: int = 0, flags: int = 0, capacity: int | None = None,

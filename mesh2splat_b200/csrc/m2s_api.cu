@@ -17,11 +17,11 @@ namespace m2s {
 int convert_warps_per_cta(int layout);
 size_t tri_frag_bytes(int layout);
 cudaError_t convert_configure(int layout, int* raster_blocks_per_sm, int* fragment_blocks_per_sm);
-cudaError_t convert_launch(int layout, const ConvertArgs& args, int raster_grid, int fragment_grid, cudaStream_t stream);
+cudaError_t convert_launch(int layout, const ConvertArgs& args, int raster_grid, int fragment_grid, cudaStream_t stream, cudaEvent_t mid);
 cudaError_t gather_wait_launch(const unsigned long long* xch, uint32_t world, unsigned long long epoch, unsigned long long gcap,
                                unsigned long long* total_global, cudaStream_t stream);
 cudaError_t mip_down_launch(const uint32_t* src, uint32_t sw, uint32_t sh, uint32_t* dst, uint32_t dw, uint32_t dh,
-                            cudaStream_t stream);
+                            uint32_t y_begin, uint32_t y_end, cudaStream_t stream);
 cudaError_t ply_rows_launch(const void* ref96, unsigned long long count, const unsigned long long* d_count,
                             uint32_t format, float mult, void* rows, cudaStream_t stream);
 // host-side helpers implemented in m2s_host.cpp
@@ -50,7 +50,7 @@ struct m2s_ctx {
     unsigned long long* d_total = nullptr;   // published count
     uint32_t* d_nitems = nullptr;            // work items queued by the last raster launch
     unsigned long long* h_total = nullptr;   // pinned
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;
     // convert_host pipeline: a second stream for the downloads, per-chunk counts and events
     static constexpr int kMaxChunks = 8;
     cudaStream_t stream2 = nullptr;
@@ -71,7 +71,6 @@ struct m2s_ctx {
     unsigned long long* d_keys = nullptr; size_t keys_bytes = 0;
     // intermediates between the raster and the fragment kernel
     void* d_trifrag = nullptr;  size_t trifrag_bytes = 0;   // TriRec per triangle of the shard
-    void* d_units = nullptr;    size_t units_bytes = 0;     // UnitDesc per work unit
     void* d_items = nullptr;    size_t items_bytes = 0;     // FragItem queue
 };
 
@@ -87,7 +86,13 @@ struct m2s_dscene {
     uint32_t ntex = 0;
     std::vector<DTexture> h_texs;
     std::vector<void*> allocs;
+    // lazily uploaded textures (host pipeline): level-0 rows travel in groups of kTexGroupRows rows, each group brings
+    // its own rows of the mip levels 1..4 with it (a group of 16 rows is closed under the 2x2 box filter)
+    std::vector<const uint8_t*> h_rgba;              // host images (valid for the duration of the call that uploads lazily)
+    std::vector<std::vector<uint8_t>> present;       // per texture, per row group: already on the device
+    uint64_t h2d_bytes = 0;                          // payload copied host -> device for this scene so far
 };
+constexpr uint32_t kTexGroupRows = 16;               // = 2^M2S_MAX_MIP_LEVEL
 
 static unsigned long long* g_trace = nullptr;  // debugging aid for M2S_TRACE builds (scripts/trace_raster.py)
 extern "C" __attribute__((visibility("default"))) void m2s_debug_set_trace(void* p) { g_trace = (unsigned long long*)p; }
@@ -194,7 +199,6 @@ M2S_EXPORT void m2s_ctx_destroy(m2s_ctx* c) {
     if (c->d_out) cudaFreeAsync(c->d_out, c->stream);
     if (c->d_keys) cudaFreeAsync(c->d_keys, c->stream);
     if (c->d_trifrag) cudaFreeAsync(c->d_trifrag, c->stream);
-    if (c->d_units) cudaFreeAsync(c->d_units, c->stream);
     if (c->d_items) cudaFreeAsync(c->d_items, c->stream);
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_sched); cudaFree(c->d_counter); cudaFree(c->d_total); cudaFree(c->d_nitems);
@@ -202,7 +206,7 @@ M2S_EXPORT void m2s_ctx_destroy(m2s_ctx* c) {
     cudaFree(c->d_chunk_tot); cudaFreeHost(c->h_chunk_tot);
     for (int i = 0; i < 2; ++i) if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
     for (int i = 0; i < m2s_ctx::kMaxChunks; ++i) if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
-    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); if (c->ev_mid) cudaEventDestroy(c->ev_mid);
     if (c->stream2) cudaStreamDestroy(c->stream2);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -248,9 +252,85 @@ M2S_EXPORT void m2s_scene_free(m2s_ctx* ctx, m2s_dscene* s) {
     delete s;
 }
 
+// rows [g0, g1) x kTexGroupRows of texture t: one contiguous H2D copy, then the rows of levels 1.. that they determine
+static m2s_status upload_texture_groups(m2s_ctx* ctx, m2s_dscene* d, uint32_t t, uint32_t g0, uint32_t g1) {
+    const DTexture& dt = d->h_texs[t];
+    const uint32_t H = dt.h[0], W = dt.w[0];
+    const uint32_t r0 = g0 * kTexGroupRows, r1 = std::min<uint32_t>(H, g1 * kTexGroupRows);
+    if (r0 >= r1) return M2S_OK;
+    CUDA_TRY(cudaMemcpyAsync(d->d_arena + dt.off[0] + (size_t)r0 * W, d->h_rgba[t] + (size_t)r0 * W * 4, (size_t)(r1 - r0) * W * 4,
+                             cudaMemcpyHostToDevice, ctx->stream));
+    for (uint32_t l = 1; l < dt.nlevels; ++l)  // level-l row j needs level-(l-1) rows 2j, 2j+1: inside the same 16-row group
+        CUDA_TRY(mip_down_launch(d->d_arena + dt.off[l - 1], dt.w[l - 1], dt.h[l - 1], d->d_arena + dt.off[l], dt.w[l], dt.h[l],
+                                 (g0 * kTexGroupRows) >> l, (g1 * kTexGroupRows) >> l, ctx->stream));
+    for (uint32_t g = g0; g < g1 && g < d->present[t].size(); ++g) d->present[t][g] = 1;
+    d->h2d_bytes += (uint64_t)(r1 - r0) * W * 4;
+    return M2S_OK;
+}
+
+// Brings in the texture rows the triangles [lo, hi) can sample (lazily uploaded scenes): per primitive the v-range of
+// its triangles in the range gives the level-0 rows; +-3 row groups cover the footprints of all five mip levels
+// (level l reaches 2^(l+1) level-0 rows beyond the sample point, plus the drift of non-power-of-two chains) and the
+// REPEAT wrap at both ends.  A range whose v spans a whole period (or is not finite) takes the whole image.
+static m2s_status ensure_textures_for_range(m2s_ctx* ctx, m2s_dscene* d, const m2s_scene* sc, uint64_t lo, uint64_t hi) {
+    std::vector<std::vector<uint8_t>> need(d->ntex);
+    bool any = false;
+    for (uint32_t p = 0; p < sc->primitive_count; ++p) {
+        const m2s_primitive& pr = sc->primitives[p];
+        const uint64_t a = std::max<uint64_t>(pr.first_triangle, lo), b = std::min<uint64_t>(pr.first_triangle + pr.triangle_count, hi);
+        if (a >= b) continue;
+        const int32_t ti[3] = {pr.albedo_texture, pr.normal_texture, pr.metallic_roughness_texture};
+        bool wanted = false;
+        for (int m = 0; m < 3; ++m)
+            if (ti[m] >= 0 && (uint32_t)ti[m] < d->ntex)
+                for (uint8_t g : d->present[ti[m]]) if (!g) { wanted = true; break; }
+        if (!wanted) continue;
+        float vmin = 3.402823466e+38f, vmax = -3.402823466e+38f;
+        bool finite = true;
+        for (uint64_t t = a; t < b; ++t)
+            for (int k = 0; k < 3; ++k) {
+                const float v = sc->triangles[t * M2S_FLOATS_PER_TRIANGLE + M2S_FLOATS_PER_VERTEX * k + 11];
+                if (!(v >= -1e30f && v <= 1e30f)) finite = false;
+                vmin = std::min(vmin, v); vmax = std::max(vmax, v);
+            }
+        for (int m = 0; m < 3; ++m) {
+            if (ti[m] < 0 || (uint32_t)ti[m] >= d->ntex) continue;
+            const uint32_t t = (uint32_t)ti[m];
+            const uint32_t ng = (uint32_t)d->present[t].size();
+            if (need[t].empty()) need[t].assign(ng, 0);
+            any = true;
+            const float fl = std::floor(vmin);
+            if (!finite || !(vmax - fl < 1.0f) || ng <= 8) { std::fill(need[t].begin(), need[t].end(), 1); continue; }
+            const float H = (float)d->h_texs[t].h[0];
+            const long long ra = (long long)std::floor((vmin - fl) * H) - 1, rb = (long long)std::floor((vmax - fl) * H) + 1;
+            const long long ga = ra / (long long)kTexGroupRows - 3 - (ra < 0), gb = rb / (long long)kTexGroupRows + 3;
+            for (long long g = ga; g <= gb; ++g) need[t][(size_t)(((g % ng) + ng) % ng)] = 1;  // REPEAT: wraps at both ends
+        }
+    }
+    if (!any) return M2S_OK;
+    for (uint32_t t = 0; t < d->ntex; ++t) {
+        if (need[t].empty()) continue;
+        const uint32_t ng = (uint32_t)need[t].size();
+        for (uint32_t g = 0; g < ng;) {
+            if (!need[t][g] || d->present[t][g]) { ++g; continue; }
+            uint32_t e = g;
+            while (e < ng && need[t][e] && !d->present[t][e]) ++e;
+            m2s_status st = upload_texture_groups(ctx, d, t, g, e);
+            if (st != M2S_OK) return st;
+            g = e;
+        }
+    }
+    return M2S_OK;
+}
+
 // first_tris < triangle_count: only that many triangles are copied here (the caller streams the rest into
 // d_tris itself, interleaved with its launches) and the stream is not synchronised.
-static m2s_status scene_upload_impl(m2s_ctx* ctx, const m2s_scene* sc, m2s_dscene** out, uint64_t first_tris, bool sync) {
+// lazy_tex: the images are NOT copied here; the caller brings in the row groups its triangle ranges sample with
+// ensure_textures_for_range (m2s_convert_host pipelines them with the triangle chunks, m2s_scene_upload_range
+// uploads what one shard needs).
+static m2s_status upload_texture_groups(m2s_ctx* ctx, m2s_dscene* d, uint32_t t, uint32_t g0, uint32_t g1);
+static m2s_status scene_upload_impl(m2s_ctx* ctx, const m2s_scene* sc, m2s_dscene** out, uint64_t first_tris, bool sync,
+                                    uint64_t tri_offset = 0, bool lazy_tex = false) {
     if (!ctx || !sc || !out) { set_error("m2s_scene_upload: NULL argument"); return M2S_E_INVALID; }
     *out = nullptr;
     if (sc->triangle_count && !sc->triangles) { set_error("m2s_scene_upload: triangles is NULL"); return M2S_E_INVALID; }
@@ -304,8 +384,12 @@ static m2s_status scene_upload_impl(m2s_ctx* ctx, const m2s_scene* sc, m2s_dscen
     };
     d->ntri = sc->triangle_count;
     UP_TRY(dalloc((void**)&d->d_tris, sc->triangle_count * (size_t)kTriBytes));
-    if (sc->triangle_count)
-        UP_TRY(cudaMemcpyAsync(d->d_tris, sc->triangles, std::min<uint64_t>(first_tris, sc->triangle_count) * (size_t)kTriBytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (sc->triangle_count && tri_offset < sc->triangle_count && first_tris)  // triangles [tri_offset, tri_offset + first_tris)
+        UP_TRY(cudaMemcpyAsync(reinterpret_cast<unsigned char*>(d->d_tris) + tri_offset * (size_t)kTriBytes,
+                               reinterpret_cast<const unsigned char*>(sc->triangles) + tri_offset * (size_t)kTriBytes,
+                               std::min<uint64_t>(first_tris, sc->triangle_count - tri_offset) * (size_t)kTriBytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (sc->triangle_count && tri_offset < sc->triangle_count && first_tris)
+        d->h2d_bytes += std::min<uint64_t>(first_tris, sc->triangle_count - tri_offset) * (uint64_t)kTriBytes;
     d->nranges = (uint32_t)ranges.size();
     UP_TRY(dalloc((void**)&d->d_ranges, ranges.size() * sizeof(DRange)));
     if (!ranges.empty())
@@ -336,11 +420,16 @@ static m2s_status scene_upload_impl(m2s_ctx* ctx, const m2s_scene* sc, m2s_dscen
         }
     }
     UP_TRY(dalloc((void**)&d->d_arena, arena_texels * 4));
+    d->h_rgba.resize(sc->texture_count);
+    d->present.resize(sc->texture_count);
     for (uint32_t t = 0; t < sc->texture_count; ++t) {
-        const DTexture& dt = d->h_texs[t];
-        UP_TRY(cudaMemcpyAsync(d->d_arena + dt.off[0], sc->textures[t].rgba, (size_t)dt.w[0] * dt.h[0] * 4, cudaMemcpyHostToDevice, ctx->stream));
-        for (uint32_t l = 1; l < dt.nlevels; ++l)
-            UP_TRY(mip_down_launch(d->d_arena + dt.off[l - 1], dt.w[l - 1], dt.h[l - 1], d->d_arena + dt.off[l], dt.w[l], dt.h[l], ctx->stream));
+        const uint32_t ngroups = (d->h_texs[t].h[0] + kTexGroupRows - 1) / kTexGroupRows;
+        d->h_rgba[t] = sc->textures[t].rgba;
+        d->present[t].assign(ngroups, 0);
+        if (!lazy_tex) {
+            m2s_status st = upload_texture_groups(ctx, d, t, 0, ngroups);
+            if (st != M2S_OK) return fail(st);
+        }
     }
     UP_TRY(dalloc((void**)&d->d_texs, d->h_texs.size() * sizeof(DTexture)));
     if (!d->h_texs.empty())
@@ -354,6 +443,9 @@ static m2s_status scene_upload_impl(m2s_ctx* ctx, const m2s_scene* sc, m2s_dscen
 M2S_EXPORT m2s_status m2s_scene_upload(m2s_ctx* ctx, const m2s_scene* sc, m2s_dscene** out) {
     return scene_upload_impl(ctx, sc, out, UINT64_MAX, true);
 }
+
+
+M2S_EXPORT uint64_t m2s_scene_h2d_bytes(const m2s_dscene* s) { return s ? s->h2d_bytes : 0; }
 
 M2S_EXPORT m2s_status m2s_scene_read_mip(m2s_ctx* ctx, const m2s_dscene* s, uint32_t texture, uint32_t level, uint8_t* dst,
                                          uint32_t* width, uint32_t* height) {
@@ -378,7 +470,7 @@ static uint64_t effective_cap(const m2s_dscene* s, const m2s_params* p, uint64_t
 static m2s_status convert_enqueue_impl(m2s_ctx* ctx, const m2s_dscene* s, const m2s_params* p, void* d_out, uint64_t out_capacity,
                                        uint64_t* d_keys, uint64_t* d_total, void* stream_, const m2s_peers* peers,
                                        const unsigned long long* prev_totals = nullptr, uint32_t nprev = 0,
-                                       unsigned long long* host_total = nullptr, unsigned long long host_tag = 0) {
+                                       unsigned long long* host_total = nullptr, unsigned long long host_tag = 0, cudaEvent_t mid = nullptr) {
     if (!ctx || !s || !p) { set_error("m2s_convert: NULL argument"); return M2S_E_INVALID; }
     if (p->resolution < 1 || p->resolution > 4096) { set_error("m2s_convert: resolution must be in 1..4096"); return M2S_E_INVALID; }
     if (p->layout > M2S_LAYOUT_PLY_COMPRESSED) { set_error("m2s_convert: unknown layout"); return M2S_E_INVALID; }
@@ -410,13 +502,23 @@ static m2s_status convert_enqueue_impl(m2s_ctx* ctx, const m2s_dscene* s, const 
         unit_tris = std::min<uint64_t>(std::max<uint64_t>(unit_tris, 1), kUnitTris);
         n_units = (count + unit_tris - 1) / unit_tris;
     }
-    // item queue: an item takes a slot only if it starts below the cap, and live items cover disjoint output
-    // ranges: at most one end-of-unit item per unit, cap/32 items closed by 32 non-empty blocks, cap/1024 closed by
-    // their fragment count, cap/2048 pieces of oversized blocks — the queue cannot overflow
-    const uint64_t queue_cap = std::min<uint64_t>(n_units + cap / 32 + cap / kFlushFrags + cap / kItemMaxFrags + 64, 0x7fffffffu);
+    // work-item granularity: ~8 items per SM at the expected output (O(2 R^2) fragments) so that small conversions
+    // still spread over the GPU, at most 2048 fragments; an oversized row block (<= 32 rows x R pixels) takes at most
+    // kMaxSplit queue slots
+    uint32_t item_max = (uint32_t)std::min<uint64_t>(kItemMaxFrags, (2ull * p->resolution * p->resolution) / ((uint64_t)ctx->sm_count * 8));
+    item_max = std::max<uint32_t>({item_max, 64u, (32u * p->resolution + kMaxSplit - 1) / kMaxSplit});
+    item_max = std::min<uint32_t>((item_max + 31u) & ~31u, kItemMaxFrags);
+    const uint32_t flush_frags = std::max<uint32_t>(32u, item_max / 2);
+    // item queue: a warp stops taking slots once it has seen the counter pass the cap, so live items cover disjoint
+    // output ranges below it: per unit one item of small triangles and one end-of-unit item, cap/32 items closed by
+    // 32 non-empty blocks, cap/flush closed by their fragment count, cap/item_max pieces of oversized blocks; plus
+    // ONE reservation per raster warp that may straddle the cap (<= max(kStashItems, kMaxSplit) slots).  The queue
+    // cannot overflow.
+    const uint64_t raster_warps = (uint64_t)grid * convert_warps_per_cta(klayout);
+    const uint64_t queue_cap = std::min<uint64_t>(2 * n_units + cap / 32 + cap / flush_frags + cap / item_max +
+                                                  raster_warps * std::max<uint64_t>(kStashItems, kMaxSplit) + 64, (1u << 24) - 1);
     {   // scratch between the two kernels (grown on demand, kept by the context)
         m2s_status st = grow(ctx, &ctx->d_trifrag, &ctx->trifrag_bytes, std::max<uint64_t>(count, 1) * tri_frag_bytes(klayout), stream);
-        if (st == M2S_OK) st = grow(ctx, &ctx->d_units, &ctx->units_bytes, std::max<uint64_t>(n_units, 1) * sizeof(UnitDesc), stream);
         if (st == M2S_OK) st = grow(ctx, &ctx->d_items, &ctx->items_bytes, queue_cap * sizeof(FragItem), stream);
         if (st != M2S_OK) return st;
     }
@@ -439,9 +541,10 @@ static m2s_status convert_enqueue_impl(m2s_ctx* ctx, const m2s_dscene* s, const 
     a.mult = p->gaussian_std / (float)p->resolution;
     a.log_sz = logf(1e-7f * a.mult);
     a.tri_frag = (unsigned char*)ctx->d_trifrag;
-    a.unit_desc = (UnitDesc*)ctx->d_units;
     a.items = (FragItem*)ctx->d_items;
     a.queue_cap = (uint32_t)queue_cap;
+    a.item_max_frags = item_max;
+    a.flush_frags = flush_frags;
     a.n_items_out = ctx->d_nitems;
     a.out = (uint8_t*)kout;
     a.cap = cap;
@@ -464,7 +567,7 @@ static m2s_status convert_enqueue_impl(m2s_ctx* ctx, const m2s_dscene* s, const 
         a.gcap = out_capacity;
     }
     const int fgrid = ctx->sm_count * ctx->frag_blocks_per_sm[klayout];
-    cudaError_t e = convert_launch(klayout, a, grid, fgrid, stream);
+    cudaError_t e = convert_launch(klayout, a, grid, fgrid, stream, mid);
     if (e != cudaSuccess) { ctx->dirty = true; set_error(std::string("convert launch: ") + cudaGetErrorString(e)); return M2S_E_CUDA; }
     if (peers && peers->world > 1)
         CUDA_TRY(gather_wait_launch((const unsigned long long*)peers->xch[peers->rank], peers->world, a.epoch, out_capacity,
@@ -510,6 +613,27 @@ M2S_EXPORT m2s_status m2s_convert(m2s_ctx* ctx, const m2s_dscene* s, const m2s_p
     return M2S_OK;
 }
 
+// Measurement aid: one conversion with an event between the two kernels (no programmatic dependent launch, so they do
+// not overlap): the per-kernel shares of the step, measured live instead of read from a profile.
+M2S_EXPORT m2s_status m2s_convert_timed(m2s_ctx* ctx, const m2s_dscene* s, const m2s_params* p, void* d_out, uint64_t out_capacity,
+                                        float* raster_ms, float* fragment_ms) {
+    if (!ctx) { set_error("m2s_convert_timed: ctx is NULL"); return M2S_E_INVALID; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (!ctx->ev_mid) CUDA_TRY(cudaEventCreate(&ctx->ev_mid));
+    CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+    m2s_status st = convert_enqueue_impl(ctx, s, p, d_out, out_capacity, nullptr, nullptr, ctx->stream, nullptr, nullptr, 0, nullptr, 0, ctx->ev_mid);
+    if (st != M2S_OK) return st;
+    CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { ctx->dirty = true; set_error(std::string("convert_timed: ") + cudaGetErrorString(e)); return M2S_E_CUDA; }
+    float a = 0.f, b = 0.f;
+    cudaEventElapsedTime(&a, ctx->ev0, ctx->ev_mid);
+    cudaEventElapsedTime(&b, ctx->ev_mid, ctx->ev1);
+    if (raster_ms) *raster_ms = a;
+    if (fragment_ms) *fragment_ms = b;
+    return M2S_OK;
+}
+
 // Upload only the maps a layout consumes: PACKED56 carries neither normal nor metallic/roughness, the
 // standard .ply row no metallic/roughness — their texels would cross PCIe for nothing.
 struct SlimScene {
@@ -532,6 +656,28 @@ struct SlimScene {
     }
 };
 
+// One shard of a scene: the triangles [first, first + count) (at their global indices) and only the texture rows they
+// can sample, only the maps `layout` consumes — what one rank of a multi-GPU conversion needs on its device.
+M2S_EXPORT m2s_status m2s_scene_upload_range(m2s_ctx* ctx, const m2s_scene* sc, uint32_t layout, uint64_t first_triangle,
+                                             uint64_t triangle_count, m2s_dscene** out) {
+    if (!ctx || !sc || !out) { set_error("m2s_scene_upload_range: NULL argument"); return M2S_E_INVALID; }
+    if (layout > M2S_LAYOUT_PLY_COMPRESSED) { set_error("m2s_scene_upload_range: unknown layout"); return M2S_E_INVALID; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    SlimScene slim(sc, layout);
+    const uint64_t first = std::min<uint64_t>(first_triangle, sc->triangle_count);
+    uint64_t count = triangle_count;
+    if (count == 0 || first + count > sc->triangle_count) count = sc->triangle_count - first;
+    m2s_dscene* ds = nullptr;
+    m2s_status st = scene_upload_impl(ctx, &slim.scene, &ds, count, false, first, true);
+    if (st != M2S_OK) return st;
+    st = ensure_textures_for_range(ctx, ds, &slim.scene, first, first + count);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (st == M2S_OK && e != cudaSuccess) { set_error(std::string("m2s_scene_upload_range: ") + cudaGetErrorString(e)); st = M2S_E_CUDA; }
+    if (st != M2S_OK) { m2s_scene_free(ctx, ds); return st; }
+    *out = ds;
+    return M2S_OK;
+}
+
 M2S_EXPORT m2s_status m2s_convert_host(m2s_ctx* ctx, const m2s_scene* sc, const m2s_params* p, void* h_out, uint64_t out_capacity,
                                        uint64_t* h_keys, m2s_result* res) {
     if (!ctx || !sc || !p || (!h_out && out_capacity)) { set_error("m2s_convert_host: NULL argument"); return M2S_E_INVALID; }
@@ -547,14 +693,19 @@ M2S_EXPORT m2s_status m2s_convert_host(m2s_ctx* ctx, const m2s_scene* sc, const 
     uint64_t count = p->triangle_count;
     if (count == 0 || first + count > sc->triangle_count) count = sc->triangle_count - first;
     int nchunks = 1;
-    if (p->layout <= M2S_LAYOUT_PACKED56 && count >= 16384) {
-        nchunks = 4;
+    if (count >= 16384) {  // every layout: the fragment kernel appends after the earlier chunks' records itself
+        nchunks = 8;
         if (const char* e = std::getenv("M2S_HOST_CHUNKS")) nchunks = std::max(1, std::min(m2s_ctx::kMaxChunks, std::atoi(e)));
     }
     const uint64_t per = (count + nchunks - 1) / nchunks;
     m2s_dscene* ds = nullptr;
-    m2s_status st = scene_upload_impl(ctx, &slim, &ds, nchunks > 1 ? first + per : UINT64_MAX, nchunks == 1);
+    // triangles and texture rows travel with the chunk that needs them (ensure_textures_for_range): the first records
+    // exist after 1/nchunks of the upload, and a shard (first_triangle/triangle_count) never uploads rows it does not sample
+    const uint64_t first_n = nchunks > 1 ? std::min(per, count) : count;
+    m2s_status st = scene_upload_impl(ctx, &slim, &ds, first_n, false, first, true);
     if (st != M2S_OK) return st;
+    st = ensure_textures_for_range(ctx, ds, &slim, first, first + first_n);
+    if (st != M2S_OK) { cudaStreamSynchronize(ctx->stream); m2s_scene_free(ctx, ds); return st; }
     st = grow(ctx, &ctx->d_out, &ctx->out_bytes, std::max<uint64_t>(out_capacity, 1) * stride);
     if (st == M2S_OK && h_keys) st = grow(ctx, (void**)&ctx->d_keys, &ctx->keys_bytes, std::max<uint64_t>(out_capacity, 1) * 8);
     if (st != M2S_OK) { cudaStreamSynchronize(ctx->stream); m2s_scene_free(ctx, ds); return st; }
@@ -593,6 +744,8 @@ M2S_EXPORT m2s_status m2s_convert_host(m2s_ctx* ctx, const m2s_scene* sc, const 
                                     reinterpret_cast<const unsigned char*>(sc->triangles) + lo * (size_t)kTriBytes,
                                     (hi - lo) * (size_t)kTriBytes, cudaMemcpyHostToDevice, ctx->stream);
                 if (e != cudaSuccess) return bail("convert_host upload", e);
+                st = ensure_textures_for_range(ctx, ds, &slim, lo, hi);
+                if (st != M2S_OK) { cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->stream2); ctx->dirty = true; m2s_scene_free(ctx, ds); return st; }
             }
             m2s_params pc = *p;
             pc.first_triangle = lo;

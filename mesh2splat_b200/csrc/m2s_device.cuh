@@ -11,21 +11,18 @@ constexpr int kUnitTris = 32;            // max triangles per work unit (one lan
 constexpr int kTriBytes = 144;           // 36 floats
 constexpr uint32_t kSmallCand = 64;      // <= this many candidate pixels (and <= 32 rows): coverage as a 64-bit mask
 constexpr int kItemBlocks = 32;          // row blocks (<= 32 pixel rows of one triangle) per fragment work item
-constexpr uint32_t kFlushFrags = 1024;   // a warp's pending row blocks become one item once they hold this many fragments
-constexpr uint32_t kItemMaxFrags = 2048; // a single row block with more fragments is cut into items of this size
+constexpr int kStashItems = 4;           // work items a raster warp publishes with one atomic
+constexpr uint32_t kItemMaxFrags = 2048; // upper bound of ConvertArgs::item_max_frags
+constexpr uint32_t kMaxSplit = 64;       // queue slots one oversized row block can take (item_max_frags >= R / 2)
+constexpr unsigned long long kFragMask = (1ull << 40) - 1;  // ConvertArgs::counter: fragments | queue slots << 40
 constexpr float kGuard = 8192.0f;        // window-coordinate guard band (|xw| beyond -> triangle dropped)
 
 // ---- raster_kernel -> fragment_kernel interface (context-owned scratch, L2-resident at the sizes of interest) ----
 // The raster kernel only COUNTS: per triangle it leaves a record (TriRec, m2s_kernels.cu) holding the exact edge
 // functions, the shading constants and — for small triangles — the 64-bit coverage mask of the candidate box; the
 // fragment kernel enumerates the covered pixels itself (mask rows / exact row spans, m2s_span.cuh).
-// Work of the fragment kernel = n_units "unit items" (the small triangles of one work unit, UnitDesc) followed by
-// the queued FragItems (row blocks of the larger triangles of one unit).
-struct UnitDesc {               // 16 B per work unit
-    unsigned long long first;   // output index (this launch) of the unit's first small-triangle fragment
-    uint32_t total;             // fragments of the unit's small triangles (triangle-major, TriRec::first = prefix)
-    uint32_t pad;
-};
+// Work of the fragment kernel = the queued FragItems: the small triangles of one work unit, or up to 32 row blocks of
+// its larger triangles, or a fragment sub-range of one oversized row block.
 struct BlockRef {               // <= 32 consecutive pixel rows of one triangle
     uint32_t prefix;            // fragments of the item before this block
     uint32_t ref;               // slot in the unit (5 bits) | first row relative to the box (12) << 5 | rows (6) << 17
@@ -33,7 +30,7 @@ struct BlockRef {               // <= 32 consecutive pixel rows of one triangle
 struct FragItem {               // 288 B
     unsigned long long first;   // output index (this launch) of fragment 0 of the item
     uint32_t unit;              // work unit the blocks' triangles belong to
-    uint32_t nblocks;
+    uint32_t nblocks;           // bit 31: the blocks are implicit — block t = small triangle t of the unit (TriRec::first/hits)
     uint32_t frag_begin, frag_end;  // fragments [frag_begin, frag_end) of the item are this item's work
     uint32_t pad[2];
     BlockRef blocks[kItemBlocks];
@@ -87,23 +84,24 @@ struct ConvertArgs {
     // intermediates between the two kernels (context-owned scratch, L2-resident at the sizes of interest);
     // the fragment kernel reads the vertices themselves from `tris`
     unsigned char* tri_frag;           // one TriRec per triangle of the shard
-    UnitDesc* unit_desc;               // [n_units]
     FragItem* items;                   // [queue_cap]
     uint32_t queue_cap;
+    uint32_t item_max_frags;           // a row block with more fragments is cut into items of this size (multiple of 32)
+    uint32_t flush_frags;              // pending row blocks become one item once they hold this many fragments
     uint32_t* n_items_out;             // items queued by this launch (published by the raster kernel's last CTA)
     uint8_t* out;
     unsigned long long cap;
     unsigned long long* keys;          // optional
-    unsigned long long* counter;       // fragments generated (the reference's atomic counter); context-owned,
-                                       // zero at launch, re-zeroed by the last CTA
+    unsigned long long* counter;       // low 40 bits: fragments generated (the reference's atomic counter), high 24 bits:
+                                       // work items queued; context-owned, zero at launch, re-zeroed by the last CTA
     unsigned long long* total_out;     // receives the final count (last CTA out)
     const unsigned long long* prev_totals;  // appended launches: counts of the earlier chunks (records start after them)
     uint32_t nprev;
     unsigned long long* host_total;    // optional, mapped pinned host memory: {count, tag} written by the raster kernel's
     unsigned long long host_tag;       // last CTA so the host can size the download while the fragment kernel still runs
     // scheduling state (zero at launch, re-armed by the last CTA)
-    uint32_t* sched;                   // words 128 B apart: 0 unit counter, 2 item-queue tail, 4 raster CTAs finished,
-                                       // 6 fragment CTAs finished (fused gather)
+    uint32_t* sched;                   // words 128 B apart: 0 unit counter, 4 raster CTAs finished, 6 fragment CTAs finished
+                                       // (fused gather)
     uint32_t unit_tris;                // triangles per work unit (<= 32), chosen by the host for balance
     uint32_t n_units;
     unsigned long long* trace;         // M2S_TRACE builds only: 16 globaltimer stamps per raster warp

@@ -197,7 +197,9 @@ template <int RK>
 struct __align__(128) WarpBlock {
     float4 tri[kUnitTris * 9];                    // 4608 B, TMA destination
     TriRec<RCfg<RK>::kMaps> rec[kUnitTris];       // TMA source
-    BlockRef pend[kItemBlocks];                   // row blocks waiting to become a work item
+    BlockRef pend[kStashItems * kItemBlocks];     // the stash: row blocks of up to kStashItems work items
+    uint32_t itN[kStashItems];                    // blocks per item | kItUnit / kItSplit
+    uint32_t itTotal[kStashItems];                // fragments per item
     uint64_t bar;
 };
 
@@ -402,9 +404,14 @@ __device__ __forceinline__ uint32_t setup_triangle(const float4* __restrict__ t4
 // ------------------------------------------------------------------------------------------
 // sampler: RGBA8 unorm, REPEAT, bilinear within a level, linear between levels
 // ------------------------------------------------------------------------------------------
-struct Bilin {          // one bilinear footprint: texel indices relative to the level start + weights
-    uint32_t i00, i10, i01, i11;
-    float w00, w10, w01, w11;  // already scaled by 1/255
+// Blackwell's packed fp32 (fma/add/mul .f32x2, one instruction for two lanes of a 64-bit register pair): the two mip
+// levels of a trilinear lookup are the two halves of every pair below — .x = level 0, .y = level 1 — so footprint
+// set-up, byte->float conversion and the weighted sum of both levels cost what ONE level costs in scalar code.
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
+struct Bilin2 {             // the 2x2 footprints of one map on its two mip levels
+    uint32_t i00[2], i10[2], i01[2], i11[2];  // texel indices relative to the level starts
+    float2 w00, w10, w01, w11;                // weights: bilinear x 1/255 x level blend (1-f, f)
 };
 // small non-negative int -> float on the FMA pipe (no I2F): 2^23 | v is the float 2^23 + v
 __device__ __forceinline__ float u2f(uint32_t v) { return __uint_as_float(0x4B000000u | v) - 8388608.0f; }
@@ -415,37 +422,56 @@ __device__ __forceinline__ float fast_floor(float x, int& i) {
     i = __float_as_int(t) - 0x4B400000;
     return t - 12582912.0f;
 }
-__device__ __forceinline__ Bilin bilin_setup(uint32_t W, uint32_t H, float u, float v) {
-    // REPEAT: wrap in the normalised domain (exact for u in [0,1)), then fix the one-texel overhang
-    int ix, iy;
-    u -= fast_floor(u, ix);
-    v -= fast_floor(v, iy);
-    const float x = u * u2f(W) - 0.5f, y = v * u2f(H) - 0.5f;
-    const float fx = fast_floor(x, ix), fy = fast_floor(y, iy);
-    const float ax = x - fx, ay = y - fy;
-    // ix in [-1, W]: wrap, then clamp so that even NaN/huge uv can never index outside the level
-    int x0 = ix < 0 ? ix + (int)W : ix;
-    int y0 = iy < 0 ? iy + (int)H : iy;
-    x0 = min(max(x0, 0), (int)W - 1);
-    y0 = min(max(y0, 0), (int)H - 1);
-    const int x1 = x0 + 1 >= (int)W ? 0 : x0 + 1;
-    const int y1 = y0 + 1 >= (int)H ? 0 : y0 + 1;
-    Bilin b;
-    const uint32_t r0 = (uint32_t)y0 * W, r1 = (uint32_t)y1 * W;
-    b.i00 = r0 + x0; b.i10 = r0 + x1; b.i01 = r1 + x0; b.i11 = r1 + x1;
-    const float k = 1.0f / 255.0f;
-    const float bx = 1.0f - ax, by = (1.0f - ay) * k, cy = ay * k;
-    b.w00 = bx * by; b.w10 = ax * by; b.w01 = bx * cy; b.w11 = ax * cy;
+__device__ __forceinline__ float2 fast_floor2(float2 x, int& i0, int& i1) {
+    const float2 t = __fadd2_rn(__fadd2_rn(x, f2(-0.5f)), f2(12582912.0f));
+    i0 = __float_as_int(t.x) - 0x4B400000;
+    i1 = __float_as_int(t.y) - 0x4B400000;
+    return __fadd2_rn(t, f2(-12582912.0f));
+}
+// REPEAT in the normalised domain: uv -> [0, 1]; NaN / huge values are pinned first so that the texel indices below
+// can never leave the level (fmaxf(NaN, x) = x)
+__device__ __forceinline__ float wrap01(float u) {
+    int d;
+    u = fminf(fmaxf(u, -1048576.0f), 1048576.0f);
+    return u - fast_floor(u, d);
+}
+// the four texel indices of a footprint whose lower-left texel is (ix, iy), ix in [-1, W-1], iy in [-1, H-1]
+__device__ __forceinline__ void footprint(int ix, int iy, int W, int H, uint32_t& i00, uint32_t& i10, uint32_t& i01, uint32_t& i11) {
+    const int x0 = ix + ((ix >> 31) & W), y0 = iy + ((iy >> 31) & H);   // -1 wraps to the last texel
+    const int x1 = x0 + 1 == W ? 0 : x0 + 1, y1 = y0 + 1 == H ? 0 : y0 + 1;
+    i00 = (uint32_t)(y0 * W + x0); i10 = (uint32_t)(y0 * W + x1);
+    i01 = (uint32_t)(y1 * W + x0); i11 = (uint32_t)(y1 * W + x1);
+}
+// u, v already wrapped to [0, 1]; lw = level weights (1-f, f) (or (1, 0) for a single level)
+__device__ __forceinline__ Bilin2 bilin_setup2(const TexRef& r, float u, float v, float2 lw) {
+    const float2 W = f2(u2f(r.w0), u2f(r.w1)), H = f2(u2f(r.h0), u2f(r.h1));
+    const float2 x = __ffma2_rn(f2(u), W, f2(-0.5f)), y = __ffma2_rn(f2(v), H, f2(-0.5f));
+    int ix0, ix1, iy0, iy1;
+    const float2 fx = fast_floor2(x, ix0, ix1), fy = fast_floor2(y, iy0, iy1);
+    const float2 ax = __ffma2_rn(fx, f2(-1.0f), x), ay = __ffma2_rn(fy, f2(-1.0f), y);
+    Bilin2 b;
+    footprint(ix0, iy0, (int)r.w0, (int)r.h0, b.i00[0], b.i10[0], b.i01[0], b.i11[0]);
+    footprint(ix1, iy1, (int)r.w1, (int)r.h1, b.i00[1], b.i10[1], b.i01[1], b.i11[1]);
+    const float2 k = __fmul2_rn(lw, f2(1.0f / 255.0f));
+    const float2 bx = __ffma2_rn(ax, f2(-1.0f), f2(1.0f));
+    const float2 cy = __fmul2_rn(ay, k), by = __ffma2_rn(ay, f2(-k.x, -k.y), k);
+    b.w00 = __fmul2_rn(bx, by); b.w10 = __fmul2_rn(ax, by); b.w01 = __fmul2_rn(bx, cy); b.w11 = __fmul2_rn(ax, cy);
     return b;
 }
-// byte c of a texel as float, without the conversion pipe: 0x4B000000 | byte is 2^23 + byte
+// channel CH of the texel pair (level 0, level 1) as floats, without the conversion pipe: 0x4B000000 | byte = 2^23 + byte
 template <int CH>
-__device__ __forceinline__ float tex_ch(uint32_t t) {
-    return __uint_as_float(__byte_perm(t, 0x4B000000u, 0x7440u | CH)) - 8388608.0f;
+__device__ __forceinline__ float2 tex_ch2(uint32_t t0, uint32_t t1) {
+    return __fadd2_rn(f2(__uint_as_float(__byte_perm(t0, 0x4B000000u, 0x7440u | CH)), __uint_as_float(__byte_perm(t1, 0x4B000000u, 0x7440u | CH))),
+                      f2(-8388608.0f));
 }
+// trilinear value of channel CH: tx[0..3] = level-0 texels (00, 10, 01, 11), tx[4..7] = level-1 texels
 template <int CH>
-__device__ __forceinline__ float filt(const Bilin& b, uint32_t t00, uint32_t t10, uint32_t t01, uint32_t t11) {
-    return b.w00 * tex_ch<CH>(t00) + b.w10 * tex_ch<CH>(t10) + b.w01 * tex_ch<CH>(t01) + b.w11 * tex_ch<CH>(t11);
+__device__ __forceinline__ float filt2(const Bilin2& b, const uint32_t* tx) {
+    float2 acc = __fmul2_rn(b.w00, tex_ch2<CH>(tx[0], tx[4]));
+    acc = __ffma2_rn(b.w10, tex_ch2<CH>(tx[1], tx[5]), acc);
+    acc = __ffma2_rn(b.w01, tex_ch2<CH>(tx[2], tx[6]), acc);
+    acc = __ffma2_rn(b.w11, tex_ch2<CH>(tx[3], tx[7]), acc);
+    return acc.x + acc.y;
 }
 
 __device__ __forceinline__ float inv_sigmoid(float a) {  // utils.hpp:270
@@ -460,67 +486,112 @@ __device__ __forceinline__ uint32_t block_ref(uint32_t slot, uint32_t row_begin,
     return slot | (row_begin << 5) | (nrows << 17);
 }
 
-// the warp's pending row blocks become ONE work item: reserve its output range and a queue slot
+// A warp collects the work items of its current unit in shared memory (WarpBlock::pend / it*) and publishes them
+// with ONE 64-bit atomicAdd that reserves both the output range (low 40 bits: fragments) and the queue slots
+// (high 24 bits) — the reference does one atomicCounterIncrement per fragment (converterFS.glsl:46).
+struct Stash {            // warp-uniform registers
+    uint32_t n_it;        // closed items
+    uint32_t cur_nb;      // blocks of the open item
+    uint32_t cur_total;   // fragments of the open item
+    uint32_t frags;       // fragments of the closed items
+    uint32_t slots;       // queue slots of the closed items
+    unsigned long long seen;  // a lower bound of the global fragment counter (from this warp's last reservation)
+};
+constexpr uint32_t kItUnit = 0x80000000u;   // item = the unit's small triangles (one implicit block per triangle)
+constexpr uint32_t kItSplit = 0x40000000u;  // item = one oversized row block, cut into several queue slots
+
 template <int RK>
-__device__ __forceinline__ void flush_blocks(const ConvertArgs& a, WarpBlock<RK>& wb, uint32_t unit, uint32_t& npend, uint32_t& pend_total,
-                                             int lane) {
-    if (npend == 0) return;
-    __syncwarp();  // lane 0's pend[] writes are visible to the warp
-    // converterFS.glsl:48-51: the counter keeps counting, but an item that starts beyond the cap emits nothing and
-    // takes no queue slot (so the queue can be sized from the cap: live items cover disjoint ranges below it)
-    unsigned long long base = 0;
-    uint32_t slot = 0xffffffffu;
-    if (lane == 0) {
-        base = atomicAdd(a.counter, (unsigned long long)pend_total);
-        if (base < a.cap) slot = atomicAdd(SCHED(a, 2), 1u);
-    }
-    base = __shfl_sync(0xffffffffu, base, 0);
-    slot = __shfl_sync(0xffffffffu, slot, 0);
-    if (slot < a.queue_cap) {
-        FragItem* it = a.items + slot;
-        if (lane == 0) {
-            it->first = base; it->unit = unit; it->nblocks = npend;
-            it->frag_begin = 0; it->frag_end = pend_total;
+__device__ __forceinline__ void stash_flush(const ConvertArgs& a, WarpBlock<RK>& wb, uint32_t unit, Stash& st, int lane) {
+    if (st.n_it == 0) return;
+    __syncwarp();  // lane 0's stash writes are visible to the warp
+    // converterFS.glsl:48-51: the counter keeps counting, but once this warp has SEEN the counter beyond the cap its
+    // items cannot emit anything and take no queue slots (at most one reservation per warp straddles the cap; the
+    // host sizes the queue for that)
+    const uint32_t want = st.seen < a.cap ? st.slots : 0u;
+    unsigned long long r = 0;
+    if (lane == 0) r = atomicAdd(a.counter, ((unsigned long long)want << 40) | (unsigned long long)st.frags);
+    r = __shfl_sync(0xffffffffu, r, 0);
+    const unsigned long long base = r & kFragMask;
+    uint32_t slot = (uint32_t)(r >> 40);
+    st.seen = base + st.frags;
+    if (want) {
+        unsigned long long first = base;
+        for (uint32_t i = 0; i < st.n_it; ++i) {
+            const uint32_t nb = wb.itN[i], tot = wb.itTotal[i];
+            const BlockRef* blk = wb.pend + i * kItemBlocks;
+            if (nb & kItSplit) {  // fragments [k * item_max, ...) of the one block per slot
+                const uint32_t nit = (tot + a.item_max_frags - 1) / a.item_max_frags;
+                for (uint32_t k = lane; k < nit; k += 32) {
+                    if (slot + k >= a.queue_cap) break;
+                    FragItem* it = a.items + slot + k;
+                    const uint32_t fb = k * a.item_max_frags;
+                    *reinterpret_cast<uint4*>(it) = make_uint4((uint32_t)first, (uint32_t)(first >> 32), unit, 1u);
+                    *(reinterpret_cast<uint2*>(it) + 2) = make_uint2(fb, min(tot, fb + a.item_max_frags));
+                    it->blocks[0] = blk[0];
+                }
+                slot += nit;
+            } else {
+                if (slot < a.queue_cap) {
+                    FragItem* it = a.items + slot;
+                    if (lane == 0) {
+                        *reinterpret_cast<uint4*>(it) = make_uint4((uint32_t)first, (uint32_t)(first >> 32), unit, nb);
+                        *(reinterpret_cast<uint2*>(it) + 2) = make_uint2(0u, tot);
+                    }
+                    if (!(nb & kItUnit) && (uint32_t)lane < nb) it->blocks[lane] = blk[lane];
+                }
+                slot += 1;
+            }
+            first += tot;
         }
-        if ((uint32_t)lane < npend) it->blocks[lane] = wb.pend[lane];
     }
     __syncwarp();
-    npend = 0; pend_total = 0;
+    st.n_it = 0; st.frags = 0; st.slots = 0;
+}
+
+template <int RK>
+__device__ __forceinline__ void stash_close_item(const ConvertArgs& a, WarpBlock<RK>& wb, uint32_t unit, Stash& st, int lane) {
+    if (st.cur_nb == 0) return;
+    if (lane == 0) { wb.itN[st.n_it] = st.cur_nb; wb.itTotal[st.n_it] = st.cur_total; }
+    st.frags += st.cur_total; st.slots += 1; st.n_it += 1;
+    st.cur_nb = 0; st.cur_total = 0;
+    if (st.n_it == kStashItems) stash_flush<RK>(a, wb, unit, st, lane);
 }
 
 // a row block of triangle `slot` holding `bt` fragments
 template <int RK>
-__device__ __forceinline__ void push_block(const ConvertArgs& a, WarpBlock<RK>& wb, uint32_t unit, uint32_t& npend, uint32_t& pend_total,
-                                           uint32_t slot, uint32_t row_begin, uint32_t nrows, uint32_t bt, int lane) {
+__device__ __forceinline__ void stash_block(const ConvertArgs& a, WarpBlock<RK>& wb, uint32_t unit, Stash& st,
+                                            uint32_t slot, uint32_t row_begin, uint32_t nrows, uint32_t bt, int lane) {
     const uint32_t ref = block_ref(slot, row_begin, nrows);
-    if (bt > kItemMaxFrags) {  // a block of a huge triangle: several single-block items, each a fragment sub-range
-        unsigned long long base = 0;
-        uint32_t first = 0, nit = 0;
+    if (bt > a.item_max_frags) {  // a block of a huge triangle: several queue slots, each a fragment sub-range of the block
+        stash_close_item<RK>(a, wb, unit, st, lane);
         if (lane == 0) {
-            base = atomicAdd(a.counter, (unsigned long long)bt);
-            if (base < a.cap) {  // only the items that start below the cap exist
-                const unsigned long long live = min((unsigned long long)bt, a.cap - base);
-                nit = (uint32_t)((live + kItemMaxFrags - 1) / kItemMaxFrags);
-                first = atomicAdd(SCHED(a, 2), nit);
-            }
+            wb.itN[st.n_it] = 1u | kItSplit; wb.itTotal[st.n_it] = bt;
+            wb.pend[st.n_it * kItemBlocks].prefix = 0; wb.pend[st.n_it * kItemBlocks].ref = ref;
         }
-        base = __shfl_sync(0xffffffffu, base, 0);
-        first = __shfl_sync(0xffffffffu, first, 0);
-        nit = __shfl_sync(0xffffffffu, nit, 0);
-        for (uint32_t i = lane; i < nit; i += 32) {
-            if (first + i >= a.queue_cap) break;
-            FragItem* it = a.items + first + i;
-            const uint32_t fb = i * kItemMaxFrags;
-            it->first = base; it->unit = unit; it->nblocks = 1u;
-            it->frag_begin = fb; it->frag_end = min(bt, fb + kItemMaxFrags);
-            it->blocks[0].prefix = 0; it->blocks[0].ref = ref;
-        }
+        st.frags += bt; st.slots += (bt + a.item_max_frags - 1) / a.item_max_frags; st.n_it += 1;
+        stash_flush<RK>(a, wb, unit, st, lane);  // at most one split block per reservation (bounds the queue slack)
         return;
     }
-    if (lane == 0) { wb.pend[npend].prefix = pend_total; wb.pend[npend].ref = ref; }
-    ++npend;
-    pend_total += bt;
-    if (npend == kItemBlocks || pend_total >= kFlushFrags) flush_blocks<RK>(a, wb, unit, npend, pend_total, lane);
+    if (lane == 0) {
+        BlockRef& b = wb.pend[st.n_it * kItemBlocks + st.cur_nb];
+        b.prefix = st.cur_total; b.ref = ref;
+    }
+    st.cur_nb += 1;
+    st.cur_total += bt;
+    if (st.cur_nb == kItemBlocks || st.cur_total >= a.flush_frags) stash_close_item<RK>(a, wb, unit, st, lane);
+}
+
+// the unit's small triangles as one item (blocks implicit: one per triangle, TriRec::first/hits)
+template <int RK>
+__device__ __forceinline__ void stash_unit_item(const ConvertArgs& a, WarpBlock<RK>& wb, uint32_t unit, Stash& st, uint32_t total_small,
+                                                uint32_t ntri, int lane) {
+    if (total_small == 0) return;
+    // the open item (if any) stays open: closed items occupy the slots below n_it, the open one is written at n_it
+    // only when it closes — so insert the unit item by closing the open one first
+    stash_close_item<RK>(a, wb, unit, st, lane);
+    if (lane == 0) { wb.itN[st.n_it] = ntri | kItUnit; wb.itTotal[st.n_it] = total_small; }
+    st.frags += total_small; st.slots += 1; st.n_it += 1;
+    if (st.n_it == kStashItems) stash_flush<RK>(a, wb, unit, st, lane);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -573,6 +644,8 @@ __global__ void __launch_bounds__(M2S_RASTER_WARPS * 32, 1) raster_kernel(const 
         }
     }
     uint32_t phase = 0;
+    Stash st;
+    st.n_it = 0; st.cur_nb = 0; st.cur_total = 0; st.frags = 0; st.slots = 0; st.seen = 0;
     STAMP(a, 0);
 
     while (unit < a.n_units) {
@@ -644,10 +717,6 @@ __global__ void __launch_bounds__(M2S_RASTER_WARPS * 32, 1) raster_kernel(const 
             if (lane >= d) incl_scan += v;
         }
         const uint32_t total_small = __shfl_sync(0xffffffffu, incl_scan, 31);
-        // ONE atomicAdd per unit reserves the output range of its small triangles (the reference: one
-        // atomicCounterIncrement per fragment); the result is only needed for the unit descriptor at the end
-        unsigned long long ubase = 0;
-        if (lane == 0 && total_small) ubase = atomicAdd(a.counter, (unsigned long long)total_small);
         if ((uint32_t)lane < ntri) {
             myrec.hits = hits;
             myrec.first = incl_scan - nh;
@@ -657,7 +726,6 @@ __global__ void __launch_bounds__(M2S_RASTER_WARPS * 32, 1) raster_kernel(const 
         STAMP(a, 4);
 
         // ---- all other triangles: the warp counts one triangle at a time, one lane per pixel row ----
-        uint32_t npend = 0, pend_total = 0;
         unsigned gm = __ballot_sync(0xffffffffu, cnt != 0 && !small);
         while (gm) {
             const int s = __ffs(gm) - 1;
@@ -677,10 +745,14 @@ __global__ void __launch_bounds__(M2S_RASTER_WARPS * 32, 1) raster_kernel(const 
                 int xl;
                 const uint32_t n = yrel < h ? span_row(rs, yrel, xl) : 0u;
                 const uint32_t bt = __reduce_add_sync(0xffffffffu, n);
-                if (bt) push_block<RK>(a, wb, unit, npend, pend_total, (uint32_t)s, (uint32_t)rb, (uint32_t)min(32, h - rb), bt, lane);
+                if (bt) stash_block<RK>(a, wb, unit, st, (uint32_t)s, (uint32_t)rb, (uint32_t)min(32, h - rb), bt, lane);
             }
         }
-        flush_blocks<RK>(a, wb, unit, npend, pend_total, lane);
+        // ONE atomicAdd per unit (unless the stash filled up on the way) reserves the output range and the queue
+        // slots of everything the unit emits
+        stash_close_item<RK>(a, wb, unit, st, lane);
+        stash_unit_item<RK>(a, wb, unit, st, total_small, ntri, lane);
+        stash_flush<RK>(a, wb, unit, st, lane);
         STAMP(a, 5);
 
         // ---- the unit's records go to global memory for the fragment kernel: one TMA bulk store straight out of
@@ -694,8 +766,6 @@ __global__ void __launch_bounds__(M2S_RASTER_WARPS * 32, 1) raster_kernel(const 
                 tma_store_commit();
             }
         }
-        if (lane == 0)  // UnitDesc {first, total, pad}
-            *reinterpret_cast<uint4*>(a.unit_desc + unit) = make_uint4((uint32_t)ubase, (uint32_t)(ubase >> 32), total_small, 0u);
         unit = next;
         STAMP(a, 6);
     }
@@ -712,16 +782,17 @@ __global__ void __launch_bounds__(M2S_RASTER_WARPS * 32, 1) raster_kernel(const 
             if (done == gridDim.x - 1) {
                 __threadfence();
                 last = 1;
-                tot = *reinterpret_cast<volatile unsigned long long*>(a.counter);
+                const unsigned long long packed = *reinterpret_cast<volatile unsigned long long*>(a.counter);
+                tot = packed & kFragMask;                       // fragments generated
                 *a.total_out = tot;
-                *a.n_items_out = *reinterpret_cast<volatile uint32_t*>(SCHED(a, 2));
+                *a.n_items_out = (uint32_t)(packed >> 40);      // work items queued
                 *a.counter = 0ull;
                 if (a.host_total) {  // zero-copy count for the host (PCIe posted write, ~1 us)
                     *reinterpret_cast<volatile unsigned long long*>(a.host_total) = tot;
                     __threadfence_system();
                     *reinterpret_cast<volatile unsigned long long*>(a.host_total + 1) = a.host_tag;
                 }
-                *SCHED(a, 0) = 0; *SCHED(a, 2) = 0; *SCHED(a, 4) = 0;
+                *SCHED(a, 0) = 0; *SCHED(a, 4) = 0;
                 __threadfence();
             }
         }
@@ -816,55 +887,44 @@ __device__ __forceinline__ void shade(const ConvertArgs& a, const typename FragS
     const float l0 = __ll2float_rn(tf.E0[0] + (long long)tf.A[0] * dxi + (long long)tf.B[0] * dyi) * ia;
     const float l1 = __ll2float_rn(tf.E0[1] + (long long)tf.A[1] * dxi + (long long)tf.B[1] * dyi) * ia;
     const float l2 = __ll2float_rn(tf.E0[2] + (long long)tf.A[2] * dxi + (long long)tf.B[2] * dyi) * ia;
-    // vertices: 3 x {pos3 nrm3 tan4 uv2} = 9 float4 in shared memory; uv first: the texel addresses depend on nothing else
+    const float2 L0 = f2(l0), L1 = f2(l1), L2 = f2(l2);
+    // vertices: 3 x {pos3 nrm3 tan4 uv2} = 9 float4 in shared memory; attribute pairs are interpolated with packed fp32
     const float4 a2 = v[2], b2 = v[5], c2 = v[8];
-    const float u = l0 * a2.z + l1 * b2.z + l2 * c2.z, vv = l0 * a2.w + l1 * b2.w + l2 * c2.w;
+    auto lerp3 = [&](float2 A, float2 B, float2 C) { return __ffma2_rn(L2, C, __ffma2_rn(L1, B, __fmul2_rn(L0, A))); };
+    // uv first: the texel addresses depend on nothing else
+    const float2 uv = lerp3(f2(a2.z, a2.w), f2(b2.z, b2.w), f2(c2.z, c2.w));
+    const float u = wrap01(uv.x), vv = wrap01(uv.y);
     const unsigned meta = tf.meta;
 
     // ---- issue every texel load of every bound map back to back ----
     uint32_t tx[kMaps][8];
-    Bilin bl[kMaps][2];
-    bool has[kMaps], two[kMaps];
-    uint32_t offs0[kMaps], offs1[kMaps];
+    Bilin2 bl[kMaps];
+    bool has[kMaps];
 #pragma unroll
     for (int m = 0; m < kMaps; ++m) {
         const TexRef ref = tf.tex[m];
         has[m] = ref.off0 != 0xffffffffu;
-        two[m] = has[m] && tf.frac[m] > 0.0f;
-        offs0[m] = has[m] ? ref.off0 : 0u;
-        offs1[m] = ref.off1;
-        if (m == 0 || !((meta >> m) & 1u)) {
-            bl[m][0] = bilin_setup(ref.w0, ref.h0, u, vv);
-            bl[m][1] = bilin_setup(ref.w1, ref.h1, u, vv);
-        } else { bl[m][0] = bl[0][0]; bl[m][1] = bl[0][1]; }
-    }
-#pragma unroll
-    for (int m = 0; m < kMaps; ++m) {
-        const uint32_t o0 = offs0[m], o1 = offs1[m];  // uniform base + 32-bit texel index
-        tx[m][0] = has[m] ? __ldg(texb + (o0 + bl[m][0].i00)) : 0u; tx[m][1] = has[m] ? __ldg(texb + (o0 + bl[m][0].i10)) : 0u;
-        tx[m][2] = has[m] ? __ldg(texb + (o0 + bl[m][0].i01)) : 0u; tx[m][3] = has[m] ? __ldg(texb + (o0 + bl[m][0].i11)) : 0u;
-        tx[m][4] = two[m] ? __ldg(texb + (o1 + bl[m][1].i00)) : 0u; tx[m][5] = two[m] ? __ldg(texb + (o1 + bl[m][1].i10)) : 0u;
-        tx[m][6] = two[m] ? __ldg(texb + (o1 + bl[m][1].i01)) : 0u; tx[m][7] = two[m] ? __ldg(texb + (o1 + bl[m][1].i11)) : 0u;
+        const float f = tf.frac[m];
+        const bool two = has[m] && f > 0.0f;
+        if (m == 0 || !((meta >> m) & 1u)) bl[m] = bilin_setup2(ref, u, vv, f2(1.0f - f, f));
+        else bl[m] = bl[0];  // same level sizes and blend as map 0: same footprint and weights
+        const uint32_t o0 = has[m] ? ref.off0 : 0u, o1 = ref.off1;  // uniform base + 32-bit texel index
+        tx[m][0] = has[m] ? __ldg(texb + (o0 + bl[m].i00[0])) : 0u; tx[m][1] = has[m] ? __ldg(texb + (o0 + bl[m].i10[0])) : 0u;
+        tx[m][2] = has[m] ? __ldg(texb + (o0 + bl[m].i01[0])) : 0u; tx[m][3] = has[m] ? __ldg(texb + (o0 + bl[m].i11[0])) : 0u;
+        tx[m][4] = two ? __ldg(texb + (o1 + bl[m].i00[1])) : 0u; tx[m][5] = two ? __ldg(texb + (o1 + bl[m].i10[1])) : 0u;
+        tx[m][6] = two ? __ldg(texb + (o1 + bl[m].i01[1])) : 0u; tx[m][7] = two ? __ldg(texb + (o1 + bl[m].i11[1])) : 0u;
     }
     // ---- interpolate the remaining varyings while the loads are in flight ----
     const float4 a0 = v[0], b0 = v[3], c0 = v[6];
-    const float Px = l0 * a0.x + l1 * b0.x + l2 * c0.x, Py = l0 * a0.y + l1 * b0.y + l2 * c0.y,
-                Pz = l0 * a0.z + l1 * b0.z + l2 * c0.z;
+    const float2 Pxy = lerp3(f2(a0.x, a0.y), f2(b0.x, b0.y), f2(c0.x, c0.y));
+    const float2 PzNx = lerp3(f2(a0.z, a0.w), f2(b0.z, b0.w), f2(c0.z, c0.w));
+    const float Px = Pxy.x, Py = Pxy.y, Pz = PzNx.x;
 
-    // colour (converterFS.glsl:55-62,99)
+    // colour (converterFS.glsl:55-62,99): the level blend is part of the weights, a single-level lookup has weight 0
+    // (and no loads) on the second level
     float cr = 1.f, cg = 1.f, cb = 1.f, ca = 1.f;
     if (has[0]) {
-        const float f = tf.frac[0];
-        cr = filt<0>(bl[0][0], tx[0][0], tx[0][1], tx[0][2], tx[0][3]);
-        cg = filt<1>(bl[0][0], tx[0][0], tx[0][1], tx[0][2], tx[0][3]);
-        cb = filt<2>(bl[0][0], tx[0][0], tx[0][1], tx[0][2], tx[0][3]);
-        ca = filt<3>(bl[0][0], tx[0][0], tx[0][1], tx[0][2], tx[0][3]);
-        if (two[0]) {
-            cr += f * (filt<0>(bl[0][1], tx[0][4], tx[0][5], tx[0][6], tx[0][7]) - cr);
-            cg += f * (filt<1>(bl[0][1], tx[0][4], tx[0][5], tx[0][6], tx[0][7]) - cg);
-            cb += f * (filt<2>(bl[0][1], tx[0][4], tx[0][5], tx[0][6], tx[0][7]) - cb);
-            ca += f * (filt<3>(bl[0][1], tx[0][4], tx[0][5], tx[0][6], tx[0][7]) - ca);
-        }
+        cr = filt2<0>(bl[0], tx[0]); cg = filt2<1>(bl[0], tx[0]); cb = filt2<2>(bl[0], tx[0]); ca = filt2<3>(bl[0], tx[0]);
     }
     cr *= tf.factor[0]; cg *= tf.factor[1]; cb *= tf.factor[2]; ca *= tf.factor[3];
     const float kInvC0 = 1.0f / 0.28209479177387814f;  // SH_COEFF0, params.hpp:17 (parsers.cpp:484-486)
@@ -883,22 +943,16 @@ __device__ __forceinline__ void shade(const ConvertArgs& a, const typename FragS
     }
     // ---- every other layout carries the shading normal; PBR values where the layout has them ----
     constexpr int MN = kMaps > 1 ? 1 : 0, MM = kMaps > 2 ? 2 : 0;
-    const float Nx = l0 * a0.w + l1 * b0.w + l2 * c0.w;
+    const float Nx = PzNx.y;
     const float4 a1 = v[1], b1 = v[4], c1 = v[7];
-    const float Ny = l0 * a1.x + l1 * b1.x + l2 * c1.x, Nz = l0 * a1.y + l1 * b1.y + l2 * c1.y;
+    const float2 Nyz = lerp3(f2(a1.x, a1.y), f2(b1.x, b1.y), f2(c1.x, c1.y));
+    const float Ny = Nyz.x, Nz = Nyz.y;
     float nx = Nx, ny = Ny, nz = Nz;
     if (has[MN]) {  // :64-77 TBN
-        const float f = tf.frac[MN];
-        float mx = filt<0>(bl[MN][0], tx[MN][0], tx[MN][1], tx[MN][2], tx[MN][3]);
-        float my = filt<1>(bl[MN][0], tx[MN][0], tx[MN][1], tx[MN][2], tx[MN][3]);
-        float mz = filt<2>(bl[MN][0], tx[MN][0], tx[MN][1], tx[MN][2], tx[MN][3]);
-        if (two[MN]) {
-            mx += f * (filt<0>(bl[MN][1], tx[MN][4], tx[MN][5], tx[MN][6], tx[MN][7]) - mx);
-            my += f * (filt<1>(bl[MN][1], tx[MN][4], tx[MN][5], tx[MN][6], tx[MN][7]) - my);
-            mz += f * (filt<2>(bl[MN][1], tx[MN][4], tx[MN][5], tx[MN][6], tx[MN][7]) - mz);
-        }
-        const float Tx = l0 * a1.z + l1 * b1.z + l2 * c1.z, Ty = l0 * a1.w + l1 * b1.w + l2 * c1.w;
-        const float Tz = l0 * a2.x + l1 * b2.x + l2 * c2.x, Tw = l0 * a2.y + l1 * b2.y + l2 * c2.y;
+        const float mx = filt2<0>(bl[MN], tx[MN]), my = filt2<1>(bl[MN], tx[MN]), mz = filt2<2>(bl[MN], tx[MN]);
+        const float2 Txy = lerp3(f2(a1.z, a1.w), f2(b1.z, b1.w), f2(c1.z, c1.w));
+        const float2 Tzw = lerp3(f2(a2.x, a2.y), f2(b2.x, b2.y), f2(c2.x, c2.y));
+        const float Tx = Txy.x, Ty = Txy.y, Tz = Tzw.x, Tw = Tzw.y;
         float rx = mx * 2.0f - 1.0f, ry = my * 2.0f - 1.0f, rz = mz * 2.0f - 1.0f;
         float inv = rsqrtf(rx * rx + ry * ry + rz * rz);
         rx *= inv; ry *= inv; rz *= inv;
@@ -913,13 +967,8 @@ __device__ __forceinline__ void shade(const ConvertArgs& a, const typename FragS
     }
     float metal = 0.1f, rough = 0.5f;  // :83-95 (.bg)
     if (LAYOUT != 2 && has[MM]) {      // the standard .ply row carries no PBR values
-        const float f = tf.frac[MM];
-        rough = filt<1>(bl[MM][0], tx[MM][0], tx[MM][1], tx[MM][2], tx[MM][3]);
-        metal = filt<2>(bl[MM][0], tx[MM][0], tx[MM][1], tx[MM][2], tx[MM][3]);
-        if (two[MM]) {
-            rough += f * (filt<1>(bl[MM][1], tx[MM][4], tx[MM][5], tx[MM][6], tx[MM][7]) - rough);
-            metal += f * (filt<2>(bl[MM][1], tx[MM][4], tx[MM][5], tx[MM][6], tx[MM][7]) - metal);
-        }
+        rough = filt2<1>(bl[MM], tx[MM]);
+        metal = filt2<2>(bl[MM], tx[MM]);
     }
     if (LAYOUT == 0) {
         float4* s4 = reinterpret_cast<float4*>(srec_bytes);
@@ -1010,34 +1059,24 @@ __global__ void __launch_bounds__(kFragThreads) fragment_kernel(const __grid_con
         __syncthreads();
         goff = s_goff;
     }
-    const uint32_t nq = min(*reinterpret_cast<const volatile uint32_t*>(a.n_items_out), a.queue_cap);
-    const uint32_t nitems = a.n_units + nq;
+    const uint32_t nitems = min(*reinterpret_cast<const volatile uint32_t*>(a.n_items_out), a.queue_cap);
     const uint32_t* __restrict__ texb = a.tex_base;
     const bool want_keys = a.keys != nullptr;
     uint32_t phase = 0;
 
     for (uint32_t it = blockIdx.x; it < nitems; it += gridDim.x) {
         // ---- the item: a unit's small triangles (implicit: one block per triangle) or queued row blocks ----
-        unsigned long long first;
-        uint32_t unit, nblocks, fb, fe;
+        const FragItem* q = a.items + it;
+        const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(q));
+        const uint2 h1 = __ldg(reinterpret_cast<const uint2*>(q) + 2);
+        const unsigned long long first = (unsigned long long)h0.x | ((unsigned long long)h0.y << 32);
+        const uint32_t unit = h0.z, fb = h1.x, fe = h1.y;
+        const bool unit_item = (h0.w & 0x80000000u) != 0;
+        const uint32_t nblocks = h0.w & 0xffu;
         uint32_t bprefix = 0xffffffffu, bref = 0;  // lane b: block b of the item
-        const bool unit_item = it < a.n_units;
-        if (unit_item) {
-            unit = it;
-            const uint4 d = __ldg(reinterpret_cast<const uint4*>(a.unit_desc + unit));
-            first = (unsigned long long)d.x | ((unsigned long long)d.y << 32);
-            fb = 0; fe = d.z;
-            nblocks = min(a.unit_tris, a.tri_count - unit * a.unit_tris);
-        } else {
-            const FragItem* q = a.items + (it - a.n_units);
-            const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(q));
-            const uint2 h1 = __ldg(reinterpret_cast<const uint2*>(q) + 2);
-            first = (unsigned long long)h0.x | ((unsigned long long)h0.y << 32);
-            unit = h0.z; nblocks = h0.w; fb = h1.x; fe = h1.y;
-            if ((uint32_t)lane < nblocks) {
-                const uint2 b = __ldg(reinterpret_cast<const uint2*>(q->blocks + lane));
-                bprefix = b.x; bref = b.y;
-            }
+        if (!unit_item && (uint32_t)lane < nblocks) {
+            const uint2 b = __ldg(reinterpret_cast<const uint2*>(q->blocks + lane));
+            bprefix = b.x; bref = b.y;
         }
         if (fe <= fb || first + fb >= room) continue;  // uniform over the CTA: nothing to emit
         const uint32_t t0 = unit * a.unit_tris;
@@ -1185,9 +1224,9 @@ __global__ void gather_wait_kernel(const unsigned long long* xch, uint32_t world
 // mip chain: 2x2 box, round half up (matches oracle orc_mip_down)
 // ------------------------------------------------------------------------------------------
 __global__ void mip_down_kernel(const uint32_t* __restrict__ src, uint32_t sw, uint32_t sh, uint32_t* __restrict__ dst,
-                                uint32_t dw, uint32_t dh) {
-    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= dw || y >= dh) return;
+                                uint32_t dw, uint32_t dh, uint32_t y_begin, uint32_t y_end) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = y_begin + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= dw || y >= y_end || y >= dh) return;
     const uint32_t x0 = min(2 * x, sw - 1), x1 = min(2 * x + 1, sw - 1), y0 = min(2 * y, sh - 1), y1 = min(2 * y + 1, sh - 1);
     const uint32_t a = src[(size_t)y0 * sw + x0], b = src[(size_t)y0 * sw + x1], c = src[(size_t)y1 * sw + x0],
                    d = src[(size_t)y1 * sw + x1];
@@ -1302,7 +1341,9 @@ cudaError_t convert_configure(int layout, int* raster_blocks_per_sm, int* fragme
     }
 }
 
-cudaError_t convert_launch(int layout, const ConvertArgs& args, int raster_grid, int fragment_grid, cudaStream_t stream) {
+// mid != nullptr: record it between the two kernels (measurement of the per-kernel shares; disables the programmatic
+// dependent launch, so the kernels do not overlap)
+cudaError_t convert_launch(int layout, const ConvertArgs& args, int raster_grid, int fragment_grid, cudaStream_t stream, cudaEvent_t mid) {
     const size_t smem = raster_smem_bytes(layout), fsmem = fragment_smem_bytes(layout);
     switch (raster_kind(layout)) {
         case 0: raster_kernel<0><<<raster_grid, M2S_RASTER_WARPS * 32, smem, stream>>>(args); break;
@@ -1311,6 +1352,7 @@ cudaError_t convert_launch(int layout, const ConvertArgs& args, int raster_grid,
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    if (mid) { e = cudaEventRecord(mid, stream); if (e != cudaSuccess) return e; }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)fragment_grid);
     cfg.blockDim = dim3(kFragThreads);
@@ -1321,7 +1363,7 @@ cudaError_t convert_launch(int layout, const ConvertArgs& args, int raster_grid,
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
 #ifndef M2S_NO_PDL
-    cfg.numAttrs = 1;
+    cfg.numAttrs = mid ? 0 : 1;
 #else
     cfg.numAttrs = 0;
 #endif
@@ -1340,10 +1382,13 @@ cudaError_t gather_wait_launch(const unsigned long long* xch, uint32_t world, un
     return cudaGetLastError();
 }
 
+// rows [y_begin, y_end) of the destination level (the whole level: 0, dh)
 cudaError_t mip_down_launch(const uint32_t* src, uint32_t sw, uint32_t sh, uint32_t* dst, uint32_t dw, uint32_t dh,
-                            cudaStream_t stream) {
-    dim3 blk(32, 8), grd((dw + 31) / 32, (dh + 7) / 8);
-    mip_down_kernel<<<grd, blk, 0, stream>>>(src, sw, sh, dst, dw, dh);
+                            uint32_t y_begin, uint32_t y_end, cudaStream_t stream) {
+    y_end = y_end < dh ? y_end : dh;
+    if (y_begin >= y_end) return cudaSuccess;
+    dim3 blk(32, 8), grd((dw + 31) / 32, (y_end - y_begin + 7) / 8);
+    mip_down_kernel<<<grd, blk, 0, stream>>>(src, sw, sh, dst, dw, dh, y_begin, y_end);
     return cudaGetLastError();
 }
 

@@ -591,6 +591,11 @@ ORC_API uint64_t orc_convert_prepared(const m2s_scene* sc, const orc_prepared* p
         const int32_t ti[3] = {P->albedo_texture, P->normal_texture, P->metallic_roughness_texture};
         uint32_t flags = 0;
         for (int m = 0; m < 3; ++m) if (ti[m] >= 0 && (uint32_t)ti[m] < sc->texture_count) flags |= 1u << m;
+        /* only the maps the layout's record carries are sampled (the product uploads and samples the same set):
+         * PACKED56 has neither normal nor metallic/roughness, the standard .ply row no metallic/roughness; the
+         * values that ARE stored do not depend on the skipped maps */
+        if (pr->layout == M2S_LAYOUT_PACKED56) flags &= 1u;
+        else if (pr->layout == M2S_LAYOUT_PLY_STANDARD) flags &= 3u;
         const float ia = 1.0f / (float)(s->area2 < 0 ? -s->area2 : s->area2);
         uint64_t idx = offs[t];
         int64_t E[3];

@@ -359,7 +359,9 @@ def test_reference_shaped_interface(tmp_path):
 
 # ---- full-size properties (BASELINE config 2 stand-in) -------------------------------------------------
 def test_helmet_standin_density_512_full_parity(gpu_ctx):
-    s = synth.helmet_standin(1024)
+    """BASELINE config 2 exactly as bench.py runs it: 70 074 triangles, three 2048^2 maps, density 512 — every record of
+    both layouts against the oracle."""
+    s = synth.helmet_standin(2048)
     out = check(gpu_ctx, s, 512, LAYOUT_REF96)
     assert 0.4e6 < out.total < 1.2e6
     out2 = check(gpu_ctx, s, 512, LAYOUT_PACKED56)
@@ -426,6 +428,11 @@ def test_config3_sponza_standin_reference_cap_and_uncapped(gpu_ctx):
     want = np.histogram((okeys >> np.uint64(24)).astype(np.int64), bins=firsts)[0]
     assert np.array_equal(got, want)
     assert np.array_equal(np.sort(un.keys_numpy()), np.sort(okeys))
+    assert_records_match(s, LAYOUT_PACKED56, un.numpy(), un.keys_numpy(), orec, okeys)  # every record value, not only the keys
+    # the capped run stores exactly 7 M distinct fragments of the uncapped set (which ones is atomic-order dependent)
+    if capped.overflow:
+        ck = gpu_ctx.convert(ds, 1024, LAYOUT_PACKED56, want_keys=True).keys_numpy()
+        assert len(ck) == 7_000_000 and len(np.unique(ck)) == len(ck) and np.isin(ck, okeys).all()
     ds.free()
 
 
@@ -446,3 +453,64 @@ def test_config4_million_triangle_sphere(gpu_ctx):
         parts.append(o.keys_numpy())
     assert np.array_equal(np.sort(np.concatenate(parts)), np.sort(okeys))
     ds.free()
+
+
+# ---- BASELINE config 5: density sweep on the DamagedHelmet stand-in ---------------------------------------------
+@pytest.mark.parametrize("R", [64, 128, 256, 512, 1024, 2048])
+def test_config5_damaged_helmet_density_sweep(gpu_ctx, R):
+    """BASELINE.json configs[4]: density 64 -> 2048 on the DamagedHelmet stand-in (15 488 triangles, three 2048^2 maps),
+    the scene bench.py --workload damaged_helmet_standin runs.  Every record against the oracle at every density
+    (R = 2048: 9.8 M gaussians, 24 x the box of a small triangle — the row-span path), plus the size-independent
+    properties: fragment identities unique and inside the R x R grid, and the reference cap (7 M) applied to the
+    running index."""
+    s = _dh_scene()
+    out = check(gpu_ctx, s, R, LAYOUT_PACKED56, flags=FLAG_UNCAPPED, capacity=6 * R * R)
+    _keys_unique_and_in_range(out.keys_numpy(), s, R)
+    assert 2.0 * R * R < out.total < 2.8 * R * R
+    if R == 2048:  # the reference's own capacity rule clamps this one
+        ds = gpu_ctx.upload(s)
+        capped = gpu_ctx.convert(ds, R, LAYOUT_PACKED56, want_keys=True)
+        assert capped.cap == 7_000_000 and capped.overflow and capped.total == out.total and capped.written == 7_000_000
+        ck = capped.keys_numpy()
+        assert len(np.unique(ck)) == 7_000_000 and np.isin(ck, out.keys_numpy()).all()
+        ds.free()
+
+
+_DH = {}
+
+
+def _dh_scene():
+    if "s" not in _DH:
+        _DH["s"] = synth.damaged_helmet_standin(2048)
+    return _DH["s"]
+
+
+# ---- shard upload: triangles of a range + only the texture rows they sample ---------------------------------------
+@pytest.mark.parametrize("tex_hw", [(256, 256), (300, 64), (37, 100)])
+def test_upload_range_brings_every_texel_the_shard_samples(gpu_ctx, tex_hw):
+    """m2s_scene_upload_range copies a triangle range and, per 16-row group, only the texture rows (and their mip rows)
+    that range can sample.  Converting each of 5 shards from its own partial upload must give exactly the records of the
+    oracle's single pass — a missing row group would show up as a wrong colour.  Non-power-of-two and tall textures
+    exercise the group/mip-row arithmetic, the REPEAT wrap at v = 0/1 the wrap-around groups."""
+    h, w = tex_hw
+    tri = synth.displaced_sphere(48, 40, seed=21, amplitude=0.06)
+    tex = [synth.random_texture(w, h, 31), synth.random_texture(w, h, 32), synth.random_texture(w, h, 33)]
+    s = Scene(tri, [Primitive(0, len(tri), (1.0, 0.9, 0.8, 1.0), 0, 1, 2)], tex)
+    s.compute_bboxes()
+    R = 160
+    want, wkeys, total = oracle.convert(s, R, LAYOUT_REF96, flags=FLAG_UNCAPPED, capacity=6 * R * R)
+    from mesh2splat_b200.shard import plan_shards
+    recs, keys, h2d = [], [], []
+    for first, count in plan_shards(s.triangle_count, 5):
+        ds = gpu_ctx.upload_range(s, LAYOUT_REF96, first, count)
+        h2d.append(ds.h2d_bytes())
+        o = gpu_ctx.convert(ds, R, LAYOUT_REF96, flags=FLAG_UNCAPPED, capacity=6 * R * R, first_triangle=first,
+                            triangle_count=count, want_keys=True)
+        recs.append(o.numpy().copy()); keys.append(o.keys_numpy().copy())
+        ds.free()
+    got, gk = np.concatenate(recs), np.concatenate(keys)
+    assert len(got) == total
+    assert_records_match(s, LAYOUT_REF96, got, gk, want, wkeys)
+    if h >= 256:  # the sphere's rows are latitude bands: a shard needs a fraction of the image
+        full = s.triangles.nbytes + sum(t.nbytes for t in tex)
+        assert max(h2d) < 0.6 * full, (h2d, full)
