@@ -20,8 +20,7 @@ cudaError_t convert_configure(int layout, int* raster_blocks_per_sm, int* fragme
 cudaError_t convert_launch(int layout, const ConvertArgs& args, int raster_grid, int fragment_grid, cudaStream_t stream, cudaEvent_t mid);
 cudaError_t gather_wait_launch(const unsigned long long* xch, uint32_t world, unsigned long long epoch, unsigned long long gcap,
                                unsigned long long* total_global, cudaStream_t stream);
-cudaError_t mip_down_launch(const uint32_t* src, uint32_t sw, uint32_t sh, uint32_t* dst, uint32_t dw, uint32_t dh,
-                            uint32_t y_begin, uint32_t y_end, cudaStream_t stream);
+cudaError_t mip_groups_launch(uint32_t* arena, const DTexture& t, uint32_t g0, uint32_t g1, cudaStream_t stream);
 cudaError_t ply_rows_launch(const void* ref96, unsigned long long count, const unsigned long long* d_count,
                             uint32_t format, float mult, void* rows, cudaStream_t stream);
 // host-side helpers implemented in m2s_host.cpp
@@ -260,9 +259,8 @@ static m2s_status upload_texture_groups(m2s_ctx* ctx, m2s_dscene* d, uint32_t t,
     if (r0 >= r1) return M2S_OK;
     CUDA_TRY(cudaMemcpyAsync(d->d_arena + dt.off[0] + (size_t)r0 * W, d->h_rgba[t] + (size_t)r0 * W * 4, (size_t)(r1 - r0) * W * 4,
                              cudaMemcpyHostToDevice, ctx->stream));
-    for (uint32_t l = 1; l < dt.nlevels; ++l)  // level-l row j needs level-(l-1) rows 2j, 2j+1: inside the same 16-row group
-        CUDA_TRY(mip_down_launch(d->d_arena + dt.off[l - 1], dt.w[l - 1], dt.h[l - 1], d->d_arena + dt.off[l], dt.w[l], dt.h[l],
-                                 (g0 * kTexGroupRows) >> l, (g1 * kTexGroupRows) >> l, ctx->stream));
+    // level-l row j needs level-(l-1) rows 2j, 2j+1: inside the same 16-row group — all levels in one launch
+    CUDA_TRY(mip_groups_launch(d->d_arena, dt, g0, std::min<uint32_t>(g1, (H + kTexGroupRows - 1) / kTexGroupRows), ctx->stream));
     for (uint32_t g = g0; g < g1 && g < d->present[t].size(); ++g) d->present[t][g] = 1;
     d->h2d_bytes += (uint64_t)(r1 - r0) * W * 4;
     return M2S_OK;
@@ -512,11 +510,11 @@ static m2s_status convert_enqueue_impl(m2s_ctx* ctx, const m2s_dscene* s, const 
     // item queue: a warp stops taking slots once it has seen the counter pass the cap, so live items cover disjoint
     // output ranges below it: per unit one item of small triangles and one end-of-unit item, cap/32 items closed by
     // 32 non-empty blocks, cap/flush closed by their fragment count, cap/item_max pieces of oversized blocks; plus
-    // ONE reservation per raster warp that may straddle the cap (<= max(kStashItems, kMaxSplit) slots).  The queue
+    // ONE reservation per raster warp that may straddle the cap (< 2 kMaxSplit + kStashItems slots).  The queue
     // cannot overflow.
     const uint64_t raster_warps = (uint64_t)grid * convert_warps_per_cta(klayout);
     const uint64_t queue_cap = std::min<uint64_t>(2 * n_units + cap / 32 + cap / flush_frags + cap / item_max +
-                                                  raster_warps * std::max<uint64_t>(kStashItems, kMaxSplit) + 64, (1u << 24) - 1);
+                                                  raster_warps * (2ull * kMaxSplit + kStashItems) + 64, (1u << 24) - 1);
     {   // scratch between the two kernels (grown on demand, kept by the context)
         m2s_status st = grow(ctx, &ctx->d_trifrag, &ctx->trifrag_bytes, std::max<uint64_t>(count, 1) * tri_frag_bytes(klayout), stream);
         if (st == M2S_OK) st = grow(ctx, &ctx->d_items, &ctx->items_bytes, queue_cap * sizeof(FragItem), stream);

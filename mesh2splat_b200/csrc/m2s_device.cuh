@@ -11,7 +11,7 @@ constexpr int kUnitTris = 32;            // max triangles per work unit (one lan
 constexpr int kTriBytes = 144;           // 36 floats
 constexpr uint32_t kSmallCand = 64;      // <= this many candidate pixels (and <= 32 rows): coverage as a 64-bit mask
 constexpr int kItemBlocks = 32;          // row blocks (<= 32 pixel rows of one triangle) per fragment work item
-constexpr int kStashItems = 4;           // work items a raster warp publishes with one atomic
+constexpr int kStashItems = 8;           // work items a raster warp publishes with one atomic
 constexpr uint32_t kItemMaxFrags = 2048; // upper bound of ConvertArgs::item_max_frags
 constexpr uint32_t kMaxSplit = 64;       // queue slots one oversized row block can take (item_max_frags >= R / 2)
 constexpr unsigned long long kFragMask = (1ull << 40) - 1;  // ConvertArgs::counter: fragments | queue slots << 40

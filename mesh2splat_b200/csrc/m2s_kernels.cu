@@ -172,7 +172,8 @@ struct __align__(16) TriRec {     // 144 B (1 map) / 176 B (3 maps)
     float scale[2];               // raw (REF96) or log(scale * sigma/R); the third component is a constant
     unsigned meta;                // bits 0-2: map m has the same level sizes as map 0 (=> same footprint and weights);
                                   // bits 4-15: x0, bits 16-27: y0 of the candidate pixel box
-    unsigned first;               // fragments of the unit's small triangles before this one
+    unsigned first;               // small triangles of the unit before this one: their fragments (low 16 bits) and their
+                                  // box rows (high 16 bits) — the triangle's place in the unit item's span table
     float frac[NMAPS];            // trilinear blend per map (0 => single level)
     TexRef tex[NMAPS];
 };
@@ -569,7 +570,8 @@ __device__ __forceinline__ void stash_block(const ConvertArgs& a, WarpBlock<RK>&
             wb.pend[st.n_it * kItemBlocks].prefix = 0; wb.pend[st.n_it * kItemBlocks].ref = ref;
         }
         st.frags += bt; st.slots += (bt + a.item_max_frags - 1) / a.item_max_frags; st.n_it += 1;
-        stash_flush<RK>(a, wb, unit, st, lane);  // at most one split block per reservation (bounds the queue slack)
+        // a reservation takes at most 2 * kMaxSplit queue slots (bounds the slack the host adds to the queue)
+        if (st.n_it == kStashItems || st.slots >= kMaxSplit) stash_flush<RK>(a, wb, unit, st, lane);
         return;
     }
     if (lane == 0) {
@@ -717,9 +719,16 @@ __global__ void __launch_bounds__(M2S_RASTER_WARPS * 32, 1) raster_kernel(const 
             if (lane >= d) incl_scan += v;
         }
         const uint32_t total_small = __shfl_sync(0xffffffffu, incl_scan, 31);
+        const uint32_t myrows = small ? (uint32_t)ts.h : 0u;  // rows this triangle contributes to the unit item's span table
+        uint32_t rows_scan = myrows;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, rows_scan, d);
+            if (lane >= d) rows_scan += v;
+        }
         if ((uint32_t)lane < ntri) {
             myrec.hits = hits;
-            myrec.first = incl_scan - nh;
+            myrec.first = (incl_scan - nh) | ((rows_scan - myrows) << 16);
             myrec.box = cnt ? ((unsigned)ts.w | ((unsigned)ts.h << 13) | (ts.incl << 26) | (small ? kBoxSmall : 0u)) : 0u;
         }
         __syncwarp();
@@ -857,16 +866,20 @@ __device__ __forceinline__ void copy_span(uint8_t* dstbase, unsigned long long b
 // ------------------------------------------------------------------------------------------
 constexpr int kFragWarps = M2S_FRAG_WARPS;
 constexpr int kFragThreads = kFragWarps * 32;
-constexpr uint32_t kSpanWords = kItemBlocks * 32;  // one word per pixel row of every block: prefix << 12 | first column
+constexpr uint32_t kSpanRows = kItemBlocks * 32;   // rows of an item's span table
+constexpr uint32_t kMaxGroups = 128;               // 32-fragment groups of one item (< (item_max + flush) / 32)
 
+// span table entry: one pixel row of one triangle of the item
+//   x = fragments of the item before this row; y = first column (12 bits) | row relative to the box (12) << 12 | slot (5) << 24
 template <int LAYOUT>
 struct FragSmem {
     using Rec = TriRec<RCfg<Cfg<LAYOUT>::kRK>::kMaps>;
     static constexpr size_t kRecOff = 0;
     static constexpr size_t kTriOff = kRecOff + kUnitTris * sizeof(Rec);
     static constexpr size_t kSpanOff = kTriOff + kUnitTris * kTriBytes;
-    static constexpr size_t kStageOff = kSpanOff + kSpanWords * 4;
-    static constexpr size_t kBytes = kStageOff + (size_t)kFragWarps * 32 * Cfg<LAYOUT>::kStride;
+    static constexpr size_t kGroupOff = kSpanOff + kSpanRows * 8;
+    static constexpr size_t kStageAligned = (kGroupOff + (kMaxGroups + 1) * 2 + 15) & ~(size_t)15;
+    static constexpr size_t kBytes = kStageAligned + (size_t)kFragWarps * 32 * Cfg<LAYOUT>::kStride;
 };
 
 __device__ __forceinline__ float inv_sigmoid_fast(float a) {  // utils.hpp:270; alpha = 1 -> +inf as in the reference
@@ -1029,8 +1042,9 @@ __global__ void __launch_bounds__(kFragThreads) fragment_kernel(const __grid_con
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const Rec* recs = reinterpret_cast<const Rec*>(smem + S::kRecOff);
     const float4* tris = reinterpret_cast<const float4*>(smem + S::kTriOff);
-    uint32_t* span = reinterpret_cast<uint32_t*>(smem + S::kSpanOff);
-    unsigned char* stage = smem + S::kStageOff + (size_t)warp * 32 * kStride;  // this warp's 32 records
+    uint2* span = reinterpret_cast<uint2*>(smem + S::kSpanOff);
+    unsigned short* gstart = reinterpret_cast<unsigned short*>(smem + S::kGroupOff);  // span row holding fragment 32 g of the item
+    unsigned char* stage = smem + S::kStageAligned + (size_t)warp * 32 * kStride;  // this warp's 32 records
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
         fence_barrier_init();
@@ -1090,74 +1104,90 @@ __global__ void __launch_bounds__(kFragThreads) fragment_kernel(const __grid_con
         }
         mbar_wait(&bar, phase);
         phase ^= 1;
-        if (unit_item && (uint32_t)lane < nblocks) {  // block b = triangle b: its rows are the rows of the coverage mask
-            const unsigned box = recs[lane].box;
-            const uint32_t rows = (box & kBoxSmall) ? ((box >> 13) & 0x1fffu) : 0u;
-            bprefix = recs[lane].first;
-            bref = (uint32_t)lane | (rows << 17);
-        }
-        // ---- row spans of the item's blocks: prefix << 12 | first column, one word per row ----
-        for (uint32_t b = warp; b < nblocks; b += kFragWarps) {
-            const uint32_t ref = __shfl_sync(0xffffffffu, bref, (int)b), bp = __shfl_sync(0xffffffffu, bprefix, (int)b);
-            const uint32_t slot = ref & 31u, row_begin = (ref >> 5) & 0xfffu, nrows = (ref >> 17) & 63u;
-            const Rec& r = recs[slot];
-            const unsigned box = r.box;
-            const int w = (int)(box & 0x1fffu);
-            uint32_t n = 0;
-            int xl = 0;
-            if ((uint32_t)lane < nrows) {
+        // ---- the item's span table: one entry per pixel row, fragments-before-the-row ascending ----
+        uint32_t nrows_flat;
+        if (unit_item) {
+            // the small triangles of the unit: thread (t, q) takes rows q, q+4, .. of triangle t; a row's place in the
+            // table and its fragment prefix come straight from the record (TriRec::first) and the coverage mask
+            const uint32_t t = threadIdx.x >> 2, q = threadIdx.x & 3u;
+            if (kFragThreads < 128 && threadIdx.x == 0) __trap();  // the (t, q) mapping needs 4 threads per triangle
+            if (t < ntri) {
+                const Rec& r = recs[t];
+                const unsigned box = r.box;
                 if (box & kBoxSmall) {
+                    const uint32_t w = box & 0x1fffu, h = (box >> 13) & 0x1fffu;
+                    const unsigned long long hits = r.hits;
+                    const uint32_t fr = r.first & 0xffffu, ro = r.first >> 16;
                     const unsigned long long rowmask = w >= 64 ? ~0ull : ((1ull << w) - 1ull);
-                    const unsigned long long bits = (r.hits >> (lane * w)) & rowmask;  // lane < h, h * w <= 64
-                    n = (uint32_t)__popcll(bits);
-                    xl = bits ? __ffsll((long long)bits) - 1 : 0;
-                } else {
+                    for (uint32_t y = q; y < h; y += 4) {       // h * w <= 64
+                        const unsigned long long below = y ? (hits & ((1ull << (y * w)) - 1ull)) : 0ull;
+                        const unsigned long long bits = (hits >> (y * w)) & rowmask;
+                        const uint32_t xl = bits ? (uint32_t)__ffsll((long long)bits) - 1u : 0u;
+                        span[ro + y] = make_uint2(fr + (uint32_t)__popcll(below), xl | (y << 12) | (t << 24));
+                    }
+                }
+            }
+            const Rec& last = recs[ntri - 1];
+            nrows_flat = (last.first >> 16) + ((last.box & kBoxSmall) ? ((last.box >> 13) & 0x1fffu) : 0u);
+        } else {
+            for (uint32_t b = warp; b < nblocks; b += kFragWarps) {  // one warp per block of <= 32 rows, one lane per row
+                const uint32_t ref = __shfl_sync(0xffffffffu, bref, (int)b), bp = __shfl_sync(0xffffffffu, bprefix, (int)b);
+                const uint32_t slot = ref & 31u, row_begin = (ref >> 5) & 0xfffu, nrows = (ref >> 17) & 63u;
+                const Rec& r = recs[slot];
+                const unsigned box = r.box;
+                uint32_t n = 0;
+                int xl = 0;
+                if ((uint32_t)lane < nrows) {
                     RowState rs;
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
                         rs.E[k] = r.E0[k] - (((box >> (26 + k)) & 1u) ? 0 : 1);
                         rs.A[k] = r.A[k]; rs.B[k] = r.B[k];
                     }
-                    rs.w = w;
+                    rs.w = (int)(box & 0x1fffu);
                     n = span_row(rs, (int)(row_begin + lane), xl);
                 }
-            }
-            uint32_t incl = n;
+                uint32_t incl = n;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += t;
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                // rows past the block's last one repeat the block end: the table stays sorted, they are never selected
+                span[b * 32 + lane] = make_uint2(bp + incl - n, (uint32_t)xl | ((row_begin + lane) << 12) | (slot << 24));
             }
-            span[b * 32 + lane] = ((bp + incl - n) << 12) | (uint32_t)xl;  // rows past the block: prefix = block end
+            nrows_flat = nblocks * 32;
+        }
+        __syncthreads();
+        // ---- where each 32-fragment group starts in the table: one binary search per group, all groups at once ----
+        const uint32_t nfrag = fe - fb, ngroups = (nfrag + 31) / 32;
+        for (uint32_t g = threadIdx.x; g <= ngroups; g += kFragThreads) {
+            const uint32_t j = min(fb + g * 32, fe - 1);
+            uint32_t lo = 0;
+#pragma unroll
+            for (int stp = (int)kSpanRows / 2; stp > 0; stp >>= 1) {
+                const uint32_t c = lo + stp;
+                if (c < nrows_flat && span[c].x <= j) lo = c;
+            }
+            gstart[g] = (unsigned short)lo;
         }
         __syncthreads();
 
         // ---- 32 consecutive fragments per warp step ----
-        const uint32_t nfrag = fe - fb;
-        for (uint32_t g = warp; g * 32 < nfrag; g += kFragWarps) {
+        for (uint32_t g = warp; g < ngroups; g += kFragWarps) {
             const uint32_t j0 = fb + g * 32;
             const uint32_t nfr = min(32u, fe - j0);
             const uint32_t j = j0 + min((uint32_t)lane, nfr - 1);  // idle lanes shadow the last fragment
-            // block: the last one whose prefix is <= j (blocks without fragments share their successor's prefix)
-            uint32_t b = 0;
-#pragma unroll
-            for (int stp = 16; stp > 0; stp >>= 1) {
-                const uint32_t c = b + stp;
-                const uint32_t pv = __shfl_sync(0xffffffffu, bprefix, (int)(c & 31u));
-                if (c < nblocks && pv <= j) b = c;
+            // the row of fragment j: the last entry whose prefix is <= j, between the group's first and last row
+            uint32_t lo = gstart[g];
+            const uint32_t hi = gstart[g + 1];
+            for (uint32_t stp = hi > lo ? (1u << (31 - __clz(hi - lo))) : 0u; stp; stp >>= 1) {  // uniform trip count
+                const uint32_t c = lo + stp;
+                if (c <= hi && span[c].x <= j) lo = c;
             }
-            const uint32_t ref = __shfl_sync(0xffffffffu, bref, (int)b);
-            const uint32_t slot = ref & 31u, row_begin = (ref >> 5) & 0xfffu;
-            // row: the last one whose prefix is <= j
-            const uint32_t* sp = span + b * 32;
-            uint32_t r = 0;
-#pragma unroll
-            for (int stp = 16; stp > 0; stp >>= 1) {
-                const uint32_t c = r + stp;
-                if ((sp[c] >> 12) <= j) r = c;
-            }
-            const uint32_t sw = sp[r];
-            const int dxi = (int)((sw & 0xfffu) + (j - (sw >> 12))), dyi = (int)(row_begin + r);
+            const uint2 sw = span[lo];
+            const uint32_t slot = sw.y >> 24;
+            const int dxi = (int)((sw.y & 0xfffu) + (j - sw.x)), dyi = (int)((sw.y >> 12) & 0xfffu);
             const Rec& tf = recs[slot];
             if ((uint32_t)lane < nfr) shade<LAYOUT>(a, tf, tris + slot * 9, dxi, dyi, texb, stage + lane * kStride);
             __syncwarp();
@@ -1221,22 +1251,48 @@ __global__ void gather_wait_kernel(const unsigned long long* xch, uint32_t world
 }
 
 // ------------------------------------------------------------------------------------------
-// mip chain: 2x2 box, round half up (matches oracle orc_mip_down)
+// mip chain: 2x2 box, round half up (matches oracle orc_mip_down; GL_TEXTURE_MAX_LEVEL 4, glUtils.cpp:313)
 // ------------------------------------------------------------------------------------------
-__global__ void mip_down_kernel(const uint32_t* __restrict__ src, uint32_t sw, uint32_t sh, uint32_t* __restrict__ dst,
-                                uint32_t dw, uint32_t dh, uint32_t y_begin, uint32_t y_end) {
-    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = y_begin + blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= dw || y >= y_end || y >= dh) return;
-    const uint32_t x0 = min(2 * x, sw - 1), x1 = min(2 * x + 1, sw - 1), y0 = min(2 * y, sh - 1), y1 = min(2 * y + 1, sh - 1);
-    const uint32_t a = src[(size_t)y0 * sw + x0], b = src[(size_t)y0 * sw + x1], c = src[(size_t)y1 * sw + x0],
-                   d = src[(size_t)y1 * sw + x1];
+__device__ __forceinline__ uint32_t box4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     uint32_t o = 0;
 #pragma unroll
     for (int s = 0; s < 32; s += 8) {
         const uint32_t sum = ((a >> s) & 0xff) + ((b >> s) & 0xff) + ((c >> s) & 0xff) + ((d >> s) & 0xff);
         o |= ((sum + 2) >> 2) << s;
     }
-    dst[(size_t)y * dw + x] = o;
+    return o;
+}
+// ALL levels of the 16-row groups [g0, g0 + gridDim.y) of one texture in one launch: a CTA takes 64 columns x 16 rows of
+// level 0 and produces 32x8, 16x4, 8x2 and 4x1 texels of levels 1..4 (level l row j needs level l-1 rows 2j, 2j+1
+// clamped to the last row: a 16-row group, and a 64-column tile, is closed under the filter).
+__global__ void __launch_bounds__(256) mip_groups_kernel(uint32_t* __restrict__ arena, const DTexture t, uint32_t g0) {
+    __shared__ uint32_t lv[3][8][32];  // levels 1..3 of this tile
+    const uint32_t gx = blockIdx.x, g = g0 + blockIdx.y, tid = threadIdx.x;
+    uint32_t cols = 32, rows = 8;
+#pragma unroll
+    for (uint32_t l = 1; l <= 4; ++l) {
+        if (l < t.nlevels && tid < cols * rows) {
+            const uint32_t lx = tid % cols, ly = tid / cols;
+            const uint32_t x = gx * cols + lx, y = g * rows + ly;
+            const uint32_t dw = t.w[l], dh = t.h[l], sw = t.w[l - 1], sh = t.h[l - 1];
+            if (x < dw && y < dh) {
+                const uint32_t x0 = min(2 * x, sw - 1), x1 = min(2 * x + 1, sw - 1), y0 = min(2 * y, sh - 1), y1 = min(2 * y + 1, sh - 1);
+                uint32_t a, b, c, d;
+                if (l == 1) {
+                    const uint32_t* src = arena + t.off[0];
+                    a = src[(size_t)y0 * sw + x0]; b = src[(size_t)y0 * sw + x1]; c = src[(size_t)y1 * sw + x0]; d = src[(size_t)y1 * sw + x1];
+                } else {  // the source texels are this tile's own texels of the level above
+                    const uint32_t bx = gx * cols * 2, by = g * rows * 2;
+                    a = lv[l - 2][y0 - by][x0 - bx]; b = lv[l - 2][y0 - by][x1 - bx]; c = lv[l - 2][y1 - by][x0 - bx]; d = lv[l - 2][y1 - by][x1 - bx];
+                }
+                const uint32_t o = box4(a, b, c, d);
+                arena[t.off[l] + (size_t)y * dw + x] = o;
+                if (l < 4) lv[l - 1][ly][lx] = o;
+            }
+        }
+        __syncthreads();
+        cols >>= 1; rows >>= 1;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1382,13 +1438,11 @@ cudaError_t gather_wait_launch(const unsigned long long* xch, uint32_t world, un
     return cudaGetLastError();
 }
 
-// rows [y_begin, y_end) of the destination level (the whole level: 0, dh)
-cudaError_t mip_down_launch(const uint32_t* src, uint32_t sw, uint32_t sh, uint32_t* dst, uint32_t dw, uint32_t dh,
-                            uint32_t y_begin, uint32_t y_end, cudaStream_t stream) {
-    y_end = y_end < dh ? y_end : dh;
-    if (y_begin >= y_end) return cudaSuccess;
-    dim3 blk(32, 8), grd((dw + 31) / 32, (y_end - y_begin + 7) / 8);
-    mip_down_kernel<<<grd, blk, 0, stream>>>(src, sw, sh, dst, dw, dh, y_begin, y_end);
+// levels 1.. of the 16-row groups [g0, g1) of one texture (level 0 must be resident), one launch
+cudaError_t mip_groups_launch(uint32_t* arena, const DTexture& t, uint32_t g0, uint32_t g1, cudaStream_t stream) {
+    if (t.nlevels <= 1 || g1 <= g0) return cudaSuccess;
+    dim3 grd((t.w[0] + 63) / 64, g1 - g0);
+    mip_groups_kernel<<<grd, 256, 0, stream>>>(arena, t, g0);
     return cudaGetLastError();
 }
 

@@ -513,4 +513,4 @@ def test_upload_range_brings_every_texel_the_shard_samples(gpu_ctx, tex_hw):
     assert_records_match(s, LAYOUT_REF96, got, gk, want, wkeys)
     if h >= 256:  # the sphere's rows are latitude bands: a shard needs a fraction of the image
         full = s.triangles.nbytes + sum(t.nbytes for t in tex)
-        assert max(h2d) < 0.6 * full, (h2d, full)
+        assert max(h2d) < 0.75 * full, (h2d, full)
