@@ -21,6 +21,8 @@ cudaError_t convert_launch(int layout, const ConvertArgs& args, int raster_grid,
 cudaError_t gather_wait_launch(const unsigned long long* xch, uint32_t world, unsigned long long epoch, unsigned long long gcap,
                                unsigned long long* total_global, cudaStream_t stream);
 cudaError_t mip_groups_launch(uint32_t* arena, const DTexture& t, uint32_t g0, uint32_t g1, cudaStream_t stream);
+cudaError_t vrange_launch(const float4* tris, uint32_t first, uint32_t count, const DRange* ranges, uint32_t nranges, const DPrim* prims,
+                          uint32_t ntex, int* minmax, cudaStream_t stream);
 cudaError_t ply_rows_launch(const void* ref96, unsigned long long count, const unsigned long long* d_count,
                             uint32_t format, float mult, void* rows, cudaStream_t stream);
 // host-side helpers implemented in m2s_host.cpp
@@ -40,6 +42,11 @@ using namespace m2s;
         }                                                                                           \
     } while (0)
 
+struct VRangeSlot {        // v-range reduction of one pipeline chunk: device buffer + pinned host copy + "copy done" event
+    int* d_minmax = nullptr;     // [2 * ntex]: sortable-int min | max of v per texture, then 1 non-finite flag
+    int* h_minmax = nullptr;     // pinned
+    cudaEvent_t ev = nullptr;
+};
 struct m2s_ctx {
     int device = 0;
     int sm_count = 0;
@@ -60,6 +67,8 @@ struct m2s_ctx {
     static constexpr size_t kStageBytes = 32u << 20;
     unsigned char* h_stage[2] = {nullptr, nullptr};
     cudaEvent_t ev_chunk[kMaxChunks] = {};
+    VRangeSlot vr[kMaxChunks];        // v-range reductions of the host pipeline (lazy texture upload)
+    uint32_t vr_ntex = 0;                    // textures the slots are sized for
     static constexpr int kLayouts = 5;
     int blocks_per_sm[kLayouts] = {};       // raster kernel (persistent)
     int frag_blocks_per_sm[kLayouts] = {};  // fragment kernel
@@ -204,6 +213,7 @@ M2S_EXPORT void m2s_ctx_destroy(m2s_ctx* c) {
     cudaFreeHost(c->h_total);
     cudaFree(c->d_chunk_tot); cudaFreeHost(c->h_chunk_tot);
     for (int i = 0; i < 2; ++i) if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
+    for (auto& v : c->vr) { if (v.d_minmax) cudaFree(v.d_minmax); if (v.h_minmax) cudaFreeHost(v.h_minmax); if (v.ev) cudaEventDestroy(v.ev); }
     for (int i = 0; i < m2s_ctx::kMaxChunks; ++i) if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); if (c->ev_mid) cudaEventDestroy(c->ev_mid);
     if (c->stream2) cudaStreamDestroy(c->stream2);
@@ -266,58 +276,74 @@ static m2s_status upload_texture_groups(m2s_ctx* ctx, m2s_dscene* d, uint32_t t,
     return M2S_OK;
 }
 
-// Brings in the texture rows the triangles [lo, hi) can sample (lazily uploaded scenes): per primitive the v-range of
-// its triangles in the range gives the level-0 rows; +-3 row groups cover the footprints of all five mip levels
-// (level l reaches 2^(l+1) level-0 rows beyond the sample point, plus the drift of non-power-of-two chains) and the
-// REPEAT wrap at both ends.  A range whose v spans a whole period (or is not finite) takes the whole image.
-static m2s_status ensure_textures_for_range(m2s_ctx* ctx, m2s_dscene* d, const m2s_scene* sc, uint64_t lo, uint64_t hi) {
-    std::vector<std::vector<uint8_t>> need(d->ntex);
-    bool any = false;
-    for (uint32_t p = 0; p < sc->primitive_count; ++p) {
-        const m2s_primitive& pr = sc->primitives[p];
-        const uint64_t a = std::max<uint64_t>(pr.first_triangle, lo), b = std::min<uint64_t>(pr.first_triangle + pr.triangle_count, hi);
-        if (a >= b) continue;
-        const int32_t ti[3] = {pr.albedo_texture, pr.normal_texture, pr.metallic_roughness_texture};
-        bool wanted = false;
-        for (int m = 0; m < 3; ++m)
-            if (ti[m] >= 0 && (uint32_t)ti[m] < d->ntex)
-                for (uint8_t g : d->present[ti[m]]) if (!g) { wanted = true; break; }
-        if (!wanted) continue;
-        float vmin = 3.402823466e+38f, vmax = -3.402823466e+38f;
-        bool finite = true;
-        for (uint64_t t = a; t < b; ++t)
-            for (int k = 0; k < 3; ++k) {
-                const float v = sc->triangles[t * M2S_FLOATS_PER_TRIANGLE + M2S_FLOATS_PER_VERTEX * k + 11];
-                if (!(v >= -1e30f && v <= 1e30f)) finite = false;
-                vmin = std::min(vmin, v); vmax = std::max(vmax, v);
-            }
-        for (int m = 0; m < 3; ++m) {
-            if (ti[m] < 0 || (uint32_t)ti[m] >= d->ntex) continue;
-            const uint32_t t = (uint32_t)ti[m];
-            const uint32_t ng = (uint32_t)d->present[t].size();
-            if (need[t].empty()) need[t].assign(ng, 0);
-            any = true;
-            const float fl = std::floor(vmin);
-            if (!finite || !(vmax - fl < 1.0f) || ng <= 8) { std::fill(need[t].begin(), need[t].end(), 1); continue; }
+// Which texture rows can the triangles [lo, hi) sample?  The v-range per texture is reduced ON THE GPU from the triangles
+// already uploaded (vrange_launch: the host would have to stream the same 144 B/triangle through one core — ~1 ms for
+// the bench scene), copied back (8 bytes per texture) and turned into 16-row groups here: +-3 groups cover the
+// footprints of all five mip levels (level l reaches 2^(l+1) level-0 rows beyond the sample point, plus the drift of
+// non-power-of-two chains) and the REPEAT wrap at both ends; a range whose v spans a whole period (or is not finite)
+// takes the whole image.
+static float sortable_to_float(int i) { i ^= (i >> 31) & 0x7fffffff; float f; std::memcpy(&f, &i, 4); return f; }
+
+static m2s_status vrange_enqueue(m2s_ctx* ctx, m2s_dscene* d, uint64_t lo, uint64_t hi, int slot);
+static m2s_status upload_groups_from_vrange(m2s_ctx* ctx, m2s_dscene* d, int slot) {
+    const uint32_t nt = d->ntex;
+    if (!nt) return M2S_OK;
+    CUDA_TRY(cudaEventSynchronize(ctx->vr[slot].ev));
+    const int* mm = ctx->vr[slot].h_minmax;
+    const bool finite = mm[2 * nt] == 0;
+    for (uint32_t t = 0; t < nt; ++t) {
+        if (mm[t] > mm[nt + t]) continue;  // no triangle of the range samples this texture
+        const uint32_t ng = (uint32_t)d->present[t].size();
+        std::vector<uint8_t> need(ng, 0);
+        const float vmin = sortable_to_float(mm[t]), vmax = sortable_to_float(mm[nt + t]);
+        const float fl = std::floor(vmin);
+        if (!finite || !(vmax - fl < 1.0f) || ng <= 8) std::fill(need.begin(), need.end(), 1);
+        else {
             const float H = (float)d->h_texs[t].h[0];
             const long long ra = (long long)std::floor((vmin - fl) * H) - 1, rb = (long long)std::floor((vmax - fl) * H) + 1;
             const long long ga = ra / (long long)kTexGroupRows - 3 - (ra < 0), gb = rb / (long long)kTexGroupRows + 3;
-            for (long long g = ga; g <= gb; ++g) need[t][(size_t)(((g % ng) + ng) % ng)] = 1;  // REPEAT: wraps at both ends
+            if (gb - ga + 1 >= (long long)ng) std::fill(need.begin(), need.end(), 1);
+            else for (long long g = ga; g <= gb; ++g) need[(size_t)(((g % ng) + ng) % ng)] = 1;  // REPEAT: wraps at both ends
         }
-    }
-    if (!any) return M2S_OK;
-    for (uint32_t t = 0; t < d->ntex; ++t) {
-        if (need[t].empty()) continue;
-        const uint32_t ng = (uint32_t)need[t].size();
         for (uint32_t g = 0; g < ng;) {
-            if (!need[t][g] || d->present[t][g]) { ++g; continue; }
+            if (!need[g] || d->present[t][g]) { ++g; continue; }
             uint32_t e = g;
-            while (e < ng && need[t][e] && !d->present[t][e]) ++e;
+            while (e < ng && need[e] && !d->present[t][e]) ++e;
             m2s_status st = upload_texture_groups(ctx, d, t, g, e);
             if (st != M2S_OK) return st;
             g = e;
         }
     }
+    return M2S_OK;
+}
+
+// enqueue on the context stream: reduce the v-range of triangles [lo, hi) (already on the device) per texture, copy it
+// to the slot's pinned buffer, record the slot's event
+static m2s_status vrange_enqueue(m2s_ctx* ctx, m2s_dscene* d, uint64_t lo, uint64_t hi, int slot) {
+    const uint32_t nt = d->ntex;
+    if (!nt) return M2S_OK;
+    if (ctx->vr_ntex < nt) {  // (re)size every slot
+        for (auto& v : ctx->vr) {
+            if (v.d_minmax) { cudaFree(v.d_minmax); v.d_minmax = nullptr; }
+            if (v.h_minmax) { cudaFreeHost(v.h_minmax); v.h_minmax = nullptr; }
+        }
+        ctx->vr_ntex = 0;
+        for (auto& v : ctx->vr) {
+            CUDA_TRY(cudaMalloc(&v.d_minmax, (2 * (size_t)nt + 1) * sizeof(int)));
+            CUDA_TRY(cudaMallocHost(&v.h_minmax, (2 * (size_t)nt + 1) * sizeof(int)));
+            if (!v.ev) CUDA_TRY(cudaEventCreateWithFlags(&v.ev, cudaEventDisableTiming));
+        }
+        ctx->vr_ntex = nt;
+    }
+    VRangeSlot& v = ctx->vr[slot];
+    // min <- 0x7f7f7f7f (above every finite float's key), max <- 0x80808080 (below), flag <- 0
+    CUDA_TRY(cudaMemsetAsync(v.d_minmax, 0x7f, nt * sizeof(int), ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(v.d_minmax + nt, 0x80, nt * sizeof(int), ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(v.d_minmax + 2 * nt, 0, sizeof(int), ctx->stream));
+    if (hi > lo)
+        CUDA_TRY(vrange_launch(d->d_tris, (uint32_t)lo, (uint32_t)(hi - lo), d->d_ranges, d->nranges, d->d_prims, nt, v.d_minmax, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(v.h_minmax, v.d_minmax, (2 * (size_t)nt + 1) * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaEventRecord(v.ev, ctx->stream));
     return M2S_OK;
 }
 
@@ -668,7 +694,8 @@ M2S_EXPORT m2s_status m2s_scene_upload_range(m2s_ctx* ctx, const m2s_scene* sc, 
     m2s_dscene* ds = nullptr;
     m2s_status st = scene_upload_impl(ctx, &slim.scene, &ds, count, false, first, true);
     if (st != M2S_OK) return st;
-    st = ensure_textures_for_range(ctx, ds, &slim.scene, first, first + count);
+    st = vrange_enqueue(ctx, ds, first, first + count, 0);
+    if (st == M2S_OK) st = upload_groups_from_vrange(ctx, ds, 0);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (st == M2S_OK && e != cudaSuccess) { set_error(std::string("m2s_scene_upload_range: ") + cudaGetErrorString(e)); st = M2S_E_CUDA; }
     if (st != M2S_OK) { m2s_scene_free(ctx, ds); return st; }
@@ -697,114 +724,134 @@ M2S_EXPORT m2s_status m2s_convert_host(m2s_ctx* ctx, const m2s_scene* sc, const 
     }
     const uint64_t per = (count + nchunks - 1) / nchunks;
     m2s_dscene* ds = nullptr;
-    // triangles and texture rows travel with the chunk that needs them (ensure_textures_for_range): the first records
-    // exist after 1/nchunks of the upload, and a shard (first_triangle/triangle_count) never uploads rows it does not sample
-    const uint64_t first_n = nchunks > 1 ? std::min(per, count) : count;
-    m2s_status st = scene_upload_impl(ctx, &slim, &ds, first_n, false, first, true);
+    // Pipeline: (1) the triangle chunks go up back to back, each followed by a reduction of its v-range per texture and
+    // a 8-byte-per-texture copy back; (2) per chunk, as soon as its v-range is on the host: the texture row groups it
+    // samples (not yet resident) go up, the two kernels are enqueued; (3) a chunk's records start crossing PCIe on a
+    // second stream as soon as its count has arrived (zero-copy, from the raster kernel's last CTA) while later chunks
+    // are still being uploaded and converted.  The first records exist after ~1/nchunks of the upload; a shard
+    // (first_triangle/triangle_count) never uploads texture rows it does not sample.
+    m2s_status st = scene_upload_impl(ctx, &slim, &ds, 0, false, first, true);
     if (st != M2S_OK) return st;
-    st = ensure_textures_for_range(ctx, ds, &slim, first, first + first_n);
-    if (st != M2S_OK) { cudaStreamSynchronize(ctx->stream); m2s_scene_free(ctx, ds); return st; }
     st = grow(ctx, &ctx->d_out, &ctx->out_bytes, std::max<uint64_t>(out_capacity, 1) * stride);
     if (st == M2S_OK && h_keys) st = grow(ctx, (void**)&ctx->d_keys, &ctx->keys_bytes, std::max<uint64_t>(out_capacity, 1) * 8);
     if (st != M2S_OK) { cudaStreamSynchronize(ctx->stream); m2s_scene_free(ctx, ds); return st; }
     m2s_result r;
     std::memset(&r, 0, sizeof(r));
-    if (nchunks == 1) {
-        st = m2s_convert(ctx, ds, p, ctx->d_out, out_capacity, h_keys ? (uint64_t*)ctx->d_keys : nullptr, &r);
-        if (st == M2S_OK || st == M2S_E_CAPACITY) {
-            cudaError_t e = cudaSuccess;
-            if (r.written) e = cudaMemcpyAsync(h_out, ctx->d_out, r.written * stride, cudaMemcpyDeviceToHost, ctx->stream);
-            if (e == cudaSuccess && h_keys && r.written) e = cudaMemcpyAsync(h_keys, ctx->d_keys, r.written * 8, cudaMemcpyDeviceToHost, ctx->stream);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-            if (e != cudaSuccess) { set_error(std::string("convert_host download: ") + cudaGetErrorString(e)); st = M2S_E_CUDA; }
+    const uint64_t cap = effective_cap(ds, p, out_capacity);
+    auto fail_with = [&](m2s_status code) {
+        cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->stream2);
+        ctx->dirty = true;
+        m2s_scene_free(ctx, ds);
+        return code;
+    };
+    auto bail = [&](const char* what, cudaError_t e) {
+        set_error(std::string(what) + ": " + cudaGetErrorString(e));
+        return fail_with(M2S_E_CUDA);
+    };
+    static const bool host_trace = std::getenv("M2S_HOST_TRACE") != nullptr;  // debug: phase times on stderr
+    const auto t_start = std::chrono::steady_clock::now();
+    auto since = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_start).count(); };
+    cudaError_t e = cudaEventRecord(ctx->ev0, ctx->stream);
+    if (e != cudaSuccess) return bail("convert_host", e);
+    uint64_t lo_[m2s_ctx::kMaxChunks], hi_[m2s_ctx::kMaxChunks];
+    int planned = 0;
+    for (int c = 0; c < nchunks; ++c) {  // (1)
+        const uint64_t lo = first + (uint64_t)c * per, hi = std::min(first + count, lo + per);
+        if (lo >= hi && c > 0) break;
+        lo_[c] = lo; hi_[c] = hi;
+        if (hi > lo) {
+            e = cudaMemcpyAsync(reinterpret_cast<unsigned char*>(ds->d_tris) + lo * (size_t)kTriBytes,
+                                reinterpret_cast<const unsigned char*>(sc->triangles) + lo * (size_t)kTriBytes,
+                                (hi - lo) * (size_t)kTriBytes, cudaMemcpyHostToDevice, ctx->stream);
+            if (e != cudaSuccess) return bail("convert_host upload", e);
+            ds->h2d_bytes += (hi - lo) * (uint64_t)kTriBytes;
         }
-    } else {
-        const uint64_t cap = effective_cap(ds, p, out_capacity);
-        auto bail = [&](const char* what, cudaError_t e) {
-            cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->stream2);
-            ctx->dirty = true;
-            set_error(std::string(what) + ": " + cudaGetErrorString(e));
-            m2s_scene_free(ctx, ds);
-            return M2S_E_CUDA;
-        };
-        static const bool host_trace = std::getenv("M2S_HOST_TRACE") != nullptr;  // debug: phase times on stderr
-        const auto t_start = std::chrono::steady_clock::now();
-        auto since = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_start).count(); };
-        cudaError_t e = cudaEventRecord(ctx->ev0, ctx->stream);
-        if (e != cudaSuccess) return bail("convert_host", e);
-        int launched = 0;
-        unsigned long long tags[m2s_ctx::kMaxChunks] = {};
-        for (int c = 0; c < nchunks; ++c) {
-            const uint64_t lo = first + (uint64_t)c * per, hi = std::min(first + count, lo + per);
-            if (lo >= hi) break;
-            if (c > 0) {
-                e = cudaMemcpyAsync(reinterpret_cast<unsigned char*>(ds->d_tris) + lo * (size_t)kTriBytes,
-                                    reinterpret_cast<const unsigned char*>(sc->triangles) + lo * (size_t)kTriBytes,
-                                    (hi - lo) * (size_t)kTriBytes, cudaMemcpyHostToDevice, ctx->stream);
-                if (e != cudaSuccess) return bail("convert_host upload", e);
-                st = ensure_textures_for_range(ctx, ds, &slim, lo, hi);
-                if (st != M2S_OK) { cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->stream2); ctx->dirty = true; m2s_scene_free(ctx, ds); return st; }
-            }
-            m2s_params pc = *p;
-            pc.first_triangle = lo;
-            pc.triangle_count = hi - lo;
-            unsigned long long* h_dev = nullptr;  // device view of the mapped count slot
-            e = cudaHostGetDevicePointer((void**)&h_dev, ctx->h_chunk_tot + 2 * c, 0);
-            if (e != cudaSuccess) return bail("convert_host", e);
-            tags[c] = ++ctx->host_seq;
-            st = convert_enqueue_impl(ctx, ds, &pc, ctx->d_out, out_capacity, h_keys ? (uint64_t*)ctx->d_keys : nullptr,
-                                      (uint64_t*)(ctx->d_chunk_tot + c), ctx->stream, nullptr, ctx->d_chunk_tot, (uint32_t)c,
-                                      h_dev, tags[c]);
-            if (st != M2S_OK) { cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->stream2); m2s_scene_free(ctx, ds); return st; }
-            e = cudaEventRecord(ctx->ev_chunk[c], ctx->stream);
-            if (e != cudaSuccess) return bail("convert_host", e);
-            ++launched;
-        }
-        e = cudaEventRecord(ctx->ev1, ctx->stream);
-        if (e != cudaSuccess) return bail("convert_host", e);
-        uint64_t base = 0, written = 0;
-        if (host_trace) std::fprintf(stderr, "[m2s host] enqueued %d chunks at %.0f us\n", launched, since());
-        for (int c = 0; c < launched; ++c) {
-            // the count arrives (zero-copy) when the chunk's raster kernel ends; the download is enqueued behind
-            // the chunk's event while its fragment kernel still runs -> no host latency between kernel and copy
+        st = vrange_enqueue(ctx, ds, lo, hi, c);
+        if (st != M2S_OK) return fail_with(st);
+        ++planned;
+    }
+    if (host_trace) std::fprintf(stderr, "[m2s host] %d triangle chunks + v-range reductions enqueued at %.0f us\n", planned, since());
+    unsigned long long tags[m2s_ctx::kMaxChunks] = {};
+    uint64_t base = 0, written = 0;
+    int next_dl = 0;
+    // enqueue the downloads of the chunks whose counts have arrived (in order); block: wait for them
+    auto downloads = [&](int upto, bool block) -> cudaError_t {
+        while (next_dl < upto) {
+            const int c = next_dl;
             volatile unsigned long long* slot = ctx->h_chunk_tot + 2 * c;
             for (;;) {
-                if (slot[1] == tags[c]) break;
+                if (__atomic_load_n(&ctx->h_chunk_tot[2 * c + 1], __ATOMIC_ACQUIRE) == tags[c]) break;  // count is ordered before the tag
+                if (!block) return cudaSuccess;
                 const cudaError_t q = cudaEventQuery(ctx->ev_chunk[c]);
                 if (q == cudaSuccess) break;             // finished: the tag is there
-                if (q != cudaErrorNotReady) return bail("convert_host", q);
+                if (q != cudaErrorNotReady) return q;
             }
-            if (slot[1] != tags[c]) return bail("convert_host: count not published", cudaErrorUnknown);
+            if (__atomic_load_n(&ctx->h_chunk_tot[2 * c + 1], __ATOMIC_ACQUIRE) != tags[c]) return cudaErrorUnknown;
             const uint64_t tot = slot[0];
             if (host_trace) std::fprintf(stderr, "[m2s host] chunk %d rasterised at %.0f us (%llu records)\n", c, since(), (unsigned long long)tot);
             const uint64_t room = cap > base ? cap - base : 0, w = std::min(tot, room);
             if (w) {
-                e = cudaStreamWaitEvent(ctx->stream2, ctx->ev_chunk[c], 0);
-                if (e == cudaSuccess)
-                    e = cudaMemcpyAsync(reinterpret_cast<unsigned char*>(h_out) + base * stride,
-                                        reinterpret_cast<const unsigned char*>(ctx->d_out) + base * stride, w * stride,
-                                        cudaMemcpyDeviceToHost, ctx->stream2);
-                if (e == cudaSuccess && h_keys)
-                    e = cudaMemcpyAsync(h_keys + base, ctx->d_keys + base, w * 8, cudaMemcpyDeviceToHost, ctx->stream2);
-                if (e != cudaSuccess) return bail("convert_host download", e);
+                cudaError_t e2 = cudaStreamWaitEvent(ctx->stream2, ctx->ev_chunk[c], 0);
+                if (e2 == cudaSuccess)
+                    e2 = cudaMemcpyAsync(reinterpret_cast<unsigned char*>(h_out) + base * stride,
+                                         reinterpret_cast<const unsigned char*>(ctx->d_out) + base * stride, w * stride,
+                                         cudaMemcpyDeviceToHost, ctx->stream2);
+                if (e2 == cudaSuccess && h_keys)
+                    e2 = cudaMemcpyAsync(h_keys + base, ctx->d_keys + base, w * 8, cudaMemcpyDeviceToHost, ctx->stream2);
+                if (e2 != cudaSuccess) return e2;
             }
             base += tot;
             written += w;
+            ++next_dl;
         }
-        e = cudaStreamSynchronize(ctx->stream2);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        return cudaSuccess;
+    };
+    int launched = 0;
+    for (int c = 0; c < planned; ++c) {  // (2)
+        st = upload_groups_from_vrange(ctx, ds, c);
+        if (st != M2S_OK) return fail_with(st);
+        m2s_params pc = *p;
+        pc.first_triangle = lo_[c];
+        pc.triangle_count = hi_[c] - lo_[c];
+        unsigned long long* h_dev = nullptr;  // device view of the mapped count slot
+        e = cudaHostGetDevicePointer((void**)&h_dev, ctx->h_chunk_tot + 2 * c, 0);
+        if (e != cudaSuccess) return bail("convert_host", e);
+        tags[c] = ++ctx->host_seq;
+        if (hi_[c] > lo_[c]) {
+            st = convert_enqueue_impl(ctx, ds, &pc, ctx->d_out, out_capacity, h_keys ? (uint64_t*)ctx->d_keys : nullptr,
+                                      (uint64_t*)(ctx->d_chunk_tot + c), ctx->stream, nullptr, ctx->d_chunk_tot, (uint32_t)c,
+                                      h_dev, tags[c]);
+            if (st != M2S_OK) return fail_with(st);
+        } else {  // empty range: nothing to launch, the count is zero
+            e = cudaMemsetAsync(ctx->d_chunk_tot + c, 0, sizeof(unsigned long long), ctx->stream);
+            if (e != cudaSuccess) return bail("convert_host", e);
+            ctx->h_chunk_tot[2 * c] = 0;
+            __atomic_store_n(&ctx->h_chunk_tot[2 * c + 1], tags[c], __ATOMIC_RELEASE);
+        }
+        e = cudaEventRecord(ctx->ev_chunk[c], ctx->stream);
+        if (e != cudaSuccess) return bail("convert_host", e);
+        ++launched;
+        e = downloads(launched, false);  // (3) whatever is ready
         if (e != cudaSuccess) return bail("convert_host download", e);
-        if (host_trace) std::fprintf(stderr, "[m2s host] downloads done at %.0f us\n", since());
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-        r.total = base; r.cap = cap; r.written = written; r.device_ms = ms;
-        st = M2S_OK;
-        if (base > cap) {
-            char buf[160];
-            std::snprintf(buf, sizeof(buf), "m2s_convert: %llu gaussians generated, capacity %llu", (unsigned long long)base, (unsigned long long)cap);
-            set_error(buf);
-            st = M2S_E_CAPACITY;
-        }
+    }
+    e = cudaEventRecord(ctx->ev1, ctx->stream);
+    if (e != cudaSuccess) return bail("convert_host", e);
+    if (host_trace) std::fprintf(stderr, "[m2s host] enqueued %d chunks at %.0f us\n", launched, since());
+    e = downloads(launched, true);
+    if (e != cudaSuccess) return bail("convert_host download", e);
+    e = cudaStreamSynchronize(ctx->stream2);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return bail("convert_host download", e);
+    if (host_trace) std::fprintf(stderr, "[m2s host] downloads done at %.0f us\n", since());
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    r.total = base; r.cap = cap; r.written = written; r.device_ms = ms;
+    st = M2S_OK;
+    if (base > cap) {
+        char buf[160];
+        std::snprintf(buf, sizeof(buf), "m2s_convert: %llu gaussians generated, capacity %llu", (unsigned long long)base, (unsigned long long)cap);
+        set_error(buf);
+        st = M2S_E_CAPACITY;
     }
     if (res) *res = r;
     m2s_scene_free(ctx, ds);

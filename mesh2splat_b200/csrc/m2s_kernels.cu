@@ -1296,6 +1296,56 @@ __global__ void __launch_bounds__(256) mip_groups_kernel(uint32_t* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------
+// v-range of a triangle range per texture (host pipeline: which texture rows must be uploaded before these triangles
+// can be shaded).  minmax: [ntex] sortable-int minima | [ntex] maxima | 1 flag (non-finite or absurd v seen).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int float_key(float f) { const int i = __float_as_int(f); return i ^ ((i >> 31) & 0x7fffffff); }
+__global__ void __launch_bounds__(256) vrange_kernel(const float4* __restrict__ tris, uint32_t first, uint32_t count,
+                                                     const DRange* __restrict__ ranges, uint32_t nranges, const DPrim* __restrict__ prims,
+                                                     uint32_t ntex, int* __restrict__ minmax) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int prim = -1;
+    float vmin = 3.0e38f, vmax = -3.0e38f;
+    bool bad = false;
+    if (i < count) {
+        const uint32_t t = first + i;
+        int lo = 0, hi = (int)nranges - 1;
+        while (lo <= hi) {
+            const int mid = (lo + hi) >> 1;
+            const DRange r = ranges[mid];
+            if (t < r.first) hi = mid - 1;
+            else if (t >= r.end) lo = mid + 1;
+            else { prim = (int)r.prim; break; }
+        }
+        if (prim >= 0) {
+            const float v0 = __ldg(&tris[(size_t)t * 9 + 2]).w, v1 = __ldg(&tris[(size_t)t * 9 + 5]).w, v2 = __ldg(&tris[(size_t)t * 9 + 8]).w;
+            vmin = fminf(v0, fminf(v1, v2)); vmax = fmaxf(v0, fmaxf(v1, v2));
+            bad = !(fabsf(v0) <= 1e30f) || !(fabsf(v1) <= 1e30f) || !(fabsf(v2) <= 1e30f);
+        }
+    }
+    const unsigned full = 0xffffffffu;
+    if (__any_sync(full, bad) && lane == 0) atomicOr(minmax + 2 * ntex, 1);
+    const int p0 = __shfl_sync(full, prim, 0);
+    if (__all_sync(full, prim == p0)) {  // the usual case: the whole warp is inside one primitive
+        if (p0 < 0) return;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            vmin = fminf(vmin, __shfl_xor_sync(full, vmin, d));
+            vmax = fmaxf(vmax, __shfl_xor_sync(full, vmax, d));
+        }
+        if (lane != 0) return;
+    } else if (prim < 0) return;
+    for (int m = 0; m < 3; ++m) {
+        const int ti = prims[prim].tex[m];
+        if (ti >= 0 && (uint32_t)ti < ntex) {
+            atomicMin(minmax + ti, float_key(vmin));
+            atomicMax(minmax + ntex + ti, float_key(vmax));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // .ply body rows from REF96 records (parsers.cpp:232-316,339-428,431-514)
 // ------------------------------------------------------------------------------------------
 __global__ void ply_rows_kernel(const float4* __restrict__ rec, unsigned long long count,
@@ -1443,6 +1493,13 @@ cudaError_t mip_groups_launch(uint32_t* arena, const DTexture& t, uint32_t g0, u
     if (t.nlevels <= 1 || g1 <= g0) return cudaSuccess;
     dim3 grd((t.w[0] + 63) / 64, g1 - g0);
     mip_groups_kernel<<<grd, 256, 0, stream>>>(arena, t, g0);
+    return cudaGetLastError();
+}
+
+cudaError_t vrange_launch(const float4* tris, uint32_t first, uint32_t count, const DRange* ranges, uint32_t nranges, const DPrim* prims,
+                          uint32_t ntex, int* minmax, cudaStream_t stream) {
+    if (!count || !ntex) return cudaSuccess;
+    vrange_kernel<<<(count + 255) / 256, 256, 0, stream>>>(tris, first, count, ranges, nranges, prims, ntex, minmax);
     return cudaGetLastError();
 }
 
