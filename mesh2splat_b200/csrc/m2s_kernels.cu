@@ -54,6 +54,9 @@
 #ifndef M2S_FRAG_WARPS
 #define M2S_FRAG_WARPS 4
 #endif
+#ifndef M2S_FRAG_BUFS
+#define M2S_FRAG_BUFS 2   // staged-unit buffers of the fragment kernel: 2 = the next item's data flies in while this one is shaded
+#endif
 
 namespace m2s {
 
@@ -608,6 +611,11 @@ __global__ void __launch_bounds__(M2S_RASTER_WARPS * 32, 1) raster_kernel(const 
     WarpBlock<RK>& wb = *reinterpret_cast<WarpBlock<RK>*>(smem + (size_t)warp * sizeof(WarpBlock<RK>));
     const unsigned char* tri_bytes = reinterpret_cast<const unsigned char*>(a.tris);
 
+#ifdef M2S_EARLY_TRIGGER
+    // PDL early trigger: one fragment-kernel CTA per SM becomes resident beside this CTA (37 KB of shared memory are
+    // left) and parks in griddepcontrol.wait; it starts the moment this grid has drained instead of being launched then
+    asm volatile("griddepcontrol.launch_dependents;");
+#endif
     if (lane == 0) {
         mbar_init(&wb.bar, 1);
         fence_barrier_init();
@@ -874,9 +882,10 @@ constexpr uint32_t kMaxGroups = 128;               // 32-fragment groups of one 
 template <int LAYOUT>
 struct FragSmem {
     using Rec = TriRec<RCfg<Cfg<LAYOUT>::kRK>::kMaps>;
+    static constexpr size_t kBufBytes = kUnitTris * (sizeof(Rec) + kTriBytes);   // one staged unit: records, then vertices
     static constexpr size_t kRecOff = 0;
-    static constexpr size_t kTriOff = kRecOff + kUnitTris * sizeof(Rec);
-    static constexpr size_t kSpanOff = kTriOff + kUnitTris * kTriBytes;
+    static constexpr size_t kTriOff = kUnitTris * sizeof(Rec);                    // inside a buffer
+    static constexpr size_t kSpanOff = M2S_FRAG_BUFS * kBufBytes;
     static constexpr size_t kGroupOff = kSpanOff + kSpanRows * 8;
     static constexpr size_t kStageAligned = (kGroupOff + (kMaxGroups + 1) * 2 + 15) & ~(size_t)15;
     static constexpr size_t kBytes = kStageAligned + (size_t)kFragWarps * 32 * Cfg<LAYOUT>::kStride;
@@ -1037,16 +1046,15 @@ __global__ void __launch_bounds__(kFragThreads) fragment_kernel(const __grid_con
     using Rec = typename S::Rec;
     constexpr int kStride = Cfg<LAYOUT>::kStride;
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar[M2S_FRAG_BUFS];
     __shared__ unsigned long long s_goff;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const Rec* recs = reinterpret_cast<const Rec*>(smem + S::kRecOff);
-    const float4* tris = reinterpret_cast<const float4*>(smem + S::kTriOff);
     uint2* span = reinterpret_cast<uint2*>(smem + S::kSpanOff);
     unsigned short* gstart = reinterpret_cast<unsigned short*>(smem + S::kGroupOff);  // span row holding fragment 32 g of the item
     unsigned char* stage = smem + S::kStageAligned + (size_t)warp * 32 * kStride;  // this warp's 32 records
     if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
+#pragma unroll
+        for (int b = 0; b < M2S_FRAG_BUFS; ++b) mbar_init(&bar[b], 1);
         fence_barrier_init();
     }
     __syncthreads();
@@ -1076,34 +1084,63 @@ __global__ void __launch_bounds__(kFragThreads) fragment_kernel(const __grid_con
     const uint32_t nitems = min(*reinterpret_cast<const volatile uint32_t*>(a.n_items_out), a.queue_cap);
     const uint32_t* __restrict__ texb = a.tex_base;
     const bool want_keys = a.keys != nullptr;
-    uint32_t phase = 0;
+    // ---- the item pipeline: header + block list of item i+1 are loaded while item i is processed, and (2 buffers) its
+    // records and vertices are already in flight (TMA) into the other staged-unit buffer ----
+    struct Hdr { uint4 h0; uint2 h1; uint2 blk; };
+    auto load_hdr = [&](uint32_t it) {
+        Hdr h;
+        h.h0 = make_uint4(0, 0, 0, 0); h.h1 = make_uint2(0, 0); h.blk = make_uint2(0xffffffffu, 0);
+        if (it < nitems) {
+            const FragItem* q = a.items + it;
+            h.h0 = __ldg(reinterpret_cast<const uint4*>(q));
+            h.h1 = __ldg(reinterpret_cast<const uint2*>(q) + 2);
+            if (!(h.h0.w & 0x80000000u) && (uint32_t)lane < (h.h0.w & 0xffu)) h.blk = __ldg(reinterpret_cast<const uint2*>(q->blocks + lane));
+        }
+        return h;
+    };
+    auto live = [&](const Hdr& h) {  // uniform over the CTA: does the item emit anything?
+        const unsigned long long first = (unsigned long long)h.h0.x | ((unsigned long long)h.h0.y << 32);
+        return h.h1.y > h.h1.x && first + h.h1.x < room;
+    };
+    auto issue = [&](const Hdr& h, uint32_t buf) {  // thread 0: stage the unit's records and vertices: two TMA bulk copies, one mbarrier
+        const uint32_t t0 = h.h0.z * a.unit_tris;
+        const uint32_t ntri = min(a.unit_tris, a.tri_count - t0);
+        const uint32_t rb = ntri * (uint32_t)sizeof(Rec), tb = ntri * (uint32_t)kTriBytes;
+        unsigned char* dst = smem + (size_t)buf * S::kBufBytes;
+        fence_proxy_async();
+        mbar_arrive_expect_tx(&bar[buf], rb + tb);
+        tma_load_1d(dst + S::kRecOff, a.tri_frag + (size_t)t0 * sizeof(Rec), rb, &bar[buf]);
+        tma_load_1d(dst + S::kTriOff, reinterpret_cast<const unsigned char*>(a.tris) + ((size_t)a.tri_first + t0) * kTriBytes, tb, &bar[buf]);
+    };
+    uint32_t phases = 0;  // bit b: parity of the next completion of bar[b]
+    uint32_t buf = 0;
+    Hdr cur = load_hdr(blockIdx.x);
+    bool cur_live = live(cur), cur_issued = false;
+    if (M2S_FRAG_BUFS > 1 && cur_live) { if (threadIdx.x == 0) issue(cur, 0); cur_issued = true; }
+    Hdr nxt = load_hdr(blockIdx.x + gridDim.x);
 
     for (uint32_t it = blockIdx.x; it < nitems; it += gridDim.x) {
-        // ---- the item: a unit's small triangles (implicit: one block per triangle) or queued row blocks ----
-        const FragItem* q = a.items + it;
-        const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(q));
-        const uint2 h1 = __ldg(reinterpret_cast<const uint2*>(q) + 2);
-        const unsigned long long first = (unsigned long long)h0.x | ((unsigned long long)h0.y << 32);
-        const uint32_t unit = h0.z, fb = h1.x, fe = h1.y;
-        const bool unit_item = (h0.w & 0x80000000u) != 0;
-        const uint32_t nblocks = h0.w & 0xffu;
-        uint32_t bprefix = 0xffffffffu, bref = 0;  // lane b: block b of the item
-        if (!unit_item && (uint32_t)lane < nblocks) {
-            const uint2 b = __ldg(reinterpret_cast<const uint2*>(q->blocks + lane));
-            bprefix = b.x; bref = b.y;
+        const bool nxt_live = live(nxt);
+        uint32_t nbuf = buf;
+        if (M2S_FRAG_BUFS > 1 && nxt_live) {  // the other buffer is free: its last reader passed the barrier at the end of the previous item
+            nbuf = cur_issued ? buf ^ 1u : buf;
+            if (threadIdx.x == 0) issue(nxt, nbuf);
         }
-        if (fe <= fb || first + fb >= room) continue;  // uniform over the CTA: nothing to emit
+        const Hdr nn = load_hdr(it + 2 * gridDim.x);
+        if (!cur_live) { cur = nxt; cur_live = nxt_live; cur_issued = M2S_FRAG_BUFS > 1 && nxt_live; buf = nbuf; nxt = nn; continue; }
+        // ---- the item: a unit's small triangles (implicit: one block per triangle) or queued row blocks ----
+        const unsigned long long first = (unsigned long long)cur.h0.x | ((unsigned long long)cur.h0.y << 32);
+        const uint32_t unit = cur.h0.z, fb = cur.h1.x, fe = cur.h1.y;
+        const bool unit_item = (cur.h0.w & 0x80000000u) != 0;
+        const uint32_t nblocks = cur.h0.w & 0xffu;
+        const uint32_t bprefix = cur.blk.x, bref = cur.blk.y;  // lane b: block b of the item
         const uint32_t t0 = unit * a.unit_tris;
         const uint32_t ntri = min(a.unit_tris, a.tri_count - t0);
-        if (threadIdx.x == 0) {  // stage the unit's records and vertices: two TMA bulk copies, one mbarrier
-            const uint32_t rb = ntri * (uint32_t)sizeof(Rec), tb = ntri * (uint32_t)kTriBytes;
-            fence_proxy_async();
-            mbar_arrive_expect_tx(&bar, rb + tb);
-            tma_load_1d(smem + S::kRecOff, a.tri_frag + (size_t)t0 * sizeof(Rec), rb, &bar);
-            tma_load_1d(smem + S::kTriOff, reinterpret_cast<const unsigned char*>(a.tris) + ((size_t)a.tri_first + t0) * kTriBytes, tb, &bar);
-        }
-        mbar_wait(&bar, phase);
-        phase ^= 1;
+        if (M2S_FRAG_BUFS == 1 && threadIdx.x == 0) issue(cur, 0);
+        const Rec* recs = reinterpret_cast<const Rec*>(smem + (size_t)buf * S::kBufBytes + S::kRecOff);
+        const float4* tris = reinterpret_cast<const float4*>(smem + (size_t)buf * S::kBufBytes + S::kTriOff);
+        mbar_wait(&bar[buf], (phases >> buf) & 1u);
+        phases ^= 1u << buf;
         // ---- the item's span table: one entry per pixel row, fragments-before-the-row ascending ----
         uint32_t nrows_flat;
         if (unit_item) {
@@ -1218,7 +1255,8 @@ __global__ void __launch_bounds__(kFragThreads) fragment_kernel(const __grid_con
             }
             __syncwarp();
         }
-        __syncthreads();  // the next item's TMA overwrites the staged unit and the span table
+        __syncthreads();  // the span table and this staged-unit buffer may be overwritten from here on
+        cur = nxt; cur_live = nxt_live; cur_issued = M2S_FRAG_BUFS > 1 && nxt_live; buf = nbuf; nxt = nn;
     }
     if (a.world > 1) {  // last CTA out tells every peer that this rank's records have landed
         __threadfence_system();
