@@ -147,6 +147,9 @@ void m2s_params_default(m2s_params* p);
 m2s_status m2s_ctx_create(int device, m2s_ctx** out);
 void m2s_ctx_destroy(m2s_ctx* ctx);
 int m2s_ctx_device(const m2s_ctx* ctx);
+/* Conditions raised on the device that an enqueue-only call cannot return (a fused-gather wait that timed out after
+ * 2 s because a peer never published): M2S_OK or M2S_E_CUDA; clears the condition.  Call after synchronising. */
+m2s_status m2s_ctx_status(m2s_ctx* ctx);
 int m2s_ctx_sm_count(const m2s_ctx* ctx);
 
 /* ---- inputs: replaces setupMeshBuffers + generateTextures ---------------------------------- */

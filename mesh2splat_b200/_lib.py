@@ -14,7 +14,7 @@ _lib = None
 # every symbol include/m2s.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "m2s_version", "m2s_last_error", "m2s_status_string", "m2s_record_stride", "m2s_reference_capacity",
-    "m2s_params_default", "m2s_ctx_create", "m2s_ctx_destroy", "m2s_ctx_device", "m2s_ctx_sm_count",
+    "m2s_params_default", "m2s_ctx_create", "m2s_ctx_destroy", "m2s_ctx_device", "m2s_ctx_sm_count", "m2s_ctx_status",
     "m2s_compute_bboxes", "m2s_scene_upload", "m2s_scene_upload_range", "m2s_scene_h2d_bytes", "m2s_scene_free", "m2s_scene_read_mip",
     "m2s_convert_enqueue", "m2s_convert", "m2s_convert_timed", "m2s_convert_host", "m2s_convert_gather_enqueue",
     "m2s_ply_header", "m2s_ply_encode", "m2s_ply_write", "m2s_convert_file",
@@ -58,6 +58,8 @@ def lib() -> C.CDLL:
     L.m2s_ctx_destroy.argtypes = [vp]
     L.m2s_ctx_device.restype = i32
     L.m2s_ctx_device.argtypes = [vp]
+    L.m2s_ctx_status.restype = i32
+    L.m2s_ctx_status.argtypes = [vp]
     L.m2s_ctx_sm_count.restype = i32
     L.m2s_ctx_sm_count.argtypes = [vp]
     L.m2s_compute_bboxes.restype = i32

@@ -19,7 +19,7 @@ size_t tri_frag_bytes(int layout);
 cudaError_t convert_configure(int layout, int* raster_blocks_per_sm, int* fragment_blocks_per_sm);
 cudaError_t convert_launch(int layout, const ConvertArgs& args, int raster_grid, int fragment_grid, cudaStream_t stream, cudaEvent_t mid);
 cudaError_t gather_wait_launch(const unsigned long long* xch, uint32_t world, unsigned long long epoch, unsigned long long gcap,
-                               unsigned long long* total_global, cudaStream_t stream);
+                               unsigned long long* total_global, uint32_t* status, cudaStream_t stream);
 cudaError_t mip_groups_launch(uint32_t* arena, const DTexture& t, uint32_t g0, uint32_t g1, cudaStream_t stream);
 cudaError_t vrange_launch(const float4* tris, uint32_t first, uint32_t count, const DRange* ranges, uint32_t nranges, const DPrim* prims,
                           uint32_t ntex, int* minmax, cudaStream_t stream);
@@ -56,6 +56,8 @@ struct m2s_ctx {
     unsigned long long* d_total = nullptr;   // published count
     uint32_t* d_nitems = nullptr;            // work items queued by the last raster launch
     unsigned long long* h_total = nullptr;   // pinned
+    uint32_t* h_status = nullptr;            // pinned + mapped: raised by device-side waits that timed out (fused gather)
+    uint32_t* d_status = nullptr;            // its device view
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;
     // convert_host pipeline: a second stream for the downloads, per-chunk counts and events
     static constexpr int kMaxChunks = 8;
@@ -185,6 +187,9 @@ M2S_EXPORT m2s_status m2s_ctx_create(int device, m2s_ctx** out) {
     CUDA_TRY(cudaMalloc(&c->d_total, sizeof(unsigned long long)));
     CUDA_TRY(cudaMalloc(&c->d_nitems, sizeof(uint32_t)));
     CUDA_TRY(cudaMallocHost(&c->h_total, sizeof(unsigned long long)));
+    CUDA_TRY(cudaHostAlloc(&c->h_status, sizeof(uint32_t), cudaHostAllocMapped));
+    *c->h_status = 0;
+    CUDA_TRY(cudaHostGetDevicePointer((void**)&c->d_status, c->h_status, 0));
     CUDA_TRY(cudaEventCreate(&c->ev0));
     CUDA_TRY(cudaEventCreate(&c->ev1));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
@@ -211,6 +216,7 @@ M2S_EXPORT void m2s_ctx_destroy(m2s_ctx* c) {
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_sched); cudaFree(c->d_counter); cudaFree(c->d_total); cudaFree(c->d_nitems);
     cudaFreeHost(c->h_total);
+    if (c->h_status) cudaFreeHost(c->h_status);
     cudaFree(c->d_chunk_tot); cudaFreeHost(c->h_chunk_tot);
     for (int i = 0; i < 2; ++i) if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
     for (auto& v : c->vr) { if (v.d_minmax) cudaFree(v.d_minmax); if (v.h_minmax) cudaFreeHost(v.h_minmax); if (v.ev) cudaEventDestroy(v.ev); }
@@ -222,6 +228,16 @@ M2S_EXPORT void m2s_ctx_destroy(m2s_ctx* c) {
 }
 
 M2S_EXPORT int m2s_ctx_device(const m2s_ctx* c) { return c ? c->device : -1; }
+// Device-side conditions the enqueue-only entry points cannot return: call after synchronising the stream.
+M2S_EXPORT m2s_status m2s_ctx_status(m2s_ctx* c) {
+    if (!c) { set_error("m2s_ctx_status: ctx is NULL"); return M2S_E_INVALID; }
+    const uint32_t v = __atomic_exchange_n(c->h_status, 0u, __ATOMIC_ACQ_REL);
+    if (v == 0) return M2S_OK;
+    c->dirty = true;
+    set_error(std::string("fused gather: a peer rank did not publish its ") + ((v & 1u) ? "count" : "completion flag") +
+              " within 2 s (did every rank call m2s_convert_gather_enqueue the same number of times?)");
+    return M2S_E_CUDA;
+}
 M2S_EXPORT int m2s_ctx_sm_count(const m2s_ctx* c) { return c ? c->sm_count : 0; }
 
 // ---- inputs ---------------------------------------------------------------------------------
@@ -589,13 +605,14 @@ static m2s_status convert_enqueue_impl(m2s_ctx* ctx, const m2s_dscene* s, const 
         for (uint32_t r = 0; r < peers->world; ++r) { a.peer_out[r] = (uint8_t*)peers->out[r]; a.peer_xch[r] = (unsigned long long*)peers->xch[r]; }
         a.epoch = ++ctx->epoch;
         a.gcap = out_capacity;
+        a.status = ctx->d_status;
     }
     const int fgrid = ctx->sm_count * ctx->frag_blocks_per_sm[klayout];
     cudaError_t e = convert_launch(klayout, a, grid, fgrid, stream, mid);
     if (e != cudaSuccess) { ctx->dirty = true; set_error(std::string("convert launch: ") + cudaGetErrorString(e)); return M2S_E_CUDA; }
     if (peers && peers->world > 1)
         CUDA_TRY(gather_wait_launch((const unsigned long long*)peers->xch[peers->rank], peers->world, a.epoch, out_capacity,
-                                    (unsigned long long*)d_total, stream));
+                                    (unsigned long long*)d_total, ctx->d_status, stream));
     return M2S_OK;
 }
 
@@ -719,7 +736,7 @@ M2S_EXPORT m2s_status m2s_convert_host(m2s_ctx* ctx, const m2s_scene* sc, const 
     if (count == 0 || first + count > sc->triangle_count) count = sc->triangle_count - first;
     int nchunks = 1;
     if (count >= 16384) {  // every layout: the fragment kernel appends after the earlier chunks' records itself
-        nchunks = 8;
+        nchunks = 6;
         if (const char* e = std::getenv("M2S_HOST_CHUNKS")) nchunks = std::max(1, std::min(m2s_ctx::kMaxChunks, std::atoi(e)));
     }
     const uint64_t per = (count + nchunks - 1) / nchunks;
@@ -754,23 +771,31 @@ M2S_EXPORT m2s_status m2s_convert_host(m2s_ctx* ctx, const m2s_scene* sc, const 
     cudaError_t e = cudaEventRecord(ctx->ev0, ctx->stream);
     if (e != cudaSuccess) return bail("convert_host", e);
     uint64_t lo_[m2s_ctx::kMaxChunks], hi_[m2s_ctx::kMaxChunks];
-    int planned = 0;
-    for (int c = 0; c < nchunks; ++c) {  // (1)
+    int planned = 0, uploaded = 0;
+    for (int c = 0; c < nchunks; ++c) {
         const uint64_t lo = first + (uint64_t)c * per, hi = std::min(first + count, lo + per);
         if (lo >= hi && c > 0) break;
         lo_[c] = lo; hi_[c] = hi;
-        if (hi > lo) {
-            e = cudaMemcpyAsync(reinterpret_cast<unsigned char*>(ds->d_tris) + lo * (size_t)kTriBytes,
-                                reinterpret_cast<const unsigned char*>(sc->triangles) + lo * (size_t)kTriBytes,
-                                (hi - lo) * (size_t)kTriBytes, cudaMemcpyHostToDevice, ctx->stream);
-            if (e != cudaSuccess) return bail("convert_host upload", e);
-            ds->h2d_bytes += (hi - lo) * (uint64_t)kTriBytes;
-        }
-        st = vrange_enqueue(ctx, ds, lo, hi, c);
-        if (st != M2S_OK) return fail_with(st);
         ++planned;
     }
-    if (host_trace) std::fprintf(stderr, "[m2s host] %d triangle chunks + v-range reductions enqueued at %.0f us\n", planned, since());
+    // (1) triangle chunk c goes up, followed by the reduction of its v-range per texture and the copy back of the result
+    auto upload_tris = [&](int c) -> m2s_status {
+        if (hi_[c] > lo_[c]) {
+            cudaError_t e1 = cudaMemcpyAsync(reinterpret_cast<unsigned char*>(ds->d_tris) + lo_[c] * (size_t)kTriBytes,
+                                             reinterpret_cast<const unsigned char*>(sc->triangles) + lo_[c] * (size_t)kTriBytes,
+                                             (hi_[c] - lo_[c]) * (size_t)kTriBytes, cudaMemcpyHostToDevice, ctx->stream);
+            if (e1 != cudaSuccess) { set_error(std::string("convert_host upload: ") + cudaGetErrorString(e1)); return M2S_E_CUDA; }
+            ds->h2d_bytes += (hi_[c] - lo_[c]) * (uint64_t)kTriBytes;
+        }
+        return vrange_enqueue(ctx, ds, lo_[c], hi_[c], c);
+    };
+    // one chunk of look-ahead keeps the copy engine busy while the host waits for a v-range: the stream sees
+    // tris0 tris1 | rows0 kernels0 | tris2 | rows1 kernels1 | ... and the first records exist after ~2/nchunks of the
+    // triangles and 1/nchunks of the texture rows
+    for (; uploaded < std::min(planned, 2); ++uploaded) {
+        st = upload_tris(uploaded);
+        if (st != M2S_OK) return fail_with(st);
+    }
     unsigned long long tags[m2s_ctx::kMaxChunks] = {};
     uint64_t base = 0, written = 0;
     int next_dl = 0;
@@ -810,6 +835,10 @@ M2S_EXPORT m2s_status m2s_convert_host(m2s_ctx* ctx, const m2s_scene* sc, const 
     for (int c = 0; c < planned; ++c) {  // (2)
         st = upload_groups_from_vrange(ctx, ds, c);
         if (st != M2S_OK) return fail_with(st);
+        if (uploaded < planned) {  // next look-ahead chunk: behind this chunk's rows in the copy queue, ahead of its kernels' results
+            st = upload_tris(uploaded++);
+            if (st != M2S_OK) return fail_with(st);
+        }
         m2s_params pc = *p;
         pc.first_triangle = lo_[c];
         pc.triangle_count = hi_[c] - lo_[c];

@@ -114,6 +114,7 @@ struct ConvertArgs {
     unsigned long long* peer_xch[kMaxPeers];
     unsigned long long epoch;
     unsigned long long gcap;           // capacity of the final buffers (records)
+    uint32_t* status;                  // context status word (mapped pinned host memory): bit 0/1 = a gather wait timed out
 };
 
 }  // namespace m2s

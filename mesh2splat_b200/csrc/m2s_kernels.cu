@@ -55,7 +55,9 @@
 #define M2S_FRAG_WARPS 4
 #endif
 #ifndef M2S_FRAG_BUFS
-#define M2S_FRAG_BUFS 2   // staged-unit buffers of the fragment kernel: 2 = the next item's data flies in while this one is shaded
+#define M2S_FRAG_BUFS 1   // staged-unit buffers of the fragment kernel.  2 = the next item's records and vertices fly in (TMA) while this
+                          // one is shaded: measured NO gain (helmet 44.9 vs 44.3 us, R = 2048 251 vs 244 us, profiles/r02_ab_variants.txt) —
+                          // the second buffer costs a resident CTA per SM and the other CTAs already hide the load; kept as an option
 #endif
 
 namespace m2s {
@@ -123,6 +125,25 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     unsigned long long v;
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ unsigned long long gtimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+// Bounded wait for a peer's flag (fused gather): a rank that never launches its kernels must not hang every GPU of the
+// node forever.  After kSpinTimeoutNs the waiter gives up, raises bit `why` in the context's status word (mapped pinned
+// host memory, read by m2s_ctx_status) and carries on with whatever it has — the host call then reports M2S_E_CUDA.
+constexpr unsigned long long kSpinTimeoutNs = 2000000000ull;
+__device__ __forceinline__ bool wait_epoch(const unsigned long long* flag, unsigned long long epoch, uint32_t* status, uint32_t why) {
+    if (ld_acquire_sys(flag) == epoch) return true;
+    const unsigned long long t0 = gtimer_ns();
+    unsigned ns = 100;
+    while (ld_acquire_sys(flag) != epoch) {
+        __nanosleep(ns);
+        ns = min(ns * 2u, 2000u);
+        if (gtimer_ns() - t0 > kSpinTimeoutNs) {
+            if (status) { *reinterpret_cast<volatile uint32_t*>(status) = why; __threadfence_system(); }  // plain store: zero-copy memory
+            return false;
+        }
+    }
+    return true;
 }
 constexpr int kSchedStride = 32;  // scheduler words live on separate 128-byte lines
 #define SCHED(a, i) ((a).sched + (i) * kSchedStride)
@@ -1073,7 +1094,7 @@ __global__ void __launch_bounds__(kFragThreads) fragment_kernel(const __grid_con
             const unsigned long long* x = a.peer_xch[a.rank];
             unsigned long long off = 0;
             for (uint32_t r = 0; r < a.world; ++r) {
-                while (ld_acquire_sys(x + r * 4 + 1) != a.epoch) __nanosleep(100);
+                wait_epoch(x + r * 4 + 1, a.epoch, a.status, 1u);  // bounded: see wait_epoch
                 if (r < a.rank) off += *reinterpret_cast<const volatile unsigned long long*>(x + r * 4);
             }
             s_goff = off;
@@ -1278,10 +1299,10 @@ __global__ void __launch_bounds__(kFragThreads) fragment_kernel(const __grid_con
 // waits until every rank's records of this epoch have landed in THIS rank's final buffer, publishes the
 // total; one thread — the data path never returns to the host
 __global__ void gather_wait_kernel(const unsigned long long* xch, uint32_t world, unsigned long long epoch,
-                                   unsigned long long gcap, unsigned long long* total_global) {
+                                   unsigned long long gcap, unsigned long long* total_global, uint32_t* status) {
     unsigned long long tot = 0;
     for (uint32_t r = 0; r < world; ++r) {
-        while (ld_acquire_sys(xch + r * 4 + 2) != epoch) __nanosleep(200);
+        wait_epoch(xch + r * 4 + 2, epoch, status, 2u);
         tot += *reinterpret_cast<const volatile unsigned long long*>(xch + r * 4);
     }
     if (total_global) *total_global = tot;
@@ -1521,8 +1542,8 @@ cudaError_t convert_launch(int layout, const ConvertArgs& args, int raster_grid,
 }
 
 cudaError_t gather_wait_launch(const unsigned long long* xch, uint32_t world, unsigned long long epoch, unsigned long long gcap,
-                               unsigned long long* total_global, cudaStream_t stream) {
-    gather_wait_kernel<<<1, 1, 0, stream>>>(xch, world, epoch, gcap, total_global);
+                               unsigned long long* total_global, uint32_t* status, cudaStream_t stream) {
+    gather_wait_kernel<<<1, 1, 0, stream>>>(xch, world, epoch, gcap, total_global, status);
     return cudaGetLastError();
 }
 

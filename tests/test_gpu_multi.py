@@ -51,6 +51,9 @@ def _worker(rank: int, world: int, port: int, q):
             for _ in range(3):  # repeated calls: epochs must pair up
                 pg.convert_enqueue(ds, p)
             got, n = pg.records(layout)
+            from mesh2splat_b200._lib import lib
+            if lib().m2s_ctx_status(ctx.handle) != 0:
+                ok, msg = False, "m2s_ctx_status: a gather wait timed out"
             whole = ctx.convert(ds, R, layout, flags=_abi.FLAG_UNCAPPED, capacity=cap)
             want = whole.numpy()
             a = np.sort(np.frombuffer(got.tobytes(), np.dtype((np.void, stride))))
@@ -67,19 +70,32 @@ def _worker(rank: int, world: int, port: int, q):
         dist.destroy_process_group()
 
 
-def test_fused_gather_two_gpus():
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+def _run_world(world: int):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=240) for _ in procs]
+    res = [q.get(timeout=300) for _ in procs]
     for p in procs:
         p.join(timeout=60)
     for rank, ok, msg in res:
         assert ok, f"rank {rank}: {msg}"
+
+
+def test_fused_gather_two_gpus():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run_world(2)
+
+
+def test_fused_gather_all_gpus():
+    """The same check on every GPU of the box (4 or 8 ranks): the gathered buffer is the single-GPU multiset on every rank."""
+    import torch
+    n = min(torch.cuda.device_count(), 8)
+    if n < 4:
+        pytest.skip("needs >= 4 GPUs")
+    _run_world(n)
