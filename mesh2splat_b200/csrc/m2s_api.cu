@@ -301,10 +301,18 @@ static m2s_status upload_texture_groups(m2s_ctx* ctx, m2s_dscene* d, uint32_t t,
 static float sortable_to_float(int i) { i ^= (i >> 31) & 0x7fffffff; float f; std::memcpy(&f, &i, 4); return f; }
 
 static m2s_status vrange_enqueue(m2s_ctx* ctx, m2s_dscene* d, uint64_t lo, uint64_t hi, int slot);
-static m2s_status upload_groups_from_vrange(m2s_ctx* ctx, m2s_dscene* d, int slot) {
+// `idle` (optional) is called while the host waits for the reduction: the host pipeline enqueues ready downloads there
+template <class Idle>
+static m2s_status upload_groups_from_vrange(m2s_ctx* ctx, m2s_dscene* d, int slot, Idle idle) {
     const uint32_t nt = d->ntex;
     if (!nt) return M2S_OK;
-    CUDA_TRY(cudaEventSynchronize(ctx->vr[slot].ev));
+    for (;;) {
+        const cudaError_t q = cudaEventQuery(ctx->vr[slot].ev);
+        if (q == cudaSuccess) break;
+        if (q != cudaErrorNotReady) { set_error(std::string("v-range reduction: ") + cudaGetErrorString(q)); return M2S_E_CUDA; }
+        const cudaError_t ie = idle();
+        if (ie != cudaSuccess) { set_error(std::string("convert_host download: ") + cudaGetErrorString(ie)); return M2S_E_CUDA; }
+    }
     const int* mm = ctx->vr[slot].h_minmax;
     const bool finite = mm[2 * nt] == 0;
     for (uint32_t t = 0; t < nt; ++t) {
@@ -313,7 +321,7 @@ static m2s_status upload_groups_from_vrange(m2s_ctx* ctx, m2s_dscene* d, int slo
         std::vector<uint8_t> need(ng, 0);
         const float vmin = sortable_to_float(mm[t]), vmax = sortable_to_float(mm[nt + t]);
         const float fl = std::floor(vmin);
-        if (!finite || !(vmax - fl < 1.0f) || ng <= 8) std::fill(need.begin(), need.end(), 1);
+        if (!finite || !(vmax - fl <= 1.0f) || ng <= 8) std::fill(need.begin(), need.end(), 1);  // v = 1.0 exactly wraps to the first rows (modulo below)
         else {
             const float H = (float)d->h_texs[t].h[0];
             const long long ra = (long long)std::floor((vmin - fl) * H) - 1, rb = (long long)std::floor((vmax - fl) * H) + 1;
@@ -712,7 +720,7 @@ M2S_EXPORT m2s_status m2s_scene_upload_range(m2s_ctx* ctx, const m2s_scene* sc, 
     m2s_status st = scene_upload_impl(ctx, &slim.scene, &ds, count, false, first, true);
     if (st != M2S_OK) return st;
     st = vrange_enqueue(ctx, ds, first, first + count, 0);
-    if (st == M2S_OK) st = upload_groups_from_vrange(ctx, ds, 0);
+    if (st == M2S_OK) st = upload_groups_from_vrange(ctx, ds, 0, [] { return cudaSuccess; });
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (st == M2S_OK && e != cudaSuccess) { set_error(std::string("m2s_scene_upload_range: ") + cudaGetErrorString(e)); st = M2S_E_CUDA; }
     if (st != M2S_OK) { m2s_scene_free(ctx, ds); return st; }
@@ -833,7 +841,7 @@ M2S_EXPORT m2s_status m2s_convert_host(m2s_ctx* ctx, const m2s_scene* sc, const 
     };
     int launched = 0;
     for (int c = 0; c < planned; ++c) {  // (2)
-        st = upload_groups_from_vrange(ctx, ds, c);
+        st = upload_groups_from_vrange(ctx, ds, c, [&] { return downloads(launched, false); });  // (3) while waiting: whatever is ready
         if (st != M2S_OK) return fail_with(st);
         if (uploaded < planned) {  // next look-ahead chunk: behind this chunk's rows in the copy queue, ahead of its kernels' results
             st = upload_tris(uploaded++);
