@@ -213,7 +213,7 @@ template <> struct RCfg<2> { static constexpr int kMaps = 3; static constexpr bo
 // output layouts (m2s_layout)
 template <int LAYOUT> struct Cfg;
 template <> struct Cfg<0> { static constexpr int kStride = 96, kRK = 0; };   // REF96
-template <> struct Cfg<1> { static constexpr int kStride = 56, kRK = 1; };   // PACKED56
+template <> struct Cfg<1> { static constexpr int kStride = 56, kRK = 1; };   // PACKED56 (fragment kernel: 8 CTAs/SM = 64 registers)
 template <> struct Cfg<2> { static constexpr int kStride = 248, kRK = 2; };  // PLY_STANDARD (parsers.cpp:431-514)
 template <> struct Cfg<3> { static constexpr int kStride = 76, kRK = 2; };   // PLY_PBR      (parsers.cpp:232-316)
 template <> struct Cfg<4> { static constexpr int kStride = 48, kRK = 2; };   // PLY_COMPRESSED (parsers.cpp:339-428)
@@ -483,19 +483,25 @@ __device__ __forceinline__ Bilin2 bilin_setup2(const TexRef& r, float u, float v
     b.w00 = __fmul2_rn(bx, by); b.w10 = __fmul2_rn(ax, by); b.w01 = __fmul2_rn(bx, cy); b.w11 = __fmul2_rn(ax, cy);
     return b;
 }
-// channel CH of the texel pair (level 0, level 1) as floats, without the conversion pipe: 0x4B000000 | byte = 2^23 + byte
+// channel CH of the texel pair (level 0, level 1) as floats, without the conversion pipe: 0x4B000000 | byte = 2^23 + byte.
+// PRMT takes ONE immediate: with 0x4B000000 as the immediate the selector would need a register (re-materialised per
+// use: ~34 extra moves per fragment in the SASS); so the constant lives in a register the compiler cannot fold (k4b,
+// produced once per kernel by an opaque mov) and the selector is the immediate.
+__device__ __forceinline__ uint32_t opaque_4b() { uint32_t k; asm volatile("mov.u32 %0, 0x4B000000;" : "=r"(k)); return k; }
 template <int CH>
-__device__ __forceinline__ float2 tex_ch2(uint32_t t0, uint32_t t1) {
-    return __fadd2_rn(f2(__uint_as_float(__byte_perm(t0, 0x4B000000u, 0x7440u | CH)), __uint_as_float(__byte_perm(t1, 0x4B000000u, 0x7440u | CH))),
-                      f2(-8388608.0f));
+__device__ __forceinline__ float2 tex_ch2(uint32_t t0, uint32_t t1, uint32_t k4b) {
+    uint32_t a, b;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(a) : "r"(t0), "r"(k4b), "n"(0x7440 | CH));
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(b) : "r"(t1), "r"(k4b), "n"(0x7440 | CH));
+    return __fadd2_rn(f2(__uint_as_float(a), __uint_as_float(b)), f2(-8388608.0f));
 }
 // trilinear value of channel CH: tx[0..3] = level-0 texels (00, 10, 01, 11), tx[4..7] = level-1 texels
 template <int CH>
-__device__ __forceinline__ float filt2(const Bilin2& b, const uint32_t* tx) {
-    float2 acc = __fmul2_rn(b.w00, tex_ch2<CH>(tx[0], tx[4]));
-    acc = __ffma2_rn(b.w10, tex_ch2<CH>(tx[1], tx[5]), acc);
-    acc = __ffma2_rn(b.w01, tex_ch2<CH>(tx[2], tx[6]), acc);
-    acc = __ffma2_rn(b.w11, tex_ch2<CH>(tx[3], tx[7]), acc);
+__device__ __forceinline__ float filt2(const Bilin2& b, const uint32_t* tx, uint32_t k4b) {
+    float2 acc = __fmul2_rn(b.w00, tex_ch2<CH>(tx[0], tx[4], k4b));
+    acc = __ffma2_rn(b.w10, tex_ch2<CH>(tx[1], tx[5], k4b), acc);
+    acc = __ffma2_rn(b.w01, tex_ch2<CH>(tx[2], tx[6], k4b), acc);
+    acc = __ffma2_rn(b.w11, tex_ch2<CH>(tx[3], tx[7], k4b), acc);
     return acc.x + acc.y;
 }
 
@@ -926,6 +932,7 @@ template <int LAYOUT>
 __device__ __forceinline__ void shade(const ConvertArgs& a, const typename FragSmem<LAYOUT>::Rec& tf, const float4* __restrict__ v,
                                       int dxi, int dyi, const uint32_t* __restrict__ texb, unsigned char* __restrict__ srec_bytes) {
     constexpr int kMaps = RCfg<Cfg<LAYOUT>::kRK>::kMaps;
+    const uint32_t k4b = opaque_4b();
     const float ia = tf.inv_area;
     const float l0 = __ll2float_rn(tf.E0[0] + (long long)tf.A[0] * dxi + (long long)tf.B[0] * dyi) * ia;
     const float l1 = __ll2float_rn(tf.E0[1] + (long long)tf.A[1] * dxi + (long long)tf.B[1] * dyi) * ia;
@@ -967,7 +974,7 @@ __device__ __forceinline__ void shade(const ConvertArgs& a, const typename FragS
     // (and no loads) on the second level
     float cr = 1.f, cg = 1.f, cb = 1.f, ca = 1.f;
     if (has[0]) {
-        cr = filt2<0>(bl[0], tx[0]); cg = filt2<1>(bl[0], tx[0]); cb = filt2<2>(bl[0], tx[0]); ca = filt2<3>(bl[0], tx[0]);
+        cr = filt2<0>(bl[0], tx[0], k4b); cg = filt2<1>(bl[0], tx[0], k4b); cb = filt2<2>(bl[0], tx[0], k4b); ca = filt2<3>(bl[0], tx[0], k4b);
     }
     cr *= tf.factor[0]; cg *= tf.factor[1]; cb *= tf.factor[2]; ca *= tf.factor[3];
     const float kInvC0 = 1.0f / 0.28209479177387814f;  // SH_COEFF0, params.hpp:17 (parsers.cpp:484-486)
@@ -992,7 +999,7 @@ __device__ __forceinline__ void shade(const ConvertArgs& a, const typename FragS
     const float Ny = Nyz.x, Nz = Nyz.y;
     float nx = Nx, ny = Ny, nz = Nz;
     if (has[MN]) {  // :64-77 TBN
-        const float mx = filt2<0>(bl[MN], tx[MN]), my = filt2<1>(bl[MN], tx[MN]), mz = filt2<2>(bl[MN], tx[MN]);
+        const float mx = filt2<0>(bl[MN], tx[MN], k4b), my = filt2<1>(bl[MN], tx[MN], k4b), mz = filt2<2>(bl[MN], tx[MN], k4b);
         const float2 Txy = lerp3(f2(a1.z, a1.w), f2(b1.z, b1.w), f2(c1.z, c1.w));
         const float2 Tzw = lerp3(f2(a2.x, a2.y), f2(b2.x, b2.y), f2(c2.x, c2.y));
         const float Tx = Txy.x, Ty = Txy.y, Tz = Tzw.x, Tw = Tzw.y;
@@ -1010,8 +1017,8 @@ __device__ __forceinline__ void shade(const ConvertArgs& a, const typename FragS
     }
     float metal = 0.1f, rough = 0.5f;  // :83-95 (.bg)
     if (LAYOUT != 2 && has[MM]) {      // the standard .ply row carries no PBR values
-        rough = filt2<1>(bl[MM], tx[MM]);
-        metal = filt2<2>(bl[MM], tx[MM]);
+        rough = filt2<1>(bl[MM], tx[MM], k4b);
+        metal = filt2<2>(bl[MM], tx[MM], k4b);
     }
     if (LAYOUT == 0) {
         float4* s4 = reinterpret_cast<float4*>(srec_bytes);
@@ -1062,7 +1069,7 @@ __device__ __forceinline__ void shade(const ConvertArgs& a, const typename FragS
 }
 
 template <int LAYOUT>
-__global__ void __launch_bounds__(kFragThreads) fragment_kernel(const __grid_constant__ ConvertArgs a) {
+__global__ void __launch_bounds__(kFragThreads, (LAYOUT == 1 ? 1024 : 512) / kFragThreads) fragment_kernel(const __grid_constant__ ConvertArgs a) {
     using S = FragSmem<LAYOUT>;
     using Rec = typename S::Rec;
     constexpr int kStride = Cfg<LAYOUT>::kStride;
