@@ -62,6 +62,10 @@ struct m2s_ctx {
     // convert_host pipeline: a second stream for the downloads, per-chunk counts and events
     static constexpr int kMaxChunks = 8;
     cudaStream_t stream2 = nullptr;
+    cudaStream_t stream3 = nullptr;              // uploads of the host pipeline: the copy engine keeps going while chunk kernels run
+    cudaStream_t up = nullptr;                   // stream texture rows / triangle chunks are uploaded on (= stream, or stream3 inside the pipeline)
+    cudaEvent_t ev_up[kMaxChunks] = {};          // "chunk c's triangles and texture rows are resident"
+    cudaEvent_t ev_alloc = nullptr;
     unsigned long long* d_chunk_tot = nullptr;   // [kMaxChunks]
     unsigned long long* h_chunk_tot = nullptr;   // pinned + mapped: {count, tag} per chunk, written by the raster kernel
     unsigned long long host_seq = 0;             // tag generator
@@ -193,6 +197,10 @@ M2S_EXPORT m2s_status m2s_ctx_create(int device, m2s_ctx** out) {
     CUDA_TRY(cudaEventCreate(&c->ev0));
     CUDA_TRY(cudaEventCreate(&c->ev1));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
+    c->up = c->stream;
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_alloc, cudaEventDisableTiming));
+    for (int i = 0; i < m2s_ctx::kMaxChunks; ++i) CUDA_TRY(cudaEventCreateWithFlags(&c->ev_up[i], cudaEventDisableTiming));
     CUDA_TRY(cudaMalloc(&c->d_chunk_tot, m2s_ctx::kMaxChunks * sizeof(unsigned long long)));
     CUDA_TRY(cudaHostAlloc(&c->h_chunk_tot, 2 * m2s_ctx::kMaxChunks * sizeof(unsigned long long), cudaHostAllocMapped));
     std::memset(c->h_chunk_tot, 0, 2 * m2s_ctx::kMaxChunks * sizeof(unsigned long long));
@@ -223,6 +231,9 @@ M2S_EXPORT void m2s_ctx_destroy(m2s_ctx* c) {
     for (int i = 0; i < m2s_ctx::kMaxChunks; ++i) if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); if (c->ev_mid) cudaEventDestroy(c->ev_mid);
     if (c->stream2) cudaStreamDestroy(c->stream2);
+    if (c->stream3) cudaStreamDestroy(c->stream3);
+    if (c->ev_alloc) cudaEventDestroy(c->ev_alloc);
+    for (int i = 0; i < m2s_ctx::kMaxChunks; ++i) if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -284,9 +295,9 @@ static m2s_status upload_texture_groups(m2s_ctx* ctx, m2s_dscene* d, uint32_t t,
     const uint32_t r0 = g0 * kTexGroupRows, r1 = std::min<uint32_t>(H, g1 * kTexGroupRows);
     if (r0 >= r1) return M2S_OK;
     CUDA_TRY(cudaMemcpyAsync(d->d_arena + dt.off[0] + (size_t)r0 * W, d->h_rgba[t] + (size_t)r0 * W * 4, (size_t)(r1 - r0) * W * 4,
-                             cudaMemcpyHostToDevice, ctx->stream));
+                             cudaMemcpyHostToDevice, ctx->up));
     // level-l row j needs level-(l-1) rows 2j, 2j+1: inside the same 16-row group — all levels in one launch
-    CUDA_TRY(mip_groups_launch(d->d_arena, dt, g0, std::min<uint32_t>(g1, (H + kTexGroupRows - 1) / kTexGroupRows), ctx->stream));
+    CUDA_TRY(mip_groups_launch(d->d_arena, dt, g0, std::min<uint32_t>(g1, (H + kTexGroupRows - 1) / kTexGroupRows), ctx->up));
     for (uint32_t g = g0; g < g1 && g < d->present[t].size(); ++g) d->present[t][g] = 1;
     d->h2d_bytes += (uint64_t)(r1 - r0) * W * 4;
     return M2S_OK;
@@ -361,13 +372,13 @@ static m2s_status vrange_enqueue(m2s_ctx* ctx, m2s_dscene* d, uint64_t lo, uint6
     }
     VRangeSlot& v = ctx->vr[slot];
     // min <- 0x7f7f7f7f (above every finite float's key), max <- 0x80808080 (below), flag <- 0
-    CUDA_TRY(cudaMemsetAsync(v.d_minmax, 0x7f, nt * sizeof(int), ctx->stream));
-    CUDA_TRY(cudaMemsetAsync(v.d_minmax + nt, 0x80, nt * sizeof(int), ctx->stream));
-    CUDA_TRY(cudaMemsetAsync(v.d_minmax + 2 * nt, 0, sizeof(int), ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(v.d_minmax, 0x7f, nt * sizeof(int), ctx->up));
+    CUDA_TRY(cudaMemsetAsync(v.d_minmax + nt, 0x80, nt * sizeof(int), ctx->up));
+    CUDA_TRY(cudaMemsetAsync(v.d_minmax + 2 * nt, 0, sizeof(int), ctx->up));
     if (hi > lo)
-        CUDA_TRY(vrange_launch(d->d_tris, (uint32_t)lo, (uint32_t)(hi - lo), d->d_ranges, d->nranges, d->d_prims, nt, v.d_minmax, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(v.h_minmax, v.d_minmax, (2 * (size_t)nt + 1) * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaEventRecord(v.ev, ctx->stream));
+        CUDA_TRY(vrange_launch(d->d_tris, (uint32_t)lo, (uint32_t)(hi - lo), d->d_ranges, d->nranges, d->d_prims, nt, v.d_minmax, ctx->up));
+    CUDA_TRY(cudaMemcpyAsync(v.h_minmax, v.d_minmax, (2 * (size_t)nt + 1) * sizeof(int), cudaMemcpyDeviceToHost, ctx->up));
+    CUDA_TRY(cudaEventRecord(v.ev, ctx->up));
     return M2S_OK;
 }
 
@@ -744,7 +755,7 @@ M2S_EXPORT m2s_status m2s_convert_host(m2s_ctx* ctx, const m2s_scene* sc, const 
     if (count == 0 || first + count > sc->triangle_count) count = sc->triangle_count - first;
     int nchunks = 1;
     if (count >= 16384) {  // every layout: the fragment kernel appends after the earlier chunks' records itself
-        nchunks = 6;
+        nchunks = 8;
         if (const char* e = std::getenv("M2S_HOST_CHUNKS")) nchunks = std::max(1, std::min(m2s_ctx::kMaxChunks, std::atoi(e)));
     }
     const uint64_t per = (count + nchunks - 1) / nchunks;
@@ -764,7 +775,7 @@ M2S_EXPORT m2s_status m2s_convert_host(m2s_ctx* ctx, const m2s_scene* sc, const 
     std::memset(&r, 0, sizeof(r));
     const uint64_t cap = effective_cap(ds, p, out_capacity);
     auto fail_with = [&](m2s_status code) {
-        cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->stream2);
+        cudaStreamSynchronize(ctx->stream3); cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->stream2);
         ctx->dirty = true;
         m2s_scene_free(ctx, ds);
         return code;
@@ -778,6 +789,13 @@ M2S_EXPORT m2s_status m2s_convert_host(m2s_ctx* ctx, const m2s_scene* sc, const 
     auto since = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_start).count(); };
     cudaError_t e = cudaEventRecord(ctx->ev0, ctx->stream);
     if (e != cudaSuccess) return bail("convert_host", e);
+    // uploads run on their own stream (behind the allocations and table copies made above on the context stream): the
+    // copy engine streams triangles and texture rows continuously while the chunks' kernels run on the context stream
+    e = cudaEventRecord(ctx->ev_alloc, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream3, ctx->ev_alloc, 0);
+    if (e != cudaSuccess) return bail("convert_host", e);
+    struct UpGuard { m2s_ctx* c; ~UpGuard() { c->up = c->stream; } } up_guard{ctx};
+    ctx->up = ctx->stream3;
     uint64_t lo_[m2s_ctx::kMaxChunks], hi_[m2s_ctx::kMaxChunks];
     int planned = 0, uploaded = 0;
     for (int c = 0; c < nchunks; ++c) {
@@ -791,7 +809,7 @@ M2S_EXPORT m2s_status m2s_convert_host(m2s_ctx* ctx, const m2s_scene* sc, const 
         if (hi_[c] > lo_[c]) {
             cudaError_t e1 = cudaMemcpyAsync(reinterpret_cast<unsigned char*>(ds->d_tris) + lo_[c] * (size_t)kTriBytes,
                                              reinterpret_cast<const unsigned char*>(sc->triangles) + lo_[c] * (size_t)kTriBytes,
-                                             (hi_[c] - lo_[c]) * (size_t)kTriBytes, cudaMemcpyHostToDevice, ctx->stream);
+                                             (hi_[c] - lo_[c]) * (size_t)kTriBytes, cudaMemcpyHostToDevice, ctx->up);
             if (e1 != cudaSuccess) { set_error(std::string("convert_host upload: ") + cudaGetErrorString(e1)); return M2S_E_CUDA; }
             ds->h2d_bytes += (hi_[c] - lo_[c]) * (uint64_t)kTriBytes;
         }
@@ -843,7 +861,10 @@ M2S_EXPORT m2s_status m2s_convert_host(m2s_ctx* ctx, const m2s_scene* sc, const 
     for (int c = 0; c < planned; ++c) {  // (2)
         st = upload_groups_from_vrange(ctx, ds, c, [&] { return downloads(launched, false); });  // (3) while waiting: whatever is ready
         if (st != M2S_OK) return fail_with(st);
-        if (uploaded < planned) {  // next look-ahead chunk: behind this chunk's rows in the copy queue, ahead of its kernels' results
+        e = cudaEventRecord(ctx->ev_up[c], ctx->up);   // chunk c's triangles and texture rows are resident
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->ev_up[c], 0);
+        if (e != cudaSuccess) return bail("convert_host", e);
+        if (uploaded < planned) {  // next look-ahead chunk: behind this chunk's rows in the copy queue
             st = upload_tris(uploaded++);
             if (st != M2S_OK) return fail_with(st);
         }
@@ -878,6 +899,7 @@ M2S_EXPORT m2s_status m2s_convert_host(m2s_ctx* ctx, const m2s_scene* sc, const 
     if (e != cudaSuccess) return bail("convert_host download", e);
     e = cudaStreamSynchronize(ctx->stream2);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream3);
     if (e != cudaSuccess) return bail("convert_host download", e);
     if (host_trace) std::fprintf(stderr, "[m2s host] downloads done at %.0f us\n", since());
     float ms = 0.f;
