@@ -626,6 +626,28 @@ __device__ __forceinline__ void stash_unit_item(const ConvertArgs& a, WarpBlock<
     if (st.n_it == kStashItems) stash_flush<RK>(a, wb, unit, st, lane);
 }
 
+// count the row blocks [rb0, rb1) (32 rows each) of one larger triangle: one lane per pixel row, exact intervals
+template <int RK, class RecT>
+__device__ __forceinline__ void count_blocks(const ConvertArgs& a, WarpBlock<RK>& wb, uint32_t unit, Stash& st, const RecT& r, uint32_t slot,
+                                             int rb0, int rb1, int lane) {
+    const unsigned box = r.box;
+    RowState rs;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        rs.E[k] = r.E0[k] - (((box >> (26 + k)) & 1u) ? 0 : 1);
+        rs.A[k] = r.A[k]; rs.B[k] = r.B[k];
+    }
+    rs.w = (int)(box & 0x1fffu);
+    const int h = (int)((box >> 13) & 0x1fffu);
+    for (int rb = rb0 * 32; rb < h && rb < rb1 * 32; rb += 32) {
+        const int yrel = rb + lane;
+        int xl;
+        const uint32_t n = yrel < h ? span_row(rs, yrel, xl) : 0u;
+        const uint32_t bt = __reduce_add_sync(0xffffffffu, n);
+        if (bt) stash_block<RK>(a, wb, unit, st, slot, (uint32_t)rb, (uint32_t)min(32, h - rb), bt, lane);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // raster_kernel
 // ------------------------------------------------------------------------------------------
@@ -769,28 +791,20 @@ __global__ void __launch_bounds__(M2S_RASTER_WARPS * 32, 1) raster_kernel(const 
         __syncwarp();
         STAMP(a, 4);
 
-        // ---- all other triangles: the warp counts one triangle at a time, one lane per pixel row ----
-        unsigned gm = __ballot_sync(0xffffffffu, cnt != 0 && !small);
+        // ---- all other triangles: the warp counts one triangle at a time, one lane per pixel row.  A unit whose
+        // larger triangles add up to many row blocks (a wall of a building: 28 triangles x 4 blocks x 2000 fragments)
+        // would keep ONE warp busy while the grid idles: its tall triangles are deferred to a global queue instead
+        // and counted by all warps after the units (entries of <= kDeferBlocks blocks) ----
+        const uint32_t gm_all = __ballot_sync(0xffffffffu, cnt != 0 && !small);
+        const uint32_t myblocks = (cnt != 0 && !small) ? (uint32_t)(ts.h + 31) / 32u : 0u;
+        const uint32_t unit_blocks = __reduce_add_sync(0xffffffffu, myblocks);
+        const bool defer_unit = unit_blocks > kDeferUnitBlocks && a.defer_cap != 0;
+        const uint32_t dm = __ballot_sync(0xffffffffu, defer_unit && myblocks >= 2);   // triangles handed to the queue
+        unsigned gm = gm_all & ~dm;
         while (gm) {
             const int s = __ffs(gm) - 1;
             gm &= gm - 1;
-            const Rec& r = wb.rec[s];  // broadcast reads
-            const unsigned box = r.box;
-            RowState rs;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                rs.E[k] = r.E0[k] - (((box >> (26 + k)) & 1u) ? 0 : 1);
-                rs.A[k] = r.A[k]; rs.B[k] = r.B[k];
-            }
-            rs.w = (int)(box & 0x1fffu);
-            const int h = (int)((box >> 13) & 0x1fffu);
-            for (int rb = 0; rb < h; rb += 32) {
-                const int yrel = rb + lane;
-                int xl;
-                const uint32_t n = yrel < h ? span_row(rs, yrel, xl) : 0u;
-                const uint32_t bt = __reduce_add_sync(0xffffffffu, n);
-                if (bt) stash_block<RK>(a, wb, unit, st, (uint32_t)s, (uint32_t)rb, (uint32_t)min(32, h - rb), bt, lane);
-            }
+            count_blocks<RK>(a, wb, unit, st, wb.rec[s], (uint32_t)s, 0, 1 << 20, lane);  // broadcast reads of the record
         }
         // ONE atomicAdd per unit (unless the stash filled up on the way) reserves the output range and the queue
         // slots of everything the unit emits
@@ -810,10 +824,69 @@ __global__ void __launch_bounds__(M2S_RASTER_WARPS * 32, 1) raster_kernel(const 
                 tma_store_commit();
             }
         }
+        if (dm) {  // publish the deferred triangles: their records must be in global memory first
+            const uint32_t myent = ((dm >> lane) & 1u) ? (myblocks + kDeferBlocks - 1) / kDeferBlocks : 0u;
+            uint32_t scan = myent;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, scan, d);
+                if (lane >= d) scan += v;
+            }
+            const uint32_t nent = __shfl_sync(0xffffffffu, scan, 31);
+            uint32_t base = 0;
+            if (lane == 0) {
+                tma_store_wait_all();
+                __threadfence();
+                base = atomicAdd(SCHED(a, 2), nent);
+            }
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + nent <= a.defer_cap) {
+                for (uint32_t e = 0; e < myent; ++e)
+                    a.defer[base + scan - myent + e] = make_uint4(unit, (uint32_t)lane, e * kDeferBlocks, min(myblocks, (e + 1) * kDeferBlocks));
+            } else {  // queue full: the reserved slots stay empty, the triangles are counted here after all
+                for (uint32_t e = lane; e < nent; e += 32)
+                    if (base + e < a.defer_cap) a.defer[base + e] = make_uint4(0xffffffffu, 0u, 0u, 0u);
+                __syncwarp();
+                unsigned m2 = dm;
+                while (m2) {
+                    const int s2 = __ffs(m2) - 1;
+                    m2 &= m2 - 1;
+                    count_blocks<RK>(a, wb, unit, st, wb.rec[s2], (uint32_t)s2, 0, 1 << 20, lane);
+                }
+                stash_close_item<RK>(a, wb, unit, st, lane);
+                stash_flush<RK>(a, wb, unit, st, lane);
+            }
+            __threadfence();
+        }
+        __syncwarp();
+        if (lane == 0) atomicAdd(SCHED(a, 1), 1u);  // this unit's deferred entries (if any) are visible
         unit = next;
         STAMP(a, 6);
     }
     STAMP(a, 7);
+    // ---- drain: the deferred tall triangles, <= kDeferBlocks row blocks per entry, all warps of the grid ----
+    if (a.defer_cap) {
+        if (lane == 0) {
+            unsigned ns = 100;
+            while (ld_acquire_u32(SCHED(a, 1)) < a.n_units) { __nanosleep(ns); ns = min(ns * 2u, 1000u); }  // every unit has published
+        }
+        __syncwarp();
+        uint32_t tail = 0;
+        if (lane == 0) tail = ld_acquire_u32(SCHED(a, 2));
+        tail = min(__shfl_sync(0xffffffffu, tail, 0), a.defer_cap);
+        while (tail) {
+            uint32_t it = 0;
+            if (lane == 0) it = atomicAdd(SCHED(a, 3), 1u);
+            it = __shfl_sync(0xffffffffu, it, 0);
+            if (it >= tail) break;
+            const uint4 e = a.defer[it];
+            if (e.x == 0xffffffffu) continue;  // slot of a publication that did not fit
+            const Rec* r = reinterpret_cast<const Rec*>(a.tri_frag) + (size_t)e.x * a.unit_tris + e.y;  // uniform address: broadcast loads
+            count_blocks<RK>(a, wb, e.x, st, *r, e.y, (int)e.z, (int)e.w, lane);
+            stash_close_item<RK>(a, wb, e.x, st, lane);
+            stash_flush<RK>(a, wb, e.x, st, lane);
+        }
+    }
     if (lane == 0) tma_store_wait_all();  // record stores are complete (not just read) before the kernel ends
     // ---- last CTA out publishes the counts and re-arms the scheduler for the next launch ---------
     __syncthreads();
@@ -836,7 +909,7 @@ __global__ void __launch_bounds__(M2S_RASTER_WARPS * 32, 1) raster_kernel(const 
                     __threadfence_system();
                     *reinterpret_cast<volatile unsigned long long*>(a.host_total + 1) = a.host_tag;
                 }
-                *SCHED(a, 0) = 0; *SCHED(a, 4) = 0;
+                *SCHED(a, 0) = 0; *SCHED(a, 1) = 0; *SCHED(a, 2) = 0; *SCHED(a, 3) = 0; *SCHED(a, 4) = 0;
                 __threadfence();
             }
         }
