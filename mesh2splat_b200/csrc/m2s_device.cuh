@@ -102,7 +102,7 @@ struct ConvertArgs {
     unsigned long long* host_total;    // optional, mapped pinned host memory: {count, tag} written by the raster kernel's
     unsigned long long host_tag;       // last CTA so the host can size the download while the fragment kernel still runs
     // scheduling state (zero at launch, re-armed by the last CTA)
-    uint32_t* sched;                   // words 128 B apart: 0 unit counter, 1 units finished, 2 deferred-queue tail, 3 its head,
+    uint32_t* sched;                   // words 128 B apart: 0 unit counter, 1 units finished, 2 deferred-queue reservations, 3 its head, 5 its committed tail,
                                        // 4 raster CTAs finished, 6 fragment CTAs finished (fused gather)
     uint4* defer;                      // deferred tall triangles: {unit, slot, first row block, end row block}
     uint32_t defer_cap;

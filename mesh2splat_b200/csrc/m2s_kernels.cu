@@ -840,13 +840,21 @@ __global__ void __launch_bounds__(M2S_RASTER_WARPS * 32, 1) raster_kernel(const 
                 base = atomicAdd(SCHED(a, 2), nent);
             }
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (base + nent <= a.defer_cap) {
+            const bool fits = base + nent <= a.defer_cap;
+            if (fits) {
                 for (uint32_t e = 0; e < myent; ++e)
                     a.defer[base + scan - myent + e] = make_uint4(unit, (uint32_t)lane, e * kDeferBlocks, min(myblocks, (e + 1) * kDeferBlocks));
-            } else {  // queue full: the reserved slots stay empty, the triangles are counted here after all
+            } else {  // queue full: the reserved slots stay empty
                 for (uint32_t e = lane; e < nent; e += 32)
                     if (base + e < a.defer_cap) a.defer[base + e] = make_uint4(0xffffffffu, 0u, 0u, 0u);
-                __syncwarp();
+            }
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) {  // commit in reservation order: consumers only ever see completely written entries
+                while (ld_acquire_u32(SCHED(a, 5)) != base) __nanosleep(20);
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(SCHED(a, 5)), "r"(base + nent) : "memory");
+            }
+            if (!fits) {  // ... and the triangles are counted here after all
                 unsigned m2 = dm;
                 while (m2) {
                     const int s2 = __ffs(m2) - 1;
@@ -856,36 +864,41 @@ __global__ void __launch_bounds__(M2S_RASTER_WARPS * 32, 1) raster_kernel(const 
                 stash_close_item<RK>(a, wb, unit, st, lane);
                 stash_flush<RK>(a, wb, unit, st, lane);
             }
-            __threadfence();
         }
         __syncwarp();
-        if (lane == 0) atomicAdd(SCHED(a, 1), 1u);  // this unit's deferred entries (if any) are visible
+        if (lane == 0) atomicAdd(SCHED(a, 1), 1u);  // units finished (only warps that never had a unit wait for it)
         unit = next;
         STAMP(a, 6);
     }
     STAMP(a, 7);
-    // ---- drain: the deferred tall triangles, <= kDeferBlocks row blocks per entry, all warps of the grid ----
-    if (a.defer_cap) {
+    // ---- drain: the deferred tall triangles, <= kDeferBlocks row blocks per entry.  A warp helps with whatever is
+    // committed when it runs out of units and leaves when the queue is empty — entries committed later are drained by
+    // their own publisher, which is still alive.  Only warps that never had a unit wait for the units to finish (a
+    // mesh of two huge triangles: one warp publishes, 2367 help). ----
+    const bool idle_warp = blockIdx.x + gridDim.x * (uint32_t)warp >= a.n_units;
+    for (;;) {
+        uint32_t item = 0xffffffffu;
         if (lane == 0) {
-            unsigned ns = 100;
-            while (ld_acquire_u32(SCHED(a, 1)) < a.n_units) { __nanosleep(ns); ns = min(ns * 2u, 1000u); }  // every unit has published
+            const uint32_t c = min(ld_acquire_u32(SCHED(a, 5)), a.defer_cap);
+            const uint32_t h = *reinterpret_cast<volatile uint32_t*>(SCHED(a, 3));
+            if (h < c) item = atomicCAS(SCHED(a, 3), h, h + 1) == h ? h : 0xfffffffeu;  // 0xfffffffe: lost the race, retry
         }
-        __syncwarp();
-        uint32_t tail = 0;
-        if (lane == 0) tail = ld_acquire_u32(SCHED(a, 2));
-        tail = min(__shfl_sync(0xffffffffu, tail, 0), a.defer_cap);
-        while (tail) {
-            uint32_t it = 0;
-            if (lane == 0) it = atomicAdd(SCHED(a, 3), 1u);
-            it = __shfl_sync(0xffffffffu, it, 0);
-            if (it >= tail) break;
-            const uint4 e = a.defer[it];
-            if (e.x == 0xffffffffu) continue;  // slot of a publication that did not fit
-            const Rec* r = reinterpret_cast<const Rec*>(a.tri_frag) + (size_t)e.x * a.unit_tris + e.y;  // uniform address: broadcast loads
-            count_blocks<RK>(a, wb, e.x, st, *r, e.y, (int)e.z, (int)e.w, lane);
-            stash_close_item<RK>(a, wb, e.x, st, lane);
-            stash_flush<RK>(a, wb, e.x, st, lane);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item == 0xfffffffeu) continue;
+        if (item == 0xffffffffu) {
+            if (!idle_warp) break;
+            uint32_t done = 0;
+            if (lane == 0) done = ld_acquire_u32(SCHED(a, 1)) >= a.n_units && *reinterpret_cast<volatile uint32_t*>(SCHED(a, 3)) >= min(ld_acquire_u32(SCHED(a, 5)), a.defer_cap);
+            if (__shfl_sync(0xffffffffu, done, 0)) break;
+            __nanosleep(200);
+            continue;
         }
+        const uint4 e = a.defer[item];
+        if (e.x == 0xffffffffu) continue;  // slot of a publication that did not fit
+        const Rec* r = reinterpret_cast<const Rec*>(a.tri_frag) + (size_t)e.x * a.unit_tris + e.y;  // uniform address: broadcast loads
+        count_blocks<RK>(a, wb, e.x, st, *r, e.y, (int)e.z, (int)e.w, lane);
+        stash_close_item<RK>(a, wb, e.x, st, lane);
+        stash_flush<RK>(a, wb, e.x, st, lane);
     }
     if (lane == 0) tma_store_wait_all();  // record stores are complete (not just read) before the kernel ends
     // ---- last CTA out publishes the counts and re-arms the scheduler for the next launch ---------
@@ -909,7 +922,7 @@ __global__ void __launch_bounds__(M2S_RASTER_WARPS * 32, 1) raster_kernel(const 
                     __threadfence_system();
                     *reinterpret_cast<volatile unsigned long long*>(a.host_total + 1) = a.host_tag;
                 }
-                *SCHED(a, 0) = 0; *SCHED(a, 1) = 0; *SCHED(a, 2) = 0; *SCHED(a, 3) = 0; *SCHED(a, 4) = 0;
+                *SCHED(a, 0) = 0; *SCHED(a, 1) = 0; *SCHED(a, 2) = 0; *SCHED(a, 3) = 0; *SCHED(a, 4) = 0; *SCHED(a, 5) = 0;
                 __threadfence();
             }
         }
