@@ -86,7 +86,6 @@ struct m2s_ctx {
     // intermediates between the raster and the fragment kernel
     void* d_trifrag = nullptr;  size_t trifrag_bytes = 0;   // TriRec per triangle of the shard
     void* d_items = nullptr;    size_t items_bytes = 0;     // FragItem queue
-    void* d_defer = nullptr;    size_t defer_bytes = 0;     // deferred tall triangles of the raster kernel
 };
 
 struct m2s_dscene {
@@ -222,7 +221,6 @@ M2S_EXPORT void m2s_ctx_destroy(m2s_ctx* c) {
     if (c->d_keys) cudaFreeAsync(c->d_keys, c->stream);
     if (c->d_trifrag) cudaFreeAsync(c->d_trifrag, c->stream);
     if (c->d_items) cudaFreeAsync(c->d_items, c->stream);
-    if (c->d_defer) cudaFreeAsync(c->d_defer, c->stream);
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_sched); cudaFree(c->d_counter); cudaFree(c->d_total); cudaFree(c->d_nitems);
     cudaFreeHost(c->h_total);
@@ -578,12 +576,9 @@ static m2s_status convert_enqueue_impl(m2s_ctx* ctx, const m2s_dscene* s, const 
     const uint64_t raster_warps = (uint64_t)grid * convert_warps_per_cta(klayout);
     const uint64_t queue_cap = std::min<uint64_t>(2 * n_units + cap / 32 + cap / flush_frags + cap / item_max +
                                                   raster_warps * (2ull * kMaxSplit + kStashItems) + 64, (1u << 24) - 1);
-    // deferred tall triangles: a full queue only means the owning warp counts them itself
-    const uint64_t defer_cap = std::max<uint64_t>(65536, count / 4);
     {   // scratch between the two kernels (grown on demand, kept by the context)
         m2s_status st = grow(ctx, &ctx->d_trifrag, &ctx->trifrag_bytes, std::max<uint64_t>(count, 1) * tri_frag_bytes(klayout), stream);
         if (st == M2S_OK) st = grow(ctx, &ctx->d_items, &ctx->items_bytes, queue_cap * sizeof(FragItem), stream);
-        if (st == M2S_OK) st = grow(ctx, &ctx->d_defer, &ctx->defer_bytes, defer_cap * sizeof(uint4), stream);
         if (st != M2S_OK) return st;
     }
     if (ctx->dirty) {
@@ -610,8 +605,6 @@ static m2s_status convert_enqueue_impl(m2s_ctx* ctx, const m2s_dscene* s, const 
     a.item_max_frags = item_max;
     a.flush_frags = flush_frags;
     a.n_items_out = ctx->d_nitems;
-    a.defer = (uint4*)ctx->d_defer;
-    a.defer_cap = (uint32_t)defer_cap;
     a.out = (uint8_t*)kout;
     a.cap = cap;
     a.keys = (unsigned long long*)d_keys;

@@ -13,8 +13,8 @@ constexpr uint32_t kSmallCand = 64;      // <= this many candidate pixels (and <
 constexpr int kItemBlocks = 32;          // row blocks (<= 32 pixel rows of one triangle) per fragment work item
 constexpr int kStashItems = 8;           // work items a raster warp publishes with one atomic
 constexpr uint32_t kItemMaxFrags = 2048; // upper bound of ConvertArgs::item_max_frags
-constexpr uint32_t kDeferUnitBlocks = 24; // a work unit whose larger triangles have more row blocks than this defers the tall ones
-constexpr uint32_t kDeferBlocks = 4;      // row blocks per deferred-queue entry
+constexpr uint32_t kDeferUnitBlocks = 24; // a work unit whose larger triangles have more row blocks than this posts the tall ones to its CTA's help queue
+constexpr uint32_t kDeferBlocks = 4;      // row blocks per help-queue entry
 constexpr uint32_t kMaxSplit = 64;       // queue slots one oversized row block can take (item_max_frags >= R / 2)
 constexpr unsigned long long kFragMask = (1ull << 40) - 1;  // ConvertArgs::counter: fragments | queue slots << 40
 constexpr float kGuard = 8192.0f;        // window-coordinate guard band (|xw| beyond -> triangle dropped)
@@ -102,10 +102,8 @@ struct ConvertArgs {
     unsigned long long* host_total;    // optional, mapped pinned host memory: {count, tag} written by the raster kernel's
     unsigned long long host_tag;       // last CTA so the host can size the download while the fragment kernel still runs
     // scheduling state (zero at launch, re-armed by the last CTA)
-    uint32_t* sched;                   // words 128 B apart: 0 unit counter, 1 units finished, 2 deferred-queue reservations, 3 its head, 5 its committed tail,
-                                       // 4 raster CTAs finished, 6 fragment CTAs finished (fused gather)
-    uint4* defer;                      // deferred tall triangles: {unit, slot, first row block, end row block}
-    uint32_t defer_cap;
+    uint32_t* sched;                   // words 128 B apart: 0 unit counter, 4 raster CTAs finished, 6 fragment CTAs finished
+                                       // (fused gather)
     uint32_t unit_tris;                // triangles per work unit (<= 32), chosen by the host for balance
     uint32_t n_units;
     unsigned long long* trace;         // M2S_TRACE builds only: 16 globaltimer stamps per raster warp

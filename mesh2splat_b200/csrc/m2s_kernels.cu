@@ -627,18 +627,9 @@ __device__ __forceinline__ void stash_unit_item(const ConvertArgs& a, WarpBlock<
 }
 
 // count the row blocks [rb0, rb1) (32 rows each) of one larger triangle: one lane per pixel row, exact intervals
-template <int RK, class RecT>
-__device__ __forceinline__ void count_blocks(const ConvertArgs& a, WarpBlock<RK>& wb, uint32_t unit, Stash& st, const RecT& r, uint32_t slot,
-                                             int rb0, int rb1, int lane) {
-    const unsigned box = r.box;
-    RowState rs;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        rs.E[k] = r.E0[k] - (((box >> (26 + k)) & 1u) ? 0 : 1);
-        rs.A[k] = r.A[k]; rs.B[k] = r.B[k];
-    }
-    rs.w = (int)(box & 0x1fffu);
-    const int h = (int)((box >> 13) & 0x1fffu);
+template <int RK>
+__device__ __forceinline__ void count_blocks(const ConvertArgs& a, WarpBlock<RK>& wb, uint32_t unit, Stash& st, const RowState& rs, int h,
+                                             uint32_t slot, int rb0, int rb1, int lane) {
     for (int rb = rb0 * 32; rb < h && rb < rb1 * 32; rb += 32) {
         const int yrel = rb + lane;
         int xl;
@@ -647,6 +638,40 @@ __device__ __forceinline__ void count_blocks(const ConvertArgs& a, WarpBlock<RK>
         if (bt) stash_block<RK>(a, wb, unit, st, slot, (uint32_t)rb, (uint32_t)min(32, h - rb), bt, lane);
     }
 }
+template <class RecT>
+__device__ __forceinline__ RowState row_state(const RecT& r, int& h) {
+    const unsigned box = r.box;
+    RowState rs;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        rs.E[k] = r.E0[k] - (((box >> (26 + k)) & 1u) ? 0 : 1);
+        rs.A[k] = r.A[k]; rs.B[k] = r.B[k];
+    }
+    rs.w = (int)(box & 0x1fffu);
+    h = (int)((box >> 13) & 0x1fffu);
+    return rs;
+}
+
+// CTA-local help queue (shared memory): a work unit whose larger triangles add up to many row blocks (a wall of a
+// building: 28 triangles x 4 blocks x 2000 fragments) would keep ONE warp busy for hundreds of microseconds while the
+// others are done: it posts its tall triangles here, in pieces of kDeferBlocks row blocks, and every warp of the CTA that
+// has run out of units takes tickets.  Shared-memory atomics only: a grid-wide queue was tried (r02) and lost to the
+// serialisation of same-address global atomics (one per unit / per claim: 8-30 us at 2-30 k units).
+struct CtaEntry {
+    RowState rs;                  // 64 B
+    int h;
+    uint32_t unit, slot, rb0, rb1;
+    volatile uint32_t ready;      // written last
+    uint32_t pad[2];
+};
+constexpr uint32_t kCtaQueueCap = 40;
+struct CtaQueue {
+    uint32_t tail;                // entries posted (may exceed the capacity: the poster keeps the overflow)
+    uint32_t head;                // tickets taken
+    uint32_t active;              // warps of the CTA still inside their unit loop
+    uint32_t pad;
+    CtaEntry q[kCtaQueueCap];
+};
 
 // ------------------------------------------------------------------------------------------
 // raster_kernel
@@ -702,6 +727,10 @@ __global__ void __launch_bounds__(M2S_RASTER_WARPS * 32, 1) raster_kernel(const 
             __syncthreads();  // the only CTA-wide barrier before the end of the kernel
         }
     }
+    CtaQueue& cq = *reinterpret_cast<CtaQueue*>(smem + (size_t)M2S_RASTER_WARPS * sizeof(WarpBlock<RK>) + kTableSmemBytes);
+    if (threadIdx.x == 0) { cq.tail = 0; cq.head = 0; cq.active = blockDim.x >> 5; }
+    if (threadIdx.x < kCtaQueueCap) cq.q[threadIdx.x].ready = 0u;
+    __syncthreads();
     uint32_t phase = 0;
     Stash st;
     st.n_it = 0; st.cur_nb = 0; st.cur_total = 0; st.frags = 0; st.slots = 0; st.seen = 0;
@@ -791,20 +820,41 @@ __global__ void __launch_bounds__(M2S_RASTER_WARPS * 32, 1) raster_kernel(const 
         __syncwarp();
         STAMP(a, 4);
 
-        // ---- all other triangles: the warp counts one triangle at a time, one lane per pixel row.  A unit whose
-        // larger triangles add up to many row blocks (a wall of a building: 28 triangles x 4 blocks x 2000 fragments)
-        // would keep ONE warp busy while the grid idles: its tall triangles are deferred to a global queue instead
-        // and counted by all warps after the units (entries of <= kDeferBlocks blocks) ----
+        // ---- all other triangles: the warp counts one triangle at a time, one lane per pixel row; the tall triangles of
+        // a heavy unit are posted to the CTA's help queue instead (see CtaQueue) ----
         const uint32_t gm_all = __ballot_sync(0xffffffffu, cnt != 0 && !small);
         const uint32_t myblocks = (cnt != 0 && !small) ? (uint32_t)(ts.h + 31) / 32u : 0u;
         const uint32_t unit_blocks = __reduce_add_sync(0xffffffffu, myblocks);
-        const bool defer_unit = unit_blocks > kDeferUnitBlocks && a.defer_cap != 0;
-        const uint32_t dm = __ballot_sync(0xffffffffu, defer_unit && myblocks >= 2);   // triangles handed to the queue
-        unsigned gm = gm_all & ~dm;
+        unsigned gm = gm_all;
+        if (unit_blocks > kDeferUnitBlocks) {
+            unsigned dm = __ballot_sync(0xffffffffu, myblocks >= 2);
+            while (dm) {
+                const int s = __ffs(dm) - 1;
+                dm &= dm - 1;
+                int h;
+                const RowState rs = row_state(wb.rec[s], h);
+                const uint32_t nb = (uint32_t)(h + 31) / 32u, nent = (nb + kDeferBlocks - 1) / kDeferBlocks;
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd_block(&cq.tail, nent);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const uint32_t fit = base < kCtaQueueCap ? min(nent, kCtaQueueCap - base) : 0u;  // the first `fit` pieces go to the queue
+                if ((uint32_t)lane < fit) {
+                    CtaEntry& e = cq.q[base + lane];
+                    e.rs = rs; e.h = h; e.unit = unit; e.slot = (uint32_t)s;
+                    e.rb0 = lane * kDeferBlocks; e.rb1 = min(nb, (lane + 1) * kDeferBlocks);
+                    __threadfence_block();
+                    e.ready = 1u;
+                }
+                if (fit < nent) count_blocks<RK>(a, wb, unit, st, rs, h, (uint32_t)s, (int)(fit * kDeferBlocks), 1 << 20, lane);  // the rest stays here
+                gm &= ~(1u << s);
+            }
+        }
         while (gm) {
             const int s = __ffs(gm) - 1;
             gm &= gm - 1;
-            count_blocks<RK>(a, wb, unit, st, wb.rec[s], (uint32_t)s, 0, 1 << 20, lane);  // broadcast reads of the record
+            int h;
+            const RowState rs = row_state(wb.rec[s], h);  // broadcast reads of the record
+            count_blocks<RK>(a, wb, unit, st, rs, h, (uint32_t)s, 0, 1 << 20, lane);
         }
         // ONE atomicAdd per unit (unless the stash filled up on the way) reserves the output range and the queue
         // slots of everything the unit emits
@@ -824,81 +874,36 @@ __global__ void __launch_bounds__(M2S_RASTER_WARPS * 32, 1) raster_kernel(const 
                 tma_store_commit();
             }
         }
-        if (dm) {  // publish the deferred triangles: their records must be in global memory first
-            const uint32_t myent = ((dm >> lane) & 1u) ? (myblocks + kDeferBlocks - 1) / kDeferBlocks : 0u;
-            uint32_t scan = myent;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t v = __shfl_up_sync(0xffffffffu, scan, d);
-                if (lane >= d) scan += v;
-            }
-            const uint32_t nent = __shfl_sync(0xffffffffu, scan, 31);
-            uint32_t base = 0;
-            if (lane == 0) {
-                tma_store_wait_all();
-                __threadfence();
-                base = atomicAdd(SCHED(a, 2), nent);
-            }
-            base = __shfl_sync(0xffffffffu, base, 0);
-            const bool fits = base + nent <= a.defer_cap;
-            if (fits) {
-                for (uint32_t e = 0; e < myent; ++e)
-                    a.defer[base + scan - myent + e] = make_uint4(unit, (uint32_t)lane, e * kDeferBlocks, min(myblocks, (e + 1) * kDeferBlocks));
-            } else {  // queue full: the reserved slots stay empty
-                for (uint32_t e = lane; e < nent; e += 32)
-                    if (base + e < a.defer_cap) a.defer[base + e] = make_uint4(0xffffffffu, 0u, 0u, 0u);
-            }
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) {  // commit in reservation order: consumers only ever see completely written entries
-                while (ld_acquire_u32(SCHED(a, 5)) != base) __nanosleep(20);
-                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(SCHED(a, 5)), "r"(base + nent) : "memory");
-            }
-            if (!fits) {  // ... and the triangles are counted here after all
-                unsigned m2 = dm;
-                while (m2) {
-                    const int s2 = __ffs(m2) - 1;
-                    m2 &= m2 - 1;
-                    count_blocks<RK>(a, wb, unit, st, wb.rec[s2], (uint32_t)s2, 0, 1 << 20, lane);
-                }
-                stash_close_item<RK>(a, wb, unit, st, lane);
-                stash_flush<RK>(a, wb, unit, st, lane);
-            }
-        }
-        __syncwarp();
-        if (lane == 0) atomicAdd(SCHED(a, 1), 1u);  // units finished (only warps that never had a unit wait for it)
         unit = next;
         STAMP(a, 6);
     }
     STAMP(a, 7);
-    // ---- drain: the deferred tall triangles, <= kDeferBlocks row blocks per entry.  A warp helps with whatever is
-    // committed when it runs out of units and leaves when the queue is empty — entries committed later are drained by
-    // their own publisher, which is still alive.  Only warps that never had a unit wait for the units to finish (a
-    // mesh of two huge triangles: one warp publishes, 2367 help). ----
-    const bool idle_warp = blockIdx.x + gridDim.x * (uint32_t)warp >= a.n_units;
+    // ---- help: tickets on the CTA's queue until no warp of the CTA can post any more ----
+    if (lane == 0) atomicSub_block(&cq.active, 1u);
     for (;;) {
-        uint32_t item = 0xffffffffu;
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd_block(&cq.head, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= kCtaQueueCap) break;  // beyond the capacity nothing is ever posted
+        bool have = false;
         if (lane == 0) {
-            const uint32_t c = min(ld_acquire_u32(SCHED(a, 5)), a.defer_cap);
-            const uint32_t h = *reinterpret_cast<volatile uint32_t*>(SCHED(a, 3));
-            if (h < c) item = atomicCAS(SCHED(a, 3), h, h + 1) == h ? h : 0xfffffffeu;  // 0xfffffffe: lost the race, retry
+            for (;;) {
+                if (*reinterpret_cast<volatile uint32_t*>(&cq.tail) > t) { have = true; break; }
+                if (*reinterpret_cast<volatile uint32_t*>(&cq.active) == 0 && *reinterpret_cast<volatile uint32_t*>(&cq.tail) <= t) break;
+                __nanosleep(40);
+            }
+            if (have) while (cq.q[t].ready == 0u) __nanosleep(20);
+            __threadfence_block();
         }
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if (item == 0xfffffffeu) continue;
-        if (item == 0xffffffffu) {
-            if (!idle_warp) break;
-            uint32_t done = 0;
-            if (lane == 0) done = ld_acquire_u32(SCHED(a, 1)) >= a.n_units && *reinterpret_cast<volatile uint32_t*>(SCHED(a, 3)) >= min(ld_acquire_u32(SCHED(a, 5)), a.defer_cap);
-            if (__shfl_sync(0xffffffffu, done, 0)) break;
-            __nanosleep(200);
-            continue;
-        }
-        const uint4 e = a.defer[item];
-        if (e.x == 0xffffffffu) continue;  // slot of a publication that did not fit
-        const Rec* r = reinterpret_cast<const Rec*>(a.tri_frag) + (size_t)e.x * a.unit_tris + e.y;  // uniform address: broadcast loads
-        count_blocks<RK>(a, wb, e.x, st, *r, e.y, (int)e.z, (int)e.w, lane);
-        stash_close_item<RK>(a, wb, e.x, st, lane);
-        stash_flush<RK>(a, wb, e.x, st, lane);
+        if (!__shfl_sync(0xffffffffu, (int)have, 0)) break;
+        const CtaEntry& e = cq.q[t];
+        const RowState rs = e.rs;
+        const int h = e.h;
+        const uint32_t eu = e.unit, es = e.slot;
+        const int rb0 = (int)e.rb0, rb1 = (int)e.rb1;
+        count_blocks<RK>(a, wb, eu, st, rs, h, es, rb0, rb1, lane);
+        stash_close_item<RK>(a, wb, eu, st, lane);
+        stash_flush<RK>(a, wb, eu, st, lane);
     }
     if (lane == 0) tma_store_wait_all();  // record stores are complete (not just read) before the kernel ends
     // ---- last CTA out publishes the counts and re-arms the scheduler for the next launch ---------
@@ -922,7 +927,7 @@ __global__ void __launch_bounds__(M2S_RASTER_WARPS * 32, 1) raster_kernel(const 
                     __threadfence_system();
                     *reinterpret_cast<volatile unsigned long long*>(a.host_total + 1) = a.host_tag;
                 }
-                *SCHED(a, 0) = 0; *SCHED(a, 1) = 0; *SCHED(a, 2) = 0; *SCHED(a, 3) = 0; *SCHED(a, 4) = 0; *SCHED(a, 5) = 0;
+                *SCHED(a, 0) = 0; *SCHED(a, 4) = 0;
                 __threadfence();
             }
         }
@@ -1554,7 +1559,7 @@ static int raster_kind(int layout) { return layout == 0 ? 0 : (layout == 1 ? 1 :
 size_t raster_smem_bytes(int layout) {
     const int rk = raster_kind(layout);
     const size_t wb = rk == 0 ? sizeof(WarpBlock<0>) : (rk == 1 ? sizeof(WarpBlock<1>) : sizeof(WarpBlock<2>));
-    return wb * M2S_RASTER_WARPS + kTableSmemBytes;
+    return wb * M2S_RASTER_WARPS + kTableSmemBytes + sizeof(CtaQueue);
 }
 size_t fragment_smem_bytes(int layout) {
     switch (layout) {
