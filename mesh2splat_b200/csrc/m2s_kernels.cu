@@ -530,6 +530,8 @@ struct Stash {            // warp-uniform registers
 };
 constexpr uint32_t kItUnit = 0x80000000u;   // item = the unit's small triangles (one implicit block per triangle)
 constexpr uint32_t kItSplit = 0x40000000u;  // item = one oversized row block, cut into several queue slots
+constexpr uint32_t kItMicro = 0x20000000u;  // unit item of <= 32 fragments: the block area holds the fragments themselves
+                                            // (slot | x << 5 | y << 11, box-relative), one warp shades it with direct loads
 
 template <int RK>
 __device__ __forceinline__ void stash_flush(const ConvertArgs& a, WarpBlock<RK>& wb, uint32_t unit, Stash& st, int lane) {
@@ -568,7 +570,8 @@ __device__ __forceinline__ void stash_flush(const ConvertArgs& a, WarpBlock<RK>&
                         *reinterpret_cast<uint4*>(it) = make_uint4((uint32_t)first, (uint32_t)(first >> 32), unit, nb);
                         *(reinterpret_cast<uint2*>(it) + 2) = make_uint2(0u, tot);
                     }
-                    if (!(nb & kItUnit) && (uint32_t)lane < nb) it->blocks[lane] = blk[lane];
+                    if (nb & kItMicro) { if (lane < 16) it->blocks[lane] = blk[lane]; }   // 32 packed fragments
+                    else if (!(nb & kItUnit) && (uint32_t)lane < nb) it->blocks[lane] = blk[lane];
                 }
                 slot += 1;
             }
@@ -613,15 +616,29 @@ __device__ __forceinline__ void stash_block(const ConvertArgs& a, WarpBlock<RK>&
     if (st.cur_nb == kItemBlocks || st.cur_total >= a.flush_frags) stash_close_item<RK>(a, wb, unit, st, lane);
 }
 
-// the unit's small triangles as one item (blocks implicit: one per triangle, TriRec::first/hits)
+// the unit's small triangles as one item (blocks implicit: one per triangle, TriRec::first/hits).  A unit with at
+// most 32 such fragments (sub-pixel meshes: most units of a 1 M-triangle scan) lists them in the item instead: the
+// fragment kernel then needs neither the staged unit nor its span table.  hits/w/first: this lane's triangle.
 template <int RK>
 __device__ __forceinline__ void stash_unit_item(const ConvertArgs& a, WarpBlock<RK>& wb, uint32_t unit, Stash& st, uint32_t total_small,
-                                                uint32_t ntri, int lane) {
+                                                uint32_t ntri, unsigned long long hits, uint32_t w, uint32_t first, int lane) {
     if (total_small == 0) return;
     // the open item (if any) stays open: closed items occupy the slots below n_it, the open one is written at n_it
     // only when it closes — so insert the unit item by closing the open one first
     stash_close_item<RK>(a, wb, unit, st, lane);
-    if (lane == 0) { wb.itN[st.n_it] = ntri | kItUnit; wb.itTotal[st.n_it] = total_small; }
+    const bool micro = total_small <= 32;
+    if (micro) {
+        uint32_t* list = reinterpret_cast<uint32_t*>(wb.pend + st.n_it * kItemBlocks);
+        const uint32_t inv = (65536u + w - 1u) / w;  // row = bit / w by a 16.16 reciprocal (exact for bit < 64, w <= 64)
+        uint32_t k = first;
+        while (hits) {
+            const uint32_t b = (uint32_t)__ffsll((long long)hits) - 1u;
+            hits &= hits - 1ull;
+            const uint32_t row = (b * inv) >> 16, col = b - row * w;
+            list[k++] = (uint32_t)lane | (col << 5) | (row << 11);
+        }
+    }
+    if (lane == 0) { wb.itN[st.n_it] = ntri | kItUnit | (micro ? kItMicro : 0u); wb.itTotal[st.n_it] = total_small; }
     st.frags += total_small; st.slots += 1; st.n_it += 1;
     if (st.n_it == kStashItems) stash_flush<RK>(a, wb, unit, st, lane);
 }
@@ -859,7 +876,7 @@ __global__ void __launch_bounds__(M2S_RASTER_WARPS * 32, 1) raster_kernel(const 
         // ONE atomicAdd per unit (unless the stash filled up on the way) reserves the output range and the queue
         // slots of everything the unit emits
         stash_close_item<RK>(a, wb, unit, st, lane);
-        stash_unit_item<RK>(a, wb, unit, st, total_small, ntri, lane);
+        stash_unit_item<RK>(a, wb, unit, st, total_small, ntri, hits, (uint32_t)w, incl_scan - nh, lane);
         stash_flush<RK>(a, wb, unit, st, lane);
         STAMP(a, 5);
 
@@ -1159,6 +1176,45 @@ __device__ __forceinline__ void shade(const ConvertArgs& a, const typename FragS
     }
 }
 
+// A micro item (kItMicro): <= 32 fragments listed in the item itself, shaded by one warp with direct loads.  Out of line:
+// the second copy of the shading code must not add to the register pressure of the main loop.
+template <int LAYOUT>
+__device__ __noinline__ void micro_item(const ConvertArgs& a, uint32_t it, uint4 h0, uint32_t nfr, unsigned long long base, unsigned long long room,
+                                        unsigned long long goff, const uint32_t* __restrict__ texb, unsigned char* stage, int lane) {
+    using Rec = typename FragSmem<LAYOUT>::Rec;
+    constexpr int kStride = Cfg<LAYOUT>::kStride;
+    const unsigned long long first = (unsigned long long)h0.x | ((unsigned long long)h0.y << 32);
+    const uint32_t t0 = h0.z * a.unit_tris;
+    const uint32_t w32 = (uint32_t)lane < nfr ? __ldg(reinterpret_cast<const uint32_t*>((a.items + it)->blocks) + lane) : 0u;
+    const uint32_t slot = w32 & 31u;
+    const Rec* tfp = reinterpret_cast<const Rec*>(a.tri_frag) + (size_t)t0 + slot;
+    if ((uint32_t)lane < nfr)
+        shade<LAYOUT>(a, *tfp, a.tris + ((size_t)a.tri_first + t0 + slot) * 9, (int)((w32 >> 5) & 63u), (int)((w32 >> 11) & 63u), texb,
+                      stage + lane * kStride);
+    __syncwarp();
+    uint32_t nval = 0;
+    if (first < room) nval = (uint32_t)min((unsigned long long)nfr, room - first);
+    if (a.world <= 1) {
+        copy_span<kStride>(a.out, (base + first) * (unsigned long long)kStride, stage, nval * kStride, lane);
+    } else {
+        const unsigned long long gbase = goff + first;
+        uint32_t gval = 0;
+        if (gbase < a.gcap) gval = (uint32_t)min((unsigned long long)nval, a.gcap - gbase);
+        uint32_t p = (a.rank + 1u + it) % a.world;
+        for (uint32_t i = 0; i < a.world; ++i) {
+            copy_span<kStride>(a.peer_out[p], gbase * (unsigned long long)kStride, stage, gval * kStride, lane);
+            p = p + 1 == a.world ? 0 : p + 1;
+        }
+    }
+    if (a.keys != nullptr && (uint32_t)lane < nval) {
+        const unsigned meta = tfp->meta;
+        const unsigned long long tg = a.tri_first + t0 + slot;
+        a.keys[base + first + lane] = (tg << 24) | ((unsigned long long)(((meta >> 16) & 0xfffu) + ((w32 >> 11) & 63u)) << 12) |
+                                      (unsigned long long)(((meta >> 4) & 0xfffu) + ((w32 >> 5) & 63u));
+    }
+    __syncwarp();
+}
+
 template <int LAYOUT>
 __global__ void __launch_bounds__(kFragThreads, (LAYOUT == 1 ? 1024 : 512) / kFragThreads) fragment_kernel(const __grid_constant__ ConvertArgs a) {
     using S = FragSmem<LAYOUT>;
@@ -1234,19 +1290,29 @@ __global__ void __launch_bounds__(kFragThreads, (LAYOUT == 1 ? 1024 : 512) / kFr
     uint32_t phases = 0;  // bit b: parity of the next completion of bar[b]
     uint32_t buf = 0;
     Hdr cur = load_hdr(blockIdx.x);
+    auto staged = [&](const Hdr& h) { return live(h) && !(h.h0.w & kItMicro); };  // micro items need no staged unit
     bool cur_live = live(cur), cur_issued = false;
-    if (M2S_FRAG_BUFS > 1 && cur_live) { if (threadIdx.x == 0) issue(cur, 0); cur_issued = true; }
+    if (M2S_FRAG_BUFS > 1 && staged(cur)) { if (threadIdx.x == 0) issue(cur, 0); cur_issued = true; }
     Hdr nxt = load_hdr(blockIdx.x + gridDim.x);
 
     for (uint32_t it = blockIdx.x; it < nitems; it += gridDim.x) {
-        const bool nxt_live = live(nxt);
+        const bool nxt_live = live(nxt), nxt_staged = staged(nxt);
         uint32_t nbuf = buf;
-        if (M2S_FRAG_BUFS > 1 && nxt_live) {  // the other buffer is free: its last reader passed the barrier at the end of the previous item
+        if (M2S_FRAG_BUFS > 1 && nxt_staged) {  // the other buffer is free: its last reader passed the barrier at the end of the previous item
             nbuf = cur_issued ? buf ^ 1u : buf;
             if (threadIdx.x == 0) issue(nxt, nbuf);
         }
         const Hdr nn = load_hdr(it + 2 * gridDim.x);
-        if (!cur_live) { cur = nxt; cur_live = nxt_live; cur_issued = M2S_FRAG_BUFS > 1 && nxt_live; buf = nbuf; nxt = nn; continue; }
+        if (!cur_live) { cur = nxt; cur_live = nxt_live; cur_issued = M2S_FRAG_BUFS > 1 && nxt_staged; buf = nbuf; nxt = nn; continue; }
+        if (cur.h0.w & kItMicro) {
+            // ---- micro item: <= 32 fragments listed in the item; ONE warp (round robin) shades it with direct loads of the
+            // records and vertices it touches — no staged unit, no span table, no CTA barrier: four consecutive micro
+            // items are in flight per CTA ----
+            if ((uint32_t)warp == ((it / gridDim.x) & (kFragWarps - 1)))
+                micro_item<LAYOUT>(a, it, cur.h0, cur.h1.y, base, room, goff, texb, stage, lane);
+            cur = nxt; cur_live = nxt_live; cur_issued = M2S_FRAG_BUFS > 1 && nxt_staged; buf = nbuf; nxt = nn;
+            continue;
+        }
         // ---- the item: a unit's small triangles (implicit: one block per triangle) or queued row blocks ----
         const unsigned long long first = (unsigned long long)cur.h0.x | ((unsigned long long)cur.h0.y << 32);
         const uint32_t unit = cur.h0.z, fb = cur.h1.x, fe = cur.h1.y;
@@ -1375,7 +1441,7 @@ __global__ void __launch_bounds__(kFragThreads, (LAYOUT == 1 ? 1024 : 512) / kFr
             __syncwarp();
         }
         __syncthreads();  // the span table and this staged-unit buffer may be overwritten from here on
-        cur = nxt; cur_live = nxt_live; cur_issued = M2S_FRAG_BUFS > 1 && nxt_live; buf = nbuf; nxt = nn;
+        cur = nxt; cur_live = nxt_live; cur_issued = M2S_FRAG_BUFS > 1 && nxt_staged; buf = nbuf; nxt = nn;
     }
     if (a.world > 1) {  // last CTA out tells every peer that this rank's records have landed
         __threadfence_system();
