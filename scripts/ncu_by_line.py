@@ -26,15 +26,19 @@ for l in sass:
     m = re.match(r"\s*/\*([0-9a-f]{4,})\*/", l)
     if m:
         off2line[int(m.group(1), 16)] = cur
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+kflt = "raster_kernel" if "raster" in sect else ("fragment_kernel" if "fragment" in sect else sect)
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kflt], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr = rows[1]
 ia, isrc, isamp, iex = hdr.index("Address"), hdr.index("Source"), hdr.index("# Samples"), hdr.index("Instructions Executed")
 base = int(rows[2][ia], 16)
 agg = {}
 tot_ex = tot_s = 0
+seen_hdr = 0
 for r in rows[2:]:
-    if len(r) <= iex:
+    if r and r[0] == 'Kernel Name':
+        break  # the same kernel listed again
+    if len(r) <= iex or r[ia] == 'Address':
         continue
     off = int(r[ia], 16) - base
     line = off2line.get(off, ("?", -1))
@@ -42,6 +46,8 @@ for r in rows[2:]:
     a = agg.setdefault(line, [0, 0]); a[0] += ex; a[1] += sm
     tot_ex += ex; tot_s += sm
 src = open(os.path.join(root, "mesh2splat_b200", "csrc", "m2s_kernels.cu")).read().splitlines()
+shift = int(os.environ.get('M2S_LINE_SHIFT', '0'))  # the library was built from an older source: lines moved by this much
+src = [''] * max(0, -shift) + src[max(0, shift):] if shift else src
 print(f"total warp-instr {tot_ex}  samples {tot_s}")
 for (f, ln), (ex, sm) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
     text = src[ln - 1].strip()[:90] if f == "m2s_kernels.cu" and 0 < ln <= len(src) else f

@@ -6,7 +6,7 @@ import numpy as np, torch
 from mesh2splat_b200 import synth, _abi
 from mesh2splat_b200.api import Context
 P, Rf, U = _abi.LAYOUT_PACKED56, _abi.LAYOUT_REF96, _abi.FLAG_UNCAPPED
-CONFIGS = {"helmet512": ("helmet", 512, P), "helmet512_ref96": ("helmet", 512, Rf), "dh2048": ("dh", 2048, P), "dh1024": ("dh", 1024, P),
+CONFIGS = {"helmet512": ("helmet", 512, P), "helmet512_ref96": ("helmet", 512, Rf), "dh2048": ("dh", 2048, P), "dh1024": ("dh", 1024, P), "dh512": ("dh", 512, P),
            "sphere1m": ("sphere1m", 256, P), "sponza1024": ("sponza", 1024, P), "quad64": ("quad", 64, Rf)}
 SCENES = {"helmet": lambda: synth.helmet_standin(2048), "dh": lambda: synth.damaged_helmet_standin(2048),
           "sphere1m": lambda: synth.sphere_1m(2048), "sponza": lambda: synth.sponza_standin(1024), "quad": synth.unit_quad}

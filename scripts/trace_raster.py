@@ -19,7 +19,7 @@ for i in range(5):
     out = ctx.convert(ds, R, layout, flags=_abi.FLAG_UNCAPPED, capacity=6 * R * R, out=out.data if out else None)
 t = tr.cpu().numpy().reshape(nw, 16).astype(np.float64)
 t0 = t[:, 0][t[:, 0] > 0].min()
-names = ["start", "tma_done", "setup_done", "walk1_done", "atomic_done", "walk2_done", "unit_end", "units_done", "poll_done", "drain_done", "pre_sync", "post_sync"]
+names = ["start", "tma_done", "setup_done", "walk_done", "scan_done", "flush_done", "unit_end", "units_done", "list_done", "direct_done"]
 if os.environ.get("TRACE_SETUP"):
     names += ["s:prim_loaded", "s:quat_done", "s:scale_done", "s:raster_done"]
 print(f"{which} R={R} layout={layout}: device_ms={out.device_ms:.4f} total={out.total}")
@@ -28,8 +28,10 @@ for k, n in enumerate(names):
     if len(v):
         r = (v - t0) / 1e3
         print(f"{n:12s} n={len(v):5d}  min {r.min():7.2f}  p50 {np.median(r):7.2f}  p90 {np.percentile(r, 90):7.2f}  max {r.max():7.2f} us")
-if os.environ.get("TRACE_SETUP"):
-    sys.exit(0)
+d = (t[:, 9] - t[:, 8]) / 1e3; n = t[:, 10]; m = (t[:, 9] > 0)
+if m.any():
+    print("direct shading per warp: us p50 %.2f p90 %.2f max %.2f; fragments p50 %d max %d; us per 32-fragment group p50 %.2f" % (np.median(d[m]), np.percentile(d[m], 90), d[m].max(), np.median(n[m]), n[m].max(), np.median(d[m] / np.maximum(1, np.ceil(n[m] / 32)))))
+sys.exit(0)
 it = t[:, 12]
 print("drain items/warp: mean %.1f max %d; per-item us: load %.2f setup %.2f raster+flush %.2f" % (
     it.mean(), it.max(), t[:, 13].sum() / max(it.sum(), 1) / 1e3, t[:, 14].sum() / max(it.sum(), 1) / 1e3, t[:, 15].sum() / max(it.sum(), 1) / 1e3))

@@ -18,6 +18,11 @@ POS_TOL_REL_DIAG = 1e-5
 REL_TOL = 1e-5
 COLOR_TOL = 1e-4
 NORMAL_TOL = 1e-3  # FMA-order noise is amplified by ill-conditioned TBN bases in the fuzz inputs
+# ... and by normal-map texels near (0.5, 0.5, 0.5): normalize(tex * 2 - 1) of an almost-zero vector multiplies the fp32
+# rounding of the interpolated uv (1 ulp = 1e-7 = 3e-5 texel of a 256^2 white-noise map) by up to 1/|v|.  At most this
+# fraction of the records may exceed NORMAL_TOL, and then by no more than the contract's bound (1e-2)
+NORMAL_OUTLIER_FRACTION = 2e-4
+NORMAL_TOL_OUTLIER = 1e-2
 
 
 def scene_diag(scene: _abi.Scene) -> float:
@@ -35,12 +40,16 @@ def sort_by_key(rec: np.ndarray, keys: np.ndarray):
     return rec[order], keys[order]
 
 
-def _close(a, b, rtol, atol, what):
+def _close(a, b, rtol, atol, what, outlier_fraction=0.0, outlier_atol=0.0):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     both_nan = np.isnan(a) & np.isnan(b)
     both_inf = np.isinf(a) & np.isinf(b) & (np.sign(a) == np.sign(b))
     ok = both_nan | both_inf | (np.abs(a - b) <= atol + rtol * np.abs(b))
+    if outlier_fraction and not ok.all():
+        rows_bad = np.count_nonzero(~ok.reshape(len(ok), -1).all(axis=1))
+        if rows_bad <= outlier_fraction * len(ok):
+            ok = both_nan | both_inf | (np.abs(a - b) <= outlier_atol + rtol * np.abs(b))
     if not ok.all():
         bad = np.argwhere(~ok)[0]
         raise AssertionError(f"{what}: {np.count_nonzero(~ok)} mismatches, first at {tuple(bad)}: "
@@ -68,7 +77,7 @@ def assert_records_match(scene: _abi.Scene, layout: int, got, got_keys, want, wa
         _close(g["scale"], w["scale"], REL_TOL, 1e-12, "scale")
         _close(g["rotation"], w["rotation"], REL_TOL, 1e-6, "rotation")
         _close(g["color"], w["color"], 0, COLOR_TOL, "color")
-        _close(g["normal"], w["normal"], 0, NORMAL_TOL, "normal")
+        _close(g["normal"], w["normal"], 0, NORMAL_TOL, "normal", NORMAL_OUTLIER_FRACTION, NORMAL_TOL_OUTLIER)
         _close(g["pbr"], w["pbr"], 0, COLOR_TOL, "pbr")
     elif layout == _abi.LAYOUT_PACKED56:
         _close(g["xyz"], w["xyz"], 0, POS_TOL_REL_DIAG * diag, "xyz")
@@ -78,7 +87,7 @@ def assert_records_match(scene: _abi.Scene, layout: int, got, got_keys, want, wa
         _close(_sigmoid(g["opacity"]), _sigmoid(w["opacity"]), 0, COLOR_TOL, "sigmoid(opacity)")
     elif layout in (_abi.LAYOUT_PLY_STANDARD, _abi.LAYOUT_PLY_PBR):
         _close(g["xyz"], w["xyz"], 0, POS_TOL_REL_DIAG * diag, "xyz")
-        _close(g["normal"], w["normal"], 0, NORMAL_TOL, "normal")
+        _close(g["normal"], w["normal"], 0, NORMAL_TOL, "normal", NORMAL_OUTLIER_FRACTION, NORMAL_TOL_OUTLIER)
         _close(g["f_dc"], w["f_dc"], 0, COLOR_TOL / 0.28209479177387814, "f_dc")
         _close(_sigmoid(g["opacity"]), _sigmoid(w["opacity"]), 0, COLOR_TOL, "sigmoid(opacity)")
         _close(g["scale"], w["scale"], REL_TOL, 1e-5, "scale")
@@ -95,7 +104,8 @@ def assert_records_match(scene: _abi.Scene, layout: int, got, got_keys, want, wa
         for f in ("rgba", "octa", "roughness", "metallic"):  # u8 quantisation: off by one at rounding boundaries
             d = np.abs(g[f].astype(np.int32) - w[f].astype(np.int32))
             assert d.max(initial=0) <= 1, f"{f}: max byte diff {d.max()}"
-            assert np.count_nonzero(d) <= max(4, 0.002 * d.size), f"{f}: too many byte diffs"
+            # a value within COLOR_TOL of a rounding boundary may round either way: that is 2 * COLOR_TOL * 255 of all values
+            assert np.count_nonzero(d) <= max(4, 2 * COLOR_TOL * 255 * d.size), f"{f}: too many byte diffs"
     else:
         raise ValueError(layout)
 
