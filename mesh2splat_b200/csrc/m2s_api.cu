@@ -47,17 +47,8 @@ struct VRangeSlot {        // v-range reduction of one pipeline chunk: device bu
     int* h_minmax = nullptr;     // pinned
     cudaEvent_t ev = nullptr;
 };
-// one mip level of one texture as the fragment stage samples it: a CUDA array (hardware-tiled, created with
-// cudaArrayTextureGather) and its texture object (REPEAT, unorm8 -> float, normalised coordinates)
-struct TexArray {
-    cudaArray_t arr = nullptr;
-    cudaTextureObject_t obj = 0;
-    uint32_t w = 0, h = 0;
-};
 struct m2s_ctx {
     int device = 0;
-    std::vector<TexArray> tex_pool;          // arrays of freed scenes, reused by size: steady-state uploads (m2s_convert_host
-                                             // builds and frees a device scene per call) never allocate or free an array
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     uint32_t* d_sched = nullptr;             // 8 x 128 B (one scheduler word per cache line)
@@ -105,10 +96,8 @@ struct m2s_dscene {
     DPrim* d_prims = nullptr;
     uint32_t nprims = 0;
     DTexture* d_texs = nullptr;
-    uint32_t* d_arena = nullptr;  // all mip chains of all textures, pitch-linear: upload target, mip generation, m2s_scene_read_mip
+    uint32_t* d_arena = nullptr;  // all mip chains of all textures
     uint32_t ntex = 0;
-    std::vector<TexArray> arrays; // [ntex * kMaxLevels]: what the kernels sample (filled from the arena row group by row group)
-    DTexLevel* d_texlv = nullptr;
     std::vector<DTexture> h_texs;
     std::vector<void*> allocs;
     // lazily uploaded textures (host pipeline): level-0 rows travel in groups of kTexGroupRows rows, each group brings
@@ -119,11 +108,6 @@ struct m2s_dscene {
 };
 constexpr uint32_t kTexGroupRows = 16;               // = 2^M2S_MAX_MIP_LEVEL
 
-static void destroy_tex_array(TexArray& t) {
-    if (t.obj) cudaDestroyTextureObject(t.obj);
-    if (t.arr) cudaFreeArray(t.arr);
-    t = TexArray();
-}
 static unsigned long long* g_trace = nullptr;  // debugging aid for M2S_TRACE builds (scripts/trace_raster.py)
 extern "C" __attribute__((visibility("default"))) void m2s_debug_set_trace(void* p) { g_trace = (unsigned long long*)p; }
 
@@ -238,8 +222,6 @@ M2S_EXPORT void m2s_ctx_destroy(m2s_ctx* c) {
     if (c->d_trifrag) cudaFreeAsync(c->d_trifrag, c->stream);
     if (c->d_items) cudaFreeAsync(c->d_items, c->stream);
     cudaStreamSynchronize(c->stream);
-    for (TexArray& t : c->tex_pool) destroy_tex_array(t);
-    c->tex_pool.clear();
     cudaFree(c->d_sched); cudaFree(c->d_counter); cudaFree(c->d_total); cudaFree(c->d_nitems);
     cudaFreeHost(c->h_total);
     if (c->h_status) cudaFreeHost(c->h_status);
@@ -297,50 +279,11 @@ static uint32_t mip_levels(uint32_t w, uint32_t h) {
     return std::min<uint32_t>(q, M2S_MAX_MIP_LEVEL) + 1;
 }
 
-constexpr size_t kTexPoolMax = 1024;
-
-// a w x h RGBA8 array + texture object: from the context's pool when one of that size is there
-static cudaError_t acquire_tex_array(m2s_ctx* ctx, uint32_t w, uint32_t h, TexArray* out) {
-    for (size_t i = 0; i < ctx->tex_pool.size(); ++i)
-        if (ctx->tex_pool[i].w == w && ctx->tex_pool[i].h == h) {
-            *out = ctx->tex_pool[i];
-            ctx->tex_pool[i] = ctx->tex_pool.back();
-            ctx->tex_pool.pop_back();
-            return cudaSuccess;
-        }
-    TexArray t;
-    t.w = w; t.h = h;
-    const cudaChannelFormatDesc cd = cudaCreateChannelDesc<uchar4>();
-    cudaError_t e = cudaMallocArray(&t.arr, &cd, w, h, cudaArrayTextureGather);
-    if (e != cudaSuccess) return e;
-    cudaResourceDesc rd;
-    std::memset(&rd, 0, sizeof(rd));
-    rd.resType = cudaResourceTypeArray;
-    rd.res.array.array = t.arr;
-    cudaTextureDesc td;
-    std::memset(&td, 0, sizeof(td));
-    td.addressMode[0] = td.addressMode[1] = cudaAddressModeWrap;   // GL_REPEAT (glUtils.cpp:308-309)
-    td.filterMode = cudaFilterModePoint;                            // the kernel filters itself (exact fp32 weights)
-    td.readMode = cudaReadModeNormalizedFloat;
-    td.normalizedCoords = 1;
-    e = cudaCreateTextureObject(&t.obj, &rd, &td, nullptr);
-    if (e != cudaSuccess) { cudaFreeArray(t.arr); return e; }
-    *out = t;
-    return cudaSuccess;
-}
-
-// The streams that used the scene must be idle (m2s.h): its arrays go back to the context's pool and may be
-// overwritten by the next upload.
 M2S_EXPORT void m2s_scene_free(m2s_ctx* ctx, m2s_dscene* s) {
     if (!s) return;
     if (ctx) {
         cudaSetDevice(ctx->device);
         for (void* p : s->allocs) cudaFreeAsync(p, ctx->stream);
-    }
-    for (TexArray& t : s->arrays) {
-        if (!t.arr) continue;
-        if (ctx && ctx->tex_pool.size() < kTexPoolMax) ctx->tex_pool.push_back(t);
-        else destroy_tex_array(t);
     }
     delete s;
 }
@@ -355,14 +298,6 @@ static m2s_status upload_texture_groups(m2s_ctx* ctx, m2s_dscene* d, uint32_t t,
                              cudaMemcpyHostToDevice, ctx->up));
     // level-l row j needs level-(l-1) rows 2j, 2j+1: inside the same 16-row group — all levels in one launch
     CUDA_TRY(mip_groups_launch(d->d_arena, dt, g0, std::min<uint32_t>(g1, (H + kTexGroupRows - 1) / kTexGroupRows), ctx->up));
-    // the rows of every level these groups determine -> the level's array (device-to-device, the copy tiles them)
-    for (uint32_t l = 0; l < dt.nlevels; ++l) {
-        const uint32_t per = kTexGroupRows >> l, hl = dt.h[l], wl = dt.w[l];
-        const uint32_t a0 = std::min<uint32_t>(hl, g0 * per), a1 = std::min<uint32_t>(hl, g1 * per);
-        if (a1 <= a0) continue;
-        CUDA_TRY(cudaMemcpy2DToArrayAsync(d->arrays[(size_t)t * kMaxLevels + l].arr, 0, a0, d->d_arena + dt.off[l] + (size_t)a0 * wl,
-                                          (size_t)wl * 4, (size_t)wl * 4, a1 - a0, cudaMemcpyDeviceToDevice, ctx->up));
-    }
     for (uint32_t g = g0; g < g1 && g < d->present[t].size(); ++g) d->present[t][g] = 1;
     d->h2d_bytes += (uint64_t)(r1 - r0) * W * 4;
     return M2S_OK;
@@ -544,25 +479,6 @@ static m2s_status scene_upload_impl(m2s_ctx* ctx, const m2s_scene* sc, m2s_dscen
         }
     }
     UP_TRY(dalloc((void**)&d->d_arena, arena_texels * 4));
-    d->arrays.assign((size_t)sc->texture_count * kMaxLevels, TexArray());
-    std::vector<DTexLevel> texlv((size_t)sc->texture_count * kMaxLevels + 1);  // + 1: the kernel reads entry k + 1 beside entry k
-    for (uint32_t t = 0; t < sc->texture_count; ++t)
-        for (uint32_t l = 0; l < (uint32_t)kMaxLevels; ++l) {
-            const DTexture& dt = d->h_texs[t];
-            const uint32_t ls = std::min<uint32_t>(l, dt.nlevels - 1);   // entries past the last level repeat it
-            TexArray& ta = d->arrays[(size_t)t * kMaxLevels + l];
-            if (l < dt.nlevels) UP_TRY(acquire_tex_array(ctx, dt.w[l], dt.h[l], &ta));
-            DTexLevel& e = texlv[(size_t)t * kMaxLevels + l];
-            e.obj = (unsigned long long)d->arrays[(size_t)t * kMaxLevels + ls].obj;
-            e.w = (float)dt.w[ls]; e.h = (float)dt.h[ls];
-            e.iw = 1.0f / e.w; e.ih = 1.0f / e.h;
-            e.pad = 0;
-        }
-    std::memset(&texlv.back(), 0, sizeof(DTexLevel));
-    if (texlv.size() > 1) texlv.back() = texlv[texlv.size() - 2];
-    UP_TRY(dalloc((void**)&d->d_texlv, texlv.size() * sizeof(DTexLevel)));
-    if (!texlv.empty())
-        UP_TRY(cudaMemcpyAsync(d->d_texlv, texlv.data(), texlv.size() * sizeof(DTexLevel), cudaMemcpyHostToDevice, ctx->stream));
     d->h_rgba.resize(sc->texture_count);
     d->present.resize(sc->texture_count);
     for (uint32_t t = 0; t < sc->texture_count; ++t) {
@@ -676,7 +592,7 @@ static m2s_status convert_enqueue_impl(m2s_ctx* ctx, const m2s_dscene* s, const 
     a.tri_first = (uint32_t)first;
     a.tri_count = (uint32_t)count;
     a.ranges = s->d_ranges; a.nranges = s->nranges;
-    a.prims = s->d_prims; a.nprims = s->nprims; a.texs = s->d_texs; a.tex_base = s->d_arena; a.texlv = s->d_texlv; a.ntex = s->ntex;
+    a.prims = s->d_prims; a.nprims = s->nprims; a.texs = s->d_texs; a.tex_base = s->d_arena; a.ntex = s->ntex;
     a.R = p->resolution;
     a.row_begin = std::min(p->row_begin, p->resolution);
     a.row_end = (p->row_end == 0 || p->row_end > p->resolution) ? p->resolution : p->row_end;

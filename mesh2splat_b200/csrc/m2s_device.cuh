@@ -50,20 +50,6 @@ struct DTexture {
 };
 static_assert(sizeof(DTexture) == 48, "DTexture layout");
 
-// What the fragment stage samples: one entry per (texture, mip level), indexed texture * kMaxLevels + level.  Every level
-// is a CUDA array of its own (hardware-tiled: a bilinear footprint is one or two 32-byte sectors whatever its
-// orientation) behind a texture object with REPEAT addressing, read as unorm8 -> float; the 2x2 footprint of a lookup
-// is fetched with ONE texture-gather instruction per channel and filtered in fp32 by the kernel (exact weights: the
-// texture unit's own filter has 8-bit weights).  The pitch-linear arena (DTexture) stays the source of the mip
-// generation and of m2s_scene_read_mip.
-struct DTexLevel {
-    float w, h;               // level size
-    float iw, ih;             // reciprocals                      (one 16-byte load)
-    unsigned long long obj;   // cudaTextureObject_t
-    unsigned long long pad;
-};
-static_assert(sizeof(DTexLevel) == 32, "DTexLevel layout");
-
 // One glTF primitive: the uniforms ConversionPass::conversion uploads per draw call
 // (ConversionPass.cpp:77-112).
 struct DPrim {
@@ -90,8 +76,7 @@ struct ConvertArgs {
     const DPrim* prims;
     uint32_t nprims;
     const DTexture* texs;
-    const uint32_t* tex_base;  // texture arena (mip generation, m2s_scene_read_mip)
-    const DTexLevel* texlv;    // [ntex * kMaxLevels]: what the fragment stage samples
+    const uint32_t* tex_base;  // texture arena
     uint32_t ntex;
     uint32_t R;
     uint32_t row_begin, row_end;  // pixel-row band [row_begin, row_end) of the R x R grid (whole grid: 0, R)

@@ -59,7 +59,7 @@
 #define M2S_FRAG_WARPS 4
 #endif
 #ifndef M2S_FRAG_THREADS_P56
-#define M2S_FRAG_THREADS_P56 640   // resident fragment-kernel threads per SM for PACKED56 (register cap = 65536 / this)
+#define M2S_FRAG_THREADS_P56 1024   // resident fragment-kernel threads per SM for PACKED56 (register cap = 65536 / this)
 #endif
 // (a second staged-unit buffer with the next item's TMA in flight was measured in r02: no gain, it costs a resident CTA
 // per SM and the other CTAs already hide the load — profiles/r02_ab_variants.txt; removed)
@@ -181,8 +181,12 @@ __device__ __forceinline__ f3 cross3(f3 x, f3 y) {
 // ------------------------------------------------------------------------------------------
 // per-triangle record: everything the fragment kernel needs besides the vertices
 // ------------------------------------------------------------------------------------------
+struct __align__(8) TexRef {  // 16 B — one map, resolved for one triangle
+    uint32_t off0, off1;          // texel offsets of the two mip levels in the arena; off0 == ~0u: no map
+    unsigned short w0, h0, w1, h1;
+};
 template <int NMAPS>
-struct __align__(16) TriRec {     // 176 B (1 map) / 288 B (3 maps)
+struct __align__(16) TriRec {     // 192 B (1 map) / 336 B (3 maps)
     // coverage (row spans of larger triangles, m2s_span.cuh): E_k(x,y) = E0_k + A_k (x-x0) + B_k (y-y0) at pixel centres,
     // inside <=> E_k - (edge k owns its zero set ? 0 : 1) >= 0 for all k
     long long E0[3];              // edge functions at the centre of pixel (x0, y0), the box origin
@@ -194,9 +198,10 @@ struct __align__(16) TriRec {     // 176 B (1 map) / 288 B (3 maps)
                                   // bits 4-15: x0, bits 16-27: y0 of the candidate pixel box
     unsigned first;               // small triangles of the unit before this one: their fragments (low 16 bits) and their
                                   // box rows (high 16 bits) — the triangle's place in the unit item's span table
-    unsigned tex[NMAPS];          // DTexLevel index (texture * kMaxLevels + finer level; the coarser level is the next entry); ~0u: no map
     float frac[NMAPS];            // trilinear blend per map (0 => single level)
+    TexRef tex[NMAPS];            // resolved sampler state per map
     float sx;                     // scale[0]: raw (REF96) or log(scale * sigma/R)
+    float pad_[NMAPS == 1 ? 1 : 3];
     float quat[4];                // (w,x,y,z)                                  — 16-byte aligned from here on
     float factor[4];              // u_materialFactor
     // the varyings as PLANES over the pixel grid (affine in window space, GL 4.6 eq. 14.9 with w = 1): value(x, y) =
@@ -206,7 +211,7 @@ struct __align__(16) TriRec {     // 176 B (1 map) / 288 B (3 maps)
     float plane[NMAPS == 1 ? 15 : 36];
     float sy;                     // scale[1]; the third component is a constant
 };
-static_assert(sizeof(TriRec<1>) == 176 && sizeof(TriRec<3>) == 288, "TriRec layout");
+static_assert(sizeof(TriRec<1>) == 192 && sizeof(TriRec<3>) == 336, "TriRec layout");
 static_assert(offsetof(TriRec<1>, quat) % 16 == 0 && offsetof(TriRec<1>, plane) % 16 == 0, "TriRec<1> alignment");
 static_assert(offsetof(TriRec<3>, quat) % 16 == 0 && offsetof(TriRec<3>, plane) % 16 == 0, "TriRec<3> alignment");
 constexpr unsigned kBoxSmall = 1u << 29;
@@ -244,7 +249,7 @@ struct Tables {
     const DTexture* texs;
     uint32_t nranges;
 };
-constexpr uint32_t kTableSmemBytes = 24 * 1024;
+constexpr uint32_t kTableSmemBytes = 16 * 1024;
 
 // what the raster kernel itself keeps of a triangle after the set-up (registers of the owning lane)
 struct TriSetup {
@@ -350,8 +355,10 @@ __device__ __forceinline__ uint32_t setup_triangle(const float4* __restrict__ t4
     ts.incl = incl;
     ts.w = x1 - x0 + 1; ts.h = y1 - y0 + 1;
     // the varyings as planes over the pixel grid.  lambda_k(x, y) = (E0_k + A_k (x-x0) + B_k (y-y0)) / |area2| belongs to
-    // vertex k; base / ddx / ddy of a varying are the lambda-weighted sums of its three vertex values.  fp64: the three
-    // coefficients are correctly rounded, so a fragment's value is two FMAs away from the exact affine interpolation
+    // vertex k; base / ddx / ddy of a varying are the lambda-weighted sums of its three vertex values.  fp64: for a thin
+    // triangle the box origin lies far outside it and |lambda| >> 1 — the sums cancel (an fp32 version put 5e-4 of error
+    // into positions of the golden-vector triangles); the correctly rounded coefficients themselves are benign (the
+    // varyings are affine over the whole box), so a fragment's value is two fp32 FMAs away from the exact interpolation
     {
         const double inv = 1.0 / (double)(area2 < 0 ? -area2 : area2);
         const double lb0 = (double)ts.E0[0] * inv, lb1 = (double)ts.E0[1] * inv, lb2 = (double)ts.E0[2] * inv;
@@ -424,13 +431,12 @@ __device__ __forceinline__ uint32_t setup_triangle(const float4* __restrict__ t4
     // sampler state (GL 4.6 8.14): the steps of the mesh uv are constant per triangle, so lambda, the
     // level pair and the blend fraction are too
     unsigned share = 0;
-    unsigned short sz0[4] = {0, 0, 0, 0};
-    bool has0 = false;
+    TexRef ref0;
     float frac0 = 0.f;
 #pragma unroll
     for (int m = 0; m < C::kMaps; ++m) {
-        unsigned ref = 0xffffffffu;
-        unsigned short sz[4] = {1, 1, 1, 1};
+        TexRef ref;
+        ref.off0 = 0xffffffffu; ref.off1 = 0; ref.w0 = ref.h0 = ref.w1 = ref.h1 = 1;
         float frac = 0.f;
         const int ti = pr.tex[m];
         if (ti >= 0) {
@@ -443,12 +449,13 @@ __device__ __forceinline__ uint32_t setup_triangle(const float4* __restrict__ t4
             if (!(lam > 0.0f)) { l0 = 0; }                       // magnification: LINEAR on level 0
             else if (lam >= (float)q) { l0 = q; }                 // clamped to the last level
             else { const float d = floorf(lam); l0 = (int)d; frac = lam - d; }
-            const int l1 = min(l0 + 1, q);                        // frac > 0 => l1 == l0 + 1
-            ref = (unsigned)ti * (unsigned)kMaxLevels + (unsigned)l0;
-            sz[0] = t.w[l0]; sz[1] = t.h[l0]; sz[2] = t.w[l1]; sz[3] = t.h[l1];
+            const int l1 = min(l0 + 1, q);
+            ref.off0 = t.off[l0]; ref.off1 = t.off[l1];
+            ref.w0 = t.w[l0]; ref.h0 = t.h[l0]; ref.w1 = t.w[l1]; ref.h1 = t.h[l1];
         }
-        if (m == 0) { has0 = ti >= 0; frac0 = frac; sz0[0] = sz[0]; sz0[1] = sz[1]; sz0[2] = sz[2]; sz0[3] = sz[3]; }
-        else if (ti >= 0 && has0 && sz[0] == sz0[0] && sz[1] == sz0[1] && sz[2] == sz0[2] && sz[3] == sz0[3] && frac == frac0)
+        if (m == 0) { ref0 = ref; frac0 = frac; }
+        else if (ti >= 0 && ref0.off0 != 0xffffffffu && ref.w0 == ref0.w0 && ref.h0 == ref0.h0 && ref.w1 == ref0.w1 &&
+                 ref.h1 == ref0.h1 && frac == frac0)
             share |= 1u << m;
         tf.tex[m] = ref;
         tf.frac[m] = frac;
@@ -458,99 +465,82 @@ __device__ __forceinline__ uint32_t setup_triangle(const float4* __restrict__ t4
 }
 
 // ------------------------------------------------------------------------------------------
-// sampler: RGBA8 unorm, REPEAT, bilinear within a level, linear between levels (GL 4.6 8.14; glUtils.cpp:308-313)
+// sampler: RGBA8 unorm, REPEAT, bilinear within a level, linear between levels
 // ------------------------------------------------------------------------------------------
-// Every mip level is a hardware-tiled CUDA array behind a texture object (DTexLevel).  The kernel computes the 2x2
-// footprint and its weights itself, in fp32 (the texture unit's own filter has 8-bit weights: not the arithmetic of
-// converterFS.glsl's texture() on a conformant implementation within 1e-4), and fetches the four texels of one channel
-// with ONE texture-gather instruction (SASS TLD4) addressed at the footprint's CENTRE — half a texel away from every
-// rounding decision of the unit, which also applies the REPEAT wrap and the unorm8 -> float conversion (exactly
-// b / 255, measured: scripts/probes/tex_gather_probe.cu).  Against 8 scalar loads + 32 byte extractions + 32
-// conversions per trilinear RGBA lookup this is 8 instructions, and the filter runs on Blackwell's packed fp32
-// (fma.rn.f32x2): the gather's (x, y) and (z, w) results are register pairs.
+// Blackwell's packed fp32 (fma/add/mul .f32x2, one instruction for two lanes of a 64-bit register pair): the two mip
+// levels of a trilinear lookup are the two halves of every pair below — .x = level 0, .y = level 1 — so footprint
+// set-up, byte->float conversion and the weighted sum of both levels cost what ONE level costs in scalar code.
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
+struct Bilin2 {             // the 2x2 footprints of one map on its two mip levels
+    uint32_t i00[2], i10[2], i01[2], i11[2];  // texel indices relative to the level starts
+    float2 w00, w10, w01, w11;                // weights: bilinear x 1/255 x level blend (1-f, f)
+};
 // small non-negative int -> float on the FMA pipe (no I2F): 2^23 | v is the float 2^23 + v
 __device__ __forceinline__ float u2f(uint32_t v) { return __uint_as_float(0x4B000000u | v) - 8388608.0f; }
 // floor for |x| < 2^22 on the FMA pipe: round-to-nearest of x - 0.5 via the 1.5*2^23 trick.  At exact
 // integers it may return x - 1 with fraction 1, which selects the same texels with the same weights.
-__device__ __forceinline__ float fast_floor(float x) { return ((x - 0.5f) + 12582912.0f) - 12582912.0f; }
-__device__ __forceinline__ float2 fast_floor2(float2 x) {
-    return __fadd2_rn(__fadd2_rn(__fadd2_rn(x, f2(-0.5f)), f2(12582912.0f)), f2(-12582912.0f));
+__device__ __forceinline__ float fast_floor(float x, int& i) {
+    const float t = (x - 0.5f) + 12582912.0f;
+    i = __float_as_int(t) - 0x4B400000;
+    return t - 12582912.0f;
 }
-// REPEAT in the normalised domain: uv -> [0, 1]; NaN / huge values are pinned first (fmaxf(NaN, x) = x)
+__device__ __forceinline__ float2 fast_floor2(float2 x, int& i0, int& i1) {
+    const float2 t = __fadd2_rn(__fadd2_rn(x, f2(-0.5f)), f2(12582912.0f));
+    i0 = __float_as_int(t.x) - 0x4B400000;
+    i1 = __float_as_int(t.y) - 0x4B400000;
+    return __fadd2_rn(t, f2(-12582912.0f));
+}
+// REPEAT in the normalised domain: uv -> [0, 1]; NaN / huge values are pinned first so that the texel indices below
+// can never leave the level (fmaxf(NaN, x) = x)
 __device__ __forceinline__ float wrap01(float u) {
+    int d;
     u = fminf(fmaxf(u, -1048576.0f), 1048576.0f);
-    return u - fast_floor(u);
+    return u - fast_floor(u, d);
 }
-struct Foot2 {                 // one map's footprints on its two mip levels
-    float cu[2], cv[2];        // normalised coordinates of the footprint centres
-    float2 wxy[2], wzw[2];     // weights of the gather components (x, y) = texels (x0,y1), (x1,y1) and (z, w) = (x1,y0), (x0,y0);
-                               // the level blend (1-f, f) is folded in
-};
+// the four texel indices of a footprint whose lower-left texel is (ix, iy), ix in [-1, W-1], iy in [-1, H-1]
+__device__ __forceinline__ void footprint(int ix, int iy, int W, int H, uint32_t& i00, uint32_t& i10, uint32_t& i01, uint32_t& i11) {
+    const int x0 = ix + ((ix >> 31) & W), y0 = iy + ((iy >> 31) & H);   // -1 wraps to the last texel
+    const int x1 = x0 + 1 == W ? 0 : x0 + 1, y1 = y0 + 1 == H ? 0 : y0 + 1;
+    i00 = (uint32_t)(y0 * W + x0); i10 = (uint32_t)(y0 * W + x1);
+    i01 = (uint32_t)(y1 * W + x0); i11 = (uint32_t)(y1 * W + x1);
+}
 // u, v already wrapped to [0, 1]; lw = level weights (1-f, f) (or (1, 0) for a single level)
-__device__ __forceinline__ Foot2 foot_setup2(float2 W, float2 H, float2 iW, float2 iH, float u, float v, float2 lw) {
+__device__ __forceinline__ Bilin2 bilin_setup2(const TexRef& r, float u, float v, float2 lw) {
+    const float2 W = f2(u2f(r.w0), u2f(r.w1)), H = f2(u2f(r.h0), u2f(r.h1));
     const float2 x = __ffma2_rn(f2(u), W, f2(-0.5f)), y = __ffma2_rn(f2(v), H, f2(-0.5f));
-    const float2 fx = fast_floor2(x), fy = fast_floor2(y);
+    int ix0, ix1, iy0, iy1;
+    const float2 fx = fast_floor2(x, ix0, ix1), fy = fast_floor2(y, iy0, iy1);
     const float2 ax = __ffma2_rn(fx, f2(-1.0f), x), ay = __ffma2_rn(fy, f2(-1.0f), y);
-    const float2 cu = __ffma2_rn(fx, iW, iW), cv = __ffma2_rn(fy, iH, iH);       // (floor + 1) / size: the centre of the 2x2 footprint
+    Bilin2 b;
+    footprint(ix0, iy0, (int)r.w0, (int)r.h0, b.i00[0], b.i10[0], b.i01[0], b.i11[0]);
+    footprint(ix1, iy1, (int)r.w1, (int)r.h1, b.i00[1], b.i10[1], b.i01[1], b.i11[1]);
+    const float2 k = __fmul2_rn(lw, f2(1.0f / 255.0f));
     const float2 bx = __ffma2_rn(ax, f2(-1.0f), f2(1.0f));
-    const float2 cy = __fmul2_rn(ay, lw), by = __ffma2_rn(ay, f2(-lw.x, -lw.y), lw);
-    Foot2 f;
-    f.cu[0] = cu.x; f.cu[1] = cu.y; f.cv[0] = cv.x; f.cv[1] = cv.y;
-    f.wxy[0] = __fmul2_rn(f2(bx.x, ax.x), f2(cy.x)); f.wzw[0] = __fmul2_rn(f2(ax.x, bx.x), f2(by.x));
-    f.wxy[1] = __fmul2_rn(f2(bx.y, ax.y), f2(cy.y)); f.wzw[1] = __fmul2_rn(f2(ax.y, bx.y), f2(by.y));
-    return f;
+    const float2 cy = __fmul2_rn(ay, k), by = __ffma2_rn(ay, f2(-k.x, -k.y), k);
+    b.w00 = __fmul2_rn(bx, by); b.w10 = __fmul2_rn(ax, by); b.w01 = __fmul2_rn(bx, cy); b.w11 = __fmul2_rn(ax, cy);
+    return b;
 }
-// trilinear value of one channel from its two gathers
-__device__ __forceinline__ float filt2(const Foot2& f, float4 g0, float4 g1) {
-    float2 acc = __fmul2_rn(f.wxy[0], f2(g0.x, g0.y));
-    acc = __ffma2_rn(f.wzw[0], f2(g0.z, g0.w), acc);
-    acc = __ffma2_rn(f.wxy[1], f2(g1.x, g1.y), acc);
-    acc = __ffma2_rn(f.wzw[1], f2(g1.z, g1.w), acc);
+// channel CH of the texel pair (level 0, level 1) as floats, without the conversion pipe: 0x4B000000 | byte = 2^23 + byte.
+// PRMT takes ONE immediate: with 0x4B000000 as the immediate the selector would need a register (re-materialised per
+// use: ~34 extra moves per fragment in the SASS); so the constant lives in a register the compiler cannot fold (k4b,
+// produced once per kernel by an opaque mov) and the selector is the immediate.
+__device__ __forceinline__ uint32_t opaque_4b() { uint32_t k; asm volatile("mov.u32 %0, 0x4B000000;" : "=r"(k)); return k; }
+template <int CH>
+__device__ __forceinline__ float2 tex_ch2(uint32_t t0, uint32_t t1, uint32_t k4b) {
+    uint32_t a, b;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(a) : "r"(t0), "r"(k4b), "n"(0x7440 | CH));
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(b) : "r"(t1), "r"(k4b), "n"(0x7440 | CH));
+    return __fadd2_rn(f2(__uint_as_float(a), __uint_as_float(b)), f2(-8388608.0f));
+}
+// trilinear value of channel CH: tx[0..3] = level-0 texels (00, 10, 01, 11), tx[4..7] = level-1 texels
+template <int CH>
+__device__ __forceinline__ float filt2(const Bilin2& b, const uint32_t* tx, uint32_t k4b) {
+    float2 acc = __fmul2_rn(b.w00, tex_ch2<CH>(tx[0], tx[4], k4b));
+    acc = __ffma2_rn(b.w10, tex_ch2<CH>(tx[1], tx[5], k4b), acc);
+    acc = __ffma2_rn(b.w01, tex_ch2<CH>(tx[2], tx[6], k4b), acc);
+    acc = __ffma2_rn(b.w11, tex_ch2<CH>(tx[3], tx[7], k4b), acc);
     return acc.x + acc.y;
-}
-
-// The gathers of one map: channels [C0, C1) of its two levels.  The texture unit takes ONE descriptor per instruction
-// (a uniform register): the warp visits the distinct mip-level pairs of its 32 fragments one after the other (usually
-// one or two: the same material, neighbouring triangles) — __reduce_min_sync yields a warp-uniform table index, the
-// lanes it belongs to fetch.  All 32 lanes must call (idle lanes shadow a live fragment).  A level pair none of whose
-// lanes blends (magnification, or the clamped last level) costs no second-level gathers; a lane that does not blend
-// beside lanes that do fetches the coarser level with weight 0.
-template <int C0, int C1>
-__device__ __forceinline__ bool fetch_map(const DTexLevel* __restrict__ texlv, unsigned ref, float frac, float u, float v, bool reuse,
-                                          const Foot2& ft0, Foot2& ft, float4 (&g0)[4], float4 (&g1)[4]) {
-    const bool has = ref != 0xffffffffu;
-    const bool two = has && frac > 0.0f;
-    bool pending = has;
-    for (;;) {
-        const unsigned k = __reduce_min_sync(0xffffffffu, pending ? ref : 0xffffffffu);   // warp-uniform
-        if (k == 0xffffffffu) break;
-        const DTexLevel* __restrict__ e0 = texlv + k;
-        const float4 s0 = *reinterpret_cast<const float4*>(e0), s1 = *reinterpret_cast<const float4*>(e0 + 1);  // w h 1/w 1/h  (global or shared memory)
-        const unsigned long long t0 = e0->obj, t1 = (e0 + 1)->obj;
-        const bool mine = pending && ref == k;
-        const bool two_u = __any_sync(0xffffffffu, mine && two);
-        if (mine) {
-            pending = false;
-            if (reuse) ft = ft0;  // same level sizes and blend as map 0: same footprint and weights
-            else ft = foot_setup2(f2(s0.x, s1.x), f2(s0.y, s1.y), f2(s0.z, s1.z), f2(s0.w, s1.w), u, v, f2(1.0f - frac, frac));
-            if (two_u) {
-#pragma unroll
-                for (int c = C0; c < C1; ++c) {
-                    g0[c] = tex2Dgather<float4>((cudaTextureObject_t)t0, ft.cu[0], ft.cv[0], c);
-                    g1[c] = tex2Dgather<float4>((cudaTextureObject_t)t1, ft.cu[1], ft.cv[1], c);
-                }
-            } else {
-#pragma unroll
-                for (int c = C0; c < C1; ++c) {
-                    g0[c] = tex2Dgather<float4>((cudaTextureObject_t)t0, ft.cu[0], ft.cv[0], c);
-                    g1[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            }
-        }
-    }
-    return has;
 }
 
 __device__ __forceinline__ float inv_sigmoid(float a) {  // utils.hpp:270
@@ -748,28 +738,23 @@ struct CtaQueue {
 // defined below, with the fragment kernel; the raster kernel shades the small triangles of light units itself
 template <int LAYOUT>
 __device__ __forceinline__ void shade(const ConvertArgs& a, const TriRec<RCfg<Cfg<LAYOUT>::kRK>::kMaps>& tf, int dxi, int dyi,
-                                      const DTexLevel* __restrict__ texlv, unsigned char* __restrict__ srec_bytes);
+                                      const uint32_t* __restrict__ texb, unsigned char* __restrict__ srec_bytes);
 template <int STRIDE>
 __device__ __forceinline__ void copy_span(uint8_t* dstbase, unsigned long long boff, const unsigned char* stage, uint32_t nbytes, int lane);
+template <int STRIDE>
+__device__ __forceinline__ uint32_t stage_shift(unsigned long long record_index);
 #ifndef M2S_DIRECT_MAX
 #define M2S_DIRECT_MAX 512   // a unit whose small triangles emit at most this many fragments is shaded by the raster kernel itself (<= 1024)
 #endif
-// DIRECT path: the fragments of a light unit's small triangles, listed in the unit's shared-memory slice, are shaded by
-// the raster kernel itself in groups of 32.  One slot per warp of the CTA describes its unit's groups; in a launch where
-// every warp has at most one unit (n_units <= resident warps: the BASELINE density-512 case) the records and lists stay
-// in shared memory until the kernel ends, and the warps of a CTA take groups from EACH OTHER's units (shared-memory
-// atomics) — a unit with 500 fragments beside one with 150 no longer decides when the SM is done.
-struct DirectSlot {
-    unsigned long long dfirst;    // output index (this launch) of the unit's first direct fragment
-    uint32_t t0;                  // first triangle of the unit
-    uint32_t next;                // groups taken
-    volatile uint32_t total;      // fragments; 0: not published yet; kNoDirect: nothing to take
-    uint32_t pad[3];
-};
-constexpr uint32_t kNoDirect = 0xffffffffu;
+// DIRECT path: the fragments of a light unit's small triangles, listed in the unit's shared-memory slice, are shaded
+// by the warp that rasterised them, in groups of 32 (direct_run).  Used when the warps have several units each
+// (n_units > resident warps: meshes of > 75 k triangles, where most units emit a handful of fragments and a work item
+// + a staged unit per unit would cost more than the shading); with one unit per warp the 16 warps of an SM are too
+// few to hide the latency of the shading chain and the unit goes to the fragment kernel (measured both ways, and with
+// CTA-level group stealing and software pipelining: profiles/r02_direct_path.txt).
 template <int RK>
-__device__ __noinline__ void direct_run(const ConvertArgs& a, unsigned char* smem, DirectSlot* slots, const DTexLevel* texlv, int warp, int lane,
-                                        bool steal, unsigned long long base_prev, unsigned long long room);
+__device__ __noinline__ void direct_run(const ConvertArgs& a, WarpBlock<RK>& wb, uint32_t total, unsigned long long dfirst, uint32_t t0,
+                                        unsigned long long base_prev, unsigned long long room, int lane);
 
 template <int RK>
 __global__ void __launch_bounds__(RCfg<RK>::kWarps * 32, 1) raster_kernel(const __grid_constant__ ConvertArgs a) {
@@ -805,34 +790,26 @@ __global__ void __launch_bounds__(RCfg<RK>::kWarps * 32, 1) raster_kernel(const 
 
     // descriptor tables -> shared memory (once per CTA) when they fit
     Tables tabs{a.ranges, a.prims, a.texs, a.nranges};
-    const DTexLevel* texlv = a.texlv;   // what the direct path samples through: from shared memory as well when it fits
     {
         const uint32_t br = a.nranges * (uint32_t)sizeof(DRange), bp = a.nprims * (uint32_t)sizeof(DPrim), bt = a.ntex * (uint32_t)sizeof(DTexture);
-        const uint32_t bl = (a.ntex * (uint32_t)kMaxLevels + 1u) * (uint32_t)sizeof(DTexLevel);
-        const uint32_t ol = (br + bp + bt + 15u) & ~15u;   // DTexLevel is read with 16-byte loads (DPrim is 56 bytes)
-        if (ol + bl <= kTableSmemBytes) {  // uniform across the grid
+        if (br + bp + bt <= kTableSmemBytes) {  // uniform across the grid
             unsigned char* base = smem + (size_t)C::kWarps * sizeof(WarpBlock<RK>);
-            uint32_t* dst = reinterpret_cast<uint32_t*>(base);  // word-wise: the structs are 16, 56, 48 and 32 bytes
+            uint32_t* dst = reinterpret_cast<uint32_t*>(base);  // word-wise: the structs are 16, 56 and 48 bytes
             const uint32_t* s0 = reinterpret_cast<const uint32_t*>(a.ranges);
             const uint32_t* s1 = reinterpret_cast<const uint32_t*>(a.prims);
             const uint32_t* s2 = reinterpret_cast<const uint32_t*>(a.texs);
-            const uint32_t* s3 = reinterpret_cast<const uint32_t*>(a.texlv);
-            const uint32_t n0 = br / 4, n1 = bp / 4, n2 = bt / 4, n3 = bl / 4;
+            const uint32_t n0 = br / 4, n1 = bp / 4, n2 = bt / 4;
             for (uint32_t i = threadIdx.x; i < n0 + n1 + n2; i += blockDim.x)
                 dst[i] = i < n0 ? s0[i] : (i < n0 + n1 ? s1[i - n0] : s2[i - n0 - n1]);
-            for (uint32_t i = threadIdx.x; i < n3; i += blockDim.x) dst[ol / 4 + i] = s3[i];
             tabs.ranges = reinterpret_cast<const DRange*>(base);
             tabs.prims = reinterpret_cast<const DPrim*>(base + br);
             tabs.texs = reinterpret_cast<const DTexture*>(base + br + bp);
-            texlv = reinterpret_cast<const DTexLevel*>(base + ol);
-            __syncthreads();  // the only CTA-wide barrier before the end of the kernel
+            __syncthreads();  // the only CTA-wide barrier before the direct path's hand-over
         }
     }
     CtaQueue& cq = *reinterpret_cast<CtaQueue*>(smem + (size_t)C::kWarps * sizeof(WarpBlock<RK>) + kTableSmemBytes);
-    DirectSlot* slots = reinterpret_cast<DirectSlot*>(smem + (size_t)C::kWarps * sizeof(WarpBlock<RK>) + kTableSmemBytes + sizeof(CtaQueue));
     if (threadIdx.x == 0) { cq.tail = 0; cq.head = 0; cq.active = blockDim.x >> 5; }
     if (threadIdx.x < kCtaQueueCap) cq.q[threadIdx.x].ready = 0u;
-    if (threadIdx.x < (uint32_t)C::kWarps) { slots[threadIdx.x].total = 0u; slots[threadIdx.x].next = 0u; }
     __syncthreads();
     // appended launches (m2s_convert_host pipelines a scene in triangle chunks): this launch's records follow those of
     // the earlier chunks; the cap applies to the running index, as the reference's counter does (direct path)
@@ -840,8 +817,7 @@ __global__ void __launch_bounds__(RCfg<RK>::kWarps * 32, 1) raster_kernel(const 
     for (uint32_t j = 0; j < a.nprev; ++j) base_prev += *reinterpret_cast<const volatile unsigned long long*>(a.prev_totals + j);
     const unsigned long long room = a.cap > base_prev ? a.cap - base_prev : 0ull;
     constexpr bool kDirectOK = (RK == 0 || RK == 1);
-    const bool steal = a.n_units <= nwarps_total;   // every warp has at most one unit: the CTA's warps share their direct groups
-    bool published = false;
+    const bool multi_round = a.n_units > nwarps_total;   // the warps take several units each
     uint32_t phase = 0;
     Stash st;
     st.n_it = 0; st.cur_nb = 0; st.cur_total = 0; st.frags = 0; st.slots = 0; st.seen = 0;
@@ -932,7 +908,7 @@ __global__ void __launch_bounds__(RCfg<RK>::kWarps * 32, 1) raster_kernel(const 
         // this warp shades them itself, straight from the records in its shared-memory slice — no work item, no record
         // round trip through L2, no second kernel on the critical path.  The triangle staging area (dead since the set-up)
         // is the warp's output stage then, so the next unit's triangles start flying in after the shading instead of now.
-        const bool direct = kDirectOK && a.world <= 1 && total_small != 0 && total_small <= (uint32_t)M2S_DIRECT_MAX;
+        const bool direct = kDirectOK && multi_round && a.world <= 1 && total_small != 0 && total_small <= (uint32_t)M2S_DIRECT_MAX;
         if (!direct && lane == 0 && next < a.n_units) issue_load(next);
 
         // ---- all other triangles: the warp counts one triangle at a time, one lane per pixel row; the tall triangles of
@@ -1000,22 +976,11 @@ __global__ void __launch_bounds__(RCfg<RK>::kWarps * 32, 1) raster_kernel(const 
                 __syncwarp();
                 STAMP(a, 8);
                 STAMPV(a, 10, total_small);
-                if (lane == 0) {
-                    DirectSlot& ds = slots[warp];
-                    ds.dfirst = dfirst; ds.t0 = t0; ds.next = 0u;
-                    __threadfence_block();     // the list, the records and the slot before the count
-                    ds.total = total_small;
-                }
-                published = true;
+                direct_run<RK>(a, wb, total_small, dfirst, t0, base_prev, room, lane);
+                STAMP(a, 9);
+                // the stage was written through the generic proxy: every writer fences before the TMA engine writes there again
+                fence_proxy_async();
                 __syncwarp();
-                if (!steal) {   // several units per warp: this warp shades its unit now (the slice is reused by the next unit)
-                    direct_run<RK>(a, smem, slots, texlv, warp, lane, false, base_prev, room);
-                    if (lane == 0) slots[warp].total = 0u;
-                    STAMP(a, 9);
-                    // the stage was written through the generic proxy: every writer fences before the TMA engine writes there again
-                    fence_proxy_async();
-                    __syncwarp();
-                }
                 if (lane == 0 && next < a.n_units) issue_load(next);
             }
         }
@@ -1035,15 +1000,6 @@ __global__ void __launch_bounds__(RCfg<RK>::kWarps * 32, 1) raster_kernel(const 
         STAMP(a, 6);
     }
     STAMP(a, 7);
-    if constexpr (kDirectOK) {
-        if (steal) {   // one unit per warp at most: take 32-fragment groups from any unit of the CTA, one's own first
-            if (!published && lane == 0) slots[warp].total = kNoDirect;
-            __syncwarp();
-            direct_run<RK>(a, smem, slots, texlv, warp, lane, true, base_prev, room);
-            STAMP(a, 9);
-            __syncthreads();   // the helpers below reuse their stash areas — the lists other warps may still be reading
-        }
-    }
     // ---- help: tickets on the CTA's queue until no warp of the CTA can post any more ----
     if (lane == 0) atomicSub_block(&cq.active, 1u);
     for (;;) {
@@ -1112,36 +1068,40 @@ __global__ void __launch_bounds__(RCfg<RK>::kWarps * 32, 1) raster_kernel(const 
     }
 }
 
-// A warp's staged records (shared memory, 16-byte aligned) -> one contiguous span of global memory at byte
-// offset `boff` of `dstbase`.  The widest store the destination alignment allows: 16-byte when the span starts
-// 16-byte aligned (REF96 always; PACKED56 at even record offsets), else 8-byte (strides that are multiples of 8)
-// or 4-byte pieces (the 76-byte .ply row); a sub-vector tail is copied word-wise.
+// A warp's staged records (shared memory) -> one contiguous span of global memory at byte offset `boff` of `dstbase`
+// (16-byte aligned).  Strides that are multiples of 16 (REF96, the 48-byte row): 16-byte stores throughout.  Strides
+// that are 8 mod 16 (PACKED56, the 248-byte row): a span that starts at an odd record is only 8-byte aligned — the
+// caller stages its records 8 bytes into the stage (stage_shift) so that source and destination share the misalignment:
+// one 8-byte head, a 16-byte body, one 8-byte tail.  The 76-byte row goes out in 4-byte pieces.
+template <int STRIDE>
+__device__ __forceinline__ uint32_t stage_shift(unsigned long long record_index) {
+    return (STRIDE % 16 == 8) ? (uint32_t)(record_index & 1ull) << 3 : 0u;
+}
 template <int STRIDE>
 __device__ __forceinline__ void copy_span(uint8_t* dstbase, unsigned long long boff, const unsigned char* stage, uint32_t nbytes, int lane) {
     static_assert(STRIDE % 4 == 0, "record strides are multiples of 4");
-    const uint32_t nw = nbytes / 4;
-    uint32_t done = 0;  // words copied by the vector body
-    if ((boff & 15ull) == 0) {
-        float4* dst = reinterpret_cast<float4*>(dstbase + boff);
-        const float4* src = reinterpret_cast<const float4*>(stage);
-        const uint32_t n16 = nw / 4;
+    if (nbytes == 0) return;
+    if (STRIDE % 8 == 0) {
+        uint32_t pos = 0;
+        if (STRIDE % 16 == 8) {
+            stage += (uint32_t)(boff & 8ull);   // == stage_shift of the first record
+            if (boff & 8ull) {
+                if (lane == 0) *reinterpret_cast<float2*>(dstbase + boff) = *reinterpret_cast<const float2*>(stage);
+                pos = 8;
+            }
+        }
+        const uint32_t n16 = (nbytes - pos) / 16;
+        float4* dst = reinterpret_cast<float4*>(dstbase + boff + pos);
+        const float4* src = reinterpret_cast<const float4*>(stage + pos);
 #pragma unroll
         for (int j = 0; j < (32 * STRIDE / 16 + 31) / 32; ++j) {
             const uint32_t c = lane + 32 * j;
             if (c < n16) dst[c] = src[c];
         }
-        done = n16 * 4;
-    } else if ((boff & 7ull) == 0) {
-        float2* dst = reinterpret_cast<float2*>(dstbase + boff);
-        const float2* src = reinterpret_cast<const float2*>(stage);
-        const uint32_t n8 = nw / 2;
-#pragma unroll
-        for (int j = 0; j < (32 * STRIDE / 8 + 31) / 32; ++j) {
-            const uint32_t c = lane + 32 * j;
-            if (c < n8) dst[c] = src[c];
-        }
-        done = n8 * 2;
+        pos += n16 * 16;
+        if (pos < nbytes && lane == 0) *reinterpret_cast<float2*>(dstbase + boff + pos) = *reinterpret_cast<const float2*>(stage + pos);
     } else {
+        const uint32_t nw = nbytes / 4;
         uint32_t* dst = reinterpret_cast<uint32_t*>(dstbase + boff);
         const uint32_t* src = reinterpret_cast<const uint32_t*>(stage);
 #pragma unroll
@@ -1149,10 +1109,7 @@ __device__ __forceinline__ void copy_span(uint8_t* dstbase, unsigned long long b
             const uint32_t c = lane + 32 * j;
             if (c < nw) dst[c] = src[c];
         }
-        done = nw;
     }
-    if (done + lane < nw)  // at most 3 trailing words
-        reinterpret_cast<uint32_t*>(dstbase + boff)[done + lane] = reinterpret_cast<const uint32_t*>(stage)[done + lane];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1173,7 +1130,8 @@ struct FragSmem {
     static constexpr size_t kSpanOff = kBufBytes;
     static constexpr size_t kGroupOff = kSpanOff + kSpanRows * 8;
     static constexpr size_t kStageAligned = (kGroupOff + (kMaxGroups + 1) * 2 + 15) & ~(size_t)15;
-    static constexpr size_t kBytes = kStageAligned + (size_t)kFragWarps * 32 * Cfg<LAYOUT>::kStride;
+    static constexpr size_t kWarpStage = 32 * Cfg<LAYOUT>::kStride + 16;              // + the shift of a span that starts at an odd record
+    static constexpr size_t kBytes = kStageAligned + (size_t)kFragWarps * kWarpStage;
 };
 
 __device__ __forceinline__ float inv_sigmoid_fast(float a) {  // utils.hpp:270; alpha = 1 -> +inf as in the reference
@@ -1185,15 +1143,15 @@ __device__ __forceinline__ unsigned char to_byte(float v) {
     return (unsigned char)roundf(v * 255.0f);
 }
 
-// PACKED56 in two halves, so that a warp can have the gathers of its NEXT 32 fragments in flight while it filters and
-// encodes the current ones (direct path of the raster kernel): everything a fragment needs between the halves.
+// PACKED56 in two halves, so that a warp can have the texel loads of its NEXT 32 fragments in flight while it filters
+// and encodes the current ones (direct path of the raster kernel): everything a fragment needs between the halves.
 struct Frag1 {
     float Px, Py, Pz, sy;
-    float2 wxy0, wzw0, wxy1, wzw1;   // filter weights (Foot2)
-    float4 g0[4], g1[4];             // gathers: rgba of the two levels
+    float2 w00, w10, w01, w11;   // filter weights: bilinear x 1/255 x level blend, (level 0, level 1)
+    uint32_t tx[8];              // RGBA8 texels: level-0 footprint (00, 10, 01, 11), level-1 footprint
     bool has;
 };
-__device__ __forceinline__ void shade1_fetch(const TriRec<1>& tf, int dxi, int dyi, const DTexLevel* __restrict__ texlv, Frag1& s) {
+__device__ __forceinline__ void shade1_fetch(const TriRec<1>& tf, int dxi, int dyi, const uint32_t* __restrict__ texb, Frag1& s) {
     const float2 FX = f2(u2f((uint32_t)dxi)), FY = f2(u2f((uint32_t)dyi));
     const float4* __restrict__ pl = reinterpret_cast<const float4*>(tf.plane);
     const float4 b0 = pl[0], x0 = pl[1], y0 = pl[2], b1 = pl[3];         // (Px, Py, Pz, u) planes; (v, dv/dx, dv/dy, sy)
@@ -1201,22 +1159,32 @@ __device__ __forceinline__ void shade1_fetch(const TriRec<1>& tf, int dxi, int d
     const float2 Pxy = __ffma2_rn(FY, f2(y0.x, y0.y), __ffma2_rn(FX, f2(x0.x, x0.y), f2(b0.x, b0.y)));
     s.Px = Pxy.x; s.Py = Pxy.y; s.Pz = Pzu.x; s.sy = b1.w;
     const float u = wrap01(Pzu.y), v = wrap01(fmaf(FY.x, b1.z, fmaf(FX.x, b1.y, b1.x)));
-    Foot2 ft;
-    s.has = fetch_map<0, 4>(texlv, tf.tex[0], tf.frac[0], u, v, false, ft, ft, s.g0, s.g1);
-    s.wxy0 = ft.wxy[0]; s.wzw0 = ft.wzw[0]; s.wxy1 = ft.wxy[1]; s.wzw1 = ft.wzw[1];
+    const TexRef ref = tf.tex[0];
+    s.has = ref.off0 != 0xffffffffu;
+    const float f = tf.frac[0];
+    const bool two = s.has && f > 0.0f;
+    const Bilin2 bl = bilin_setup2(ref, u, v, f2(1.0f - f, f));
+    s.w00 = bl.w00; s.w10 = bl.w10; s.w01 = bl.w01; s.w11 = bl.w11;
+    const uint32_t o0 = s.has ? ref.off0 : 0u, o1 = ref.off1;  // uniform base + 32-bit texel index
+    s.tx[0] = s.has ? __ldg(texb + (o0 + bl.i00[0])) : 0u; s.tx[1] = s.has ? __ldg(texb + (o0 + bl.i10[0])) : 0u;
+    s.tx[2] = s.has ? __ldg(texb + (o0 + bl.i01[0])) : 0u; s.tx[3] = s.has ? __ldg(texb + (o0 + bl.i11[0])) : 0u;
+    s.tx[4] = two ? __ldg(texb + (o1 + bl.i00[1])) : 0u; s.tx[5] = two ? __ldg(texb + (o1 + bl.i10[1])) : 0u;
+    s.tx[6] = two ? __ldg(texb + (o1 + bl.i01[1])) : 0u; s.tx[7] = two ? __ldg(texb + (o1 + bl.i11[1])) : 0u;
 }
-__device__ __forceinline__ float filt2s(const Frag1& s, int c) {
-    float2 acc = __fmul2_rn(s.wxy0, f2(s.g0[c].x, s.g0[c].y));
-    acc = __ffma2_rn(s.wzw0, f2(s.g0[c].z, s.g0[c].w), acc);
-    acc = __ffma2_rn(s.wxy1, f2(s.g1[c].x, s.g1[c].y), acc);
-    acc = __ffma2_rn(s.wzw1, f2(s.g1[c].z, s.g1[c].w), acc);
+template <int CH>
+__device__ __forceinline__ float filt2s(const Frag1& s, uint32_t k4b) {
+    float2 acc = __fmul2_rn(s.w00, tex_ch2<CH>(s.tx[0], s.tx[4], k4b));
+    acc = __ffma2_rn(s.w10, tex_ch2<CH>(s.tx[1], s.tx[5], k4b), acc);
+    acc = __ffma2_rn(s.w01, tex_ch2<CH>(s.tx[2], s.tx[6], k4b), acc);
+    acc = __ffma2_rn(s.w11, tex_ch2<CH>(s.tx[3], s.tx[7], k4b), acc);
     return acc.x + acc.y;
 }
 __device__ __forceinline__ float inv_sigmoid_fast(float a);
 __device__ __forceinline__ void shade1_finish(const ConvertArgs& a, const TriRec<1>& tf, const Frag1& s, unsigned char* __restrict__ srec_bytes) {
     // converterFS.glsl:55-62,99; parsers.cpp:484-499: SH0, opacity logit, log scale (per triangle)
+    const uint32_t k4b = opaque_4b();
     float cr = 1.f, cg = 1.f, cb = 1.f, ca = 1.f;
-    if (s.has) { cr = filt2s(s, 0); cg = filt2s(s, 1); cb = filt2s(s, 2); ca = filt2s(s, 3); }
+    if (s.has) { cr = filt2s<0>(s, k4b); cg = filt2s<1>(s, k4b); cb = filt2s<2>(s, k4b); ca = filt2s<3>(s, k4b); }
     const float4 q = *reinterpret_cast<const float4*>(tf.quat), fc = *reinterpret_cast<const float4*>(tf.factor);
     cr *= fc.x; cg *= fc.y; cb *= fc.z; ca *= fc.w;
     const float kInvC0 = 1.0f / 0.28209479177387814f;  // SH_COEFF0, params.hpp:17 (parsers.cpp:484-486)
@@ -1233,11 +1201,11 @@ __device__ __forceinline__ void shade1_finish(const ConvertArgs& a, const TriRec
 // One fragment: pixel (dx, dy) relative to the box origin of the triangle whose record is `tf` (shared or global memory).
 template <int LAYOUT>
 __device__ __forceinline__ void shade(const ConvertArgs& a, const TriRec<RCfg<Cfg<LAYOUT>::kRK>::kMaps>& tf, int dxi, int dyi,
-                                      const DTexLevel* __restrict__ texlv, unsigned char* __restrict__ srec_bytes) {
+                                      const uint32_t* __restrict__ texb, unsigned char* __restrict__ srec_bytes) {
     constexpr int kMaps = RCfg<Cfg<LAYOUT>::kRK>::kMaps;
     if constexpr (LAYOUT == 1) {
         Frag1 s;
-        shade1_fetch(tf, dxi, dyi, texlv, s);
+        shade1_fetch(tf, dxi, dyi, texb, s);
         shade1_finish(a, tf, s, srec_bytes);
         return;
     }
@@ -1256,22 +1224,35 @@ __device__ __forceinline__ void shade(const ConvertArgs& a, const TriRec<RCfg<Cf
     const float u = wrap01(Pzu.y), vv = wrap01(vraw);
     const unsigned meta = tf.meta;
 
-    // ---- the gathers of the albedo map (and of the normal map behind them), then the remaining varyings while they fly ----
-    float4 gA0[4], gA1[4], gN0[4], gN1[4], gM0[4], gM1[4];
-    Foot2 ftA, ftN, ftM;
-    const bool hasA = fetch_map<0, 4>(texlv, tf.tex[0], tf.frac[0], u, vv, false, ftA, ftA, gA0, gA1);
-    bool hasN = false, hasM = false;
-    if (kMaps > 1) hasN = fetch_map<0, 3>(texlv, tf.tex[kMaps > 1 ? 1 : 0], tf.frac[kMaps > 1 ? 1 : 0], u, vv, ((meta >> 1) & 1u) != 0, ftA, ftN, gN0, gN1);
-
-    // colour (converterFS.glsl:55-62,99): the level blend is part of the weights, a single-level lookup has weight 0 on
-    // the second level
-    float cr = 1.f, cg = 1.f, cb = 1.f, ca = 1.f;
-    if (hasA) {
-        cr = filt2(ftA, gA0[0], gA1[0]); cg = filt2(ftA, gA0[1], gA1[1]);
-        cb = filt2(ftA, gA0[2], gA1[2]); ca = filt2(ftA, gA0[3], gA1[3]);
+    // ---- issue every texel load of every bound map back to back ----
+    const uint32_t k4b = opaque_4b();
+    uint32_t tx[kMaps][8];
+    Bilin2 bl[kMaps];
+    bool has[kMaps];
+#pragma unroll
+    for (int m = 0; m < kMaps; ++m) {
+        if (LAYOUT == 2 && m == 2) { has[m] = false; continue; }   // the standard .ply row carries no PBR values
+        const TexRef ref = tf.tex[m];
+        has[m] = ref.off0 != 0xffffffffu;
+        const float f = tf.frac[m];
+        const bool two = has[m] && f > 0.0f;
+        if (m == 0 || !((meta >> m) & 1u)) bl[m] = bilin_setup2(ref, u, vv, f2(1.0f - f, f));
+        else bl[m] = bl[0];  // same level sizes and blend as map 0: same footprint and weights
+        const uint32_t o0 = has[m] ? ref.off0 : 0u, o1 = ref.off1;  // uniform base + 32-bit texel index
+        tx[m][0] = has[m] ? __ldg(texb + (o0 + bl[m].i00[0])) : 0u; tx[m][1] = has[m] ? __ldg(texb + (o0 + bl[m].i10[0])) : 0u;
+        tx[m][2] = has[m] ? __ldg(texb + (o0 + bl[m].i01[0])) : 0u; tx[m][3] = has[m] ? __ldg(texb + (o0 + bl[m].i11[0])) : 0u;
+        tx[m][4] = two ? __ldg(texb + (o1 + bl[m].i00[1])) : 0u; tx[m][5] = two ? __ldg(texb + (o1 + bl[m].i10[1])) : 0u;
+        tx[m][6] = two ? __ldg(texb + (o1 + bl[m].i01[1])) : 0u; tx[m][7] = two ? __ldg(texb + (o1 + bl[m].i11[1])) : 0u;
     }
-    // the metallic-roughness gathers go out once the albedo registers are free (the standard .ply row carries no PBR values)
-    if (kMaps > 2 && LAYOUT != 2) hasM = fetch_map<1, 3>(texlv, tf.tex[kMaps > 2 ? 2 : 0], tf.frac[kMaps > 2 ? 2 : 0], u, vv, ((meta >> 2) & 1u) != 0, ftA, ftM, gM0, gM1);
+    constexpr int MN = kMaps > 1 ? 1 : 0, MM = kMaps > 2 ? 2 : 0;
+    const bool hasN = kMaps > 1 && has[MN], hasM = kMaps > 2 && has[MM];
+
+    // colour (converterFS.glsl:55-62,99): the level blend is part of the weights, a single-level lookup has weight 0
+    // (and no loads) on the second level
+    float cr = 1.f, cg = 1.f, cb = 1.f, ca = 1.f;
+    if (has[0]) {
+        cr = filt2<0>(bl[0], tx[0], k4b); cg = filt2<1>(bl[0], tx[0], k4b); cb = filt2<2>(bl[0], tx[0], k4b); ca = filt2<3>(bl[0], tx[0], k4b);
+    }
     cr *= tf.factor[0]; cg *= tf.factor[1]; cb *= tf.factor[2]; ca *= tf.factor[3];
     const float kInvC0 = 1.0f / 0.28209479177387814f;  // SH_COEFF0, params.hpp:17 (parsers.cpp:484-486)
 
@@ -1280,7 +1261,7 @@ __device__ __forceinline__ void shade(const ConvertArgs& a, const TriRec<RCfg<Cf
     const float Nx = NxNy.x, Ny = NxNy.y, Nz = fmaf(FY.x, y1.w, fmaf(FX.x, x1.w, b1.w));
     float nx = Nx, ny = Ny, nz = Nz;
     if (hasN) {  // :64-77 TBN
-        const float mx = filt2(ftN, gN0[0], gN1[0]), my = filt2(ftN, gN0[1], gN1[1]), mz = filt2(ftN, gN0[2], gN1[2]);
+        const float mx = filt2<0>(bl[MN], tx[MN], k4b), my = filt2<1>(bl[MN], tx[MN], k4b), mz = filt2<2>(bl[MN], tx[MN], k4b);
         const float4 b2 = pl[6], x2 = pl[7], y2 = pl[8];                  // (Tx, Ty, Tz, Tw)
         const float2 Txy = __ffma2_rn(FY, f2(y2.x, y2.y), __ffma2_rn(FX, f2(x2.x, x2.y), f2(b2.x, b2.y)));
         const float2 Tzw = __ffma2_rn(FY, f2(y2.z, y2.w), __ffma2_rn(FX, f2(x2.z, x2.w), f2(b2.z, b2.w)));
@@ -1299,8 +1280,8 @@ __device__ __forceinline__ void shade(const ConvertArgs& a, const TriRec<RCfg<Cf
     }
     float metal = 0.1f, rough = 0.5f;  // :83-95 (.bg)
     if (hasM) {
-        rough = filt2(ftM, gM0[1], gM1[1]);
-        metal = filt2(ftM, gM0[2], gM1[2]);
+        rough = filt2<1>(bl[MM], tx[MM], k4b);
+        metal = filt2<2>(bl[MM], tx[MM], k4b);
     }
     if (LAYOUT == 0) {
         float4* s4 = reinterpret_cast<float4*>(srec_bytes);
@@ -1350,90 +1331,33 @@ __device__ __forceinline__ void shade(const ConvertArgs& a, const TriRec<RCfg<Cf
     }
 }
 
-// The direct path's worker (see DirectSlot).  steal: take groups from every unit of the CTA, starting with one's own;
-// else: this warp's own unit only.  Out of line: its registers are not the raster loop's.
+// The direct path's worker: the `total` listed fragments of this warp's unit, 32 at a time.  Out of line: its registers
+// are not the raster loop's.
 template <int RK>
-__device__ __noinline__ void direct_run(const ConvertArgs& a, unsigned char* smem, DirectSlot* slots, const DTexLevel* texlv, int warp, int lane,
-                                        bool steal, unsigned long long base_prev, unsigned long long room) {
-    using Rec = TriRec<RCfg<RK>::kMaps>;
+__device__ __noinline__ void direct_run(const ConvertArgs& a, WarpBlock<RK>& wb, uint32_t total, unsigned long long dfirst, uint32_t t0,
+                                        unsigned long long base_prev, unsigned long long room, int lane) {
     constexpr int kStride = Cfg<RK>::kStride;   // layout == raster kind for REF96 / PACKED56
-    constexpr uint32_t kW = RCfg<RK>::kWarps;
     static_assert(32 * kStride <= kUnitTris * kTriBytes, "the output stage lives in the triangle staging area");
-    WarpBlock<RK>* wbs = reinterpret_cast<WarpBlock<RK>*>(smem);
-    unsigned char* stage = reinterpret_cast<unsigned char*>(wbs[warp].tri);   // dead since the set-up of this warp's unit
-    uint32_t v = (uint32_t)warp, visited = 0, local_next = 0;
-    struct Claim { uint32_t v, g, nfr, t0; unsigned long long idx0; };
-    // the next 32-fragment group: of unit v while it has any, then of the next unit of the CTA
-    auto claim = [&](Claim& c) -> bool {
-        for (;;) {
-            if (visited >= (steal ? kW : 1u)) return false;
-            DirectSlot& sl = slots[v];
-            uint32_t tot = 0;
-            if (lane == 0) {
-                unsigned ns = 32;
-                while ((tot = sl.total) == 0u) { __nanosleep(ns); ns = min(ns * 2u, 1024u); }   // not published yet: its warp is still rasterising
-                __threadfence_block();
-            }
-            tot = __shfl_sync(0xffffffffu, tot, 0);
-            if (tot != kNoDirect) {
-                uint32_t g = local_next;
-                if (steal) {
-                    if (lane == 0) g = atomicAdd_block(&sl.next, 1u);
-                    g = __shfl_sync(0xffffffffu, g, 0);
-                } else ++local_next;
-                if (g * 32u < tot) {
-                    c.v = v; c.g = g; c.nfr = min(32u, tot - g * 32u); c.t0 = sl.t0; c.idx0 = sl.dfirst + g * 32u;
-                    return true;
-                }
-            }
-            ++visited; v = v + 1u == kW ? 0u : v + 1u; local_next = 0;
-        }
-    };
-    auto frag_of = [&](const Claim& c, uint32_t& slot, int& dxi, int& dyi) {
-        const unsigned short* list = reinterpret_cast<const unsigned short*>(wbs[c.v].pend);
-        const uint32_t e = list[c.g * 32u + min((uint32_t)lane, c.nfr - 1u)];  // idle lanes shadow the last fragment
-        slot = e & 31u; dxi = (int)((e >> 5) & 63u); dyi = (int)(e >> 11);
-    };
-    auto emit = [&](const Claim& c, uint32_t slot, int dxi, int dyi) {   // the warp's 32 staged records -> global memory
+    unsigned char* stage = reinterpret_cast<unsigned char*>(wb.tri);   // dead since the set-up of the unit
+    const unsigned short* list = reinterpret_cast<const unsigned short*>(wb.pend);
+    for (uint32_t g0 = 0; g0 < total; g0 += 32) {
+        const uint32_t nfr = min(32u, total - g0);
+        const uint32_t e = list[g0 + min((uint32_t)lane, nfr - 1u)];  // idle lanes shadow the last fragment
+        const uint32_t slot = e & 31u;
+        const int dxi = (int)((e >> 5) & 63u), dyi = (int)(e >> 11);
+        const unsigned long long idx0 = dfirst + g0;
+        shade<RK>(a, wb.rec[slot], dxi, dyi, a.tex_base, stage + stage_shift<kStride>(base_prev + idx0) + lane * kStride);
         __syncwarp();
         uint32_t nval = 0;
-        if (c.idx0 < room) nval = (uint32_t)min((unsigned long long)c.nfr, room - c.idx0);
-        copy_span<kStride>(a.out, (base_prev + c.idx0) * (unsigned long long)kStride, stage, nval * kStride, lane);
+        if (idx0 < room) nval = (uint32_t)min((unsigned long long)nfr, room - idx0);
+        copy_span<kStride>(a.out, (base_prev + idx0) * (unsigned long long)kStride, stage, nval * kStride, lane);
         if (a.keys != nullptr && (uint32_t)lane < nval) {
-            const unsigned meta = wbs[c.v].rec[slot].meta;
-            const unsigned long long tg = a.tri_first + c.t0 + slot;
-            a.keys[base_prev + c.idx0 + lane] = (tg << 24) | ((unsigned long long)(((meta >> 16) & 0xfffu) + (unsigned)dyi) << 12) |
-                                                (unsigned long long)(((meta >> 4) & 0xfffu) + (unsigned)dxi);
+            const unsigned meta = wb.rec[slot].meta;
+            const unsigned long long tg = a.tri_first + t0 + slot;
+            a.keys[base_prev + idx0 + lane] = (tg << 24) | ((unsigned long long)(((meta >> 16) & 0xfffu) + (unsigned)dyi) << 12) |
+                                              (unsigned long long)(((meta >> 4) & 0xfffu) + (unsigned)dxi);
         }
         __syncwarp();
-    };
-    if constexpr (RK == 1) {
-        // PACKED56, software-pipelined: the gathers of the next group are in flight while this one is filtered and encoded
-        Claim cA, cB;
-        Frag1 sA, sB;
-        uint32_t slotA = 0, slotB = 0;
-        int xA = 0, yA = 0, xB = 0, yB = 0;
-        bool hA = claim(cA), hB = false;
-        if (hA) { frag_of(cA, slotA, xA, yA); shade1_fetch(wbs[cA.v].rec[slotA], xA, yA, texlv, sA); }
-        while (hA) {
-            hB = claim(cB);
-            if (hB) { frag_of(cB, slotB, xB, yB); shade1_fetch(wbs[cB.v].rec[slotB], xB, yB, texlv, sB); }
-            shade1_finish(a, wbs[cA.v].rec[slotA], sA, stage + lane * kStride);
-            emit(cA, slotA, xA, yA);
-            if (!hB) break;
-            hA = claim(cA);
-            if (hA) { frag_of(cA, slotA, xA, yA); shade1_fetch(wbs[cA.v].rec[slotA], xA, yA, texlv, sA); }
-            shade1_finish(a, wbs[cB.v].rec[slotB], sB, stage + lane * kStride);
-            emit(cB, slotB, xB, yB);
-        }
-    } else {
-        Claim c;
-        while (claim(c)) {
-            uint32_t slot; int dxi, dyi;
-            frag_of(c, slot, dxi, dyi);
-            shade<RK>(a, wbs[c.v].rec[slot], dxi, dyi, texlv, stage + lane * kStride);
-            emit(c, slot, dxi, dyi);
-        }
     }
 }
 
@@ -1441,7 +1365,7 @@ __device__ __noinline__ void direct_run(const ConvertArgs& a, unsigned char* sme
 // the second copy of the shading code must not add to the register pressure of the main loop.
 template <int LAYOUT>
 __device__ __noinline__ void micro_item(const ConvertArgs& a, uint32_t it, uint4 h0, uint32_t nfr, unsigned long long base, unsigned long long room,
-                                        unsigned long long goff, const DTexLevel* __restrict__ texlv, unsigned char* stage, int lane) {
+                                        unsigned long long goff, const uint32_t* __restrict__ texb, unsigned char* stage, int lane) {
     using Rec = typename FragSmem<LAYOUT>::Rec;
     constexpr int kStride = Cfg<LAYOUT>::kStride;
     const unsigned long long first = (unsigned long long)h0.x | ((unsigned long long)h0.y << 32);
@@ -1449,7 +1373,8 @@ __device__ __noinline__ void micro_item(const ConvertArgs& a, uint32_t it, uint4
     const uint32_t w32 = __ldg(reinterpret_cast<const uint32_t*>((a.items + it)->blocks) + min((uint32_t)lane, nfr - 1u));  // idle lanes shadow the last fragment
     const uint32_t slot = w32 & 31u;
     const Rec* tfp = reinterpret_cast<const Rec*>(a.tri_frag) + (size_t)t0 + slot;
-    shade<LAYOUT>(a, *tfp, (int)((w32 >> 5) & 63u), (int)((w32 >> 11) & 63u), texlv, stage + lane * kStride);  
+    const unsigned long long mrec = a.world <= 1 ? base + first : goff + first;   // first record of the span in its destination
+    shade<LAYOUT>(a, *tfp, (int)((w32 >> 5) & 63u), (int)((w32 >> 11) & 63u), texb, stage + stage_shift<kStride>(mrec) + lane * kStride);  
     __syncwarp();
     uint32_t nval = 0;
     if (first < room) nval = (uint32_t)min((unsigned long long)nfr, room - first);
@@ -1485,7 +1410,7 @@ __global__ void __launch_bounds__(kFragThreads, (LAYOUT == 1 ? M2S_FRAG_THREADS_
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint2* span = reinterpret_cast<uint2*>(smem + S::kSpanOff);
     unsigned short* gstart = reinterpret_cast<unsigned short*>(smem + S::kGroupOff);  // span row holding fragment 32 g of the item
-    unsigned char* stage = smem + S::kStageAligned + (size_t)warp * 32 * kStride;  // this warp's 32 records
+    unsigned char* stage = smem + S::kStageAligned + (size_t)warp * S::kWarpStage;  // this warp's 32 records
     if (threadIdx.x == 0) {
         mbar_init(&bar[0], 1);
         fence_barrier_init();
@@ -1515,7 +1440,7 @@ __global__ void __launch_bounds__(kFragThreads, (LAYOUT == 1 ? M2S_FRAG_THREADS_
         goff = s_goff;
     }
     const uint32_t nitems = min(*reinterpret_cast<const volatile uint32_t*>(a.n_items_out), a.queue_cap);
-    const DTexLevel* __restrict__ texlv = a.texlv;
+    const uint32_t* __restrict__ texb = a.tex_base;
     const bool want_keys = a.keys != nullptr;
     // ---- the item pipeline: header + block list of item i+1 are loaded while item i is processed, and (2 buffers) its
     // records and vertices are already in flight (TMA) into the other staged-unit buffer ----
@@ -1556,7 +1481,7 @@ __global__ void __launch_bounds__(kFragThreads, (LAYOUT == 1 ? M2S_FRAG_THREADS_
             // records it touches — no staged unit, no span table, no CTA barrier: four consecutive micro items are in
             // flight per CTA ----
             if ((uint32_t)warp == ((it / gridDim.x) & (kFragWarps - 1)))
-                micro_item<LAYOUT>(a, it, cur.h0, cur.h1.y, base, room, goff, texlv, stage, lane);
+                micro_item<LAYOUT>(a, it, cur.h0, cur.h1.y, base, room, goff, texb, stage, lane);
             continue;
         }
         // ---- the item: a unit's small triangles (implicit: one block per triangle) or queued row blocks ----
@@ -1656,10 +1581,10 @@ __global__ void __launch_bounds__(kFragThreads, (LAYOUT == 1 ? M2S_FRAG_THREADS_
             const uint32_t slot = sw.y >> 24;
             const int dxi = (int)((sw.y & 0xfffu) + (j - sw.x)), dyi = (int)((sw.y >> 12) & 0xfffu);
             const Rec& tf = recs[slot];
-            shade<LAYOUT>(a, tf, dxi, dyi, texlv, stage + lane * kStride);  // all 32 lanes (idle ones shadow the last fragment)
+            const unsigned long long idx0 = first + j0;  // index within this launch
+            shade<LAYOUT>(a, tf, dxi, dyi, texb, stage + stage_shift<kStride>(a.world <= 1 ? base + idx0 : goff + idx0) + lane * kStride);  // all 32 lanes (idle ones shadow the last fragment)
             __syncwarp();
             // ---- the warp's records are one contiguous span: straight vector copy -----------------------
-            const unsigned long long idx0 = first + j0;  // index within this launch
             uint32_t nval = 0;
             if (idx0 < room) nval = (uint32_t)min((unsigned long long)nfr, room - idx0);
             if (a.world <= 1) {
@@ -1866,13 +1791,13 @@ __global__ void ply_rows_kernel(const float4* __restrict__ rec, unsigned long lo
 // launch wrappers used by m2s_api.cu
 // ------------------------------------------------------------------------------------------
 static int raster_kind(int layout) { return layout == 0 ? 0 : (layout == 1 ? 1 : 2); }
-static_assert(sizeof(WarpBlock<0>) * RCfg<0>::kWarps + kTableSmemBytes + sizeof(CtaQueue) + sizeof(DirectSlot) * M2S_RASTER_WARPS <= 232448 &&
-              sizeof(WarpBlock<1>) * RCfg<1>::kWarps + kTableSmemBytes + sizeof(CtaQueue) + sizeof(DirectSlot) * M2S_RASTER_WARPS <= 232448 &&
-              sizeof(WarpBlock<2>) * RCfg<2>::kWarps + kTableSmemBytes + sizeof(CtaQueue) + sizeof(DirectSlot) * M2S_RASTER_WARPS <= 232448, "raster kernel: 227 KB of shared memory per CTA");
+static_assert(sizeof(WarpBlock<0>) * RCfg<0>::kWarps + kTableSmemBytes + sizeof(CtaQueue) <= 232448 &&
+              sizeof(WarpBlock<1>) * RCfg<1>::kWarps + kTableSmemBytes + sizeof(CtaQueue) <= 232448 &&
+              sizeof(WarpBlock<2>) * RCfg<2>::kWarps + kTableSmemBytes + sizeof(CtaQueue) <= 232448, "raster kernel: 227 KB of shared memory per CTA");
 size_t raster_smem_bytes(int layout) {
     const int rk = raster_kind(layout);
     const size_t wb = rk == 0 ? sizeof(WarpBlock<0>) * RCfg<0>::kWarps : (rk == 1 ? sizeof(WarpBlock<1>) * RCfg<1>::kWarps : sizeof(WarpBlock<2>) * RCfg<2>::kWarps);
-    return wb + kTableSmemBytes + sizeof(CtaQueue) + sizeof(DirectSlot) * M2S_RASTER_WARPS;
+    return wb + kTableSmemBytes + sizeof(CtaQueue);
 }
 size_t fragment_smem_bytes(int layout) {
     switch (layout) {
