@@ -50,7 +50,7 @@
 #define M2S_RASTER_WARPS 16
 #endif
 #ifndef M2S_RASTER_WARPS_3MAP
-#define M2S_RASTER_WARPS_3MAP 12   // three-map layouts: 288-byte records, 16 warp slices would not fit in 227 KB
+#define M2S_RASTER_WARPS_3MAP 16
 #endif
 #ifndef M2S_RASTER_REGS
 #define M2S_RASTER_REGS 128
@@ -185,10 +185,14 @@ struct __align__(8) TexRef {  // 16 B — one map, resolved for one triangle
     uint32_t off0, off1;          // texel offsets of the two mip levels in the arena; off0 == ~0u: no map
     unsigned short w0, h0, w1, h1;
 };
+// Three-map layouts (REF96, the .ply rows): 176 B — the fragment stage interpolates the varyings from the staged vertices
+// with exact barycentrics (12 varyings as planes would make the record 336 B: 16 warp slices of the raster kernel would
+// no longer fit in shared memory, and 12 warps per SM need two rounds for the 70 k-triangle bench scene: measured
+// 81 vs 62 us).
 template <int NMAPS>
-struct __align__(16) TriRec {     // 192 B (1 map) / 336 B (3 maps)
-    // coverage (row spans of larger triangles, m2s_span.cuh): E_k(x,y) = E0_k + A_k (x-x0) + B_k (y-y0) at pixel centres,
-    // inside <=> E_k - (edge k owns its zero set ? 0 : 1) >= 0 for all k
+struct __align__(16) TriRec {
+    // exact barycentrics: lambda_k(x,y) = (E0_k + A_k (x-x0) + B_k (y-y0)) * inv_area  (GL 4.6 eq. 14.9, w = 1);
+    // coverage: E0_k - (edge k owns its zero set ? 0 : 1) >= 0
     long long E0[3];              // edge functions at the centre of pixel (x0, y0), the box origin
     unsigned long long hits;      // small triangles: coverage mask of the w x h box, bit = row * w + column
     int A[3];
@@ -198,22 +202,38 @@ struct __align__(16) TriRec {     // 192 B (1 map) / 336 B (3 maps)
                                   // bits 4-15: x0, bits 16-27: y0 of the candidate pixel box
     unsigned first;               // small triangles of the unit before this one: their fragments (low 16 bits) and their
                                   // box rows (high 16 bits) — the triangle's place in the unit item's span table
+    float inv_area;
+    float sx, sy;                 // scale[0..1]: raw (REF96) or log(scale * sigma/R); the third component is a constant
     float frac[NMAPS];            // trilinear blend per map (0 => single level)
+    float quat[4];                // (w,x,y,z)
+    float factor[4];              // u_materialFactor
     TexRef tex[NMAPS];            // resolved sampler state per map
-    float sx;                     // scale[0]: raw (REF96) or log(scale * sigma/R)
-    float pad_[NMAPS == 1 ? 1 : 3];
+};
+// One map (PACKED56): 192 B — the varyings the layout carries (position, uv) as PLANES over the pixel grid; the fragment
+// stage needs neither the vertices nor 64-bit arithmetic.
+template <>
+struct __align__(16) TriRec<1> {
+    long long E0[3];
+    unsigned long long hits;
+    int A[3];
+    int B[3];
+    unsigned box;
+    unsigned meta;
+    unsigned first;
+    float frac[1];
+    TexRef tex[1];
+    float sx;                     // log(scale[0] * sigma/R)
+    float pad_;
     float quat[4];                // (w,x,y,z)                                  — 16-byte aligned from here on
     float factor[4];              // u_materialFactor
-    // the varyings as PLANES over the pixel grid (affine in window space, GL 4.6 eq. 14.9 with w = 1): value(x, y) =
-    // base + (x-x0) ddx + (y-y0) ddy, stored as float4 triples {base4, ddx4, ddy4}: (Px,Py,Pz,u) [, (v,Nx,Ny,Nz), (Tx,Ty,Tz,Tw)];
-    // with one map the last triple is just (v, dv/dx, dv/dy).  Computed once per triangle in fp64 from the exact edge
-    // functions; the fragment stage needs neither the vertices nor 64-bit arithmetic
-    float plane[NMAPS == 1 ? 15 : 36];
-    float sy;                     // scale[1]; the third component is a constant
+    // value(x, y) = base + (x-x0) ddx + (y-y0) ddy (affine in window space, GL 4.6 eq. 14.9 with w = 1), stored as
+    // {base4, ddx4, ddy4} of (Px, Py, Pz, u), then (v, dv/dx, dv/dy).  Computed once per triangle in fp64 from the exact
+    // edge functions
+    float plane[15];
+    float sy;                     // log(scale[1] * sigma/R); the third component is a constant
 };
-static_assert(sizeof(TriRec<1>) == 192 && sizeof(TriRec<3>) == 336, "TriRec layout");
+static_assert(sizeof(TriRec<1>) == 192 && sizeof(TriRec<3>) == 176, "TriRec layout");
 static_assert(offsetof(TriRec<1>, quat) % 16 == 0 && offsetof(TriRec<1>, plane) % 16 == 0, "TriRec<1> alignment");
-static_assert(offsetof(TriRec<3>, quat) % 16 == 0 && offsetof(TriRec<3>, plane) % 16 == 0, "TriRec<3> alignment");
 constexpr unsigned kBoxSmall = 1u << 29;
 
 // raster kinds: what the per-triangle stage has to prepare (maps to resolve, raw or log scale)
@@ -354,12 +374,13 @@ __device__ __forceinline__ uint32_t setup_triangle(const float4* __restrict__ t4
     }
     ts.incl = incl;
     ts.w = x1 - x0 + 1; ts.h = y1 - y0 + 1;
-    // the varyings as planes over the pixel grid.  lambda_k(x, y) = (E0_k + A_k (x-x0) + B_k (y-y0)) / |area2| belongs to
+    if constexpr (C::kMaps != 1) tf.inv_area = ia;
+    // one map: the varyings as planes over the pixel grid.  lambda_k(x, y) = (E0_k + A_k (x-x0) + B_k (y-y0)) / |area2| belongs to
     // vertex k; base / ddx / ddy of a varying are the lambda-weighted sums of its three vertex values.  fp64: for a thin
     // triangle the box origin lies far outside it and |lambda| >> 1 — the sums cancel (an fp32 version put 5e-4 of error
     // into positions of the golden-vector triangles); the correctly rounded coefficients themselves are benign (the
     // varyings are affine over the whole box), so a fragment's value is two fp32 FMAs away from the exact interpolation
-    {
+    if constexpr (C::kMaps == 1) {
         const double inv = 1.0 / (double)(area2 < 0 ? -area2 : area2);
         const double lb0 = (double)ts.E0[0] * inv, lb1 = (double)ts.E0[1] * inv, lb2 = (double)ts.E0[2] * inv;
         const double lx0 = (double)ts.A[0] * inv, lx1 = (double)ts.A[1] * inv, lx2 = (double)ts.A[2] * inv;
@@ -372,14 +393,7 @@ __device__ __forceinline__ uint32_t setup_triangle(const float4* __restrict__ t4
         };
         put(0, 4, q0.x, q3.x, q6.x); put(1, 4, q0.y, q3.y, q6.y); put(2, 4, q0.z, q3.z, q6.z);   // position
         put(3, 4, q2.z, q5.z, q8.z);                                                             // u
-        if (C::kMaps == 1) {
-            put(12, 1, q2.w, q5.w, q8.w);                                                        // v
-        } else {
-            const float4 q1 = t4[1], q4 = t4[4], q7 = t4[7];
-            put(12, 4, q2.w, q5.w, q8.w);                                                        // v
-            put(13, 4, q0.w, q3.w, q6.w); put(14, 4, q1.x, q4.x, q7.x); put(15, 4, q1.y, q4.y, q7.y);   // normal
-            put(24, 4, q1.z, q4.z, q7.z); put(25, 4, q1.w, q4.w, q7.w); put(26, 4, q2.x, q5.x, q8.x); put(27, 4, q2.y, q5.y, q8.y);  // tangent
-        }
+        put(12, 1, q2.w, q5.w, q8.w);                                                            // v
     }
 
     // :399-407 rotation -> quaternion (w,x,y,z), quat_cast :131-183
@@ -737,8 +751,8 @@ struct CtaQueue {
 // ------------------------------------------------------------------------------------------
 // defined below, with the fragment kernel; the raster kernel shades the small triangles of light units itself
 template <int LAYOUT>
-__device__ __forceinline__ void shade(const ConvertArgs& a, const TriRec<RCfg<Cfg<LAYOUT>::kRK>::kMaps>& tf, int dxi, int dyi,
-                                      const uint32_t* __restrict__ texb, unsigned char* __restrict__ srec_bytes);
+__device__ __forceinline__ void shade(const ConvertArgs& a, const TriRec<RCfg<Cfg<LAYOUT>::kRK>::kMaps>& tf, const float4* __restrict__ v,
+                                      int dxi, int dyi, const uint32_t* __restrict__ texb, unsigned char* __restrict__ srec_bytes);
 template <int STRIDE>
 __device__ __forceinline__ void copy_span(uint8_t* dstbase, unsigned long long boff, const unsigned char* stage, uint32_t nbytes, int lane);
 template <int STRIDE>
@@ -816,7 +830,7 @@ __global__ void __launch_bounds__(RCfg<RK>::kWarps * 32, 1) raster_kernel(const 
     unsigned long long base_prev = 0;
     for (uint32_t j = 0; j < a.nprev; ++j) base_prev += *reinterpret_cast<const volatile unsigned long long*>(a.prev_totals + j);
     const unsigned long long room = a.cap > base_prev ? a.cap - base_prev : 0ull;
-    constexpr bool kDirectOK = (RK == 0 || RK == 1);
+    constexpr bool kDirectOK = (RK == 1);   // PACKED56: the records carry everything the shading needs
     const bool multi_round = a.n_units > nwarps_total;   // the warps take several units each
     uint32_t phase = 0;
     Stash st;
@@ -1125,8 +1139,10 @@ constexpr uint32_t kMaxGroups = 128;               // 32-fragment groups of one 
 template <int LAYOUT>
 struct FragSmem {
     using Rec = TriRec<RCfg<Cfg<LAYOUT>::kRK>::kMaps>;
-    static constexpr size_t kBufBytes = kUnitTris * sizeof(Rec);                  // one staged unit: its records (the varyings are planes in the record)
+    static constexpr bool kVerts = LAYOUT != 1;                                   // PACKED56: the varyings are planes in the record
+    static constexpr size_t kBufBytes = kUnitTris * (sizeof(Rec) + (kVerts ? kTriBytes : 0));   // one staged unit: records, then vertices
     static constexpr size_t kRecOff = 0;
+    static constexpr size_t kTriOff = kUnitTris * sizeof(Rec);
     static constexpr size_t kSpanOff = kBufBytes;
     static constexpr size_t kGroupOff = kSpanOff + kSpanRows * 8;
     static constexpr size_t kStageAligned = (kGroupOff + (kMaxGroups + 1) * 2 + 15) & ~(size_t)15;
@@ -1198,40 +1214,37 @@ __device__ __forceinline__ void shade1_finish(const ConvertArgs& a, const TriRec
     s2[6] = make_float2((cb - 0.5f) * kInvC0, inv_sigmoid_fast(ca));
 }
 
-// One fragment: pixel (dx, dy) relative to the box origin of the triangle whose record is `tf` (shared or global memory).
+// One fragment: pixel (dx, dy) relative to the box origin of the triangle whose record is `tf`; v: its 9 float4 of vertex
+// data (three-map layouts; unused by PACKED56).
 template <int LAYOUT>
-__device__ __forceinline__ void shade(const ConvertArgs& a, const TriRec<RCfg<Cfg<LAYOUT>::kRK>::kMaps>& tf, int dxi, int dyi,
-                                      const uint32_t* __restrict__ texb, unsigned char* __restrict__ srec_bytes) {
+__device__ __forceinline__ void shade(const ConvertArgs& a, const TriRec<RCfg<Cfg<LAYOUT>::kRK>::kMaps>& tf, const float4* __restrict__ v,
+                                      int dxi, int dyi, const uint32_t* __restrict__ texb, unsigned char* __restrict__ srec_bytes) {
     constexpr int kMaps = RCfg<Cfg<LAYOUT>::kRK>::kMaps;
-    if constexpr (LAYOUT == 1) {
+    if constexpr (LAYOUT == 1) {   // PACKED56: planes in the record, no vertices
         Frag1 s;
         shade1_fetch(tf, dxi, dyi, texb, s);
         shade1_finish(a, tf, s, srec_bytes);
-        return;
-    }
-    // the varyings: base + dx ddx + dy ddy, two lanes of a register pair per instruction
-    const float2 FX = f2(u2f((uint32_t)dxi)), FY = f2(u2f((uint32_t)dyi));
-    const float4* __restrict__ pl = reinterpret_cast<const float4*>(tf.plane);
-    const float4 b0 = pl[0], x0 = pl[1], y0 = pl[2];                     // (Px, Py, Pz, u)
-    const float2 Pzu = __ffma2_rn(FY, f2(y0.z, y0.w), __ffma2_rn(FX, f2(x0.z, x0.w), f2(b0.z, b0.w)));
-    const float2 Pxy = __ffma2_rn(FY, f2(y0.x, y0.y), __ffma2_rn(FX, f2(x0.x, x0.y), f2(b0.x, b0.y)));
-    const float Px = Pxy.x, Py = Pxy.y, Pz = Pzu.x;
-    float4 b1, x1, y1;                                                   // (v, Nx, Ny, Nz) — with one map: (v, dv/dx, dv/dy, sy)
-    float vraw;
-    if (kMaps == 1) { b1 = pl[3]; vraw = fmaf(FY.x, b1.z, fmaf(FX.x, b1.y, b1.x)); }
-    else { b1 = pl[3]; x1 = pl[4]; y1 = pl[5]; vraw = fmaf(FY.x, y1.x, fmaf(FX.x, x1.x, b1.x)); }
-    // uv first: the texel fetches depend on nothing else
-    const float u = wrap01(Pzu.y), vv = wrap01(vraw);
+    } else {
+    const uint32_t k4b = opaque_4b();
+    const float ia = tf.inv_area;
+    const float l0 = __ll2float_rn(tf.E0[0] + (long long)tf.A[0] * dxi + (long long)tf.B[0] * dyi) * ia;
+    const float l1 = __ll2float_rn(tf.E0[1] + (long long)tf.A[1] * dxi + (long long)tf.B[1] * dyi) * ia;
+    const float l2 = __ll2float_rn(tf.E0[2] + (long long)tf.A[2] * dxi + (long long)tf.B[2] * dyi) * ia;
+    const float2 L0 = f2(l0), L1 = f2(l1), L2 = f2(l2);
+    // vertices: 3 x {pos3 nrm3 tan4 uv2} = 9 float4 in shared memory; attribute pairs are interpolated with packed fp32
+    const float4 a2 = v[2], b2 = v[5], c2 = v[8];
+    auto lerp3 = [&](float2 A, float2 B, float2 C) { return __ffma2_rn(L2, C, __ffma2_rn(L1, B, __fmul2_rn(L0, A))); };
+    // uv first: the texel addresses depend on nothing else
+    const float2 uv = lerp3(f2(a2.z, a2.w), f2(b2.z, b2.w), f2(c2.z, c2.w));
+    const float u = wrap01(uv.x), vv = wrap01(uv.y);
     const unsigned meta = tf.meta;
 
     // ---- issue every texel load of every bound map back to back ----
-    const uint32_t k4b = opaque_4b();
     uint32_t tx[kMaps][8];
     Bilin2 bl[kMaps];
     bool has[kMaps];
 #pragma unroll
     for (int m = 0; m < kMaps; ++m) {
-        if (LAYOUT == 2 && m == 2) { has[m] = false; continue; }   // the standard .ply row carries no PBR values
         const TexRef ref = tf.tex[m];
         has[m] = ref.off0 != 0xffffffffu;
         const float f = tf.frac[m];
@@ -1244,8 +1257,11 @@ __device__ __forceinline__ void shade(const ConvertArgs& a, const TriRec<RCfg<Cf
         tx[m][4] = two ? __ldg(texb + (o1 + bl[m].i00[1])) : 0u; tx[m][5] = two ? __ldg(texb + (o1 + bl[m].i10[1])) : 0u;
         tx[m][6] = two ? __ldg(texb + (o1 + bl[m].i01[1])) : 0u; tx[m][7] = two ? __ldg(texb + (o1 + bl[m].i11[1])) : 0u;
     }
-    constexpr int MN = kMaps > 1 ? 1 : 0, MM = kMaps > 2 ? 2 : 0;
-    const bool hasN = kMaps > 1 && has[MN], hasM = kMaps > 2 && has[MM];
+    // ---- interpolate the remaining varyings while the loads are in flight ----
+    const float4 a0 = v[0], b0 = v[3], c0 = v[6];
+    const float2 Pxy = lerp3(f2(a0.x, a0.y), f2(b0.x, b0.y), f2(c0.x, c0.y));
+    const float2 PzNx = lerp3(f2(a0.z, a0.w), f2(b0.z, b0.w), f2(c0.z, c0.w));
+    const float Px = Pxy.x, Py = Pxy.y, Pz = PzNx.x;
 
     // colour (converterFS.glsl:55-62,99): the level blend is part of the weights, a single-level lookup has weight 0
     // (and no loads) on the second level
@@ -1257,14 +1273,16 @@ __device__ __forceinline__ void shade(const ConvertArgs& a, const TriRec<RCfg<Cf
     const float kInvC0 = 1.0f / 0.28209479177387814f;  // SH_COEFF0, params.hpp:17 (parsers.cpp:484-486)
 
     // ---- every other layout carries the shading normal; PBR values where the layout has them ----
-    const float2 NxNy = __ffma2_rn(FY, f2(y1.y, y1.z), __ffma2_rn(FX, f2(x1.y, x1.z), f2(b1.y, b1.z)));
-    const float Nx = NxNy.x, Ny = NxNy.y, Nz = fmaf(FY.x, y1.w, fmaf(FX.x, x1.w, b1.w));
+    constexpr int MN = kMaps > 1 ? 1 : 0, MM = kMaps > 2 ? 2 : 0;
+    const float Nx = PzNx.y;
+    const float4 a1 = v[1], b1 = v[4], c1 = v[7];
+    const float2 Nyz = lerp3(f2(a1.x, a1.y), f2(b1.x, b1.y), f2(c1.x, c1.y));
+    const float Ny = Nyz.x, Nz = Nyz.y;
     float nx = Nx, ny = Ny, nz = Nz;
-    if (hasN) {  // :64-77 TBN
+    if (has[MN]) {  // :64-77 TBN
         const float mx = filt2<0>(bl[MN], tx[MN], k4b), my = filt2<1>(bl[MN], tx[MN], k4b), mz = filt2<2>(bl[MN], tx[MN], k4b);
-        const float4 b2 = pl[6], x2 = pl[7], y2 = pl[8];                  // (Tx, Ty, Tz, Tw)
-        const float2 Txy = __ffma2_rn(FY, f2(y2.x, y2.y), __ffma2_rn(FX, f2(x2.x, x2.y), f2(b2.x, b2.y)));
-        const float2 Tzw = __ffma2_rn(FY, f2(y2.z, y2.w), __ffma2_rn(FX, f2(x2.z, x2.w), f2(b2.z, b2.w)));
+        const float2 Txy = lerp3(f2(a1.z, a1.w), f2(b1.z, b1.w), f2(c1.z, c1.w));
+        const float2 Tzw = lerp3(f2(a2.x, a2.y), f2(b2.x, b2.y), f2(c2.x, c2.y));
         const float Tx = Txy.x, Ty = Txy.y, Tz = Tzw.x, Tw = Tzw.y;
         float rx = mx * 2.0f - 1.0f, ry = my * 2.0f - 1.0f, rz = mz * 2.0f - 1.0f;
         float inv = rsqrtf(rx * rx + ry * ry + rz * rz);
@@ -1279,7 +1297,7 @@ __device__ __forceinline__ void shade(const ConvertArgs& a, const TriRec<RCfg<Cf
         nx = ox * inv; ny = oy * inv; nz = oz * inv;
     }
     float metal = 0.1f, rough = 0.5f;  // :83-95 (.bg)
-    if (hasM) {
+    if (LAYOUT != 2 && has[MM]) {      // the standard .ply row carries no PBR values
         rough = filt2<1>(bl[MM], tx[MM], k4b);
         metal = filt2<2>(bl[MM], tx[MM], k4b);
     }
@@ -1329,6 +1347,7 @@ __device__ __forceinline__ void shade(const ConvertArgs& a, const TriRec<RCfg<Cf
         const float qy = fminf(fmaxf(roundf((ry * 0.5f + 0.5f) * 255.0f), 0.0f), 255.0f);
         *reinterpret_cast<uchar4*>(p + 44) = make_uchar4((unsigned char)qx, (unsigned char)qy, to_byte(rough), to_byte(metal));
     }
+    }   // three-map layouts
 }
 
 // The direct path's worker: the `total` listed fragments of this warp's unit, 32 at a time.  Out of line: its registers
@@ -1346,7 +1365,7 @@ __device__ __noinline__ void direct_run(const ConvertArgs& a, WarpBlock<RK>& wb,
         const uint32_t slot = e & 31u;
         const int dxi = (int)((e >> 5) & 63u), dyi = (int)(e >> 11);
         const unsigned long long idx0 = dfirst + g0;
-        shade<RK>(a, wb.rec[slot], dxi, dyi, a.tex_base, stage + stage_shift<kStride>(base_prev + idx0) + lane * kStride);
+        shade<RK>(a, wb.rec[slot], nullptr, dxi, dyi, a.tex_base, stage + stage_shift<kStride>(base_prev + idx0) + lane * kStride);
         __syncwarp();
         uint32_t nval = 0;
         if (idx0 < room) nval = (uint32_t)min((unsigned long long)nfr, room - idx0);
@@ -1374,7 +1393,8 @@ __device__ __noinline__ void micro_item(const ConvertArgs& a, uint32_t it, uint4
     const uint32_t slot = w32 & 31u;
     const Rec* tfp = reinterpret_cast<const Rec*>(a.tri_frag) + (size_t)t0 + slot;
     const unsigned long long mrec = a.world <= 1 ? base + first : goff + first;   // first record of the span in its destination
-    shade<LAYOUT>(a, *tfp, (int)((w32 >> 5) & 63u), (int)((w32 >> 11) & 63u), texb, stage + stage_shift<kStride>(mrec) + lane * kStride);  
+    shade<LAYOUT>(a, *tfp, a.tris + ((size_t)a.tri_first + t0 + slot) * 9, (int)((w32 >> 5) & 63u), (int)((w32 >> 11) & 63u), texb,
+                  stage + stage_shift<kStride>(mrec) + lane * kStride);  
     __syncwarp();
     uint32_t nval = 0;
     if (first < room) nval = (uint32_t)min((unsigned long long)nfr, room - first);
@@ -1463,11 +1483,12 @@ __global__ void __launch_bounds__(kFragThreads, (LAYOUT == 1 ? M2S_FRAG_THREADS_
     auto issue = [&](const Hdr& h, uint32_t buf) {  // thread 0: stage the unit's records: one TMA bulk copy
         const uint32_t t0 = h.h0.z * a.unit_tris;
         const uint32_t ntri = min(a.unit_tris, a.tri_count - t0);
-        const uint32_t rb = ntri * (uint32_t)sizeof(Rec);
+        const uint32_t rb = ntri * (uint32_t)sizeof(Rec), tb = S::kVerts ? ntri * (uint32_t)kTriBytes : 0u;
         unsigned char* dst = smem + (size_t)buf * S::kBufBytes;
         fence_proxy_async();
-        mbar_arrive_expect_tx(&bar[buf], rb);
+        mbar_arrive_expect_tx(&bar[buf], rb + tb);
         tma_load_1d(dst + S::kRecOff, a.tri_frag + (size_t)t0 * sizeof(Rec), rb, &bar[buf]);
+        if (S::kVerts) tma_load_1d(dst + S::kTriOff, reinterpret_cast<const unsigned char*>(a.tris) + ((size_t)a.tri_first + t0) * kTriBytes, tb, &bar[buf]);
     };
     uint32_t phase = 0;   // parity of the next completion of the staging barrier
     constexpr uint32_t buf = 0;
@@ -1494,6 +1515,7 @@ __global__ void __launch_bounds__(kFragThreads, (LAYOUT == 1 ? M2S_FRAG_THREADS_
         const uint32_t ntri = min(a.unit_tris, a.tri_count - t0);
         if (threadIdx.x == 0) issue(cur, 0);
         const Rec* recs = reinterpret_cast<const Rec*>(smem + S::kRecOff);
+        const float4* tris = reinterpret_cast<const float4*>(smem + S::kTriOff);
         mbar_wait(&bar[buf], phase);
         phase ^= 1u;
         // ---- the item's span table: one entry per pixel row, fragments-before-the-row ascending ----
@@ -1582,7 +1604,7 @@ __global__ void __launch_bounds__(kFragThreads, (LAYOUT == 1 ? M2S_FRAG_THREADS_
             const int dxi = (int)((sw.y & 0xfffu) + (j - sw.x)), dyi = (int)((sw.y >> 12) & 0xfffu);
             const Rec& tf = recs[slot];
             const unsigned long long idx0 = first + j0;  // index within this launch
-            shade<LAYOUT>(a, tf, dxi, dyi, texb, stage + stage_shift<kStride>(a.world <= 1 ? base + idx0 : goff + idx0) + lane * kStride);  // all 32 lanes (idle ones shadow the last fragment)
+            shade<LAYOUT>(a, tf, tris + slot * 9, dxi, dyi, texb, stage + stage_shift<kStride>(a.world <= 1 ? base + idx0 : goff + idx0) + lane * kStride);  // all 32 lanes (idle ones shadow the last fragment)
             __syncwarp();
             // ---- the warp's records are one contiguous span: straight vector copy -----------------------
             uint32_t nval = 0;
