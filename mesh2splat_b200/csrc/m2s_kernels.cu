@@ -380,6 +380,7 @@ __device__ __forceinline__ uint32_t setup_triangle(const float4* __restrict__ t4
     // triangle the box origin lies far outside it and |lambda| >> 1 — the sums cancel (an fp32 version put 5e-4 of error
     // into positions of the golden-vector triangles); the correctly rounded coefficients themselves are benign (the
     // varyings are affine over the whole box), so a fragment's value is two fp32 FMAs away from the exact interpolation
+#ifndef M2S_EXP_NOPLANES   // timing experiment only: no planes (wrong output)
     if constexpr (C::kMaps == 1) {
         const double inv = 1.0 / (double)(area2 < 0 ? -area2 : area2);
         const double lb0 = (double)ts.E0[0] * inv, lb1 = (double)ts.E0[1] * inv, lb2 = (double)ts.E0[2] * inv;
@@ -395,6 +396,7 @@ __device__ __forceinline__ uint32_t setup_triangle(const float4* __restrict__ t4
         put(3, 4, q2.z, q5.z, q8.z);                                                             // u
         put(12, 1, q2.w, q5.w, q8.w);                                                            // v
     }
+#endif
 
     // :399-407 rotation -> quaternion (w,x,y,z), quat_cast :131-183
     {
@@ -778,6 +780,7 @@ __global__ void __launch_bounds__(RCfg<RK>::kWarps * 32, 1) raster_kernel(const 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpBlock<RK>& wb = *reinterpret_cast<WarpBlock<RK>*>(smem + (size_t)warp * sizeof(WarpBlock<RK>));
     const unsigned char* tri_bytes = reinterpret_cast<const unsigned char*>(a.tris);
+    STAMP(a, 11);
 
 #ifdef M2S_EARLY_TRIGGER
     // PDL early trigger: one fragment-kernel CTA per SM becomes resident beside this CTA (37 KB of shared memory are
@@ -818,19 +821,22 @@ __global__ void __launch_bounds__(RCfg<RK>::kWarps * 32, 1) raster_kernel(const 
             tabs.ranges = reinterpret_cast<const DRange*>(base);
             tabs.prims = reinterpret_cast<const DPrim*>(base + br);
             tabs.texs = reinterpret_cast<const DTexture*>(base + br + bp);
-            __syncthreads();  // the only CTA-wide barrier before the direct path's hand-over
         }
     }
     CtaQueue& cq = *reinterpret_cast<CtaQueue*>(smem + (size_t)C::kWarps * sizeof(WarpBlock<RK>) + kTableSmemBytes);
     if (threadIdx.x == 0) { cq.tail = 0; cq.head = 0; cq.active = blockDim.x >> 5; }
     if (threadIdx.x < kCtaQueueCap) cq.q[threadIdx.x].ready = 0u;
-    __syncthreads();
+    __syncthreads();  // tables + help queue: the only CTA-wide barrier before the end of the kernel
     // appended launches (m2s_convert_host pipelines a scene in triangle chunks): this launch's records follow those of
     // the earlier chunks; the cap applies to the running index, as the reference's counter does (direct path)
     unsigned long long base_prev = 0;
     for (uint32_t j = 0; j < a.nprev; ++j) base_prev += *reinterpret_cast<const volatile unsigned long long*>(a.prev_totals + j);
     const unsigned long long room = a.cap > base_prev ? a.cap - base_prev : 0ull;
+    #ifndef M2S_EXP_NODIRECT
     constexpr bool kDirectOK = (RK == 1);   // PACKED56: the records carry everything the shading needs
+#else
+    constexpr bool kDirectOK = false;
+#endif
     const bool multi_round = a.n_units > nwarps_total;   // the warps take several units each
     uint32_t phase = 0;
     Stash st;
@@ -1028,7 +1034,7 @@ __global__ void __launch_bounds__(RCfg<RK>::kWarps * 32, 1) raster_kernel(const 
                 if (*reinterpret_cast<volatile uint32_t*>(&cq.tail) > t) { have = true; break; }
                 if (*reinterpret_cast<volatile uint32_t*>(&cq.active) == 0 && *reinterpret_cast<volatile uint32_t*>(&cq.tail) <= t) break;
                 __nanosleep(ns);
-                ns = min(ns * 2u, 2048u);
+                ns = min(ns * 2u, 256u);
             }
             if (have) while (cq.q[t].ready == 0u) __nanosleep(20);
             __threadfence_block();
@@ -1043,9 +1049,12 @@ __global__ void __launch_bounds__(RCfg<RK>::kWarps * 32, 1) raster_kernel(const 
         stash_close_item<RK>(a, wb, eu, st, lane);
         stash_flush<RK>(a, wb, eu, st, lane);
     }
+    STAMP(a, 12);
     if (lane == 0) tma_store_wait_all();  // record stores are complete (not just read) before the kernel ends
+    STAMP(a, 13);
     // ---- last CTA out publishes the counts and re-arms the scheduler for the next launch ---------
     __syncthreads();
+    STAMP(a, 14);
     if (warp == 0) {
         uint32_t last = 0;
         unsigned long long tot = 0;
@@ -1459,16 +1468,15 @@ __global__ void __launch_bounds__(kFragThreads, (LAYOUT == 1 ? M2S_FRAG_THREADS_
         __syncthreads();
         goff = s_goff;
     }
-    const uint32_t nitems = min(*reinterpret_cast<const volatile uint32_t*>(a.n_items_out), a.queue_cap);
     const uint32_t* __restrict__ texb = a.tex_base;
     const bool want_keys = a.keys != nullptr;
     // ---- the item pipeline: header + block list of item i+1 are loaded while item i is processed, and (2 buffers) its
     // records and vertices are already in flight (TMA) into the other staged-unit buffer ----
     struct Hdr { uint4 h0; uint2 h1; uint2 blk; };
-    auto load_hdr = [&](uint32_t it) {
+    auto load_hdr = [&](uint32_t it, uint32_t bound) {
         Hdr h;
         h.h0 = make_uint4(0, 0, 0, 0); h.h1 = make_uint2(0, 0); h.blk = make_uint2(0xffffffffu, 0);
-        if (it < nitems) {
+        if (it < bound) {
             const FragItem* q = a.items + it;
             h.h0 = __ldg(reinterpret_cast<const uint4*>(q));
             h.h1 = __ldg(reinterpret_cast<const uint2*>(q) + 2);
@@ -1494,8 +1502,11 @@ __global__ void __launch_bounds__(kFragThreads, (LAYOUT == 1 ? M2S_FRAG_THREADS_
     constexpr uint32_t buf = 0;
     // one header in flight per CTA: the other resident CTAs of the SM hide the load (a software pipeline over the queue
     // was measured: no gain, 16 more registers in the shading loop)
-    for (uint32_t it = blockIdx.x; it < nitems; it += gridDim.x) {
-        const Hdr cur = load_hdr(it);
+    // the first header is loaded together with the item count (one global round trip instead of two before the first
+    // TMA): whatever an unused queue slot holds is discarded by the loop condition
+    Hdr cur = load_hdr(blockIdx.x, a.queue_cap);
+    const uint32_t nitems = min(*reinterpret_cast<const volatile uint32_t*>(a.n_items_out), a.queue_cap);
+    for (uint32_t it = blockIdx.x; it < nitems; it += gridDim.x, cur = load_hdr(it, nitems)) {
         if (!live(cur)) continue;
         if (cur.h0.w & kItMicro) {
             // ---- micro item: <= 32 fragments listed in the item; ONE warp (round robin) shades it with direct loads of the

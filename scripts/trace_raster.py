@@ -18,8 +18,8 @@ for i in range(5):
     tr.zero_()
     out = ctx.convert(ds, R, layout, flags=_abi.FLAG_UNCAPPED, capacity=6 * R * R, out=out.data if out else None)
 t = tr.cpu().numpy().reshape(nw, 16).astype(np.float64)
-t0 = t[:, 0][t[:, 0] > 0].min()
-names = ["start", "tma_done", "setup_done", "walk_done", "scan_done", "flush_done", "unit_end", "units_done", "list_done", "direct_done"]
+t0 = t[:, 11][t[:, 11] > 0].min() if (t[:, 11] > 0).any() else t[:, 0][t[:, 0] > 0].min()
+names = ["start", "tma_done", "setup_done", "walk_done", "scan_done", "flush_done", "unit_end", "units_done", "list_done", "direct_done", "-", "kernel_entry", "help_done", "stores_done", "cta_synced"]
 if os.environ.get("TRACE_SETUP"):
     names += ["s:prim_loaded", "s:quat_done", "s:scale_done", "s:raster_done"]
 print(f"{which} R={R} layout={layout}: device_ms={out.device_ms:.4f} total={out.total}")
