@@ -820,7 +820,12 @@ M2S_EXPORT m2s_status m2s_convert_host(m2s_ctx* ctx, const m2s_scene* sc, const 
     // one chunk of look-ahead keeps the copy engine busy while the host waits for a v-range: the stream sees
     // tris0 tris1 | rows0 kernels0 | tris2 | rows1 kernels1 | ... and the first records exist after ~2/nchunks of the
     // triangles and 1/nchunks of the texture rows
-    for (; uploaded < std::min(planned, 2); ++uploaded) {
+    // look-ahead: how many triangle chunks are queued before the first chunk's texture rows.  All of them (default): the
+    // copy queue never runs dry while the host waits for a v-range, and the v-ranges of the later chunks are on the host
+    // long before they are needed — every extra chunk then only shortens the tail (the last chunk's download)
+    int lookahead = planned;
+    if (const char* e = std::getenv("M2S_HOST_LOOKAHEAD")) lookahead = std::max(1, std::atoi(e));
+    for (; uploaded < std::min(planned, lookahead); ++uploaded) {
         st = upload_tris(uploaded);
         if (st != M2S_OK) return fail_with(st);
     }

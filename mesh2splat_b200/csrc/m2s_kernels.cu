@@ -2,8 +2,8 @@
 //
 // Two kernels on one stream replace the reference's geometry shader, fixed-function rasteriser, fragment shader
 // and SSBO atomic append (converter{GS,FS}.glsl, ConversionPass.cpp:114-116).  The second kernel is launched with
-// programmatic dependent launch.  What crosses between them is small and stays in the 126 MB L2: one 144-176 B
-// record per triangle, 16 B per work unit, 288 B per queued work item — never anything per fragment.
+// programmatic dependent launch.  What crosses between them is small and stays in the 126 MB L2: one 176-192 B
+// record per triangle, 288 B per queued work item — never anything per fragment.
 //
 // raster_kernel — per-TRIANGLE work: set-up and COUNTING (persistent, one CTA per SM, every warp an autonomous
 // pipeline; one __syncthreads after the descriptor tables are copied to shared memory, none in the steady state)
@@ -25,16 +25,20 @@
 //       fragments is cut into several items — a 2-triangle quad at R = 2048 becomes 4096 items for the
 //       whole GPU, while its raster work is 128 warp steps
 //   the unit's records leave shared memory as ONE TMA bulk store (cp.async.bulk.global.shared::cta)
+//   PACKED56 records also carry the varyings the layout needs (position, uv) as PLANES over the pixel grid (fp64
+//     coefficients from the exact edge functions): the fragment stage needs neither the vertices nor 64-bit arithmetic
+//   DIRECT path (PACKED56, launches where the warps take several units each): the small triangles of a light unit are
+//     shaded by the warp that rasterised them, straight from the records in its shared-memory slice (direct_run)
 // fragment_kernel — per-FRAGMENT work (converterFS.glsl:44-104); a CTA of 4 warps takes one work item:
-//   TMA stages the unit's records and its 144 B/triangle vertices into shared memory (one mbarrier), every
+//   TMA stages the unit's records (three-map layouts: and its 144 B/triangle vertices) into shared memory, every
 //   warp rebuilds the row spans of its share of the item's blocks (mask rows / m2s_span.cuh) into a prefix
-//   table; then a warp takes 32 consecutive fragments = 32 consecutive output records: two 5-step searches
-//   (block by shuffle, row in shared memory) give (triangle, x, y); exact barycentrics from the int64 edge
-//   functions, attributes from the staged vertices, all texel loads of all bound maps issued back to back,
+//   table; then a warp takes 32 consecutive fragments = 32 consecutive output records: a search between the group's
+//   first and last row gives (triangle, x, y); varyings from the planes (PACKED56) or from the staged vertices with
+//   exact barycentrics (REF96, .ply rows); all texel loads of all bound maps issued back to back,
 //   trilinear filter on the FMA pipe (u8->f32 by PRMT+FADD), TBN normal, encode (REF96 / PACKED56 / the three
 //   .ply row formats directly); the 32 records are transposed through shared memory and written as one
-//   contiguous span (16-byte stores when aligned) — locally, or into every rank's final buffer over NVLink
-//   (fused multi-GPU gather), or after the earlier chunks' records (appended launches of the host path).
+//   contiguous span (16-byte body whatever the alignment of the span) — locally, or into every rank's final buffer
+//   over NVLink (fused multi-GPU gather), or after the earlier chunks' records (appended launches of the host path).
 //
 // Bit-exactness: every float operation of the per-triangle stage is written with __f*_rn intrinsics in the
 // operation order of the oracle (and of GLM, which the reference's GLSL-as-C++ build uses): coverage is

@@ -40,6 +40,31 @@ tu, td, tb = timed(up), timed(down), timed(both)
 print(f"H2D {up_mb} MiB: {tu:.3f} ms ({up_mb * 1.048576 / tu:.1f} GB/s)   D2H {down_mb} MiB: {td:.3f} ms ({down_mb * 1.048576 / td:.1f} GB/s)"
       f"   concurrent: {tb:.3f} ms (sum {tu + td:.3f}, max {max(tu, td):.3f})")
 
+# one direction split over several streams (several copy engines): does the link carry more than one engine delivers?
+for n in (2, 4):
+    ss = [torch.cuda.Stream(dev) for _ in range(n)]
+    def up_split():
+        step = (up_mb << 20) // n
+        for i, st in enumerate(ss):
+            with torch.cuda.stream(st):
+                d_up[i * step:(i + 1) * step].copy_(h_up[i * step:(i + 1) * step], non_blocking=True)
+    t = timed(up_split)
+    print(f"H2D {up_mb} MiB over {n} streams: {t:.3f} ms ({up_mb * 1.048576 / t:.1f} GB/s)")
+# page-locked by cudaHostRegister instead of cudaHostAlloc, and write-combined
+try:
+    rt = torch.cuda.cudart()
+    import ctypes
+    lib = ctypes.CDLL("libcudart.so.12")
+    pwc = ctypes.c_void_p()
+    if lib.cudaHostAlloc(ctypes.byref(pwc), ctypes.c_size_t(up_mb << 20), ctypes.c_uint(4)) == 0:  # cudaHostAllocWriteCombined
+        ctypes.memset(pwc, 1, up_mb << 20)
+        def up_wc():
+            lib.cudaMemcpyAsync(ctypes.c_void_p(d_up.data_ptr()), pwc, ctypes.c_size_t(up_mb << 20), ctypes.c_int(1), ctypes.c_void_p(s1.cuda_stream))
+        t = timed(up_wc)
+        print(f"H2D {up_mb} MiB from write-combined memory: {t:.3f} ms ({up_mb * 1.048576 / t:.1f} GB/s)")
+except Exception as e:  # noqa: BLE001
+    print("write-combined probe unavailable:", e)
+
 if len(sys.argv) > 1 and sys.argv[1] == "host":
     os.environ["M2S_HOST_TRACE"] = "1"
     import numpy as np

@@ -455,6 +455,36 @@ def test_config4_million_triangle_sphere(gpu_ctx):
     ds.free()
 
 
+def test_direct_path_and_queue_path_write_the_same_records(gpu_ctx):
+    """PACKED56 has two routes for the small triangles of a light work unit: in a launch where the warps take several
+    units each (here: 200 000 triangles in one call) the raster kernel shades them itself (direct path); with at most one
+    unit per warp (here: the same triangles in ranges of 25 000) they are queued for the fragment kernel.  Both run the
+    same shading code on the same per-triangle records: the two results must be the same multiset of records, bit for
+    bit, with the same fragment identities — and the whole thing must agree with the oracle."""
+    tri = synth.displaced_sphere(500, 200, seed=11, amplitude=0.04)
+    s = Scene(tri, [Primitive(0, len(tri), (0.9, 1.0, 0.8, 1.0), 0, -1, -1)], synth.make_material_textures(256, 6)[:1])
+    s.compute_bboxes()
+    R = 384
+    ds = gpu_ctx.upload(s)
+    whole = gpu_ctx.convert(ds, R, LAYOUT_PACKED56, flags=FLAG_UNCAPPED, capacity=6 * R * R, want_keys=True)
+    a, ak = whole.numpy().copy(), whole.keys_numpy().copy()
+    parts, pk = [], []
+    step = 25_000
+    for first in range(0, s.triangle_count, step):
+        o = gpu_ctx.convert(ds, R, LAYOUT_PACKED56, flags=FLAG_UNCAPPED, capacity=6 * R * R, want_keys=True, first_triangle=first,
+                            triangle_count=min(step, s.triangle_count - first))
+        parts.append(o.numpy().copy()); pk.append(o.keys_numpy().copy())
+    ds.free()
+    b, bk = np.concatenate(parts), np.concatenate(pk)
+    assert len(a) == len(b) > 100_000
+    oa, ob = np.argsort(ak, kind="stable"), np.argsort(bk, kind="stable")
+    assert np.array_equal(ak[oa], bk[ob])
+    assert a[oa].tobytes() == b[ob].tobytes(), "direct path and fragment-kernel path disagree"
+    rec, keys, total = oracle.convert(s, R, LAYOUT_PACKED56, flags=FLAG_UNCAPPED, capacity=6 * R * R, want_keys=True)
+    assert total == len(a)
+    assert_records_match(s, LAYOUT_PACKED56, a, ak, rec, keys)
+
+
 # ---- BASELINE config 5: density sweep on the DamagedHelmet stand-in ---------------------------------------------
 @pytest.mark.parametrize("R", [64, 128, 256, 512, 1024, 2048])
 def test_config5_damaged_helmet_density_sweep(gpu_ctx, R):
