@@ -23,6 +23,7 @@ cudaError_t gather_wait_launch(const unsigned long long* xch, uint32_t world, un
 cudaError_t mip_groups_launch(uint32_t* arena, const DTexture& t, uint32_t g0, uint32_t g1, cudaStream_t stream);
 cudaError_t vrange_launch(const float4* tris, uint32_t first, uint32_t count, const DRange* ranges, uint32_t nranges, const DPrim* prims,
                           uint32_t ntex, int* minmax, cudaStream_t stream);
+cudaError_t vrange_publish_launch(int* minmax, uint32_t ntex, int* host, unsigned long long* host_tag, unsigned long long tag, cudaStream_t stream);
 cudaError_t ply_rows_launch(const void* ref96, unsigned long long count, const unsigned long long* d_count,
                             uint32_t format, float mult, void* rows, cudaStream_t stream);
 // host-side helpers implemented in m2s_host.cpp
@@ -43,9 +44,13 @@ using namespace m2s;
     } while (0)
 
 struct VRangeSlot {        // v-range reduction of one pipeline chunk: device buffer + pinned host copy + "copy done" event
-    int* d_minmax = nullptr;     // [2 * ntex]: sortable-int min | max of v per texture, then 1 non-finite flag
-    int* h_minmax = nullptr;     // pinned
-    cudaEvent_t ev = nullptr;
+    int* d_minmax = nullptr;     // [2 * ntex]: sortable-int min | max of v per texture, then 1 non-finite flag (armed: see vrange_publish_kernel)
+    int* h_minmax = nullptr;     // pinned + mapped: written by the publish kernel, followed (8-byte aligned) by the tag
+    int* h_minmax_dev = nullptr; // its device view
+    unsigned long long* h_tag = nullptr;      // host view of the tag
+    unsigned long long* h_tag_dev = nullptr;
+    unsigned long long tag = 0;               // the tag the current reduction will publish
+    cudaEvent_t ev = nullptr;    // recorded behind the publish kernel (error path: a failed launch never writes the tag)
 };
 struct m2s_ctx {
     int device = 0;
@@ -63,8 +68,17 @@ struct m2s_ctx {
     static constexpr int kMaxChunks = 8;
     cudaStream_t stream2 = nullptr;
     cudaStream_t stream3 = nullptr;              // uploads of the host pipeline: the copy engine keeps going while chunk kernels run
-    cudaStream_t up = nullptr;                   // stream texture rows / triangle chunks are uploaded on (= stream, or stream3 inside the pipeline)
-    cudaEvent_t ev_up[kMaxChunks] = {};          // "chunk c's triangles and texture rows are resident"
+    cudaStream_t up = nullptr;                   // stream triangle chunks are uploaded on (= stream, or stream3 inside the pipeline)
+    // the host pipeline keeps TWO copy engines busy in the upload direction (one stream delivers 35 GB/s on these boxes, two
+    // 51 GB/s: scripts/pcie_probe.py) and never puts a kernel between two copies of a stream (a copy behind a kernel of
+    // its own stream waits for it: with the v-range and mip kernels on the copy stream every chunk cost ~40 us of bubbles)
+    cudaStream_t stream4 = nullptr;              // texture rows
+    cudaStream_t stream5 = nullptr;              // v-range reductions and their 8-byte results
+    cudaStream_t tex_up = nullptr;               // stream texture rows are uploaded on (= up, or stream4 inside the pipeline)
+    cudaStream_t mip = nullptr;                  // stream their mip rows are generated on (= tex_up, or the compute stream inside the pipeline)
+    cudaStream_t aux = nullptr;                  // stream the v-range reductions run on (= up, or stream5 inside the pipeline)
+    cudaEvent_t ev_tri[kMaxChunks] = {};         // "chunk c's triangles are resident"
+    cudaEvent_t ev_up[kMaxChunks] = {};          // "chunk c's texture rows are resident"
     cudaEvent_t ev_alloc = nullptr;
     unsigned long long* d_chunk_tot = nullptr;   // [kMaxChunks]
     unsigned long long* h_chunk_tot = nullptr;   // pinned + mapped: {count, tag} per chunk, written by the raster kernel
@@ -75,6 +89,7 @@ struct m2s_ctx {
     cudaEvent_t ev_chunk[kMaxChunks] = {};
     VRangeSlot vr[kMaxChunks];        // v-range reductions of the host pipeline (lazy texture upload)
     uint32_t vr_ntex = 0;                    // textures the slots are sized for
+    bool vr_dirty = false;                   // a pipeline was abandoned half way: the device copies must be re-armed
     static constexpr int kLayouts = 5;
     int blocks_per_sm[kLayouts] = {};       // raster kernel (persistent)
     int frag_blocks_per_sm[kLayouts] = {};  // fragment kernel
@@ -198,7 +213,10 @@ M2S_EXPORT m2s_status m2s_ctx_create(int device, m2s_ctx** out) {
     CUDA_TRY(cudaEventCreate(&c->ev1));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
-    c->up = c->stream;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream4, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream5, cudaStreamNonBlocking));
+    c->up = c->tex_up = c->mip = c->aux = c->stream;
+    for (int i = 0; i < m2s_ctx::kMaxChunks; ++i) CUDA_TRY(cudaEventCreateWithFlags(&c->ev_tri[i], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_alloc, cudaEventDisableTiming));
     for (int i = 0; i < m2s_ctx::kMaxChunks; ++i) CUDA_TRY(cudaEventCreateWithFlags(&c->ev_up[i], cudaEventDisableTiming));
     CUDA_TRY(cudaMalloc(&c->d_chunk_tot, m2s_ctx::kMaxChunks * sizeof(unsigned long long)));
@@ -232,6 +250,9 @@ M2S_EXPORT void m2s_ctx_destroy(m2s_ctx* c) {
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); if (c->ev_mid) cudaEventDestroy(c->ev_mid);
     if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream3) cudaStreamDestroy(c->stream3);
+    if (c->stream4) cudaStreamDestroy(c->stream4);
+    if (c->stream5) cudaStreamDestroy(c->stream5);
+    for (int i = 0; i < m2s_ctx::kMaxChunks; ++i) if (c->ev_tri[i]) cudaEventDestroy(c->ev_tri[i]);
     if (c->ev_alloc) cudaEventDestroy(c->ev_alloc);
     for (int i = 0; i < m2s_ctx::kMaxChunks; ++i) if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]);
     cudaStreamDestroy(c->stream);
@@ -289,15 +310,19 @@ M2S_EXPORT void m2s_scene_free(m2s_ctx* ctx, m2s_dscene* s) {
 }
 
 // rows [g0, g1) x kTexGroupRows of texture t: one contiguous H2D copy, then the rows of levels 1.. that they determine
-static m2s_status upload_texture_groups(m2s_ctx* ctx, m2s_dscene* d, uint32_t t, uint32_t g0, uint32_t g1) {
+struct MipRun { uint32_t t, g0, g1; };   // levels 1.. of the row groups [g0, g1) of texture t are still to be generated
+static m2s_status upload_texture_groups(m2s_ctx* ctx, m2s_dscene* d, uint32_t t, uint32_t g0, uint32_t g1, std::vector<MipRun>* deferred = nullptr) {
     const DTexture& dt = d->h_texs[t];
     const uint32_t H = dt.h[0], W = dt.w[0];
     const uint32_t r0 = g0 * kTexGroupRows, r1 = std::min<uint32_t>(H, g1 * kTexGroupRows);
     if (r0 >= r1) return M2S_OK;
     CUDA_TRY(cudaMemcpyAsync(d->d_arena + dt.off[0] + (size_t)r0 * W, d->h_rgba[t] + (size_t)r0 * W * 4, (size_t)(r1 - r0) * W * 4,
-                             cudaMemcpyHostToDevice, ctx->up));
-    // level-l row j needs level-(l-1) rows 2j, 2j+1: inside the same 16-row group — all levels in one launch
-    CUDA_TRY(mip_groups_launch(d->d_arena, dt, g0, std::min<uint32_t>(g1, (H + kTexGroupRows - 1) / kTexGroupRows), ctx->up));
+                             cudaMemcpyHostToDevice, ctx->tex_up));
+    // level-l row j needs level-(l-1) rows 2j, 2j+1: inside the same 16-row group — all levels in one launch; inside the
+    // host pipeline the launch is left to the caller (on the compute stream, behind an event: no kernel on the copy stream)
+    const uint32_t ge = std::min<uint32_t>(g1, (H + kTexGroupRows - 1) / kTexGroupRows);
+    if (deferred) deferred->push_back({t, g0, ge});
+    else CUDA_TRY(mip_groups_launch(d->d_arena, dt, g0, ge, ctx->tex_up));
     for (uint32_t g = g0; g < g1 && g < d->present[t].size(); ++g) d->present[t][g] = 1;
     d->h2d_bytes += (uint64_t)(r1 - r0) * W * 4;
     return M2S_OK;
@@ -314,13 +339,16 @@ static float sortable_to_float(int i) { i ^= (i >> 31) & 0x7fffffff; float f; st
 static m2s_status vrange_enqueue(m2s_ctx* ctx, m2s_dscene* d, uint64_t lo, uint64_t hi, int slot);
 // `idle` (optional) is called while the host waits for the reduction: the host pipeline enqueues ready downloads there
 template <class Idle>
-static m2s_status upload_groups_from_vrange(m2s_ctx* ctx, m2s_dscene* d, int slot, Idle idle) {
+static m2s_status upload_groups_from_vrange(m2s_ctx* ctx, m2s_dscene* d, int slot, Idle idle, std::vector<MipRun>* deferred = nullptr) {
     const uint32_t nt = d->ntex;
     if (!nt) return M2S_OK;
-    for (;;) {
-        const cudaError_t q = cudaEventQuery(ctx->vr[slot].ev);
-        if (q == cudaSuccess) break;
-        if (q != cudaErrorNotReady) { set_error(std::string("v-range reduction: ") + cudaGetErrorString(q)); return M2S_E_CUDA; }
+    for (uint32_t spin = 0;; ++spin) {
+        if (__atomic_load_n(ctx->vr[slot].h_tag, __ATOMIC_ACQUIRE) == ctx->vr[slot].tag) break;   // the values are ordered before the tag
+        if ((spin & 255u) == 255u) {  // a failed launch never writes the tag: ask the stream now and then
+            const cudaError_t q = cudaEventQuery(ctx->vr[slot].ev);
+            if (q == cudaSuccess) { if (__atomic_load_n(ctx->vr[slot].h_tag, __ATOMIC_ACQUIRE) == ctx->vr[slot].tag) break; }
+            else if (q != cudaErrorNotReady) { set_error(std::string("v-range reduction: ") + cudaGetErrorString(q)); return M2S_E_CUDA; }
+        }
         const cudaError_t ie = idle();
         if (ie != cudaSuccess) { set_error(std::string("convert_host download: ") + cudaGetErrorString(ie)); return M2S_E_CUDA; }
     }
@@ -344,7 +372,7 @@ static m2s_status upload_groups_from_vrange(m2s_ctx* ctx, m2s_dscene* d, int slo
             if (!need[g] || d->present[t][g]) { ++g; continue; }
             uint32_t e = g;
             while (e < ng && need[e] && !d->present[t][e]) ++e;
-            m2s_status st = upload_texture_groups(ctx, d, t, g, e);
+            m2s_status st = upload_texture_groups(ctx, d, t, g, e, deferred);
             if (st != M2S_OK) return st;
             g = e;
         }
@@ -357,28 +385,43 @@ static m2s_status upload_groups_from_vrange(m2s_ctx* ctx, m2s_dscene* d, int slo
 static m2s_status vrange_enqueue(m2s_ctx* ctx, m2s_dscene* d, uint64_t lo, uint64_t hi, int slot) {
     const uint32_t nt = d->ntex;
     if (!nt) return M2S_OK;
-    if (ctx->vr_ntex < nt) {  // (re)size every slot
+    if (ctx->vr_ntex != nt) {  // (re)size and arm every slot: the armed layout (min block | max block | flag) depends on the texture count
         for (auto& v : ctx->vr) {
             if (v.d_minmax) { cudaFree(v.d_minmax); v.d_minmax = nullptr; }
             if (v.h_minmax) { cudaFreeHost(v.h_minmax); v.h_minmax = nullptr; }
         }
         ctx->vr_ntex = 0;
         for (auto& v : ctx->vr) {
-            CUDA_TRY(cudaMalloc(&v.d_minmax, (2 * (size_t)nt + 1) * sizeof(int)));
-            CUDA_TRY(cudaMallocHost(&v.h_minmax, (2 * (size_t)nt + 1) * sizeof(int)));
+            const size_t nints = 2 * (size_t)nt + 1, tag_off = (nints * sizeof(int) + 7) & ~(size_t)7;
+            CUDA_TRY(cudaMalloc(&v.d_minmax, nints * sizeof(int)));
+            std::vector<int> arm(nints, 0);
+            for (size_t i = 0; i < nt; ++i) { arm[i] = 0x7f7f7f7f; arm[nt + i] = (int)0x80808080; }
+            CUDA_TRY(cudaMemcpy(v.d_minmax, arm.data(), nints * sizeof(int), cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaHostAlloc(&v.h_minmax, tag_off + 8, cudaHostAllocMapped));
+            std::memset(v.h_minmax, 0, tag_off + 8);
+            CUDA_TRY(cudaHostGetDevicePointer((void**)&v.h_minmax_dev, v.h_minmax, 0));
+            v.h_tag = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(v.h_minmax) + tag_off);
+            v.h_tag_dev = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(v.h_minmax_dev) + tag_off);
             if (!v.ev) CUDA_TRY(cudaEventCreateWithFlags(&v.ev, cudaEventDisableTiming));
         }
         ctx->vr_ntex = nt;
     }
     VRangeSlot& v = ctx->vr[slot];
     // min <- 0x7f7f7f7f (above every finite float's key), max <- 0x80808080 (below), flag <- 0
-    CUDA_TRY(cudaMemsetAsync(v.d_minmax, 0x7f, nt * sizeof(int), ctx->up));
-    CUDA_TRY(cudaMemsetAsync(v.d_minmax + nt, 0x80, nt * sizeof(int), ctx->up));
-    CUDA_TRY(cudaMemsetAsync(v.d_minmax + 2 * nt, 0, sizeof(int), ctx->up));
+    // d_minmax is armed (at allocation, then by every publish kernel); a conversion that failed in between re-arms it
+    if (ctx->vr_dirty) {
+        for (auto& w : ctx->vr) {
+            CUDA_TRY(cudaMemsetAsync(w.d_minmax, 0x7f, nt * sizeof(int), ctx->aux));
+            CUDA_TRY(cudaMemsetAsync(w.d_minmax + nt, 0x80, nt * sizeof(int), ctx->aux));
+            CUDA_TRY(cudaMemsetAsync(w.d_minmax + 2 * nt, 0, sizeof(int), ctx->aux));
+        }
+        ctx->vr_dirty = false;
+    }
     if (hi > lo)
-        CUDA_TRY(vrange_launch(d->d_tris, (uint32_t)lo, (uint32_t)(hi - lo), d->d_ranges, d->nranges, d->d_prims, nt, v.d_minmax, ctx->up));
-    CUDA_TRY(cudaMemcpyAsync(v.h_minmax, v.d_minmax, (2 * (size_t)nt + 1) * sizeof(int), cudaMemcpyDeviceToHost, ctx->up));
-    CUDA_TRY(cudaEventRecord(v.ev, ctx->up));
+        CUDA_TRY(vrange_launch(d->d_tris, (uint32_t)lo, (uint32_t)(hi - lo), d->d_ranges, d->nranges, d->d_prims, nt, v.d_minmax, ctx->aux));
+    v.tag = ++ctx->host_seq;
+    CUDA_TRY(vrange_publish_launch(v.d_minmax, nt, v.h_minmax_dev, v.h_tag_dev, v.tag, ctx->aux));
+    CUDA_TRY(cudaEventRecord(v.ev, ctx->aux));
     return M2S_OK;
 }
 
@@ -387,7 +430,6 @@ static m2s_status vrange_enqueue(m2s_ctx* ctx, m2s_dscene* d, uint64_t lo, uint6
 // lazy_tex: the images are NOT copied here; the caller brings in the row groups its triangle ranges sample with
 // ensure_textures_for_range (m2s_convert_host pipelines them with the triangle chunks, m2s_scene_upload_range
 // uploads what one shard needs).
-static m2s_status upload_texture_groups(m2s_ctx* ctx, m2s_dscene* d, uint32_t t, uint32_t g0, uint32_t g1);
 static m2s_status scene_upload_impl(m2s_ctx* ctx, const m2s_scene* sc, m2s_dscene** out, uint64_t first_tris, bool sync,
                                     uint64_t tri_offset = 0, bool lazy_tex = false) {
     if (!ctx || !sc || !out) { set_error("m2s_scene_upload: NULL argument"); return M2S_E_INVALID; }
@@ -755,9 +797,9 @@ M2S_EXPORT m2s_status m2s_convert_host(m2s_ctx* ctx, const m2s_scene* sc, const 
     if (count == 0 || first + count > sc->triangle_count) count = sc->triangle_count - first;
     int nchunks = 1;
     if (count >= 16384) {  // every layout: the fragment kernel appends after the earlier chunks' records itself
-        // measured on the bench scene (profiles/r02_e2e_chunks.log): 2 chunks 1.18-1.21 ms, 4: 1.23-1.33, 6-8: 1.33-1.46 —
-        // the upload (35 GB/s on these boxes) bounds the call and every extra chunk adds a host <-> device round trip
-        nchunks = 2;
+        // every chunk shortens the tail (the last chunk's kernels and download) and costs ~25 us of kernel latency on the
+        // compute stream, hidden behind the uploads; chunks of >= 8 k triangles keep the GPU filled
+        nchunks = (int)std::max<uint64_t>(2, std::min<uint64_t>(4, count / 16384));
         if (const char* e = std::getenv("M2S_HOST_CHUNKS")) nchunks = std::max(1, std::min(m2s_ctx::kMaxChunks, std::atoi(e)));
     }
     const uint64_t per = (count + nchunks - 1) / nchunks;
@@ -777,8 +819,9 @@ M2S_EXPORT m2s_status m2s_convert_host(m2s_ctx* ctx, const m2s_scene* sc, const 
     std::memset(&r, 0, sizeof(r));
     const uint64_t cap = effective_cap(ds, p, out_capacity);
     auto fail_with = [&](m2s_status code) {
-        cudaStreamSynchronize(ctx->stream3); cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->stream2);
-        ctx->dirty = true;
+        cudaStreamSynchronize(ctx->stream3); cudaStreamSynchronize(ctx->stream4); cudaStreamSynchronize(ctx->stream5);
+        cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->stream2);
+        ctx->dirty = true; ctx->vr_dirty = true;
         m2s_scene_free(ctx, ds);
         return code;
     };
@@ -795,9 +838,13 @@ M2S_EXPORT m2s_status m2s_convert_host(m2s_ctx* ctx, const m2s_scene* sc, const 
     // copy engine streams triangles and texture rows continuously while the chunks' kernels run on the context stream
     e = cudaEventRecord(ctx->ev_alloc, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream3, ctx->ev_alloc, 0);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream4, ctx->ev_alloc, 0);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream5, ctx->ev_alloc, 0);
     if (e != cudaSuccess) return bail("convert_host", e);
-    struct UpGuard { m2s_ctx* c; ~UpGuard() { c->up = c->stream; } } up_guard{ctx};
-    ctx->up = ctx->stream3;
+    // triangles on one copy stream, texture rows on another (two copy engines: 51 instead of 35 GB/s), the v-range
+    // reductions on a third, the mip rows on the compute stream: no copy ever queues behind a kernel
+    struct UpGuard { m2s_ctx* c; ~UpGuard() { c->up = c->tex_up = c->mip = c->aux = c->stream; } } up_guard{ctx};
+    ctx->up = ctx->stream3; ctx->tex_up = ctx->stream4; ctx->aux = ctx->stream5; ctx->mip = ctx->stream;
     uint64_t lo_[m2s_ctx::kMaxChunks], hi_[m2s_ctx::kMaxChunks];
     int planned = 0, uploaded = 0;
     for (int c = 0; c < nchunks; ++c) {
@@ -806,24 +853,28 @@ M2S_EXPORT m2s_status m2s_convert_host(m2s_ctx* ctx, const m2s_scene* sc, const 
         lo_[c] = lo; hi_[c] = hi;
         ++planned;
     }
-    // (1) triangle chunk c goes up, followed by the reduction of its v-range per texture and the copy back of the result
+    // (1) triangle chunk c goes up (its own copy stream), followed by the reduction of its v-range per texture (a kernel behind
+    // "chunk c is resident" on the aux stream, results through mapped memory)
     auto upload_tris = [&](int c) -> m2s_status {
+        cudaError_t e1 = cudaSuccess;
         if (hi_[c] > lo_[c]) {
-            cudaError_t e1 = cudaMemcpyAsync(reinterpret_cast<unsigned char*>(ds->d_tris) + lo_[c] * (size_t)kTriBytes,
-                                             reinterpret_cast<const unsigned char*>(sc->triangles) + lo_[c] * (size_t)kTriBytes,
-                                             (hi_[c] - lo_[c]) * (size_t)kTriBytes, cudaMemcpyHostToDevice, ctx->up);
-            if (e1 != cudaSuccess) { set_error(std::string("convert_host upload: ") + cudaGetErrorString(e1)); return M2S_E_CUDA; }
+            e1 = cudaMemcpyAsync(reinterpret_cast<unsigned char*>(ds->d_tris) + lo_[c] * (size_t)kTriBytes,
+                                 reinterpret_cast<const unsigned char*>(sc->triangles) + lo_[c] * (size_t)kTriBytes,
+                                 (hi_[c] - lo_[c]) * (size_t)kTriBytes, cudaMemcpyHostToDevice, ctx->up);
             ds->h2d_bytes += (hi_[c] - lo_[c]) * (uint64_t)kTriBytes;
         }
+        if (e1 == cudaSuccess) e1 = cudaEventRecord(ctx->ev_tri[c], ctx->up);
+        if (e1 == cudaSuccess) e1 = cudaStreamWaitEvent(ctx->aux, ctx->ev_tri[c], 0);
+        if (e1 != cudaSuccess) { set_error(std::string("convert_host upload: ") + cudaGetErrorString(e1)); return M2S_E_CUDA; }
         return vrange_enqueue(ctx, ds, lo_[c], hi_[c], c);
     };
-    // one chunk of look-ahead keeps the copy engine busy while the host waits for a v-range: the stream sees
-    // tris0 tris1 | rows0 kernels0 | tris2 | rows1 kernels1 | ... and the first records exist after ~2/nchunks of the
-    // triangles and 1/nchunks of the texture rows
-    // look-ahead: how many triangle chunks are queued before the first chunk's texture rows.  All of them (default): the
-    // copy queue never runs dry while the host waits for a v-range, and the v-ranges of the later chunks are on the host
-    // long before they are needed — every extra chunk then only shortens the tail (the last chunk's download)
-    int lookahead = planned;
+    // look-ahead: triangle chunks (and their v-range reductions) queued ahead of the chunk whose texture rows go up: the
+    // first records exist after ~lookahead/nchunks of the triangles and 1/nchunks of the texture rows (the downloads, 36 MB
+    // at 55 GB/s, are the longest leg of the call: they must start early).  Measured on the bench scene
+    // (profiles/r02_e2e_pipeline.txt): 4 chunks / look-ahead 2: 1.08 ms; 8 / 3: 1.09; every triangle chunk queued up front:
+    // 1.14-1.16 (first records at 0.34 ms instead of 0.20); every copy cut in halves over two streams (two streams deliver
+    // 51 GB/s against 35 for one when they carry 13 MB each — not with 1 MB pieces beside a running download): 1.23
+    int lookahead = 2;
     if (const char* e = std::getenv("M2S_HOST_LOOKAHEAD")) lookahead = std::max(1, std::atoi(e));
     for (; uploaded < std::min(planned, lookahead); ++uploaded) {
         st = upload_tris(uploaded);
@@ -866,12 +917,20 @@ M2S_EXPORT m2s_status m2s_convert_host(m2s_ctx* ctx, const m2s_scene* sc, const 
     };
     int launched = 0;
     for (int c = 0; c < planned; ++c) {  // (2)
-        st = upload_groups_from_vrange(ctx, ds, c, [&] { return downloads(launched, false); });  // (3) while waiting: whatever is ready
+        std::vector<MipRun> runs;
+        const double t_it0 = host_trace ? since() : 0.0;
+        st = upload_groups_from_vrange(ctx, ds, c, [&] { return downloads(launched, false); }, &runs);  // (3) while waiting: whatever is ready
         if (st != M2S_OK) return fail_with(st);
-        e = cudaEventRecord(ctx->ev_up[c], ctx->up);   // chunk c's triangles and texture rows are resident
+        const double t_it1 = host_trace ? since() : 0.0;
+        e = cudaEventRecord(ctx->ev_up[c], ctx->tex_up);   // chunk c's texture rows are resident (level 0)
         if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->ev_up[c], 0);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->ev_tri[c], 0);
         if (e != cudaSuccess) return bail("convert_host", e);
-        if (uploaded < planned) {  // next look-ahead chunk: behind this chunk's rows in the copy queue
+        for (const MipRun& r : runs) {   // their mip rows: on the compute stream, right before the kernels that sample them
+            e = mip_groups_launch(ds->d_arena, ds->h_texs[r.t], r.g0, r.g1, ctx->stream);
+            if (e != cudaSuccess) return bail("convert_host mips", e);
+        }
+        if (uploaded < planned) {  // the next look-ahead chunk
             st = upload_tris(uploaded++);
             if (st != M2S_OK) return fail_with(st);
         }
@@ -896,8 +955,11 @@ M2S_EXPORT m2s_status m2s_convert_host(m2s_ctx* ctx, const m2s_scene* sc, const 
         e = cudaEventRecord(ctx->ev_chunk[c], ctx->stream);
         if (e != cudaSuccess) return bail("convert_host", e);
         ++launched;
+        const double t_it2 = host_trace ? since() : 0.0;
         e = downloads(launched, false);  // (3) whatever is ready
         if (e != cudaSuccess) return bail("convert_host download", e);
+        if (host_trace) std::fprintf(stderr, "[m2s host] chunk %d: v-range wait + rows enqueued %.0f us, tris/mips/kernels enqueued %.0f us, downloads %.0f us (at %.0f us)\n",
+                                     c, t_it1 - t_it0, t_it2 - t_it1, since() - t_it2, since());
     }
     e = cudaEventRecord(ctx->ev1, ctx->stream);
     if (e != cudaSuccess) return bail("convert_host", e);
@@ -907,6 +969,8 @@ M2S_EXPORT m2s_status m2s_convert_host(m2s_ctx* ctx, const m2s_scene* sc, const 
     e = cudaStreamSynchronize(ctx->stream2);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream3);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream4);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream5);
     if (e != cudaSuccess) return bail("convert_host download", e);
     if (host_trace) std::fprintf(stderr, "[m2s host] downloads done at %.0f us\n", since());
     float ms = 0.f;

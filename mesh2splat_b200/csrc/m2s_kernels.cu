@@ -1928,6 +1928,28 @@ cudaError_t mip_groups_launch(uint32_t* arena, const DTexture& t, uint32_t g0, u
     return cudaGetLastError();
 }
 
+// The v-ranges of one chunk -> mapped pinned host memory, then a tag the host polls; the device copy is re-armed for its
+// next use (min <- 0x7f7f7f7f, max <- 0x80808080, flag <- 0).  No copy engine: the download engine is busy with records,
+// an 8-byte copy queued behind them reached the host 100-200 us late.
+__global__ void vrange_publish_kernel(int* __restrict__ minmax, uint32_t ntex, volatile int* __restrict__ host, unsigned long long* host_tag,
+                                      unsigned long long tag) {
+    const uint32_t n = 2 * ntex + 1;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        host[i] = minmax[i];
+        minmax[i] = i < ntex ? 0x7f7f7f7f : (i < 2 * ntex ? (int)0x80808080 : 0);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long*>(host_tag) = tag;
+    }
+}
+cudaError_t vrange_publish_launch(int* minmax, uint32_t ntex, int* host, unsigned long long* host_tag, unsigned long long tag, cudaStream_t stream) {
+    vrange_publish_kernel<<<1, 128, 0, stream>>>(minmax, ntex, host, host_tag, tag);
+    return cudaGetLastError();
+}
+
 cudaError_t vrange_launch(const float4* tris, uint32_t first, uint32_t count, const DRange* ranges, uint32_t nranges, const DPrim* prims,
                           uint32_t ntex, int* minmax, cudaStream_t stream) {
     if (!count || !ntex) return cudaSuccess;
