@@ -1,10 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 python __graft_entry__.py --smoke > gpurun_out/r2e_smoke.log 2>&1; echo "smoke rc=$?" | tee -a gpurun_out/r2e_smoke.log
-if ! grep -q "smoke ok" gpurun_out/r2e_smoke.log; then tail -30 gpurun_out/r2e_smoke.log; exit 1; fi
-timeout 2400 python -m pytest tests -m gpu -x -q > gpurun_out/r2e_pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/r2e_pytest.log
-tail -12 gpurun_out/r2e_pytest.log
-for c in 1 2 4 8; do echo "== chunks $c"; M2S_HOST_CHUNKS=$c M2S_HOST_TRACE=1 timeout 300 python scripts/e2e_probe.py 2>&1 | tail -14; done > gpurun_out/r2e_e2e_chunks.log 2>&1
-grep -E "chunks|e2e ms" gpurun_out/r2e_e2e_chunks.log
-timeout 600 python bench.py --steps 30 --warmup 5 > gpurun_out/r2e_bench_p56.json 2> gpurun_out/r2e_bench_p56.err; python -c "
-import json; d=json.load(open('gpurun_out/r2e_bench_p56.json')); print('value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e']['ms_per_step'],d['e2e']['resident_scene']['ms_per_step'],'frac',d['roofline']['frac'],d['roofline']['launch_shares'])"; tail -3 gpurun_out/r2e_bench_p56.err
+timeout 900 python -m pytest tests -m gpu -x -q -k "host or upload_range or file or pipel" > gpurun_out/r2e_pytest.log 2>&1; tail -3 gpurun_out/r2e_pytest.log
+for c in 2 4 8; do echo "== eager, chunks $c: $(M2S_HOST_CHUNKS=$c timeout 300 python scripts/e2e_probe.py 2>&1 | tail -1)"; done | tee gpurun_out/r2e_e2e.txt
+for c in 4; do echo "== on demand, chunks $c: $(M2S_HOST_NO_EAGER=1 M2S_HOST_CHUNKS=$c timeout 300 python scripts/e2e_probe.py 2>&1 | tail -1)"; done | tee -a gpurun_out/r2e_e2e.txt
+echo "== trace, defaults"; M2S_HOST_TRACE=1 timeout 300 python scripts/e2e_probe.py 2>&1 | tail -12 | tee -a gpurun_out/r2e_e2e.txt
