@@ -10,7 +10,8 @@ density 512.  Metric: Mgaussians/s.
   value      device-resident: scene already in HBM, CUDA events on the launching stream around the two kernel
              launches only, L2 flushed (256 MiB memset, untimed) before every timed step
   e2e        the same metric through the C ABI with HOST buffers.  N = 1: m2s_convert_host (pinned triangle + texture
-             upload, GPU mip generation, convert, download of the records).  N > 1: every rank uploads ITS triangle
+             upload, GPU mip generation, convert, download of the records: a five-stream pipeline over triangle
+             chunks).  N > 1: every rank uploads ITS triangle
              shard (+ the maps the layout samples) over its own PCIe link, converts it, and downloads its records into
              its slice of ONE shared pinned host buffer (offsets from an all-gather of the counts) — the consumer of
              the reference's exportPly is a host vector (SceneManager.cpp:651-678), so no GPU-to-GPU traffic at all.
