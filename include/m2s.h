@@ -13,6 +13,7 @@
  *     (src/renderer/renderPasses/ConversionPass.cpp:9-117)      m2s_convert_host
  *     + converter{VS,GS,FS}.glsl + SSBO atomic append
  *   SceneManager::exportPly + parsers::savePlyVector            m2s_ply_encode, m2s_ply_write
+ *   GaussiansPrepass::execute + gaussianSplattingPrepassCS.glsl  m2s_prepass, m2s_prepass_enqueue
  *     (src/utils/SceneManager.cpp:651-678,
  *      src/parsers/parsers.cpp:232-316,339-428,431-514,631-651)
  *   SceneManager::loadModel -> execute -> exportPly             m2s_convert_file
@@ -254,6 +255,40 @@ void m2s_hscene_free(m2s_hscene* scene);
 m2s_status m2s_convert_file(m2s_ctx* ctx, const char* glb_path, uint32_t resolution,
                             float gaussian_std, uint32_t ply_format, const char* ply_path,
                             m2s_result* result);
+
+/* ---- the step after the path in the reference's frame graph: the viewer prepass ----------------
+ * GaussiansPrepass::execute (src/renderer/renderPasses/GaussiansPrepass.cpp:8-55) + gaussianSplattingPrepassCS.glsl
+ * :58-204: per gaussian — model/view/clip transform, frustum cull (1.05 w), 3-D covariance from scale and rotation,
+ * EWA projection to a 2-D conic (+0.3 low-pass), screen-space axes, atomic append of one QuadNdcTransformation (96 B:
+ * gaussianMean2dNdc, quadScaleNdc, color, conic (.w = view depth), normal (.w = pbr.x), wsPos (.w = pbr.y)) and of the
+ * view-space depth the radix sort keys on.  Matrices are column-major (glm::mat4).  Input records:
+ *   M2S_LAYOUT_REF96     the reference's GaussianVertex, u_format 0 (scale * std_dev, normal through the normal matrix)
+ *   M2S_LAYOUT_PACKED56  a standard 3DGS gaussian as the reference loads it from a .ply without PBR values, u_format 1
+ *                        (scale = exp(log_scale), colour = SH0 * C0 + 0.5, alpha = sigmoid(opacity), normal = the
+ *                        shortest axis, pbr = 0)
+ * Not reproduced: the mesh depth test (u_depthTestMesh: needs the viewer's mesh depth pre-pass) and render mode 3 (debug
+ * colours from the invocation id).  Output order is unspecified, as in the reference (atomic arrival order). */
+typedef struct m2s_prepass_params {
+    float world_to_view[16];   /* renderContext.viewMat */
+    float view_to_clip[16];    /* renderContext.projMat */
+    float model_to_world[16];  /* renderContext.modelMat */
+    float resolution[2];       /* renderContext.rendererResolution */
+    float near_far[2];
+    float std_dev;             /* gaussianStd / resolutionTarget (GaussiansPrepass.cpp:18) */
+    uint32_t render_mode;      /* 0 (or 6) colour, 1 depth, 2 normal */
+    uint32_t layout;           /* M2S_LAYOUT_REF96 or M2S_LAYOUT_PACKED56 */
+    uint32_t reserved;
+} m2s_prepass_params;
+#define M2S_QUAD_BYTES 96u
+/* Enqueue-only: d_quads holds `count` x 96 B, d_depths `count` floats, d_valid one uint32 (zeroed by the call, then the
+ * number of surviving gaussians).  d_count (optional): device-side count that overrides `count` downwards (the
+ * counter of a conversion that was only enqueued). */
+m2s_status m2s_prepass_enqueue(m2s_ctx* ctx, const void* d_records, uint64_t count, const uint64_t* d_count,
+                               const m2s_prepass_params* params, void* d_quads, float* d_depths, uint32_t* d_valid,
+                               void* stream);
+/* Synchronous variant on the context stream; *valid receives the counter. */
+m2s_status m2s_prepass(m2s_ctx* ctx, const void* d_records, uint64_t count, const m2s_prepass_params* params,
+                       void* d_quads, float* d_depths, uint32_t* valid);
 
 #ifdef __cplusplus
 }

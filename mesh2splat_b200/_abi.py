@@ -55,6 +55,26 @@ class m2s_result(C.Structure):
 MAX_PEERS = 8
 
 
+class m2s_prepass_params(C.Structure):
+    """include/m2s.h: the uniforms of GaussiansPrepass::execute; matrices column-major (glm::mat4)."""
+    _fields_ = [("world_to_view", C.c_float * 16), ("view_to_clip", C.c_float * 16), ("model_to_world", C.c_float * 16),
+                ("resolution", C.c_float * 2), ("near_far", C.c_float * 2), ("std_dev", C.c_float), ("render_mode", C.c_uint32),
+                ("layout", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+QUAD_BYTES = 96
+
+
+def make_prepass_params(world_to_view, view_to_clip, model_to_world, resolution, near_far, std_dev: float, render_mode: int, layout: int):
+    p = m2s_prepass_params()
+    for name, m in (("world_to_view", world_to_view), ("view_to_clip", view_to_clip), ("model_to_world", model_to_world)):
+        setattr(p, name, (C.c_float * 16)(*[float(v) for v in np.asarray(m, np.float32).ravel()]))
+    p.resolution = (C.c_float * 2)(float(resolution[0]), float(resolution[1]))
+    p.near_far = (C.c_float * 2)(float(near_far[0]), float(near_far[1]))
+    p.std_dev, p.render_mode, p.layout, p.reserved = float(std_dev), int(render_mode), int(layout), 0
+    return p
+
+
 class m2s_peers(C.Structure):
     _fields_ = [("world", C.c_uint32), ("rank", C.c_uint32), ("out", C.c_void_p * MAX_PEERS), ("xch", C.c_void_p * MAX_PEERS)]
 

@@ -19,6 +19,7 @@ SYMBOLS = [
     "m2s_convert_enqueue", "m2s_convert", "m2s_convert_timed", "m2s_convert_host", "m2s_convert_gather_enqueue",
     "m2s_ply_header", "m2s_ply_encode", "m2s_ply_write", "m2s_convert_file",
     "m2s_glb_load", "m2s_hscene_view", "m2s_hscene_primitive_name", "m2s_hscene_free",
+    "m2s_prepass", "m2s_prepass_enqueue",
 ]
 
 
@@ -101,6 +102,10 @@ def lib() -> C.CDLL:
     L.m2s_hscene_primitive_name.argtypes = [vp, u32]
     L.m2s_hscene_free.restype = None
     L.m2s_hscene_free.argtypes = [vp]
+    L.m2s_prepass_enqueue.restype = i32
+    L.m2s_prepass_enqueue.argtypes = [vp, vp, u64, vp, C.POINTER(_abi.m2s_prepass_params), vp, vp, vp, vp]
+    L.m2s_prepass.restype = i32
+    L.m2s_prepass.argtypes = [vp, vp, u64, C.POINTER(_abi.m2s_prepass_params), vp, vp, C.POINTER(u32)]
     _lib = L
     return L
 

@@ -394,3 +394,64 @@ def ref_fs(varyings19, albedo, nrm, mr, flags: int, factor, counter_start: int =
     w = r.ref_fs(arrs[0].ctypes.data, arrs[1].ctypes.data, arrs[2].ctypes.data, arrs[3].ctypes.data, flags,
                  f.ctypes.data, counter_start, max_gaussians, rec.ctypes.data, C.byref(cnt))
     return bool(w), rec, int(cnt.value)
+
+
+# ---- viewer prepass ----------------------------------------------------------------------------
+_refpre = None
+
+
+def ref_prepass_lib():
+    """The reference's own prepass compute shader compiled as C++ (oracle/_ref/libm2s_refprepass.so), or None."""
+    global _refpre
+    if _refpre is None:
+        path = os.path.join(_HERE, "_ref", "libm2s_refprepass.so")
+        if not os.path.exists(path):
+            return None
+        _refpre = C.CDLL(path)
+        _refpre.ref_prepass.restype = C.c_uint32
+        _refpre.ref_prepass.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int,
+                                        C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+    return _refpre
+
+
+def _prepass_call(fn, gaussians24, world_to_view, view_to_clip, model_to_world, resolution, near_far, std_dev, render_mode, fmt, ply_has_pbr):
+    g = np.ascontiguousarray(gaussians24, np.float32).reshape(-1, 24)
+    mats = [np.ascontiguousarray(np.asarray(m, np.float32).reshape(4, 4).T.ravel() if transpose else m, np.float32)
+            for m, transpose in ((world_to_view, False), (view_to_clip, False), (model_to_world, False))]
+    res, nf = np.asarray(resolution, np.float32), np.asarray(near_far, np.float32)
+    quads = np.zeros((len(g), 24), np.float32)
+    depths = np.zeros(len(g), np.float32)
+    n = fn(g.ctypes.data, len(g), mats[0].ctypes.data, mats[1].ctypes.data, mats[2].ctypes.data, res.ctypes.data, nf.ctypes.data,
+           C.c_float(std_dev), int(render_mode), int(fmt), int(ply_has_pbr), quads.ctypes.data, depths.ctypes.data)
+    return quads[:n].copy(), depths[:n].copy()
+
+
+def prepass(gaussians24, world_to_view, view_to_clip, model_to_world, resolution, near_far, std_dev, render_mode=0, fmt=0, ply_has_pbr=0):
+    """orc_prepass: the C restatement of gaussianSplattingPrepassCS.glsl.  Matrices: 16 floats, column-major (glm::mat4).
+    Returns (quads [m, 24], depths [m]) in input order of the survivors."""
+    L = lib()
+    L.orc_prepass.restype = C.c_uint32
+    L.orc_prepass.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_uint32,
+                              C.c_uint32, C.c_void_p, C.c_void_p]
+    return _prepass_call(L.orc_prepass, gaussians24, world_to_view, view_to_clip, model_to_world, resolution, near_far, std_dev, render_mode, fmt, ply_has_pbr)
+
+
+def ref_prepass(gaussians24, world_to_view, view_to_clip, model_to_world, resolution, near_far, std_dev, render_mode=0, fmt=0, ply_has_pbr=0):
+    """The reference's own shader on the same inputs (needs oracle/_ref, i.e. the build container)."""
+    L = ref_prepass_lib()
+    if L is None:
+        raise RuntimeError("oracle/_ref/libm2s_refprepass.so is not built")
+    return _prepass_call(L.ref_prepass, gaussians24, world_to_view, view_to_clip, model_to_world, resolution, near_far, std_dev, render_mode, fmt, ply_has_pbr)
+
+
+def packed56_as_gaussian_vertex(packed: np.ndarray) -> np.ndarray:
+    """PACKED56 records as the GaussianVertex array the reference builds when it loads a standard .ply without PBR values
+    (parsers.cpp:560-622: scale = exp(log scale), colour = SH0 * C0 + 0.5, alpha = sigmoid(opacity), no normal, pbr = 0)."""
+    f = np.ascontiguousarray(packed).view(np.float32).reshape(-1, 14)
+    g = np.zeros((len(f), 24), np.float32)
+    g[:, 0:3] = f[:, 0:3]; g[:, 3] = 1.0
+    g[:, 4:7] = f[:, 10:13] * np.float32(0.28209479177387814) + np.float32(0.5)
+    g[:, 7] = (1.0 / (1.0 + np.exp(-f[:, 13].astype(np.float64)))).astype(np.float32)
+    g[:, 8:11] = np.exp(f[:, 7:10].astype(np.float32))
+    g[:, 16:20] = f[:, 3:7]
+    return g

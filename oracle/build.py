@@ -192,8 +192,53 @@ def build_ref_loader(force: bool = False) -> str | None:
     return out
 
 
+def glsl_prepass_to_cpp(src: str, common: str) -> str:
+    """gaussianSplattingPrepassCS.glsl + common.glsl -> one C++ include (token rewrites only)."""
+    def rw(s: str) -> str:
+        s = re.sub(r"^\s*#version.*$", "", s, flags=re.M)
+        s = s.replace("highp ", "")
+        s = _FLOAT_LIT.sub(lambda m: m.group(1) + "f", s)
+        s = re.sub(r"([(,]\s*)in\s+(\w+\s+\w+)", r"\1\2", s)
+        s = re.sub(r"([(,]\s*)out\s+(\w+)\s+(\w+)", r"\1\2& \3", s)
+        s = re.sub(r"clamp\(([^,()]+(?:\([^()]*\))?[^,()]*),\s*0,\s*1\)", r"clamp(\1, 0.0f, 1.0f)", s)   # GLSL converts the int bounds
+        # the one swizzle used as an lvalue
+        s = s.replace("pos2d.xyz = pos2d.xyz / pos2d.w;", "{ vec3 t_ = vec3(pos2d) / pos2d.w; pos2d.x = t_.x; pos2d.y = t_.y; pos2d.z = t_.z; }")
+        s = re.sub(r"\.(xyz|xy|yx)\b(?!\s*\()", r".\1()", s)                         # rvalue swizzles -> GLM swizzle functions
+        s = re.sub(r"gl_GlobalInvocationID\.(xy|yx)\(\)", r"vec2(gl_GlobalInvocationID.\1())", s)   # GLSL converts uvec2 -> vec2
+        return s
+    src = src.replace('#include "common.glsl"', "")
+    src = re.sub(r"layout\s*\(std430,\s*binding\s*=\s*\d+\)\s*(?:readonly|writeonly)?\s*buffer\s+(\w+)\s*\{\s*(\w+)\s+(\w+)\[\];\s*\}\s*(\w+)\s*;",
+                 r"static struct { \2* \3; } \4;", src)
+    src = re.sub(r"layout\s*\(binding\s*=\s*\d+\)\s*uniform\s+atomic_uint", "static atomic_uint", src)
+    src = re.sub(r"layout\s*\(local_size_x[^)]*\)\s*in\s*;", "", src)
+    src = re.sub(r"^\s*uniform\s+", "static ", src, flags=re.M)
+    src = src.replace("void main()", "void prepass_main()")
+    return rw(common) + "\n" + rw(src)
+
+
+def build_ref_prepass(force: bool = False) -> str | None:
+    """The reference's viewer prepass compute shader (row f-4), compiled where it lies against the reference's GLM."""
+    cs = os.path.join(REF, "src", "shaders", "rendering", "gaussianSplattingPrepassCS.glsl")
+    cm = os.path.join(REF, "src", "shaders", "rendering", "common.glsl")
+    glm = os.path.join(REF, "thirdParty", "glm")
+    out = os.path.join(REF_OUT, "libm2s_refprepass.so")
+    if not (os.path.exists(cs) and os.path.exists(cm) and os.path.isdir(glm)):
+        return out if os.path.exists(out) else None
+    harness = os.path.join(HERE, "ref_prepass_harness.cpp")
+    if not force and _newer(out, cs, cm, harness, __file__):
+        return out
+    os.makedirs(REF_OUT, exist_ok=True)
+    with open(cs) as f, open(cm) as g:
+        inc = glsl_prepass_to_cpp(f.read(), g.read())
+    with open(os.path.join(REF_OUT, "prepassCS.inc"), "w") as f:
+        f.write(inc)
+    _run(["g++", "-std=gnu++17", *CFLAGS, "-w", "-I", glm, "-I", REF_OUT, "-o", out, harness])
+    return out
+
+
 def build_all(force: bool = False) -> dict:
-    return {"oracle": build_oracle(force), "ref": build_ref(force), "ref_ply": build_ref_ply(force), "ref_loader": build_ref_loader(force)}
+    return {"oracle": build_oracle(force), "ref": build_ref(force), "ref_ply": build_ref_ply(force), "ref_loader": build_ref_loader(force),
+            "ref_prepass": build_ref_prepass(force)}
 
 
 if __name__ == "__main__":

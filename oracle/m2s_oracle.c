@@ -637,6 +637,146 @@ ORC_API void orc_sample(const uint8_t* rgba, uint32_t w, uint32_t h, float u, fl
     orc_tex_free(&t);
 }
 
+/* ---- viewer prepass: gaussianSplattingPrepassCS.glsl:58-204 + common.glsl ---------------------------
+ * Plain-C restatement, one invocation after the other in gid order (survivors come out in input order).  Pinned to the
+ * reference's own shader compiled here (oracle/_ref/libm2s_refprepass.so, tests/golden/ref_prepass_vectors.npz): same
+ * survivors, values within 1e-5 relative (GLM's operation order inside inverse()/matrix products is not replicated bit
+ * for bit).  Matrices are column-major: m[c * 4 + r].  format 0: GaussianVertex input as the converter writes it;
+ * format 1 (ply_has_pbr 0): a loaded standard .ply.  render_mode 3 and the mesh depth test are not restated. */
+static void m3mul(const float a[9], const float b[9], float r[9]) {   /* column-major 3x3: r = a * b */
+    for (int c = 0; c < 3; ++c)
+        for (int row = 0; row < 3; ++row)
+            r[c * 3 + row] = a[0 * 3 + row] * b[c * 3 + 0] + a[1 * 3 + row] * b[c * 3 + 1] + a[2 * 3 + row] * b[c * 3 + 2];
+}
+static void m3transpose(const float a[9], float r[9]) { for (int c = 0; c < 3; ++c) for (int k = 0; k < 3; ++k) r[c * 3 + k] = a[k * 3 + c]; }
+static void m3inverse(const float m[9], float r[9]) {
+    const float a = m[0], b = m[3], c = m[6], d = m[1], e = m[4], f = m[7], g = m[2], h = m[5], i = m[8];   /* rows */
+    const float det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g), inv = 1.0f / det;
+    r[0] = (e * i - f * h) * inv; r[3] = (c * h - b * i) * inv; r[6] = (b * f - c * e) * inv;
+    r[1] = (f * g - d * i) * inv; r[4] = (a * i - c * g) * inv; r[7] = (c * d - a * f) * inv;
+    r[2] = (d * h - e * g) * inv; r[5] = (b * g - a * h) * inv; r[8] = (a * e - b * d) * inv;
+}
+static int m4inverse(const float m[16], float inv[16]) {   /* general 4x4 (cofactors), column-major */
+    inv[0] = m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] + m[9] * m[7] * m[14] + m[13] * m[6] * m[11] - m[13] * m[7] * m[10];
+    inv[4] = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] - m[8] * m[7] * m[14] - m[12] * m[6] * m[11] + m[12] * m[7] * m[10];
+    inv[8] = m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] + m[8] * m[7] * m[13] + m[12] * m[5] * m[11] - m[12] * m[7] * m[9];
+    inv[12] = -m[4] * m[9] * m[14] + m[4] * m[10] * m[13] + m[8] * m[5] * m[14] - m[8] * m[6] * m[13] - m[12] * m[5] * m[10] + m[12] * m[6] * m[9];
+    inv[1] = -m[1] * m[10] * m[15] + m[1] * m[11] * m[14] + m[9] * m[2] * m[15] - m[9] * m[3] * m[14] - m[13] * m[2] * m[11] + m[13] * m[3] * m[10];
+    inv[5] = m[0] * m[10] * m[15] - m[0] * m[11] * m[14] - m[8] * m[2] * m[15] + m[8] * m[3] * m[14] + m[12] * m[2] * m[11] - m[12] * m[3] * m[10];
+    inv[9] = -m[0] * m[9] * m[15] + m[0] * m[11] * m[13] + m[8] * m[1] * m[15] - m[8] * m[3] * m[13] - m[12] * m[1] * m[11] + m[12] * m[3] * m[9];
+    inv[13] = m[0] * m[9] * m[14] - m[0] * m[10] * m[13] - m[8] * m[1] * m[14] + m[8] * m[2] * m[13] + m[12] * m[1] * m[10] - m[12] * m[2] * m[9];
+    inv[2] = m[1] * m[6] * m[15] - m[1] * m[7] * m[14] - m[5] * m[2] * m[15] + m[5] * m[3] * m[14] + m[13] * m[2] * m[7] - m[13] * m[3] * m[6];
+    inv[6] = -m[0] * m[6] * m[15] + m[0] * m[7] * m[14] + m[4] * m[2] * m[15] - m[4] * m[3] * m[14] - m[12] * m[2] * m[7] + m[12] * m[3] * m[6];
+    inv[10] = m[0] * m[5] * m[15] - m[0] * m[7] * m[13] - m[4] * m[1] * m[15] + m[4] * m[3] * m[13] + m[12] * m[1] * m[7] - m[12] * m[3] * m[5];
+    inv[14] = -m[0] * m[5] * m[14] + m[0] * m[6] * m[13] + m[4] * m[1] * m[14] - m[4] * m[2] * m[13] - m[12] * m[1] * m[6] + m[12] * m[2] * m[5];
+    inv[3] = -m[1] * m[6] * m[11] + m[1] * m[7] * m[10] + m[5] * m[2] * m[11] - m[5] * m[3] * m[10] - m[9] * m[2] * m[7] + m[9] * m[3] * m[6];
+    inv[7] = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] + m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
+    inv[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] - m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
+    inv[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] + m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
+    const float det = m[0] * inv[0] + m[1] * inv[4] + m[2] * inv[8] + m[3] * inv[12];
+    if (det == 0.0f) return 0;
+    const float id = 1.0f / det;
+    for (int k = 0; k < 16; ++k) inv[k] *= id;
+    return 1;
+}
+static void m4mulv(const float m[16], const float v[4], float r[4]) {
+    for (int row = 0; row < 4; ++row) r[row] = m[0 + row] * v[0] + m[4 + row] * v[1] + m[8 + row] * v[2] + m[12 + row] * v[3];
+}
+static inline float clamp01(float x) { return x < 0.0f ? 0.0f : (x > 1.0f ? 1.0f : x); }
+
+ORC_API uint32_t orc_prepass(const float* gaussians, uint32_t n, const float* world_to_view, const float* view_to_clip, const float* model_to_world,
+                             const float resolution[2], const float near_far[2], float std_dev, int render_mode, uint32_t format, uint32_t ply_has_pbr,
+                             float* quads, float* depths) {
+    const float* M = model_to_world;
+    float Minv[16], nmat[16];   /* normal matrix: transpose(inverse(M)) (:119) */
+    const int has_inv = m4inverse(M, Minv);
+    for (int c = 0; c < 4; ++c) for (int r = 0; r < 4; ++r) nmat[c * 4 + r] = has_inv ? Minv[r * 4 + c] : 0.0f;
+    const float mrot[9] = {M[0], M[1], M[2], M[4], M[5], M[6], M[8], M[9], M[10]};   /* :103-107 */
+    float mrot_inv[9];
+    m3inverse(mrot, mrot_inv);
+    const float len0 = sqrtf(M[0] * M[0] + M[1] * M[1] + M[2] * M[2] + M[3] * M[3]), len1 = sqrtf(M[4] * M[4] + M[5] * M[5] + M[6] * M[6] + M[7] * M[7]);
+    const float mscale[3] = {len0, len0, len1};   /* :96 (sic: column 0 twice, then column 1) */
+    const float W[9] = {world_to_view[0], world_to_view[1], world_to_view[2], world_to_view[4], world_to_view[5], world_to_view[6],
+                        world_to_view[8], world_to_view[9], world_to_view[10]};   /* mat3(u_worldToView) :167 */
+    uint32_t valid = 0;
+    for (uint32_t gid = 0; gid < n; ++gid) {
+        const float* g = gaussians + (size_t)gid * 24;   /* position color scale normal rotation pbr */
+        const float p4[4] = {g[0], g[1], g[2], 1.0f};
+        float ws[4], vs[4], clipv[4];
+        m4mulv(M, p4, ws);                                   /* :66 */
+        const float ws1[4] = {ws[0], ws[1], ws[2], 1.0f};
+        m4mulv(world_to_view, ws1, vs);                      /* :68 */
+        m4mulv(view_to_clip, vs, clipv);                     /* :70 */
+        const float clip = 1.05f * clipv[3];                 /* :72-76 */
+        if (clipv[2] < -clip || clipv[0] < -clip || clipv[0] > clip || clipv[1] < -clip || clipv[1] > clip) continue;
+        const float multiplier = (format == 0 || format == 3) ? std_dev : 1.0f;   /* :95-97 */
+        const float sc[3] = {g[8] * multiplier * (mscale[0] * mscale[0]), g[9] * multiplier * (mscale[1] * mscale[1]), g[10] * multiplier * (mscale[2] * mscale[2])};
+        /* castQuatToMat3 (common.glsl:22-48): the three "rows" are the COLUMNS of the GLM matrix; quat = (w, x, y, z) in .x .y .z .w */
+        const float qx = g[16], qy = g[17], qz = g[18], qw = g[19];
+        const float rot0[9] = {1.f - 2.f * (qz * qz + qw * qw), 2.f * (qy * qz - qx * qw), 2.f * (qy * qw + qx * qz),
+                               2.f * (qy * qz + qx * qw), 1.f - 2.f * (qy * qy + qw * qw), 2.f * (qz * qw - qx * qy),
+                               2.f * (qy * qw - qx * qz), 2.f * (qz * qw + qx * qy), 1.f - 2.f * (qy * qy + qz * qz)};
+        float rot[9];
+        m3mul(rot0, mrot_inv, rot);                          /* :109 */
+        /* computeCov3D (common.glsl:50-61): mMatrix = diag(scales) * rotMat; sigma = transpose(mMatrix) * mMatrix */
+        float mm[9], mmT[9], cov3d[9];
+        for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) mm[c * 3 + r] = sc[r] * rot[c * 3 + r];
+        m3transpose(mm, mmT);
+        m3mul(mmT, mm, cov3d);
+        float out_color[4] = {0, 0, 0, 0}, nrm[4] = {1, 0, 0, 0};
+        const float depth_exp = clamp01(expf(-20.0f * clamp01((-vs[2] - near_far[0]) / (near_far[1] - near_far[0]))));   /* :114, common.glsl:80-84 */
+        if (format == 0 || (format == 1 && ply_has_pbr != 0) || format == 3) {   /* :117-121 */
+            const float n4[4] = {g[12], g[13], g[14], 1.0f};
+            float nw[4];
+            m4mulv(nmat, n4, nw);
+            nrm[0] = nw[0] * 0.5f + 0.5f; nrm[1] = nw[1] * 0.5f + 0.5f; nrm[2] = nw[2] * 0.5f + 0.5f; nrm[3] = g[7];
+        } else if (format == 1) {                                                  /* :123-130 shortest axis */
+            const unsigned idx = (unsigned)((g[9] < g[10]) && (g[9] < g[8])) + (unsigned)((g[10] < g[9]) && (g[10] < g[8])) * 2u;
+            nrm[0] = rot[idx * 3 + 0] * 0.5f + 0.5f; nrm[1] = rot[idx * 3 + 1] * 0.5f + 0.5f; nrm[2] = rot[idx * 3 + 2] * 0.5f + 0.5f; nrm[3] = g[7];
+        }
+        if (render_mode == 0 || render_mode == 6) { out_color[0] = g[4]; out_color[1] = g[5]; out_color[2] = g[6]; out_color[3] = g[7]; }   /* :132-148 */
+        else if (render_mode == 1) { out_color[0] = out_color[1] = out_color[2] = depth_exp; out_color[3] = g[7]; }
+        else if (render_mode == 2) { out_color[0] = nrm[0]; out_color[1] = nrm[1]; out_color[2] = nrm[2]; out_color[3] = nrm[3]; }
+        const float ndc[4] = {clipv[0] / clipv[3], clipv[1] / clipv[3], clipv[2] / clipv[3], clipv[3]};   /* :150 */
+        /* :153-166 Jacobian of the projection; J = mat3(col0 = (jsx,0,0), col1 = (0,jsy,0), col2 = (jtx,jty,jtz)) */
+        const float tzSq = vs[2] * vs[2];
+        const float jsx = -(view_to_clip[0] * resolution[0]) / (2 * vs[2]), jsy = -(view_to_clip[5] * resolution[1]) / (2 * vs[2]);
+        const float jtx = (view_to_clip[0] * vs[0] * resolution[0]) / (2 * tzSq), jty = (view_to_clip[5] * vs[1] * resolution[1]) / (2 * tzSq);
+        const float jtz = ((near_far[1] - near_far[0]) * view_to_clip[3 * 4 + 2]) / (2 * tzSq);
+        const float J[9] = {jsx, 0.f, 0.f, 0.f, jsy, 0.f, jtx, jty, jtz};
+        float JW[9], JWT[9], t9[9], Vp[9];
+        m3mul(J, W, JW);
+        m3transpose(JW, JWT);
+        m3mul(JW, cov3d, t9);
+        m3mul(t9, JWT, Vp);                                  /* :170 */
+        float c00 = Vp[0] + 0.3f, c01 = Vp[1], c10 = Vp[3], c11 = Vp[4] + 0.3f;   /* mat2(V'), :172-176; cXY = cov2d[X][Y] (column X, row Y) */
+        const float mid = c00 + c11;
+        const float dx = c00 - c11, dy = 2 * c01;
+        const float delta = sqrtf(dx * dx + dy * dy);
+        const float lambda1 = 0.5f * (mid + delta), lambda2 = 0.5f * (mid - delta);
+        if (lambda2 < 0.0f) continue;                        /* :185 */
+        float dvx = 1.0f, dvy = (-c00 + c01 + lambda1) / (c01 - c11 + lambda1);
+        const float dinv = 1.0f / sqrtf(dvx * dvx + dvy * dvy);   /* normalize (GLM: v * inversesqrt(dot)) */
+        dvx *= dinv; dvy *= dinv;
+        const float r1 = fminf(3 * sqrtf(lambda1), 1024.0f), r2 = fminf(3 * sqrtf(lambda2), 1024.0f);
+        const float majx = r1 * dvx, majy = r1 * dvy, minx = r2 * dvy, miny = r2 * -dvx;
+        const float hx = resolution[0] * 0.5f, hy = resolution[1] * 0.5f;
+        float* q = quads + (size_t)valid * 24;
+        q[0] = ndc[0]; q[1] = ndc[1]; q[2] = ndc[2]; q[3] = ndc[3];
+        q[4] = majx / hx; q[5] = majy / hy; q[6] = minx / hx; q[7] = miny / hy;
+        q[8] = out_color[0]; q[9] = out_color[1]; q[10] = out_color[2]; q[11] = out_color[3];
+        const float det = c00 * c11 - c01 * c10;             /* inverseMat2 (common.glsl:63-78) */
+        float i00 = 0, i01 = 0, i11 = 0;
+        if (det != 0) { i00 = c11 / det; i01 = -c01 / det; i11 = c00 / det; }
+        q[12] = i00; q[13] = i01; q[14] = i11; q[15] = -vs[2];
+        q[16] = nrm[0]; q[17] = nrm[1]; q[18] = nrm[2]; q[19] = g[20];
+        q[20] = ws[0]; q[21] = ws[1]; q[22] = ws[2]; q[23] = g[21];
+        depths[valid] = vs[2];
+        ++valid;
+    }
+    return valid;
+}
+
 ORC_API int orc_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

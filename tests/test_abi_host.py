@@ -543,3 +543,14 @@ def test_every_entry_point_rejects_null_arguments_with_a_status():
     assert L.m2s_convert_file(None, None, 64, C.c_float(0.65), 0, None, None) == INV
     assert L.m2s_scene_upload(None, None, None) == INV
     assert b"NULL" in L.m2s_last_error()
+
+
+def test_prepass_entry_points_reject_bad_arguments_without_a_gpu():
+    """m2s_prepass / m2s_prepass_enqueue: NULL context or parameters -> M2S_E_INVALID before any CUDA call."""
+    import ctypes as C
+    L = _lib.lib()
+    p = _abi.make_prepass_params(np.eye(4).ravel(), np.eye(4).ravel(), np.eye(4).ravel(), (640, 480), (0.1, 10.0), 0.001, 0, _abi.LAYOUT_REF96)
+    v = C.c_uint32(0)
+    assert L.m2s_prepass(None, None, 0, C.byref(p), None, None, C.byref(v)) == _abi.M2S_E_INVALID
+    assert L.m2s_prepass_enqueue(None, None, 0, None, C.byref(p), None, None, None, None) == _abi.M2S_E_INVALID
+    assert C.sizeof(_abi.m2s_prepass_params) == 3 * 64 + 8 + 8 + 16

@@ -544,3 +544,68 @@ def test_upload_range_brings_every_texel_the_shard_samples(gpu_ctx, tex_hw):
     if h >= 256:  # the sphere's rows are latitude bands: a shard needs a fraction of the image
         full = s.triangles.nbytes + sum(t.nbytes for t in tex)
         assert max(h2d) < 0.75 * full, (h2d, full)
+
+
+# ---- the viewer prepass: GaussiansPrepass::execute + gaussianSplattingPrepassCS.glsl ------------------
+def _prepass_cases():
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_prepass_vectors.npz"))
+    for i in range(int(g["ncases"])):
+        p = g[f"params{i}"]
+        yield dict(gaussians=g[f"g{i}"], view=g[f"view{i}"], proj=g[f"proj{i}"], model=g[f"model{i}"], resolution=(float(p[0]), float(p[1])),
+                   near_far=(float(p[2]), float(p[3])), std_dev=float(p[4]), render_mode=int(p[5]), fmt=int(p[6]), quads=g[f"quads{i}"], depths=g[f"depths{i}"])
+
+
+def _as_packed56(g24: np.ndarray) -> np.ndarray:
+    """GaussianVertex values -> the PACKED56 record that decodes to them (what savePlyVector + loadPlyFile do to a gaussian)."""
+    f = np.zeros((len(g24), 14), np.float32)
+    f[:, 0:3] = g24[:, 0:3]; f[:, 3:7] = g24[:, 16:20]
+    f[:, 7:10] = np.log(g24[:, 8:11].astype(np.float64)).astype(np.float32)
+    f[:, 10:13] = ((g24[:, 4:7].astype(np.float64) - 0.5) / 0.28209479177387814).astype(np.float32)
+    a = np.clip(g24[:, 7].astype(np.float64), 1e-6, 1 - 1e-6)
+    f[:, 13] = np.log(a / (1 - a)).astype(np.float32)
+    return f
+
+
+def test_prepass_matches_reference_shader_golden_vectors(gpu_ctx):
+    """The CUDA prepass against gaussianSplattingPrepassCS.glsl's own outputs (tests/golden/ref_prepass_vectors.npz, made
+    from /root/reference by tests/golden/make_golden_prepass.py): the same survivors, values as util.assert_prepass_match
+    states.  u_format 0 cases go in as REF96 records, u_format 1 cases as the PACKED56 records that decode to them."""
+    import torch
+    from util import assert_prepass_match
+    for c in _prepass_cases():
+        if c["fmt"] == 0:
+            rec, layout, want_q, want_d = c["gaussians"], LAYOUT_REF96, c["quads"], c["depths"]
+        else:   # the record round trip (log / exp, logit / sigmoid) is part of this input: the expected values come from the oracle on the decoded records
+            rec, layout = _as_packed56(c["gaussians"]), LAYOUT_PACKED56
+            want_q, want_d = oracle.prepass(oracle.packed56_as_gaussian_vertex(rec), c["view"], c["proj"], c["model"], c["resolution"], c["near_far"],
+                                            c["std_dev"], c["render_mode"], 1, 0)
+            assert len(want_q) == len(c["quads"])   # ... and are the reference's survivors
+        d = torch.from_numpy(np.ascontiguousarray(rec).view(np.uint8).reshape(-1)).cuda()
+        quads, depths = gpu_ctx.prepass(d, len(rec), layout, c["view"], c["proj"], c["model"], c["resolution"], c["near_far"], c["std_dev"], c["render_mode"])
+        assert_prepass_match(quads, depths, want_q, want_d, c["resolution"], ordered=False)
+
+
+@pytest.mark.parametrize("layout", [LAYOUT_REF96, LAYOUT_PACKED56])
+def test_prepass_on_the_conversion_output(gpu_ctx, layout):
+    """convert -> prepass without leaving the device, both record layouts, against the oracle's prepass on the same records
+    (100 k gaussians: every warp-append and the span copies are exercised; three render modes)."""
+    from util import assert_prepass_match
+    tri = synth.displaced_sphere(96, 48, seed=5)
+    s = Scene(tri, [Primitive(0, len(tri), (1.0, 0.9, 0.8, 0.7), 0, 1, 2)], synth.make_material_textures(128, 9))
+    s.compute_bboxes()
+    ds = gpu_ctx.upload(s)
+    R = 200
+    out = gpu_ctx.convert(ds, R, layout, flags=FLAG_UNCAPPED, capacity=6 * R * R)
+    ds.free()
+    rec = out.numpy()
+    raw = np.ascontiguousarray(rec).view(np.uint8).reshape(len(rec), -1)
+    g24 = raw.view(np.float32).reshape(len(rec), 24) if layout == LAYOUT_REF96 else oracle.packed56_as_gaussian_vertex(raw)
+    cases = list(_prepass_cases())
+    for mode in (0, 1, 2):
+        c = cases[1]   # a rotated, scaled model matrix and an oblique camera
+        std = 0.65 / R
+        quads, depths = gpu_ctx.prepass(out.data, out.written, layout, c["view"], c["proj"], c["model"], c["resolution"], c["near_far"], std, mode)
+        want_q, want_d = oracle.prepass(g24, c["view"], c["proj"], c["model"], c["resolution"], c["near_far"], std, mode, 0 if layout == LAYOUT_REF96 else 1, 0)
+        assert 0.2 * len(g24) < len(want_q) <= len(g24)
+        assert_prepass_match(quads, depths, want_q, want_d, c["resolution"], ordered=False)

@@ -287,3 +287,41 @@ def test_loader_matches_live_reference_parser_on_random_scene_graphs(tmp_path):
                     assert np.array_equal(t, s.textures[idx]), (seed, q.name, which)
         compared += 1
     assert compared >= 100
+
+
+# ---- viewer prepass: the C restatement against the reference's own compute shader --------------------
+def _prepass_golden():
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_prepass_vectors.npz"))
+    for i in range(int(g["ncases"])):
+        p = g[f"params{i}"]
+        yield dict(gaussians=g[f"g{i}"], view=g[f"view{i}"], proj=g[f"proj{i}"], model=g[f"model{i}"], resolution=(float(p[0]), float(p[1])),
+                   near_far=(float(p[2]), float(p[3])), std_dev=float(p[4]), render_mode=int(p[5]), fmt=int(p[6]), quads=g[f"quads{i}"], depths=g[f"depths{i}"])
+
+
+def test_prepass_oracle_matches_reference_shader_golden_vectors():
+    """tests/golden/ref_prepass_vectors.npz holds gaussianSplattingPrepassCS.glsl's own outputs (made by
+    tests/golden/make_golden_prepass.py from /root/reference): same survivors in the same order, values as
+    util.assert_prepass_match states."""
+    from util import assert_prepass_match
+    n = 0
+    for c in _prepass_golden():
+        quads, depths = oracle.prepass(c["gaussians"], c["view"], c["proj"], c["model"], c["resolution"], c["near_far"], c["std_dev"],
+                                       c["render_mode"], c["fmt"], 0)
+        assert_prepass_match(quads, depths, c["quads"], c["depths"], c["resolution"], ordered=True)
+        n += 1
+    assert n == 5
+
+
+def test_prepass_live_reference_build_when_available():
+    """Where oracle/_ref/libm2s_refprepass.so exists (the build container), run the reference shader live on fresh seeds."""
+    if oracle.ref_prepass_lib() is None:
+        pytest.skip("oracle/_ref/libm2s_refprepass.so not built (no /root/reference on this box)")
+    from util import assert_prepass_match
+    rng = np.random.default_rng(77)
+    for c in _prepass_golden():
+        g = c["gaussians"].copy()
+        g[:, 0:3] += (rng.random((len(g), 3)).astype(np.float32) - 0.5) * 0.3
+        args = (g, c["view"], c["proj"], c["model"], c["resolution"], c["near_far"], c["std_dev"], c["render_mode"], c["fmt"], 0)
+        a, b = oracle.prepass(*args), oracle.ref_prepass(*args)
+        assert_prepass_match(a[0], a[1], b[0], b[1], c["resolution"], ordered=True)

@@ -326,3 +326,54 @@ def make_complex_glb(path: str, seed: int) -> None:
         f.write(struct.pack("<4sII", b"glTF", 2, 12 + 8 + len(js) + 8 + len(binblob)))
         f.write(struct.pack("<I4s", len(js), b"JSON")); f.write(js)
         f.write(struct.pack("<I4s", len(binblob), b"BIN\x00")); f.write(binblob)
+
+
+# ---- viewer prepass --------------------------------------------------------------------------------
+def assert_prepass_match(got_quads, got_depths, want_quads, want_depths, resolution, ordered: bool):
+    """QuadNdcTransformation arrays [n, 24] + view depths.  ordered = False: the GPU appends in atomic arrival order, both
+    sides are sorted by world position first.  Two outputs of the shader are ill-conditioned BY CONSTRUCTION and are
+    compared through what they represent: the conic (inverse of the 2-D covariance: its off-diagonal is a difference of
+    almost equal numbers for round splats) through the covariance itself, and the screen axes (eigenvectors: arbitrary —
+    in the reference even 0/0 = NaN — when the two eigenvalues coincide) through the ellipse matrix they span."""
+    g, w = np.asarray(got_quads, np.float64).reshape(-1, 24), np.asarray(want_quads, np.float64).reshape(-1, 24)
+    gd, wd = np.asarray(got_depths, np.float64), np.asarray(want_depths, np.float64)
+    assert len(g) == len(w) == len(gd) == len(wd), (len(g), len(w))
+    if not ordered:   # pair every expected quad with the produced quad at the same world position (a bijection, or the sets differ)
+        from scipy.spatial import cKDTree
+        dist, idx = cKDTree(g[:, 20:23]).query(w[:, 20:23])
+        scale = max(1.0, float(np.abs(w[:, 20:23]).max(initial=0.0)))
+        assert (dist <= 1e-5 * scale).all(), f"{np.count_nonzero(dist > 1e-5 * scale)} expected gaussians have no counterpart (max distance {dist.max()})"
+        if len(np.unique(idx)) != len(idx):   # coincident positions: fall back to a full sort of both sides on rounded keys
+            key = lambda q: np.lexsort((np.round(q[:, 9], 5), np.round(q[:, 8], 5), np.round(q[:, 22], 5), np.round(q[:, 21], 5), np.round(q[:, 20], 5)))
+            og, ow = key(g), key(w)
+            g, gd, w, wd = g[og], gd[og], w[ow], wd[ow]
+        else:
+            g, gd = g[idx], gd[idx]
+    _close(g[:, 20:24], w[:, 20:24], 1e-6, 1e-6, "wsPos / pbr.y")
+    _close(gd, wd, 1e-5, 1e-6, "view depth")
+    _close(g[:, 0:4], w[:, 0:4], 1e-5, 2e-5, "gaussianMean2dNdc")
+    _close(g[:, 8:12], w[:, 8:12], 1e-5, 1e-6, "color")
+    _close(g[:, 16:20], w[:, 16:20], 1e-5, 2e-5, "normal / pbr.x")
+    _close(g[:, 15], w[:, 15], 1e-5, 1e-6, "conic.w (view depth)")
+
+    def cov(q):
+        a, b, c = q[:, 12], q[:, 13], q[:, 14]
+        det = a * c - b * b
+        return np.stack([c / det, -b / det, a / det], 1)
+    cg, cw = cov(g), cov(w)
+    _close(cg, cw, 2e-4, 1e-5, "2-D covariance (from the conic)")
+    hx, hy = resolution[0] * 0.5, resolution[1] * 0.5
+
+    def ellipse(q):
+        mx, my, nx, ny = q[:, 4] * hx, q[:, 5] * hy, q[:, 6] * hx, q[:, 7] * hy
+        return np.stack([mx * mx + nx * nx, mx * my + nx * ny, my * my + ny * ny], 1)
+    eg, ew = ellipse(g), ellipse(w)
+    # the shader's eigenvector is normalize(1, (l1 - a + b) / (l1 - c + b)) for cov = [[a, b], [b, c]]: numerator and denominator
+    # both vanish for a round splat (0/0 = NaN in the reference itself) and, more generally, whenever a ~ c and b < 0
+    # (l1 = a + |b|): there the direction is rounding noise on both sides and is not compared
+    mid, dlt = cw[:, 0] + cw[:, 2], np.hypot(cw[:, 0] - cw[:, 2], 2 * cw[:, 1])
+    l1 = 0.5 * (mid + dlt)
+    num, den = -cw[:, 0] + cw[:, 1] + l1, cw[:, 1] - cw[:, 2] + l1
+    ok = (np.abs(num) + np.abs(den)) > 5e-3 * l1
+    assert not np.isnan(eg[ok]).any() and not np.isnan(ew[ok]).any(), "NaN axes for a splat that is not round"
+    _close(eg[ok], ew[ok], 2e-3, 1e-3, "ellipse spanned by the screen axes (pixels^2)")
