@@ -609,3 +609,25 @@ def test_prepass_on_the_conversion_output(gpu_ctx, layout):
         want_q, want_d = oracle.prepass(g24, c["view"], c["proj"], c["model"], c["resolution"], c["near_far"], std, mode, 0 if layout == LAYOUT_REF96 else 1, 0)
         assert 0.2 * len(g24) < len(want_q) <= len(g24)
         assert_prepass_match(quads, depths, want_q, want_d, c["resolution"], ordered=False)
+
+
+@pytest.mark.parametrize("layout", [LAYOUT_REF96, LAYOUT_PACKED56])
+def test_prepass_large_input_path(gpu_ctx, layout):
+    """From 2 M records on the kernel fetches a warp's records as one contiguous span through shared memory (another code
+    path than the small-input one): 2 100 001 records (an odd count: the PACKED56 span of the last warp ends on an 8-byte
+    tail) against the oracle."""
+    import torch
+    from util import assert_prepass_match
+    c = list(_prepass_cases())[0 if layout == LAYOUT_REF96 else 3]   # gaussians whose scales suit the format (u_format 1: no std_dev factor)
+    base = c["gaussians"]
+    reps = 2_100_001 // len(base) + 1
+    g = np.tile(base, (reps, 1))[:2_100_001].copy()
+    g[:, 0] += (np.arange(len(g)) // len(base)).astype(np.float32) * np.float32(2e-4)   # distinct positions per copy
+    rec = g if layout == LAYOUT_REF96 else _as_packed56(g)
+    g24 = g if layout == LAYOUT_REF96 else oracle.packed56_as_gaussian_vertex(rec)
+    d = torch.from_numpy(np.ascontiguousarray(rec).view(np.uint8).reshape(-1)).cuda()
+    fmt = 0 if layout == LAYOUT_REF96 else 1
+    quads, depths = gpu_ctx.prepass(d, len(rec), layout, c["view"], c["proj"], c["model"], c["resolution"], c["near_far"], c["std_dev"], 0)
+    want_q, want_d = oracle.prepass(g24, c["view"], c["proj"], c["model"], c["resolution"], c["near_far"], c["std_dev"], 0, fmt, 0)
+    assert len(want_q) > 1_000_000
+    assert_prepass_match(quads, depths, want_q, want_d, c["resolution"], ordered=False)
