@@ -248,6 +248,26 @@ def test_convert_host_pipelined_chunks(gpu_ctx, layout):
     assert_records_match(s, layout, rec, keys, want, wkeys)
 
 
+def test_convert_host_pipelined_chunks_through_the_direct_path(gpu_ctx):
+    """A mesh big enough that every chunk of the host pipeline is a launch in which the warps take several units each
+    (4 chunks of 90 000 triangles): the raster kernel shades the small triangles itself (direct path) and appends after
+    the earlier chunks' records.  Same multiset of records and keys as one device-resident conversion, bit for bit."""
+    tri = synth.displaced_sphere(600, 300, seed=4, amplitude=0.05)   # 360 000 triangles
+    s = Scene(tri, [Primitive(0, len(tri), (1.0, 0.8, 0.9, 1.0), 0, -1, -1)], synth.make_material_textures(256, 8)[:1])
+    s.compute_bboxes()
+    R = 300
+    rec, keys, res = gpu_ctx.convert_host(s, R, LAYOUT_PACKED56, flags=FLAG_UNCAPPED, want_keys=True)
+    ds = gpu_ctx.upload(s)
+    whole = gpu_ctx.convert(ds, R, LAYOUT_PACKED56, flags=FLAG_UNCAPPED, capacity=6 * R * R, want_keys=True)
+    ds.free()
+    assert res.total == whole.total == res.written and res.total > 100_000
+    a, ak = np.ascontiguousarray(rec), np.asarray(keys)
+    b, bk = whole.numpy(), whole.keys_numpy()
+    oa, ob = np.argsort(ak, kind="stable"), np.argsort(bk, kind="stable")
+    assert np.array_equal(ak[oa], bk[ob]) and len(np.unique(ak)) == len(ak)
+    assert a[oa].tobytes() == b[ob].tobytes()
+
+
 def test_convert_host_pipelined_capacity(gpu_ctx):
     """The cap applies to the running index across chunks: exactly `cap` records come back, the total keeps
     counting (converterFS.glsl:46-51), status M2S_E_CAPACITY."""
@@ -255,7 +275,7 @@ def test_convert_host_pipelined_capacity(gpu_ctx):
     s = Scene(tri, [Primitive(0, len(tri), (1, 1, 1, 1), 0, 1, 2)], synth.make_material_textures(64, 5))
     s.compute_bboxes()
     _, _, full = gpu_ctx.convert_host(s, 160, LAYOUT_PACKED56, flags=FLAG_UNCAPPED)
-    cap = full.total * 5 // 8 + 1  # ends inside the third of four chunks
+    cap = full.total * 5 // 8 + 1  # ends inside the second chunk
     rec, keys, res = gpu_ctx.convert_host(s, 160, LAYOUT_PACKED56, max_gaussians=cap, want_keys=True)
     assert res.total == full.total and res.written == cap and len(rec) == cap
     assert len(np.unique(keys)) == cap  # every stored record is a distinct fragment
