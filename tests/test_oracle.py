@@ -325,3 +325,22 @@ def test_prepass_live_reference_build_when_available():
         args = (g, c["view"], c["proj"], c["model"], c["resolution"], c["near_far"], c["std_dev"], c["render_mode"], c["fmt"], 0)
         a, b = oracle.prepass(*args), oracle.ref_prepass(*args)
         assert_prepass_match(a[0], a[1], b[0], b[1], c["resolution"], ordered=True)
+
+
+def test_packed56_decodes_to_the_gaussian_vertex_it_was_encoded_from():
+    """oracle.packed56_as_gaussian_vertex (what the prepass sees for a PACKED56 record, = what the reference's .ply loader
+    builds) inverts the export arithmetic of parsers.cpp:484-499: scale * sigma/R, colour, alpha and rotation come back."""
+    rng = np.random.default_rng(3)
+    n = 300
+    rec = np.zeros((n, 24), np.float32)
+    rec[:, 0:3] = rng.random((n, 3)) * 4 - 2; rec[:, 3] = 1
+    rec[:, 4:8] = rng.random((n, 4)) * 0.98 + 0.01
+    rec[:, 8:10] = rng.random((n, 2)) * 3 + 0.01; rec[:, 10] = 1e-7
+    q = rng.normal(size=(n, 4)); rec[:, 16:20] = q / np.linalg.norm(q, axis=1, keepdims=True)
+    mult = 0.65 / 512
+    packed = np.stack([oracle.encode(LAYOUT_PACKED56, rec[i], mult) for i in range(n)])   # one record per call
+    g = oracle.packed56_as_gaussian_vertex(np.ascontiguousarray(packed).view(np.uint8).reshape(n, -1))
+    assert np.allclose(g[:, 0:3], rec[:, 0:3], rtol=0, atol=0)
+    assert np.allclose(g[:, 8:11], rec[:, 8:11] * np.float32(mult), rtol=2e-6)
+    assert np.allclose(g[:, 4:7], rec[:, 4:7], atol=2e-7) and np.allclose(g[:, 7], rec[:, 7], atol=1e-6)
+    assert np.array_equal(g[:, 16:20], rec[:, 16:20])
